@@ -1,0 +1,586 @@
+// fdga_kernels.cuh -- CUDA kernels of the BSE / cache / bubble / SDE hot path (sm_100a).
+// Every kernel cites the reference function whose arithmetic it reproduces.
+#pragma once
+#include "fdga_device.cuh"
+
+namespace fdga {
+
+// Grid shape shared by all kernels
+struct Grid {
+    double T;
+    int L, NP;            // vertex / bubble momentum mesh
+    int nPiB, nPiF;       // N of the bubble meshes
+    int nK1, nK2b, nK2f, nK3b, nK3f;   // level-0 (S.F) vertex meshes = output meshes
+    int LG, nG;           // G / Sigma mesh
+};
+
+struct SymDev {            // symmetry classes (CSR); representative = first member
+    long long ncls, nmem;
+    const long long* offsets;
+    const long long* index;
+    const unsigned char* ops;
+    const int* member_class;
+};
+
+__device__ __forceinline__ C apply_op(unsigned char op, C v) {
+    if (op & 2) v = conjC(v);
+    if (op & 1) v = -v;
+    return v;
+}
+
+// ---- block reduction of a complex value (deterministic order) ---------------------------------
+__device__ __forceinline__ C block_reduce(C v) {
+    __shared__ double sx[32], sy[32];
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_down_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_down_sync(0xffffffffu, v.y, o);
+    }
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { sx[wid] = v.x; sy[wid] = v.y; }
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    if (wid == 0) {
+        v.x = lane < nw ? sx[lane] : 0.0;
+        v.y = lane < nw ? sy[lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) {
+            v.x += __shfl_down_sync(0xffffffffu, v.x, o);
+            v.y += __shfl_down_sync(0xffffffffu, v.y, o);
+        }
+    }
+    return v;   // valid in thread 0
+}
+
+// ---- elementwise helpers -----------------------------------------------------------------------
+// out = a*x + b*y  (y may be null -> a*x);  used for the t-channel post-fix (BSE_templates.jl:35-38)
+__global__ void axpby_kernel(C* __restrict__ out, const C* x, double a, const C* y, double b, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    C v = x[i] * a;
+    if (y) v += y[i] * b;
+    out[i] = v;
+}
+// out += a*x + b*y
+__global__ void add_axpby_kernel(C* __restrict__ out, const C* x, double a, const C* y, double b, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    C v = out[i] + x[i] * a;
+    if (y) v += y[i] * b;
+    out[i] = v;
+}
+__global__ void scale_copy_kernel(C* __restrict__ out, const C* __restrict__ x, double s, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = x[i] * s;
+}
+// y = x - F/factor (mfRG linear map, src/mfRG.jl:85-86)
+__global__ void mfrg_residual_kernel(C* __restrict__ y, const C* __restrict__ x, const C* __restrict__ F, double factor, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = x[i] - F[i] / factor;
+}
+
+// SG expansion: out[index[j]] = op_j(repvals[class(j)])   (MatsubaraFunctions SymmetryGroup call)
+__global__ void expand_kernel(C* __restrict__ out, const C* __restrict__ repvals, SymDev sg) {
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= sg.nmem) return;
+    out[sg.index[j]] = apply_op(sg.ops[j], repvals[sg.member_class[j]]);
+}
+// SG(f): symmetrise in place from the representatives
+__global__ void symmetrize_kernel(C* __restrict__ f, SymDev sg) {
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= sg.nmem) return;
+    long long c = sg.member_class[j];
+    long long rep = sg.offsets[c];
+    if (j == rep) return;
+    f[sg.index[j]] = apply_op(sg.ops[j], f[sg.index[rep]]);
+}
+
+// ---- s-wave tables (src/nonlocal/swave.jl:32-136): BZ means of one NL2 channel --------------------
+__global__ void swave_tables_kernel(DevLevel lv, int r, int NP, C* K1sw, C* K2swk, C* K2sww, C* K3sw) {
+    const DevChan& c = lv.ch[r];
+    int nB1 = 2 * lv.nK1 - 1, nB2 = 2 * lv.nK2b - 1, nF2 = 2 * lv.nK2f, nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
+    long long n1 = nB1, n2k = (long long)nB2 * nF2 * NP, n2w = (long long)nB2 * nF2, n3 = (long long)nB3 * nF3 * nF3;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n1) {
+        C s = zeroC();
+        for (int p = 0; p < NP; ++p) s += c.K1[i + (size_t)nB1 * p];
+        K1sw[i] = s / (double)NP;
+        return;
+    }
+    i -= n1;
+    if (i < n2k) {      // mean over the 4th axis: index (W,v,P) contiguous
+        C s = zeroC();
+        size_t sk = (size_t)nB2 * nF2 * NP;
+        for (int k = 0; k < NP; ++k) s += c.K2[i + sk * k];
+        K2swk[i] = s / (double)NP;
+        return;
+    }
+    i -= n2k;
+    if (i < n2w) {      // sum(view(f, i1, i2, :, :)) / N3 / N4
+        C s = zeroC();
+        size_t sP = (size_t)nB2 * nF2;
+        for (long long pk = 0; pk < (long long)NP * NP; ++pk) s += c.K2[i + sP * pk];
+        K2sww[i] = s / (double)NP / (double)NP;
+        return;
+    }
+    i -= n2w;
+    if (i < n3) {
+        C s = zeroC();
+        for (int p = 0; p < NP; ++p) s += c.K3[i + (size_t)n3 * p];
+        K3sw[i] = s / (double)NP;
+    }
+}
+
+// ---- bubble auxiliaries: PiT[w,q,W,P] (slab-contiguous copy) and Pisw[W,w,P] = mean_k Pi[W,w,P,k] ----
+__global__ void pi_transpose_kernel(const C* __restrict__ Pi, C* __restrict__ PiT, int nB, int nF, int NP) {
+    // one thread per output element, output index contiguous
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long n = (long long)nB * nF * NP * NP;
+    if (i >= n) return;
+    long long t = i;
+    int iw = t % nF; t /= nF; int iq = t % NP; t /= NP; int iW = t % nB; int iP = t / nB;
+    PiT[i] = Pi[iW + (size_t)nB * (iw + (size_t)nF * (iP + (size_t)NP * iq))];
+}
+__global__ void pi_swave_kernel(const C* __restrict__ Pi, C* __restrict__ Pisw, int nB, int nF, int NP) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long n = (long long)nB * nF * NP;
+    if (i >= n) return;
+    C s = zeroC();
+    for (int k = 0; k < NP; ++k) s += Pi[i + (size_t)n * k];
+    Pisw[i] = s / (double)NP;
+}
+
+// ---- right factor, hoisted out of the (nu, k) loops ---------------------------------
+//  RK_FD    : (Pi - Pi0) * F0(W, w~, inf; P, q~, k0) + Pi * FL(W, w~, inf; P, q~, k0)   BSEa_K1.jl:41-47, BSEa_K2.jl:112-118
+//  RK_MF_K1 : Pi0 * FL(W, w~, inf; P, q~, k0)                                           BSEa_K1.jl:33-37
+//  RK_MF_K2 : Pi0 * FL(W, w, inf; P, q, k0)                                             BSEa_K2.jl:100-104
+//  RK_LK2   : Pi0 * F0(W, w, inf; P, q, k0), w on the K2 nu-mesh                        BSEa_K2.jl:38-41
+// Rt layout: [iw + nw*(iq + NP*(iWo + nBo*iP))], W on the OUTPUT bosonic mesh (N = No).
+enum { RK_FD = 0, RK_MF_K1 = 1, RK_MF_K2 = 2, RK_LK2 = 3 };
+
+template <int CH, int KIND>
+__global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ DevChain FL,
+                                    const C* __restrict__ Pi0T, const C* __restrict__ PiT, C* __restrict__ Rt,
+                                    Grid g, int No, int Ninner) {
+    constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
+    const int nw = 2 * Ninner, nBo = 2 * No - 1, nFP = 2 * g.nPiF, nBP = 2 * g.nPiB - 1;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long n = (long long)nw * g.NP * nBo * g.NP;
+    if (i >= n) return;
+    long long t = i;
+    int iw = t % nw; t /= nw; int iq = t % g.NP; t /= g.NP; int iWo = t % nBo; int iP = t / nBo;
+    int W = iWo - (No - 1), w = iw - Ninner;
+    int Px = iP % g.L, Py = iP / g.L, qx = iq % g.L, qy = iq / g.L;
+    size_t pidx = posF(w, g.nPiF) + (size_t)nFP * (iq + (size_t)g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP));
+    Arg a;
+    a.W = W; a.w = FDGA_INF; a.Px = Px; a.Py = Py; a.qx = 0; a.qy = 0;
+    if (KIND == RK_FD || KIND == RK_MF_K1) {   // crossed arguments (_crossing, BSE_templates.jl:4-6)
+        a.v = (CH == CH_P) ? W - w - 1 : w;
+        a.kx = (CH == CH_P) ? Px - qx : qx; a.ky = (CH == CH_P) ? Py - qy : qy;
+    } else {
+        a.v = w; a.kx = qx; a.ky = qy;
+    }
+    C r;
+    if (KIND == RK_FD) {
+        C F0r = eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
+        C FLr = eval_vertex<false>(FL, 0, CH, SP, a, FL_ALL);
+        C p = PiT[pidx], p0 = Pi0T[pidx];
+        r = (p - p0) * F0r + p * FLr;
+    } else if (KIND == RK_LK2) {
+        r = Pi0T[pidx] * eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
+    } else {
+        r = Pi0T[pidx] * eval_vertex<false>(FL, 0, CH, SP, a, FL_ALL);
+    }
+    Rt[i] = r;
+}
+
+// ---- BSE_K1!: src/nonlocal_2/BSEa/BSEa_K1.jl:19-52.  One CTA per class representative (W, P) ------
+template <int CH>
+__global__ void bse_k1_kernel(const __grid_constant__ DevChain Fleft, const C* __restrict__ Rt, C* __restrict__ repvals,
+                              SymDev sg, long long c0, Grid g, double scale) {
+    constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
+    long long cls = c0 + blockIdx.x;
+    long long idx = sg.index[sg.offsets[cls]];
+    const int nB1 = 2 * g.nK1 - 1, nw = 2 * g.nPiF;
+    int iW = idx % nB1, iP = idx / nB1;
+    int W = iW - (g.nK1 - 1), Px = iP % g.L, Py = iP / g.L;
+    const C* slab = Rt + (size_t)nw * g.NP * (iW + (size_t)nB1 * iP);
+    C acc = zeroC();
+    for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
+        int iw = t % nw, iq = t / nw;
+        Arg a; a.W = W; a.v = FDGA_INF; a.w = iw - g.nPiF; a.Px = Px; a.Py = Py; a.kx = 0; a.ky = 0; a.qx = iq % g.L; a.qy = iq / g.L;
+        C Fl = eval_vertex<false>(Fleft, 0, CH, SP, a, FL_ALL);
+        acc += Fl * slab[t];
+    }
+    acc = block_reduce(acc);
+    if (threadIdx.x == 0) repvals[cls] = acc * scale;
+}
+
+// ---- BSE_L_K2!: src/nonlocal_2/BSEa/BSEa_K2.jl:17-43.  One CTA per representative (W, v, P, k) -----
+template <int CH>
+__global__ void bse_lk2_kernel(const __grid_constant__ DevChain F, const C* __restrict__ Rt, C* __restrict__ repvals,
+                               SymDev sg, long long c0, Grid g, double scale) {
+    constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
+    constexpr unsigned FLG = (CH == CH_P ? 0u : FL_GP) | (CH == CH_T ? 0u : FL_GT) | (CH == CH_A ? 0u : FL_GA);
+    long long cls = c0 + blockIdx.x;
+    long long idx = sg.index[sg.offsets[cls]];
+    const int nB2 = 2 * g.nK2b - 1, nF2 = 2 * g.nK2f, nw = nF2;
+    long long t0 = idx;
+    int iW = t0 % nB2; t0 /= nB2; int iv = t0 % nF2; t0 /= nF2; int iP = t0 % g.NP; int ik = t0 / g.NP;
+    int W = iW - (g.nK2b - 1), v = iv - g.nK2f, Px = iP % g.L, Py = iP / g.L, kx = ik % g.L, ky = ik / g.L;
+    const C* slab = Rt + (size_t)nw * g.NP * (iW + (size_t)nB2 * iP);
+    C acc = zeroC();
+    for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
+        int iw = t % nw, iq = t / nw;
+        int w = iw - g.nK2f, qx = iq % g.L, qy = iq / g.L;
+        Arg a; a.W = W; a.v = v; a.Px = Px; a.Py = Py; a.kx = kx; a.ky = ky;
+        a.w = (CH == CH_P) ? W - w - 1 : w;
+        a.qx = (CH == CH_P) ? Px - qx : qx; a.qy = (CH == CH_P) ? Py - qy : qy;
+        C Gl = eval_vertex<false>(F, 0, CH, SP, a, FLG);
+        acc += Gl * slab[t];
+    }
+    acc = block_reduce(acc);
+    if (threadIdx.x == 0) repvals[cls] = acc * scale;
+}
+
+// ---- BSE_K2!: src/nonlocal_2/BSEa/BSEa_K2.jl:72-125.  One CTA per representative (W, v, P, k) ------
+//  fd   : [F(W,v,w;P,k,q) - F(W,inf,w;P,k,q)] * Rt                 (Fleft = S.F)
+//  mfRG : [F0(W,v,w~;P,k,q~) - F0(W,inf,w~;P,k,q~)] * Rt           (Fleft = S.F0)
+template <int CH, bool MF>
+__global__ void bse_k2_kernel(const __grid_constant__ DevChain Fleft, const C* __restrict__ Rt, C* __restrict__ repvals,
+                              SymDev sg, long long c0, Grid g, double scale) {
+    constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
+    long long cls = c0 + blockIdx.x;
+    long long idx = sg.index[sg.offsets[cls]];
+    const int nB2 = 2 * g.nK2b - 1, nF2 = 2 * g.nK2f, nw = 2 * g.nPiF;
+    long long t0 = idx;
+    int iW = t0 % nB2; t0 /= nB2; int iv = t0 % nF2; t0 /= nF2; int iP = t0 % g.NP; int ik = t0 / g.NP;
+    int W = iW - (g.nK2b - 1), v = iv - g.nK2f, Px = iP % g.L, Py = iP / g.L, kx = ik % g.L, ky = ik / g.L;
+    const C* slab = Rt + (size_t)nw * g.NP * (iW + (size_t)nB2 * iP);
+    C acc = zeroC();
+    for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
+        int iw = t % nw, iq = t / nw;
+        int w = iw - g.nPiF, qx = iq % g.L, qy = iq / g.L;
+        Arg a; a.W = W; a.v = v; a.Px = Px; a.Py = Py; a.kx = kx; a.ky = ky;
+        if (MF) {
+            a.w = (CH == CH_P) ? W - w - 1 : w;
+            a.qx = (CH == CH_P) ? Px - qx : qx; a.qy = (CH == CH_P) ? Py - qy : qy;
+        } else { a.w = w; a.qx = qx; a.qy = qy; }
+        C f1 = eval_vertex<false>(Fleft, 0, CH, SP, a, FL_ALL);
+        a.v = FDGA_INF;
+        C f2 = eval_vertex<false>(Fleft, 0, CH, SP, a, FL_ALL);
+        acc += (f1 - f2) * slab[t];
+    }
+    acc = block_reduce(acc);
+    if (threadIdx.x == 0) repvals[cls] = acc * scale;
+}
+
+// ---- K3 index helper -----------------------------------------------------------------------------
+__device__ __forceinline__ size_t k3at(const Grid& g, int W, int v, int w, int iP) {
+    int nB = 2 * g.nK3b - 1, nF = 2 * g.nK3f;
+    return posB(W, g.nK3b) + (size_t)nB * (posF(v, g.nK3f) + (size_t)nF * (posF(w, g.nK3f) + (size_t)nF * iP));
+}
+__device__ __forceinline__ size_t piswat(const Grid& g, int W, int w, int iP) {
+    return posB(W, g.nPiB) + (size_t)(2 * g.nPiB - 1) * (posF(w, g.nPiF) + (size_t)(2 * g.nPiF) * iP);
+}
+__device__ __forceinline__ void decode_k3(const Grid& g, long long idx, int& W, int& v, int& w, int& iP) {
+    int nB = 2 * g.nK3b - 1, nF = 2 * g.nK3f;
+    int iW = idx % nB; idx /= nB; int iv = idx % nF; idx /= nF; int iw = idx % nF; iP = (int)(idx / nF);
+    W = iW - (g.nK3b - 1); v = iv - g.nK3f; w = iw - g.nK3f;
+}
+
+// ---- BSE_L_K3!: src/nonlocal_2/BSEa/BSEa_K3.jl:19-34.  One thread per representative ------------------
+__global__ void bse_lk3_kernel(const C* __restrict__ cache_G, const C* __restrict__ cache_F0, const C* __restrict__ Pi0sw,
+                               C* __restrict__ repvals, SymDev sg, long long c0, long long c1, Grid g, double scale) {
+    long long cls = c0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (cls >= c1) return;
+    long long idx = sg.index[sg.offsets[cls]];
+    int W, v, vp, iP; decode_k3(g, idx, W, v, vp, iP);
+    C val = zeroC();
+    for (int w = -g.nK3f; w < g.nK3f; ++w)
+        val += cache_G[k3at(g, W, v, w, iP)] * Pi0sw[piswat(g, W, w, iP)] * cache_F0[k3at(g, W, w, vp, iP)];
+    repvals[cls] = val * scale;
+}
+
+// ---- BSE_K3!: src/nonlocal_2/BSEa/BSEa_K3.jl:62-121.  One thread per representative -----------------
+template <int CH, bool MF>
+__global__ void bse_k3_kernel(const C* __restrict__ FLown, const C* __restrict__ FLt, const C* __restrict__ FLa,
+                              const C* __restrict__ cache_G, const C* __restrict__ cache_F, const C* __restrict__ cache_F0,
+                              const C* __restrict__ Pi0sw, const C* __restrict__ Pisw, C* __restrict__ repvals,
+                              SymDev sg, long long c0, long long c1, Grid g, double sign1, double sign2) {
+    long long cls = c0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (cls >= c1) return;
+    long long idx = sg.index[sg.offsets[cls]];
+    int W, v, vp, iP; decode_k3(g, idx, W, v, vp, iP);
+    C val = zeroC();
+    for (int w = -g.nK3f; w < g.nK3f; ++w) {
+        C Gs = (CH == CH_P) ? cache_G[k3at(g, W, w, vp, iP)] : cache_G[k3at(g, W, vp, w, iP)];
+        C Fs = cache_F[k3at(g, W, v, w, iP)];
+        C P0 = Pi0sw[piswat(g, W, w, iP)];
+        int wc = (CH == CH_P) ? W - w - 1 : w;
+        bool cin = inF(wc, g.nK3f);
+        C cen = zeroC();
+        if (cin) cen = (CH == CH_T) ? (2.0 * FLt[k3at(g, W, wc, vp, iP)] - FLa[k3at(g, W, wc, vp, iP)]) : FLown[k3at(g, W, wc, vp, iP)];
+        if (MF) {
+            val += Fs * P0 * Gs * sign1;
+            if (cin) val += Fs * P0 * cen * sign2;
+        } else {
+            C P1 = Pisw[piswat(g, W, w, iP)];
+            C F0s = cache_F0[k3at(g, W, w, vp, iP)];
+            val += Fs * ((P1 - P0) * F0s + P1 * Gs) * sign1;
+            if (cin) val += Fs * P1 * cen * sign2;
+        }
+    }
+    C add = (CH == CH_T) ? (2.0 * FLt[k3at(g, W, v, vp, iP)] - FLa[k3at(g, W, v, vp, iP)]) : FLown[k3at(g, W, v, vp, iP)];
+    repvals[cls] = val * g.T + add;
+}
+
+// ---- build_K3_cache!: src/nonlocal_2/build_K3_cache.jl:35-84.  One thread per K3 grid point ---------
+struct CachePtrs { C* c[10]; };
+__global__ void build_cache_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ DevChain F, CachePtrs out,
+                                   Grid g, long long i0, long long i1) {
+    long long i = i0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    int W, a1, b1, iP; decode_k3(g, i, W, a1, b1, iP);
+    Arg a; a.W = W; a.v = a1; a.w = b1; a.Px = iP % g.L; a.Py = iP / g.L; a.kx = a.ky = a.qx = a.qy = 0;
+    Arg ai = a; ai.w = FDGA_INF;      // second frequency -> infinity
+    Arg av = a; av.v = FDGA_INF;      // first frequency -> infinity
+    // (W, w, v') block
+    out.c[0][i] = eval_vertex<true>(F, 0, CH_P, SP_X, a, FL_GT | FL_GA);
+    out.c[1][i] = eval_vertex<true>(F0, 0, CH_P, SP_X, a, FL_ALL) - eval_vertex<true>(F0, 0, CH_P, SP_X, ai, FL_ALL);
+    C f0a = eval_vertex<true>(F0, 0, CH_A, SP_P, a, FL_ALL) - eval_vertex<true>(F0, 0, CH_A, SP_P, ai, FL_ALL);
+    C f0t = eval_vertex<true>(F0, 0, CH_T, SP_P, a, FL_ALL) - eval_vertex<true>(F0, 0, CH_T, SP_P, ai, FL_ALL);
+    out.c[2][i] = f0a;
+    out.c[3][i] = 2.0 * f0t - f0a;
+    // (W, v, w) block
+    C gpp = eval_vertex<true>(F, 0, CH_P, SP_P, a, FL_GT | FL_GA);
+    C ga  = eval_vertex<true>(F, 0, CH_A, SP_P, a, FL_GP | FL_GT);
+    C gt  = eval_vertex<true>(F, 0, CH_T, SP_P, a, FL_GP | FL_GA);
+    C fp = (eval_vertex<true>(F, 0, CH_P, SP_P, a, FL_F0 | FL_GP) - eval_vertex<true>(F, 0, CH_P, SP_P, av, FL_F0 | FL_GP)) + gpp;
+    C fa = (eval_vertex<true>(F, 0, CH_A, SP_P, a, FL_F0 | FL_GA) - eval_vertex<true>(F, 0, CH_A, SP_P, av, FL_F0 | FL_GA)) + ga;
+    C ft = (eval_vertex<true>(F, 0, CH_T, SP_P, a, FL_F0 | FL_GT) - eval_vertex<true>(F, 0, CH_T, SP_P, av, FL_F0 | FL_GT)) + gt;
+    out.c[4][i] = gpp;
+    out.c[5][i] = ga;
+    out.c[6][i] = gt * 2.0 - ga;
+    out.c[7][i] = fp;
+    out.c[8][i] = fa;
+    out.c[9][i] = ft * 2.0 - fa;
+}
+
+// ---- build_K3_cache_mfRG!: src/nonlocal_2/build_K3_cache.jl:108-161.  One thread per class rep --------
+//  kind 0: Gpx (pCh,xSp)  1: Gpp (pCh,pSp)  2: Ga  3: Gt   = S.F(...; g_r=false) - S.F.F0(...; g_r=false)
+//  kind 4: Fp  5: Fa  6: Ft                                = S.F0(W,v,w) - S.F0(W,inf,w)
+__global__ void cache_mfrg_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ DevChain F, int kind,
+                                  C* __restrict__ repvals, SymDev sg, long long c0, long long c1, Grid g) {
+    long long cls = c0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (cls >= c1) return;
+    long long idx = sg.index[sg.offsets[cls]];
+    int W, a1, b1, iP; decode_k3(g, idx, W, a1, b1, iP);
+    Arg a; a.W = W; a.v = a1; a.w = b1; a.Px = iP % g.L; a.Py = iP / g.L; a.kx = a.ky = a.qx = a.qy = 0;
+    C r;
+    if (kind < 4) {
+        int Ch = (kind <= 1) ? CH_P : (kind == 2 ? CH_A : CH_T);
+        int Sp = (kind == 0) ? SP_X : SP_P;
+        unsigned f = FL_ALL & ~(2u << Ch);
+        r = eval_vertex<true>(F, 0, Ch, Sp, a, f) - eval_vertex<true>(F, 1, Ch, Sp, a, f);
+    } else {
+        int Ch = (kind == 4) ? CH_P : (kind == 5 ? CH_A : CH_T);
+        Arg av = a; av.v = FDGA_INF;
+        r = eval_vertex<true>(F0, 0, Ch, SP_P, a, FL_ALL) - eval_vertex<true>(F0, 0, Ch, SP_P, av, FL_ALL);
+    }
+    repvals[cls] = r;
+}
+
+// ---- SDE_channel_L_pp!/ph!: src/nonlocal_2/SDE.jl:16-33, 54-73, 96-111, 130-145.  CTA per rep --------
+template <bool PP>
+__global__ void sde_L_kernel(const __grid_constant__ DevChain V, int level, const C* __restrict__ PiT,
+                             C* __restrict__ repvals, SymDev sg, long long c0, Grid g, C U, double scale, int own_only) {
+    long long cls = c0 + blockIdx.x;
+    long long idx = sg.index[sg.offsets[cls]];
+    const int nB2 = 2 * g.nK2b - 1, nF2 = 2 * g.nK2f, nw = 2 * g.nPiF, nBP = 2 * g.nPiB - 1;
+    long long t0 = idx;
+    int iW = t0 % nB2; t0 /= nB2; int iv = t0 % nF2; t0 /= nF2; int iP = t0 % g.NP; int ik = t0 / g.NP;
+    int W = iW - (g.nK2b - 1), v = iv - g.nK2f, Px = iP % g.L, Py = iP / g.L, kx = ik % g.L, ky = ik / g.L;
+    const C* slab = PiT + (size_t)nw * g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP);
+    const bool is_core = V.lev[level].type == LV_CORE;
+    C acc = zeroC();
+    for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
+        int iw = t % nw, iq = t / nw;
+        int w = iw - g.nPiF, qx = iq % g.L, qy = iq / g.L;
+        C d;
+        Arg a; a.W = W; a.Px = Px; a.Py = Py;
+        if (PP) {
+            a.v = W - w - 1; a.w = v; a.kx = Px - qx; a.ky = Py - qy; a.qx = kx; a.qy = ky;
+            if (is_core) d = core_eval(V.lev[level], CH_P, SP_P, a.W, a.v, a.w) - U;
+            else if (own_only) d = eval_vertex<false>(V, level, CH_P, SP_P, a, FL_GP);
+            else d = eval_vertex<false>(V, level, CH_P, SP_P, a, FL_F0 | FL_GP) - eval_vertex<false>(V, level + 1, CH_P, SP_P, a, FL_F0 | FL_GP);
+        } else {
+            a.v = v; a.w = w; a.kx = kx; a.ky = ky; a.qx = qx; a.qy = qy;
+            if (is_core) d = core_eval(V.lev[level], CH_A, SP_P, W, v, w) + core_eval(V.lev[level], CH_T, SP_P, W, v, w) - U - U;
+            else if (own_only) d = eval_vertex<false>(V, level, CH_A, SP_P, a, FL_GA) + eval_vertex<false>(V, level, CH_T, SP_P, a, FL_GT);
+            else d = eval_vertex<false>(V, level, CH_A, SP_P, a, FL_F0 | FL_GA) + eval_vertex<false>(V, level, CH_T, SP_P, a, FL_F0 | FL_GT)
+                   - eval_vertex<false>(V, level + 1, CH_A, SP_P, a, FL_F0 | FL_GA) - eval_vertex<false>(V, level + 1, CH_T, SP_P, a, FL_F0 | FL_GT);
+        }
+        acc += U * slab[t] * d;
+    }
+    acc = block_reduce(acc);
+    if (threadIdx.x == 0) repvals[cls] = acc * scale;
+}
+
+// ---- small DFT along one axis (FFTW conventions: sgn=-1 forward, +1 backward, unnormalised) -----------
+// data viewed as [pre][n][post] column-major; out-of-place; result multiplied by `scale`.
+__global__ void dft_axis_kernel(const C* __restrict__ in, C* __restrict__ out, long long pre, int n, long long post, int sgn, double scale) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long tot = pre * n * post;
+    if (i >= tot) return;
+    long long a = i % pre; long long t = i / pre; int k = t % n; long long b = t / n;
+    const C* p = in + a + pre * n * b;
+    C s = zeroC();
+    for (int j = 0; j < n; ++j) {
+        double sn, cs;
+        sincospi(2.0 * (double)(((long long)j * k) % n) / (double)n, &sn, &cs);
+        s += p[pre * j] * mkC(cs, sgn * sn);
+    }
+    out[i] = s * scale;
+}
+
+// G_R(n) call semantics: 0 outside the fermionic mesh
+__device__ __forceinline__ C gr_call(const C* GR, int nG, int LG, int n, int ix, int iy) {
+    if (!inF(n, nG)) return zeroC();
+    return GR[posF(n, nG) + (size_t)(2 * nG) * (ix + (size_t)LG * iy)];
+}
+
+// ---- bubbles_real_space!: src/nonlocal_2/bubble.jl:68-116.  One thread per Pi_R element ---------------
+__global__ void bubbles_rs_kernel(const C* __restrict__ GR, C* __restrict__ PippR, C* __restrict__ PiphR, Grid g) {
+    const int nBP = 2 * g.nPiB - 1, nFP = 2 * g.nPiF, L = g.L, LG = g.LG, h = L / 2;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long n = (long long)nBP * nFP * g.NP * g.NP;
+    if (i >= n) return;
+    long long t = i;
+    int iW = t % nBP; t /= nBP; int iv = t % nFP; t /= nFP; int ia = t % g.NP; int ib = t / g.NP;
+    int W = iW - (g.nPiB - 1), v = iv - g.nPiF;
+    int ax = ia % L, ay = ia / L, bx = ib % L, by = ib / L;
+    C spp = zeroC(), sph = zeroC();
+    for (int R2 = -h; R2 <= h; ++R2) { if (modL(R2, L) != ay) continue;
+    for (int R1 = -h; R1 <= h; ++R1) { if (modL(R1, L) != ax) continue;
+        C g1pp = gr_call(GR, g.nG, LG, W - v - 1, modL(R1, LG), modL(R2, LG));
+        C g1ph = gr_call(GR, g.nG, LG, W + v, modL(R1, LG), modL(R2, LG));
+        for (int Rp2 = -h; Rp2 <= h; ++Rp2) for (int Rp1 = -h; Rp1 <= h; ++Rp1) {
+            bool mpp = modL(Rp1 - R1, L) == bx && modL(Rp2 - R2, L) == by;
+            bool mph = modL(Rp1 + R1, L) == bx && modL(Rp2 + R2, L) == by;
+            if (!mpp && !mph) continue;
+            double wgt = 1.0;
+            if (LG % 2 == 0) {
+                if (abs(Rp1) == LG / 2) wgt /= 2; if (abs(Rp2) == LG / 2) wgt /= 2;
+                if (abs(R1) == LG / 2) wgt /= 2;  if (abs(R2) == LG / 2) wgt /= 2;
+            }
+            C g2 = gr_call(GR, g.nG, LG, v, modL(Rp1, LG), modL(Rp2, LG));
+            if (mpp) spp += g1pp * g2 * wgt;
+            if (mph) sph += g1ph * g2 * wgt;
+        }
+    }}
+    PippR[i] = spp; PiphR[i] = sph;
+}
+
+// ---- bubbles_momentum_space!: src/nonlocal_2/bubble.jl:1-37 -----------------------------------------
+__global__ void bubbles_ms_kernel(const C* __restrict__ G, C* __restrict__ Pipp, C* __restrict__ Piph, Grid g) {
+    const int nBP = 2 * g.nPiB - 1, nFP = 2 * g.nPiF, L = g.L, LG = g.LG, ratio = LG / L, nGf = 2 * g.nG;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long n = (long long)nBP * nFP * g.NP * g.NP;
+    if (i >= n) return;
+    long long t = i;
+    int iW = t % nBP; t /= nBP; int iv = t % nFP; t /= nFP; int iP = t % g.NP; int ik = t / g.NP;
+    int W = iW - (g.nPiB - 1), v = iv - g.nPiF;
+    int Px = (iP % L) * ratio, Py = (iP / L) * ratio, kx = (ik % L) * ratio, ky = (ik / L) * ratio;
+    C pp = zeroC(), ph = zeroC();
+    if (inF(v, g.nG)) {
+        C gk = G[posF(v, g.nG) + (size_t)nGf * kidx(kx, ky, LG)];
+        int a = W - v - 1, b = W + v;
+        if (inF(a, g.nG)) pp = gk * G[posF(a, g.nG) + (size_t)nGf * kidx(Px - kx, Py - ky, LG)];
+        if (inF(b, g.nG)) ph = gk * G[posF(b, g.nG) + (size_t)nGf * kidx(Px + kx, Py + ky, LG)];
+    }
+    Pipp[i] = pp; Piph[i] = ph;
+}
+
+// ---- Dyson!: src/dyson.jl:20-31 --------------------------------------------------------------------
+__global__ void dyson_kernel(C* __restrict__ G, const C* __restrict__ Sigma, const C* __restrict__ Gbare, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    C gb = Gbare[i];
+    double d = gb.x * gb.x + gb.y * gb.y;
+    C inv = mkC(gb.x / d, -gb.y / d) + Sigma[i];
+    double e = inv.x * inv.x + inv.y * inv.y;
+    G[i] = mkC(inv.x / e, -inv.y / e);
+}
+
+// ---- compute_occupation: src/dyson.jl:39-41 (single CTA, deterministic) ---------------------------------
+__global__ void occupation_kernel(const C* __restrict__ G, long long n, double T, double Nk, double* occ) {
+    C acc = zeroC();
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += G[i];
+    acc = block_reduce(acc);
+    if (threadIdx.x == 0) *occ = 0.5 + acc.y * T / Nk;
+}
+// Sigma += sgn * i (n - 1/2) U    (Hartree, src/nonlocal_2/SDE.jl:317-321, src/SDE.jl:19-23)
+__global__ void hartree_kernel(C* __restrict__ Sigma, const double* occ, C U, double sgn, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    C h = (U * (*occ - 0.5)) * mkC(0.0, 1.0);
+    Sigma[i] += h * sgn;
+}
+
+// ---- real-space contraction of SDE_compute!: src/nonlocal_2/SDE.jl:200-250 -----------------------------
+// SigR[v, tx, ty] (nSf x LS x LS) = T * sum_{R,Rp} [R+Rp == t] G_R(W-v; -R) Lpp_R[W,v,R,Rp] w + [-R+Rp == t] G_R(W+v; -R) Lph_R w
+__global__ void sde_rs_kernel(const C* __restrict__ GR, const C* __restrict__ LppR, const C* __restrict__ LphR,
+                              C* __restrict__ SigR, Grid g, int nSig, int LS) {
+    const int L = g.L, h = L / 2, LG = g.LG, nB = 2 * g.nK2b - 1, nF = 2 * g.nK2f, nSf = 2 * nSig;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long n = (long long)nSf * LS * LS;
+    if (i >= n) return;
+    int is = i % nSf; int tx = (i / nSf) % LS, ty = (i / nSf) / LS;
+    int v = is - nSig;
+    C acc = zeroC();
+    if (inF(v, g.nK2f)) {
+        int iv = posF(v, g.nK2f);
+        size_t pre = (size_t)nB * nF;
+        for (int R2 = -h; R2 <= h; ++R2) for (int R1 = -h; R1 <= h; ++R1) {
+            int gx = modL(-R1, LG), gy = modL(-R2, LG);
+            int iRL = modL(R1, L) + L * modL(R2, L);
+            for (int Rp2 = -h; Rp2 <= h; ++Rp2) for (int Rp1 = -h; Rp1 <= h; ++Rp1) {
+                bool mpp = modL(R1 + Rp1, LS) == tx && modL(R2 + Rp2, LS) == ty;
+                bool mph = modL(-R1 + Rp1, LS) == tx && modL(-R2 + Rp2, LS) == ty;
+                if (!mpp && !mph) continue;
+                double wgt = 1.0;
+                if (L % 2 == 0) {
+                    if (abs(Rp1) == L / 2) wgt /= 2; if (abs(Rp2) == L / 2) wgt /= 2;
+                    if (abs(R1) == L / 2) wgt /= 2;  if (abs(R2) == L / 2) wgt /= 2;
+                }
+                int iRpL = modL(Rp1, L) + L * modL(Rp2, L);
+                size_t lbase = pre * (iRL + (size_t)g.NP * iRpL) + (size_t)nB * iv;
+                for (int iW = 0; iW < nB; ++iW) {
+                    int W = iW - (g.nK2b - 1);
+                    if (mpp) acc += gr_call(GR, g.nG, LG, W - v - 1, gx, gy) * LppR[lbase + iW] * wgt;
+                    if (mph) acc += gr_call(GR, g.nG, LG, W + v, gx, gy) * LphR[lbase + iW] * wgt;
+                }
+            }
+        }
+    }
+    SigR[i] = acc * g.T;
+}
+
+// ---- SDE_U2_using_G: src/nonlocal/SDE.jl:421-438.  One thread per (nu, R) ----------------------------
+__global__ void sde_u2_kernel(const C* __restrict__ Gp, const C* __restrict__ Gm, C* __restrict__ SR, int nG, int LG, C fac) {
+    const int nGf = 2 * nG;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long n = (long long)nGf * LG * LG;
+    if (i >= n) return;
+    int iv = i % nGf; long long iR = i / nGf;
+    int v = iv - nG;
+    const C* gp = Gp + (size_t)nGf * iR; const C* gm = Gm + (size_t)nGf * iR;
+    C acc = zeroC();
+    for (int i2 = 0; i2 < nGf; ++i2) for (int i1 = 0; i1 < nGf; ++i1) {
+        int n3 = (i1 - nG) - (i2 - nG) + v;
+        if (inF(n3, nG)) acc += gm[i1] * gp[i2] * gp[posF(n3, nG)];
+    }
+    SR[i] = acc * fac;
+}
+
+}  // namespace fdga

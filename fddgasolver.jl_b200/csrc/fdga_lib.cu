@@ -1,0 +1,920 @@
+// fdga_lib.cu -- libfdga.so: context, data movement, kernel orchestration and the C-ABI of include/fdga.h.
+// Reference call structure being replaced: iterate_solver! (src/solve.jl:4-116), BSE_templates.jl:12-180,
+// SDE! (src/SDE.jl:3-48), mfRGLinearMap (src/mfRG.jl:34-89).
+#include "../../include/fdga.h"
+#include "fdga_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <dlfcn.h>
+
+using namespace fdga;
+
+extern "C" int64_t fdga_symgroup_build_host(int which_sg, int n0, int n1, int nq, int64_t* offsets, int64_t* index, uint8_t* ops);
+
+static thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------
+struct LevelBuf {
+    fdga_level_desc d;
+    C* K[3][3];          // [channel][class]
+    size_t len[3];
+    C* sw[3][4];         // [channel][K1sw, K2swk, K2sww, K3sw]
+    C* core[4];
+    size_t corelen;
+    bool sw_dirty;
+};
+struct SymGroup {
+    bool set;
+    long long ncls, nmem;
+    long long *d_offsets, *d_index;
+    unsigned char* d_ops;
+    int* d_member_class;
+    C* d_repvals;         // padded to chunk * nranks
+    long long chunk;
+    std::vector<long long> h_offsets;
+};
+struct TimedEvent { cudaEvent_t a, b; int cat; };
+
+// NCCL through dlopen (no link-time dependency; the process may already hold torch's libnccl)
+struct NcclApi {
+    void* h;
+    int (*GetUniqueId)(void*);
+    void* CommInitRank;                                  // bound with the by-value ncclUniqueId signature at the call site
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    int (*CommDestroy)(void*);
+    const char* (*GetErrorString)(int);
+};
+struct UniqueId { char b[128]; };
+
+struct fdga_ctx {
+    fdga_dims dims;
+    int device;
+    cudaStream_t stream;
+    Grid g;
+    int nlev;
+    LevelBuf lev[FDGA_MAX_LEVELS];
+    LevelBuf FL, Fbuff;
+    C* G[5]; size_t lenG;
+    C* Pi[4]; C* PiT[4]; C* Pisw[4]; size_t lenPi, lenPisw; bool pi_dirty[4];
+    C* cache[10]; size_t lenK3;
+    C* L[2];              // Lpp, Lph (K2-shaped)
+    C* Rt;                // hoisted right factor, bubble-sized
+    C* scratchA; C* scratchB; size_t lenScratch;   // bubble-sized ping-pong (DFTs)
+    C* GR; C* GRm; C* SigR; C* SigTmp; C* SigAcc;  // G-sized scratch
+    C* flat; size_t lenFlat;                       // flatten staging (device)
+    C* flat2;
+    double* d_occ;
+    SymGroup sg[FDGA_SG_COUNT];
+    // multi-GPU
+    int nranks, rank; void* comm; NcclApi nccl;
+    // profiling
+    bool profile; std::vector<TimedEvent> events; std::vector<cudaEvent_t> pool;
+    double t_ms[FDGA_T_COUNT]; long long n_launch[FDGA_T_COUNT]; long long total_launches;
+    int cur_cat; cudaEvent_t cur_a;
+    int opt_sde_own_gamma;   // FDGA_OPT_SDE_OWN_GAMMA
+    std::string err;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } } while (0)
+#define FAIL(msg) do { ctx->err = (msg); return 1; } while (0)
+
+static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
+
+// profiling scope: CUDA events on the launching stream around a group of launches
+struct Scope {
+    fdga_ctx* c; int cat; bool on;
+    Scope(fdga_ctx* c_, int cat_) : c(c_), cat(cat_), on(false) {
+        if (c->profile && c->cur_cat < 0) {
+            on = true; c->cur_cat = cat;
+            TimedEvent ev; ev.cat = cat;
+            cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
+            cudaEventRecord(ev.a, c->stream);
+            c->events.push_back(ev);
+        }
+    }
+    ~Scope() {
+        if (on) { cudaEventRecord(c->events.back().b, c->stream); c->cur_cat = -1; }
+    }
+};
+#define LAUNCH(cat, kernel, grid, block, ...) do { \
+    kernel<<<grid, block, 0, ctx->stream>>>(__VA_ARGS__); \
+    ctx->n_launch[cat]++; ctx->total_launches++; } while (0)
+
+static size_t lenK(const fdga_level_desc& d, int cls, int NP, bool nl2) {
+    size_t nB1 = 2 * d.nK1 - 1, nB2 = 2 * d.nK2[0] - 1, nF2 = 2 * d.nK2[1], nB3 = 2 * d.nK3[0] - 1, nF3 = 2 * d.nK3[1];
+    if (cls == 0) return nB1 * (nl2 ? NP : 1);
+    if (cls == 1) return nB2 * nF2 * (nl2 ? (size_t)NP * NP : 1);
+    return nB3 * nF3 * nF3 * (nl2 ? NP : 1);
+}
+
+static int alloc_level(fdga_ctx* ctx, LevelBuf& lb, const fdga_level_desc& d) {
+    memset(&lb, 0, sizeof(lb));
+    lb.d = d; lb.sw_dirty = true;
+    int NP = ctx->g.NP;
+    if (d.type == FDGA_LV_CORE) {
+        lb.corelen = (size_t)(2 * d.nK3[0] - 1) * (2 * d.nK3[1]) * (2 * d.nK3[1]);
+        if (d.nK3[0] <= 0 || d.nK3[1] <= 0) lb.corelen = 0;
+        for (int i = 0; i < 4; i++) if (lb.corelen) { CK(cudaMalloc(&lb.core[i], lb.corelen * sizeof(C))); CK(cudaMemsetAsync(lb.core[i], 0, lb.corelen * sizeof(C), ctx->stream)); }
+        return 0;
+    }
+    bool nl2 = d.type == FDGA_LV_NL2;
+    for (int cls = 0; cls < 3; cls++) lb.len[cls] = lenK(d, cls, NP, nl2);
+    for (int ch = 0; ch < 3; ch++) {
+        for (int cls = 0; cls < 3; cls++) { CK(cudaMalloc(&lb.K[ch][cls], lb.len[cls] * sizeof(C))); CK(cudaMemsetAsync(lb.K[ch][cls], 0, lb.len[cls] * sizeof(C), ctx->stream)); }
+        if (nl2) {
+            size_t n[4] = { (size_t)(2 * d.nK1 - 1), (size_t)(2 * d.nK2[0] - 1) * (2 * d.nK2[1]) * NP,
+                            (size_t)(2 * d.nK2[0] - 1) * (2 * d.nK2[1]), (size_t)(2 * d.nK3[0] - 1) * (2 * d.nK3[1]) * (2 * d.nK3[1]) };
+            for (int j = 0; j < 4; j++) CK(cudaMalloc(&lb.sw[ch][j], n[j] * sizeof(C)));
+        }
+    }
+    return 0;
+}
+static void free_level(LevelBuf& lb) {
+    for (int ch = 0; ch < 3; ch++) { for (int cls = 0; cls < 3; cls++) cudaFree(lb.K[ch][cls]); for (int j = 0; j < 4; j++) cudaFree(lb.sw[ch][j]); }
+    for (int i = 0; i < 4; i++) cudaFree(lb.core[i]);
+}
+
+static DevLevel dev_level(const LevelBuf& lb) {
+    DevLevel d; memset(&d, 0, sizeof(d));
+    d.type = lb.d.type; d.nK1 = lb.d.nK1; d.nK2b = lb.d.nK2[0]; d.nK2f = lb.d.nK2[1]; d.nK3b = lb.d.nK3[0]; d.nK3f = lb.d.nK3[1];
+    d.U = mkC(lb.d.U_re, lb.d.U_im);
+    for (int ch = 0; ch < 3; ch++) {
+        d.ch[ch].K1 = lb.K[ch][0]; d.ch[ch].K2 = lb.K[ch][1]; d.ch[ch].K3 = lb.K[ch][2];
+        d.ch[ch].K1sw = lb.sw[ch][0]; d.ch[ch].K2swk = lb.sw[ch][1]; d.ch[ch].K2sww = lb.sw[ch][2]; d.ch[ch].K3sw = lb.sw[ch][3];
+    }
+    for (int i = 0; i < 4; i++) d.core[i] = lb.core[i];
+    if (lb.d.type == FDGA_LV_CORE && lb.corelen == 0) { d.nK3b = 0; d.nK3f = 0; }
+    return d;
+}
+static DevLevel null_core() {
+    DevLevel d; memset(&d, 0, sizeof(d)); d.type = LV_CORE; d.U = zeroC(); return d;
+}
+// chain of S.F starting at `from` (0 -> S.F, 1 -> S.F0)
+static DevChain chain_F(fdga_ctx* ctx, int from) {
+    DevChain c; memset(&c, 0, sizeof(c));
+    c.L = ctx->g.L; c.NP = ctx->g.NP; c.nlev = ctx->nlev - from;
+    for (int l = from; l < ctx->nlev; l++) c.lev[l - from] = dev_level(ctx->lev[l]);
+    return c;
+}
+static DevChain chain_FL(fdga_ctx* ctx) {
+    DevChain c; memset(&c, 0, sizeof(c));
+    c.L = ctx->g.L; c.NP = ctx->g.NP; c.nlev = 2;
+    c.lev[0] = dev_level(ctx->FL); c.lev[1] = null_core();
+    return c;
+}
+static SymDev sym_dev(const SymGroup& s) {
+    SymDev d; d.ncls = s.ncls; d.nmem = s.nmem; d.offsets = s.d_offsets; d.index = s.d_index; d.ops = s.d_ops; d.member_class = s.d_member_class;
+    return d;
+}
+static C bareU(fdga_ctx* ctx) { const fdga_level_desc& d = ctx->lev[ctx->nlev - 1].d; return mkC(d.U_re, d.U_im); }
+
+// ------------------------------------------------------------------------------------------------
+// auxiliaries kept current lazily
+static int refresh_swave(fdga_ctx* ctx) {
+    for (int l = 0; l <= ctx->nlev; l++) {
+        LevelBuf& lb = (l == ctx->nlev) ? ctx->FL : ctx->lev[l];
+        if (lb.d.type != FDGA_LV_NL2 || !lb.sw_dirty) continue;
+        Scope sc(ctx, FDGA_T_SWAVE);
+        DevLevel dl = dev_level(lb);
+        long long n = (long long)(2 * lb.d.nK1 - 1) + (long long)(2 * lb.d.nK2[0] - 1) * (2 * lb.d.nK2[1]) * (ctx->g.NP + 1)
+                    + (long long)(2 * lb.d.nK3[0] - 1) * (2 * lb.d.nK3[1]) * (2 * lb.d.nK3[1]);
+        for (int ch = 0; ch < 3; ch++)
+            LAUNCH(FDGA_T_SWAVE, swave_tables_kernel, nblk(n, 128), 128, dl, ch, ctx->g.NP, lb.sw[ch][0], lb.sw[ch][1], lb.sw[ch][2], lb.sw[ch][3]);
+        lb.sw_dirty = false;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+static int refresh_pi(fdga_ctx* ctx, int which) {
+    if (!ctx->pi_dirty[which]) return 0;
+    Scope sc(ctx, FDGA_T_MISC);
+    int nB = 2 * ctx->g.nPiB - 1, nF = 2 * ctx->g.nPiF, NP = ctx->g.NP;
+    LAUNCH(FDGA_T_MISC, pi_transpose_kernel, nblk(ctx->lenPi, 256), 256, ctx->Pi[which], ctx->PiT[which], nB, nF, NP);
+    LAUNCH(FDGA_T_MISC, pi_swave_kernel, nblk(ctx->lenPisw, 256), 256, ctx->Pi[which], ctx->Pisw[which], nB, nF, NP);
+    CK(cudaGetLastError());
+    ctx->pi_dirty[which] = false;
+    return 0;
+}
+
+// SG finish: (all-gather of representative values) + expansion to all class members
+static int sg_class_range(fdga_ctx* ctx, const SymGroup& s, long long& c0, long long& c1) {
+    c0 = (long long)ctx->rank * s.chunk; c1 = c0 + s.chunk;
+    if (c0 > s.ncls) c0 = s.ncls;
+    if (c1 > s.ncls) c1 = s.ncls;
+    return 0;
+}
+static int sg_finish(fdga_ctx* ctx, SymGroup& s, C* out) {
+    if (ctx->nranks > 1) {
+        Scope sc(ctx, FDGA_T_COMM);
+        int rc = ctx->nccl.AllGather(s.d_repvals + (size_t)ctx->rank * s.chunk, s.d_repvals, (size_t)s.chunk * 2, /*ncclDouble*/ 8, ctx->comm, ctx->stream);
+        if (rc != 0) FAIL(std::string("ncclAllGather: ") + ctx->nccl.GetErrorString(rc));
+        ctx->n_launch[FDGA_T_COMM]++;
+    }
+    Scope sc(ctx, FDGA_T_EXPAND);
+    LAUNCH(FDGA_T_EXPAND, expand_kernel, nblk(s.nmem, 256), 256, out, s.d_repvals, sym_dev(s));
+    CK(cudaGetLastError());
+    return 0;
+}
+#define NEED_SG(which) do { if (!ctx->sg[which].set) FAIL("symmetry group " #which " not set (call fdga_set_symmetry_classes)"); } while (0)
+
+static int axpby(fdga_ctx* ctx, C* out, const C* x, double a, const C* y, double b, size_t n) {
+    LAUNCH(FDGA_T_MISC, axpby_kernel, nblk(n, 256), 256, out, x, a, y, b, (long long)n);
+    CK(cudaGetLastError()); return 0;
+}
+static int add_axpby(fdga_ctx* ctx, C* out, const C* x, double a, const C* y, double b, size_t n) {
+    LAUNCH(FDGA_T_MISC, add_axpby_kernel, nblk(n, 256), 256, out, x, a, y, b, (long long)n);
+    CK(cudaGetLastError()); return 0;
+}
+// t-channel post-fix: X_t <- (X_t + X_a) / 2   (BSE_templates.jl:35-38 etc.)
+static int tfix(fdga_ctx* ctx, C* Xt, const C* Xa, size_t n) { return axpby(ctx, Xt, Xt, 0.5, Xa, 0.5, n); }
+
+// 2-d DFT of a G-shaped array over its momentum axes: in -> out (tmp used), out *= scale
+static int dft2_G(fdga_ctx* ctx, const C* in, C* out, C* tmp, int sgn, double scale, int cat) {
+    long long nGf = 2 * ctx->g.nG, LG = ctx->g.LG;
+    long long n = nGf * LG * LG;
+    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, in, tmp, nGf, (int)LG, LG, sgn, 1.0);
+    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, tmp, out, nGf * LG, (int)LG, 1LL, sgn, scale);
+    CK(cudaGetLastError()); return 0;
+}
+// 4-d DFT over the momentum axes of a [pre, L, L, L, L] array; result ends up in `a` (b = scratch)
+static int dft4(fdga_ctx* ctx, C* a, C* b, long long pre, int sgn, double scale, int cat) {
+    long long L = ctx->g.L, n = pre * L * L * L * L;
+    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, a, b, pre, (int)L, L * L * L, sgn, 1.0);
+    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, b, a, pre * L, (int)L, L * L, sgn, 1.0);
+    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, a, b, pre * L * L, (int)L, L, sgn, 1.0);
+    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, b, a, pre * L * L * L, (int)L, 1LL, sgn, scale);
+    CK(cudaGetLastError()); return 0;
+}
+
+// ================================================================================================
+extern "C" {
+
+const char* fdga_last_error(fdga_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { g_create_error = std::string("no CUDA device available (libfdga has no CPU fallback): ") + cudaGetErrorString(e); return 2; }
+    if (device < 0 || device >= ndev) { g_create_error = "invalid device index"; return 2; }
+    if (dims->nlev < 2 || dims->nlev > FDGA_MAX_LEVELS || dims->lev[0].type != FDGA_LV_NL2 || dims->lev[dims->nlev - 1].type != FDGA_LV_CORE) {
+        g_create_error = "dims: need lev[0] = NL2 and lev[nlev-1] = CORE, 2 <= nlev <= FDGA_MAX_LEVELS"; return 2; }
+    for (int l = 1; l < dims->nlev - 1; l++) if (dims->lev[l].type == FDGA_LV_CORE) { g_create_error = "dims: CORE level must be last"; return 2; }
+    const fdga_level_desc& d0 = dims->lev[0];
+    if (dims->nPiB != d0.nK1) { g_create_error = "dims: bubble bosonic mesh must equal the K1 mesh (nPiB == nK1)"; return 2; }
+    if (!(d0.nK1 > d0.nK2[0] && d0.nK1 > d0.nK2[1] && d0.nK2[0] >= d0.nK3[0] && d0.nK2[1] >= d0.nK3[1] && dims->nPiF >= d0.nK2[1])) {
+        g_create_error = "dims: mesh constraints violated (src/nonlocal_2/channel.jl:26-33)"; return 2; }
+    fdga_ctx* ctx = new fdga_ctx();
+    ctx->dims = *dims; ctx->device = device; ctx->nlev = dims->nlev;
+    ctx->nranks = 1; ctx->rank = 0; ctx->comm = nullptr; memset(&ctx->nccl, 0, sizeof(ctx->nccl));
+    ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0;
+    memset(ctx->t_ms, 0, sizeof(ctx->t_ms)); memset(ctx->n_launch, 0, sizeof(ctx->n_launch));
+    Grid& g = ctx->g;
+    g.T = dims->T; g.L = dims->nq; g.NP = dims->nq * dims->nq; g.nPiB = dims->nPiB; g.nPiF = dims->nPiF;
+    g.nK1 = d0.nK1; g.nK2b = d0.nK2[0]; g.nK2f = d0.nK2[1]; g.nK3b = d0.nK3[0]; g.nK3f = d0.nK3[1]; g.LG = dims->LG; g.nG = dims->nG;
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_create_error = std::string(#call) + ": " + cudaGetErrorString(e_); delete ctx; return 1; } } while (0)
+    CKC(cudaSetDevice(device));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int l = 0; l < ctx->nlev; l++) if (alloc_level(ctx, ctx->lev[l], dims->lev[l])) { g_create_error = ctx->err; delete ctx; return 1; }
+    fdga_level_desc dz = d0; dz.type = FDGA_LV_NL2;
+    if (alloc_level(ctx, ctx->FL, dz) || alloc_level(ctx, ctx->Fbuff, dz)) { g_create_error = ctx->err; delete ctx; return 1; }
+    ctx->lenG = (size_t)2 * g.nG * g.LG * g.LG;
+    for (int i = 0; i < 5; i++) { CKC(cudaMalloc(&ctx->G[i], ctx->lenG * sizeof(C))); CKC(cudaMemsetAsync(ctx->G[i], 0, ctx->lenG * sizeof(C), ctx->stream)); }
+    ctx->lenPi = (size_t)(2 * g.nPiB - 1) * (2 * g.nPiF) * g.NP * g.NP;
+    ctx->lenPisw = (size_t)(2 * g.nPiB - 1) * (2 * g.nPiF) * g.NP;
+    for (int i = 0; i < 4; i++) {
+        CKC(cudaMalloc(&ctx->Pi[i], ctx->lenPi * sizeof(C))); CKC(cudaMemsetAsync(ctx->Pi[i], 0, ctx->lenPi * sizeof(C), ctx->stream));
+        CKC(cudaMalloc(&ctx->PiT[i], ctx->lenPi * sizeof(C))); CKC(cudaMalloc(&ctx->Pisw[i], ctx->lenPisw * sizeof(C)));
+        ctx->pi_dirty[i] = true;
+    }
+    ctx->lenK3 = ctx->lev[0].len[2];
+    for (int i = 0; i < 10; i++) { CKC(cudaMalloc(&ctx->cache[i], ctx->lenK3 * sizeof(C))); CKC(cudaMemsetAsync(ctx->cache[i], 0, ctx->lenK3 * sizeof(C), ctx->stream)); }
+    for (int i = 0; i < 2; i++) { CKC(cudaMalloc(&ctx->L[i], ctx->lev[0].len[1] * sizeof(C))); CKC(cudaMemsetAsync(ctx->L[i], 0, ctx->lev[0].len[1] * sizeof(C), ctx->stream)); }
+    CKC(cudaMalloc(&ctx->Rt, ctx->lenPi * sizeof(C)));
+    ctx->lenScratch = ctx->lenPi;
+    CKC(cudaMalloc(&ctx->scratchA, ctx->lenScratch * sizeof(C))); CKC(cudaMalloc(&ctx->scratchB, ctx->lenScratch * sizeof(C)));
+    CKC(cudaMalloc(&ctx->GR, ctx->lenG * sizeof(C))); CKC(cudaMalloc(&ctx->GRm, ctx->lenG * sizeof(C)));
+    CKC(cudaMalloc(&ctx->SigR, ctx->lenG * sizeof(C))); CKC(cudaMalloc(&ctx->SigTmp, ctx->lenG * sizeof(C))); CKC(cudaMalloc(&ctx->SigAcc, ctx->lenG * sizeof(C)));
+    ctx->lenFlat = 3 * (ctx->lev[0].len[0] + ctx->lev[0].len[1] + ctx->lev[0].len[2]);
+    CKC(cudaMalloc(&ctx->flat, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->flat2, ctx->lenFlat * sizeof(C)));
+    CKC(cudaMalloc(&ctx->d_occ, sizeof(double)));
+    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; }
+    CKC(cudaStreamSynchronize(ctx->stream));
+    *out = ctx;
+    return 0;
+}
+
+int fdga_destroy(fdga_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
+    for (int l = 0; l < ctx->nlev; l++) free_level(ctx->lev[l]);
+    free_level(ctx->FL); free_level(ctx->Fbuff);
+    for (int i = 0; i < 5; i++) cudaFree(ctx->G[i]);
+    for (int i = 0; i < 4; i++) { cudaFree(ctx->Pi[i]); cudaFree(ctx->PiT[i]); cudaFree(ctx->Pisw[i]); }
+    for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
+    cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->Rt); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB);
+    cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
+    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->d_occ);
+    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); cudaFree(s.d_repvals); }
+    for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+int fdga_set_option(fdga_ctx* ctx, int opt, int value) {
+    if (opt == FDGA_OPT_SDE_OWN_GAMMA) { ctx->opt_sde_own_gamma = value != 0; return 0; }
+    FAIL("fdga_set_option: unknown option");
+}
+int fdga_sync(fdga_ctx* ctx) { CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+void* fdga_stream(fdga_ctx* ctx) { return (void*)ctx->stream; }
+
+// ---- NCCL ----------------------------------------------------------------------------------------
+static int load_nccl(NcclApi& a, std::string& err) {
+    if (a.h) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { a.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (a.h) break; }
+    if (!a.h) { err = std::string("dlopen libnccl failed: ") + dlerror(); return 1; }
+    a.GetUniqueId = (int (*)(void*))dlsym(a.h, "ncclGetUniqueId");
+    a.CommInitRank = dlsym(a.h, "ncclCommInitRank");
+    a.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(a.h, "ncclAllGather");
+    a.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(a.h, "ncclAllReduce");
+    a.CommDestroy = (int (*)(void*))dlsym(a.h, "ncclCommDestroy");
+    a.GetErrorString = (const char* (*)(int))dlsym(a.h, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy || !a.GetErrorString) { err = "libnccl: missing symbols"; return 1; }
+    return 0;
+}
+int fdga_comm_unique_id(void* unique_id_128B) {
+    NcclApi a; memset(&a, 0, sizeof(a)); std::string err;
+    if (load_nccl(a, err)) { g_create_error = err; return 1; }
+    int rc = a.GetUniqueId(unique_id_128B);
+    if (rc) { g_create_error = std::string("ncclGetUniqueId: ") + a.GetErrorString(rc); return 1; }
+    return 0;
+}
+int fdga_comm_init(fdga_ctx* ctx, int nranks, int rank, const void* unique_id_128B) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) FAIL("fdga_comm_init: bad nranks/rank");
+    CK(cudaSetDevice(ctx->device));
+    if (nranks > 1) {
+        if (load_nccl(ctx->nccl, ctx->err)) return 1;
+        typedef int (*init_t)(void**, int, UniqueId, int);
+        init_t init = (init_t)ctx->nccl.CommInitRank;
+        UniqueId id; memcpy(id.b, unique_id_128B, 128);
+        int rc = init(&ctx->comm, nranks, id, rank);
+        if (rc) FAIL(std::string("ncclCommInitRank: ") + ctx->nccl.GetErrorString(rc));
+    }
+    ctx->nranks = nranks; ctx->rank = rank;
+    // re-chunk already registered symmetry groups
+    for (int i = 0; i < FDGA_SG_COUNT; i++) {
+        SymGroup& s = ctx->sg[i];
+        if (!s.set) continue;
+        s.chunk = (s.ncls + nranks - 1) / nranks;
+        cudaFree(s.d_repvals);
+        CK(cudaMalloc(&s.d_repvals, (size_t)s.chunk * nranks * sizeof(C)));
+        CK(cudaMemset(s.d_repvals, 0, (size_t)s.chunk * nranks * sizeof(C)));
+    }
+    return 0;
+}
+
+// ---- data movement ---------------------------------------------------------------------------------
+static LevelBuf* which_level(fdga_ctx* ctx, int which) {
+    if (which == FDGA_V_FL) return &ctx->FL;
+    if (which == FDGA_V_FBUFF) return &ctx->Fbuff;
+    if (which >= 0 && which < ctx->nlev) return &ctx->lev[which];
+    return nullptr;
+}
+int fdga_set_vertex(fdga_ctx* ctx, int which, int channel, int cls, const fdga_c64* host, int64_t n) {
+    CK(cudaSetDevice(ctx->device));
+    LevelBuf* lb = which_level(ctx, which);
+    if (!lb || lb->d.type == FDGA_LV_CORE || channel < 0 || channel > 2 || cls < 0 || cls > 2) FAIL("fdga_set_vertex: bad selector");
+    if ((size_t)n != lb->len[cls]) FAIL("fdga_set_vertex: length mismatch");
+    CK(cudaMemcpyAsync(lb->K[channel][cls], host, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    lb->sw_dirty = true;
+    return 0;
+}
+int fdga_get_vertex(fdga_ctx* ctx, int which, int channel, int cls, fdga_c64* host, int64_t n) {
+    CK(cudaSetDevice(ctx->device));
+    LevelBuf* lb = which_level(ctx, which);
+    if (!lb || lb->d.type == FDGA_LV_CORE || channel < 0 || channel > 2 || cls < 0 || cls > 2) FAIL("fdga_get_vertex: bad selector");
+    if ((size_t)n != lb->len[cls]) FAIL("fdga_get_vertex: length mismatch");
+    CK(cudaMemcpyAsync(host, lb->K[channel][cls], n * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int fdga_set_core(fdga_ctx* ctx, int level, int which4, const fdga_c64* host, int64_t n) {
+    CK(cudaSetDevice(ctx->device));
+    if (level < 0 || level >= ctx->nlev || ctx->lev[level].d.type != FDGA_LV_CORE || which4 < 0 || which4 > 3) FAIL("fdga_set_core: bad selector");
+    if ((size_t)n != ctx->lev[level].corelen) FAIL("fdga_set_core: length mismatch");
+    CK(cudaMemcpyAsync(ctx->lev[level].core[which4], host, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+#define SETGET(NAME, ARR, COUNT, LEN, DIRTY) \
+int fdga_set_##NAME(fdga_ctx* ctx, int which, const fdga_c64* host, int64_t n) { \
+    CK(cudaSetDevice(ctx->device)); \
+    if (which < 0 || which >= COUNT) FAIL("fdga_set_" #NAME ": bad selector"); \
+    if ((size_t)n != (LEN)) FAIL("fdga_set_" #NAME ": length mismatch"); \
+    CK(cudaMemcpyAsync(ctx->ARR[which], host, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream)); \
+    CK(cudaStreamSynchronize(ctx->stream)); DIRTY; return 0; } \
+int fdga_get_##NAME(fdga_ctx* ctx, int which, fdga_c64* host, int64_t n) { \
+    CK(cudaSetDevice(ctx->device)); \
+    if (which < 0 || which >= COUNT) FAIL("fdga_get_" #NAME ": bad selector"); \
+    if ((size_t)n != (LEN)) FAIL("fdga_get_" #NAME ": length mismatch"); \
+    CK(cudaMemcpyAsync(host, ctx->ARR[which], n * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream)); \
+    CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+SETGET(green, G, 5, ctx->lenG, (void)0)
+SETGET(bubble, Pi, 4, ctx->lenPi, ctx->pi_dirty[which] = true)
+SETGET(cache, cache, 10, ctx->lenK3, (void)0)
+int fdga_get_L(fdga_ctx* ctx, int is_pp, fdga_c64* host, int64_t n) {
+    CK(cudaSetDevice(ctx->device));
+    if ((size_t)n != ctx->lev[0].len[1]) FAIL("fdga_get_L: length mismatch");
+    CK(cudaMemcpyAsync(host, ctx->L[is_pp ? 0 : 1], n * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); return 0;
+}
+
+static size_t sg_target_len(fdga_ctx* ctx, int which) {
+    if (which == FDGA_SG_SIGMA) return ctx->lenG;
+    if (which == FDGA_SG_K1) return ctx->lev[0].len[0];
+    if (which == FDGA_SG_PP2 || which == FDGA_SG_PH2) return ctx->lev[0].len[1];
+    return ctx->lev[0].len[2];
+}
+int fdga_set_symmetry_classes(fdga_ctx* ctx, int which, int64_t nclasses, const int64_t* offsets, const int64_t* index, const uint8_t* ops) {
+    CK(cudaSetDevice(ctx->device));
+    if (which < 0 || which >= FDGA_SG_COUNT) FAIL("fdga_set_symmetry_classes: bad selector");
+    size_t len = sg_target_len(ctx, which);
+    long long nmem = offsets[nclasses];
+    if (nclasses <= 0 || offsets[0] != 0 || (size_t)nmem > len) FAIL("fdga_set_symmetry_classes: malformed class table");
+    std::vector<int> mclass(nmem);
+    std::vector<unsigned char> seen(len, 0);
+    for (int64_t c = 0; c < nclasses; c++) {
+        if (offsets[c + 1] <= offsets[c]) FAIL("fdga_set_symmetry_classes: empty class");
+        for (int64_t j = offsets[c]; j < offsets[c + 1]; j++) {
+            if (index[j] < 0 || (size_t)index[j] >= len || seen[index[j]]) FAIL("fdga_set_symmetry_classes: index out of range or repeated");
+            seen[index[j]] = 1; mclass[j] = (int)c;
+        }
+    }
+    SymGroup& s = ctx->sg[which];
+    cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); cudaFree(s.d_repvals);
+    s.ncls = nclasses; s.nmem = nmem; s.chunk = (nclasses + ctx->nranks - 1) / ctx->nranks;
+    s.h_offsets.assign(offsets, offsets + nclasses + 1);
+    CK(cudaMalloc(&s.d_offsets, (nclasses + 1) * sizeof(long long))); CK(cudaMalloc(&s.d_index, nmem * sizeof(long long)));
+    CK(cudaMalloc(&s.d_ops, nmem)); CK(cudaMalloc(&s.d_member_class, nmem * sizeof(int)));
+    CK(cudaMalloc(&s.d_repvals, (size_t)s.chunk * ctx->nranks * sizeof(C)));
+    CK(cudaMemset(s.d_repvals, 0, (size_t)s.chunk * ctx->nranks * sizeof(C)));
+    CK(cudaMemcpy(s.d_offsets, offsets, (nclasses + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.d_index, index, nmem * sizeof(long long), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.d_ops, ops, nmem, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.d_member_class, mclass.data(), nmem * sizeof(int), cudaMemcpyHostToDevice));
+    s.set = true;
+    return 0;
+}
+int fdga_build_symmetry_group(int which_sg, int n0, int n1, int nq, int64_t* offsets, int64_t* index, uint8_t* ops, int64_t* nclasses) {
+    if (which_sg < 0 || which_sg >= FDGA_SG_COUNT) return 1;
+    *nclasses = fdga_symgroup_build_host(which_sg, n0, n1, nq, offsets, index, ops);
+    return 0;
+}
+
+int64_t fdga_length_F(fdga_ctx* ctx) { return (int64_t)ctx->lenFlat; }
+static int flatten_dev(fdga_ctx* ctx, const LevelBuf& lb, C* dst) {
+    size_t off = 0;
+    for (int ch = 0; ch < 3; ch++) for (int cls = 0; cls < 3; cls++) {
+        CK(cudaMemcpyAsync(dst + off, lb.K[ch][cls], lb.len[cls] * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+        off += lb.len[cls];
+    }
+    return 0;
+}
+int fdga_flatten_F(fdga_ctx* ctx, fdga_c64* host_y) {
+    CK(cudaSetDevice(ctx->device));
+    if (flatten_dev(ctx, ctx->lev[0], ctx->flat)) return 1;
+    CK(cudaMemcpyAsync(host_y, ctx->flat, ctx->lenFlat * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+static int unflatten_dev(fdga_ctx* ctx, LevelBuf& lb, const C* src, double scale) {
+    size_t off = 0;
+    for (int ch = 0; ch < 3; ch++) for (int cls = 0; cls < 3; cls++) {
+        LAUNCH(FDGA_T_MISC, scale_copy_kernel, nblk(lb.len[cls], 256), 256, lb.K[ch][cls], src + off, scale, (long long)lb.len[cls]);
+        off += lb.len[cls];
+    }
+    CK(cudaGetLastError());
+    lb.sw_dirty = true;
+    return 0;
+}
+int fdga_unflatten_F(fdga_ctx* ctx, const fdga_c64* host_x, double scale) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->flat, host_x, ctx->lenFlat * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    return unflatten_dev(ctx, ctx->lev[0], ctx->flat, scale);
+}
+
+// ---- Dyson / occupation / bubbles --------------------------------------------------------------------
+int fdga_dyson(fdga_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    Scope sc(ctx, FDGA_T_MISC);
+    LAUNCH(FDGA_T_MISC, dyson_kernel, nblk(ctx->lenG, 256), 256, ctx->G[FDGA_G], ctx->G[FDGA_SIGMA], ctx->G[FDGA_GBARE], (long long)ctx->lenG);
+    CK(cudaGetLastError()); return 0;
+}
+static int occupation_dev(fdga_ctx* ctx, int which) {
+    LAUNCH(FDGA_T_MISC, occupation_kernel, 1, 1024, ctx->G[which], (long long)ctx->lenG, ctx->g.T, (double)(ctx->g.LG * ctx->g.LG), ctx->d_occ);
+    CK(cudaGetLastError()); return 0;
+}
+int fdga_occupation(fdga_ctx* ctx, int which, double* occ) {
+    CK(cudaSetDevice(ctx->device));
+    if (which != FDGA_G && which != FDGA_G0 && which != FDGA_GBARE) FAIL("fdga_occupation: bad selector");
+    if (occupation_dev(ctx, which)) return 1;
+    CK(cudaMemcpyAsync(occ, ctx->d_occ, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int fdga_bubbles_real_space(fdga_ctx* ctx, int reference) {
+    CK(cudaSetDevice(ctx->device));
+    Scope sc(ctx, FDGA_T_BUBBLE);
+    const Grid& g = ctx->g;
+    int ipp = reference ? FDGA_PI0PP : FDGA_PIPP, iph = reference ? FDGA_PI0PH : FDGA_PIPH;
+    const C* Gsrc = ctx->G[reference ? FDGA_G0 : FDGA_G];
+    if (dft2_G(ctx, Gsrc, ctx->GR, ctx->SigTmp, -1, 1.0 / ((double)g.LG * g.LG), FDGA_T_BUBBLE)) return 1;
+    LAUNCH(FDGA_T_BUBBLE, bubbles_rs_kernel, nblk(ctx->lenPi, 128), 128, ctx->GR, ctx->Pi[ipp], ctx->Pi[iph], g);
+    CK(cudaGetLastError());
+    long long pre = (long long)(2 * g.nPiB - 1) * (2 * g.nPiF);
+    if (dft4(ctx, ctx->Pi[ipp], ctx->scratchA, pre, +1, 1.0, FDGA_T_BUBBLE)) return 1;
+    if (dft4(ctx, ctx->Pi[iph], ctx->scratchA, pre, +1, 1.0, FDGA_T_BUBBLE)) return 1;
+    ctx->pi_dirty[ipp] = ctx->pi_dirty[iph] = true;
+    return 0;
+}
+int fdga_bubbles_momentum_space(fdga_ctx* ctx, int reference) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->g.LG % ctx->g.L != 0) FAIL("fdga_bubbles_momentum_space: LG must be a multiple of nq");
+    Scope sc(ctx, FDGA_T_BUBBLE);
+    int ipp = reference ? FDGA_PI0PP : FDGA_PIPP, iph = reference ? FDGA_PI0PH : FDGA_PIPH;
+    LAUNCH(FDGA_T_BUBBLE, bubbles_ms_kernel, nblk(ctx->lenPi, 128), 128, ctx->G[reference ? FDGA_G0 : FDGA_G], ctx->Pi[ipp], ctx->Pi[iph], ctx->g);
+    CK(cudaGetLastError());
+    ctx->pi_dirty[ipp] = ctx->pi_dirty[iph] = true;
+    return 0;
+}
+
+// ---- K3 cache ------------------------------------------------------------------------------------------
+int fdga_build_K3_cache(fdga_ctx* ctx, int mfrg, int first) {
+    CK(cudaSetDevice(ctx->device));
+    if (refresh_swave(ctx)) return 1;
+    Scope sc(ctx, FDGA_T_CACHE);
+    DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0);
+    if (!mfrg) {
+        CachePtrs cp; for (int i = 0; i < 10; i++) cp.c[i] = ctx->cache[i];
+        LAUNCH(FDGA_T_CACHE, build_cache_kernel, nblk(ctx->lenK3, 64), 64, F0, F, cp, ctx->g, 0LL, (long long)ctx->lenK3);
+        CK(cudaGetLastError());
+        return 0;
+    }
+    NEED_SG(FDGA_SG_PP3); NEED_SG(FDGA_SG_PH3);
+    struct { int kind, cache, sg; } jobs[7] = { {0, FDGA_C_GPX, FDGA_SG_PP3}, {1, FDGA_C_GPP, FDGA_SG_PP3}, {2, FDGA_C_GA, FDGA_SG_PH3}, {3, FDGA_C_GT, FDGA_SG_PH3},
+                                               {4, FDGA_C_FP, FDGA_SG_PP3}, {5, FDGA_C_FA, FDGA_SG_PH3}, {6, FDGA_C_FT, FDGA_SG_PH3} };
+    int njobs = first ? 7 : 4;
+    for (int j = 0; j < njobs; j++) {
+        SymGroup& s = ctx->sg[jobs[j].sg];
+        long long c0, c1; sg_class_range(ctx, s, c0, c1);
+        if (c1 > c0) LAUNCH(FDGA_T_CACHE, cache_mfrg_kernel, nblk(c1 - c0, 64), 64, F0, F, jobs[j].kind, s.d_repvals, sym_dev(s), c0, c1, ctx->g);
+        CK(cudaGetLastError());
+        if (sg_finish(ctx, s, ctx->cache[jobs[j].cache])) return 1;
+        if (jobs[j].kind == 3) { if (axpby(ctx, ctx->cache[FDGA_C_GT], ctx->cache[FDGA_C_GT], 2.0, ctx->cache[FDGA_C_GA], -1.0, ctx->lenK3)) return 1; }
+        if (jobs[j].kind == 6) { if (axpby(ctx, ctx->cache[FDGA_C_FT], ctx->cache[FDGA_C_FT], 2.0, ctx->cache[FDGA_C_FA], -1.0, ctx->lenK3)) return 1; }
+    }
+    return 0;
+}
+
+// ---- BSE kernels -----------------------------------------------------------------------------------------
+static int pi_kind(int ch, bool reference) { return ch == FDGA_PCH ? (reference ? FDGA_PI0PP : FDGA_PIPP) : (reference ? FDGA_PI0PH : FDGA_PIPH); }
+
+extern "C++" {
+template <int KIND>
+static int launch_right(fdga_ctx* ctx, int ch, const DevChain& F0, const DevChain& FL, int No, int Ninner) {
+    Scope sc(ctx, FDGA_T_RIGHT);
+    const C* p0 = ctx->PiT[pi_kind(ch, true)]; const C* p1 = ctx->PiT[pi_kind(ch, false)];
+    long long n = (long long)(2 * Ninner) * ctx->g.NP * (2 * No - 1) * ctx->g.NP;
+    if (ch == FDGA_PCH)      LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_P, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, ctx->Rt, ctx->g, No, Ninner);
+    else if (ch == FDGA_TCH) LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_T, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, ctx->Rt, ctx->g, No, Ninner);
+    else                     LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_A, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, ctx->Rt, ctx->g, No, Ninner);
+    CK(cudaGetLastError());
+    return 0;
+}
+}  // extern "C++"
+static int ensure_pi(fdga_ctx* ctx, int ch) {
+    if (refresh_pi(ctx, pi_kind(ch, true))) return 1;
+    return refresh_pi(ctx, pi_kind(ch, false));
+}
+static double chsign(int ch) { return ch == FDGA_TCH ? -1.0 : 1.0; }   // BSE_templates.jl:17,25,33
+
+int fdga_bse_K1(fdga_ctx* ctx, int ch, int mfrg) {
+    CK(cudaSetDevice(ctx->device));
+    if (ch < 0 || ch > 2) FAIL("fdga_bse_K1: bad channel");
+    NEED_SG(FDGA_SG_K1);
+    if (ensure_pi(ctx, ch)) return 1;
+    DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0), FL = chain_FL(ctx);
+    if (mfrg) { if (launch_right<RK_MF_K1>(ctx, ch, F0, FL, ctx->g.nK1, ctx->g.nPiF)) return 1; }
+    else      { if (launch_right<RK_FD>(ctx, ch, F0, FL, ctx->g.nK1, ctx->g.nPiF)) return 1; }
+    SymGroup& s = ctx->sg[FDGA_SG_K1];
+    long long c0, c1; sg_class_range(ctx, s, c0, c1);
+    double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
+    const DevChain& left = mfrg ? F0 : F;
+    {
+        Scope sc(ctx, FDGA_T_K1);
+        if (c1 > c0) {
+            if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_P>, (unsigned)(c1 - c0), 256, left, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+            else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_T>, (unsigned)(c1 - c0), 256, left, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+            else                     LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_A>, (unsigned)(c1 - c0), 256, left, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+        }
+        CK(cudaGetLastError());
+    }
+    if (sg_finish(ctx, s, ctx->Fbuff.K[ch][0])) return 1;
+    if (ch == FDGA_TCH) return tfix(ctx, ctx->Fbuff.K[FDGA_TCH][0], ctx->Fbuff.K[FDGA_ACH][0], ctx->Fbuff.len[0]);
+    return 0;
+}
+
+int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
+    CK(cudaSetDevice(ctx->device));
+    if (ch < 0 || ch > 2) FAIL("fdga_bse_L_K2: bad channel");
+    int which = ch == FDGA_PCH ? FDGA_SG_PP2 : FDGA_SG_PH2;
+    NEED_SG(which);
+    if (ensure_pi(ctx, ch)) return 1;
+    DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0), FL = chain_FL(ctx);
+    if (launch_right<RK_LK2>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nK2f)) return 1;
+    SymGroup& s = ctx->sg[which];
+    long long c0, c1; sg_class_range(ctx, s, c0, c1);
+    double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
+    {
+        Scope sc(ctx, FDGA_T_L_K2);
+        if (c1 > c0) {
+            if (ch == FDGA_PCH)      LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_P>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+            else if (ch == FDGA_TCH) LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_T>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+            else                     LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_A>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+        }
+        CK(cudaGetLastError());
+    }
+    if (sg_finish(ctx, s, ctx->FL.K[ch][1])) return 1;
+    ctx->FL.sw_dirty = true;
+    if (ch == FDGA_TCH) return tfix(ctx, ctx->FL.K[FDGA_TCH][1], ctx->FL.K[FDGA_ACH][1], ctx->FL.len[1]);
+    return 0;
+}
+
+int fdga_bse_K2(fdga_ctx* ctx, int ch, int mfrg) {
+    CK(cudaSetDevice(ctx->device));
+    if (ch < 0 || ch > 2) FAIL("fdga_bse_K2: bad channel");
+    int which = ch == FDGA_PCH ? FDGA_SG_PP2 : FDGA_SG_PH2;
+    NEED_SG(which);
+    if (ensure_pi(ctx, ch)) return 1;
+    DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0), FL = chain_FL(ctx);
+    if (mfrg) { if (launch_right<RK_MF_K2>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1; }
+    else      { if (launch_right<RK_FD>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1; }
+    SymGroup& s = ctx->sg[which];
+    long long c0, c1; sg_class_range(ctx, s, c0, c1);
+    double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
+    {
+        Scope sc(ctx, FDGA_T_K2);
+        unsigned nb = (unsigned)(c1 - c0);
+        if (c1 > c0) {
+            if (mfrg) {
+                if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_P, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+                else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_T, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+                else                     LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_A, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+            } else {
+                if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_P, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+                else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_T, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+                else                     LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_A, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+            }
+        }
+        CK(cudaGetLastError());
+    }
+    C* out = ctx->Fbuff.K[ch][1];
+    if (sg_finish(ctx, s, out)) return 1;
+    Scope sc(ctx, FDGA_T_MISC);
+    size_t n = ctx->Fbuff.len[1];
+    if (ch == FDGA_TCH) {      // BSEa_K2.jl:130-132 then BSE_templates.jl:107-108
+        if (add_axpby(ctx, out, ctx->FL.K[FDGA_TCH][1], 2.0, ctx->FL.K[FDGA_ACH][1], -1.0, n)) return 1;
+        return tfix(ctx, out, ctx->Fbuff.K[FDGA_ACH][1], n);
+    }
+    return add_axpby(ctx, out, ctx->FL.K[ch][1], 1.0, nullptr, 0.0, n);
+}
+
+int fdga_bse_L_K3(fdga_ctx* ctx, int ch) {
+    CK(cudaSetDevice(ctx->device));
+    if (ch < 0 || ch > 2) FAIL("fdga_bse_L_K3: bad channel");
+    int which = ch == FDGA_PCH ? FDGA_SG_PPL3 : FDGA_SG_PHL3;
+    NEED_SG(which);
+    if (ensure_pi(ctx, ch)) return 1;
+    SymGroup& s = ctx->sg[which];
+    long long c0, c1; sg_class_range(ctx, s, c0, c1);
+    // (cache_G, cache_F0, sign): BSE_templates.jl:122,130,138
+    int cg = ch == FDGA_ACH ? FDGA_C_GA : (ch == FDGA_PCH ? FDGA_C_GPP : FDGA_C_GT);
+    int cf0 = ch == FDGA_ACH ? FDGA_C_F0A : (ch == FDGA_PCH ? FDGA_C_F0P : FDGA_C_F0T);
+    double sign = ch == FDGA_ACH ? 1.0 : -1.0;
+    {
+        Scope sc(ctx, FDGA_T_L_K3);
+        if (c1 > c0) LAUNCH(FDGA_T_L_K3, bse_lk3_kernel, nblk(c1 - c0, 64), 64, ctx->cache[cg], ctx->cache[cf0], ctx->Pisw[pi_kind(ch, true)], s.d_repvals, sym_dev(s), c0, c1, ctx->g, ctx->g.T * sign);
+        CK(cudaGetLastError());
+    }
+    if (sg_finish(ctx, s, ctx->FL.K[ch][2])) return 1;
+    ctx->FL.sw_dirty = true;
+    if (ch == FDGA_TCH) return tfix(ctx, ctx->FL.K[FDGA_TCH][2], ctx->FL.K[FDGA_ACH][2], ctx->FL.len[2]);
+    return 0;
+}
+
+int fdga_bse_K3(fdga_ctx* ctx, int ch, int mfrg) {
+    CK(cudaSetDevice(ctx->device));
+    if (ch < 0 || ch > 2) FAIL("fdga_bse_K3: bad channel");
+    int which = ch == FDGA_PCH ? FDGA_SG_PP3 : FDGA_SG_PH3;
+    NEED_SG(which);
+    if (ensure_pi(ctx, ch)) return 1;
+    SymGroup& s = ctx->sg[which];
+    long long c0, c1; sg_class_range(ctx, s, c0, c1);
+    // (cache_G, cache_F, cache_F0, sign1, sign2): BSE_templates.jl:156,164,172
+    int cg = ch == FDGA_ACH ? FDGA_C_GA : (ch == FDGA_PCH ? FDGA_C_GPX : FDGA_C_GT);
+    int cf = ch == FDGA_ACH ? FDGA_C_FA : (ch == FDGA_PCH ? FDGA_C_FP : FDGA_C_FT);
+    int cf0 = ch == FDGA_ACH ? FDGA_C_F0A : (ch == FDGA_PCH ? FDGA_C_F0P : FDGA_C_F0T);
+    double s1 = ch == FDGA_ACH ? 1.0 : -1.0, s2 = ch == FDGA_TCH ? -1.0 : 1.0;
+    const C* Pi0sw = ctx->Pisw[pi_kind(ch, true)]; const C* Pisw = ctx->Pisw[pi_kind(ch, false)];
+    const C *FLo = ctx->FL.K[ch][2], *FLt = ctx->FL.K[FDGA_TCH][2], *FLa = ctx->FL.K[FDGA_ACH][2];
+    {
+        Scope sc(ctx, FDGA_T_K3);
+        unsigned nb = nblk(c1 - c0, 64);
+#define K3L(CHT, MFT) LAUNCH(FDGA_T_K3, (bse_k3_kernel<CHT, MFT>), nb, 64, FLo, FLt, FLa, ctx->cache[cg], ctx->cache[cf], ctx->cache[cf0], Pi0sw, Pisw, s.d_repvals, sym_dev(s), c0, c1, ctx->g, s1, s2)
+        if (c1 > c0) {
+            if (mfrg) { if (ch == FDGA_PCH) K3L(CH_P, true); else if (ch == FDGA_TCH) K3L(CH_T, true); else K3L(CH_A, true); }
+            else      { if (ch == FDGA_PCH) K3L(CH_P, false); else if (ch == FDGA_TCH) K3L(CH_T, false); else K3L(CH_A, false); }
+        }
+#undef K3L
+        CK(cudaGetLastError());
+    }
+    if (sg_finish(ctx, s, ctx->Fbuff.K[ch][2])) return 1;
+    if (ch == FDGA_TCH) return tfix(ctx, ctx->Fbuff.K[FDGA_TCH][2], ctx->Fbuff.K[FDGA_ACH][2], ctx->Fbuff.len[2]);
+    return 0;
+}
+
+int fdga_set_F_from_Fbuff(fdga_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    for (int ch = 0; ch < 3; ch++) for (int cls = 0; cls < 3; cls++)
+        CK(cudaMemcpyAsync(ctx->lev[0].K[ch][cls], ctx->Fbuff.K[ch][cls], ctx->Fbuff.len[cls] * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->lev[0].sw_dirty = true;
+    return 0;
+}
+
+// ---- SDE -------------------------------------------------------------------------------------------------
+// SDE_compute!(Sigma_out, G, Pipp, Piph, Lpp, Lph, F = chain[level..], ...): src/nonlocal_2/SDE.jl:154-324
+static int sde_compute(fdga_ctx* ctx, C* Sout, int gwhich, bool reference, int level, bool include_U2, bool include_Hartree) {
+    NEED_SG(FDGA_SG_SIGMA); NEED_SG(FDGA_SG_PP2); NEED_SG(FDGA_SG_PH2);
+    const Grid& g = ctx->g;
+    if (refresh_pi(ctx, reference ? FDGA_PI0PP : FDGA_PIPP) || refresh_pi(ctx, reference ? FDGA_PI0PH : FDGA_PIPH)) return 1;
+    DevChain V = chain_F(ctx, 0);
+    C U = bareU(ctx);
+    double scale = g.T / (double)g.NP;
+    for (int pp = 1; pp >= 0; pp--) {
+        SymGroup& s = ctx->sg[pp ? FDGA_SG_PP2 : FDGA_SG_PH2];
+        long long c0, c1; sg_class_range(ctx, s, c0, c1);
+        const C* PiT = ctx->PiT[pp ? (reference ? FDGA_PI0PP : FDGA_PIPP) : (reference ? FDGA_PI0PH : FDGA_PIPH)];
+        {
+            Scope sc(ctx, FDGA_T_SDE_L);
+            if (c1 > c0) {
+                if (pp) LAUNCH(FDGA_T_SDE_L, sde_L_kernel<true>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma);
+                else    LAUNCH(FDGA_T_SDE_L, sde_L_kernel<false>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma);
+            }
+            CK(cudaGetLastError());
+        }
+        if (sg_finish(ctx, s, ctx->L[pp ? 0 : 1])) return 1;
+    }
+    {
+        Scope sc(ctx, FDGA_T_SDE_RS);
+        if (dft2_G(ctx, ctx->G[gwhich], ctx->GR, ctx->SigTmp, -1, 1.0 / ((double)g.LG * g.LG), FDGA_T_SDE_RS)) return 1;
+        long long pre = (long long)(2 * g.nK2b - 1) * (2 * g.nK2f);
+        double nrm = 1.0 / ((double)g.L * g.L * g.L * g.L);
+        size_t nK2 = ctx->lev[0].len[1];
+        // L arrays are transformed in place (clobbered, as in the reference: SURVEY E4)
+        if (dft4(ctx, ctx->L[0], ctx->scratchA, pre, -1, nrm, FDGA_T_SDE_RS)) return 1;
+        if (dft4(ctx, ctx->L[1], ctx->scratchA, pre, -1, nrm, FDGA_T_SDE_RS)) return 1;
+        (void)nK2;
+        LAUNCH(FDGA_T_SDE_RS, sde_rs_kernel, nblk(ctx->lenG, 64), 64, ctx->GR, ctx->L[0], ctx->L[1], ctx->SigR, g, g.nG, g.LG);
+        CK(cudaGetLastError());
+        if (dft2_G(ctx, ctx->SigR, Sout, ctx->SigTmp, +1, 1.0, FDGA_T_SDE_RS)) return 1;
+        SymGroup& ss = ctx->sg[FDGA_SG_SIGMA];
+        LAUNCH(FDGA_T_SDE_RS, symmetrize_kernel, nblk(ss.nmem, 256), 256, Sout, sym_dev(ss));
+        if (ctx->lev[level].d.type == FDGA_LV_CORE)
+            LAUNCH(FDGA_T_SDE_RS, scale_copy_kernel, nblk(ctx->lenG, 256), 256, Sout, Sout, 1.0 / 3.0, (long long)ctx->lenG);
+        CK(cudaGetLastError());
+    }
+    if (include_U2) {
+        Scope sc(ctx, FDGA_T_SDE_U2);
+        double inv = 1.0 / ((double)g.LG * g.LG);
+        // GR already holds fft(G)/LG^2 ; GRm = bfft(G)/LG^2
+        if (dft2_G(ctx, ctx->G[gwhich], ctx->GRm, ctx->SigTmp, +1, inv, FDGA_T_SDE_U2)) return 1;
+        C fac = (U * U) * (g.T * g.T);
+        LAUNCH(FDGA_T_SDE_U2, sde_u2_kernel, nblk(ctx->lenG, 64), 64, ctx->GR, ctx->GRm, ctx->SigR, g.nG, g.LG, fac);
+        if (dft2_G(ctx, ctx->SigR, ctx->GRm, ctx->SigTmp, +1, 1.0, FDGA_T_SDE_U2)) return 1;
+        SymGroup& ss = ctx->sg[FDGA_SG_SIGMA];
+        LAUNCH(FDGA_T_SDE_U2, symmetrize_kernel, nblk(ss.nmem, 256), 256, ctx->GRm, sym_dev(ss));
+        LAUNCH(FDGA_T_SDE_U2, add_axpby_kernel, nblk(ctx->lenG, 256), 256, Sout, ctx->GRm, 1.0, (const C*)nullptr, 0.0, (long long)ctx->lenG);
+        CK(cudaGetLastError());
+    }
+    if (include_Hartree) {
+        Scope sc(ctx, FDGA_T_MISC);
+        if (occupation_dev(ctx, gwhich)) return 1;
+        LAUNCH(FDGA_T_MISC, hartree_kernel, nblk(ctx->lenG, 256), 256, Sout, ctx->d_occ, U, 1.0, (long long)ctx->lenG);
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+// SDE!(Sigma, G, ..., F = chain[from..]): recursion over the F0 chain, src/SDE.jl:35-48.  acc += sgn * result
+static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool reference, int from, bool include_U2, bool include_Hartree) {
+    for (int l = from; l < ctx->nlev; l++) {
+        bool top = (l == from);
+        if (sde_compute(ctx, ctx->SigAcc, gwhich, reference, l, top && include_U2, top && include_Hartree)) return 1;
+        LAUNCH(FDGA_T_MISC, add_axpby_kernel, nblk(ctx->lenG, 256), 256, acc, ctx->SigAcc, sgn, (const C*)nullptr, 0.0, (long long)ctx->lenG);
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+int fdga_sde(fdga_ctx* ctx, int strategy, int include_U2, int include_Hartree) {
+    CK(cudaSetDevice(ctx->device));
+    C* S = ctx->G[FDGA_SIGMA];
+    CK(cudaMemsetAsync(S, 0, ctx->lenG * sizeof(C), ctx->stream));
+    if (sde_chain(ctx, S, 1.0, FDGA_G, false, 0, include_U2, include_Hartree)) return 1;
+    if (strategy == FDGA_FDPA) {      // src/SDE.jl:13-24
+        if (sde_chain(ctx, S, -1.0, FDGA_G0, true, 1, include_U2, include_Hartree)) return 1;
+        LAUNCH(FDGA_T_MISC, add_axpby_kernel, nblk(ctx->lenG, 256), 256, S, ctx->G[FDGA_SIGMA0], 1.0, (const C*)nullptr, 0.0, (long long)ctx->lenG);
+        if (include_Hartree) {
+            if (occupation_dev(ctx, FDGA_G0)) return 1;
+            LAUNCH(FDGA_T_MISC, hartree_kernel, nblk(ctx->lenG, 256), 256, S, ctx->d_occ, bareU(ctx), -1.0, (long long)ctx->lenG);
+        }
+        CK(cudaGetLastError());
+    } else if (strategy != FDGA_SCPA) FAIL("fdga_sde: unknown strategy");
+    return 0;
+}
+
+// ---- drivers ---------------------------------------------------------------------------------------------
+int fdga_iterate_solver(fdga_ctx* ctx, int strategy, int update_sigma) {
+    if (strategy != FDGA_SCPA && strategy != FDGA_FDPA) FAIL("fdga_iterate_solver: strategy must be scPA or fdPA");
+    if (update_sigma) { if (fdga_dyson(ctx) || fdga_bubbles_real_space(ctx, 0)) return 1; }
+    if (fdga_build_K3_cache(ctx, 0, 0)) return 1;
+    const int order[3] = {FDGA_PCH, FDGA_ACH, FDGA_TCH};      // p, a, t (BSE_templates.jl:35-38 needs a before t)
+    if (strategy == FDGA_FDPA) {
+        for (int i = 0; i < 3; i++) if (fdga_bse_L_K2(ctx, order[i])) return 1;
+        for (int i = 0; i < 3; i++) if (fdga_bse_L_K3(ctx, order[i])) return 1;
+    }
+    for (int i = 0; i < 3; i++) if (fdga_bse_K1(ctx, order[i], 0)) return 1;
+    for (int i = 0; i < 3; i++) if (fdga_bse_K2(ctx, order[i], 0)) return 1;
+    for (int i = 0; i < 3; i++) if (fdga_bse_K3(ctx, order[i], 0)) return 1;
+    if (fdga_set_F_from_Fbuff(ctx)) return 1;
+    if (update_sigma) { if (fdga_sde(ctx, strategy, 1, 1)) return 1; }
+    return 0;
+}
+
+int fdga_mfrg_matvec(fdga_ctx* ctx, const fdga_c64* host_x, fdga_c64* host_y, int first) {
+    CK(cudaSetDevice(ctx->device));
+    const double factor = 1e-2;                                  // src/mfRG.jl:37
+    CK(cudaMemcpyAsync(ctx->flat2, host_x, ctx->lenFlat * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    if (unflatten_dev(ctx, ctx->lev[0], ctx->flat2, factor)) return 1;
+    if (fdga_build_K3_cache(ctx, 1, first)) return 1;
+    const int order[3] = {FDGA_PCH, FDGA_ACH, FDGA_TCH};
+    for (int i = 0; i < 3; i++) if (fdga_bse_L_K2(ctx, order[i])) return 1;
+    for (int i = 0; i < 3; i++) if (fdga_bse_K1(ctx, order[i], 1)) return 1;
+    for (int i = 0; i < 3; i++) if (fdga_bse_K2(ctx, order[i], 1)) return 1;
+    for (int i = 0; i < 3; i++) if (fdga_bse_L_K3(ctx, order[i])) return 1;
+    for (int i = 0; i < 3; i++) if (fdga_bse_K3(ctx, order[i], 1)) return 1;
+    if (fdga_set_F_from_Fbuff(ctx)) return 1;
+    if (flatten_dev(ctx, ctx->lev[0], ctx->flat)) return 1;
+    LAUNCH(FDGA_T_MISC, mfrg_residual_kernel, nblk(ctx->lenFlat, 256), 256, ctx->flat, ctx->flat2, ctx->flat, factor, (long long)ctx->lenFlat);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host_y, ctx->flat, ctx->lenFlat * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- introspection -----------------------------------------------------------------------------------------
+int fdga_profile_enable(fdga_ctx* ctx, int on) { ctx->profile = on != 0; return 0; }
+static int profile_collect(fdga_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& ev : ctx->events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) ctx->t_ms[ev.cat] += ms;
+        cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+    }
+    ctx->events.clear();
+    return 0;
+}
+int fdga_profile_reset(fdga_ctx* ctx) {
+    if (profile_collect(ctx)) return 1;
+    memset(ctx->t_ms, 0, sizeof(ctx->t_ms)); memset(ctx->n_launch, 0, sizeof(ctx->n_launch)); ctx->total_launches = 0;
+    return 0;
+}
+int fdga_kernel_time_ms(fdga_ctx* ctx, int id, double* ms, int64_t* launches) {
+    if (id < 0 || id >= FDGA_T_COUNT) FAIL("fdga_kernel_time_ms: bad id");
+    if (profile_collect(ctx)) return 1;
+    *ms = ctx->t_ms[id]; *launches = ctx->n_launch[id];
+    return 0;
+}
+int64_t fdga_total_launches(fdga_ctx* ctx) { return ctx->total_launches; }
+
+}  // extern "C"

@@ -1,0 +1,393 @@
+"""Host-side mirror of the reference's NL2_ParquetSolver API, driving libfdga through the C-ABI.
+
+Same names, argument meaning and call order as the reference (Julia ``!`` dropped):
+  NL2_ParquetSolver                     src/nonlocal_2/ParquetSolver.jl:1-154
+  parquet_solver_hubbard_parquet_approximation_NL2   :167-196
+  init_sym_grp!                         :200-291
+  Dyson!, compute_occupation            src/dyson.jl
+  bubbles!                              src/nonlocal_2/ParquetSolver.jl:309-312 -> nonlocal_2/bubble.jl:42-122
+  build_K3_cache!, build_K3_cache_mfRG! src/nonlocal_2/build_K3_cache.jl
+  BSE_L_K2!, BSE_L_K3!, BSE_K1!, BSE_K2!, BSE_K3!    src/BSE_templates.jl:12-180
+  SDE!                                  src/SDE.jl:3-48
+  iterate_solver!, fixed_point!         src/solve.jl:4-157
+  mfRGLinearMap                         src/mfRG.jl:20-89
+All compute happens on the GPU inside libfdga; this module only moves arrays and sequences calls.
+The solver keeps host copies of its arrays (like the Julia struct); ``push``/``pull`` synchronise them.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .types import (CH_NAME, CHANNELS, NL2_Vertex, RefVertex, Vertex, aCh, nB, nF, pCh, tCh, vertex_chain, zeros)
+
+STRATEGY = {"scPA": L.SCPA, "fdPA": L.FDPA}
+_G_NAMES = {"G": L.G, "G0": L.G0, "Gbare": L.GBARE, "Σ": L.SIGMA, "Σ0": L.SIGMA0}
+_PI_NAMES = {"Π0pp": L.PI0PP, "Π0ph": L.PI0PH, "Πpp": L.PIPP, "Πph": L.PIPH}
+_CACHE_NAMES = ["cache_Γpx", "cache_F0p", "cache_F0a", "cache_F0t", "cache_Γpp", "cache_Γa", "cache_Γt",
+                "cache_Fp", "cache_Fa", "cache_Ft"]
+
+
+class NL2_ParquetSolver:
+    """State of one nonlocal (NL2) parquet / fdDΓA problem, resident on one GPU.
+
+    Gbare, G0, Σ0: complex128 arrays of shape (2 nG, LG*LG) holding i*G (src/models/hubbard.jl:23-24).
+    F0: reference vertex: RefVertex | Vertex | NL2_Vertex (arbitrarily nested).
+    L: linear size of the vertex momentum mesh mK_Γ.
+    """
+
+    def __init__(self, nK1, nK2, nK3, L_, Gbare, G0, Σ0, F0, *, T, mode="threads", mΠν_factor=1, device=0,
+                 compute_bubbles=True):
+        lib = L.load()
+        self._lib = lib
+        self.mode = mode          # accepted and ignored: parallelism is the GPU's
+        self.T = float(T)
+        self.L = int(L_)
+        self.NP = self.L * self.L
+        self.nK1, self.nK2, self.nK3 = int(nK1), tuple(nK2), tuple(nK3)
+        Gbare = np.asfortranarray(Gbare, dtype=np.complex128)
+        assert Gbare.ndim == 2 and Gbare.shape == G0.shape == Σ0.shape
+        self.nG = Gbare.shape[0] // 2
+        self.LG = int(round(np.sqrt(Gbare.shape[1])))
+        assert self.LG * self.LG == Gbare.shape[1]
+        self.nΠB, self.nΠF = self.nK1, self.nK1 * int(mΠν_factor)     # ParquetSolver.jl:95-97
+
+        self.Gbare = Gbare
+        self.G0 = np.asfortranarray(G0, dtype=np.complex128).copy(order="F")
+        self.Σ0 = np.asfortranarray(Σ0, dtype=np.complex128).copy(order="F")
+        self.G = self.G0.copy(order="F")
+        self.Σ = self.Σ0.copy(order="F")
+        self.F0 = F0
+        self.F = NL2_Vertex(F0, self.T, nK1, nK2, nK3, self.L)
+        null = RefVertex(self.T, 0.0)
+        self.Fbuff = NL2_Vertex(null, self.T, nK1, nK2, nK3, self.L)
+        self.FL = NL2_Vertex(null.copy(), self.T, nK1, nK2, nK3, self.L)
+        shpΠ = (nB(self.nΠB), nF(self.nΠF), self.NP, self.NP)
+        self.Π0pp, self.Π0ph, self.Πpp, self.Πph = (None,) * 4     # pulled on demand (large)
+        self._shpΠ = shpΠ
+        self.Lpp = zeros(self.F.γp.K2.shape)
+        self.Lph = zeros(self.F.γp.K2.shape)
+        for n in _CACHE_NAMES:
+            setattr(self, n, zeros(self.F.γp.K3.shape))
+
+        # ---- device context
+        self._chain = vertex_chain(self.F)
+        d = L.Dims()
+        d.T, d.nq, d.LG, d.nG, d.nPiB, d.nPiF = self.T, self.L, self.LG, self.nG, self.nΠB, self.nΠF
+        d.nlev = len(self._chain)
+        if d.nlev > L.FDGA_MAX_LEVELS:
+            raise L.FdgaError("vertex chain too deep")
+        for i, V in enumerate(self._chain):
+            lv = d.lev[i]
+            if isinstance(V, RefVertex):
+                lv.type = L.LV_CORE
+                lv.nK3[0], lv.nK3[1] = V.numK3
+                lv.U_re, lv.U_im = V.U.real, V.U.imag
+            else:
+                lv.type = L.LV_NL2 if isinstance(V, NL2_Vertex) else L.LV_LOCAL
+                if isinstance(V, NL2_Vertex) and V.L != self.L:
+                    raise L.FdgaError("all NL2 levels must share the momentum mesh")
+                lv.nK1 = V.numK1
+                lv.nK2[0], lv.nK2[1] = V.numK2
+                lv.nK3[0], lv.nK3[1] = V.numK3
+        self._dims = d
+        ctx = C.c_void_p()
+        rc = lib.fdga_create(C.byref(d), int(device), C.byref(ctx))
+        if rc != 0:
+            raise L.FdgaError("fdga_create failed: " + lib.fdga_last_error(None).decode())
+        self._ctx = ctx
+        self._sg = {}
+        self.reset_sym_grp()
+
+        self.push("Gbare", "G0", "Σ0", "G", "Σ", "F0")
+        # reference bubbles, Dyson, target bubbles (ParquetSolver.jl:100-111)
+        if compute_bubbles:
+            self._call("fdga_bubbles_real_space", 1)
+            self._call("fdga_dyson")
+            self._call("fdga_bubbles_real_space", 0)
+            self.pull("G")
+
+    # ------------------------------------------------------------------ plumbing
+    def _call(self, name, *args):
+        rc = getattr(self._lib, name)(self._ctx, *args)
+        L.check(self._ctx, rc, name)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.fdga_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name, value):
+        """options of include/fdga.h; 'sde_own_gamma' toggles the SURVEY-E2 reading of the NL2 SDE L kernels"""
+        self._call("fdga_set_option", {"sde_own_gamma": 0}[name], int(value))
+
+    def sync(self):
+        self._call("fdga_sync")
+
+    def _vertex_io(self, which, V, put):
+        fn = "fdga_set_vertex" if put else "fdga_get_vertex"
+        for ch in CHANNELS:
+            g = V.channel(ch)
+            for cls, a in enumerate(g.arrays()):
+                self._call(fn, which, ch, cls, L.ptr(a), a.size)
+
+    def push(self, *names):
+        """host -> device for the named groups: F, F0 (whole reference chain), FL, Fbuff, G, G0, Gbare, Σ, Σ0, Π*, cache"""
+        for n in names:
+            if n == "F":
+                self._vertex_io(0, self.F, True)
+            elif n == "F0":
+                for i, V in enumerate(self._chain[1:], start=1):
+                    if isinstance(V, RefVertex):
+                        for j, a in enumerate(V.arrays()):
+                            self._call("fdga_set_core", i, j, L.ptr(a), a.size)
+                    else:
+                        self._vertex_io(i, V, True)
+            elif n == "FL":
+                self._vertex_io(L.V_FL, self.FL, True)
+            elif n == "Fbuff":
+                self._vertex_io(L.V_FBUFF, self.Fbuff, True)
+            elif n in _G_NAMES:
+                a = getattr(self, n)
+                self._call("fdga_set_green", _G_NAMES[n], L.ptr(a), a.size)
+            elif n in _PI_NAMES:
+                a = getattr(self, n)
+                self._call("fdga_set_bubble", _PI_NAMES[n], L.ptr(a), a.size)
+            elif n == "cache":
+                for i, cn in enumerate(_CACHE_NAMES):
+                    a = getattr(self, cn)
+                    self._call("fdga_set_cache", i, L.ptr(a), a.size)
+            else:
+                raise KeyError(n)
+
+    def pull(self, *names):
+        """device -> host for the named groups"""
+        for n in names:
+            if n == "F":
+                self._vertex_io(0, self.F, False)
+            elif n == "FL":
+                self._vertex_io(L.V_FL, self.FL, False)
+            elif n == "Fbuff":
+                self._vertex_io(L.V_FBUFF, self.Fbuff, False)
+            elif n in _G_NAMES:
+                a = getattr(self, n)
+                self._call("fdga_get_green", _G_NAMES[n], L.ptr(a), a.size)
+            elif n in _PI_NAMES:
+                if getattr(self, n) is None:
+                    setattr(self, n, zeros(self._shpΠ))
+                a = getattr(self, n)
+                self._call("fdga_get_bubble", _PI_NAMES[n], L.ptr(a), a.size)
+            elif n == "Π":
+                self.pull(*_PI_NAMES)
+            elif n == "cache":
+                for i, cn in enumerate(_CACHE_NAMES):
+                    a = getattr(self, cn)
+                    self._call("fdga_get_cache", i, L.ptr(a), a.size)
+            elif n == "L":
+                self._call("fdga_get_L", 1, L.ptr(self.Lpp), self.Lpp.size)
+                self._call("fdga_get_L", 0, L.ptr(self.Lph), self.Lph.size)
+            else:
+                raise KeyError(n)
+
+    # ------------------------------------------------------------------ symmetry groups
+    def _sg_len(self, which):
+        if which == L.SG_SIGMA:
+            return self.Σ.size
+        if which == L.SG_K1:
+            return self.F.γp.K1.size
+        if which in (L.SG_PP2, L.SG_PH2):
+            return self.F.γp.K2.size
+        return self.F.γp.K3.size
+
+    def set_symmetry_classes(self, which, offsets, index, ops):
+        """Register SG.classes (flattened) for one symmetry group; what a Julia shim passes in drop-in use."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        index = np.ascontiguousarray(index, dtype=np.int64)
+        ops = np.ascontiguousarray(ops, dtype=np.uint8)
+        self._call("fdga_set_symmetry_classes", which, len(offsets) - 1, L.ptr(offsets), L.ptr(index), L.ptr(ops))
+        self._sg[which] = (offsets, index, ops)
+
+    def reset_sym_grp(self):
+        """trivial groups (every element its own class), ParquetSolver.jl:124-132, 293-303"""
+        for which in range(8):
+            self.set_symmetry_classes(which, *L.trivial_symmetry_group(self._sg_len(which)))
+
+    def init_sym_grp(self):
+        """init_sym_grp!(S): src/nonlocal_2/ParquetSolver.jl:200-291"""
+        n = {L.SG_SIGMA: (self.nG, 0), L.SG_K1: (self.nK1, 0),
+             L.SG_PP2: self.nK2, L.SG_PH2: self.nK2,
+             L.SG_PP3: self.nK3, L.SG_PH3: self.nK3, L.SG_PPL3: self.nK3, L.SG_PHL3: self.nK3}
+        for which, (n0, n1) in n.items():
+            nq = self.LG if which == L.SG_SIGMA else self.L
+            self.set_symmetry_classes(which, *L.build_symmetry_group(which, n0, n1, nq, self._sg_len(which)))
+
+    def num_classes(self, which):
+        return len(self._sg[which][0]) - 1
+
+    # ------------------------------------------------------------------ flatten / unflatten (device resident F)
+    def length_F(self):
+        return int(self._lib.fdga_length_F(self._ctx))
+
+    def flatten_F(self, out=None):
+        out = np.empty(self.length_F(), dtype=np.complex128) if out is None else out
+        self._call("fdga_flatten_F", L.ptr(out))
+        return out
+
+    def unflatten_F(self, x, scale=1.0):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        assert x.size == self.length_F()
+        self._call("fdga_unflatten_F", L.ptr(x), float(scale))
+        self.sync()
+
+    # ------------------------------------------------------------------ profiling
+    def profile(self, on=True):
+        self._call("fdga_profile_enable", int(on))
+
+    def profile_reset(self):
+        self._call("fdga_profile_reset")
+
+    def kernel_times(self):
+        out = {}
+        for i, n in enumerate(L.T_NAMES):
+            ms, cnt = C.c_double(0), C.c_int64(0)
+            self._call("fdga_kernel_time_ms", i, C.byref(ms), C.byref(cnt))
+            out[n] = (ms.value, cnt.value)
+        return out
+
+    def total_launches(self):
+        return int(self._lib.fdga_total_launches(self._ctx))
+
+    def stream(self):
+        return self._lib.fdga_stream(self._ctx)
+
+
+# ---------------------------------------------------------------------- reference-named operations
+def init_sym_grp(S):
+    S.init_sym_grp()
+
+
+def Dyson(S):
+    S._call("fdga_dyson")
+
+
+def compute_occupation(S, which="G"):
+    occ = C.c_double(0)
+    S._call("fdga_occupation", _G_NAMES[which], C.byref(occ))
+    return occ.value
+
+
+def bubbles(S):
+    """bubbles!(S) = bubbles_real_space!(S.Πpp, S.Πph, S.G)"""
+    S._call("fdga_bubbles_real_space", 0)
+
+
+def bubbles_real_space(S, reference=False):
+    S._call("fdga_bubbles_real_space", int(reference))
+
+
+def bubbles_momentum_space(S, reference=False):
+    S._call("fdga_bubbles_momentum_space", int(reference))
+
+
+def build_K3_cache(S):
+    S._call("fdga_build_K3_cache", 0, 0)
+
+
+def build_K3_cache_mfRG(S, is_first_iteration):
+    S._call("fdga_build_K3_cache", 1, int(is_first_iteration))
+
+
+def BSE_L_K2(S, Ch, is_mfRG=False):
+    S._call("fdga_bse_L_K2", Ch)
+
+
+def BSE_L_K3(S, Ch, is_mfRG=False):
+    S._call("fdga_bse_L_K3", Ch)
+
+
+def BSE_K1(S, Ch, is_mfRG=False):
+    S._call("fdga_bse_K1", Ch, int(is_mfRG))
+
+
+def BSE_K2(S, Ch, is_mfRG=False):
+    S._call("fdga_bse_K2", Ch, int(is_mfRG))
+
+
+def BSE_K3(S, Ch, is_mfRG=False):
+    S._call("fdga_bse_K3", Ch, int(is_mfRG))
+
+
+def SDE(S, strategy="scPA", include_U2=True, include_Hartree=True):
+    S._call("fdga_sde", STRATEGY[strategy], int(include_U2), int(include_Hartree))
+
+
+def iterate_solver(S, strategy="fdPA", update_Σ=True):
+    """iterate_solver!(S; strategy, update_Σ): src/solve.jl:4-116 (fused inside the library)"""
+    S._call("fdga_iterate_solver", STRATEGY[strategy], int(update_Σ))
+
+
+def iterate_solver_stepwise(S, strategy="fdPA", update_Σ=True):
+    """Same sequence as iterate_solver, issued call by call (used by the tests to check the fused driver)."""
+    if update_Σ:
+        Dyson(S)
+        bubbles(S)
+    build_K3_cache(S)
+    order = (pCh, aCh, tCh)
+    if strategy == "fdPA":
+        for ch in order:
+            BSE_L_K2(S, ch)
+        for ch in order:
+            BSE_L_K3(S, ch)
+    for ch in order:
+        BSE_K1(S, ch)
+    for ch in order:
+        BSE_K2(S, ch)
+    for ch in order:
+        BSE_K3(S, ch)
+    S._call("fdga_set_F_from_Fbuff")
+    if update_Σ:
+        SDE(S, strategy)
+
+
+def fixed_point(R, x, S, strategy="fdPA", update_Σ=True):
+    """fixed_point!(R, x, S): R = iterate(x) - x on the flattened [F; Σ] (src/solve.jl:119-157, src/ParquetSolver.jl:277-306)"""
+    nF_ = S.length_F()
+    S.unflatten_F(x[:nF_])
+    if update_Σ:
+        S.Σ[...] = np.asarray(x[nF_:]).reshape(S.Σ.shape, order="F")
+        S.push("Σ")
+    iterate_solver(S, strategy, update_Σ)
+    S.flatten_F(R[:nF_])
+    if update_Σ:
+        S.pull("Σ")
+        R[nF_:] = S.Σ.ravel(order="F")
+    R -= x
+    return R
+
+
+class mfRGLinearMap:
+    """mfRGLinearMap(S, :fdPA): y = x - BSE_lin(1e-2 x)/1e-2 (src/mfRG.jl:20-89)"""
+
+    def __init__(self, S, strategy="fdPA"):
+        if strategy != "fdPA":
+            raise ValueError("only strategy fdPA is implemented")
+        self.S = S
+        self.is_first_iteration = True
+        n = S.length_F()
+        self.shape = (n, n)
+
+    def __matmul__(self, x):
+        return self.matvec(x)
+
+    def matvec(self, x):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        y = np.empty_like(x)
+        self.S._call("fdga_mfrg_matvec", L.ptr(x), L.ptr(y), int(self.is_first_iteration))
+        self.is_first_iteration = False
+        return y

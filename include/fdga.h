@@ -1,0 +1,163 @@
+/* ======================================================================================
+ * fdga.h -- C-ABI of libfdga.so, the B200 (sm_100a) implementation of the Bethe-Salpeter /
+ * K3-cache / bubble / Schwinger-Dyson hot path of jaemolihm/fdDGAsolver.jl.
+ *
+ * The reference has no FFI: its seam is Julia multiple dispatch on the concrete array
+ * aliases of src/types.jl:105-129.  Every entry point below replaces one reference method
+ * (cited as file:line relative to the reference tree) and is what a Julia `ccall` shim
+ *  binds.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions
+ *  - All arrays are column-major (first index fastest) interleaved complex double, i.e. the
+ *    memory of a Julia Array{ComplexF64,N} / a numpy complex128 array in Fortran order.
+ *  - The caller owns host memory; the library owns device memory.  set_* copies H2D, get_*
+ *    copies D2H; kernels work on the resident device state.
+ *  - Every function returns 0 on success, non-zero on error; fdga_last_error() gives the text.
+ *    Nothing throws across the boundary.  A context is not thread-safe; distinct contexts are
+ *    independent.  There is NO CPU fallback: fdga_create fails if no CUDA device is usable.
+ *  - Matsubara meshes (MatsubaraFunctions.jl): fermionic mesh N -> indices -N..N-1 (2N points),
+ *    bosonic mesh N -> indices -(N-1)..N-1 (2N-1 points).  Momentum mesh nq x nq, linear index
+ *    ix + nq*iy (0-based).
+ *  - Channels: 0 = pCh, 1 = tCh, 2 = aCh (flatten order of src/vertex.jl:153-167).
+ * ====================================================================================== */
+#ifndef FDGA_H
+#define FDGA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fdga_ctx fdga_ctx;
+typedef struct { double re, im; } fdga_c64;
+
+enum { FDGA_PCH = 0, FDGA_TCH = 1, FDGA_ACH = 2 };
+enum { FDGA_K1 = 0, FDGA_K2 = 1, FDGA_K3 = 2 };
+/* level types of the nested vertex chain S.F -> S.F.F0 -> ... (src/vertex.jl, src/refvertex.jl) */
+enum { FDGA_LV_NL2 = 0,    /* NL2_Vertex  (src/nonlocal_2/vertex.jl:1-32)  K1[W,P] K2[W,v,P,k] K3[W,v,v',P] */
+       FDGA_LV_LOCAL = 1,  /* Vertex      (src/vertex.jl:7-36)             K1[W]   K2[W,v]     K3[W,v,v']   */
+       FDGA_LV_CORE = 2 }; /* RefVertex   (src/refvertex.jl:1-35)          U + Fp_p, Fp_x, Ft_p, Ft_x       */
+
+#define FDGA_MAX_LEVELS 6
+
+typedef struct {
+    int32_t type;
+    int32_t nK1;         /* N of the bosonic K1 mesh                                   */
+    int32_t nK2[2];      /* N of the (bosonic, fermionic) K2 meshes                    */
+    int32_t nK3[2];      /* N of the (bosonic, fermionic) K3 meshes; CORE: the core box */
+    double  U_re, U_im;  /* CORE only: bare vertex                                     */
+} fdga_level_desc;
+
+/* Shape of an NL2_ParquetSolver (src/nonlocal_2/ParquetSolver.jl:1-154).
+ * lev[0] is S.F's own NL2 level; lev[1..nlev-1] is the chain of S.F0 (S.F.F0 === S.F0),
+ * terminated by a CORE level.  S.Fbuff and S.FL have lev[0]'s grids and a null core. */
+typedef struct {
+    double  T;           /* temperature                                       */
+    int32_t nq;          /* linear size L of the vertex / bubble momentum mesh */
+    int32_t LG;          /* linear size of the G / Sigma momentum mesh         */
+    int32_t nG;          /* N of the fermionic mesh of G, Sigma               */
+    int32_t nPiB, nPiF;  /* N of the bubble's bosonic / fermionic meshes      */
+    int32_t nlev;
+    fdga_level_desc lev[FDGA_MAX_LEVELS];
+} fdga_dims;
+
+/* which-vertex selectors for set/get_vertex: a level index 0..nlev-1, or: */
+enum { FDGA_V_FL = 100, FDGA_V_FBUFF = 101 };
+enum { FDGA_G = 0, FDGA_G0 = 1, FDGA_GBARE = 2, FDGA_SIGMA = 3, FDGA_SIGMA0 = 4 };
+enum { FDGA_PI0PP = 0, FDGA_PI0PH = 1, FDGA_PIPP = 2, FDGA_PIPH = 3 };
+/* K3-shaped caches, src/nonlocal_2/ParquetSolver.jl:138-147 */
+enum { FDGA_C_GPX = 0, FDGA_C_F0P = 1, FDGA_C_F0A = 2, FDGA_C_F0T = 3, FDGA_C_GPP = 4,
+       FDGA_C_GA = 5, FDGA_C_GT = 6, FDGA_C_FP = 7, FDGA_C_FA = 8, FDGA_C_FT = 9 };
+/* symmetry groups, src/nonlocal_2/ParquetSolver.jl:200-291 (SGxx[i] -> K(i) class) */
+enum { FDGA_SG_SIGMA = 0, FDGA_SG_K1 = 1, FDGA_SG_PP2 = 2, FDGA_SG_PH2 = 3, FDGA_SG_PP3 = 4,
+       FDGA_SG_PH3 = 5, FDGA_SG_PPL3 = 6, FDGA_SG_PHL3 = 7, FDGA_SG_COUNT = 8 };
+enum { FDGA_SCPA = 0, FDGA_FDPA = 1 };   /* strategies of src/solve.jl:10, src/SDE.jl:3-33 */
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+int  fdga_create(const fdga_dims* dims, int device, fdga_ctx** out);
+int  fdga_destroy(fdga_ctx* ctx);
+const char* fdga_last_error(fdga_ctx* ctx);         /* ctx may be NULL: error of the last failed create */
+int  fdga_sync(fdga_ctx* ctx);
+/* Options.  FDGA_OPT_SDE_OWN_GAMMA: 0 (default) = SDE L kernels exactly as coded in src/nonlocal_2/SDE.jl:26-29,64-69
+ * (F(...; own gamma) - F.F0(...; own gamma), which for a nested nonlocal F0 also contains F0's cross channels);
+ * 1 = as the in-line comments there state (own-channel gamma of F only).  See DESIGN.md "E2". */
+enum { FDGA_OPT_SDE_OWN_GAMMA = 0 };
+int  fdga_set_option(fdga_ctx* ctx, int opt, int value);
+/* one process per GPU; `unique_id` = the 128-byte ncclUniqueId obtained on rank 0 by
+ * fdga_comm_unique_id and broadcast by the host (MPI in Julia, torch.distributed in tests). */
+int  fdga_comm_unique_id(void* unique_id_128B);
+int  fdga_comm_init(fdga_ctx* ctx, int nranks, int rank, const void* unique_id_128B);
+
+/* ---- data in / out (replace MeshFunction .data assignment / set!, src/channel.jl:80-150) -- */
+int  fdga_set_vertex(fdga_ctx*, int which, int channel, int cls, const fdga_c64* host, int64_t n);
+int  fdga_get_vertex(fdga_ctx*, int which, int channel, int cls, fdga_c64* host, int64_t n);
+int  fdga_set_core(fdga_ctx*, int level, int which4 /*0 Fp_p 1 Fp_x 2 Ft_p 3 Ft_x*/, const fdga_c64* host, int64_t n);
+int  fdga_set_green(fdga_ctx*, int which, const fdga_c64* host, int64_t n);
+int  fdga_get_green(fdga_ctx*, int which, fdga_c64* host, int64_t n);
+int  fdga_set_bubble(fdga_ctx*, int which, const fdga_c64* host, int64_t n);
+int  fdga_get_bubble(fdga_ctx*, int which, fdga_c64* host, int64_t n);
+int  fdga_set_cache(fdga_ctx*, int which, const fdga_c64* host, int64_t n);
+int  fdga_get_cache(fdga_ctx*, int which, fdga_c64* host, int64_t n);
+int  fdga_get_L(fdga_ctx*, int is_pp, fdga_c64* host, int64_t n);
+/* SG.classes flattened (MatsubaraFunctions SymmetryGroup): CSR offsets (nclasses+1), 0-based linear
+ * member indices, op bits (bit0 = sgn, bit1 = con); representative = first member of a class. */
+int  fdga_set_symmetry_classes(fdga_ctx*, int which_sg, int64_t nclasses, const int64_t* offsets,
+                               const int64_t* index, const uint8_t* ops);
+/* Stand-alone class-table builder (host, integer only) restating SymmetryGroup(symmetries, f) for the
+ * generator lists of init_sym_grp! (src/nonlocal_2/ParquetSolver.jl:200-291; generators
+ * src/nonlocal/symmetries.jl, src/nonlocal_2/symmetries.jl).  n0 = N of the first mesh, n1 = N of the
+ * fermionic meshes.  offsets needs len+1 entries, index/ops len entries (len = array length). */
+int  fdga_build_symmetry_group(int which_sg, int n0, int n1, int nq, int64_t* offsets, int64_t* index,
+                               uint8_t* ops, int64_t* nclasses);
+/* flatten(S.F) / unflatten!(S.F, x*scale): src/vertex.jl:153-195, src/channel.jl:155-210 */
+int64_t fdga_length_F(fdga_ctx*);
+int  fdga_flatten_F(fdga_ctx*, fdga_c64* host_y);
+int  fdga_unflatten_F(fdga_ctx*, const fdga_c64* host_x, double scale);
+
+/* ---- kernels: one per reference function ---------------------------------------------- */
+/* Dyson!(S): src/dyson.jl:20-31 */
+int  fdga_dyson(fdga_ctx*);
+/* compute_occupation(G): src/dyson.jl:39-41; which = FDGA_G or FDGA_G0 */
+int  fdga_occupation(fdga_ctx*, int which, double* occ);
+/* bubbles_real_space!(Pipp, Piph, G): src/nonlocal_2/bubble.jl:42-122; reference != 0 -> (Pi0, G0) */
+int  fdga_bubbles_real_space(fdga_ctx*, int reference);
+/* bubbles_momentum_space!: src/nonlocal_2/bubble.jl:1-37 (cross-check; needs LG % nq == 0) */
+int  fdga_bubbles_momentum_space(fdga_ctx*, int reference);
+/* build_K3_cache!(S): src/nonlocal_2/build_K3_cache.jl:18-94; mfrg != 0 -> build_K3_cache_mfRG!(S, first) :97-164 */
+int  fdga_build_K3_cache(fdga_ctx*, int mfrg, int first);
+/* BSE_L_K2!(S, Ch): src/BSE_templates.jl:47-76 -> src/nonlocal_2/BSEa/BSEa_K2.jl:1-49 */
+int  fdga_bse_L_K2(fdga_ctx*, int ch);
+/* BSE_L_K3!(S, Ch): src/BSE_templates.jl:117-146 -> src/nonlocal_2/BSEa/BSEa_K3.jl:1-40 */
+int  fdga_bse_L_K3(fdga_ctx*, int ch);
+/* BSE_K1!(S, Ch, is_mfRG): src/BSE_templates.jl:12-41 -> src/nonlocal_2/BSEa/BSEa_K1.jl:2-58 */
+int  fdga_bse_K1(fdga_ctx*, int ch, int mfrg);
+/* BSE_K2!(S, Ch, is_mfRG): src/BSE_templates.jl:82-111 -> src/nonlocal_2/BSEa/BSEa_K2.jl:55-138 */
+int  fdga_bse_K2(fdga_ctx*, int ch, int mfrg);
+/* BSE_K3!(S, Ch, is_mfRG): src/BSE_templates.jl:151-180 -> src/nonlocal_2/BSEa/BSEa_K3.jl:43-128 */
+int  fdga_bse_K3(fdga_ctx*, int ch, int mfrg);
+/* set!(S.F, S.Fbuff): src/solve.jl:87 */
+int  fdga_set_F_from_Fbuff(fdga_ctx*);
+/* SDE!(S; strategy, include_U2, include_Hartree): src/SDE.jl:3-48 -> src/nonlocal_2/SDE.jl:154-324 */
+int  fdga_sde(fdga_ctx*, int strategy, int include_U2, int include_Hartree);
+/* iterate_solver!(S; strategy, update_Sigma): src/solve.jl:4-116 (strategies scPA, fdPA) */
+int  fdga_iterate_solver(fdga_ctx*, int strategy, int update_sigma);
+/* mfRGLinearMap matvec: src/mfRG.jl:34-89 (strategy fdPA); first = is_first_iteration */
+int  fdga_mfrg_matvec(fdga_ctx*, const fdga_c64* host_x, fdga_c64* host_y, int first);
+
+/* ---- introspection --------------------------------------------------------------------- */
+/* accumulated device time (CUDA events on the launching stream) and launch counts per kernel id */
+enum { FDGA_T_CACHE = 0, FDGA_T_L_K2 = 1, FDGA_T_L_K3 = 2, FDGA_T_K1 = 3, FDGA_T_K2 = 4, FDGA_T_K3 = 5,
+       FDGA_T_SDE_L = 6, FDGA_T_SDE_RS = 7, FDGA_T_SDE_U2 = 8, FDGA_T_BUBBLE = 9, FDGA_T_RIGHT = 10,
+       FDGA_T_SWAVE = 11, FDGA_T_EXPAND = 12, FDGA_T_MISC = 13, FDGA_T_COMM = 14, FDGA_T_COUNT = 15 };
+int  fdga_profile_enable(fdga_ctx*, int on);
+int  fdga_profile_reset(fdga_ctx*);
+int  fdga_kernel_time_ms(fdga_ctx*, int kernel_id, double* ms, int64_t* launches);
+int64_t fdga_total_launches(fdga_ctx*);
+/* the stream all kernels of this context are launched on (cudaStream_t as void*) */
+void* fdga_stream(fdga_ctx*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDGA_H */

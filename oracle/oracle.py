@@ -1,0 +1,408 @@
+"""Python adapter of the CPU oracle (oracle/fdga_oracle.cpp).  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+It restates the reference's host-level call structure (BSE_templates.jl wrappers, iterate_solver!, SDE!,
+mfRGLinearMap) on top of the C++ restatement of the kernels, operating on plain numpy arrays.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+import fddgasolver_jl_b200  # noqa: E402,F401  (data containers only; no device code is touched)
+from fddgasolver_jl_b200.types import (NL2_Vertex, RefVertex, Vertex, aCh, dSp, nB, nF, pCh, pSp, tCh,  # noqa: E402
+                                       vertex_chain, xSp, zeros)
+
+LIB = os.path.join(_HERE, "_build", "libfdga_oracle.so")
+INF = (2 ** 31 - 1) // 4
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "fdga_oracle.cpp")
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-fopenmp", "-shared", "-fPIC", "-std=c++17", "-o", LIB, src])
+    return LIB
+
+
+class _Level(C.Structure):
+    _fields_ = [("type", C.c_int), ("nK1", C.c_int), ("nK2b", C.c_int), ("nK2f", C.c_int), ("nK3b", C.c_int), ("nK3f", C.c_int),
+                ("U_re", C.c_double), ("U_im", C.c_double),
+                ("K1", C.c_void_p * 3), ("K2", C.c_void_p * 3), ("K3", C.c_void_p * 3), ("core", C.c_void_p * 4)]
+
+
+class _Vertex(C.Structure):
+    _fields_ = [("nlev", C.c_int), ("lev", _Level * 8)]
+
+
+class _Grid(C.Structure):
+    _fields_ = [("T", C.c_double), ("L", C.c_int), ("nPiB", C.c_int), ("nPiF", C.c_int)]
+
+
+class _SG(C.Structure):
+    _fields_ = [("nclasses", C.c_int64), ("offsets", C.c_void_p), ("index", C.c_void_p), ("op", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+        _lib.orc_occupation.restype = C.c_double
+        _lib.orc_build_symmetry_group.restype = C.c_int64
+        _lib.orc_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    assert a.flags["F_CONTIGUOUS"] or a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+def vertex_struct(V):
+    """ctypes descriptor of the nested vertex chain V -> V.F0 -> ... (arrays are referenced, not copied)"""
+    out = _Vertex()
+    chain = vertex_chain(V)
+    out.nlev = len(chain)
+    for i, X in enumerate(chain):
+        lv = out.lev[i]
+        if isinstance(X, RefVertex):
+            lv.type = 2
+            lv.nK3b, lv.nK3f = X.numK3
+            lv.U_re, lv.U_im = X.U.real, X.U.imag
+            for j, a in enumerate(X.arrays()):
+                lv.core[j] = a.ctypes.data
+        else:
+            lv.type = 0 if isinstance(X, NL2_Vertex) else 1
+            lv.nK1 = X.numK1
+            lv.nK2b, lv.nK2f = X.numK2
+            lv.nK3b, lv.nK3f = X.numK3
+            for r, g in enumerate(X.channels()):
+                lv.K1[r], lv.K2[r], lv.K3[r] = g.K1.ctypes.data, g.K2.ctypes.data, g.K3.ctypes.data
+    out._keep = chain
+    return out
+
+
+def sg_struct(tbl):
+    offsets, index, ops = tbl
+    s = _SG()
+    s.nclasses = len(offsets) - 1
+    s.offsets, s.index, s.op = offsets.ctypes.data, index.ctypes.data, ops.ctypes.data
+    s._keep = tbl
+    return s
+
+
+def build_symmetry_group(kind, n0, n1, L, length):
+    offsets = np.zeros(length + 1, dtype=np.int64)
+    index = np.zeros(length, dtype=np.int64)
+    ops = np.zeros(length, dtype=np.uint8)
+    n = lib().orc_build_symmetry_group(kind, n0, n1, L, _p(offsets), _p(index), _p(ops))
+    return offsets[: n + 1].copy(), index, ops
+
+
+def trivial_group(length):
+    return (np.arange(length + 1, dtype=np.int64), np.arange(length, dtype=np.int64), np.zeros(length, dtype=np.uint8))
+
+
+def eval_vertex(V, L, W, v, w, P, k, q, Ch, Sp, F0=True, γp=True, γt=True, γa=True, level=0):
+    """V(Ω, ν, ω, P, k, q, Ch, Sp; F0, γp, γt, γa); k / q may be the string 'sw'; ν / ω may be INF."""
+    vs = vertex_struct(V)
+    out = np.zeros(1, dtype=np.complex128)
+    ksw, qsw = isinstance(k, str), isinstance(q, str)
+    Pa = (C.c_int * 2)(*P)
+    ka = (C.c_int * 2)(*(k if not ksw else (0, 0)))
+    qa = (C.c_int * 2)(*(q if not qsw else (0, 0)))
+    lib().orc_eval_vertex(C.byref(vs), L, level, W, v, w, Pa, ka, qa, int(ksw), int(qsw), Ch, Sp,
+                          int(F0), int(γp), int(γt), int(γa), _p(out))
+    return complex(out[0])
+
+
+def eval_channel(V, L, r, W, v, w, P, k, q, K1=True, K2=True, K3=True, level=0):
+    vs = vertex_struct(V)
+    out = np.zeros(1, dtype=np.complex128)
+    sw = (1 if isinstance(P, str) else 0) | (2 if isinstance(k, str) else 0) | (4 if isinstance(q, str) else 0)
+    arr = [(C.c_int * 2)(*(x if not isinstance(x, str) else (0, 0))) for x in (P, k, q)]
+    lib().orc_eval_channel(C.byref(vs), L, level, r, W, v, w, arr[0], arr[1], arr[2], sw, int(K1), int(K2), int(K3), _p(out))
+    return complex(out[0])
+
+
+_CACHE_NAMES = ["cache_Γpx", "cache_F0p", "cache_F0a", "cache_F0t", "cache_Γpp", "cache_Γa", "cache_Γt",
+                "cache_Fp", "cache_Fa", "cache_Ft"]
+SG_SIGMA, SG_K1, SG_PP2, SG_PH2, SG_PP3, SG_PH3, SG_PPL3, SG_PHL3 = range(8)
+
+
+class OracleSolver:
+    """CPU restatement of NL2_ParquetSolver (src/nonlocal_2/ParquetSolver.jl:1-154)."""
+
+    def __init__(self, nK1, nK2, nK3, L_, Gbare, G0, Σ0, F0, *, T, mΠν_factor=1, compute_bubbles=True):
+        self.T, self.L, self.NP = float(T), int(L_), int(L_) ** 2
+        self.nK1, self.nK2, self.nK3 = int(nK1), tuple(nK2), tuple(nK3)
+        self.Gbare = np.asfortranarray(Gbare, dtype=np.complex128)
+        self.nG = self.Gbare.shape[0] // 2
+        self.LG = int(round(np.sqrt(self.Gbare.shape[1])))
+        self.nΠB, self.nΠF = self.nK1, self.nK1 * int(mΠν_factor)
+        self.G0 = np.array(G0, dtype=np.complex128, order="F")
+        self.Σ0 = np.array(Σ0, dtype=np.complex128, order="F")
+        self.G = self.G0.copy(order="F")
+        self.Σ = self.Σ0.copy(order="F")
+        self.F0 = F0
+        self.F = NL2_Vertex(F0, self.T, nK1, nK2, nK3, self.L)
+        self.Fbuff = NL2_Vertex(RefVertex(self.T, 0.0), self.T, nK1, nK2, nK3, self.L)
+        self.FL = NL2_Vertex(RefVertex(self.T, 0.0), self.T, nK1, nK2, nK3, self.L)
+        shpΠ = (nB(self.nΠB), nF(self.nΠF), self.NP, self.NP)
+        self.Π0pp, self.Π0ph, self.Πpp, self.Πph = zeros(shpΠ), zeros(shpΠ), zeros(shpΠ), zeros(shpΠ)
+        self.Lpp, self.Lph = zeros(self.F.γp.K2.shape), zeros(self.F.γp.K2.shape)
+        for n in _CACHE_NAMES:
+            setattr(self, n, zeros(self.F.γp.K3.shape))
+        self.grid = _Grid(self.T, self.L, self.nΠB, self.nΠF)
+        self.reset_sym_grp()
+        if compute_bubbles:
+            bubbles_real_space(self, self.Π0pp, self.Π0ph, self.G0)
+            Dyson(self)
+            bubbles_real_space(self, self.Πpp, self.Πph, self.G)
+
+    def _sg_len(self, which):
+        return {SG_SIGMA: self.Σ.size, SG_K1: self.F.γp.K1.size, SG_PP2: self.F.γp.K2.size, SG_PH2: self.F.γp.K2.size}.get(which, self.F.γp.K3.size)
+
+    def reset_sym_grp(self):
+        self.sg = {w: trivial_group(self._sg_len(w)) for w in range(8)}
+
+    def init_sym_grp(self):
+        n = {SG_SIGMA: (self.nG, 0), SG_K1: (self.nK1, 0), SG_PP2: self.nK2, SG_PH2: self.nK2,
+             SG_PP3: self.nK3, SG_PH3: self.nK3, SG_PPL3: self.nK3, SG_PHL3: self.nK3}
+        for w, (n0, n1) in n.items():
+            self.sg[w] = build_symmetry_group(w, n0, n1, self.LG if w == SG_SIGMA else self.L, self._sg_len(w))
+
+    def set_symmetry_classes(self, which, offsets, index, ops):
+        self.sg[which] = (np.ascontiguousarray(offsets, dtype=np.int64), np.ascontiguousarray(index, dtype=np.int64),
+                          np.ascontiguousarray(ops, dtype=np.uint8))
+
+    def caches(self):
+        return [getattr(self, n) for n in _CACHE_NAMES]
+
+
+# ------------------------------------------------------------------------------- reference-named operations
+def Dyson(S):
+    lib().orc_dyson(_p(S.G), _p(S.Σ), _p(S.Gbare), C.c_int64(S.G.size))
+
+
+def compute_occupation(S, G=None):
+    G = S.G if G is None else G
+    return lib().orc_occupation(_p(G), S.nG, S.LG, C.c_double(S.T))
+
+
+def hubbard_bare_Green(T, nG, LG, *, μ, t1, t2=0.0, t3=0.0):
+    G = zeros((2 * nG, LG * LG))
+    lib().orc_hubbard_bare_green(_p(G), nG, LG, C.c_double(T), C.c_double(μ), C.c_double(t1), C.c_double(t2), C.c_double(t3))
+    return G
+
+
+def bubbles_real_space(S, Πpp, Πph, G):
+    lib().orc_bubbles_real_space(_p(Πpp), _p(Πph), _p(G), S.nG, S.LG, C.byref(S.grid))
+
+
+def bubbles_momentum_space(S, Πpp, Πph, G):
+    lib().orc_bubbles_momentum_space(_p(Πpp), _p(Πph), _p(G), S.nG, S.LG, C.byref(S.grid))
+
+
+def bubbles(S):
+    bubbles_real_space(S, S.Πpp, S.Πph, S.G)
+
+
+def _pi(S, ch, reference):
+    if ch == pCh:
+        return S.Π0pp if reference else S.Πpp
+    return S.Π0ph if reference else S.Πph
+
+
+def _sign_sp(ch):
+    # (sign, Sp) of BSE_templates.jl:17,25,33
+    return (-1, dSp) if ch == tCh else (+1, pSp)
+
+
+def _tfix(Xt, Xa):
+    # γt = (γt^d + γa) / 2, BSE_templates.jl:35-38
+    Xt += Xa
+    Xt /= 2
+
+
+def build_K3_cache(S, i0=0, i1=-1):
+    cs = S.caches()
+    if i0 == 0 and i1 < 0:
+        for c in cs:
+            c[...] = 0
+    arr = (C.c_void_p * 10)(*[c.ctypes.data for c in cs])
+    lib().orc_build_K3_cache(arr, S.nK3[0], S.nK3[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)),
+                             C.byref(S.grid), C.c_int64(i0), C.c_int64(i1))
+
+
+def build_K3_cache_mfRG(S, is_first_iteration):
+    cs = S.caches()
+    arr = (C.c_void_p * 10)(*[c.ctypes.data for c in cs])
+    lib().orc_build_K3_cache_mfRG(arr, S.nK3[0], S.nK3[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)),
+                                  C.byref(sg_struct(S.sg[SG_PP3])), C.byref(sg_struct(S.sg[SG_PH3])), int(is_first_iteration), C.byref(S.grid))
+
+
+def BSE_K1(S, ch, is_mfRG=False, c0=0, c1=-1):
+    sign, Sp = _sign_sp(ch)
+    K1 = S.Fbuff.channel(ch).K1
+    lib().orc_bse_K1(_p(K1), S.nK1, C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)), C.byref(vertex_struct(S.FL)),
+                     _p(_pi(S, ch, True)), _p(_pi(S, ch, False)), C.byref(sg_struct(S.sg[SG_K1])), sign, ch, Sp, int(is_mfRG),
+                     C.byref(S.grid), C.c_int64(c0), C.c_int64(c1))
+    if ch == tCh:
+        _tfix(S.Fbuff.γt.K1, S.Fbuff.γa.K1)
+
+
+def BSE_L_K2(S, ch, is_mfRG=False, c0=0, c1=-1):
+    sign, Sp = _sign_sp(ch)
+    K2 = S.FL.channel(ch).K2
+    sg = S.sg[SG_PP2 if ch == pCh else SG_PH2]
+    lib().orc_bse_L_K2(_p(K2), S.nK2[0], S.nK2[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)),
+                       _p(_pi(S, ch, True)), C.byref(sg_struct(sg)), sign, ch, Sp, C.byref(S.grid), C.c_int64(c0), C.c_int64(c1))
+    if ch == tCh:
+        _tfix(S.FL.γt.K2, S.FL.γa.K2)
+
+
+def BSE_K2(S, ch, is_mfRG=False, c0=0, c1=-1):
+    sign, Sp = _sign_sp(ch)
+    K2 = S.Fbuff.channel(ch).K2
+    sg = S.sg[SG_PP2 if ch == pCh else SG_PH2]
+    lib().orc_bse_K2(_p(K2), S.nK2[0], S.nK2[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)), C.byref(vertex_struct(S.FL)),
+                     _p(_pi(S, ch, True)), _p(_pi(S, ch, False)), C.byref(sg_struct(sg)), sign, ch, Sp, int(is_mfRG),
+                     C.byref(S.grid), C.c_int64(c0), C.c_int64(c1))
+    if ch == tCh:       # BSEa_K2.jl:130-135
+        K2 += 2 * S.FL.γt.K2
+        K2 += -1 * S.FL.γa.K2
+        _tfix(S.Fbuff.γt.K2, S.Fbuff.γa.K2)
+    else:
+        K2 += S.FL.channel(ch).K2
+
+
+def BSE_L_K3(S, ch, is_mfRG=False):
+    # (cache_Γ, cache_F0, sign): BSE_templates.jl:122,130,138
+    cG, cF0, sign = {aCh: (S.cache_Γa, S.cache_F0a, +1), pCh: (S.cache_Γpp, S.cache_F0p, -1), tCh: (S.cache_Γt, S.cache_F0t, -1)}[ch]
+    sg = S.sg[SG_PPL3 if ch == pCh else SG_PHL3]
+    K3 = S.FL.channel(ch).K3
+    lib().orc_bse_L_K3(_p(K3), S.nK3[0], S.nK3[1], _p(cG), _p(cF0), _p(_pi(S, ch, True)), C.byref(sg_struct(sg)), sign, C.byref(S.grid))
+    if ch == tCh:
+        _tfix(S.FL.γt.K3, S.FL.γa.K3)
+
+
+def BSE_K3(S, ch, is_mfRG=False):
+    # BSE_templates.jl:156,164,172
+    cG, cF, cF0, s1, s2 = {aCh: (S.cache_Γa, S.cache_Fa, S.cache_F0a, +1, +1), pCh: (S.cache_Γpx, S.cache_Fp, S.cache_F0p, -1, +1),
+                           tCh: (S.cache_Γt, S.cache_Ft, S.cache_F0t, -1, -1)}[ch]
+    sg = S.sg[SG_PP3 if ch == pCh else SG_PH3]
+    K3 = S.Fbuff.channel(ch).K3
+    lib().orc_bse_K3(_p(K3), S.nK3[0], S.nK3[1], _p(S.FL.channel(ch).K3), _p(S.FL.γt.K3), _p(S.FL.γa.K3), _p(cG), _p(cF), _p(cF0),
+                     _p(_pi(S, ch, True)), _p(_pi(S, ch, False)), C.byref(sg_struct(sg)), s1, s2, ch, int(is_mfRG), C.byref(S.grid))
+    if ch == tCh:
+        _tfix(S.Fbuff.γt.K3, S.Fbuff.γa.K3)
+
+
+def SDE_channel_L(S, Lout, Π, V, level, is_pp, c0=0, c1=-1):
+    sg = S.sg[SG_PP2 if is_pp else SG_PH2]
+    lib().orc_sde_L(_p(Lout), S.nK2[0], S.nK2[1], C.byref(vertex_struct(V)), level, _p(Π), C.byref(sg_struct(sg)), int(is_pp),
+                    C.byref(S.grid), C.c_int64(c0), C.c_int64(c1))
+
+
+def SDE_compute(S, G, Πpp, Πph, V, level, include_U2=True, include_Hartree=True):
+    """SDE_compute!(copy(Σ), G, Πpp, Πph, Lpp, Lph, F = chain(V)[level:], ...): src/nonlocal_2/SDE.jl:154-324"""
+    chain = vertex_chain(V)
+    U = chain[-1].U
+    SDE_channel_L(S, S.Lpp, Πpp, V, level, True)
+    SDE_channel_L(S, S.Lph, Πph, V, level, False)
+    Σ = zeros(S.Σ.shape)
+    sgΣ = sg_struct(S.sg[SG_SIGMA])
+    lib().orc_sde_real_space(_p(Σ), S.nG, S.LG, _p(G), S.nG, S.LG, _p(S.Lpp), _p(S.Lph), S.nK2[0], S.nK2[1], C.byref(sgΣ), C.byref(S.grid))
+    if isinstance(chain[level], RefVertex):
+        Σ *= 1 / 3
+    if include_U2:
+        ΣU2 = zeros(S.Σ.shape)
+        lib().orc_sde_U2(_p(ΣU2), _p(G), S.nG, S.LG, C.c_double(U.real), C.c_double(U.imag), C.c_double(S.T), C.byref(sgΣ))
+        Σ += ΣU2
+    if include_Hartree:
+        n = compute_occupation(S, G)
+        Σ += (n - 1 / 2) * U * 1j
+    return Σ
+
+
+def _SDE_chain(S, Σ, G, Πpp, Πph, V, level, include_U2, include_Hartree):
+    # SDE!(Σ, G, ..., F): src/SDE.jl:35-48
+    chain = vertex_chain(V)
+    for l in range(level, len(chain)):
+        top = l == level
+        Σ += SDE_compute(S, G, Πpp, Πph, V, l, include_U2 and top, include_Hartree and top)
+    return Σ
+
+
+def SDE(S, strategy="scPA", include_U2=True, include_Hartree=True):
+    """SDE!(S; strategy): src/SDE.jl:3-33"""
+    S.Σ[...] = 0
+    _SDE_chain(S, S.Σ, S.G, S.Πpp, S.Πph, S.F, 0, include_U2, include_Hartree)
+    if strategy == "fdPA":
+        Σ0part = _SDE_chain(S, zeros(S.Σ.shape), S.G0, S.Π0pp, S.Π0ph, S.F, 1, include_U2, include_Hartree)
+        S.Σ += -1 * Σ0part
+        S.Σ += S.Σ0
+        if include_Hartree:
+            n0 = compute_occupation(S, S.G0)
+            S.Σ -= (n0 - 1 / 2) * S.F.bare_vertex() * 1j
+
+
+def iterate_solver(S, strategy="fdPA", update_Σ=True):
+    """iterate_solver!(S; strategy, update_Σ): src/solve.jl:4-116"""
+    if update_Σ:
+        Dyson(S)
+        bubbles(S)
+    build_K3_cache(S)
+    if strategy == "fdPA":
+        for ch in (pCh, aCh, tCh):
+            BSE_L_K2(S, ch)
+        for ch in (pCh, aCh, tCh):
+            BSE_L_K3(S, ch)
+    for ch in (pCh, aCh, tCh):
+        BSE_K1(S, ch)
+    for ch in (pCh, aCh, tCh):
+        BSE_K2(S, ch)
+    for ch in (pCh, aCh, tCh):
+        BSE_K3(S, ch)
+    S.F.set(S.Fbuff)
+    if update_Σ:
+        SDE(S, strategy)
+
+
+class mfRGLinearMap:
+    """src/mfRG.jl:20-89"""
+
+    def __init__(self, S):
+        self.S = S
+        self.is_first_iteration = True
+
+    def matvec(self, x):
+        S = self.S
+        factor = 1e-2
+        S.F.unflatten(np.asarray(x) * factor)
+        build_K3_cache_mfRG(S, self.is_first_iteration)
+        self.is_first_iteration = False
+        for ch in (pCh, aCh, tCh):
+            BSE_L_K2(S, ch)
+        for ch in (pCh, aCh, tCh):
+            BSE_K1(S, ch, True)
+        for ch in (pCh, aCh, tCh):
+            BSE_K2(S, ch, True)
+        for ch in (pCh, aCh, tCh):
+            BSE_L_K3(S, ch)
+        for ch in (pCh, aCh, tCh):
+            BSE_K3(S, ch, True)
+        S.F.set(S.Fbuff)
+        y = S.F.flatten()
+        return x - y / factor
