@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- parquet BSE iterations/sec at the nonlocal Wu point (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one synthetic vertex:
+    iterate_solver!(S; strategy = :fdPA, update_Σ = false)   (script/benchmark_Wu.jl:53, src/solve.jl:4-116)
+  + SDE!(S; strategy = :scPA)                                 (src/mfRG.jl:335)
+on an NL2_ParquetSolver with the grid sizes of script/benchmark_Wu.jl:78 (nmax = 4, nq = 8, LG = 48; "config 3").
+
+  python bench.py --gpus N --steps K --warmup W            our arm (libfdga, CUDA sm_100a)
+  python bench.py --impl reference ...                     CPU arm: the oracle restatement of the reference's
+                                                           algorithm on the host cores (Julia is not installed)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "parquet_bse_iterations_per_sec"
+UNIT = "iterations/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--nmax", type=int, default=4)
+    p.add_argument("--nq", type=int, default=8)
+    p.add_argument("--LG", type=int, default=48)
+    p.add_argument("--cpu-fraction", type=float, default=1.0 / 48, help="fraction of class representatives timed on the CPU per step")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def workload_name(a):
+    return f"NL2 Wu point U=5.6 T=0.2 (script/benchmark_Wu.jl): nmax={a.nmax} (nK1={4 * a.nmax}, nK2=nK3=({a.nmax},{a.nmax})), nq={a.nq}, LG={a.LG}"
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_iteration_seconds(o, R, frac):
+    """Time the oracle (reference loop structure, OpenMP over class representatives = the reference's
+    Threads.@threads over SG classes) on a contiguous sample of `frac` of the class representatives of every
+    kernel, and extrapolate each kernel linearly in the number of representatives to one full iteration."""
+    import fddgasolver_jl_b200 as fd
+    t_total, parts = 0.0, {}
+
+    def timed(name, fn, n_total, n_sample):
+        nonlocal t_total
+        t0 = time.perf_counter()
+        fn(n_sample)
+        dt = (time.perf_counter() - t0) * n_total / max(n_sample, 1)
+        parts[name] = parts.get(name, 0.0) + dt
+        t_total += dt
+
+    ns = lambda n: max(1, int(round(n * frac)))
+    n3 = R.F.γp.K3.size
+    timed("cache", lambda n: o.build_K3_cache(R, 0, n), n3, ns(n3))
+    order = (fd.pCh, fd.aCh, fd.tCh)
+    for ch in order:
+        n2 = len(R.sg[o.SG_PP2 if ch == fd.pCh else o.SG_PH2][0]) - 1
+        timed("L_K2", lambda n: o.BSE_L_K2(R, ch, c0=0, c1=n), n2, ns(n2))
+    t0 = time.perf_counter()
+    for ch in order:
+        o.BSE_L_K3(R, ch)
+    parts["L_K3"] = time.perf_counter() - t0; t_total += parts["L_K3"]
+    for ch in order:
+        n1 = len(R.sg[o.SG_K1][0]) - 1
+        timed("K1", lambda n: o.BSE_K1(R, ch, c0=0, c1=n), n1, max(1, min(n1, int(round(n1 * frac * 4)))))
+    for ch in order:
+        n2 = len(R.sg[o.SG_PP2 if ch == fd.pCh else o.SG_PH2][0]) - 1
+        timed("K2", lambda n: o.BSE_K2(R, ch, c0=0, c1=n), n2, ns(n2))
+    t0 = time.perf_counter()
+    for ch in order:
+        o.BSE_K3(R, ch)
+    parts["K3"] = time.perf_counter() - t0; t_total += parts["K3"]
+    # SDE!(scPA): L kernels for every level of the F0 chain (sampled), real-space contraction and U^2 term (full, once)
+    nlev = len(fd.vertex_chain(R.F))
+    for lvl in range(nlev):
+        n2 = len(R.sg[o.SG_PP2][0]) - 1
+        timed("sde_L", lambda n: o.SDE_channel_L(R, R.Lpp, R.Πpp, R.F, lvl, True, 0, n), n2, ns(n2))
+        timed("sde_L", lambda n: o.SDE_channel_L(R, R.Lph, R.Πph, R.F, lvl, False, 0, n), n2, ns(n2))
+    t0 = time.perf_counter()
+    import ctypes as C
+    Σ = np.zeros_like(R.Σ)
+    sgΣ = o.sg_struct(R.sg[o.SG_SIGMA])
+    o.lib().orc_sde_real_space(o._p(Σ), R.nG, R.LG, o._p(R.G), R.nG, R.LG, o._p(R.Lpp), o._p(R.Lph), R.nK2[0], R.nK2[1], C.byref(sgΣ), C.byref(R.grid))
+    dt_rs = time.perf_counter() - t0
+    parts["sde_rs"] = dt_rs * nlev; t_total += dt_rs * nlev
+    t0 = time.perf_counter()
+    o.lib().orc_sde_U2(o._p(Σ), o._p(R.G), R.nG, R.LG, C.c_double(5.6), C.c_double(0.0), C.c_double(R.T), C.byref(sgΣ))
+    parts["sde_U2"] = time.perf_counter() - t0; t_total += parts["sde_U2"]
+    return t_total, parts
+
+
+def make_oracle_solver(o, inp, share_bubbles_from=None):
+    R = o.OracleSolver(inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"], T=inp["T"],
+                       compute_bubbles=share_bubbles_from is None)
+    if share_bubbles_from is not None:
+        S = share_bubbles_from
+        S.pull("Π", "G")
+        R.Π0pp, R.Π0ph, R.Πpp, R.Πph, R.G = S.Π0pp, S.Π0ph, S.Πpp, S.Πph, S.G.copy(order="F")
+    R.init_sym_grp()
+    R.F.set(inp["F"])
+    R.FL.set(inp["F"])     # any non-trivial FL: timing only
+    return R
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fddgasolver_jl_b200 as fd
+    import oracle as o
+    o.build()
+    inp = fd.wu_point_inputs(a.nmax, a.nq, a.LG, F0_scale=0.02)
+    R = make_oracle_solver(o, inp)
+    cores = o.lib().orc_num_threads()
+    frac = a.cpu_fraction
+    for _ in range(a.warmup):
+        cpu_iteration_seconds(o, R, frac / 4)
+    ts = []
+    for _ in range(a.steps):
+        t, parts = cpu_iteration_seconds(o, R, frac)
+        ts.append(t)
+    sec = float(np.mean(ts))
+    val = 1.0 / sec
+    sample = f"{frac:.4f} of the class representatives of every BSE/SDE-L kernel per step, extrapolated linearly; K3 kernels, real-space SDE and U^2 term in full"
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex)",
+           "data": "synthetic", "config": {"workload": workload_name(a), "timing": "host wall clock of the CPU restatement (oracle/) of the reference algorithm; Julia + MatsubaraFunctions.jl are not installed"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "parts_s": {k: round(v, 3) for k, v in parts.items()}}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import torch
+    import fddgasolver_jl_b200 as fd
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    inp = fd.wu_point_inputs(a.nmax, a.nq, a.LG, F0_scale=0.02)
+    S = fd.NL2_ParquetSolver(inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"], T=inp["T"], device=local)
+    S.F.set(inp["F"]); S.push("F"); S.init_sym_grp()
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.from_numpy(S.comm_unique_id())
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        S.comm_init(world, rank, uid.cpu().numpy())
+    stream = torch.cuda.ExternalStream(S.stream())
+    nF = S.length_F()
+    x_host = torch.empty(nF, dtype=torch.complex128).pin_memory()
+    y_host = torch.empty(nF, dtype=torch.complex128).pin_memory()
+    s_host = torch.empty(S.Σ.size, dtype=torch.complex128).pin_memory()
+    x_np, y_np, s_np = x_host.numpy(), y_host.numpy(), s_host.numpy()
+    x_np[:] = inp["F"].flatten()
+
+    def barrier():
+        torch.cuda.synchronize(); S.sync()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(); S.sync()
+
+    def step_resident():
+        S.unstash_F()
+        fd.iterate_solver(S, "fdPA", update_Σ=False)
+        fd.SDE(S, "scPA")
+
+    def step_e2e():
+        S.unflatten_F_async(x_np)                       # H2D of this step's input vertex
+        fd.iterate_solver(S, "fdPA", update_Σ=False)
+        fd.SDE(S, "scPA")
+        S.flatten_F(y_np)                               # D2H of the updated vertex (synchronises)
+        S.get_green_into("Σ", s_np)                     # D2H of the self-energy
+
+    def timed(step, K, W):
+        for _ in range(W):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = S.total_launches()
+        e0.record(stream)
+        for _ in range(K):
+            step()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, S.total_launches() - n0
+
+    S.unflatten_F(x_np); S.stash_F()
+    W = max(a.warmup, 3)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, launches = timed(step_resident, a.steps, W)
+    ms_e2e, _ = timed(step_e2e, a.steps, 1)
+    clk = clocks.stop() if rank == 0 else None
+    value = a.steps / (ms * 1e-3)
+    e2e = a.steps / (ms_e2e * 1e-3)
+
+    # per-kernel device times (CUDA events on the library's stream) over a few profiled steps
+    S.profile(True); S.profile_reset()
+    PS = min(a.steps, 5)
+    for _ in range(PS):
+        step_resident()
+    kt = S.kernel_times()
+    S.profile(False)
+    kernels = {k: {"ms_per_step": v[0] / PS, "launches_per_step": v[1] / PS} for k, v in kt.items() if v[1]}
+
+    # roofline of the dominant kernel (BSE_K2!, one launch per channel; DESIGN.md "Roofline")
+    n2cls = [S.num_classes(fd._lib.SG_PP2), S.num_classes(fd._lib.SG_PH2), S.num_classes(fd._lib.SG_PH2)]
+    nB2, nF2, NP, nFΠ = 2 * S.nK2[0] - 1, 2 * S.nK2[1], S.NP, 2 * S.nΠF
+    chunk = [(-(-n // world)) for n in n2cls]           # representatives per rank
+    tables = sum(sum(arr.size for arr in V.γp.arrays()) * 3 * 16 for V in fd.vertex_chain(S.F)[:-1]) + 4 * fd.vertex_chain(S.F)[-1].Fp_p.size * 16
+    bytes_per_launch = nB2 * NP * nFΠ * NP * 16 / world + tables + np.mean(chunk) * 16
+    flop_per_launch = 26.0 * np.mean(chunk) * nFΠ * NP
+    k2 = kernels.get("K2", {"ms_per_step": float("nan"), "launches_per_step": 3})
+    k2_ms_launch = k2["ms_per_step"] / max(k2["launches_per_step"], 1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+    ach = bytes_per_launch / (k2_ms_launch * 1e-3) / 1e9
+    roofline = {"kernel": "bse_k2_kernel (BSE_K2!, src/nonlocal_2/BSEa/BSEa_K2.jl:55-138)", "bound": "hbm", "achieved": ach, "peak": peak_hbm,
+                "unit": "GB/s", "frac": ach / peak_hbm, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": k2_ms_launch,
+                "note": "gather/issue-bound FP64 kernel, not HBM-bound: see fp64",
+                "fp64": {"algorithmic_gflop_per_launch": flop_per_launch / 1e9, "achieved_tflops": flop_per_launch / (k2_ms_launch * 1e-3) / 1e12}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as o
+        o.build()
+        R = make_oracle_solver(o, inp, share_bubbles_from=S)
+        sec, parts = cpu_iteration_seconds(o, R, a.cpu_fraction)
+        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": o.lib().orc_num_threads(), "kind": "port",
+               "sample": f"{a.cpu_fraction:.4f} of the class representatives of every BSE/SDE-L kernel, extrapolated linearly; K3, real-space SDE, U^2 in full",
+               "s_per_iteration": sec, "parts_s": {k: round(v, 3) for k, v in parts.items()}}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W, "ms_per_step": ms / a.steps,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex)", "data": "synthetic",
+               "config": {"workload": workload_name(a), "l2": "inputs larger than L2: 4 bubbles x %.0f MB + hoisted right factor %.0f MB per channel are streamed every step" % (S.length_F() * 0 + 16e-6 * np.prod(S._shpΠ), 16e-6 * np.prod(S._shpΠ)),
+                          "symmetry_classes": {"K1": S.num_classes(fd._lib.SG_K1), "K2pp": n2cls[0], "K2ph": n2cls[1], "K3pp": S.num_classes(fd._lib.SG_PP3), "K3ph": S.num_classes(fd._lib.SG_PH3)},
+                          "parallelism": f"class representatives sharded over {world} rank(s), NCCL all-gather per kernel" if world > 1 else "1 GPU"},
+               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(nF * 16), "d2h_bytes_per_step": int(nF * 16 + S.Σ.size * 16), "ms_per_step": ms_e2e / a.steps},
+               "gpu_launches": int(launches), "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
+        print(json.dumps(out))
+    S.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
