@@ -30,7 +30,7 @@ EXPORTS = [
     "fdga_set_vertex", "fdga_get_vertex", "fdga_set_core", "fdga_set_green", "fdga_get_green",
     "fdga_set_bubble", "fdga_get_bubble", "fdga_set_cache", "fdga_get_cache", "fdga_get_L",
     "fdga_set_symmetry_classes", "fdga_build_symmetry_group", "fdga_length_F", "fdga_flatten_F",
-    "fdga_unflatten_F", "fdga_dyson", "fdga_occupation", "fdga_bubbles_real_space",
+    "fdga_unflatten_F", "fdga_stash_F", "fdga_unstash_F", "fdga_dyson", "fdga_occupation", "fdga_bubbles_real_space",
     "fdga_bubbles_momentum_space", "fdga_build_K3_cache", "fdga_bse_L_K2", "fdga_bse_L_K3", "fdga_bse_K1",
     "fdga_bse_K2", "fdga_bse_K3", "fdga_set_F_from_Fbuff", "fdga_sde", "fdga_iterate_solver",
     "fdga_mfrg_matvec", "fdga_profile_enable", "fdga_profile_reset", "fdga_kernel_time_ms",
@@ -87,6 +87,8 @@ def load():
     lib.fdga_length_F.argtypes = [vp]
     lib.fdga_flatten_F.argtypes = [vp, vp]
     lib.fdga_unflatten_F.argtypes = [vp, vp, dbl]
+    lib.fdga_stash_F.argtypes = [vp]
+    lib.fdga_unstash_F.argtypes = [vp]
     lib.fdga_dyson.argtypes = [vp]
     lib.fdga_occupation.argtypes = [vp, i32, C.POINTER(dbl)]
     lib.fdga_bubbles_real_space.argtypes = [vp, i32]

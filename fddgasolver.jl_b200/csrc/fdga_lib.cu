@@ -68,6 +68,7 @@ struct fdga_ctx {
     C* GR; C* GRm; C* SigR; C* SigTmp; C* SigAcc;  // G-sized scratch
     C* flat; size_t lenFlat;                       // flatten staging (device)
     C* flat2;
+    C* stash;                                      // fdga_stash_F / fdga_unstash_F
     double* d_occ;
     SymGroup sg[FDGA_SG_COUNT];
     // multi-GPU
@@ -302,7 +303,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     CKC(cudaMalloc(&ctx->GR, ctx->lenG * sizeof(C))); CKC(cudaMalloc(&ctx->GRm, ctx->lenG * sizeof(C)));
     CKC(cudaMalloc(&ctx->SigR, ctx->lenG * sizeof(C))); CKC(cudaMalloc(&ctx->SigTmp, ctx->lenG * sizeof(C))); CKC(cudaMalloc(&ctx->SigAcc, ctx->lenG * sizeof(C)));
     ctx->lenFlat = 3 * (ctx->lev[0].len[0] + ctx->lev[0].len[1] + ctx->lev[0].len[2]);
-    CKC(cudaMalloc(&ctx->flat, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->flat2, ctx->lenFlat * sizeof(C)));
+    CKC(cudaMalloc(&ctx->flat, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->flat2, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->stash, ctx->lenFlat * sizeof(C)));
     CKC(cudaMalloc(&ctx->d_occ, sizeof(double)));
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; }
     CKC(cudaStreamSynchronize(ctx->stream));
@@ -322,7 +323,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
     cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->Rt); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB);
     cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
-    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->d_occ);
+    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ);
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); cudaFree(s.d_repvals); }
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     cudaStreamDestroy(ctx->stream);
@@ -508,6 +509,8 @@ static int unflatten_dev(fdga_ctx* ctx, LevelBuf& lb, const C* src, double scale
     lb.sw_dirty = true;
     return 0;
 }
+int fdga_stash_F(fdga_ctx* ctx) { CK(cudaSetDevice(ctx->device)); return flatten_dev(ctx, ctx->lev[0], ctx->stash); }
+int fdga_unstash_F(fdga_ctx* ctx) { CK(cudaSetDevice(ctx->device)); return unflatten_dev(ctx, ctx->lev[0], ctx->stash, 1.0); }
 int fdga_unflatten_F(fdga_ctx* ctx, const fdga_c64* host_x, double scale) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->flat, host_x, ctx->lenFlat * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));

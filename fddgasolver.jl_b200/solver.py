@@ -245,6 +245,35 @@ class NL2_ParquetSolver:
         self._call("fdga_unflatten_F", L.ptr(x), float(scale))
         self.sync()
 
+    def unflatten_F_async(self, x, scale=1.0):
+        """unflatten!(S.F, x * scale) without a host synchronisation (x must stay alive, ideally pinned)"""
+        assert x.dtype == np.complex128 and x.size == self.length_F()
+        self._call("fdga_unflatten_F", L.ptr(x), float(scale))
+
+    def stash_F(self):
+        self._call("fdga_stash_F")
+
+    def unstash_F(self):
+        self._call("fdga_unstash_F")
+
+    def get_green_into(self, name, out):
+        self._call("fdga_get_green", _G_NAMES[name], L.ptr(out), out.size)
+
+    # ------------------------------------------------------------------ multi-GPU (one process per GPU)
+    def comm_unique_id(self):
+        """128-byte ncclUniqueId (call on rank 0, broadcast with the host's own transport)"""
+        uid = np.zeros(128, dtype=np.uint8)
+        rc = self._lib.fdga_comm_unique_id(L.ptr(uid))
+        if rc != 0:
+            raise L.FdgaError("fdga_comm_unique_id failed: " + self._lib.fdga_last_error(None).decode())
+        return uid
+
+    def comm_init(self, nranks, rank, uid):
+        uid = np.ascontiguousarray(uid, dtype=np.uint8)
+        assert uid.size == 128
+        self._call("fdga_comm_init", int(nranks), int(rank), L.ptr(uid))
+        self.nranks, self.rank = int(nranks), int(rank)
+
     # ------------------------------------------------------------------ profiling
     def profile(self, on=True):
         self._call("fdga_profile_enable", int(on))

@@ -113,7 +113,10 @@ int  fdga_build_symmetry_group(int which_sg, int n0, int n1, int nq, int64_t* of
 /* flatten(S.F) / unflatten!(S.F, x*scale): src/vertex.jl:153-195, src/channel.jl:155-210 */
 int64_t fdga_length_F(fdga_ctx*);
 int  fdga_flatten_F(fdga_ctx*, fdga_c64* host_y);
-int  fdga_unflatten_F(fdga_ctx*, const fdga_c64* host_x, double scale);
+int  fdga_unflatten_F(fdga_ctx*, const fdga_c64* host_x, double scale);   /* asynchronous on the context stream */
+/* device-resident copy of S.F (copy(S.F) / set!(S.F, copy)): lets a caller restart iterations without host traffic */
+int  fdga_stash_F(fdga_ctx*);
+int  fdga_unstash_F(fdga_ctx*);
 
 /* ---- kernels: one per reference function ---------------------------------------------- */
 /* Dyson!(S): src/dyson.jl:20-31 */
