@@ -1,0 +1,284 @@
+// fdga_column.cuh -- "column" kernels: the optimised form of the full-momentum gather contractions
+//   BSE_K2! (fd / mfRG)   src/nonlocal_2/BSEa/BSEa_K2.jl:72-125
+//   BSE_L_K2!             src/nonlocal_2/BSEa/BSEa_K2.jl:17-43
+//   SDE_channel_L_pp!/ph! src/nonlocal_2/SDE.jl:16-33, 54-73
+//
+// All four have the shape  out[W,nu,P,k] = scale * sum_{w,q} L(nu,k; w,q) * R[w,q | W,P]  with a left factor L made of
+// vertex evaluations.  Work decomposition:
+//   * one CTA per output COLUMN (W, P, k) holding up to NV class representatives (different nu);
+//   * one thread per inner momentum q (and a contiguous chunk of inner frequencies w): every momentum conversion /
+//     Brillouin-zone fold / table base offset is computed ONCE per (column, q) and kept in registers, so the innermost
+//     loops over (w, nu) only do Matsubara box tests and gathers at fixed momenta;
+//   * momentum-independent levels of the F0 chain (local Vertex, RefVertex core) are pre-tabulated per (W, nu, w)
+//     by loc_table_kernel with the generic evaluator and enter as one cached load per term;
+//   * the own-channel nu -> infinity differences are taken analytically (K2[W,nu,P,k] + K3[W,nu,w,P] inside the boxes)
+//     instead of evaluating F twice (the reference's (F(nu) - F(inf)) differs from this by rounding only).
+#pragma once
+#include "fdga_kernels.cuh"
+
+namespace fdga {
+
+#define FDGA_NV 8    // representatives (nu values) per column chunk
+
+enum { JOB_K2 = 0, JOB_K2_MF = 1, JOB_LK2 = 2, JOB_SDE_PP = 3, JOB_SDE_PH = 4 };
+
+struct ColDev {                 // columns of class representatives, built on the host (fdga_lib.cu: build_columns)
+    int ncol;
+    const int* iW;              // position of W in the OUTPUT (K2) bosonic mesh
+    const int* iP;
+    const int* ik;
+    const int* start;           // ncol + 1
+    const int* rep_inu;         // position of nu in the K2 fermionic mesh
+    const int* rep_cls;         // class id (slot in repvals)
+};
+
+struct ColJob {
+    int lev_first;              // K2 / LK2: first level of the left chain; SDE: the level l of the recursion
+    int n_nl2;                  // number of leading NL2 levels in the chain
+    int own_only;               // SDE: SURVEY-E2 toggle
+    int nw, Ninner;             // inner frequency mesh (count, N)
+    int slabW_N;                // bosonic mesh N used to index the R slab ([w + nw*(q + NP*(posB(W) + nB*iP))])
+    double scale_re, scale_im;  // complex prefactor applied at the end
+};
+
+struct MomOff { int oK1, oK2A, oK2B, oK3; };
+
+__device__ __forceinline__ int fold1(int a, int L) {   // a in (-3L, 3L)
+    a += (a < 0) ? L : 0; a += (a < 0) ? L : 0; a += (a < 0) ? L : 0;
+    a -= (a >= L) ? L : 0; a -= (a >= L) ? L : 0; a -= (a >= L) ? L : 0;
+    return a;
+}
+__device__ __forceinline__ int foldidx(int x, int y, int L) { return fold1(x, L) + L * fold1(y, L); }
+
+// offsets of the frequency sub-arrays of channel r of level lv at momenta converted from `form` to r
+__device__ __forceinline__ MomOff mom_offsets(const DevLevel& lv, int form, int r, int L, int NP,
+                                              int Px, int Py, int kx, int ky, int qx, int qy) {
+    Arg a; a.W = 0; a.v = 0; a.w = 0; a.Px = Px; a.Py = Py; a.kx = kx; a.ky = ky; a.qx = qx; a.qy = qy;
+    Arg b = convert(a, form, r);
+    int iP = foldidx(b.Px, b.Py, L), ik = foldidx(b.kx, b.ky, L), iq = foldidx(b.qx, b.qy, L);
+    int nB2 = 2 * lv.nK2b - 1, nF2 = 2 * lv.nK2f, nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
+    MomOff m;
+    m.oK1 = (2 * lv.nK1 - 1) * iP;
+    m.oK2A = nB2 * nF2 * (iP + NP * ik);
+    m.oK2B = nB2 * nF2 * (iP + NP * iq);
+    m.oK3 = nB3 * nF3 * nF3 * iP;
+    return m;
+}
+// gamma_r at fixed momenta, all K switches on; v, w finite (same box logic as nl2_chan)
+__device__ __forceinline__ C chan_off(const DevLevel& lv, int r, const MomOff& m, int W, int v, int w) {
+    C val = zeroC();
+    if (!inB(W, lv.nK1)) return val;
+    const DevChan& c = lv.ch[r];
+    val += ldg(c.K1 + m.oK1 + posB(W, lv.nK1));
+    if (!inB(W, lv.nK2b)) return val;
+    const bool a = inF(v, lv.nK2f), b = inF(w, lv.nK2f);
+    const int nB = 2 * lv.nK2b - 1;
+    const int pW = posB(W, lv.nK2b);
+    if (a) val += ldg(c.K2 + m.oK2A + pW + nB * posF(v, lv.nK2f));
+    if (b) val += ldg(c.K2 + m.oK2B + pW + nB * posF(w, lv.nK2f));
+    if (a && b && inB(W, lv.nK3b) && inF(v, lv.nK3f) && inF(w, lv.nK3f)) {
+        const int nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
+        val += ldg(c.K3 + m.oK3 + posB(W, lv.nK3b) + nB3 * (posF(v, lv.nK3f) + nF3 * posF(w, lv.nK3f)));
+    }
+    return val;
+}
+// gamma_r(W, v, w) - gamma_r(W, inf, w) at fixed momenta: K2[W,v,P,k] + K3[W,v,w,P] inside the boxes
+__device__ __forceinline__ C chan_off_diff_v(const DevLevel& lv, int r, const MomOff& m, int W, int v, int w) {
+    C val = zeroC();
+    if (!inB(W, lv.nK2b) || !inF(v, lv.nK2f)) return val;     // K2 Omega-box is inside the K1 box
+    const DevChan& c = lv.ch[r];
+    const int nB = 2 * lv.nK2b - 1;
+    val += ldg(c.K2 + m.oK2A + posB(W, lv.nK2b) + nB * posF(v, lv.nK2f));
+    if (inF(w, lv.nK2f) && inB(W, lv.nK3b) && inF(v, lv.nK3f) && inF(w, lv.nK3f)) {
+        const int nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
+        val += ldg(c.K3 + m.oK3 + posB(W, lv.nK3b) + nB3 * (posF(v, lv.nK3f) + nF3 * posF(w, lv.nK3f)));
+    }
+    return val;
+}
+
+// frequency part of _convert_channel (no momenta)
+__device__ __forceinline__ void convert_freq(int W, int v, int w, int from, int to, int& W2, int& v2, int& w2) {
+    Arg a; a.W = W; a.v = v; a.w = w; a.Px = a.Py = a.kx = a.ky = a.qx = a.qy = 0;
+    Arg b = convert(a, from, to);
+    W2 = b.W; v2 = b.v; w2 = b.w;
+}
+
+// forms (channel parametrisations evaluated in parallel spin) and their weights:
+//   K2 / LK2 jobs: p -> {(p,1)}, a -> {(a,1)}, t (dSp = 2 pSp + xSp, xSp(t) = -a-form) -> {(t,2),(a,-1)}
+//   SDE pp -> {(p,1)} ; SDE ph -> {(a,1),(t,1)}
+template <int KIND, int CH> struct Forms;
+template <int KIND> struct Forms<KIND, CH_P> { static constexpr int n = 1; __device__ static int ch(int) { return CH_P; } __device__ static double coef(int) { return 1.0; } };
+template <int KIND> struct Forms<KIND, CH_A> { static constexpr int n = 1; __device__ static int ch(int) { return CH_A; } __device__ static double coef(int) { return 1.0; } };
+template <int KIND> struct Forms<KIND, CH_T> { static constexpr int n = 2; __device__ static int ch(int i) { return i == 0 ? CH_T : CH_A; } __device__ static double coef(int i) { return i == 0 ? 2.0 : -1.0; } };
+template <> struct Forms<JOB_SDE_PH, CH_A> { static constexpr int n = 2; __device__ static int ch(int i) { return i == 0 ? CH_A : CH_T; } __device__ static double coef(int) { return 1.0; } };
+
+// map (output nu, inner w) -> vertex frequency arguments (v, w) of the job
+template <int KIND, int CH>
+__device__ __forceinline__ void job_freq_args(int W, int nu, int win, int& v, int& w) {
+    if (KIND == JOB_K2 || KIND == JOB_SDE_PH) { v = nu; w = win; }
+    else if (KIND == JOB_K2_MF || KIND == JOB_LK2) { v = nu; w = (CH == CH_P) ? W - win - 1 : win; }
+    else { v = W - win - 1; w = nu; }                                   // JOB_SDE_PP: F(W, W - w, nu, ...)
+}
+
+// ---- momentum-independent part of the left factor, tabulated per (W, nu, w) -----------------------------------
+// T[iw + nw*(inu + nF2*iWo)]  (W on the output K2 bosonic mesh, nu on the output K2 fermionic mesh)
+template <int KIND, int CH>
+__global__ void loc_table_kernel(const __grid_constant__ DevChain V, ColJob job, Grid g, C* __restrict__ T) {
+    typedef Forms<KIND, CH> FM;
+    const int nB2 = 2 * g.nK2b - 1, nF2 = 2 * g.nK2f;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long n = (long long)job.nw * nF2 * nB2;
+    if (i >= n) return;
+    int iw = i % job.nw; int inu = (i / job.nw) % nF2; int iWo = i / ((long long)job.nw * nF2);
+    int W = iWo - (g.nK2b - 1), nu = inu - g.nK2f, win = iw - job.Ninner;
+    Arg a; a.W = W; a.Px = a.Py = a.kx = a.ky = a.qx = a.qy = 0;
+    job_freq_args<KIND, CH>(W, nu, win, a.v, a.w);
+    C val = zeroC();
+    const int lloc = job.n_nl2;                     // first momentum-independent level of the chain
+#pragma unroll
+    for (int f = 0; f < FM::n; ++f) {
+        const int form = FM::ch(f);
+        C x = zeroC();
+        if (KIND == JOB_K2 || KIND == JOB_K2_MF) {
+            if (lloc < V.nlev) {
+                Arg ai = a; ai.v = FDGA_INF;
+                x = eval_vertex<false>(V, max(lloc, job.lev_first), form, SP_P, a, FL_ALL) - eval_vertex<false>(V, max(lloc, job.lev_first), form, SP_P, ai, FL_ALL);
+            }
+        } else if (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH) {
+            const int l = job.lev_first;
+            const DevLevel& lv = V.lev[l];
+            if (lv.type == LV_CORE) {
+                x = core_eval(lv, form, SP_P, a.W, a.v, a.w) - lv.U;
+            } else {
+                if (lv.type == LV_LOCAL) x += loc_chan(lv, form, a.W, a.v, a.w);
+                if (!job.own_only && l + 1 < V.nlev && V.lev[l + 1].type == LV_LOCAL) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) if (r != form) { Arg b = convert(a, form, r); x += loc_chan(V.lev[l + 1], r, b.W, b.v, b.w); }
+                }
+            }
+        }
+        val += x * FM::coef(f);
+    }
+    T[i] = val;
+}
+
+// ---- the column kernel -----------------------------------------------------------------------------------------
+template <int KIND, int CH>
+__global__ void __launch_bounds__(128)
+column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const C* __restrict__ R, const C* __restrict__ T,
+              C* __restrict__ repvals, Grid g) {
+    typedef Forms<KIND, CH> FM;
+    constexpr int NV = FDGA_NV;
+    const int col = blockIdx.x;
+    const int iW = cols.iW[col], iP = cols.iP[col], ik = cols.ik[col];
+    const int r0 = cols.start[col], nrep = cols.start[col + 1] - r0;
+    const int W = iW - (g.nK2b - 1);
+    const int L = g.L, NP = g.NP;
+    const int Px = iP % L, Py = iP / L, kx = ik % L, ky = ik / L;
+    const int nw = job.nw;
+    const int nF2 = 2 * g.nK2f;
+    int nus[NV];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) nus[n] = (n < nrep) ? cols.rep_inu[r0 + n] - g.nK2f : 0;
+    const C* slab = R + (size_t)nw * NP * (posB(W, job.slabW_N) + (size_t)(2 * job.slabW_N - 1) * iP);
+    const C* Tw = T + (size_t)nw * nF2 * iW;
+    C acc[NV];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) acc[n] = zeroC();
+
+    // w is split in WS chunks so that small momentum meshes still fill the CTA
+    int WS = 1;
+    while (NP * WS * 2 <= (int)blockDim.x && WS * 2 <= nw) WS *= 2;
+    const int wchunk = (nw + WS - 1) / WS;
+    const int l0 = job.lev_first;
+
+    for (int item = threadIdx.x; item < NP * WS; item += blockDim.x) {
+        const int iq = item / WS, ws = item % WS;
+        const int qx = iq % L, qy = iq / L;
+        const int w_lo = ws * wchunk, w_hi = min(nw, w_lo + wchunk);
+        // momentum arguments of the vertex for this (k, q)
+        int akx, aky, aqx, aqy;
+        if (KIND == JOB_K2 || KIND == JOB_SDE_PH) { akx = kx; aky = ky; aqx = qx; aqy = qy; }
+        else if (KIND == JOB_K2_MF || KIND == JOB_LK2) { akx = kx; aky = ky; aqx = (CH == CH_P) ? Px - qx : qx; aqy = (CH == CH_P) ? Py - qy : qy; }
+        else { akx = Px - qx; aky = Py - qy; aqx = kx; aqy = ky; }              // SDE pp: (P, P - q, k)
+        const C* Rq = slab + (size_t)nw * iq;
+
+#pragma unroll
+        for (int f = 0; f < FM::n; ++f) {
+            const int form = FM::ch(f);
+            const double cf = FM::coef(f);
+            // which pieces come from which NL2 level:
+            //   K2 jobs : every leading NL2 level of the left chain: cross channels + own-channel (nu - inf) difference
+            //   L_K2    : level l0 only, cross channels only (F0 = false, own gamma off)
+            //   SDE     : own gamma of level l0 in full + cross channels of level l0 + 1 ("as coded")
+            const bool is_sde = (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH);
+            const int l_end = (KIND == JOB_LK2) ? l0 + 1 : (is_sde ? min(l0 + 2, job.n_nl2) : job.n_nl2);
+            for (int l = l0; l < l_end; ++l) {
+                const DevLevel& lv = V.lev[l];
+                bool do_own_full = false, do_own_diff = false, do_cross = false;
+                if (KIND == JOB_K2 || KIND == JOB_K2_MF) { do_own_diff = true; do_cross = true; }
+                else if (KIND == JOB_LK2) { do_cross = true; }
+                else {
+                    if (l == l0) do_own_full = true;
+                    else { do_cross = !job.own_only; if (!do_cross) break; }
+                }
+                MomOff mo[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) mo[r] = mom_offsets(lv, form, r, L, NP, Px, Py, akx, aky, aqx, aqy);
+                for (int iw = w_lo; iw < w_hi; ++iw) {
+                    const C Rv = Rq[iw] * cf;
+                    const int win = iw - job.Ninner;
+#pragma unroll
+                    for (int n = 0; n < NV; ++n) {
+                        if (n >= nrep) break;
+                        int v, w; job_freq_args<KIND, CH>(W, nus[n], win, v, w);
+                        C val = zeroC();
+                        if (do_cross) {
+#pragma unroll
+                            for (int r = 0; r < 3; ++r) {
+                                if (r == form) continue;
+                                int W2, v2, w2; convert_freq(W, v, w, form, r, W2, v2, w2);
+                                val += chan_off(lv, r, mo[r], W2, v2, w2);
+                            }
+                        }
+                        if (do_own_diff) val += chan_off_diff_v(lv, form, mo[form], W, v, w);
+                        if (do_own_full) val += chan_off(lv, form, mo[form], W, v, w);
+                        acc[n] += val * Rv;
+                    }
+                }
+            }
+        }
+        // momentum-independent levels (pre-tabulated, forms and weights already folded in)
+        if (T != nullptr) {
+            for (int iw = w_lo; iw < w_hi; ++iw) {
+                const C Rv = Rq[iw];
+#pragma unroll
+                for (int n = 0; n < NV; ++n) {
+                    if (n >= nrep) break;
+                    acc[n] += ldg(Tw + iw + nw * (nus[n] + g.nK2f)) * Rv;
+                }
+            }
+        }
+    }
+
+    // block reduction of the NV accumulators
+    __shared__ double red[NV][2][4];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int n = 0; n < NV; ++n) {
+        double x = acc[n].x, y = acc[n].y;
+        for (int o = 16; o > 0; o >>= 1) { x += __shfl_down_sync(0xffffffffu, x, o); y += __shfl_down_sync(0xffffffffu, y, o); }
+        if (lane == 0) { red[n][0][wid] = x; red[n][1][wid] = y; }
+    }
+    __syncthreads();
+    if (threadIdx.x < nrep) {
+        const int n = threadIdx.x;
+        const int nwarp = blockDim.x >> 5;
+        double x = 0.0, y = 0.0;
+        for (int i = 0; i < nwarp; ++i) { x += red[n][0][i]; y += red[n][1][i]; }
+        C s = mkC(job.scale_re, job.scale_im);
+        repvals[cols.rep_cls[r0 + n]] = mkC(x, y) * s;
+    }
+}
+
+}  // namespace fdga

@@ -94,16 +94,18 @@ __global__ void symmetrize_kernel(C* __restrict__ f, SymDev sg) {
     f[sg.index[j]] = apply_op(sg.ops[j], f[sg.index[rep]]);
 }
 
-// ---- s-wave tables (src/nonlocal/swave.jl:32-136): BZ means of one NL2 channel --------------------
-__global__ void swave_tables_kernel(DevLevel lv, int r, int NP, C* K1sw, C* K2swk, C* K2sww, C* K3sw) {
+// ---- s-wave tables (src/nonlocal/swave.jl:32-136): BZ means of the three channels of one NL2 level --------------
+struct SwOut { C* p[3][4]; };    // [channel][K1sw, K2swk, K2sww, K3sw]
+__global__ void swave_tables_kernel(DevLevel lv, int NP, SwOut out) {
+    const int r = blockIdx.y;
     const DevChan& c = lv.ch[r];
     int nB1 = 2 * lv.nK1 - 1, nB2 = 2 * lv.nK2b - 1, nF2 = 2 * lv.nK2f, nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
-    long long n1 = nB1, n2k = (long long)nB2 * nF2 * NP, n2w = (long long)nB2 * nF2, n3 = (long long)nB3 * nF3 * nF3;
+    long long n1 = nB1, n2k = (long long)nB2 * nF2 * NP, n3 = (long long)nB3 * nF3 * nF3;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n1) {
         C s = zeroC();
         for (int p = 0; p < NP; ++p) s += c.K1[i + (size_t)nB1 * p];
-        K1sw[i] = s / (double)NP;
+        out.p[r][0][i] = s / (double)NP;
         return;
     }
     i -= n1;
@@ -111,23 +113,26 @@ __global__ void swave_tables_kernel(DevLevel lv, int r, int NP, C* K1sw, C* K2sw
         C s = zeroC();
         size_t sk = (size_t)nB2 * nF2 * NP;
         for (int k = 0; k < NP; ++k) s += c.K2[i + sk * k];
-        K2swk[i] = s / (double)NP;
+        out.p[r][1][i] = s / (double)NP;
         return;
     }
     i -= n2k;
-    if (i < n2w) {      // sum(view(f, i1, i2, :, :)) / N3 / N4
-        C s = zeroC();
-        size_t sP = (size_t)nB2 * nF2;
-        for (long long pk = 0; pk < (long long)NP * NP; ++pk) s += c.K2[i + sP * pk];
-        K2sww[i] = s / (double)NP / (double)NP;
-        return;
-    }
-    i -= n2w;
     if (i < n3) {
         C s = zeroC();
         for (int p = 0; p < NP; ++p) s += c.K3[i + (size_t)n3 * p];
-        K3sw[i] = s / (double)NP;
+        out.p[r][3][i] = s / (double)NP;
     }
+}
+// K2[W, v, kSW, kSW] = sum(view(f, i1, i2, :, :)) / N3 / N4, taken as the P-mean of the k-means (differs by rounding only)
+__global__ void swave_tables2_kernel(DevLevel lv, int NP, SwOut out) {
+    const int r = blockIdx.y;
+    int nB2 = 2 * lv.nK2b - 1, nF2 = 2 * lv.nK2f;
+    long long n2w = (long long)nB2 * nF2;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n2w) return;
+    C s = zeroC();
+    for (int p = 0; p < NP; ++p) s += out.p[r][1][i + n2w * p];
+    out.p[r][2][i] = s / (double)NP;
 }
 
 // ---- bubble auxiliaries: PiT[w,q,W,P] (slab-contiguous copy) and Pisw[W,w,P] = mean_k Pi[W,w,P,k] ----
@@ -528,42 +533,48 @@ __global__ void hartree_kernel(C* __restrict__ Sigma, const double* occ, C U, do
 }
 
 // ---- real-space contraction of SDE_compute!: src/nonlocal_2/SDE.jl:200-250 -----------------------------
-// SigR[v, tx, ty] (nSf x LS x LS) = T * sum_{R,Rp} [R+Rp == t] G_R(W-v; -R) Lpp_R[W,v,R,Rp] w + [-R+Rp == t] G_R(W+v; -R) Lph_R w
+// SigR[v, tx, ty] (nSf x LS x LS, pre-zeroed) = T * sum_{R,Rp in [-h,h]^2} w(R,Rp) *
+//     ( [R+Rp == t mod LS] G_R(W-v; -R) Lpp_R[W,v,R,Rp] + [-R+Rp == t mod LS] G_R(W+v; -R) Lph_R[W,v,R,Rp] )
+// One thread per (v on the K2 mesh, t); Rp enumerated by congruence instead of scanning all (R, Rp) pairs.
 __global__ void sde_rs_kernel(const C* __restrict__ GR, const C* __restrict__ LppR, const C* __restrict__ LphR,
                               C* __restrict__ SigR, Grid g, int nSig, int LS) {
     const int L = g.L, h = L / 2, LG = g.LG, nB = 2 * g.nK2b - 1, nF = 2 * g.nK2f, nSf = 2 * nSig;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long n = (long long)nSf * LS * LS;
+    long long n = (long long)nF * LS * LS;
     if (i >= n) return;
-    int is = i % nSf; int tx = (i / nSf) % LS, ty = (i / nSf) / LS;
-    int v = is - nSig;
+    int iv = i % nF; int tx = (i / nF) % LS, ty = (i / nF) / LS;
+    int v = iv - g.nK2f;
+    if (!inF(v, nSig)) return;
     C acc = zeroC();
-    if (inF(v, g.nK2f)) {
-        int iv = posF(v, g.nK2f);
-        size_t pre = (size_t)nB * nF;
-        for (int R2 = -h; R2 <= h; ++R2) for (int R1 = -h; R1 <= h; ++R1) {
-            int gx = modL(-R1, LG), gy = modL(-R2, LG);
-            int iRL = modL(R1, L) + L * modL(R2, L);
-            for (int Rp2 = -h; Rp2 <= h; ++Rp2) for (int Rp1 = -h; Rp1 <= h; ++Rp1) {
-                bool mpp = modL(R1 + Rp1, LS) == tx && modL(R2 + Rp2, LS) == ty;
-                bool mph = modL(-R1 + Rp1, LS) == tx && modL(-R2 + Rp2, LS) == ty;
-                if (!mpp && !mph) continue;
-                double wgt = 1.0;
-                if (L % 2 == 0) {
-                    if (abs(Rp1) == L / 2) wgt /= 2; if (abs(Rp2) == L / 2) wgt /= 2;
-                    if (abs(R1) == L / 2) wgt /= 2;  if (abs(R2) == L / 2) wgt /= 2;
-                }
-                int iRpL = modL(Rp1, L) + L * modL(Rp2, L);
-                size_t lbase = pre * (iRL + (size_t)g.NP * iRpL) + (size_t)nB * iv;
+    const size_t pre = (size_t)nB * nF;
+    const bool even = (L % 2 == 0);
+    for (int R2 = -h; R2 <= h; ++R2) for (int R1 = -h; R1 <= h; ++R1) {
+        const int gx = modL(-R1, LG), gy = modL(-R2, LG);
+        const int iRL = modL(R1, L) + L * modL(R2, L);
+        double wR = 1.0;
+        if (even) { if (abs(R1) == h) wR *= 0.5; if (abs(R2) == h) wR *= 0.5; }
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+            // pp: Rp = t - R ; ph: Rp = t + R  (mod LS), restricted to [-h, h]
+            int c1 = modL(ph ? tx + R1 : tx - R1, LS), c2 = modL(ph ? ty + R2 : ty - R2, LS);
+            while (c1 > h) c1 -= LS;
+            while (c2 > h) c2 -= LS;
+            while (c1 + LS <= h) c1 += LS;      // start from the largest representative <= h (only matters for LS <= h)
+            while (c2 + LS <= h) c2 += LS;
+            for (int Rp2 = c2; Rp2 >= -h; Rp2 -= LS) for (int Rp1 = c1; Rp1 >= -h; Rp1 -= LS) {
+                double wgt = wR;
+                if (even) { if (abs(Rp1) == h) wgt *= 0.5; if (abs(Rp2) == h) wgt *= 0.5; }
+                const int iRpL = modL(Rp1, L) + L * modL(Rp2, L);
+                const size_t lbase = pre * (iRL + (size_t)g.NP * iRpL) + (size_t)nB * iv;
+                const C* Lr = ph ? LphR : LppR;
                 for (int iW = 0; iW < nB; ++iW) {
-                    int W = iW - (g.nK2b - 1);
-                    if (mpp) acc += gr_call(GR, g.nG, LG, W - v - 1, gx, gy) * LppR[lbase + iW] * wgt;
-                    if (mph) acc += gr_call(GR, g.nG, LG, W + v, gx, gy) * LphR[lbase + iW] * wgt;
+                    const int W = iW - (g.nK2b - 1);
+                    acc += gr_call(GR, g.nG, LG, ph ? W + v : W - v - 1, gx, gy) * Lr[lbase + iW] * wgt;
                 }
             }
         }
     }
-    SigR[i] = acc * g.T;
+    SigR[posF(v, nSig) + (size_t)nSf * (tx + (size_t)LS * ty)] = acc * g.T;
 }
 
 // ---- SDE_U2_using_G: src/nonlocal/SDE.jl:421-438.  One thread per (nu, R) ----------------------------

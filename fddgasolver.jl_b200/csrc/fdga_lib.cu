@@ -2,13 +2,14 @@
 // Reference call structure being replaced: iterate_solver! (src/solve.jl:4-116), BSE_templates.jl:12-180,
 // SDE! (src/SDE.jl:3-48), mfRGLinearMap (src/mfRG.jl:34-89).
 #include "../../include/fdga.h"
-#include "fdga_kernels.cuh"
+#include "fdga_column.cuh"
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <dlfcn.h>
 
 using namespace fdga;
@@ -35,7 +36,9 @@ struct SymGroup {
     int* d_member_class;
     C* d_repvals;         // padded to chunk * nranks
     long long chunk;
-    std::vector<long long> h_offsets;
+    std::vector<long long> h_offsets, h_index;
+    // columns (W, P, k) of this rank's class representatives (K2-shaped groups only)
+    int ncol; int *d_col_iW, *d_col_iP, *d_col_ik, *d_col_start, *d_rep_inu, *d_rep_cls;
 };
 struct TimedEvent { cudaEvent_t a, b; int cat; };
 
@@ -78,6 +81,9 @@ struct fdga_ctx {
     double t_ms[FDGA_T_COUNT]; long long n_launch[FDGA_T_COUNT]; long long total_launches;
     int cur_cat; cudaEvent_t cur_a;
     int opt_sde_own_gamma;   // FDGA_OPT_SDE_OWN_GAMMA
+    int opt_generic;         // FDGA_OPT_GENERIC_KERNELS
+    int n_nl2;               // leading NL2 levels of the F chain
+    C* Ttab;                 // momentum-independent left-factor table [nw, nF2, nB2]
     std::string err;
 };
 
@@ -178,15 +184,17 @@ static C bareU(fdga_ctx* ctx) { const fdga_level_desc& d = ctx->lev[ctx->nlev - 
 // ------------------------------------------------------------------------------------------------
 // auxiliaries kept current lazily
 static int refresh_swave(fdga_ctx* ctx) {
-    for (int l = 0; l <= ctx->nlev; l++) {
-        LevelBuf& lb = (l == ctx->nlev) ? ctx->FL : ctx->lev[l];
+    for (int l = 0; l < ctx->nlev; l++) {          // S.FL is never evaluated at kSW: its tables are not needed
+        LevelBuf& lb = ctx->lev[l];
         if (lb.d.type != FDGA_LV_NL2 || !lb.sw_dirty) continue;
         Scope sc(ctx, FDGA_T_SWAVE);
         DevLevel dl = dev_level(lb);
-        long long n = (long long)(2 * lb.d.nK1 - 1) + (long long)(2 * lb.d.nK2[0] - 1) * (2 * lb.d.nK2[1]) * (ctx->g.NP + 1)
+        SwOut out; for (int ch = 0; ch < 3; ch++) for (int j = 0; j < 4; j++) out.p[ch][j] = lb.sw[ch][j];
+        long long n = (long long)(2 * lb.d.nK1 - 1) + (long long)(2 * lb.d.nK2[0] - 1) * (2 * lb.d.nK2[1]) * ctx->g.NP
                     + (long long)(2 * lb.d.nK3[0] - 1) * (2 * lb.d.nK3[1]) * (2 * lb.d.nK3[1]);
-        for (int ch = 0; ch < 3; ch++)
-            LAUNCH(FDGA_T_SWAVE, swave_tables_kernel, nblk(n, 128), 128, dl, ch, ctx->g.NP, lb.sw[ch][0], lb.sw[ch][1], lb.sw[ch][2], lb.sw[ch][3]);
+        long long n2 = (long long)(2 * lb.d.nK2[0] - 1) * (2 * lb.d.nK2[1]);
+        LAUNCH(FDGA_T_SWAVE, swave_tables_kernel, dim3(nblk(n, 128), 3), 128, dl, ctx->g.NP, out);
+        LAUNCH(FDGA_T_SWAVE, swave_tables2_kernel, dim3(nblk(n2, 64), 3), 64, dl, ctx->g.NP, out);
         lb.sw_dirty = false;
     }
     CK(cudaGetLastError());
@@ -253,6 +261,45 @@ static int dft4(fdga_ctx* ctx, C* a, C* b, long long pre, int sgn, double scale,
     CK(cudaGetLastError()); return 0;
 }
 
+// group this rank's class representatives of a K2-shaped symmetry group into columns (W, P, k) of <= FDGA_NV reps
+static int build_columns(fdga_ctx* ctx, SymGroup& s) {
+    cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls);
+    s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = nullptr; s.ncol = 0;
+    long long c0 = (long long)ctx->rank * s.chunk, c1 = c0 + s.chunk;
+    if (c0 > s.ncls) c0 = s.ncls; if (c1 > s.ncls) c1 = s.ncls;
+    const int nB2 = 2 * ctx->g.nK2b - 1, nF2 = 2 * ctx->g.nK2f, NP = ctx->g.NP;
+    struct Rep { long long key; int inu; int cls; };
+    std::vector<Rep> reps; reps.reserve(c1 - c0);
+    for (long long c = c0; c < c1; c++) {
+        long long idx = s.h_index[s.h_offsets[c]];
+        int iW = idx % nB2; idx /= nB2; int inu = idx % nF2; idx /= nF2; int iP = idx % NP; int ik = (int)(idx / NP);
+        Rep r; r.key = ((long long)ik * NP + iP) * nB2 + iW; r.inu = inu; r.cls = (int)c;
+        reps.push_back(r);
+    }
+    std::stable_sort(reps.begin(), reps.end(), [](const Rep& a, const Rep& b) { return a.key < b.key; });
+    std::vector<int> ciW, ciP, cik, cstart, rinu, rcls;
+    for (size_t i = 0; i < reps.size();) {
+        size_t j = i;
+        while (j < reps.size() && reps[j].key == reps[i].key && j - i < FDGA_NV) j++;
+        long long key = reps[i].key;
+        ciW.push_back((int)(key % nB2)); key /= nB2; ciP.push_back((int)(key % NP)); cik.push_back((int)(key / NP));
+        cstart.push_back((int)i);
+        i = j;
+    }
+    cstart.push_back((int)reps.size());
+    for (auto& r : reps) { rinu.push_back(r.inu); rcls.push_back(r.cls); }
+    s.ncol = (int)ciW.size();
+    if (s.ncol == 0) return 0;
+    auto up = [&](int*& d, const std::vector<int>& h) -> int {
+        CK(cudaMalloc(&d, h.size() * sizeof(int))); CK(cudaMemcpy(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice)); return 0; };
+    if (up(s.d_col_iW, ciW) || up(s.d_col_iP, ciP) || up(s.d_col_ik, cik) || up(s.d_col_start, cstart) || up(s.d_rep_inu, rinu) || up(s.d_rep_cls, rcls)) return 1;
+    return 0;
+}
+static ColDev col_dev(const SymGroup& s) {
+    ColDev c; c.ncol = s.ncol; c.iW = s.d_col_iW; c.iP = s.d_col_iP; c.ik = s.d_col_ik; c.start = s.d_col_start; c.rep_inu = s.d_rep_inu; c.rep_cls = s.d_rep_cls;
+    return c;
+}
+
 // ================================================================================================
 extern "C" {
 
@@ -267,6 +314,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     if (dims->nlev < 2 || dims->nlev > FDGA_MAX_LEVELS || dims->lev[0].type != FDGA_LV_NL2 || dims->lev[dims->nlev - 1].type != FDGA_LV_CORE) {
         g_create_error = "dims: need lev[0] = NL2 and lev[nlev-1] = CORE, 2 <= nlev <= FDGA_MAX_LEVELS"; return 2; }
     for (int l = 1; l < dims->nlev - 1; l++) if (dims->lev[l].type == FDGA_LV_CORE) { g_create_error = "dims: CORE level must be last"; return 2; }
+    for (int l = 1; l < dims->nlev - 1; l++) if (dims->lev[l].type == FDGA_LV_NL2 && dims->lev[l - 1].type != FDGA_LV_NL2) { g_create_error = "dims: NL2 levels must precede LOCAL levels"; return 2; }
     const fdga_level_desc& d0 = dims->lev[0];
     if (dims->nPiB != d0.nK1) { g_create_error = "dims: bubble bosonic mesh must equal the K1 mesh (nPiB == nK1)"; return 2; }
     if (!(d0.nK1 > d0.nK2[0] && d0.nK1 > d0.nK2[1] && d0.nK2[0] >= d0.nK3[0] && d0.nK2[1] >= d0.nK3[1] && dims->nPiF >= d0.nK2[1])) {
@@ -274,7 +322,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     fdga_ctx* ctx = new fdga_ctx();
     ctx->dims = *dims; ctx->device = device; ctx->nlev = dims->nlev;
     ctx->nranks = 1; ctx->rank = 0; ctx->comm = nullptr; memset(&ctx->nccl, 0, sizeof(ctx->nccl));
-    ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0;
+    ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0; ctx->opt_generic = 0;
     memset(ctx->t_ms, 0, sizeof(ctx->t_ms)); memset(ctx->n_launch, 0, sizeof(ctx->n_launch));
     Grid& g = ctx->g;
     g.T = dims->T; g.L = dims->nq; g.NP = dims->nq * dims->nq; g.nPiB = dims->nPiB; g.nPiF = dims->nPiF;
@@ -305,7 +353,9 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     ctx->lenFlat = 3 * (ctx->lev[0].len[0] + ctx->lev[0].len[1] + ctx->lev[0].len[2]);
     CKC(cudaMalloc(&ctx->flat, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->flat2, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->stash, ctx->lenFlat * sizeof(C)));
     CKC(cudaMalloc(&ctx->d_occ, sizeof(double)));
-    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; }
+    ctx->n_nl2 = 0; while (ctx->n_nl2 < ctx->nlev && dims->lev[ctx->n_nl2].type == FDGA_LV_NL2) ctx->n_nl2++;
+    CKC(cudaMalloc(&ctx->Ttab, (size_t)(2 * g.nPiF) * (2 * g.nK2f) * (2 * g.nK2b - 1) * sizeof(C)));
+    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; s.ncol = 0; s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = nullptr; }
     CKC(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return 0;
@@ -323,8 +373,9 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
     cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->Rt); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB);
     cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
-    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ);
-    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); cudaFree(s.d_repvals); }
+    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); cudaFree(ctx->Ttab);
+    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); cudaFree(s.d_repvals);
+        cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); }
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -333,6 +384,7 @@ int fdga_destroy(fdga_ctx* ctx) {
 
 int fdga_set_option(fdga_ctx* ctx, int opt, int value) {
     if (opt == FDGA_OPT_SDE_OWN_GAMMA) { ctx->opt_sde_own_gamma = value != 0; return 0; }
+    if (opt == FDGA_OPT_GENERIC_KERNELS) { ctx->opt_generic = value != 0; return 0; }
     FAIL("fdga_set_option: unknown option");
 }
 int fdga_sync(fdga_ctx* ctx) { CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
@@ -380,6 +432,7 @@ int fdga_comm_init(fdga_ctx* ctx, int nranks, int rank, const void* unique_id_12
         cudaFree(s.d_repvals);
         CK(cudaMalloc(&s.d_repvals, (size_t)s.chunk * nranks * sizeof(C)));
         CK(cudaMemset(s.d_repvals, 0, (size_t)s.chunk * nranks * sizeof(C)));
+        if ((i == FDGA_SG_PP2 || i == FDGA_SG_PH2) && build_columns(ctx, s)) return 1;
     }
     return 0;
 }
@@ -466,6 +519,7 @@ int fdga_set_symmetry_classes(fdga_ctx* ctx, int which, int64_t nclasses, const 
     cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); cudaFree(s.d_repvals);
     s.ncls = nclasses; s.nmem = nmem; s.chunk = (nclasses + ctx->nranks - 1) / ctx->nranks;
     s.h_offsets.assign(offsets, offsets + nclasses + 1);
+    s.h_index.assign(index, index + nmem);
     CK(cudaMalloc(&s.d_offsets, (nclasses + 1) * sizeof(long long))); CK(cudaMalloc(&s.d_index, nmem * sizeof(long long)));
     CK(cudaMalloc(&s.d_ops, nmem)); CK(cudaMalloc(&s.d_member_class, nmem * sizeof(int)));
     CK(cudaMalloc(&s.d_repvals, (size_t)s.chunk * ctx->nranks * sizeof(C)));
@@ -475,6 +529,7 @@ int fdga_set_symmetry_classes(fdga_ctx* ctx, int which, int64_t nclasses, const 
     CK(cudaMemcpy(s.d_ops, ops, nmem, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s.d_member_class, mclass.data(), nmem * sizeof(int), cudaMemcpyHostToDevice));
     s.set = true;
+    if (which == FDGA_SG_PP2 || which == FDGA_SG_PH2) return build_columns(ctx, s);
     return 0;
 }
 int fdga_build_symmetry_group(int which_sg, int n0, int n1, int nq, int64_t* offsets, int64_t* index, uint8_t* ops, int64_t* nclasses) {
@@ -605,7 +660,33 @@ static int launch_right(fdga_ctx* ctx, int ch, const DevChain& F0, const DevChai
     CK(cudaGetLastError());
     return 0;
 }
+
+// column path (fdga_column.cuh): momentum-independent table + one CTA per output column
+template <int KIND, int CH>
+static int launch_column_t(fdga_ctx* ctx, const DevChain& V, ColJob job, SymGroup& s, const C* R, int cat) {
+    Scope sc(ctx, cat);
+    const C* T = nullptr;
+    if (KIND != JOB_LK2) {
+        long long n = (long long)job.nw * (2 * ctx->g.nK2f) * (2 * ctx->g.nK2b - 1);
+        LAUNCH(cat, (loc_table_kernel<KIND, CH>), nblk(n, 128), 128, V, job, ctx->g, ctx->Ttab);
+        T = ctx->Ttab;
+    }
+    if (s.ncol > 0) LAUNCH(cat, (column_kernel<KIND, CH>), (unsigned)s.ncol, 128, V, job, col_dev(s), R, T, s.d_repvals, ctx->g);
+    CK(cudaGetLastError());
+    return 0;
+}
+template <int KIND>
+static int launch_column(fdga_ctx* ctx, int ch, const DevChain& V, ColJob job, SymGroup& s, const C* R, int cat) {
+    if (ch == FDGA_PCH) return launch_column_t<KIND, CH_P>(ctx, V, job, s, R, cat);
+    if (ch == FDGA_TCH) return launch_column_t<KIND, CH_T>(ctx, V, job, s, R, cat);
+    return launch_column_t<KIND, CH_A>(ctx, V, job, s, R, cat);
+}
 }  // extern "C++"
+static ColJob make_job(fdga_ctx* ctx, int lev_first, int nw, int Ninner, int slabN, C scale) {
+    ColJob j; j.lev_first = lev_first; j.n_nl2 = ctx->n_nl2; j.own_only = ctx->opt_sde_own_gamma; j.nw = nw; j.Ninner = Ninner;
+    j.slabW_N = slabN; j.scale_re = scale.x; j.scale_im = scale.y;
+    return j;
+}
 static int ensure_pi(fdga_ctx* ctx, int ch) {
     if (refresh_pi(ctx, pi_kind(ch, true))) return 1;
     return refresh_pi(ctx, pi_kind(ch, false));
@@ -649,7 +730,10 @@ int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
     SymGroup& s = ctx->sg[which];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
     double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
-    {
+    if (!ctx->opt_generic) {
+        ColJob job = make_job(ctx, 0, 2 * ctx->g.nK2f, ctx->g.nK2f, ctx->g.nK2b, mkC(scale, 0.0));
+        if (launch_column<JOB_LK2>(ctx, ch, F, job, s, ctx->Rt, FDGA_T_L_K2)) return 1;
+    } else {
         Scope sc(ctx, FDGA_T_L_K2);
         if (c1 > c0) {
             if (ch == FDGA_PCH)      LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_P>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
@@ -676,7 +760,11 @@ int fdga_bse_K2(fdga_ctx* ctx, int ch, int mfrg) {
     SymGroup& s = ctx->sg[which];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
     double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
-    {
+    if (!ctx->opt_generic) {
+        ColJob job = make_job(ctx, mfrg ? 1 : 0, 2 * ctx->g.nPiF, ctx->g.nPiF, ctx->g.nK2b, mkC(scale, 0.0));
+        if (mfrg) { if (launch_column<JOB_K2_MF>(ctx, ch, F, job, s, ctx->Rt, FDGA_T_K2)) return 1; }
+        else      { if (launch_column<JOB_K2>(ctx, ch, F, job, s, ctx->Rt, FDGA_T_K2)) return 1; }
+    } else {
         Scope sc(ctx, FDGA_T_K2);
         unsigned nb = (unsigned)(c1 - c0);
         if (c1 > c0) {
@@ -778,7 +866,11 @@ static int sde_compute(fdga_ctx* ctx, C* Sout, int gwhich, bool reference, int l
         SymGroup& s = ctx->sg[pp ? FDGA_SG_PP2 : FDGA_SG_PH2];
         long long c0, c1; sg_class_range(ctx, s, c0, c1);
         const C* PiT = ctx->PiT[pp ? (reference ? FDGA_PI0PP : FDGA_PIPP) : (reference ? FDGA_PI0PH : FDGA_PIPH)];
-        {
+        if (!ctx->opt_generic) {
+            ColJob job = make_job(ctx, level, 2 * g.nPiF, g.nPiF, g.nPiB, U * scale);
+            if (pp) { if (launch_column_t<JOB_SDE_PP, CH_P>(ctx, V, job, s, PiT, FDGA_T_SDE_L)) return 1; }
+            else    { if (launch_column_t<JOB_SDE_PH, CH_A>(ctx, V, job, s, PiT, FDGA_T_SDE_L)) return 1; }
+        } else {
             Scope sc(ctx, FDGA_T_SDE_L);
             if (c1 > c0) {
                 if (pp) LAUNCH(FDGA_T_SDE_L, sde_L_kernel<true>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma);
@@ -798,7 +890,8 @@ static int sde_compute(fdga_ctx* ctx, C* Sout, int gwhich, bool reference, int l
         if (dft4(ctx, ctx->L[0], ctx->scratchA, pre, -1, nrm, FDGA_T_SDE_RS)) return 1;
         if (dft4(ctx, ctx->L[1], ctx->scratchA, pre, -1, nrm, FDGA_T_SDE_RS)) return 1;
         (void)nK2;
-        LAUNCH(FDGA_T_SDE_RS, sde_rs_kernel, nblk(ctx->lenG, 64), 64, ctx->GR, ctx->L[0], ctx->L[1], ctx->SigR, g, g.nG, g.LG);
+        CK(cudaMemsetAsync(ctx->SigR, 0, ctx->lenG * sizeof(C), ctx->stream));
+        LAUNCH(FDGA_T_SDE_RS, sde_rs_kernel, nblk((long long)(2 * g.nK2f) * g.LG * g.LG, 64), 64, ctx->GR, ctx->L[0], ctx->L[1], ctx->SigR, g, g.nG, g.LG);
         CK(cudaGetLastError());
         if (dft2_G(ctx, ctx->SigR, Sout, ctx->SigTmp, +1, 1.0, FDGA_T_SDE_RS)) return 1;
         SymGroup& ss = ctx->sg[FDGA_SG_SIGMA];

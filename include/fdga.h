@@ -82,7 +82,8 @@ int  fdga_sync(fdga_ctx* ctx);
 /* Options.  FDGA_OPT_SDE_OWN_GAMMA: 0 (default) = SDE L kernels exactly as coded in src/nonlocal_2/SDE.jl:26-29,64-69
  * (F(...; own gamma) - F.F0(...; own gamma), which for a nested nonlocal F0 also contains F0's cross channels);
  * 1 = as the in-line comments there state (own-channel gamma of F only).  See DESIGN.md "E2". */
-enum { FDGA_OPT_SDE_OWN_GAMMA = 0 };
+enum { FDGA_OPT_SDE_OWN_GAMMA = 0,
+       FDGA_OPT_GENERIC_KERNELS = 1 /* 1 = use the straightforward per-term kernels instead of the column kernels (A/B check) */ };
 int  fdga_set_option(fdga_ctx* ctx, int opt, int value);
 /* one process per GPU; `unique_id` = the 128-byte ncclUniqueId obtained on rank 0 by
  * fdga_comm_unique_id and broadcast by the host (MPI in Julia, torch.distributed in tests). */

@@ -264,3 +264,21 @@ def test_fullsize_sampled_classes_and_symmetry(orc):
             orc.lib().orc_symmetrize(orc._p(sym), __import__("ctypes").byref(orc.sg_struct(S._sg[which])))
             assert np.array_equal(sym, flat), (ch, cls)
     S.close()
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_column_kernels_match_generic_kernels(orc, sym):
+    """A/B on the device: optimised column kernels vs the straightforward per-term kernels (FDGA_OPT_GENERIC_KERNELS)"""
+    import fddgasolver_jl_b200 as fd
+    res = []
+    for generic in (0, 1):
+        S, _ = make_pair(orc, nmax=3, nq=4, LG=8, sym=sym)
+        S.set_option("generic_kernels", generic)
+        fd.iterate_solver(S, "fdPA", True)
+        A = fd.mfRGLinearMap(S)
+        y = A.matvec(S.F.flatten())
+        S.pull("F", "Σ", "FL")
+        res.append((S.F.flatten(), S.FL.flatten(), S.Σ.copy(), y))
+        S.close()
+    for a, b in zip(*res):
+        assert rel(a, b) < TOL
