@@ -43,15 +43,15 @@ struct ColJob {
 
 struct MomOff { int oK1, oK2A, oK2B, oK3; };
 
-__device__ __forceinline__ int fold1(int a, int L) {   // a in (-3L, 3L)
+FDGA_HD int fold1(int a, int L) {   // a in (-3L, 3L)
     a += (a < 0) ? L : 0; a += (a < 0) ? L : 0; a += (a < 0) ? L : 0;
     a -= (a >= L) ? L : 0; a -= (a >= L) ? L : 0; a -= (a >= L) ? L : 0;
     return a;
 }
-__device__ __forceinline__ int foldidx(int x, int y, int L) { return fold1(x, L) + L * fold1(y, L); }
+FDGA_HD int foldidx(int x, int y, int L) { return fold1(x, L) + L * fold1(y, L); }
 
 // offsets of the frequency sub-arrays of channel r of level lv at momenta converted from `form` to r
-__device__ __forceinline__ MomOff mom_offsets(const DevLevel& lv, int form, int r, int L, int NP,
+FDGA_HD MomOff mom_offsets(const DevLevel& lv, int form, int r, int L, int NP,
                                               int Px, int Py, int kx, int ky, int qx, int qy) {
     Arg a; a.W = 0; a.v = 0; a.w = 0; a.Px = Px; a.Py = Py; a.kx = kx; a.ky = ky; a.qx = qx; a.qy = qy;
     Arg b = convert(a, form, r);
@@ -65,7 +65,7 @@ __device__ __forceinline__ MomOff mom_offsets(const DevLevel& lv, int form, int 
     return m;
 }
 // gamma_r at fixed momenta, all K switches on; v, w finite (same box logic as nl2_chan)
-__device__ __forceinline__ C chan_off(const DevLevel& lv, int r, const MomOff& m, int W, int v, int w) {
+FDGA_HD C chan_off(const DevLevel& lv, int r, const MomOff& m, int W, int v, int w) {
     C val = zeroC();
     if (!inB(W, lv.nK1)) return val;
     const DevChan& c = lv.ch[r];
@@ -83,7 +83,7 @@ __device__ __forceinline__ C chan_off(const DevLevel& lv, int r, const MomOff& m
     return val;
 }
 // gamma_r(W, v, w) - gamma_r(W, inf, w) at fixed momenta: K2[W,v,P,k] + K3[W,v,w,P] inside the boxes
-__device__ __forceinline__ C chan_off_diff_v(const DevLevel& lv, int r, const MomOff& m, int W, int v, int w) {
+FDGA_HD C chan_off_diff_v(const DevLevel& lv, int r, const MomOff& m, int W, int v, int w) {
     C val = zeroC();
     if (!inB(W, lv.nK2b) || !inF(v, lv.nK2f)) return val;     // K2 Omega-box is inside the K1 box
     const DevChan& c = lv.ch[r];
@@ -97,24 +97,80 @@ __device__ __forceinline__ C chan_off_diff_v(const DevLevel& lv, int r, const Mo
 }
 
 // frequency part of _convert_channel (no momenta)
-__device__ __forceinline__ void convert_freq(int W, int v, int w, int from, int to, int& W2, int& v2, int& w2) {
+FDGA_HD void convert_freq(int W, int v, int w, int from, int to, int& W2, int& v2, int& w2) {
     Arg a; a.W = W; a.v = v; a.w = w; a.Px = a.Py = a.kx = a.ky = a.qx = a.qy = 0;
     Arg b = convert(a, from, to);
     W2 = b.W; v2 = b.v; w2 = b.w;
+}
+
+// ---- interval machinery: after channel conversion every Matsubara argument is LINEAR in the inner index `win`
+// with slope in {-1, 0, +1}, so "argument inside a mesh box" is a contiguous interval of win.
+struct Lin { int x0, s; };      // x(win) = x0 + s * win
+FDGA_HD void clip_interval(const Lin& x, int lo, int hi, int& a, int& b) {   // intersect [a, b] with {win : lo <= x(win) <= hi}
+    if (x.s > 0) { a = max(a, lo - x.x0); b = min(b, hi - x.x0); }
+    else if (x.s < 0) { a = max(a, x.x0 - hi); b = min(b, x.x0 - lo); }
+    else if (x.x0 < lo || x.x0 > hi) { b = a - 1; }
+}
+// sum over iw in [w_lo, w_hi) of gamma_r(W2, v2, w2) * Rq[iw] at fixed momenta (all K switches on), W2/v2/w2 linear in win = iw - Nin.
+// Same box logic as chan_off.  K1 (needed for nearly every win) is a branch-free streaming correlation over its
+// in-box interval; the K2 / K3 terms only exist inside the (short) K2 Omega-box band and are evaluated term by term there.
+FDGA_HD C chan_lin_sum(const DevLevel& lv, int r, const MomOff& m, Lin W2, Lin v2, Lin w2,
+                       const C* __restrict__ Rq, int Nin, int w_lo, int w_hi) {
+    const DevChan& c = lv.ch[r];
+    C part = zeroC();
+    const int a0 = w_lo - Nin, b0 = w_hi - 1 - Nin;      // inclusive win range of this chunk
+    {
+        int a = a0, b = b0; clip_interval(W2, -(lv.nK1 - 1), lv.nK1 - 1, a, b);
+        const int o1 = m.oK1 + posB(W2.x0, lv.nK1);      // integer offsets: never form a pointer outside the table
+#pragma unroll 4
+        for (int win = a; win <= b; ++win) part += ldg(c.K1 + (o1 + W2.s * win)) * Rq[win + Nin];
+    }
+    int a = a0, b = b0; clip_interval(W2, -(lv.nK2b - 1), lv.nK2b - 1, a, b);
+    const int nB = 2 * lv.nK2b - 1, nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
+    for (int win = a; win <= b; ++win) {
+        const int Wc = W2.x0 + W2.s * win, vc = v2.x0 + v2.s * win, wc = w2.x0 + w2.s * win;
+        const bool A = inF(vc, lv.nK2f), B = inF(wc, lv.nK2f);
+        const int pW = posB(Wc, lv.nK2b);
+        C val = zeroC();
+        if (A) val += ldg(c.K2 + (m.oK2A + pW + nB * posF(vc, lv.nK2f)));
+        if (B) val += ldg(c.K2 + (m.oK2B + pW + nB * posF(wc, lv.nK2f)));
+        if (A && B && inB(Wc, lv.nK3b) && inF(vc, lv.nK3f) && inF(wc, lv.nK3f))
+            val += ldg(c.K3 + (m.oK3 + posB(Wc, lv.nK3b) + nB3 * (posF(vc, lv.nK3f) + nF3 * posF(wc, lv.nK3f))));
+        part += val * Rq[win + Nin];
+    }
+    return part;
+}
+// same for gamma_r(W, v, w) - gamma_r(W, inf, w): K2[W, v | P, k] + K3[W, v, w | P] inside the boxes
+FDGA_HD C chan_lin_sum_diff_v(const DevLevel& lv, int r, const MomOff& m, Lin W2, Lin v2, Lin w2,
+                              const C* __restrict__ Rq, int Nin, int w_lo, int w_hi) {
+    const DevChan& c = lv.ch[r];
+    C part = zeroC();
+    int a = w_lo - Nin, b = w_hi - 1 - Nin;
+    clip_interval(W2, -(lv.nK2b - 1), lv.nK2b - 1, a, b);
+    clip_interval(v2, -lv.nK2f, lv.nK2f - 1, a, b);
+    const int nB = 2 * lv.nK2b - 1, nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
+    for (int win = a; win <= b; ++win) {
+        const int Wc = W2.x0 + W2.s * win, vc = v2.x0 + v2.s * win, wc = w2.x0 + w2.s * win;
+        C val = ldg(c.K2 + (m.oK2A + posB(Wc, lv.nK2b) + nB * posF(vc, lv.nK2f)));
+        if (inF(wc, lv.nK2f) && inB(Wc, lv.nK3b) && inF(vc, lv.nK3f) && inF(wc, lv.nK3f))
+            val += ldg(c.K3 + (m.oK3 + posB(Wc, lv.nK3b) + nB3 * (posF(vc, lv.nK3f) + nF3 * posF(wc, lv.nK3f))));
+        part += val * Rq[win + Nin];
+    }
+    return part;
 }
 
 // forms (channel parametrisations evaluated in parallel spin) and their weights:
 //   K2 / LK2 jobs: p -> {(p,1)}, a -> {(a,1)}, t (dSp = 2 pSp + xSp, xSp(t) = -a-form) -> {(t,2),(a,-1)}
 //   SDE pp -> {(p,1)} ; SDE ph -> {(a,1),(t,1)}
 template <int KIND, int CH> struct Forms;
-template <int KIND> struct Forms<KIND, CH_P> { static constexpr int n = 1; __device__ static int ch(int) { return CH_P; } __device__ static double coef(int) { return 1.0; } };
-template <int KIND> struct Forms<KIND, CH_A> { static constexpr int n = 1; __device__ static int ch(int) { return CH_A; } __device__ static double coef(int) { return 1.0; } };
-template <int KIND> struct Forms<KIND, CH_T> { static constexpr int n = 2; __device__ static int ch(int i) { return i == 0 ? CH_T : CH_A; } __device__ static double coef(int i) { return i == 0 ? 2.0 : -1.0; } };
-template <> struct Forms<JOB_SDE_PH, CH_A> { static constexpr int n = 2; __device__ static int ch(int i) { return i == 0 ? CH_A : CH_T; } __device__ static double coef(int) { return 1.0; } };
+template <int KIND> struct Forms<KIND, CH_P> { static constexpr int n = 1; __host__ __device__ static int ch(int) { return CH_P; } __host__ __device__ static double coef(int) { return 1.0; } };
+template <int KIND> struct Forms<KIND, CH_A> { static constexpr int n = 1; __host__ __device__ static int ch(int) { return CH_A; } __host__ __device__ static double coef(int) { return 1.0; } };
+template <int KIND> struct Forms<KIND, CH_T> { static constexpr int n = 2; __host__ __device__ static int ch(int i) { return i == 0 ? CH_T : CH_A; } __host__ __device__ static double coef(int i) { return i == 0 ? 2.0 : -1.0; } };
+template <> struct Forms<JOB_SDE_PH, CH_A> { static constexpr int n = 2; __host__ __device__ static int ch(int i) { return i == 0 ? CH_A : CH_T; } __host__ __device__ static double coef(int) { return 1.0; } };
 
 // map (output nu, inner w) -> vertex frequency arguments (v, w) of the job
 template <int KIND, int CH>
-__device__ __forceinline__ void job_freq_args(int W, int nu, int win, int& v, int& w) {
+FDGA_HD void job_freq_args(int W, int nu, int win, int& v, int& w) {
     if (KIND == JOB_K2 || KIND == JOB_SDE_PH) { v = nu; w = win; }
     else if (KIND == JOB_K2_MF || KIND == JOB_LK2) { v = nu; w = (CH == CH_P) ? W - win - 1 : win; }
     else { v = W - win - 1; w = nu; }                                   // JOB_SDE_PP: F(W, W - w, nu, ...)
@@ -123,12 +179,9 @@ __device__ __forceinline__ void job_freq_args(int W, int nu, int win, int& v, in
 // ---- momentum-independent part of the left factor, tabulated per (W, nu, w) -----------------------------------
 // T[iw + nw*(inu + nF2*iWo)]  (W on the output K2 bosonic mesh, nu on the output K2 fermionic mesh)
 template <int KIND, int CH>
-__global__ void loc_table_kernel(const __grid_constant__ DevChain V, ColJob job, Grid g, C* __restrict__ T) {
+FDGA_HD C loc_table_entry(const DevChain& V, const ColJob& job, const Grid& g, long long i) {
     typedef Forms<KIND, CH> FM;
-    const int nB2 = 2 * g.nK2b - 1, nF2 = 2 * g.nK2f;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long n = (long long)job.nw * nF2 * nB2;
-    if (i >= n) return;
+    const int nF2 = 2 * g.nK2f;
     int iw = i % job.nw; int inu = (i / job.nw) % nF2; int iWo = i / ((long long)job.nw * nF2);
     int W = iWo - (g.nK2b - 1), nu = inu - g.nK2f, win = iw - job.Ninner;
     Arg a; a.W = W; a.Px = a.Py = a.kx = a.ky = a.qx = a.qy = 0;
@@ -159,17 +212,23 @@ __global__ void loc_table_kernel(const __grid_constant__ DevChain V, ColJob job,
         }
         val += x * FM::coef(f);
     }
-    T[i] = val;
+    return val;
+}
+template <int KIND, int CH>
+__global__ void loc_table_kernel(const __grid_constant__ DevChain V, ColJob job, Grid g, C* __restrict__ T) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long n = (long long)job.nw * (2 * g.nK2f) * (2 * g.nK2b - 1);
+    if (i < n) T[i] = loc_table_entry<KIND, CH>(V, job, g, i);
 }
 
 // ---- the column kernel -----------------------------------------------------------------------------------------
+// thread <-> (representative nu, inner momentum slot): lanes with consecutive nu gather neighbouring table entries,
+// the R slab element is a warp broadcast, and every thread carries a single accumulator.
+// per-thread part (host-callable for CPU unit tests): contribution of thread `tid` of `nthreads` to column `col`
 template <int KIND, int CH>
-__global__ void __launch_bounds__(128)
-column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const C* __restrict__ R, const C* __restrict__ T,
-              C* __restrict__ repvals, Grid g) {
+FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols, const C* __restrict__ R, const C* __restrict__ T,
+                        const Grid& g, int col, int tid, int nthreads) {
     typedef Forms<KIND, CH> FM;
-    constexpr int NV = FDGA_NV;
-    const int col = blockIdx.x;
     const int iW = cols.iW[col], iP = cols.iP[col], ik = cols.ik[col];
     const int r0 = cols.start[col], nrep = cols.start[col + 1] - r0;
     const int W = iW - (g.nK2b - 1);
@@ -177,23 +236,27 @@ column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const
     const int Px = iP % L, Py = iP / L, kx = ik % L, ky = ik / L;
     const int nw = job.nw;
     const int nF2 = 2 * g.nK2f;
-    int nus[NV];
-#pragma unroll
-    for (int n = 0; n < NV; ++n) nus[n] = (n < nrep) ? cols.rep_inu[r0 + n] - g.nK2f : 0;
+    int NVc = 1;
+    while (NVc < nrep) NVc <<= 1;                         // 1, 2, 4, 8 (<= FDGA_NV)
+    const int n = tid & (NVc - 1);
+    const int qs = tid / NVc, nqs = nthreads / NVc;
+    const bool active = n < nrep;
+    const int nu = active ? cols.rep_inu[r0 + n] - g.nK2f : 0;
     const C* slab = R + (size_t)nw * NP * (posB(W, job.slabW_N) + (size_t)(2 * job.slabW_N - 1) * iP);
-    const C* Tw = T + (size_t)nw * nF2 * iW;
-    C acc[NV];
-#pragma unroll
-    for (int n = 0; n < NV; ++n) acc[n] = zeroC();
+    const C* Tw = (T != nullptr) ? T + (size_t)nw * (nu + g.nK2f + (size_t)nF2 * iW) : nullptr;
+    C acc = zeroC();
 
     // w is split in WS chunks so that small momentum meshes still fill the CTA
     int WS = 1;
-    while (NP * WS * 2 <= (int)blockDim.x && WS * 2 <= nw) WS *= 2;
+    while (NP * WS < nqs && WS * 2 <= nw) WS *= 2;
     const int wchunk = (nw + WS - 1) / WS;
     const int l0 = job.lev_first;
+    const bool is_sde = (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH);
+    const int l_end = (KIND == JOB_LK2) ? l0 + 1 : (is_sde ? min(l0 + 2, job.n_nl2) : job.n_nl2);
 
-    for (int item = threadIdx.x; item < NP * WS; item += blockDim.x) {
-        const int iq = item / WS, ws = item % WS;
+    if (active)
+    for (int item = qs; item < NP * WS; item += nqs) {
+        const int iq = item / WS, ws = item - iq * WS;
         const int qx = iq % L, qy = iq / L;
         const int w_lo = ws * wchunk, w_hi = min(nw, w_lo + wchunk);
         // momentum arguments of the vertex for this (k, q)
@@ -211,8 +274,6 @@ column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const
             //   K2 jobs : every leading NL2 level of the left chain: cross channels + own-channel (nu - inf) difference
             //   L_K2    : level l0 only, cross channels only (F0 = false, own gamma off)
             //   SDE     : own gamma of level l0 in full + cross channels of level l0 + 1 ("as coded")
-            const bool is_sde = (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH);
-            const int l_end = (KIND == JOB_LK2) ? l0 + 1 : (is_sde ? min(l0 + 2, job.n_nl2) : job.n_nl2);
             for (int l = l0; l < l_end; ++l) {
                 const DevLevel& lv = V.lev[l];
                 bool do_own_full = false, do_own_diff = false, do_cross = false;
@@ -225,59 +286,58 @@ column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const
                 MomOff mo[3];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) mo[r] = mom_offsets(lv, form, r, L, NP, Px, Py, akx, aky, aqx, aqy);
-                for (int iw = w_lo; iw < w_hi; ++iw) {
-                    const C Rv = Rq[iw] * cf;
-                    const int win = iw - job.Ninner;
+                // vertex frequency arguments are linear in win: v(win), w(win)
+                int v_a, w_a, v_b, w_b;
+                job_freq_args<KIND, CH>(W, nu, 0, v_a, w_a); job_freq_args<KIND, CH>(W, nu, 1, v_b, w_b);
+                C part = zeroC();
+                if (do_cross) {
 #pragma unroll
-                    for (int n = 0; n < NV; ++n) {
-                        if (n >= nrep) break;
-                        int v, w; job_freq_args<KIND, CH>(W, nus[n], win, v, w);
-                        C val = zeroC();
-                        if (do_cross) {
-#pragma unroll
-                            for (int r = 0; r < 3; ++r) {
-                                if (r == form) continue;
-                                int W2, v2, w2; convert_freq(W, v, w, form, r, W2, v2, w2);
-                                val += chan_off(lv, r, mo[r], W2, v2, w2);
-                            }
-                        }
-                        if (do_own_diff) val += chan_off_diff_v(lv, form, mo[form], W, v, w);
-                        if (do_own_full) val += chan_off(lv, form, mo[form], W, v, w);
-                        acc[n] += val * Rv;
+                    for (int r = 0; r < 3; ++r) {
+                        if (r == form) continue;
+                        int W0, v0, w0, W1, v1, w1;
+                        convert_freq(W, v_a, w_a, form, r, W0, v0, w0); convert_freq(W, v_b, w_b, form, r, W1, v1, w1);
+                        Lin lW = {W0, W1 - W0}, lv2 = {v0, v1 - v0}, lw2 = {w0, w1 - w0};
+                        part += chan_lin_sum(lv, r, mo[r], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi);
                     }
                 }
+                if (do_own_diff || do_own_full) {
+                    Lin lW = {W, 0}, lv2 = {v_a, v_b - v_a}, lw2 = {w_a, w_b - w_a};
+                    if (do_own_diff) part += chan_lin_sum_diff_v(lv, form, mo[form], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi);
+                    else part += chan_lin_sum(lv, form, mo[form], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi);
+                }
+                acc += part * cf;
             }
         }
         // momentum-independent levels (pre-tabulated, forms and weights already folded in)
-        if (T != nullptr) {
-            for (int iw = w_lo; iw < w_hi; ++iw) {
-                const C Rv = Rq[iw];
-#pragma unroll
-                for (int n = 0; n < NV; ++n) {
-                    if (n >= nrep) break;
-                    acc[n] += ldg(Tw + iw + nw * (nus[n] + g.nK2f)) * Rv;
-                }
-            }
+        if (Tw != nullptr) {
+            C part = zeroC();
+#pragma unroll 4
+            for (int iw = w_lo; iw < w_hi; ++iw) part += ldg(Tw + iw) * Rq[iw];
+            acc += part;
         }
     }
 
-    // block reduction of the NV accumulators
-    __shared__ double red[NV][2][4];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int n = 0; n < NV; ++n) {
-        double x = acc[n].x, y = acc[n].y;
-        for (int o = 16; o > 0; o >>= 1) { x += __shfl_down_sync(0xffffffffu, x, o); y += __shfl_down_sync(0xffffffffu, y, o); }
-        if (lane == 0) { red[n][0][wid] = x; red[n][1][wid] = y; }
-    }
+    return acc;
+}
+
+template <int KIND, int CH>
+__global__ void __launch_bounds__(128, 4)
+column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const C* __restrict__ R, const C* __restrict__ T,
+              C* __restrict__ repvals, Grid g) {
+    const int col = blockIdx.x;
+    const int r0 = cols.start[col], nrep = cols.start[col + 1] - r0;
+    int NVc = 1;
+    while (NVc < nrep) NVc <<= 1;
+    const C acc = column_thread<KIND, CH>(V, job, cols, R, T, g, col, threadIdx.x, blockDim.x);
+    // reduction over the momentum slots of each representative
+    __shared__ double redx[128], redy[128];
+    redx[threadIdx.x] = acc.x; redy[threadIdx.x] = acc.y;
     __syncthreads();
     if (threadIdx.x < nrep) {
-        const int n = threadIdx.x;
-        const int nwarp = blockDim.x >> 5;
         double x = 0.0, y = 0.0;
-        for (int i = 0; i < nwarp; ++i) { x += red[n][0][i]; y += red[n][1][i]; }
+        for (int i = threadIdx.x; i < (int)blockDim.x; i += NVc) { x += redx[i]; y += redy[i]; }
         C s = mkC(job.scale_re, job.scale_im);
-        repvals[cols.rep_cls[r0 + n]] = mkC(x, y) * s;
+        repvals[cols.rep_cls[r0 + threadIdx.x]] = mkC(x, y) * s;
     }
 }
 

@@ -15,38 +15,44 @@
 #include <stdint.h>
 
 #define FDGA_MAXLEV 6
+// evaluators are host-callable too so that the index machinery can be unit-tested without a GPU (tests/host_eval_test.cu)
+#define FDGA_HD __host__ __device__ __forceinline__
 
 namespace fdga {
 
 struct __align__(16) C {
     double x, y;
 };
-__host__ __device__ __forceinline__ C mkC(double x, double y) { C r; r.x = x; r.y = y; return r; }
-__host__ __device__ __forceinline__ C operator+(C a, C b) { return mkC(a.x + b.x, a.y + b.y); }
-__host__ __device__ __forceinline__ C operator-(C a, C b) { return mkC(a.x - b.x, a.y - b.y); }
-__host__ __device__ __forceinline__ C operator-(C a) { return mkC(-a.x, -a.y); }
-__host__ __device__ __forceinline__ C operator*(C a, C b) { return mkC(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__host__ __device__ __forceinline__ C operator*(C a, double s) { return mkC(a.x * s, a.y * s); }
-__host__ __device__ __forceinline__ C operator*(double s, C a) { return mkC(a.x * s, a.y * s); }
-__host__ __device__ __forceinline__ C operator/(C a, double s) { return mkC(a.x / s, a.y / s); }
-__host__ __device__ __forceinline__ C& operator+=(C& a, C b) { a.x += b.x; a.y += b.y; return a; }
-__host__ __device__ __forceinline__ C conjC(C a) { return mkC(a.x, -a.y); }
-__host__ __device__ __forceinline__ C zeroC() { return mkC(0.0, 0.0); }
+FDGA_HD C mkC(double x, double y) { C r; r.x = x; r.y = y; return r; }
+FDGA_HD C operator+(C a, C b) { return mkC(a.x + b.x, a.y + b.y); }
+FDGA_HD C operator-(C a, C b) { return mkC(a.x - b.x, a.y - b.y); }
+FDGA_HD C operator-(C a) { return mkC(-a.x, -a.y); }
+FDGA_HD C operator*(C a, C b) { return mkC(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+FDGA_HD C operator*(C a, double s) { return mkC(a.x * s, a.y * s); }
+FDGA_HD C operator*(double s, C a) { return mkC(a.x * s, a.y * s); }
+FDGA_HD C operator/(C a, double s) { return mkC(a.x / s, a.y / s); }
+FDGA_HD C& operator+=(C& a, C b) { a.x += b.x; a.y += b.y; return a; }
+FDGA_HD C conjC(C a) { return mkC(a.x, -a.y); }
+FDGA_HD C zeroC() { return mkC(0.0, 0.0); }
 
-__device__ __forceinline__ C ldg(const C* p) {
+FDGA_HD C ldg(const C* p) {
+#if defined(__CUDA_ARCH__) && !defined(FDGA_PLAIN_LDG)
     double2 v = __ldg(reinterpret_cast<const double2*>(p));
     return mkC(v.x, v.y);
+#else
+    return *p;
+#endif
 }
 
 // ---- Matsubara index arithmetic (fermion n <-> (2n+1) pi T, boson m <-> 2 m pi T) ----------
 #define FDGA_INF (1 << 28)
-__host__ __device__ __forceinline__ bool isinfF(int a) { return a >= (1 << 27); }
-__host__ __device__ __forceinline__ bool inB(int m, int N) { return m >= -(N - 1) && m <= N - 1; }
-__host__ __device__ __forceinline__ bool inF(int n, int N) { return n >= -N && n <= N - 1; }   // false for FDGA_INF
-__host__ __device__ __forceinline__ int posB(int m, int N) { return m + N - 1; }
-__host__ __device__ __forceinline__ int posF(int n, int N) { return n + N; }
-__host__ __device__ __forceinline__ int modL(int a, int L) { int r = a % L; return r < 0 ? r + L : r; }
-__host__ __device__ __forceinline__ int kidx(int x, int y, int L) { return modL(x, L) + L * modL(y, L); }
+FDGA_HD bool isinfF(int a) { return a >= (1 << 27); }
+FDGA_HD bool inB(int m, int N) { return m >= -(N - 1) && m <= N - 1; }
+FDGA_HD bool inF(int n, int N) { return n >= -N && n <= N - 1; }   // false for FDGA_INF
+FDGA_HD int posB(int m, int N) { return m + N - 1; }
+FDGA_HD int posF(int n, int N) { return n + N; }
+FDGA_HD int modL(int a, int L) { int r = a % L; return r < 0 ? r + L : r; }
+FDGA_HD int kidx(int x, int y, int L) { return modL(x, L) + L * modL(y, L); }
 
 enum { CH_P = 0, CH_T = 1, CH_A = 2 };
 enum { SP_P = 0, SP_X = 1, SP_D = 2 };
@@ -74,7 +80,7 @@ struct DevChain {
 // ---- channel evaluators (all K switches on) -------------------------------------------------
 // v or w may be FDGA_INF; the unified form below reproduces the four reference methods
 // (src/nonlocal_2/channel.jl:58-194) for K1 = K2 = K3 = true.
-__device__ __forceinline__ C nl2_chan(const DevLevel& lv, int r, int NP, int W, int v, int w, int iP, int ik, int iq) {
+FDGA_HD C nl2_chan(const DevLevel& lv, int r, int NP, int W, int v, int w, int iP, int ik, int iq) {
     C val = zeroC();
     if (!inB(W, lv.nK1)) return val;
     const DevChan& c = lv.ch[r];
@@ -92,7 +98,7 @@ __device__ __forceinline__ C nl2_chan(const DevLevel& lv, int r, int NP, int W, 
     return val;
 }
 // own channel with k = q = kSW: K1[W,P] + mean_k K2[W,v,P,k] + mean_k K2[W,w,P,k] + K3[W,v,w,P]
-__device__ __forceinline__ C nl2_chan_sw_own(const DevLevel& lv, int r, int NP, int W, int v, int w, int iP) {
+FDGA_HD C nl2_chan_sw_own(const DevLevel& lv, int r, int NP, int W, int v, int w, int iP) {
     C val = zeroC();
     if (!inB(W, lv.nK1)) return val;
     const DevChan& c = lv.ch[r];
@@ -109,7 +115,7 @@ __device__ __forceinline__ C nl2_chan_sw_own(const DevLevel& lv, int r, int NP, 
     return val;
 }
 // cross channel with (kSW, kSW, kSW): everything BZ-averaged
-__device__ __forceinline__ C nl2_chan_sw_cross(const DevLevel& lv, int r, int W, int v, int w) {
+FDGA_HD C nl2_chan_sw_cross(const DevLevel& lv, int r, int W, int v, int w) {
     C val = zeroC();
     if (!inB(W, lv.nK1)) return val;
     const DevChan& c = lv.ch[r];
@@ -125,7 +131,7 @@ __device__ __forceinline__ C nl2_chan_sw_cross(const DevLevel& lv, int r, int W,
     }
     return val;
 }
-__device__ __forceinline__ C loc_chan(const DevLevel& lv, int r, int W, int v, int w) {
+FDGA_HD C loc_chan(const DevLevel& lv, int r, int W, int v, int w) {
     C val = zeroC();
     if (!inB(W, lv.nK1)) return val;
     const DevChan& c = lv.ch[r];
@@ -143,12 +149,12 @@ __device__ __forceinline__ C loc_chan(const DevLevel& lv, int r, int W, int v, i
 }
 
 // ---- RefVertex (src/refvertex.jl:90-216) ---------------------------------------------------
-__device__ __forceinline__ C core_call(const DevLevel& lv, int which, int W, int v, int w) {
+FDGA_HD C core_call(const DevLevel& lv, int which, int W, int v, int w) {
     if (!(inB(W, lv.nK3b) && inF(v, lv.nK3f) && inF(w, lv.nK3f))) return zeroC();
     int nB = 2 * lv.nK3b - 1, nF = 2 * lv.nK3f;
     return ldg(lv.core[which] + posB(W, lv.nK3b) + (size_t)nB * (posF(v, lv.nK3f) + (size_t)nF * posF(w, lv.nK3f)));
 }
-__device__ __forceinline__ C core_eval_px(const DevLevel& lv, int Ch, int Sp, int W, int v, int w) {
+FDGA_HD C core_eval_px(const DevLevel& lv, int Ch, int Sp, int W, int v, int w) {
     if (isinfF(v) || isinfF(w)) return (Sp == SP_X) ? -lv.U : lv.U;
     if (Sp == SP_P) {
         if (Ch == CH_P) return core_call(lv, 0, W, v, w) + lv.U;
@@ -159,7 +165,7 @@ __device__ __forceinline__ C core_eval_px(const DevLevel& lv, int Ch, int Sp, in
     if (Ch == CH_T) return core_call(lv, 3, W, v, w) - lv.U;
     return -core_call(lv, 2, W, w, v) - lv.U;
 }
-__device__ __forceinline__ C core_eval(const DevLevel& lv, int Ch, int Sp, int W, int v, int w) {
+FDGA_HD C core_eval(const DevLevel& lv, int Ch, int Sp, int W, int v, int w) {
     if (Sp != SP_D) return core_eval_px(lv, Ch, Sp, W, v, w);
     if (isinfF(v) || isinfF(w)) return lv.U;
     return 2.0 * core_eval_px(lv, Ch, SP_P, W, v, w) + core_eval_px(lv, Ch, SP_X, W, v, w);
@@ -171,7 +177,7 @@ struct Arg {
     int W, v, w;          // Matsubara indices (finite)
     int Px, Py, kx, ky, qx, qy;
 };
-__device__ __forceinline__ Arg convert(const Arg& a, int from, int to) {
+FDGA_HD Arg convert(const Arg& a, int from, int to) {
     Arg b = a;
     if (from == to) return b;
     if (from == CH_P && to == CH_T) {
@@ -202,7 +208,7 @@ __device__ __forceinline__ Arg convert(const Arg& a, int from, int to) {
 // `flags` (F0 / gamma switches) act on level lev0 only: the reference calls F.F0(...) without
 // forwarding them (src/nonlocal/vertex.jl:87-89).
 template <bool SW>
-__device__ __forceinline__ C eval_p(const DevChain& c, int lev0, int Ch, const Arg& a, unsigned flags) {
+FDGA_HD C eval_p(const DevChain& c, int lev0, int Ch, const Arg& a, unsigned flags) {
     C val = zeroC();
     const bool anyinf = isinfF(a.v) || isinfF(a.w);
     const int L = c.L, NP = c.NP;
@@ -239,13 +245,13 @@ __device__ __forceinline__ C eval_p(const DevChain& c, int lev0, int Ch, const A
 }
 
 // crossed spin: src/nonlocal/vertex.jl:157-185 (gamma_t / gamma_a switches swapped)
-__device__ __forceinline__ unsigned swap_ta(unsigned f) {
+FDGA_HD unsigned swap_ta(unsigned f) {
     return (f & (FL_F0 | FL_GP)) | ((f & FL_GT) ? FL_GA : 0u) | ((f & FL_GA) ? FL_GT : 0u);
 }
 
 // generic entry: chain from lev0, any spin.  Sp, Ch are compile-time constants at all call sites.
 template <bool SW>
-__device__ __forceinline__ C eval_vertex(const DevChain& c, int lev0, int Ch, int Sp, const Arg& a, unsigned flags) {
+FDGA_HD C eval_vertex(const DevChain& c, int lev0, int Ch, int Sp, const Arg& a, unsigned flags) {
     if (c.lev[lev0].type == LV_CORE) return core_eval(c.lev[lev0], Ch, Sp, a.W, a.v, a.w);
     C val = zeroC();
     if (Sp == SP_P || Sp == SP_D) {

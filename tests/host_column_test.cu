@@ -1,0 +1,165 @@
+// Host-side (CPU) test of the complete column-kernel arithmetic against the straightforward per-term evaluator
+// (eval_vertex) for every job kind / channel on a random nested chain NL2 -> NL2 -> LOCAL -> CORE with ragged boxes.
+// Built and run by tests/test_host_eval.py (nvcc, no GPU needed).
+#include <cstdio>
+#include "../fddgasolver.jl_b200/csrc/fdga_column.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cmath>
+using namespace fdga;
+
+static double rnd() { return rand() / (double)RAND_MAX - 0.5; }
+static std::vector<std::vector<C>> g_store;
+#ifdef DEVICE_CHECK
+static const C* rnd_array(size_t n, double scale = 1.0) {
+    C* p; cudaMallocManaged(&p, n * sizeof(C));
+    for (size_t i = 0; i < n; ++i) p[i] = mkC(scale * rnd(), scale * rnd());
+    return p;
+}
+template <int KIND, int CH>
+__global__ void dev_run(DevChain V, ColJob job, ColDev cols, const C* R, const C* T, Grid g, C* out) {
+    out[threadIdx.x] = column_thread<KIND, CH>(V, job, cols, R, T, g, 0, threadIdx.x, blockDim.x);
+}
+#else
+static const C* rnd_array(size_t n, double scale = 1.0) {
+    g_store.emplace_back(n);
+    for (auto& x : g_store.back()) x = mkC(scale * rnd(), scale * rnd());
+    return g_store.back().data();
+}
+#endif
+
+template <int KIND, int CH>
+static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_only, int Nin) {
+    constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
+    const int NP = g.NP, L = g.L, nw = 2 * Nin, nB2 = 2 * g.nK2b - 1, nF2 = 2 * g.nK2f;
+    const bool is_sde = (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH);
+    const int slabN = is_sde ? g.nPiB : g.nK2b, nBs = 2 * slabN - 1;
+    ColJob job; job.lev_first = lev_first; job.n_nl2 = 0; while (job.n_nl2 < V.nlev && V.lev[job.n_nl2].type == LV_NL2) job.n_nl2++;
+    job.own_only = own_only; job.nw = nw; job.Ninner = Nin; job.slabW_N = slabN; job.scale_re = 1.0; job.scale_im = 0.0;
+    const C* R = rnd_array((size_t)nw * NP * nBs * NP);
+#ifdef DEVICE_CHECK
+    C* Tm; cudaMallocManaged(&Tm, (size_t)nw * nF2 * nB2 * sizeof(C));
+    struct { C* p; size_t n; C* data() { return p; } size_t size() { return n; } C& operator[](size_t i) { return p[i]; } } T = {Tm, (size_t)nw * nF2 * nB2};
+    int* mi; cudaMallocManaged(&mi, 64 * sizeof(int)); C* dout; cudaMallocManaged(&dout, 128 * sizeof(C));
+    double maxdev = 0.0;
+#else
+    std::vector<C> T((size_t)nw * nF2 * nB2);
+#endif
+    for (size_t i = 0; i < T.size(); ++i) T[i] = loc_table_entry<KIND, CH>(V, job, g, (long long)i);
+    double maxerr = 0.0, maxval = 0.0;
+    for (int trial = 0; trial < 12; ++trial) {
+        int iW = rand() % nB2, iP = rand() % NP, ik = rand() % NP;
+        int nrep = 1 + rand() % std::min(FDGA_NV, nF2);
+        std::vector<int> inu(nrep), cls(nrep);
+        for (int n = 0; n < nrep; ++n) { inu[n] = (n * 3 + trial) % nF2; cls[n] = n; }
+        int start[2] = {0, nrep};
+        ColDev cols; cols.ncol = 1; cols.iW = &iW; cols.iP = &iP; cols.ik = &ik; cols.start = start; cols.rep_inu = inu.data(); cols.rep_cls = cls.data();
+        int NVc = 1; while (NVc < nrep) NVc <<= 1;
+        std::vector<C> got(nrep, zeroC());
+        const int nthreads = 128;
+        for (int tid = 0; tid < nthreads; ++tid) {
+            C a = column_thread<KIND, CH>(V, job, cols, R, (KIND == JOB_LK2) ? nullptr : T.data(), g, 0, tid, nthreads);
+            int n = tid & (NVc - 1);
+            if (n < nrep) got[n] += a;
+        }
+#ifdef DEVICE_CHECK
+        {   // the same column_thread on the device
+            mi[0] = iW; mi[1] = iP; mi[2] = ik; mi[3] = 0; mi[4] = nrep;
+            for (int n = 0; n < nrep; ++n) { mi[8 + n] = inu[n]; mi[24 + n] = cls[n]; }
+            ColDev dc; dc.ncol = 1; dc.iW = mi; dc.iP = mi + 1; dc.ik = mi + 2; dc.start = mi + 3; dc.rep_inu = mi + 8; dc.rep_cls = mi + 24;
+            dev_run<KIND, CH><<<1, nthreads>>>(V, job, dc, R, (KIND == JOB_LK2) ? nullptr : T.data(), g, dout);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); exit(2); }
+            std::vector<C> dgot(nrep, zeroC());
+            for (int tid = 0; tid < nthreads; ++tid) { int n = tid & (NVc - 1); if (n < nrep) dgot[n] += dout[tid]; }
+            for (int n = 0; n < nrep; ++n) {
+                double d = std::max(std::fabs(dgot[n].x - got[n].x), std::fabs(dgot[n].y - got[n].y));
+                if (d > 1e-10) printf("    DEVICE != HOST trial %d rep %d (iW %d iP %d ik %d inu %d nrep %d): dev (%g,%g) host (%g,%g)\n", trial, n, iW, iP, ik, inu[n], nrep, dgot[n].x, dgot[n].y, got[n].x, got[n].y);
+                maxdev = std::max(maxdev, d);
+            }
+        }
+#endif
+        // brute force with the per-term evaluator (the arithmetic of bse_k2_kernel / bse_lk2_kernel / sde_L_kernel)
+        const int W = iW - (g.nK2b - 1), Px = iP % L, Py = iP / L, kx = ik % L, ky = ik / L;
+        const C* slab = R + (size_t)nw * NP * (posB(W, slabN) + (size_t)nBs * iP);
+        for (int n = 0; n < nrep; ++n) {
+            const int nu = inu[n] - g.nK2f;
+            C ref = zeroC();
+            for (int iq = 0; iq < NP; ++iq) for (int iw = 0; iw < nw; ++iw) {
+                const int w = iw - Nin, qx = iq % L, qy = iq / L;
+                Arg a; a.W = W; a.Px = Px; a.Py = Py;
+                C d;
+                if (KIND == JOB_K2 || KIND == JOB_K2_MF) {
+                    a.v = nu; a.kx = kx; a.ky = ky;
+                    if (KIND == JOB_K2_MF) { a.w = (CH == CH_P) ? W - w - 1 : w; a.qx = (CH == CH_P) ? Px - qx : qx; a.qy = (CH == CH_P) ? Py - qy : qy; }
+                    else { a.w = w; a.qx = qx; a.qy = qy; }
+                    C f1 = eval_vertex<false>(V, lev_first, CH, SP, a, FL_ALL); a.v = FDGA_INF;
+                    d = f1 - eval_vertex<false>(V, lev_first, CH, SP, a, FL_ALL);
+                } else if (KIND == JOB_LK2) {
+                    const unsigned FLG = (CH == CH_P ? 0u : FL_GP) | (CH == CH_T ? 0u : FL_GT) | (CH == CH_A ? 0u : FL_GA);
+                    a.v = nu; a.kx = kx; a.ky = ky; a.w = (CH == CH_P) ? W - w - 1 : w; a.qx = (CH == CH_P) ? Px - qx : qx; a.qy = (CH == CH_P) ? Py - qy : qy;
+                    d = eval_vertex<false>(V, 0, CH, SP, a, FLG);
+                } else if (KIND == JOB_SDE_PP) {
+                    a.v = W - w - 1; a.w = nu; a.kx = Px - qx; a.ky = Py - qy; a.qx = kx; a.qy = ky;
+                    const DevLevel& lv = V.lev[lev_first];
+                    if (lv.type == LV_CORE) d = core_eval(lv, CH_P, SP_P, a.W, a.v, a.w) - lv.U;
+                    else if (own_only) d = eval_vertex<false>(V, lev_first, CH_P, SP_P, a, FL_GP);
+                    else d = eval_vertex<false>(V, lev_first, CH_P, SP_P, a, FL_F0 | FL_GP) - eval_vertex<false>(V, lev_first + 1, CH_P, SP_P, a, FL_F0 | FL_GP);
+                } else {
+                    a.v = nu; a.w = w; a.kx = kx; a.ky = ky; a.qx = qx; a.qy = qy;
+                    const DevLevel& lv = V.lev[lev_first];
+                    if (lv.type == LV_CORE) d = core_eval(lv, CH_A, SP_P, W, nu, w) + core_eval(lv, CH_T, SP_P, W, nu, w) - lv.U - lv.U;
+                    else if (own_only) d = eval_vertex<false>(V, lev_first, CH_A, SP_P, a, FL_GA) + eval_vertex<false>(V, lev_first, CH_T, SP_P, a, FL_GT);
+                    else d = eval_vertex<false>(V, lev_first, CH_A, SP_P, a, FL_F0 | FL_GA) + eval_vertex<false>(V, lev_first, CH_T, SP_P, a, FL_F0 | FL_GT)
+                           - eval_vertex<false>(V, lev_first + 1, CH_A, SP_P, a, FL_F0 | FL_GA) - eval_vertex<false>(V, lev_first + 1, CH_T, SP_P, a, FL_F0 | FL_GT);
+                }
+                ref += d * slab[iw + (size_t)nw * iq];
+            }
+            maxerr = std::max(maxerr, std::max(std::fabs(ref.x - got[n].x), std::fabs(ref.y - got[n].y)));
+            maxval = std::max(maxval, std::max(std::fabs(ref.x), std::fabs(ref.y)));
+        }
+    }
+    return maxerr / std::max(maxval, 1e-300);
+}
+
+static DevLevel make_level(int type, int nK1, int nK2b, int nK2f, int nK3b, int nK3f, int NP) {
+    DevLevel lv; memset(&lv, 0, sizeof(lv));
+    lv.type = type; lv.nK1 = nK1; lv.nK2b = nK2b; lv.nK2f = nK2f; lv.nK3b = nK3b; lv.nK3f = nK3f;
+    int np = (type == LV_NL2) ? NP : 1;
+    for (int r = 0; r < 3; ++r) {
+        lv.ch[r].K1 = rnd_array((size_t)(2 * nK1 - 1) * np);
+        lv.ch[r].K2 = rnd_array((size_t)(2 * nK2b - 1) * (2 * nK2f) * np * np);
+        lv.ch[r].K3 = rnd_array((size_t)(2 * nK3b - 1) * (2 * nK3f) * (2 * nK3f) * np);
+    }
+    return lv;
+}
+
+int main() {
+    setvbuf(stdout, NULL, _IONBF, 0);
+    srand(4242);
+    double worst = 0.0;
+    for (int cfg = 0; cfg < 3; ++cfg) {
+        g_store.clear(); g_store.reserve(4096);
+        const int L = (cfg == 0) ? 3 : (cfg == 1 ? 4 : 2), NP = L * L;
+        Grid g; memset(&g, 0, sizeof(g));
+        g.T = 0.3; g.L = L; g.NP = NP; g.nK1 = (cfg == 1) ? 6 : 5; g.nPiB = g.nK1; g.nPiF = g.nK1;
+        g.nK2b = 3; g.nK2f = (cfg == 1) ? 4 : 2; g.nK3b = 2; g.nK3f = 2;
+        DevChain V; memset(&V, 0, sizeof(V)); V.L = L; V.NP = NP; V.nlev = 4;
+        V.lev[0] = make_level(LV_NL2, g.nK1, g.nK2b, g.nK2f, g.nK3b, g.nK3f, NP);
+        V.lev[1] = (cfg == 2) ? make_level(LV_NL2, 7, 4, 3, 2, 1, NP) : make_level(LV_NL2, g.nK1, g.nK2b, g.nK2f, g.nK3b, g.nK3f, NP);
+        V.lev[2] = make_level(LV_LOCAL, 9, 5, 4, 1, 1, NP);
+        DevLevel core; memset(&core, 0, sizeof(core)); core.type = LV_CORE; core.nK3b = 3; core.nK3f = 2; core.U = mkC(1.7, 0.0);
+        for (int i = 0; i < 4; ++i) core.core[i] = rnd_array((size_t)5 * 4 * 4);
+        V.lev[3] = core;
+        double e = 0;
+#define RUN(K, CHT, lf, oo, NN) { double x = run_job<K, CHT>(V, g, lf, oo, NN); printf("  cfg %d %-10s ch %d lev %d own %d : %.3e\n", cfg, #K, CHT, lf, oo, x); e = std::max(e, x); }
+        RUN(JOB_K2, CH_P, 0, 0, g.nPiF) RUN(JOB_K2, CH_T, 0, 0, g.nPiF) RUN(JOB_K2, CH_A, 0, 0, g.nPiF)
+        RUN(JOB_K2_MF, CH_P, 1, 0, g.nPiF) RUN(JOB_K2_MF, CH_T, 1, 0, g.nPiF) RUN(JOB_K2_MF, CH_A, 1, 0, g.nPiF)
+        RUN(JOB_LK2, CH_P, 0, 0, g.nK2f) RUN(JOB_LK2, CH_T, 0, 0, g.nK2f) RUN(JOB_LK2, CH_A, 0, 0, g.nK2f)
+        for (int lf = 0; lf < 4; ++lf) for (int oo = 0; oo < 2; ++oo) { RUN(JOB_SDE_PP, CH_P, lf, oo, g.nPiF) RUN(JOB_SDE_PH, CH_A, lf, oo, g.nPiF) }
+        worst = std::max(worst, e);
+    }
+    printf("WORST %.3e\n", worst);
+    return worst < 1e-11 ? 0 : 1;
+}
