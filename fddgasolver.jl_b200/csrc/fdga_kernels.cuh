@@ -84,6 +84,12 @@ __global__ void expand_kernel(C* __restrict__ out, const C* __restrict__ repvals
     if (j >= sg.nmem) return;
     out[sg.index[j]] = apply_op(sg.ops[j], repvals[sg.member_class[j]]);
 }
+// accumulate variant: out[index[j]] += w * op_j(repvals[class(j)])
+__global__ void expand_add_kernel(C* __restrict__ out, const C* __restrict__ repvals, SymDev sg, double w) {
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= sg.nmem) return;
+    out[sg.index[j]] += apply_op(sg.ops[j], repvals[sg.member_class[j]]) * w;
+}
 // SG(f): symmetrise in place from the representatives
 __global__ void symmetrize_kernel(C* __restrict__ f, SymDev sg) {
     long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -433,19 +439,28 @@ __global__ void sde_L_kernel(const __grid_constant__ DevChain V, int level, cons
 
 // ---- small DFT along one axis (FFTW conventions: sgn=-1 forward, +1 backward, unnormalised) -----------
 // data viewed as [pre][n][post] column-major; out-of-place; result multiplied by `scale`.
-__global__ void dft_axis_kernel(const C* __restrict__ in, C* __restrict__ out, long long pre, int n, long long post, int sgn, double scale) {
+__global__ void dft_axis_kernel(const C* __restrict__ in, C* __restrict__ out, long long pre, int n, long long post, int sgn, double scale,
+                                const C* __restrict__ tw /* tw[j] = exp(+2 pi i j / n) */) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long tot = pre * n * post;
     if (i >= tot) return;
     long long a = i % pre; long long t = i / pre; int k = t % n; long long b = t / n;
     const C* p = in + a + pre * n * b;
     C s = zeroC();
+    int jk = 0;
     for (int j = 0; j < n; ++j) {
-        double sn, cs;
-        sincospi(2.0 * (double)(((long long)j * k) % n) / (double)n, &sn, &cs);
-        s += p[pre * j] * mkC(cs, sgn * sn);
+        C w = tw[jk];
+        if (sgn < 0) w.y = -w.y;
+        s += p[pre * j] * w;
+        jk += k; if (jk >= n) jk -= n;
     }
     out[i] = s * scale;
+}
+__global__ void twiddle_kernel(C* tw, int n) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double sn, cs; sincospi(2.0 * (double)j / (double)n, &sn, &cs);
+    tw[j] = mkC(cs, sn);
 }
 
 // G_R(n) call semantics: 0 outside the fermionic mesh

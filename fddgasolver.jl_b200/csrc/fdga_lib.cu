@@ -84,6 +84,8 @@ struct fdga_ctx {
     int opt_generic;         // FDGA_OPT_GENERIC_KERNELS
     int n_nl2;               // leading NL2 levels of the F chain
     C* Ttab;                 // momentum-independent left-factor table [nw, nF2, nB2]
+    C* twL; C* twLG;         // DFT twiddles exp(2 pi i j / n) for n = L, LG
+    C* Rt3[3]; int rt_kind[3]; // per-channel right factors (W on the bubble mesh) reused between BSE_K1! and BSE_K2!
     std::string err;
 };
 
@@ -91,6 +93,7 @@ struct fdga_ctx {
     ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } } while (0)
 #define FAIL(msg) do { ctx->err = (msg); return 1; } while (0)
 
+static void invalidate_rt(fdga_ctx* ctx) { ctx->rt_kind[0] = ctx->rt_kind[1] = ctx->rt_kind[2] = -1; }
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
 // profiling scope: CUDA events on the launching stream around a group of launches
@@ -247,17 +250,17 @@ static int tfix(fdga_ctx* ctx, C* Xt, const C* Xa, size_t n) { return axpby(ctx,
 static int dft2_G(fdga_ctx* ctx, const C* in, C* out, C* tmp, int sgn, double scale, int cat) {
     long long nGf = 2 * ctx->g.nG, LG = ctx->g.LG;
     long long n = nGf * LG * LG;
-    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, in, tmp, nGf, (int)LG, LG, sgn, 1.0);
-    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, tmp, out, nGf * LG, (int)LG, 1LL, sgn, scale);
+    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, in, tmp, nGf, (int)LG, LG, sgn, 1.0, ctx->twLG);
+    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, tmp, out, nGf * LG, (int)LG, 1LL, sgn, scale, ctx->twLG);
     CK(cudaGetLastError()); return 0;
 }
 // 4-d DFT over the momentum axes of a [pre, L, L, L, L] array; result ends up in `a` (b = scratch)
 static int dft4(fdga_ctx* ctx, C* a, C* b, long long pre, int sgn, double scale, int cat) {
     long long L = ctx->g.L, n = pre * L * L * L * L;
-    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, a, b, pre, (int)L, L * L * L, sgn, 1.0);
-    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, b, a, pre * L, (int)L, L * L, sgn, 1.0);
-    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, a, b, pre * L * L, (int)L, L, sgn, 1.0);
-    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, b, a, pre * L * L * L, (int)L, 1LL, sgn, scale);
+    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, a, b, pre, (int)L, L * L * L, sgn, 1.0, ctx->twL);
+    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, b, a, pre * L, (int)L, L * L, sgn, 1.0, ctx->twL);
+    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, a, b, pre * L * L, (int)L, L, sgn, 1.0, ctx->twL);
+    LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, b, a, pre * L * L * L, (int)L, 1LL, sgn, scale, ctx->twL);
     CK(cudaGetLastError()); return 0;
 }
 
@@ -354,6 +357,10 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     CKC(cudaMalloc(&ctx->flat, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->flat2, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->stash, ctx->lenFlat * sizeof(C)));
     CKC(cudaMalloc(&ctx->d_occ, sizeof(double)));
     ctx->n_nl2 = 0; while (ctx->n_nl2 < ctx->nlev && dims->lev[ctx->n_nl2].type == FDGA_LV_NL2) ctx->n_nl2++;
+    CKC(cudaMalloc(&ctx->twL, g.L * sizeof(C))); CKC(cudaMalloc(&ctx->twLG, g.LG * sizeof(C)));
+    twiddle_kernel<<<nblk(g.L, 64), 64, 0, ctx->stream>>>(ctx->twL, g.L);
+    twiddle_kernel<<<nblk(g.LG, 64), 64, 0, ctx->stream>>>(ctx->twLG, g.LG);
+    for (int i = 0; i < 3; i++) { CKC(cudaMalloc(&ctx->Rt3[i], ctx->lenPi * sizeof(C))); ctx->rt_kind[i] = -1; }
     CKC(cudaMalloc(&ctx->Ttab, (size_t)(2 * g.nPiF) * (2 * g.nK2f) * (2 * g.nK2b - 1) * sizeof(C)));
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; s.ncol = 0; s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = nullptr; }
     CKC(cudaStreamSynchronize(ctx->stream));
@@ -373,7 +380,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
     cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->Rt); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB);
     cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
-    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); cudaFree(ctx->Ttab);
+    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); cudaFree(ctx->Ttab); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]);
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); cudaFree(s.d_repvals);
         cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); }
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
@@ -452,6 +459,7 @@ int fdga_set_vertex(fdga_ctx* ctx, int which, int channel, int cls, const fdga_c
     CK(cudaMemcpyAsync(lb->K[channel][cls], host, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     lb->sw_dirty = true;
+    invalidate_rt(ctx);
     return 0;
 }
 int fdga_get_vertex(fdga_ctx* ctx, int which, int channel, int cls, fdga_c64* host, int64_t n) {
@@ -469,6 +477,7 @@ int fdga_set_core(fdga_ctx* ctx, int level, int which4, const fdga_c64* host, in
     if ((size_t)n != ctx->lev[level].corelen) FAIL("fdga_set_core: length mismatch");
     CK(cudaMemcpyAsync(ctx->lev[level].core[which4], host, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    invalidate_rt(ctx);
     return 0;
 }
 #define SETGET(NAME, ARR, COUNT, LEN, DIRTY) \
@@ -485,7 +494,7 @@ int fdga_get_##NAME(fdga_ctx* ctx, int which, fdga_c64* host, int64_t n) { \
     CK(cudaMemcpyAsync(host, ctx->ARR[which], n * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream)); \
     CK(cudaStreamSynchronize(ctx->stream)); return 0; }
 SETGET(green, G, 5, ctx->lenG, (void)0)
-SETGET(bubble, Pi, 4, ctx->lenPi, ctx->pi_dirty[which] = true)
+SETGET(bubble, Pi, 4, ctx->lenPi, (ctx->pi_dirty[which] = true, invalidate_rt(ctx)))
 SETGET(cache, cache, 10, ctx->lenK3, (void)0)
 int fdga_get_L(fdga_ctx* ctx, int is_pp, fdga_c64* host, int64_t n) {
     CK(cudaSetDevice(ctx->device));
@@ -604,6 +613,7 @@ int fdga_bubbles_real_space(fdga_ctx* ctx, int reference) {
     if (dft4(ctx, ctx->Pi[ipp], ctx->scratchA, pre, +1, 1.0, FDGA_T_BUBBLE)) return 1;
     if (dft4(ctx, ctx->Pi[iph], ctx->scratchA, pre, +1, 1.0, FDGA_T_BUBBLE)) return 1;
     ctx->pi_dirty[ipp] = ctx->pi_dirty[iph] = true;
+    invalidate_rt(ctx);
     return 0;
 }
 int fdga_bubbles_momentum_space(fdga_ctx* ctx, int reference) {
@@ -614,6 +624,7 @@ int fdga_bubbles_momentum_space(fdga_ctx* ctx, int reference) {
     LAUNCH(FDGA_T_BUBBLE, bubbles_ms_kernel, nblk(ctx->lenPi, 128), 128, ctx->G[reference ? FDGA_G0 : FDGA_G], ctx->Pi[ipp], ctx->Pi[iph], ctx->g);
     CK(cudaGetLastError());
     ctx->pi_dirty[ipp] = ctx->pi_dirty[iph] = true;
+    invalidate_rt(ctx);
     return 0;
 }
 
@@ -650,13 +661,14 @@ static int pi_kind(int ch, bool reference) { return ch == FDGA_PCH ? (reference 
 
 extern "C++" {
 template <int KIND>
-static int launch_right(fdga_ctx* ctx, int ch, const DevChain& F0, const DevChain& FL, int No, int Ninner) {
+static int launch_right(fdga_ctx* ctx, int ch, const DevChain& F0, const DevChain& FL, int No, int Ninner, C* Rdst = nullptr) {
+    if (!Rdst) Rdst = ctx->Rt;
     Scope sc(ctx, FDGA_T_RIGHT);
     const C* p0 = ctx->PiT[pi_kind(ch, true)]; const C* p1 = ctx->PiT[pi_kind(ch, false)];
     long long n = (long long)(2 * Ninner) * ctx->g.NP * (2 * No - 1) * ctx->g.NP;
-    if (ch == FDGA_PCH)      LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_P, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, ctx->Rt, ctx->g, No, Ninner);
-    else if (ch == FDGA_TCH) LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_T, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, ctx->Rt, ctx->g, No, Ninner);
-    else                     LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_A, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, ctx->Rt, ctx->g, No, Ninner);
+    if (ch == FDGA_PCH)      LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_P, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner);
+    else if (ch == FDGA_TCH) LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_T, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner);
+    else                     LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_A, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner);
     CK(cudaGetLastError());
     return 0;
 }
@@ -687,6 +699,19 @@ static ColJob make_job(fdga_ctx* ctx, int lev_first, int nw, int Ninner, int sla
     j.slabW_N = slabN; j.scale_re = scale.x; j.scale_im = scale.y;
     return j;
 }
+// right factor of channel ch with W on the bubble mesh, cached per channel (K1 and K2 share it: SURVEY App. C.3)
+static int cached_right(fdga_ctx* ctx, int ch, int kind, const DevChain& F0, const DevChain& FL) {
+    int tag = kind;
+    if (kind == RK_MF_K2 && ch != FDGA_PCH) tag = RK_MF_K1;      // _crossing is the identity for a, t
+    if (ctx->rt_kind[ch] == tag) return 0;
+    int rc;
+    if (kind == RK_FD) rc = launch_right<RK_FD>(ctx, ch, F0, FL, ctx->g.nPiB, ctx->g.nPiF, ctx->Rt3[ch]);
+    else if (kind == RK_MF_K1) rc = launch_right<RK_MF_K1>(ctx, ch, F0, FL, ctx->g.nPiB, ctx->g.nPiF, ctx->Rt3[ch]);
+    else rc = launch_right<RK_MF_K2>(ctx, ch, F0, FL, ctx->g.nPiB, ctx->g.nPiF, ctx->Rt3[ch]);
+    if (rc) return rc;
+    ctx->rt_kind[ch] = tag;
+    return 0;
+}
 static int ensure_pi(fdga_ctx* ctx, int ch) {
     if (refresh_pi(ctx, pi_kind(ch, true))) return 1;
     return refresh_pi(ctx, pi_kind(ch, false));
@@ -699,8 +724,7 @@ int fdga_bse_K1(fdga_ctx* ctx, int ch, int mfrg) {
     NEED_SG(FDGA_SG_K1);
     if (ensure_pi(ctx, ch)) return 1;
     DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0), FL = chain_FL(ctx);
-    if (mfrg) { if (launch_right<RK_MF_K1>(ctx, ch, F0, FL, ctx->g.nK1, ctx->g.nPiF)) return 1; }
-    else      { if (launch_right<RK_FD>(ctx, ch, F0, FL, ctx->g.nK1, ctx->g.nPiF)) return 1; }
+    if (cached_right(ctx, ch, mfrg ? RK_MF_K1 : RK_FD, F0, FL)) return 1;
     SymGroup& s = ctx->sg[FDGA_SG_K1];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
     double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
@@ -708,9 +732,9 @@ int fdga_bse_K1(fdga_ctx* ctx, int ch, int mfrg) {
     {
         Scope sc(ctx, FDGA_T_K1);
         if (c1 > c0) {
-            if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_P>, (unsigned)(c1 - c0), 256, left, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
-            else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_T>, (unsigned)(c1 - c0), 256, left, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
-            else                     LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_A>, (unsigned)(c1 - c0), 256, left, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+            if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_P>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+            else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_T>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+            else                     LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_A>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale);
         }
         CK(cudaGetLastError());
     }
@@ -743,7 +767,7 @@ int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
         CK(cudaGetLastError());
     }
     if (sg_finish(ctx, s, ctx->FL.K[ch][1])) return 1;
-    ctx->FL.sw_dirty = true;
+    ctx->FL.sw_dirty = true; invalidate_rt(ctx);
     if (ch == FDGA_TCH) return tfix(ctx, ctx->FL.K[FDGA_TCH][1], ctx->FL.K[FDGA_ACH][1], ctx->FL.len[1]);
     return 0;
 }
@@ -755,15 +779,16 @@ int fdga_bse_K2(fdga_ctx* ctx, int ch, int mfrg) {
     NEED_SG(which);
     if (ensure_pi(ctx, ch)) return 1;
     DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0), FL = chain_FL(ctx);
-    if (mfrg) { if (launch_right<RK_MF_K2>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1; }
-    else      { if (launch_right<RK_FD>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1; }
+    if (!ctx->opt_generic) { if (cached_right(ctx, ch, mfrg ? RK_MF_K2 : RK_FD, F0, FL)) return 1; }
+    else if (mfrg) { if (launch_right<RK_MF_K2>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1; }
+    else           { if (launch_right<RK_FD>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1; }
     SymGroup& s = ctx->sg[which];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
     double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
     if (!ctx->opt_generic) {
-        ColJob job = make_job(ctx, mfrg ? 1 : 0, 2 * ctx->g.nPiF, ctx->g.nPiF, ctx->g.nK2b, mkC(scale, 0.0));
-        if (mfrg) { if (launch_column<JOB_K2_MF>(ctx, ch, F, job, s, ctx->Rt, FDGA_T_K2)) return 1; }
-        else      { if (launch_column<JOB_K2>(ctx, ch, F, job, s, ctx->Rt, FDGA_T_K2)) return 1; }
+        ColJob job = make_job(ctx, mfrg ? 1 : 0, 2 * ctx->g.nPiF, ctx->g.nPiF, ctx->g.nPiB, mkC(scale, 0.0));
+        if (mfrg) { if (launch_column<JOB_K2_MF>(ctx, ch, F, job, s, ctx->Rt3[ch], FDGA_T_K2)) return 1; }
+        else      { if (launch_column<JOB_K2>(ctx, ch, F, job, s, ctx->Rt3[ch], FDGA_T_K2)) return 1; }
     } else {
         Scope sc(ctx, FDGA_T_K2);
         unsigned nb = (unsigned)(c1 - c0);
@@ -809,7 +834,7 @@ int fdga_bse_L_K3(fdga_ctx* ctx, int ch) {
         CK(cudaGetLastError());
     }
     if (sg_finish(ctx, s, ctx->FL.K[ch][2])) return 1;
-    ctx->FL.sw_dirty = true;
+    ctx->FL.sw_dirty = true; invalidate_rt(ctx);
     if (ch == FDGA_TCH) return tfix(ctx, ctx->FL.K[FDGA_TCH][2], ctx->FL.K[FDGA_ACH][2], ctx->FL.len[2]);
     return 0;
 }
@@ -854,50 +879,64 @@ int fdga_set_F_from_Fbuff(fdga_ctx* ctx) {
 }
 
 // ---- SDE -------------------------------------------------------------------------------------------------
-// SDE_compute!(Sigma_out, G, Pipp, Piph, Lpp, Lph, F = chain[level..], ...): src/nonlocal_2/SDE.jl:154-324
-static int sde_compute(fdga_ctx* ctx, C* Sout, int gwhich, bool reference, int level, bool include_U2, bool include_Hartree) {
+// SDE!(Sigma, G, ..., F = chain[from..]): src/SDE.jl:35-48 with SDE_compute! (src/nonlocal_2/SDE.jl:154-324) per level.
+// The real-space contraction, the back transform and SG_Sigma are linear in (Lpp, Lph), so the L arrays of all levels
+// of the F0 chain are accumulated first (weight 1/3 for the RefVertex level, SDE.jl:305-309) and transformed ONCE:
+// identical to the reference's per-level sum up to rounding.  acc += sgn * result.
+static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool reference, int from, bool include_U2, bool include_Hartree) {
     NEED_SG(FDGA_SG_SIGMA); NEED_SG(FDGA_SG_PP2); NEED_SG(FDGA_SG_PH2);
     const Grid& g = ctx->g;
     if (refresh_pi(ctx, reference ? FDGA_PI0PP : FDGA_PIPP) || refresh_pi(ctx, reference ? FDGA_PI0PH : FDGA_PIPH)) return 1;
     DevChain V = chain_F(ctx, 0);
     C U = bareU(ctx);
     double scale = g.T / (double)g.NP;
-    for (int pp = 1; pp >= 0; pp--) {
-        SymGroup& s = ctx->sg[pp ? FDGA_SG_PP2 : FDGA_SG_PH2];
-        long long c0, c1; sg_class_range(ctx, s, c0, c1);
-        const C* PiT = ctx->PiT[pp ? (reference ? FDGA_PI0PP : FDGA_PIPP) : (reference ? FDGA_PI0PH : FDGA_PIPH)];
-        if (!ctx->opt_generic) {
-            ColJob job = make_job(ctx, level, 2 * g.nPiF, g.nPiF, g.nPiB, U * scale);
-            if (pp) { if (launch_column_t<JOB_SDE_PP, CH_P>(ctx, V, job, s, PiT, FDGA_T_SDE_L)) return 1; }
-            else    { if (launch_column_t<JOB_SDE_PH, CH_A>(ctx, V, job, s, PiT, FDGA_T_SDE_L)) return 1; }
-        } else {
-            Scope sc(ctx, FDGA_T_SDE_L);
-            if (c1 > c0) {
-                if (pp) LAUNCH(FDGA_T_SDE_L, sde_L_kernel<true>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma);
-                else    LAUNCH(FDGA_T_SDE_L, sde_L_kernel<false>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma);
+    size_t nK2 = ctx->lev[0].len[1];
+    CK(cudaMemsetAsync(ctx->L[0], 0, nK2 * sizeof(C), ctx->stream));
+    CK(cudaMemsetAsync(ctx->L[1], 0, nK2 * sizeof(C), ctx->stream));
+    for (int level = from; level < ctx->nlev; level++) {
+        double wl = (ctx->lev[level].d.type == FDGA_LV_CORE) ? 1.0 / 3.0 : 1.0;
+        for (int pp = 1; pp >= 0; pp--) {
+            SymGroup& s = ctx->sg[pp ? FDGA_SG_PP2 : FDGA_SG_PH2];
+            long long c0, c1; sg_class_range(ctx, s, c0, c1);
+            const C* PiT = ctx->PiT[pp ? (reference ? FDGA_PI0PP : FDGA_PIPP) : (reference ? FDGA_PI0PH : FDGA_PIPH)];
+            if (!ctx->opt_generic) {
+                ColJob job = make_job(ctx, level, 2 * g.nPiF, g.nPiF, g.nPiB, U * scale);
+                if (pp) { if (launch_column_t<JOB_SDE_PP, CH_P>(ctx, V, job, s, PiT, FDGA_T_SDE_L)) return 1; }
+                else    { if (launch_column_t<JOB_SDE_PH, CH_A>(ctx, V, job, s, PiT, FDGA_T_SDE_L)) return 1; }
+            } else {
+                Scope sc(ctx, FDGA_T_SDE_L);
+                if (c1 > c0) {
+                    if (pp) LAUNCH(FDGA_T_SDE_L, sde_L_kernel<true>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma);
+                    else    LAUNCH(FDGA_T_SDE_L, sde_L_kernel<false>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma);
+                }
+                CK(cudaGetLastError());
             }
+            if (ctx->nranks > 1) {
+                Scope sc(ctx, FDGA_T_COMM);
+                int rc = ctx->nccl.AllGather(s.d_repvals + (size_t)ctx->rank * s.chunk, s.d_repvals, (size_t)s.chunk * 2, /*ncclDouble*/ 8, ctx->comm, ctx->stream);
+                if (rc != 0) FAIL(std::string("ncclAllGather: ") + ctx->nccl.GetErrorString(rc));
+                ctx->n_launch[FDGA_T_COMM]++;
+            }
+            Scope sc(ctx, FDGA_T_EXPAND);
+            LAUNCH(FDGA_T_EXPAND, expand_add_kernel, nblk(s.nmem, 256), 256, ctx->L[pp ? 0 : 1], s.d_repvals, sym_dev(s), wl);
             CK(cudaGetLastError());
         }
-        if (sg_finish(ctx, s, ctx->L[pp ? 0 : 1])) return 1;
     }
+    C* Sout = ctx->SigAcc;
     {
         Scope sc(ctx, FDGA_T_SDE_RS);
         if (dft2_G(ctx, ctx->G[gwhich], ctx->GR, ctx->SigTmp, -1, 1.0 / ((double)g.LG * g.LG), FDGA_T_SDE_RS)) return 1;
         long long pre = (long long)(2 * g.nK2b - 1) * (2 * g.nK2f);
         double nrm = 1.0 / ((double)g.L * g.L * g.L * g.L);
-        size_t nK2 = ctx->lev[0].len[1];
         // L arrays are transformed in place (clobbered, as in the reference: SURVEY E4)
         if (dft4(ctx, ctx->L[0], ctx->scratchA, pre, -1, nrm, FDGA_T_SDE_RS)) return 1;
         if (dft4(ctx, ctx->L[1], ctx->scratchA, pre, -1, nrm, FDGA_T_SDE_RS)) return 1;
-        (void)nK2;
         CK(cudaMemsetAsync(ctx->SigR, 0, ctx->lenG * sizeof(C), ctx->stream));
         LAUNCH(FDGA_T_SDE_RS, sde_rs_kernel, nblk((long long)(2 * g.nK2f) * g.LG * g.LG, 64), 64, ctx->GR, ctx->L[0], ctx->L[1], ctx->SigR, g, g.nG, g.LG);
         CK(cudaGetLastError());
         if (dft2_G(ctx, ctx->SigR, Sout, ctx->SigTmp, +1, 1.0, FDGA_T_SDE_RS)) return 1;
         SymGroup& ss = ctx->sg[FDGA_SG_SIGMA];
         LAUNCH(FDGA_T_SDE_RS, symmetrize_kernel, nblk(ss.nmem, 256), 256, Sout, sym_dev(ss));
-        if (ctx->lev[level].d.type == FDGA_LV_CORE)
-            LAUNCH(FDGA_T_SDE_RS, scale_copy_kernel, nblk(ctx->lenG, 256), 256, Sout, Sout, 1.0 / 3.0, (long long)ctx->lenG);
         CK(cudaGetLastError());
     }
     if (include_U2) {
@@ -919,16 +958,8 @@ static int sde_compute(fdga_ctx* ctx, C* Sout, int gwhich, bool reference, int l
         LAUNCH(FDGA_T_MISC, hartree_kernel, nblk(ctx->lenG, 256), 256, Sout, ctx->d_occ, U, 1.0, (long long)ctx->lenG);
         CK(cudaGetLastError());
     }
-    return 0;
-}
-// SDE!(Sigma, G, ..., F = chain[from..]): recursion over the F0 chain, src/SDE.jl:35-48.  acc += sgn * result
-static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool reference, int from, bool include_U2, bool include_Hartree) {
-    for (int l = from; l < ctx->nlev; l++) {
-        bool top = (l == from);
-        if (sde_compute(ctx, ctx->SigAcc, gwhich, reference, l, top && include_U2, top && include_Hartree)) return 1;
-        LAUNCH(FDGA_T_MISC, add_axpby_kernel, nblk(ctx->lenG, 256), 256, acc, ctx->SigAcc, sgn, (const C*)nullptr, 0.0, (long long)ctx->lenG);
-        CK(cudaGetLastError());
-    }
+    LAUNCH(FDGA_T_MISC, add_axpby_kernel, nblk(ctx->lenG, 256), 256, acc, Sout, sgn, (const C*)nullptr, 0.0, (long long)ctx->lenG);
+    CK(cudaGetLastError());
     return 0;
 }
 int fdga_sde(fdga_ctx* ctx, int strategy, int include_U2, int include_Hartree) {
