@@ -198,15 +198,17 @@ FDGA_HD C loc_table_entry(const DevChain& V, const ColJob& job, const Grid& g, l
                 x = eval_vertex<false>(V, max(lloc, job.lev_first), form, SP_P, a, FL_ALL) - eval_vertex<false>(V, max(lloc, job.lev_first), form, SP_P, ai, FL_ALL);
             }
         } else if (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH) {
-            const int l = job.lev_first;
-            const DevLevel& lv = V.lev[l];
-            if (lv.type == LV_CORE) {
-                x = core_eval(lv, form, SP_P, a.W, a.v, a.w) - lv.U;
-            } else {
-                if (lv.type == LV_LOCAL) x += loc_chan(lv, form, a.W, a.v, a.w);
-                if (!job.own_only && l + 1 < V.nlev && V.lev[l + 1].type == LV_LOCAL) {
+            // all momentum-independent pieces of the fused recursion: own gamma of every LOCAL level m >= l0, the cross
+            // channels of every LOCAL level m > l0 (E2), and (core - U) / 3 for the terminating RefVertex
+            for (int m = job.lev_first; m < V.nlev; ++m) {
+                const DevLevel& lv = V.lev[m];
+                if (lv.type == LV_CORE) { x += (core_eval(lv, form, SP_P, a.W, a.v, a.w) - lv.U) * (1.0 / 3.0); }
+                else if (lv.type == LV_LOCAL) {
+                    x += loc_chan(lv, form, a.W, a.v, a.w);
+                    if (!job.own_only && m > job.lev_first) {
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) if (r != form) { Arg b = convert(a, form, r); x += loc_chan(V.lev[l + 1], r, b.W, b.v, b.w); }
+                        for (int r = 0; r < 3; ++r) if (r != form) { Arg b = convert(a, form, r); x += loc_chan(lv, r, b.W, b.v, b.w); }
+                    }
                 }
             }
         }
@@ -252,7 +254,7 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
     const int wchunk = (nw + WS - 1) / WS;
     const int l0 = job.lev_first;
     const bool is_sde = (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH);
-    const int l_end = (KIND == JOB_LK2) ? l0 + 1 : (is_sde ? min(l0 + 2, job.n_nl2) : job.n_nl2);
+    const int l_end = (KIND == JOB_LK2) ? l0 + 1 : job.n_nl2;
 
     if (active)
     for (int item = qs; item < NP * WS; item += nqs) {
@@ -273,16 +275,14 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
             // which pieces come from which NL2 level:
             //   K2 jobs : every leading NL2 level of the left chain: cross channels + own-channel (nu - inf) difference
             //   L_K2    : level l0 only, cross channels only (F0 = false, own gamma off)
-            //   SDE     : own gamma of level l0 in full + cross channels of level l0 + 1 ("as coded")
+            //   SDE     : all levels l >= l0 of the recursion SDE!(..., F.F0) fused: own gamma of level l in full, plus
+            //             ("as coded") the cross channels of every level l > l0
             for (int l = l0; l < l_end; ++l) {
                 const DevLevel& lv = V.lev[l];
                 bool do_own_full = false, do_own_diff = false, do_cross = false;
                 if (KIND == JOB_K2 || KIND == JOB_K2_MF) { do_own_diff = true; do_cross = true; }
                 else if (KIND == JOB_LK2) { do_cross = true; }
-                else {
-                    if (l == l0) do_own_full = true;
-                    else { do_cross = !job.own_only; if (!do_cross) break; }
-                }
+                else { do_own_full = true; do_cross = (!job.own_only && l > l0); }
                 MomOff mo[3];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) mo[r] = mom_offsets(lv, form, r, L, NP, Px, Py, akx, aky, aqx, aqy);

@@ -85,6 +85,7 @@ struct fdga_ctx {
     int n_nl2;               // leading NL2 levels of the F chain
     C* Ttab;                 // momentum-independent left-factor table [nw, nF2, nB2]
     C* twL; C* twLG;         // DFT twiddles exp(2 pi i j / n) for n = L, LG
+    LevelBuf Fsum; bool has_fsum, fsum_dirty;   // K tables of lev[0] + lev[1] when both are NL2 on identical meshes
     C* Rt3[3]; int rt_kind[3]; // per-channel right factors (W on the bubble mesh) reused between BSE_K1! and BSE_K2!
     std::string err;
 };
@@ -178,6 +179,14 @@ static DevChain chain_FL(fdga_ctx* ctx) {
     c.lev[0] = dev_level(ctx->FL); c.lev[1] = null_core();
     return c;
 }
+// chain [lev0 + lev1, lev2, ...] used as the left vertex of BSE_K2! (fd) when the two NL2 levels share their meshes
+static DevChain chain_F_merged(fdga_ctx* ctx) {
+    DevChain c; memset(&c, 0, sizeof(c));
+    c.L = ctx->g.L; c.NP = ctx->g.NP; c.nlev = ctx->nlev - 1;
+    c.lev[0] = dev_level(ctx->Fsum);
+    for (int l = 2; l < ctx->nlev; l++) c.lev[l - 1] = dev_level(ctx->lev[l]);
+    return c;
+}
 static SymDev sym_dev(const SymGroup& s) {
     SymDev d; d.ncls = s.ncls; d.nmem = s.nmem; d.offsets = s.d_offsets; d.index = s.d_index; d.ops = s.d_ops; d.member_class = s.d_member_class;
     return d;
@@ -201,6 +210,18 @@ static int refresh_swave(fdga_ctx* ctx) {
         lb.sw_dirty = false;
     }
     CK(cudaGetLastError());
+    return 0;
+}
+static int refresh_fsum(fdga_ctx* ctx) {
+    if (!ctx->has_fsum || !ctx->fsum_dirty) return 0;
+    Scope sc(ctx, FDGA_T_MISC);
+    for (int ch = 0; ch < 3; ch++) for (int cls = 0; cls < 3; cls++) {
+        size_t n = ctx->Fsum.len[cls];
+        axpby_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->Fsum.K[ch][cls], ctx->lev[0].K[ch][cls], 1.0, ctx->lev[1].K[ch][cls], 1.0, (long long)n);
+        ctx->n_launch[FDGA_T_MISC]++; ctx->total_launches++;
+    }
+    CK(cudaGetLastError());
+    ctx->fsum_dirty = false;
     return 0;
 }
 static int refresh_pi(fdga_ctx* ctx, int which) {
@@ -356,6 +377,12 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     ctx->lenFlat = 3 * (ctx->lev[0].len[0] + ctx->lev[0].len[1] + ctx->lev[0].len[2]);
     CKC(cudaMalloc(&ctx->flat, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->flat2, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->stash, ctx->lenFlat * sizeof(C)));
     CKC(cudaMalloc(&ctx->d_occ, sizeof(double)));
+    {   // merged level (S.F + S.F0) for the K2 left factor
+        const fdga_level_desc& a = dims->lev[0]; const fdga_level_desc& b = dims->lev[1];
+        ctx->has_fsum = dims->nlev >= 3 && b.type == FDGA_LV_NL2 && a.nK1 == b.nK1 && a.nK2[0] == b.nK2[0] && a.nK2[1] == b.nK2[1] && a.nK3[0] == b.nK3[0] && a.nK3[1] == b.nK3[1];
+        ctx->fsum_dirty = true; memset(&ctx->Fsum, 0, sizeof(ctx->Fsum));
+        if (ctx->has_fsum && alloc_level(ctx, ctx->Fsum, d0)) { g_create_error = ctx->err; delete ctx; return 1; }
+    }
     ctx->n_nl2 = 0; while (ctx->n_nl2 < ctx->nlev && dims->lev[ctx->n_nl2].type == FDGA_LV_NL2) ctx->n_nl2++;
     CKC(cudaMalloc(&ctx->twL, g.L * sizeof(C))); CKC(cudaMalloc(&ctx->twLG, g.LG * sizeof(C)));
     twiddle_kernel<<<nblk(g.L, 64), 64, 0, ctx->stream>>>(ctx->twL, g.L);
@@ -374,7 +401,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
     for (int l = 0; l < ctx->nlev; l++) free_level(ctx->lev[l]);
-    free_level(ctx->FL); free_level(ctx->Fbuff);
+    free_level(ctx->FL); free_level(ctx->Fbuff); if (ctx->has_fsum) free_level(ctx->Fsum);
     for (int i = 0; i < 5; i++) cudaFree(ctx->G[i]);
     for (int i = 0; i < 4; i++) { cudaFree(ctx->Pi[i]); cudaFree(ctx->PiT[i]); cudaFree(ctx->Pisw[i]); }
     for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
@@ -458,7 +485,7 @@ int fdga_set_vertex(fdga_ctx* ctx, int which, int channel, int cls, const fdga_c
     if ((size_t)n != lb->len[cls]) FAIL("fdga_set_vertex: length mismatch");
     CK(cudaMemcpyAsync(lb->K[channel][cls], host, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    lb->sw_dirty = true;
+    lb->sw_dirty = true; ctx->fsum_dirty = true;
     invalidate_rt(ctx);
     return 0;
 }
@@ -570,7 +597,7 @@ static int unflatten_dev(fdga_ctx* ctx, LevelBuf& lb, const C* src, double scale
         off += lb.len[cls];
     }
     CK(cudaGetLastError());
-    lb.sw_dirty = true;
+    lb.sw_dirty = true; ctx->fsum_dirty = true;
     return 0;
 }
 int fdga_stash_F(fdga_ctx* ctx) { CK(cudaSetDevice(ctx->device)); return flatten_dev(ctx, ctx->lev[0], ctx->stash); }
@@ -788,6 +815,11 @@ int fdga_bse_K2(fdga_ctx* ctx, int ch, int mfrg) {
     if (!ctx->opt_generic) {
         ColJob job = make_job(ctx, mfrg ? 1 : 0, 2 * ctx->g.nPiF, ctx->g.nPiF, ctx->g.nPiB, mkC(scale, 0.0));
         if (mfrg) { if (launch_column<JOB_K2_MF>(ctx, ch, F, job, s, ctx->Rt3[ch], FDGA_T_K2)) return 1; }
+        else if (ctx->has_fsum) {
+            if (refresh_fsum(ctx)) return 1;
+            job.n_nl2 = ctx->n_nl2 - 1;
+            if (launch_column<JOB_K2>(ctx, ch, chain_F_merged(ctx), job, s, ctx->Rt3[ch], FDGA_T_K2)) return 1;
+        }
         else      { if (launch_column<JOB_K2>(ctx, ch, F, job, s, ctx->Rt3[ch], FDGA_T_K2)) return 1; }
     } else {
         Scope sc(ctx, FDGA_T_K2);
@@ -874,7 +906,7 @@ int fdga_set_F_from_Fbuff(fdga_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     for (int ch = 0; ch < 3; ch++) for (int cls = 0; cls < 3; cls++)
         CK(cudaMemcpyAsync(ctx->lev[0].K[ch][cls], ctx->Fbuff.K[ch][cls], ctx->Fbuff.len[cls] * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
-    ctx->lev[0].sw_dirty = true;
+    ctx->lev[0].sw_dirty = true; ctx->fsum_dirty = true;
     return 0;
 }
 
@@ -893,17 +925,24 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
     size_t nK2 = ctx->lev[0].len[1];
     CK(cudaMemsetAsync(ctx->L[0], 0, nK2 * sizeof(C), ctx->stream));
     CK(cudaMemsetAsync(ctx->L[1], 0, nK2 * sizeof(C), ctx->stream));
+    if (!ctx->opt_generic) {
+        // fused recursion: one column launch per bubble kind covers every level of the chain (fdga_column.cuh)
+        for (int pp = 1; pp >= 0; pp--) {
+            SymGroup& s = ctx->sg[pp ? FDGA_SG_PP2 : FDGA_SG_PH2];
+            const C* PiT = ctx->PiT[pp ? (reference ? FDGA_PI0PP : FDGA_PIPP) : (reference ? FDGA_PI0PH : FDGA_PIPH)];
+            ColJob job = make_job(ctx, from, 2 * g.nPiF, g.nPiF, g.nPiB, U * scale);
+            if (pp) { if (launch_column_t<JOB_SDE_PP, CH_P>(ctx, V, job, s, PiT, FDGA_T_SDE_L)) return 1; }
+            else    { if (launch_column_t<JOB_SDE_PH, CH_A>(ctx, V, job, s, PiT, FDGA_T_SDE_L)) return 1; }
+            if (sg_finish(ctx, s, ctx->L[pp ? 0 : 1])) return 1;
+        }
+    } else
     for (int level = from; level < ctx->nlev; level++) {
         double wl = (ctx->lev[level].d.type == FDGA_LV_CORE) ? 1.0 / 3.0 : 1.0;
         for (int pp = 1; pp >= 0; pp--) {
             SymGroup& s = ctx->sg[pp ? FDGA_SG_PP2 : FDGA_SG_PH2];
             long long c0, c1; sg_class_range(ctx, s, c0, c1);
             const C* PiT = ctx->PiT[pp ? (reference ? FDGA_PI0PP : FDGA_PIPP) : (reference ? FDGA_PI0PH : FDGA_PIPH)];
-            if (!ctx->opt_generic) {
-                ColJob job = make_job(ctx, level, 2 * g.nPiF, g.nPiF, g.nPiB, U * scale);
-                if (pp) { if (launch_column_t<JOB_SDE_PP, CH_P>(ctx, V, job, s, PiT, FDGA_T_SDE_L)) return 1; }
-                else    { if (launch_column_t<JOB_SDE_PH, CH_A>(ctx, V, job, s, PiT, FDGA_T_SDE_L)) return 1; }
-            } else {
+            {
                 Scope sc(ctx, FDGA_T_SDE_L);
                 if (c1 > c0) {
                     if (pp) LAUNCH(FDGA_T_SDE_L, sde_L_kernel<true>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma);

@@ -100,19 +100,26 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
                     const unsigned FLG = (CH == CH_P ? 0u : FL_GP) | (CH == CH_T ? 0u : FL_GT) | (CH == CH_A ? 0u : FL_GA);
                     a.v = nu; a.kx = kx; a.ky = ky; a.w = (CH == CH_P) ? W - w - 1 : w; a.qx = (CH == CH_P) ? Px - qx : qx; a.qy = (CH == CH_P) ? Py - qy : qy;
                     d = eval_vertex<false>(V, 0, CH, SP, a, FLG);
-                } else if (KIND == JOB_SDE_PP) {
-                    a.v = W - w - 1; a.w = nu; a.kx = Px - qx; a.ky = Py - qy; a.qx = kx; a.qy = ky;
-                    const DevLevel& lv = V.lev[lev_first];
-                    if (lv.type == LV_CORE) d = core_eval(lv, CH_P, SP_P, a.W, a.v, a.w) - lv.U;
-                    else if (own_only) d = eval_vertex<false>(V, lev_first, CH_P, SP_P, a, FL_GP);
-                    else d = eval_vertex<false>(V, lev_first, CH_P, SP_P, a, FL_F0 | FL_GP) - eval_vertex<false>(V, lev_first + 1, CH_P, SP_P, a, FL_F0 | FL_GP);
                 } else {
-                    a.v = nu; a.w = w; a.kx = kx; a.ky = ky; a.qx = qx; a.qy = qy;
-                    const DevLevel& lv = V.lev[lev_first];
-                    if (lv.type == LV_CORE) d = core_eval(lv, CH_A, SP_P, W, nu, w) + core_eval(lv, CH_T, SP_P, W, nu, w) - lv.U - lv.U;
-                    else if (own_only) d = eval_vertex<false>(V, lev_first, CH_A, SP_P, a, FL_GA) + eval_vertex<false>(V, lev_first, CH_T, SP_P, a, FL_GT);
-                    else d = eval_vertex<false>(V, lev_first, CH_A, SP_P, a, FL_F0 | FL_GA) + eval_vertex<false>(V, lev_first, CH_T, SP_P, a, FL_F0 | FL_GT)
-                           - eval_vertex<false>(V, lev_first + 1, CH_A, SP_P, a, FL_F0 | FL_GA) - eval_vertex<false>(V, lev_first + 1, CH_T, SP_P, a, FL_F0 | FL_GT);
+                    // fused recursion: sum over levels l >= lev_first of the per-level integrand of sde_L_kernel (core level / 3)
+                    d = zeroC();
+                    for (int l = lev_first; l < V.nlev; ++l) {
+                        const DevLevel& lv = V.lev[l];
+                        C dl;
+                        if (KIND == JOB_SDE_PP) {
+                            a.v = W - w - 1; a.w = nu; a.kx = Px - qx; a.ky = Py - qy; a.qx = kx; a.qy = ky;
+                            if (lv.type == LV_CORE) dl = (core_eval(lv, CH_P, SP_P, a.W, a.v, a.w) - lv.U) * (1.0 / 3.0);
+                            else if (own_only) dl = eval_vertex<false>(V, l, CH_P, SP_P, a, FL_GP);
+                            else dl = eval_vertex<false>(V, l, CH_P, SP_P, a, FL_F0 | FL_GP) - eval_vertex<false>(V, l + 1, CH_P, SP_P, a, FL_F0 | FL_GP);
+                        } else {
+                            a.v = nu; a.w = w; a.kx = kx; a.ky = ky; a.qx = qx; a.qy = qy;
+                            if (lv.type == LV_CORE) dl = (core_eval(lv, CH_A, SP_P, W, nu, w) + core_eval(lv, CH_T, SP_P, W, nu, w) - lv.U - lv.U) * (1.0 / 3.0);
+                            else if (own_only) dl = eval_vertex<false>(V, l, CH_A, SP_P, a, FL_GA) + eval_vertex<false>(V, l, CH_T, SP_P, a, FL_GT);
+                            else dl = eval_vertex<false>(V, l, CH_A, SP_P, a, FL_F0 | FL_GA) + eval_vertex<false>(V, l, CH_T, SP_P, a, FL_F0 | FL_GT)
+                                    - eval_vertex<false>(V, l + 1, CH_A, SP_P, a, FL_F0 | FL_GA) - eval_vertex<false>(V, l + 1, CH_T, SP_P, a, FL_F0 | FL_GT);
+                        }
+                        d += dl;
+                    }
                 }
                 ref += d * slab[iw + (size_t)nw * iq];
             }
