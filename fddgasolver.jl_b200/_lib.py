@@ -26,7 +26,7 @@ T_NAMES = ["cache", "L_K2", "L_K3", "K1", "K2", "K3", "sde_L", "sde_rs", "sde_U2
 
 # every symbol include/fdga.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
-    "fdga_create", "fdga_destroy", "fdga_last_error", "fdga_sync", "fdga_set_option", "fdga_comm_unique_id", "fdga_comm_init",
+    "fdga_create", "fdga_destroy", "fdga_last_error", "fdga_sync", "fdga_set_option", "fdga_comm_unique_id", "fdga_comm_init", "fdga_partition",
     "fdga_set_vertex", "fdga_get_vertex", "fdga_set_core", "fdga_set_green", "fdga_get_green",
     "fdga_set_bubble", "fdga_get_bubble", "fdga_set_cache", "fdga_get_cache", "fdga_get_L",
     "fdga_set_symmetry_classes", "fdga_build_symmetry_group", "fdga_length_F", "fdga_flatten_F",
@@ -74,6 +74,7 @@ def load():
     lib.fdga_set_option.argtypes = [vp, i32, i32]
     lib.fdga_comm_unique_id.argtypes = [vp]
     lib.fdga_comm_init.argtypes = [vp, i32, i32, vp]
+    lib.fdga_partition.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.fdga_set_vertex.argtypes = [vp, i32, i32, i32, vp, i64]
     lib.fdga_get_vertex.argtypes = [vp, i32, i32, i32, vp, i64]
     lib.fdga_set_core.argtypes = [vp, i32, i32, vp, i64]
@@ -140,6 +141,14 @@ def build_symmetry_group(which, n0, n1, nq, length):
     if rc != 0:
         raise FdgaError("fdga_build_symmetry_group failed")
     return offsets[: ncls.value + 1].copy(), index, ops
+
+
+def partition(nclasses, nranks, rank):
+    """(c0, c1, chunk): class representatives [c0, c1) computed by `rank`; `chunk` all-gather slots per rank"""
+    c0, c1, ch = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    if load().fdga_partition(nclasses, nranks, rank, C.byref(c0), C.byref(c1), C.byref(ch)) != 0:
+        raise FdgaError("fdga_partition: bad arguments")
+    return c0.value, c1.value, ch.value
 
 
 def trivial_symmetry_group(length):

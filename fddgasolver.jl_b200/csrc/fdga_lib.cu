@@ -236,10 +236,21 @@ static int refresh_pi(fdga_ctx* ctx, int which) {
 }
 
 // SG finish: (all-gather of representative values) + expansion to all class members
+// contiguous block partition of the class representatives over the ranks (every rank gets `chunk` slots, the
+// last ones may be short or empty); the same arithmetic shards the reference's mpi_split(1:length) ranges
+extern "C" int fdga_partition(int64_t nclasses, int nranks, int rank, int64_t* c0, int64_t* c1, int64_t* chunk) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || nclasses < 0) return 1;
+    int64_t ch = (nclasses + nranks - 1) / nranks;
+    int64_t a = (int64_t)rank * ch, b = a + ch;
+    if (a > nclasses) a = nclasses;
+    if (b > nclasses) b = nclasses;
+    *c0 = a; *c1 = b; if (chunk) *chunk = ch;
+    return 0;
+}
 static int sg_class_range(fdga_ctx* ctx, const SymGroup& s, long long& c0, long long& c1) {
-    c0 = (long long)ctx->rank * s.chunk; c1 = c0 + s.chunk;
-    if (c0 > s.ncls) c0 = s.ncls;
-    if (c1 > s.ncls) c1 = s.ncls;
+    int64_t a, b;
+    fdga_partition(s.ncls, ctx->nranks, ctx->rank, &a, &b, nullptr);
+    c0 = a; c1 = b;
     return 0;
 }
 static int sg_finish(fdga_ctx* ctx, SymGroup& s, C* out) {

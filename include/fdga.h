@@ -89,6 +89,9 @@ int  fdga_set_option(fdga_ctx* ctx, int opt, int value);
  * fdga_comm_unique_id and broadcast by the host (MPI in Julia, torch.distributed in tests). */
 int  fdga_comm_unique_id(void* unique_id_128B);
 int  fdga_comm_init(fdga_ctx* ctx, int nranks, int rank, const void* unique_id_128B);
+/* how class representatives are sharded: rank r computes classes [c0, c1) and all-gathers `chunk` slots per rank
+ * (host-only helper, no context; replaces the mpi_split of src/nonlocal_2/build_K3_cache.jl:35 / SG(...; mode = :hybrid)) */
+int  fdga_partition(int64_t nclasses, int nranks, int rank, int64_t* c0, int64_t* c1, int64_t* chunk);
 
 /* ---- data in / out (replace MeshFunction .data assignment / set!, src/channel.jl:80-150) -- */
 int  fdga_set_vertex(fdga_ctx*, int which, int channel, int cls, const fdga_c64* host, int64_t n);
