@@ -198,6 +198,7 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("FDGA_NCCL_DEBUG", "NONE")     # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     inp = fd.wu_point_inputs(a.nmax, a.nq, a.LG, F0_scale=0.02)
@@ -297,6 +298,18 @@ def run_ours(a):
                 "note": "gather/issue-bound FP64 kernel, not HBM-bound: see fp64",
                 "fp64": {"algorithmic_gflop_per_launch": flop_per_launch / 1e9, "achieved_tflops": flop_per_launch / (k2_ms_launch * 1e-3) / 1e12}}
 
+    # state fingerprint after one more iteration from the stashed vertex: identical on every rank and for every N
+    import hashlib
+    step_resident()
+    S.flatten_F(y_np); S.get_green_into("Σ", s_np)
+    digest = hashlib.sha1(y_np.tobytes() + s_np.tobytes()).hexdigest()[:16]
+    checksum = float(np.abs(y_np).sum() + np.abs(s_np).sum())
+    if dist is not None:
+        objs = [None] * world
+        dist.all_gather_object(objs, digest)
+        if rank == 0 and len(set(objs)) != 1:
+            raise SystemExit(f"bench.py: ranks disagree on the iterated state: {objs}")
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -315,7 +328,7 @@ def run_ours(a):
                           "symmetry_classes": {"K1": S.num_classes(fd._lib.SG_K1), "K2pp": n2cls[0], "K2ph": n2cls[1], "K3pp": S.num_classes(fd._lib.SG_PP3), "K3ph": S.num_classes(fd._lib.SG_PH3)},
                           "parallelism": f"class representatives sharded over {world} rank(s), NCCL all-gather per kernel" if world > 1 else "1 GPU"},
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(nF * 16), "d2h_bytes_per_step": int(nF * 16 + S.Σ.size * 16), "ms_per_step": ms_e2e / a.steps},
-               "gpu_launches": int(launches), "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
+               "gpu_launches": int(launches), "state_sha1": digest, "state_checksum": checksum, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
         print(json.dumps(out))
     S.close()
     if dist is not None:
