@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfdga.so")
+LIB_PATH = os.environ.get("FDGA_LIB_PATH", os.path.join(_HERE, "libfdga.so"))   # override only for A/B experiments
 
 FDGA_MAX_LEVELS = 6
 PCH, TCH, ACH = 0, 1, 2

@@ -122,8 +122,15 @@ FDGA_HD C chan_lin_sum(const DevLevel& lv, int r, const MomOff& m, Lin W2, Lin v
     {
         int a = a0, b = b0; clip_interval(W2, -(lv.nK1 - 1), lv.nK1 - 1, a, b);
         const int o1 = m.oK1 + posB(W2.x0, lv.nK1);      // integer offsets: never form a pointer outside the table
+        C p0 = zeroC(), p1 = zeroC();                    // two accumulators: no serial FMA chain across iterations
+        int win = a;
 #pragma unroll 4
-        for (int win = a; win <= b; ++win) part += ldg(c.K1 + (o1 + W2.s * win)) * Rq[win + Nin];
+        for (; win + 1 <= b; win += 2) {
+            p0 += ldg(c.K1 + (o1 + W2.s * win)) * Rq[win + Nin];
+            p1 += ldg(c.K1 + (o1 + W2.s * (win + 1))) * Rq[win + 1 + Nin];
+        }
+        if (win <= b) p0 += ldg(c.K1 + (o1 + W2.s * win)) * Rq[win + Nin];
+        part = p0 + p1;
     }
     int a = a0, b = b0; clip_interval(W2, -(lv.nK2b - 1), lv.nK2b - 1, a, b);
     const int nB = 2 * lv.nK2b - 1, nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
@@ -320,8 +327,11 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
     return acc;
 }
 
+#ifndef FDGA_COL_MINB
+#define FDGA_COL_MINB 6
+#endif
 template <int KIND, int CH>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, FDGA_COL_MINB)
 column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const C* __restrict__ R, const C* __restrict__ T,
               C* __restrict__ repvals, Grid g) {
     const int col = blockIdx.x;

@@ -168,17 +168,20 @@ __global__ void pi_swave_kernel(const C* __restrict__ Pi, C* __restrict__ Pisw, 
 // Rt layout: [iw + nw*(iq + NP*(iWo + nBo*iP))], W on the OUTPUT bosonic mesh (N = No).
 enum { RK_FD = 0, RK_MF_K1 = 1, RK_MF_K2 = 2, RK_LK2 = 3 };
 
+// Only the slabs (W, P) that hold class representatives of this rank are filled: `slabs` lists (iWo, iP) pairs.
 template <int CH, int KIND>
 __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ DevChain FL,
                                     const C* __restrict__ Pi0T, const C* __restrict__ PiT, C* __restrict__ Rt,
-                                    Grid g, int No, int Ninner) {
+                                    Grid g, int No, int Ninner, const int2* __restrict__ slabs, int nslabs) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
     const int nw = 2 * Ninner, nBo = 2 * No - 1, nFP = 2 * g.nPiF, nBP = 2 * g.nPiB - 1;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long n = (long long)nw * g.NP * nBo * g.NP;
+    long long n = (long long)nw * g.NP * nslabs;
     if (i >= n) return;
     long long t = i;
-    int iw = t % nw; t /= nw; int iq = t % g.NP; t /= g.NP; int iWo = t % nBo; int iP = t / nBo;
+    int iw = t % nw; t /= nw; int iq = t % g.NP; int sl = (int)(t / g.NP);
+    const int2 s2 = slabs[sl];
+    const int iWo = s2.x, iP = s2.y;
     int W = iWo - (No - 1), w = iw - Ninner;
     int Px = iP % g.L, Py = iP / g.L, qx = iq % g.L, qy = iq / g.L;
     size_t pidx = posF(w, g.nPiF) + (size_t)nFP * (iq + (size_t)g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP));
@@ -201,7 +204,7 @@ __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const _
     } else {
         r = Pi0T[pidx] * eval_vertex<false>(FL, 0, CH, SP, a, FL_ALL);
     }
-    Rt[i] = r;
+    Rt[iw + (size_t)nw * (iq + (size_t)g.NP * (iWo + (size_t)nBo * iP))] = r;
 }
 
 // ---- BSE_K1!: src/nonlocal_2/BSEa/BSEa_K1.jl:19-52.  One CTA per class representative (W, P) ------

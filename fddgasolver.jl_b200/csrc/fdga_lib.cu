@@ -86,6 +86,7 @@ struct fdga_ctx {
     C* Ttab;                 // momentum-independent left-factor table [nw, nF2, nB2]
     C* twL; C* twLG;         // DFT twiddles exp(2 pi i j / n) for n = L, LG
     LevelBuf Fsum; bool has_fsum, fsum_dirty;   // K tables of lev[0] + lev[1] when both are NL2 on identical meshes
+    int2* d_slabs[4]; int n_slabs[4]; bool slabs_dirty;   // active (W,P) slabs: [pp|ph] x [bubble mesh | K2 mesh]
     C* Rt3[3]; int rt_kind[3]; // per-channel right factors (W on the bubble mesh) reused between BSE_K1! and BSE_K2!
     std::string err;
 };
@@ -335,6 +336,48 @@ static ColDev col_dev(const SymGroup& s) {
     return c;
 }
 
+// (W, P) slabs of the hoisted right factor that this rank actually reads: those of its K1 representatives and of its
+// K2 columns.  Everything else of Rt stays unwritten (and unread).
+static int ensure_slabs(fdga_ctx* ctx) {
+    if (!ctx->slabs_dirty) return 0;
+    const Grid& g = ctx->g;
+    const int nB1 = 2 * g.nK1 - 1, nB2 = 2 * g.nK2b - 1, nF2 = 2 * g.nK2f, NP = g.NP;
+    for (int kind = 0; kind < 4; kind++) {
+        const bool pp = (kind % 2 == 0), bubble_mesh = kind < 2;
+        const int nBo = bubble_mesh ? 2 * g.nPiB - 1 : nB2;
+        std::vector<unsigned char> mark((size_t)nBo * NP, 0);
+        const SymGroup& s2 = ctx->sg[pp ? FDGA_SG_PP2 : FDGA_SG_PH2];
+        if (s2.set) {
+            long long c0 = std::min((long long)ctx->rank * s2.chunk, s2.ncls), c1 = std::min(c0 + s2.chunk, s2.ncls);
+            for (long long c = c0; c < c1; c++) {
+                long long idx = s2.h_index[s2.h_offsets[c]];
+                int iW = idx % nB2; idx /= nB2; idx /= nF2; int iP = idx % NP;
+                int iWo = bubble_mesh ? posB(iW - (g.nK2b - 1), g.nPiB) : iW;
+                mark[iWo + (size_t)nBo * iP] = 1;
+            }
+        }
+        const SymGroup& s1 = ctx->sg[FDGA_SG_K1];
+        if (bubble_mesh && s1.set) {
+            long long c0 = std::min((long long)ctx->rank * s1.chunk, s1.ncls), c1 = std::min(c0 + s1.chunk, s1.ncls);
+            for (long long c = c0; c < c1; c++) {
+                long long idx = s1.h_index[s1.h_offsets[c]];
+                int iW = idx % nB1, iP = (int)(idx / nB1);
+                mark[posB(iW - (g.nK1 - 1), g.nPiB) + (size_t)nBo * iP] = 1;
+            }
+        }
+        std::vector<int2> list;
+        for (int iP = 0; iP < NP; iP++) for (int iW = 0; iW < nBo; iW++) if (mark[iW + (size_t)nBo * iP]) list.push_back(make_int2(iW, iP));
+        cudaFree(ctx->d_slabs[kind]); ctx->d_slabs[kind] = nullptr; ctx->n_slabs[kind] = (int)list.size();
+        if (!list.empty()) {
+            CK(cudaMalloc(&ctx->d_slabs[kind], list.size() * sizeof(int2)));
+            CK(cudaMemcpy(ctx->d_slabs[kind], list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        }
+    }
+    ctx->slabs_dirty = false;
+    invalidate_rt(ctx);
+    return 0;
+}
+
 // ================================================================================================
 extern "C" {
 
@@ -399,6 +442,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     twiddle_kernel<<<nblk(g.L, 64), 64, 0, ctx->stream>>>(ctx->twL, g.L);
     twiddle_kernel<<<nblk(g.LG, 64), 64, 0, ctx->stream>>>(ctx->twLG, g.LG);
     for (int i = 0; i < 3; i++) { CKC(cudaMalloc(&ctx->Rt3[i], ctx->lenPi * sizeof(C))); ctx->rt_kind[i] = -1; }
+    for (int i = 0; i < 4; i++) { ctx->d_slabs[i] = nullptr; ctx->n_slabs[i] = 0; } ctx->slabs_dirty = true;
     CKC(cudaMalloc(&ctx->Ttab, (size_t)(2 * g.nPiF) * (2 * g.nK2f) * (2 * g.nK2b - 1) * sizeof(C)));
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; s.ncol = 0; s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = nullptr; }
     CKC(cudaStreamSynchronize(ctx->stream));
@@ -418,7 +462,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
     cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->Rt); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB);
     cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
-    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); cudaFree(ctx->Ttab); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]);
+    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); cudaFree(ctx->Ttab); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) cudaFree(ctx->d_slabs[i]);
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); cudaFree(s.d_repvals);
         cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); }
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
@@ -468,7 +512,7 @@ int fdga_comm_init(fdga_ctx* ctx, int nranks, int rank, const void* unique_id_12
         int rc = init(&ctx->comm, nranks, id, rank);
         if (rc) FAIL(std::string("ncclCommInitRank: ") + ctx->nccl.GetErrorString(rc));
     }
-    ctx->nranks = nranks; ctx->rank = rank;
+    ctx->nranks = nranks; ctx->rank = rank; ctx->slabs_dirty = true;
     // re-chunk already registered symmetry groups
     for (int i = 0; i < FDGA_SG_COUNT; i++) {
         SymGroup& s = ctx->sg[i];
@@ -575,7 +619,7 @@ int fdga_set_symmetry_classes(fdga_ctx* ctx, int which, int64_t nclasses, const 
     CK(cudaMemcpy(s.d_index, index, nmem * sizeof(long long), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s.d_ops, ops, nmem, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s.d_member_class, mclass.data(), nmem * sizeof(int), cudaMemcpyHostToDevice));
-    s.set = true;
+    s.set = true; ctx->slabs_dirty = true;
     if (which == FDGA_SG_PP2 || which == FDGA_SG_PH2) return build_columns(ctx, s);
     return 0;
 }
@@ -701,12 +745,16 @@ extern "C++" {
 template <int KIND>
 static int launch_right(fdga_ctx* ctx, int ch, const DevChain& F0, const DevChain& FL, int No, int Ninner, C* Rdst = nullptr) {
     if (!Rdst) Rdst = ctx->Rt;
+    if (ensure_slabs(ctx)) return 1;
     Scope sc(ctx, FDGA_T_RIGHT);
     const C* p0 = ctx->PiT[pi_kind(ch, true)]; const C* p1 = ctx->PiT[pi_kind(ch, false)];
-    long long n = (long long)(2 * Ninner) * ctx->g.NP * (2 * No - 1) * ctx->g.NP;
-    if (ch == FDGA_PCH)      LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_P, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner);
-    else if (ch == FDGA_TCH) LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_T, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner);
-    else                     LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_A, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner);
+    const int kind = (ch == FDGA_PCH ? 0 : 1) + (No == ctx->g.nPiB ? 0 : 2);
+    const int nsl = ctx->n_slabs[kind]; const int2* sl = ctx->d_slabs[kind];
+    long long n = (long long)(2 * Ninner) * ctx->g.NP * nsl;
+    if (n == 0) return 0;
+    if (ch == FDGA_PCH)      LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_P, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl);
+    else if (ch == FDGA_TCH) LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_T, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl);
+    else                     LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_A, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl);
     CK(cudaGetLastError());
     return 0;
 }
