@@ -111,57 +111,71 @@ FDGA_HD void clip_interval(const Lin& x, int lo, int hi, int& a, int& b) {   // 
     else if (x.s < 0) { a = max(a, x.x0 - hi); b = min(b, x.x0 - lo); }
     else if (x.x0 < lo || x.x0 > hi) { b = a - 1; }
 }
+// streaming correlation  sum_{win in [a, b]} tab[o + st * win] * Rq[win + Nin]  with two independent accumulators;
+// a constant table entry (st == 0) over the full chunk uses the pre-summed R of the chunk instead of a loop
+FDGA_HD C stream_sum(const C* __restrict__ tab, int o, int st, int a, int b, const C* __restrict__ Rq, int Nin,
+                     int a0, int b0, C rs_chunk) {
+    if (a > b) return zeroC();
+    if (st == 0 && a == a0 && b == b0) return ldg(tab + o) * rs_chunk;
+    C p0 = zeroC(), p1 = zeroC();
+    int win = a;
+#pragma unroll 4
+    for (; win + 1 <= b; win += 2) {
+        p0 += ldg(tab + (o + st * win)) * Rq[win + Nin];
+        p1 += ldg(tab + (o + st * (win + 1))) * Rq[win + 1 + Nin];
+    }
+    if (win <= b) p0 += ldg(tab + (o + st * win)) * Rq[win + Nin];
+    return p0 + p1;
+}
 // sum over iw in [w_lo, w_hi) of gamma_r(W2, v2, w2) * Rq[iw] at fixed momenta (all K switches on), W2/v2/w2 linear in win = iw - Nin.
-// Same box logic as chan_off.  K1 (needed for nearly every win) is a branch-free streaming correlation over its
-// in-box interval; the K2 / K3 terms only exist inside the (short) K2 Omega-box band and are evaluated term by term there.
+// Same box logic as chan_off: every term is a streaming correlation over its analytically clipped in-box interval; only the
+// (rare) K3 term is evaluated term by term inside the K2 band.  rs_chunk = sum of Rq over the chunk.
 FDGA_HD C chan_lin_sum(const DevLevel& lv, int r, const MomOff& m, Lin W2, Lin v2, Lin w2,
-                       const C* __restrict__ Rq, int Nin, int w_lo, int w_hi) {
+                       const C* __restrict__ Rq, int Nin, int w_lo, int w_hi, C rs_chunk) {
     const DevChan& c = lv.ch[r];
-    C part = zeroC();
     const int a0 = w_lo - Nin, b0 = w_hi - 1 - Nin;      // inclusive win range of this chunk
+    C part;
     {
         int a = a0, b = b0; clip_interval(W2, -(lv.nK1 - 1), lv.nK1 - 1, a, b);
-        const int o1 = m.oK1 + posB(W2.x0, lv.nK1);      // integer offsets: never form a pointer outside the table
-        C p0 = zeroC(), p1 = zeroC();                    // two accumulators: no serial FMA chain across iterations
-        int win = a;
-#pragma unroll 4
-        for (; win + 1 <= b; win += 2) {
-            p0 += ldg(c.K1 + (o1 + W2.s * win)) * Rq[win + Nin];
-            p1 += ldg(c.K1 + (o1 + W2.s * (win + 1))) * Rq[win + 1 + Nin];
-        }
-        if (win <= b) p0 += ldg(c.K1 + (o1 + W2.s * win)) * Rq[win + Nin];
-        part = p0 + p1;
+        part = stream_sum(c.K1, m.oK1 + posB(W2.x0, lv.nK1), W2.s, a, b, Rq, Nin, a0, b0, rs_chunk);
     }
     int a = a0, b = b0; clip_interval(W2, -(lv.nK2b - 1), lv.nK2b - 1, a, b);
+    if (a > b) return part;
     const int nB = 2 * lv.nK2b - 1, nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
-    for (int win = a; win <= b; ++win) {
-        const int Wc = W2.x0 + W2.s * win, vc = v2.x0 + v2.s * win, wc = w2.x0 + w2.s * win;
-        const bool A = inF(vc, lv.nK2f), B = inF(wc, lv.nK2f);
-        const int pW = posB(Wc, lv.nK2b);
-        C val = zeroC();
-        if (A) val += ldg(c.K2 + (m.oK2A + pW + nB * posF(vc, lv.nK2f)));
-        if (B) val += ldg(c.K2 + (m.oK2B + pW + nB * posF(wc, lv.nK2f)));
-        if (A && B && inB(Wc, lv.nK3b) && inF(vc, lv.nK3f) && inF(wc, lv.nK3f))
-            val += ldg(c.K3 + (m.oK3 + posB(Wc, lv.nK3b) + nB3 * (posF(vc, lv.nK3f) + nF3 * posF(wc, lv.nK3f))));
-        part += val * Rq[win + Nin];
+    {
+        int aa = a, bb = b; clip_interval(v2, -lv.nK2f, lv.nK2f - 1, aa, bb);
+        part += stream_sum(c.K2, m.oK2A + posB(W2.x0, lv.nK2b) + nB * posF(v2.x0, lv.nK2f), W2.s + nB * v2.s, aa, bb, Rq, Nin, a0, b0, rs_chunk);
+    }
+    {
+        int aa = a, bb = b; clip_interval(w2, -lv.nK2f, lv.nK2f - 1, aa, bb);
+        part += stream_sum(c.K2, m.oK2B + posB(W2.x0, lv.nK2b) + nB * posF(w2.x0, lv.nK2f), W2.s + nB * w2.s, aa, bb, Rq, Nin, a0, b0, rs_chunk);
+    }
+    {   // K3: short loop inside the K3 Omega-box band, explicit box tests (see DESIGN.md "toolchain pitfall")
+        int aa = a, bb = b; clip_interval(W2, -(lv.nK3b - 1), lv.nK3b - 1, aa, bb);
+        for (int win = aa; win <= bb; ++win) {
+            const int Wc = W2.x0 + W2.s * win, vc = v2.x0 + v2.s * win, wc = w2.x0 + w2.s * win;
+            if (inF(vc, lv.nK2f) && inF(wc, lv.nK2f) && inF(vc, lv.nK3f) && inF(wc, lv.nK3f))
+                part += ldg(c.K3 + (m.oK3 + posB(Wc, lv.nK3b) + nB3 * (posF(vc, lv.nK3f) + nF3 * posF(wc, lv.nK3f)))) * Rq[win + Nin];
+        }
     }
     return part;
 }
 // same for gamma_r(W, v, w) - gamma_r(W, inf, w): K2[W, v | P, k] + K3[W, v, w | P] inside the boxes
 FDGA_HD C chan_lin_sum_diff_v(const DevLevel& lv, int r, const MomOff& m, Lin W2, Lin v2, Lin w2,
-                              const C* __restrict__ Rq, int Nin, int w_lo, int w_hi) {
+                              const C* __restrict__ Rq, int Nin, int w_lo, int w_hi, C rs_chunk) {
     const DevChan& c = lv.ch[r];
-    C part = zeroC();
-    int a = w_lo - Nin, b = w_hi - 1 - Nin;
+    const int a0 = w_lo - Nin, b0 = w_hi - 1 - Nin;
+    int a = a0, b = b0;
     clip_interval(W2, -(lv.nK2b - 1), lv.nK2b - 1, a, b);
     clip_interval(v2, -lv.nK2f, lv.nK2f - 1, a, b);
+    if (a > b) return zeroC();
     const int nB = 2 * lv.nK2b - 1, nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
-    for (int win = a; win <= b; ++win) {
+    C part = stream_sum(c.K2, m.oK2A + posB(W2.x0, lv.nK2b) + nB * posF(v2.x0, lv.nK2f), W2.s + nB * v2.s, a, b, Rq, Nin, a0, b0, rs_chunk);
+    int aa = a, bb = b; clip_interval(W2, -(lv.nK3b - 1), lv.nK3b - 1, aa, bb);
+    for (int win = aa; win <= bb; ++win) {
         const int Wc = W2.x0 + W2.s * win, vc = v2.x0 + v2.s * win, wc = w2.x0 + w2.s * win;
-        C val = ldg(c.K2 + (m.oK2A + posB(Wc, lv.nK2b) + nB * posF(vc, lv.nK2f)));
-        if (inF(wc, lv.nK2f) && inB(Wc, lv.nK3b) && inF(vc, lv.nK3f) && inF(wc, lv.nK3f))
-            val += ldg(c.K3 + (m.oK3 + posB(Wc, lv.nK3b) + nB3 * (posF(vc, lv.nK3f) + nF3 * posF(wc, lv.nK3f))));
-        part += val * Rq[win + Nin];
+        if (inF(wc, lv.nK2f) && inF(vc, lv.nK3f) && inF(wc, lv.nK3f))
+            part += ldg(c.K3 + (m.oK3 + posB(Wc, lv.nK3b) + nB3 * (posF(vc, lv.nK3f) + nF3 * posF(wc, lv.nK3f)))) * Rq[win + Nin];
     }
     return part;
 }
@@ -274,6 +288,9 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
         else if (KIND == JOB_K2_MF || KIND == JOB_LK2) { akx = kx; aky = ky; aqx = (CH == CH_P) ? Px - qx : qx; aqy = (CH == CH_P) ? Py - qy : qy; }
         else { akx = Px - qx; aky = Py - qy; aqx = kx; aqy = ky; }              // SDE pp: (P, P - q, k)
         const C* Rq = slab + (size_t)nw * iq;
+        C rs_chunk = zeroC();                                   // sum of R over this chunk (constant table entries use it)
+#pragma unroll 4
+        for (int iw = w_lo; iw < w_hi; ++iw) rs_chunk += Rq[iw];
 
 #pragma unroll
         for (int f = 0; f < FM::n; ++f) {
@@ -304,13 +321,13 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
                         int W0, v0, w0, W1, v1, w1;
                         convert_freq(W, v_a, w_a, form, r, W0, v0, w0); convert_freq(W, v_b, w_b, form, r, W1, v1, w1);
                         Lin lW = {W0, W1 - W0}, lv2 = {v0, v1 - v0}, lw2 = {w0, w1 - w0};
-                        part += chan_lin_sum(lv, r, mo[r], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi);
+                        part += chan_lin_sum(lv, r, mo[r], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi, rs_chunk);
                     }
                 }
                 if (do_own_diff || do_own_full) {
                     Lin lW = {W, 0}, lv2 = {v_a, v_b - v_a}, lw2 = {w_a, w_b - w_a};
-                    if (do_own_diff) part += chan_lin_sum_diff_v(lv, form, mo[form], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi);
-                    else part += chan_lin_sum(lv, form, mo[form], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi);
+                    if (do_own_diff) part += chan_lin_sum_diff_v(lv, form, mo[form], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi, rs_chunk);
+                    else part += chan_lin_sum(lv, form, mo[form], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi, rs_chunk);
                 }
                 acc += part * cf;
             }
