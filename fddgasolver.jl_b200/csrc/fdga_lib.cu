@@ -34,13 +34,16 @@ struct SymGroup {
     long long *d_offsets, *d_index;
     unsigned char* d_ops;
     int* d_member_class;
-    C* d_repvals;         // padded to chunk * nranks
+    C* d_repvals;         // current slot (= d_rep[channel]); padded to chunk * nranks
+    C* d_rep[3];          // one slot per channel so that the all-gathers of p, a, t can be issued as one NCCL group
     long long chunk;
     std::vector<long long> h_offsets, h_index;
     // columns (W, P, k) of this rank's class representatives (K2-shaped groups only)
     int ncol; int *d_col_iW, *d_col_iP, *d_col_ik, *d_col_start, *d_rep_inu, *d_rep_cls;
 };
 struct TimedEvent { cudaEvent_t a, b; int cat; };
+struct Pending { SymGroup* s; C* rep; C* out; int kind, ch; };
+enum { PK_K1 = 0, PK_LK2 = 1, PK_K2 = 2, PK_LK3 = 3, PK_K3 = 4 };
 
 // NCCL through dlopen (no link-time dependency; the process may already hold torch's libnccl)
 struct NcclApi {
@@ -50,6 +53,7 @@ struct NcclApi {
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
     int (*CommDestroy)(void*);
+    int (*GroupStart)(); int (*GroupEnd)();
     const char* (*GetErrorString)(int);
 };
 struct UniqueId { char b[128]; };
@@ -82,6 +86,7 @@ struct fdga_ctx {
     int cur_cat; cudaEvent_t cur_a;
     int opt_sde_own_gamma;   // FDGA_OPT_SDE_OWN_GAMMA
     int opt_generic;         // FDGA_OPT_GENERIC_KERNELS
+    bool defer; std::vector<struct Pending> pending;   // batched SG finishes (one NCCL group per BSE stage)
     int n_nl2;               // leading NL2 levels of the F chain
     C* Ttab;                 // momentum-independent left-factor table [nw, nF2, nB2]
     C* twL; C* twLG;         // DFT twiddles exp(2 pi i j / n) for n = L, LG
@@ -400,7 +405,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     fdga_ctx* ctx = new fdga_ctx();
     ctx->dims = *dims; ctx->device = device; ctx->nlev = dims->nlev;
     ctx->nranks = 1; ctx->rank = 0; ctx->comm = nullptr; memset(&ctx->nccl, 0, sizeof(ctx->nccl));
-    ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0; ctx->opt_generic = 0;
+    ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0; ctx->opt_generic = 0; ctx->defer = false;
     memset(ctx->t_ms, 0, sizeof(ctx->t_ms)); memset(ctx->n_launch, 0, sizeof(ctx->n_launch));
     Grid& g = ctx->g;
     g.T = dims->T; g.L = dims->nq; g.NP = dims->nq * dims->nq; g.nPiB = dims->nPiB; g.nPiF = dims->nPiF;
@@ -444,7 +449,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     for (int i = 0; i < 3; i++) { CKC(cudaMalloc(&ctx->Rt3[i], ctx->lenPi * sizeof(C))); ctx->rt_kind[i] = -1; }
     for (int i = 0; i < 4; i++) { ctx->d_slabs[i] = nullptr; ctx->n_slabs[i] = 0; } ctx->slabs_dirty = true;
     CKC(cudaMalloc(&ctx->Ttab, (size_t)(2 * g.nPiF) * (2 * g.nK2f) * (2 * g.nK2b - 1) * sizeof(C)));
-    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; s.ncol = 0; s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = nullptr; }
+    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; s.d_rep[0] = s.d_rep[1] = s.d_rep[2] = nullptr; s.ncol = 0; s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = nullptr; }
     CKC(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return 0;
@@ -463,7 +468,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->Rt); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB);
     cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
     cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); cudaFree(ctx->Ttab); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) cudaFree(ctx->d_slabs[i]);
-    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); cudaFree(s.d_repvals);
+    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); for (int k = 0; k < 3; k++) cudaFree(s.d_rep[k]);
         cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); }
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     cudaStreamDestroy(ctx->stream);
@@ -490,8 +495,9 @@ static int load_nccl(NcclApi& a, std::string& err) {
     a.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(a.h, "ncclAllGather");
     a.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(a.h, "ncclAllReduce");
     a.CommDestroy = (int (*)(void*))dlsym(a.h, "ncclCommDestroy");
+    a.GroupStart = (int (*)())dlsym(a.h, "ncclGroupStart"); a.GroupEnd = (int (*)())dlsym(a.h, "ncclGroupEnd");
     a.GetErrorString = (const char* (*)(int))dlsym(a.h, "ncclGetErrorString");
-    if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy || !a.GetErrorString) { err = "libnccl: missing symbols"; return 1; }
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy || !a.GetErrorString || !a.GroupStart || !a.GroupEnd) { err = "libnccl: missing symbols"; return 1; }
     return 0;
 }
 int fdga_comm_unique_id(void* unique_id_128B) {
@@ -518,9 +524,12 @@ int fdga_comm_init(fdga_ctx* ctx, int nranks, int rank, const void* unique_id_12
         SymGroup& s = ctx->sg[i];
         if (!s.set) continue;
         s.chunk = (s.ncls + nranks - 1) / nranks;
-        cudaFree(s.d_repvals);
-        CK(cudaMalloc(&s.d_repvals, (size_t)s.chunk * nranks * sizeof(C)));
-        CK(cudaMemset(s.d_repvals, 0, (size_t)s.chunk * nranks * sizeof(C)));
+        for (int k = 0; k < 3; k++) {
+            cudaFree(s.d_rep[k]);
+            CK(cudaMalloc(&s.d_rep[k], (size_t)s.chunk * nranks * sizeof(C)));
+            CK(cudaMemset(s.d_rep[k], 0, (size_t)s.chunk * nranks * sizeof(C)));
+        }
+        s.d_repvals = s.d_rep[0];
         if ((i == FDGA_SG_PP2 || i == FDGA_SG_PH2) && build_columns(ctx, s)) return 1;
     }
     return 0;
@@ -607,14 +616,17 @@ int fdga_set_symmetry_classes(fdga_ctx* ctx, int which, int64_t nclasses, const 
         }
     }
     SymGroup& s = ctx->sg[which];
-    cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); cudaFree(s.d_repvals);
+    cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); for (int k = 0; k < 3; k++) cudaFree(s.d_rep[k]);
     s.ncls = nclasses; s.nmem = nmem; s.chunk = (nclasses + ctx->nranks - 1) / ctx->nranks;
     s.h_offsets.assign(offsets, offsets + nclasses + 1);
     s.h_index.assign(index, index + nmem);
     CK(cudaMalloc(&s.d_offsets, (nclasses + 1) * sizeof(long long))); CK(cudaMalloc(&s.d_index, nmem * sizeof(long long)));
     CK(cudaMalloc(&s.d_ops, nmem)); CK(cudaMalloc(&s.d_member_class, nmem * sizeof(int)));
-    CK(cudaMalloc(&s.d_repvals, (size_t)s.chunk * ctx->nranks * sizeof(C)));
-    CK(cudaMemset(s.d_repvals, 0, (size_t)s.chunk * ctx->nranks * sizeof(C)));
+    for (int k = 0; k < 3; k++) {
+        CK(cudaMalloc(&s.d_rep[k], (size_t)s.chunk * ctx->nranks * sizeof(C)));
+        CK(cudaMemset(s.d_rep[k], 0, (size_t)s.chunk * ctx->nranks * sizeof(C)));
+    }
+    s.d_repvals = s.d_rep[0];
     CK(cudaMemcpy(s.d_offsets, offsets, (nclasses + 1) * sizeof(long long), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s.d_index, index, nmem * sizeof(long long), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s.d_ops, ops, nmem, cudaMemcpyHostToDevice));
@@ -804,6 +816,58 @@ static int ensure_pi(fdga_ctx* ctx, int ch) {
 }
 static double chsign(int ch) { return ch == FDGA_TCH ? -1.0 : 1.0; }   // BSE_templates.jl:17,25,33
 
+// post-processing that follows the SG(...) fill of one BSE call (BSE_templates.jl:35-38 etc., BSEa_K2.jl:130-135)
+static int post_fix(fdga_ctx* ctx, int kind, int ch) {
+    Scope sc(ctx, FDGA_T_MISC);
+    switch (kind) {
+    case PK_K1:  if (ch == FDGA_TCH) return tfix(ctx, ctx->Fbuff.K[FDGA_TCH][0], ctx->Fbuff.K[FDGA_ACH][0], ctx->Fbuff.len[0]); return 0;
+    case PK_LK2: ctx->FL.sw_dirty = true; invalidate_rt(ctx);
+                 if (ch == FDGA_TCH) return tfix(ctx, ctx->FL.K[FDGA_TCH][1], ctx->FL.K[FDGA_ACH][1], ctx->FL.len[1]); return 0;
+    case PK_K2: {
+        C* out = ctx->Fbuff.K[ch][1]; size_t n = ctx->Fbuff.len[1];
+        if (ch == FDGA_TCH) {
+            if (add_axpby(ctx, out, ctx->FL.K[FDGA_TCH][1], 2.0, ctx->FL.K[FDGA_ACH][1], -1.0, n)) return 1;
+            return tfix(ctx, out, ctx->Fbuff.K[FDGA_ACH][1], n);
+        }
+        return add_axpby(ctx, out, ctx->FL.K[ch][1], 1.0, nullptr, 0.0, n);
+    }
+    case PK_LK3: ctx->FL.sw_dirty = true; invalidate_rt(ctx);
+                 if (ch == FDGA_TCH) return tfix(ctx, ctx->FL.K[FDGA_TCH][2], ctx->FL.K[FDGA_ACH][2], ctx->FL.len[2]); return 0;
+    case PK_K3:  if (ch == FDGA_TCH) return tfix(ctx, ctx->Fbuff.K[FDGA_TCH][2], ctx->Fbuff.K[FDGA_ACH][2], ctx->Fbuff.len[2]); return 0;
+    }
+    return 0;
+}
+static int finish_or_defer(fdga_ctx* ctx, SymGroup& s, C* out, int kind, int ch) {
+    if (ctx->defer) { Pending p; p.s = &s; p.rep = s.d_repvals; p.out = out; p.kind = kind; p.ch = ch; ctx->pending.push_back(p); return 0; }
+    if (sg_finish(ctx, s, out)) return 1;
+    return post_fix(ctx, kind, ch);
+}
+// one NCCL group for all deferred all-gathers of a stage, then the expansions and post-fixes in call order
+static int flush_pending(fdga_ctx* ctx) {
+    if (ctx->pending.empty()) return 0;
+    if (ctx->nranks > 1) {
+        Scope sc(ctx, FDGA_T_COMM);
+        ctx->nccl.GroupStart();
+        for (auto& p : ctx->pending) {
+            int rc = ctx->nccl.AllGather(p.rep + (size_t)ctx->rank * p.s->chunk, p.rep, (size_t)p.s->chunk * 2, /*ncclDouble*/ 8, ctx->comm, ctx->stream);
+            if (rc != 0) { ctx->nccl.GroupEnd(); ctx->pending.clear(); FAIL(std::string("ncclAllGather: ") + ctx->nccl.GetErrorString(rc)); }
+        }
+        int rc = ctx->nccl.GroupEnd();
+        if (rc != 0) { ctx->pending.clear(); FAIL(std::string("ncclGroupEnd: ") + ctx->nccl.GetErrorString(rc)); }
+        ctx->n_launch[FDGA_T_COMM]++;
+    }
+    std::vector<Pending> todo; todo.swap(ctx->pending);
+    for (auto& p : todo) {
+        {
+            Scope sc(ctx, FDGA_T_EXPAND);
+            LAUNCH(FDGA_T_EXPAND, expand_kernel, nblk(p.s->nmem, 256), 256, p.out, p.rep, sym_dev(*p.s));
+            CK(cudaGetLastError());
+        }
+        if (post_fix(ctx, p.kind, p.ch)) return 1;
+    }
+    return 0;
+}
+
 int fdga_bse_K1(fdga_ctx* ctx, int ch, int mfrg) {
     CK(cudaSetDevice(ctx->device));
     if (ch < 0 || ch > 2) FAIL("fdga_bse_K1: bad channel");
@@ -811,7 +875,7 @@ int fdga_bse_K1(fdga_ctx* ctx, int ch, int mfrg) {
     if (ensure_pi(ctx, ch)) return 1;
     DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0), FL = chain_FL(ctx);
     if (cached_right(ctx, ch, mfrg ? RK_MF_K1 : RK_FD, F0, FL)) return 1;
-    SymGroup& s = ctx->sg[FDGA_SG_K1];
+    SymGroup& s = ctx->sg[FDGA_SG_K1]; s.d_repvals = s.d_rep[ch];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
     double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
     const DevChain& left = mfrg ? F0 : F;
@@ -824,9 +888,7 @@ int fdga_bse_K1(fdga_ctx* ctx, int ch, int mfrg) {
         }
         CK(cudaGetLastError());
     }
-    if (sg_finish(ctx, s, ctx->Fbuff.K[ch][0])) return 1;
-    if (ch == FDGA_TCH) return tfix(ctx, ctx->Fbuff.K[FDGA_TCH][0], ctx->Fbuff.K[FDGA_ACH][0], ctx->Fbuff.len[0]);
-    return 0;
+    return finish_or_defer(ctx, s, ctx->Fbuff.K[ch][0], PK_K1, ch);
 }
 
 int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
@@ -837,7 +899,7 @@ int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
     if (ensure_pi(ctx, ch)) return 1;
     DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0), FL = chain_FL(ctx);
     if (launch_right<RK_LK2>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nK2f)) return 1;
-    SymGroup& s = ctx->sg[which];
+    SymGroup& s = ctx->sg[which]; s.d_repvals = s.d_rep[ch];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
     double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
     if (!ctx->opt_generic) {
@@ -852,10 +914,7 @@ int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
         }
         CK(cudaGetLastError());
     }
-    if (sg_finish(ctx, s, ctx->FL.K[ch][1])) return 1;
-    ctx->FL.sw_dirty = true; invalidate_rt(ctx);
-    if (ch == FDGA_TCH) return tfix(ctx, ctx->FL.K[FDGA_TCH][1], ctx->FL.K[FDGA_ACH][1], ctx->FL.len[1]);
-    return 0;
+    return finish_or_defer(ctx, s, ctx->FL.K[ch][1], PK_LK2, ch);
 }
 
 int fdga_bse_K2(fdga_ctx* ctx, int ch, int mfrg) {
@@ -868,7 +927,7 @@ int fdga_bse_K2(fdga_ctx* ctx, int ch, int mfrg) {
     if (!ctx->opt_generic) { if (cached_right(ctx, ch, mfrg ? RK_MF_K2 : RK_FD, F0, FL)) return 1; }
     else if (mfrg) { if (launch_right<RK_MF_K2>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1; }
     else           { if (launch_right<RK_FD>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1; }
-    SymGroup& s = ctx->sg[which];
+    SymGroup& s = ctx->sg[which]; s.d_repvals = s.d_rep[ch];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
     double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
     if (!ctx->opt_generic) {
@@ -896,15 +955,7 @@ int fdga_bse_K2(fdga_ctx* ctx, int ch, int mfrg) {
         }
         CK(cudaGetLastError());
     }
-    C* out = ctx->Fbuff.K[ch][1];
-    if (sg_finish(ctx, s, out)) return 1;
-    Scope sc(ctx, FDGA_T_MISC);
-    size_t n = ctx->Fbuff.len[1];
-    if (ch == FDGA_TCH) {      // BSEa_K2.jl:130-132 then BSE_templates.jl:107-108
-        if (add_axpby(ctx, out, ctx->FL.K[FDGA_TCH][1], 2.0, ctx->FL.K[FDGA_ACH][1], -1.0, n)) return 1;
-        return tfix(ctx, out, ctx->Fbuff.K[FDGA_ACH][1], n);
-    }
-    return add_axpby(ctx, out, ctx->FL.K[ch][1], 1.0, nullptr, 0.0, n);
+    return finish_or_defer(ctx, s, ctx->Fbuff.K[ch][1], PK_K2, ch);
 }
 
 int fdga_bse_L_K3(fdga_ctx* ctx, int ch) {
@@ -913,7 +964,7 @@ int fdga_bse_L_K3(fdga_ctx* ctx, int ch) {
     int which = ch == FDGA_PCH ? FDGA_SG_PPL3 : FDGA_SG_PHL3;
     NEED_SG(which);
     if (ensure_pi(ctx, ch)) return 1;
-    SymGroup& s = ctx->sg[which];
+    SymGroup& s = ctx->sg[which]; s.d_repvals = s.d_rep[ch];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
     // (cache_G, cache_F0, sign): BSE_templates.jl:122,130,138
     int cg = ch == FDGA_ACH ? FDGA_C_GA : (ch == FDGA_PCH ? FDGA_C_GPP : FDGA_C_GT);
@@ -924,10 +975,7 @@ int fdga_bse_L_K3(fdga_ctx* ctx, int ch) {
         if (c1 > c0) LAUNCH(FDGA_T_L_K3, bse_lk3_kernel, nblk(c1 - c0, 64), 64, ctx->cache[cg], ctx->cache[cf0], ctx->Pisw[pi_kind(ch, true)], s.d_repvals, sym_dev(s), c0, c1, ctx->g, ctx->g.T * sign);
         CK(cudaGetLastError());
     }
-    if (sg_finish(ctx, s, ctx->FL.K[ch][2])) return 1;
-    ctx->FL.sw_dirty = true; invalidate_rt(ctx);
-    if (ch == FDGA_TCH) return tfix(ctx, ctx->FL.K[FDGA_TCH][2], ctx->FL.K[FDGA_ACH][2], ctx->FL.len[2]);
-    return 0;
+    return finish_or_defer(ctx, s, ctx->FL.K[ch][2], PK_LK3, ch);
 }
 
 int fdga_bse_K3(fdga_ctx* ctx, int ch, int mfrg) {
@@ -936,7 +984,7 @@ int fdga_bse_K3(fdga_ctx* ctx, int ch, int mfrg) {
     int which = ch == FDGA_PCH ? FDGA_SG_PP3 : FDGA_SG_PH3;
     NEED_SG(which);
     if (ensure_pi(ctx, ch)) return 1;
-    SymGroup& s = ctx->sg[which];
+    SymGroup& s = ctx->sg[which]; s.d_repvals = s.d_rep[ch];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
     // (cache_G, cache_F, cache_F0, sign1, sign2): BSE_templates.jl:156,164,172
     int cg = ch == FDGA_ACH ? FDGA_C_GA : (ch == FDGA_PCH ? FDGA_C_GPX : FDGA_C_GT);
@@ -956,9 +1004,7 @@ int fdga_bse_K3(fdga_ctx* ctx, int ch, int mfrg) {
 #undef K3L
         CK(cudaGetLastError());
     }
-    if (sg_finish(ctx, s, ctx->Fbuff.K[ch][2])) return 1;
-    if (ch == FDGA_TCH) return tfix(ctx, ctx->Fbuff.K[FDGA_TCH][2], ctx->Fbuff.K[FDGA_ACH][2], ctx->Fbuff.len[2]);
-    return 0;
+    return finish_or_defer(ctx, s, ctx->Fbuff.K[ch][2], PK_K3, ch);
 }
 
 int fdga_set_F_from_Fbuff(fdga_ctx* ctx) {
@@ -1083,13 +1129,21 @@ int fdga_iterate_solver(fdga_ctx* ctx, int strategy, int update_sigma) {
     if (update_sigma) { if (fdga_dyson(ctx) || fdga_bubbles_real_space(ctx, 0)) return 1; }
     if (fdga_build_K3_cache(ctx, 0, 0)) return 1;
     const int order[3] = {FDGA_PCH, FDGA_ACH, FDGA_TCH};      // p, a, t (BSE_templates.jl:35-38 needs a before t)
+    // the three channels of a stage are independent up to their post-fixes: one batched SG finish per stage
+    ctx->defer = true;
+    int rc = 0;
     if (strategy == FDGA_FDPA) {
-        for (int i = 0; i < 3; i++) if (fdga_bse_L_K2(ctx, order[i])) return 1;
-        for (int i = 0; i < 3; i++) if (fdga_bse_L_K3(ctx, order[i])) return 1;
+        for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_L_K2(ctx, order[i]);
+        for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_L_K3(ctx, order[i]);      // reads caches and bubbles only
+        if (!rc) rc = flush_pending(ctx);
     }
-    for (int i = 0; i < 3; i++) if (fdga_bse_K1(ctx, order[i], 0)) return 1;
-    for (int i = 0; i < 3; i++) if (fdga_bse_K2(ctx, order[i], 0)) return 1;
-    for (int i = 0; i < 3; i++) if (fdga_bse_K3(ctx, order[i], 0)) return 1;
+    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_K1(ctx, order[i], 0);
+    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_K2(ctx, order[i], 0);         // K1 and K2 share inputs (FL, right factor)
+    if (!rc) rc = flush_pending(ctx);
+    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_K3(ctx, order[i], 0);
+    if (!rc) rc = flush_pending(ctx);
+    ctx->defer = false; ctx->pending.clear();
+    if (rc) return 1;
     if (fdga_set_F_from_Fbuff(ctx)) return 1;
     if (update_sigma) { if (fdga_sde(ctx, strategy, 1, 1)) return 1; }
     return 0;
@@ -1102,11 +1156,18 @@ int fdga_mfrg_matvec(fdga_ctx* ctx, const fdga_c64* host_x, fdga_c64* host_y, in
     if (unflatten_dev(ctx, ctx->lev[0], ctx->flat2, factor)) return 1;
     if (fdga_build_K3_cache(ctx, 1, first)) return 1;
     const int order[3] = {FDGA_PCH, FDGA_ACH, FDGA_TCH};
-    for (int i = 0; i < 3; i++) if (fdga_bse_L_K2(ctx, order[i])) return 1;
-    for (int i = 0; i < 3; i++) if (fdga_bse_K1(ctx, order[i], 1)) return 1;
-    for (int i = 0; i < 3; i++) if (fdga_bse_K2(ctx, order[i], 1)) return 1;
-    for (int i = 0; i < 3; i++) if (fdga_bse_L_K3(ctx, order[i])) return 1;
-    for (int i = 0; i < 3; i++) if (fdga_bse_K3(ctx, order[i], 1)) return 1;
+    ctx->defer = true;
+    int rc = 0;
+    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_L_K2(ctx, order[i]);
+    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_L_K3(ctx, order[i]);
+    if (!rc) rc = flush_pending(ctx);
+    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_K1(ctx, order[i], 1);
+    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_K2(ctx, order[i], 1);
+    if (!rc) rc = flush_pending(ctx);
+    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_K3(ctx, order[i], 1);
+    if (!rc) rc = flush_pending(ctx);
+    ctx->defer = false; ctx->pending.clear();
+    if (rc) return 1;
     if (fdga_set_F_from_Fbuff(ctx)) return 1;
     if (flatten_dev(ctx, ctx->lev[0], ctx->flat)) return 1;
     LAUNCH(FDGA_T_MISC, mfrg_residual_kernel, nblk(ctx->lenFlat, 256), 256, ctx->flat, ctx->flat2, ctx->flat, factor, (long long)ctx->lenFlat);
