@@ -283,7 +283,7 @@ def run_ours(a):
     bytes_per_launch = nB2 * NP * nFΠ * NP * 16 / world + tables + np.mean(chunk) * 16
     flop_per_launch = 26.0 * np.mean(chunk) * nFΠ * NP
     k2 = kernels.get("K2", {"ms_per_step": float("nan"), "launches_per_step": 3})
-    k2_ms_launch = k2["ms_per_step"] / max(k2["launches_per_step"], 1)
+    k2_ms_launch = k2["ms_per_step"] / 3.0        # one column launch per channel (its small table prologue is included)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -291,12 +291,28 @@ def run_ours(a):
         pass
     peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
     ach = bytes_per_launch / (k2_ms_launch * 1e-3) / 1e9
-    roofline = {"kernel": "bse_k2_kernel (BSE_K2!, src/nonlocal_2/BSEa/BSEa_K2.jl:55-138)", "bound": "hbm", "achieved": ach, "peak": peak_hbm,
-                "unit": "GB/s", "frac": ach / peak_hbm, "traffic": None,
+    roofline = {"kernel": "column_kernel<JOB_K2> (BSE_K2!, src/nonlocal_2/BSEa/BSEa_K2.jl:55-138), mean over the p, t, a launches", "bound": "hbm", "achieved": ach, "peak": peak_hbm,
+                "unit": "GB/s", "frac": ach / peak_hbm,
+                # dram__bytes_read.sum + dram__bytes_write.sum of column_kernel<JOB_K2, pCh> at config 3, world 1, from
+                # profiles/r01_final_column_kernel_ncu_full.txt (ncu --set full); None for other workloads
+                "traffic": 22.93e6 if (a.nmax, a.nq, a.LG, world) == (4, 8, 48, 1) else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": k2_ms_launch,
                 "note": "gather/issue-bound FP64 kernel, not HBM-bound: see fp64",
                 "fp64": {"algorithmic_gflop_per_launch": flop_per_launch / 1e9, "achieved_tflops": flop_per_launch / (k2_ms_launch * 1e-3) / 1e12}}
+
+    # second hot entry of the reference: the mfRG linear map y = A x (src/mfRG.jl:34-89, script/benchmark_Wu.jl:60-64),
+    # host vectors in and out exactly as Krylov.dqgmres calls it
+    A = fd.mfRGLinearMap(S)
+    xm = x_np.copy()
+    A.matvec(xm); A.matvec(xm)
+    barrier()
+    t0 = time.perf_counter()
+    nmv = max(3, a.steps)
+    for _ in range(nmv):
+        A.matvec(xm)
+    barrier()
+    mfrg_per_s = nmv / (time.perf_counter() - t0)
 
     # state fingerprint after one more iteration from the stashed vertex: identical on every rank and for every N
     import hashlib
@@ -328,7 +344,7 @@ def run_ours(a):
                           "symmetry_classes": {"K1": S.num_classes(fd._lib.SG_K1), "K2pp": n2cls[0], "K2ph": n2cls[1], "K3pp": S.num_classes(fd._lib.SG_PP3), "K3ph": S.num_classes(fd._lib.SG_PH3)},
                           "parallelism": f"class representatives sharded over {world} rank(s), NCCL all-gather per kernel" if world > 1 else "1 GPU"},
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(nF * 16), "d2h_bytes_per_step": int(nF * 16 + S.Σ.size * 16), "ms_per_step": ms_e2e / a.steps},
-               "gpu_launches": int(launches), "state_sha1": digest, "state_checksum": checksum, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
+               "gpu_launches": int(launches), "mfrg_matvecs_per_sec_e2e": mfrg_per_s, "state_sha1": digest, "state_checksum": checksum, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
         print(json.dumps(out))
     S.close()
     if dist is not None:
