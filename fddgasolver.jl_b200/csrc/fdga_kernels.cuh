@@ -483,22 +483,25 @@ __global__ void bubbles_rs_kernel(const C* __restrict__ GR, C* __restrict__ Pipp
     int W = iW - (g.nPiB - 1), v = iv - g.nPiF;
     int ax = ia % L, ay = ia / L, bx = ib % L, by = ib / L;
     C spp = zeroC(), sph = zeroC();
+    const bool even = (LG % 2 == 0);
     for (int R2 = -h; R2 <= h; ++R2) { if (modL(R2, L) != ay) continue;
     for (int R1 = -h; R1 <= h; ++R1) { if (modL(R1, L) != ax) continue;
-        C g1pp = gr_call(GR, g.nG, LG, W - v - 1, modL(R1, LG), modL(R2, LG));
-        C g1ph = gr_call(GR, g.nG, LG, W + v, modL(R1, LG), modL(R2, LG));
-        for (int Rp2 = -h; Rp2 <= h; ++Rp2) for (int Rp1 = -h; Rp1 <= h; ++Rp1) {
-            bool mpp = modL(Rp1 - R1, L) == bx && modL(Rp2 - R2, L) == by;
-            bool mph = modL(Rp1 + R1, L) == bx && modL(Rp2 + R2, L) == by;
-            if (!mpp && !mph) continue;
-            double wgt = 1.0;
-            if (LG % 2 == 0) {
-                if (abs(Rp1) == LG / 2) wgt /= 2; if (abs(Rp2) == LG / 2) wgt /= 2;
-                if (abs(R1) == LG / 2) wgt /= 2;  if (abs(R2) == LG / 2) wgt /= 2;
+        const C g1pp = gr_call(GR, g.nG, LG, W - v - 1, modL(R1, LG), modL(R2, LG));
+        const C g1ph = gr_call(GR, g.nG, LG, W + v, modL(R1, LG), modL(R2, LG));
+        double wR = 1.0;
+        if (even) { if (abs(R1) == LG / 2) wR *= 0.5; if (abs(R2) == LG / 2) wR *= 0.5; }
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+            // pp: R' - R == b (mod L)  ->  R' == b + R ; ph: R' + R == b  ->  R' == b - R ; R' restricted to [-h, h]
+            int c1 = modL(ph ? bx - R1 : bx + R1, L), c2 = modL(ph ? by - R2 : by + R2, L);
+            while (c1 > h) c1 -= L;
+            while (c2 > h) c2 -= L;
+            for (int Rp2 = c2; Rp2 >= -h; Rp2 -= L) for (int Rp1 = c1; Rp1 >= -h; Rp1 -= L) {
+                double wgt = wR;
+                if (even) { if (abs(Rp1) == LG / 2) wgt *= 0.5; if (abs(Rp2) == LG / 2) wgt *= 0.5; }
+                const C g2 = gr_call(GR, g.nG, LG, v, modL(Rp1, LG), modL(Rp2, LG));
+                if (ph) sph += g1ph * g2 * wgt; else spp += g1pp * g2 * wgt;
             }
-            C g2 = gr_call(GR, g.nG, LG, v, modL(Rp1, LG), modL(Rp2, LG));
-            if (mpp) spp += g1pp * g2 * wgt;
-            if (mph) sph += g1ph * g2 * wgt;
         }
     }}
     PippR[i] = spp; PiphR[i] = sph;
