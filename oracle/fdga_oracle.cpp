@@ -1041,4 +1041,57 @@ int64_t orc_build_symmetry_group(int kind, int n0, int n1, int L, int64_t* offse
     return ncls;
 }
 
+
+// =====================================================================================================
+// Local (ParquetSolver, impurity) variants.  A local Vertex is carried as an NL2 vertex on a 1 x 1 momentum mesh
+// (K1[W,1], K2[W,v,1,1], K3[W,v,w,1]); with NP = 1 the NL2 restatements above coincide term by term with
+// src/BSEa/BSEa_K1.jl:2-54, BSEa_K2.jl:43-103, BSEa_K3.jl:1-128, src/build_K3_cache.jl:20-95 and src/SDE.jl:60-290
+// (diffed against the NL2 files).  The functions that DIFFER are restated here.
+
+// ---- BSE_L_K2! local, src/BSEa/BSEa_K2.jl:1-40: omega over the BUBBLE mesh, crossing on the right vertex ----
+void orc_bse_L_K2_local(cplx* K2, int nK2b, int nK2f, const orc_vertex* F0, const orc_vertex* F,
+                        const cplx* Pi0, const orc_sg* SG, int sign, int Ch, int Sp, const orc_grid* g) {
+    VertexEval EF0 = {F0, 1, 1}, EF = {F, 1, 1};
+    int nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF;
+    K2Shape s = {nK2b, nK2f, 1};
+    double T = g->T;
+    Mom z = mk(0, 0);
+    Flags fl = {false, Ch != pCh, Ch != tCh, Ch != aCh};
+    auto diagram = [&](int64_t idx) -> cplx {
+        int W, v; Mom P, k; decodeK2(idx, s, 1, W, v, P, k);
+        int iW = posB(W, g->nPiB);
+        cplx val = 0;
+        for (int iw = 0; iw < nFP; iw++) {
+            int w = iw - g->nPiF;
+            cplx Gp  = EF.eval(0, W, v, w, z, z, z, Ch, Sp, fl);
+            cplx F0p = EF0.eval(0, W, crossingF(W, w, Ch), INF, z, z, z, Ch, Sp, ALLF());
+            val += Gp * Pi0[iW + (size_t)nBP * iw] * F0p;
+        }
+        return T * val * (double)sign;
+    };
+    sg_apply(K2, SG, diagram);
+}
+
+// ---- bubbles! local, src/bubble.jl:9-36 (use_G_tail = true: 1/nu outside the G mesh) ------------------------
+void orc_bubbles_local(cplx* Pipp, cplx* Piph, const cplx* G, int nG, const orc_grid* g) {
+    int nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF;
+    double T = g->T;
+    auto Gt = [&](int n) -> cplx { return inF(n, nG) ? G[posF(n, nG)] : cplx(1.0 / ((2 * n + 1) * M_PI * T), 0.0); };
+    for (int iW = 0; iW < nBP; iW++) for (int iv = 0; iv < nFP; iv++) {
+        int W = iW - (g->nPiB - 1), v = iv - g->nPiF;
+        cplx Gv = Gt(v), Gm = Gt(B_minus_F(W, v)), Gp = Gt(B_plus_F(W, v));
+        Pipp[iW + (size_t)nBP * iv] = Gv * Gm;
+        Piph[iW + (size_t)nBP * iv] = Gv * Gp;
+    }
+}
+
+// ---- siam_bare_Green, src/models/siam.jl:9-28 (stores i*G) --------------------------------------------------
+void orc_siam_bare_green(cplx* G, int nG, double T, double e, double Delta, double D) {
+    for (int n = -nG; n < nG; n++) {
+        double nu = (2 * n + 1) * M_PI * T;
+        if (std::isinf(D)) G[posF(n, nG)] = 1.0 / (cplx(nu, e) + Delta * (nu > 0 ? 1.0 : -1.0));
+        else G[posF(n, nG)] = 1.0 / (cplx(nu, e) + 2 * Delta / M_PI * std::atan(D / nu));
+    }
+}
+
 }  // extern "C"

@@ -345,6 +345,12 @@ def _SDE_chain(S, Σ, G, Πpp, Πph, V, level, include_U2, include_Hartree):
     return Σ
 
 
+# Quirk toggle: True (default) = as coded in src/SDE.jl:13-24: the reference Hartree term is
+# subtracted inside SDE!(..., G0, ..., F0; include_Hartree) AND once more explicitly.  False = subtracted once, which is
+# what reproduces the reference's own golden number test/test_siam_fdPA.jl:84 (see tests/test_oracle_siam_golden.py).
+QUIRK_E1 = True
+
+
 def SDE(S, strategy="scPA", include_U2=True, include_Hartree=True):
     """SDE!(S; strategy): src/SDE.jl:3-33"""
     S.Σ[...] = 0
@@ -353,7 +359,7 @@ def SDE(S, strategy="scPA", include_U2=True, include_Hartree=True):
         Σ0part = _SDE_chain(S, zeros(S.Σ.shape), S.G0, S.Π0pp, S.Π0ph, S.F, 1, include_U2, include_Hartree)
         S.Σ += -1 * Σ0part
         S.Σ += S.Σ0
-        if include_Hartree:
+        if include_Hartree and QUIRK_E1:
             n0 = compute_occupation(S, S.G0)
             S.Σ -= (n0 - 1 / 2) * S.F.bare_vertex() * 1j
 
@@ -406,3 +412,73 @@ class mfRGLinearMap:
         S.F.set(S.Fbuff)
         y = S.F.flatten()
         return x - y / factor
+
+
+# ================================================================================================ local solver
+class OracleLocalSolver(OracleSolver):
+    """CPU restatement of the local ParquetSolver (src/ParquetSolver.jl:5-157): an OracleSolver on a 1 x 1 momentum mesh
+    with the local bubbles (1/ν tail, mΠν_factor = 6), the local BSE_L_K2! and the local SDE L kernels (own γ only)."""
+
+    def __init__(self, nK1, nK2, nK3, Gbare, G0, Σ0, F0, *, T, mΠν_factor=6):
+        col = lambda a: np.asfortranarray(np.asarray(a, dtype=np.complex128).reshape(-1, 1))
+        super().__init__(nK1, nK2, nK3, 1, col(Gbare), col(G0), col(Σ0), F0, T=T, mΠν_factor=mΠν_factor, compute_bubbles=False)
+        self.local = True
+        bubbles_local(self, self.Π0pp, self.Π0ph, self.G0)
+        Dyson(self)
+        bubbles_local(self, self.Πpp, self.Πph, self.G)
+
+
+def siam_bare_Green(T, nG, *, e, Δ, D):
+    G = zeros((2 * nG, 1))
+    lib().orc_siam_bare_green(_p(G), nG, C.c_double(T), C.c_double(e), C.c_double(Δ), C.c_double(D))
+    return G
+
+
+def bubbles_local(S, Πpp, Πph, G):
+    lib().orc_bubbles_local(_p(Πpp), _p(Πph), _p(G), S.nG, C.byref(S.grid))
+
+
+def BSE_L_K2_local(S, ch):
+    sign, Sp = _sign_sp(ch)
+    K2 = S.FL.channel(ch).K2
+    sg = S.sg[SG_PP2 if ch == pCh else SG_PH2]
+    lib().orc_bse_L_K2_local(_p(K2), S.nK2[0], S.nK2[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)),
+                             _p(_pi(S, ch, True)), C.byref(sg_struct(sg)), sign, ch, Sp, C.byref(S.grid))
+    if ch == tCh:
+        _tfix(S.FL.γt.K2, S.FL.γa.K2)
+
+
+def iterate_solver_local(S, strategy="fdPA", update_Σ=True):
+    """iterate_solver!(S::ParquetSolver): src/solve.jl:4-116 with the local kernels"""
+    if update_Σ:
+        Dyson(S)
+        bubbles_local(S, S.Πpp, S.Πph, S.G)
+    build_K3_cache(S)
+    if strategy == "fdPA":
+        for ch in (pCh, aCh, tCh):
+            BSE_L_K2_local(S, ch)
+        for ch in (pCh, aCh, tCh):
+            BSE_L_K3(S, ch)
+    for ch in (pCh, aCh, tCh):
+        BSE_K1(S, ch)
+    for ch in (pCh, aCh, tCh):
+        BSE_K2(S, ch)
+    for ch in (pCh, aCh, tCh):
+        BSE_K3(S, ch)
+    S.F.set(S.Fbuff)
+    if update_Σ:
+        lib().orc_set_quirk_E2(0)          # local SDE L kernels: F(...; F0 = false, own γ) (src/SDE.jl:102-103, 138-140)
+        try:
+            SDE(S, strategy)
+        finally:
+            lib().orc_set_quirk_E2(1)
+
+
+def interp_boson(K1col, T, N, x):
+    """MeshFunction call with a Float64 argument: linear interpolation on the bosonic Matsubara mesh"""
+    m = x / (2 * np.pi * T)
+    m0 = int(np.floor(m))
+    if m0 >= N - 1:
+        m0 = N - 2
+    w = m - m0
+    return (1 - w) * K1col[m0 + N - 1] + w * K1col[m0 + 1 + N - 1]
