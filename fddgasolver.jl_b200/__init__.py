@@ -7,9 +7,9 @@ name contains a dot; the top-level shim ``fddgasolver_jl_b200.py`` registers it 
 from ._lib import FdgaError, LIB_PATH, EXPORTS  # noqa: F401
 from .types import (pCh, tCh, aCh, pSp, xSp, dSp, Channel, NL2_Channel, RefVertex, Vertex, NL2_Vertex,  # noqa: F401
                     vertex_chain, nB, nF)
-from .models import hubbard_bare_Green, hubbard_band  # noqa: F401
-from .solver import (NL2_ParquetSolver, init_sym_grp, Dyson, compute_occupation, bubbles, bubbles_real_space,  # noqa: F401
+from .models import hubbard_bare_Green, hubbard_band, siam_bare_Green  # noqa: F401
+from .solver import (NL2_ParquetSolver, ParquetSolver, init_sym_grp, Dyson, compute_occupation, bubbles, bubbles_real_space,  # noqa: F401
                      bubbles_momentum_space, build_K3_cache, build_K3_cache_mfRG, BSE_L_K2, BSE_L_K3, BSE_K1,
                      BSE_K2, BSE_K3, SDE, iterate_solver, iterate_solver_stepwise, fixed_point, mfRGLinearMap)
-from .synthetic import (parquet_solver_hubbard_parquet_approximation_NL2, synthetic_local_vertex,  # noqa: F401
+from .synthetic import (parquet_solver_hubbard_parquet_approximation_NL2, parquet_solver_siam_parquet_approximation, synthetic_local_vertex,  # noqa: F401
                         wu_point_solver, wu_point_inputs, randomize_vertex)

@@ -31,7 +31,7 @@ EXPORTS = [
     "fdga_set_bubble", "fdga_get_bubble", "fdga_set_cache", "fdga_get_cache", "fdga_get_L",
     "fdga_set_symmetry_classes", "fdga_build_symmetry_group", "fdga_length_F", "fdga_flatten_F",
     "fdga_unflatten_F", "fdga_stash_F", "fdga_unstash_F", "fdga_dyson", "fdga_occupation", "fdga_bubbles_real_space",
-    "fdga_bubbles_momentum_space", "fdga_build_K3_cache", "fdga_bse_L_K2", "fdga_bse_L_K3", "fdga_bse_K1",
+    "fdga_bubbles_momentum_space", "fdga_bubbles_local", "fdga_build_K3_cache", "fdga_bse_L_K2", "fdga_bse_L_K3", "fdga_bse_K1",
     "fdga_bse_K2", "fdga_bse_K3", "fdga_set_F_from_Fbuff", "fdga_sde", "fdga_iterate_solver",
     "fdga_mfrg_matvec", "fdga_profile_enable", "fdga_profile_reset", "fdga_kernel_time_ms",
     "fdga_total_launches", "fdga_stream",
@@ -94,6 +94,7 @@ def load():
     lib.fdga_occupation.argtypes = [vp, i32, C.POINTER(dbl)]
     lib.fdga_bubbles_real_space.argtypes = [vp, i32]
     lib.fdga_bubbles_momentum_space.argtypes = [vp, i32]
+    lib.fdga_bubbles_local.argtypes = [vp, i32]
     lib.fdga_build_K3_cache.argtypes = [vp, i32, i32]
     lib.fdga_bse_L_K2.argtypes = [vp, i32]
     lib.fdga_bse_L_K3.argtypes = [vp, i32]

@@ -20,7 +20,8 @@ namespace fdga {
 
 #define FDGA_NV 8    // representatives (nu values) per column chunk
 
-enum { JOB_K2 = 0, JOB_K2_MF = 1, JOB_LK2 = 2, JOB_SDE_PP = 3, JOB_SDE_PH = 4 };
+enum { JOB_K2 = 0, JOB_K2_MF = 1, JOB_LK2 = 2, JOB_SDE_PP = 3, JOB_SDE_PH = 4,
+       JOB_LK2_LOC = 5 /* BSE_L_K2! of the local solver, src/BSEa/BSEa_K2.jl:17-34: left vertex at uncrossed arguments */ };
 
 struct ColDev {                 // columns of class representatives, built on the host (fdga_lib.cu: build_columns)
     int ncol;
@@ -192,7 +193,7 @@ template <> struct Forms<JOB_SDE_PH, CH_A> { static constexpr int n = 2; __host_
 // map (output nu, inner w) -> vertex frequency arguments (v, w) of the job
 template <int KIND, int CH>
 FDGA_HD void job_freq_args(int W, int nu, int win, int& v, int& w) {
-    if (KIND == JOB_K2 || KIND == JOB_SDE_PH) { v = nu; w = win; }
+    if (KIND == JOB_K2 || KIND == JOB_SDE_PH || KIND == JOB_LK2_LOC) { v = nu; w = win; }
     else if (KIND == JOB_K2_MF || KIND == JOB_LK2) { v = nu; w = (CH == CH_P) ? W - win - 1 : win; }
     else { v = W - win - 1; w = nu; }                                   // JOB_SDE_PP: F(W, W - w, nu, ...)
 }
@@ -274,8 +275,7 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
     while (NP * WS < nqs && WS * 2 <= nw) WS *= 2;
     const int wchunk = (nw + WS - 1) / WS;
     const int l0 = job.lev_first;
-    const bool is_sde = (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH);
-    const int l_end = (KIND == JOB_LK2) ? l0 + 1 : job.n_nl2;
+    const int l_end = (KIND == JOB_LK2 || KIND == JOB_LK2_LOC) ? l0 + 1 : job.n_nl2;
 
     if (active)
     for (int item = qs; item < NP * WS; item += nqs) {
@@ -284,7 +284,7 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
         const int w_lo = ws * wchunk, w_hi = min(nw, w_lo + wchunk);
         // momentum arguments of the vertex for this (k, q)
         int akx, aky, aqx, aqy;
-        if (KIND == JOB_K2 || KIND == JOB_SDE_PH) { akx = kx; aky = ky; aqx = qx; aqy = qy; }
+        if (KIND == JOB_K2 || KIND == JOB_SDE_PH || KIND == JOB_LK2_LOC) { akx = kx; aky = ky; aqx = qx; aqy = qy; }
         else if (KIND == JOB_K2_MF || KIND == JOB_LK2) { akx = kx; aky = ky; aqx = (CH == CH_P) ? Px - qx : qx; aqy = (CH == CH_P) ? Py - qy : qy; }
         else { akx = Px - qx; aky = Py - qy; aqx = kx; aqy = ky; }              // SDE pp: (P, P - q, k)
         const C* Rq = slab + (size_t)nw * iq;
@@ -305,7 +305,7 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
                 const DevLevel& lv = V.lev[l];
                 bool do_own_full = false, do_own_diff = false, do_cross = false;
                 if (KIND == JOB_K2 || KIND == JOB_K2_MF) { do_own_diff = true; do_cross = true; }
-                else if (KIND == JOB_LK2) { do_cross = true; }
+                else if (KIND == JOB_LK2 || KIND == JOB_LK2_LOC) { do_cross = true; }
                 else { do_own_full = true; do_cross = (!job.own_only && l > l0); }
                 MomOff mo[3];
 #pragma unroll

@@ -166,7 +166,8 @@ __global__ void pi_swave_kernel(const C* __restrict__ Pi, C* __restrict__ Pisw, 
 //  RK_MF_K2 : Pi0 * FL(W, w, inf; P, q, k0)                                             BSEa_K2.jl:100-104
 //  RK_LK2   : Pi0 * F0(W, w, inf; P, q, k0), w on the K2 nu-mesh                        BSEa_K2.jl:38-41
 // Rt layout: [iw + nw*(iq + NP*(iWo + nBo*iP))], W on the OUTPUT bosonic mesh (N = No).
-enum { RK_FD = 0, RK_MF_K1 = 1, RK_MF_K2 = 2, RK_LK2 = 3 };
+//  RK_LK2_LOC : Pi0 * F0(W, w~, inf), w on the bubble nu-mesh (local solver)                src/BSEa/BSEa_K2.jl:27-30
+enum { RK_FD = 0, RK_MF_K1 = 1, RK_MF_K2 = 2, RK_LK2 = 3, RK_LK2_LOC = 4 };
 
 // Only the slabs (W, P) that hold class representatives of this rank are filled: `slabs` lists (iWo, iP) pairs.
 template <int CH, int KIND>
@@ -187,7 +188,7 @@ __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const _
     size_t pidx = posF(w, g.nPiF) + (size_t)nFP * (iq + (size_t)g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP));
     Arg a;
     a.W = W; a.w = FDGA_INF; a.Px = Px; a.Py = Py; a.qx = 0; a.qy = 0;
-    if (KIND == RK_FD || KIND == RK_MF_K1) {   // crossed arguments (_crossing, BSE_templates.jl:4-6)
+    if (KIND == RK_FD || KIND == RK_MF_K1 || KIND == RK_LK2_LOC) {   // crossed arguments (_crossing, BSE_templates.jl:4-6)
         a.v = (CH == CH_P) ? W - w - 1 : w;
         a.kx = (CH == CH_P) ? Px - qx : qx; a.ky = (CH == CH_P) ? Py - qy : qy;
     } else {
@@ -199,7 +200,7 @@ __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const _
         C FLr = eval_vertex<false>(FL, 0, CH, SP, a, FL_ALL);
         C p = PiT[pidx], p0 = Pi0T[pidx];
         r = (p - p0) * F0r + p * FLr;
-    } else if (KIND == RK_LK2) {
+    } else if (KIND == RK_LK2 || KIND == RK_LK2_LOC) {
         r = Pi0T[pidx] * eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
     } else {
         r = Pi0T[pidx] * eval_vertex<false>(FL, 0, CH, SP, a, FL_ALL);
@@ -525,6 +526,18 @@ __global__ void bubbles_ms_kernel(const C* __restrict__ G, C* __restrict__ Pipp,
         if (inF(b, g.nG)) ph = gk * G[posF(b, g.nG) + (size_t)nGf * kidx(Px + kx, Py + ky, LG)];
     }
     Pipp[i] = pp; Piph[i] = ph;
+}
+
+// ---- bubbles! of the local solver: src/bubble.jl:9-36 (use_G_tail = true: 1/nu outside the G mesh) -------------
+__global__ void bubbles_local_kernel(const C* __restrict__ G, C* __restrict__ Pipp, C* __restrict__ Piph, Grid g) {
+    const int nBP = 2 * g.nPiB - 1, nFP = 2 * g.nPiF;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)nBP * nFP) return;
+    int W = (int)(i % nBP) - (g.nPiB - 1), v = (int)(i / nBP) - g.nPiF;
+    auto Gt = [&](int n) -> C { return inF(n, g.nG) ? G[posF(n, g.nG)] : mkC(1.0 / ((2 * n + 1) * 3.141592653589793 * g.T), 0.0); };
+    C Gv = Gt(v);
+    Pipp[i] = Gv * Gt(W - v - 1);
+    Piph[i] = Gv * Gt(W + v);
 }
 
 // ---- Dyson!: src/dyson.jl:20-31 --------------------------------------------------------------------

@@ -86,6 +86,8 @@ struct fdga_ctx {
     int cur_cat; cudaEvent_t cur_a;
     int opt_sde_own_gamma;   // FDGA_OPT_SDE_OWN_GAMMA
     int opt_generic;         // FDGA_OPT_GENERIC_KERNELS
+    int opt_hartree_once;    // FDGA_OPT_FD_HARTREE_ONCE
+    int opt_local;           // FDGA_OPT_LOCAL_SOLVER
     bool defer; std::vector<struct Pending> pending;   // batched SG finishes (one NCCL group per BSE stage)
     int n_nl2;               // leading NL2 levels of the F chain
     C* Ttab;                 // momentum-independent left-factor table [nw, nF2, nB2]
@@ -405,7 +407,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     fdga_ctx* ctx = new fdga_ctx();
     ctx->dims = *dims; ctx->device = device; ctx->nlev = dims->nlev;
     ctx->nranks = 1; ctx->rank = 0; ctx->comm = nullptr; memset(&ctx->nccl, 0, sizeof(ctx->nccl));
-    ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0; ctx->opt_generic = 0; ctx->defer = false;
+    ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0; ctx->opt_generic = 0; ctx->opt_hartree_once = 0; ctx->opt_local = 0; ctx->defer = false;
     memset(ctx->t_ms, 0, sizeof(ctx->t_ms)); memset(ctx->n_launch, 0, sizeof(ctx->n_launch));
     Grid& g = ctx->g;
     g.T = dims->T; g.L = dims->nq; g.NP = dims->nq * dims->nq; g.nPiB = dims->nPiB; g.nPiF = dims->nPiF;
@@ -479,6 +481,11 @@ int fdga_destroy(fdga_ctx* ctx) {
 int fdga_set_option(fdga_ctx* ctx, int opt, int value) {
     if (opt == FDGA_OPT_SDE_OWN_GAMMA) { ctx->opt_sde_own_gamma = value != 0; return 0; }
     if (opt == FDGA_OPT_GENERIC_KERNELS) { ctx->opt_generic = value != 0; return 0; }
+    if (opt == FDGA_OPT_FD_HARTREE_ONCE) { ctx->opt_hartree_once = value != 0; return 0; }
+    if (opt == FDGA_OPT_LOCAL_SOLVER) {
+        if (value && (ctx->g.L != 1 || ctx->g.LG != 1)) FAIL("FDGA_OPT_LOCAL_SOLVER needs nq = LG = 1");
+        ctx->opt_local = value != 0; invalidate_rt(ctx); return 0;
+    }
     FAIL("fdga_set_option: unknown option");
 }
 int fdga_sync(fdga_ctx* ctx) { CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
@@ -710,6 +717,17 @@ int fdga_bubbles_real_space(fdga_ctx* ctx, int reference) {
     invalidate_rt(ctx);
     return 0;
 }
+int fdga_bubbles_local(fdga_ctx* ctx, int reference) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->g.L != 1 || ctx->g.LG != 1) FAIL("fdga_bubbles_local: needs nq = LG = 1");
+    Scope sc(ctx, FDGA_T_BUBBLE);
+    int ipp = reference ? FDGA_PI0PP : FDGA_PIPP, iph = reference ? FDGA_PI0PH : FDGA_PIPH;
+    LAUNCH(FDGA_T_BUBBLE, bubbles_local_kernel, nblk(ctx->lenPi, 128), 128, ctx->G[reference ? FDGA_G0 : FDGA_G], ctx->Pi[ipp], ctx->Pi[iph], ctx->g);
+    CK(cudaGetLastError());
+    ctx->pi_dirty[ipp] = ctx->pi_dirty[iph] = true;
+    invalidate_rt(ctx);
+    return 0;
+}
 int fdga_bubbles_momentum_space(fdga_ctx* ctx, int reference) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->g.LG % ctx->g.L != 0) FAIL("fdga_bubbles_momentum_space: LG must be a multiple of nq");
@@ -776,7 +794,7 @@ template <int KIND, int CH>
 static int launch_column_t(fdga_ctx* ctx, const DevChain& V, ColJob job, SymGroup& s, const C* R, int cat) {
     Scope sc(ctx, cat);
     const C* T = nullptr;
-    if (KIND != JOB_LK2) {
+    if (KIND != JOB_LK2 && KIND != JOB_LK2_LOC) {
         long long n = (long long)job.nw * (2 * ctx->g.nK2f) * (2 * ctx->g.nK2b - 1);
         LAUNCH(cat, (loc_table_kernel<KIND, CH>), nblk(n, 128), 128, V, job, ctx->g, ctx->Ttab);
         T = ctx->Ttab;
@@ -898,10 +916,16 @@ int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
     NEED_SG(which);
     if (ensure_pi(ctx, ch)) return 1;
     DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0), FL = chain_FL(ctx);
-    if (launch_right<RK_LK2>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nK2f)) return 1;
     SymGroup& s = ctx->sg[which]; s.d_repvals = s.d_rep[ch];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
     double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
+    if (ctx->opt_local) {       // local solver: omega over the bubble mesh, crossing on the right vertex
+        if (launch_right<RK_LK2_LOC>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1;
+        ColJob job = make_job(ctx, 0, 2 * ctx->g.nPiF, ctx->g.nPiF, ctx->g.nK2b, mkC(scale, 0.0));
+        if (launch_column<JOB_LK2_LOC>(ctx, ch, F, job, s, ctx->Rt, FDGA_T_L_K2)) return 1;
+        return finish_or_defer(ctx, s, ctx->FL.K[ch][1], PK_LK2, ch);
+    }
+    if (launch_right<RK_LK2>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nK2f)) return 1;
     if (!ctx->opt_generic) {
         ColJob job = make_job(ctx, 0, 2 * ctx->g.nK2f, ctx->g.nK2f, ctx->g.nK2b, mkC(scale, 0.0));
         if (launch_column<JOB_LK2>(ctx, ch, F, job, s, ctx->Rt, FDGA_T_L_K2)) return 1;
@@ -1114,7 +1138,7 @@ int fdga_sde(fdga_ctx* ctx, int strategy, int include_U2, int include_Hartree) {
     if (strategy == FDGA_FDPA) {      // src/SDE.jl:13-24
         if (sde_chain(ctx, S, -1.0, FDGA_G0, true, 1, include_U2, include_Hartree)) return 1;
         LAUNCH(FDGA_T_MISC, add_axpby_kernel, nblk(ctx->lenG, 256), 256, S, ctx->G[FDGA_SIGMA0], 1.0, (const C*)nullptr, 0.0, (long long)ctx->lenG);
-        if (include_Hartree) {
+        if (include_Hartree && !ctx->opt_hartree_once) {
             if (occupation_dev(ctx, FDGA_G0)) return 1;
             LAUNCH(FDGA_T_MISC, hartree_kernel, nblk(ctx->lenG, 256), 256, S, ctx->d_occ, bareU(ctx), -1.0, (long long)ctx->lenG);
         }
@@ -1126,7 +1150,7 @@ int fdga_sde(fdga_ctx* ctx, int strategy, int include_U2, int include_Hartree) {
 // ---- drivers ---------------------------------------------------------------------------------------------
 int fdga_iterate_solver(fdga_ctx* ctx, int strategy, int update_sigma) {
     if (strategy != FDGA_SCPA && strategy != FDGA_FDPA) FAIL("fdga_iterate_solver: strategy must be scPA or fdPA");
-    if (update_sigma) { if (fdga_dyson(ctx) || fdga_bubbles_real_space(ctx, 0)) return 1; }
+    if (update_sigma) { if (fdga_dyson(ctx) || (ctx->opt_local ? fdga_bubbles_local(ctx, 0) : fdga_bubbles_real_space(ctx, 0))) return 1; }
     if (fdga_build_K3_cache(ctx, 0, 0)) return 1;
     const int order[3] = {FDGA_PCH, FDGA_ACH, FDGA_TCH};      // p, a, t (BSE_templates.jl:35-38 needs a before t)
     // the three channels of a stage are independent up to their post-fixes: one batched SG finish per stage

@@ -18,3 +18,11 @@ def hubbard_bare_Green(T, nG, LG, *, μ, t1, t2=0.0, t3=0.0):
     ek = ek.reshape(LG * LG, order="F")                                   # linear index ix + LG * iy
     G = 1.0 / (1j * nu[:, None] + μ - ek[None, :]) * 1j
     return np.asfortranarray(G, dtype=np.complex128)
+
+
+def siam_bare_Green(T, nG, *, e, Δ, D):
+    """i * G0(ν) of the single-impurity Anderson model (src/models/siam.jl:9-28): array of length 2 nG."""
+    nu = (2 * np.arange(-nG, nG) + 1) * np.pi * T
+    if np.isinf(D):
+        return 1.0 / (nu + 1j * e + Δ * np.sign(nu))
+    return 1.0 / (nu + 1j * e + 2 * Δ / np.pi * np.arctan(D / nu))

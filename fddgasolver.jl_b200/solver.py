@@ -125,7 +125,7 @@ class NL2_ParquetSolver:
 
     def set_option(self, name, value):
         """options of include/fdga.h; 'sde_own_gamma' toggles the SURVEY-E2 reading of the NL2 SDE L kernels"""
-        self._call("fdga_set_option", {"sde_own_gamma": 0, "generic_kernels": 1}[name], int(value))
+        self._call("fdga_set_option", {"sde_own_gamma": 0, "generic_kernels": 1, "fd_hartree_once": 2, "local_solver": 3}[name], int(value))
 
     def sync(self):
         self._call("fdga_sync")
@@ -296,6 +296,28 @@ class NL2_ParquetSolver:
         return self._lib.fdga_stream(self._ctx)
 
 
+class ParquetSolver(NL2_ParquetSolver):
+    """Local (impurity) solver, src/ParquetSolver.jl:5-157, carried as an NL2 solver on a 1 x 1 momentum mesh.
+
+    With a single momentum the NL2 kernels coincide term by term with the local ones (src/BSEa/*.jl, src/build_K3_cache.jl,
+    src/SDE.jl); the pieces that differ are switched by FDGA_OPT_LOCAL_SOLVER: BSE_L_K2! in its local form,
+    bubbles! with the 1/ν tail, SDE L kernels with the own-channel γ only.  Gbare, G0, Σ0: arrays of length 2 nG holding
+    i*G; F0: RefVertex or the F of another ParquetSolver.  The local Vertex arrays are K1[Ω,1], K2[Ω,ν,1,1], K3[Ω,ν,ν',1]."""
+
+    local = True
+
+    def __init__(self, nK1, nK2, nK3, Gbare, G0, Σ0, F0, *, T, mode="threads", mΠν_factor=6, device=0):
+        col = lambda a: np.asfortranarray(np.asarray(a, dtype=np.complex128).reshape(-1, 1))
+        super().__init__(nK1, nK2, nK3, 1, col(Gbare), col(G0), col(Σ0), F0, T=T, mode=mode, mΠν_factor=mΠν_factor,
+                         device=device, compute_bubbles=False)
+        self.set_option("local_solver", 1)
+        self.set_option("sde_own_gamma", 1)          # src/SDE.jl:102-103, 138-140: F(...; F0 = false, own γ)
+        self._call("fdga_bubbles_local", 1)
+        self._call("fdga_dyson")
+        self._call("fdga_bubbles_local", 0)
+        self.pull("G")
+
+
 # ---------------------------------------------------------------------- reference-named operations
 def init_sym_grp(S):
     S.init_sym_grp()
@@ -312,8 +334,8 @@ def compute_occupation(S, which="G"):
 
 
 def bubbles(S):
-    """bubbles!(S) = bubbles_real_space!(S.Πpp, S.Πph, S.G)"""
-    S._call("fdga_bubbles_real_space", 0)
+    """bubbles!(S) = bubbles_real_space!(S.Πpp, S.Πph, S.G)  (local solver: src/bubble.jl:9-36)"""
+    S._call("fdga_bubbles_local" if getattr(S, "local", False) else "fdga_bubbles_real_space", 0)
 
 
 def bubbles_real_space(S, reference=False):

@@ -6,8 +6,8 @@ core box N=(24,16) (sizes decoded from data/Wu_point*.h5, SURVEY.md section 2 ro
 """
 import numpy as np
 
-from .models import hubbard_bare_Green
-from .solver import NL2_ParquetSolver
+from .models import hubbard_bare_Green, siam_bare_Green
+from .solver import NL2_ParquetSolver, ParquetSolver
 from .types import NL2_Vertex, RefVertex, Vertex, nB, nF
 
 
@@ -19,6 +19,13 @@ def parquet_solver_hubbard_parquet_approximation_NL2(nG, nK1, nK2, nK3, LG, L, *
     Σ0 = np.zeros_like(Gbare)
     F0 = RefVertex(T, U)
     return NL2_ParquetSolver(nK1, nK2, nK3, L, Gbare, G0, Σ0, F0, T=T, mode=mode, device=device)
+
+
+def parquet_solver_siam_parquet_approximation(nG, nK1, nK2, nK3, *, e, Δ, D, T, U, mode="threads", mΠν_factor=6, device=0):
+    """Parquet approximation for the SIAM: G0 = Σ0 = 0, F0 = U (src/ParquetSolver.jl:170-200)."""
+    Gbare = siam_bare_Green(T, nG, e=e, Δ=Δ, D=D)
+    z = np.zeros_like(Gbare)
+    return ParquetSolver(nK1, nK2, nK3, Gbare, z, z, RefVertex(T, U), T=T, mode=mode, mΠν_factor=mΠν_factor, device=device)
 
 
 def _decay_b(N):

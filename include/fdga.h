@@ -83,7 +83,12 @@ int  fdga_sync(fdga_ctx* ctx);
  * (F(...; own gamma) - F.F0(...; own gamma), which for a nested nonlocal F0 also contains F0's cross channels);
  * 1 = as the in-line comments there state (own-channel gamma of F only).  See DESIGN.md "E2". */
 enum { FDGA_OPT_SDE_OWN_GAMMA = 0,
-       FDGA_OPT_GENERIC_KERNELS = 1 /* 1 = use the straightforward per-term kernels instead of the column kernels (A/B check) */ };
+       FDGA_OPT_GENERIC_KERNELS = 1, /* 1 = use the straightforward per-term kernels instead of the column kernels (A/B check) */
+       FDGA_OPT_FD_HARTREE_ONCE = 2, /* 0 (default) = fdPA SDE! exactly as coded in src/SDE.jl:13-24 (reference Hartree term
+                                        subtracted twice); 1 = subtracted once (reproduces test/test_siam_fdPA.jl:84) */
+       FDGA_OPT_LOCAL_SOLVER = 3     /* 1 = the context models the local ParquetSolver (src/ParquetSolver.jl) on a 1 x 1
+                                        momentum mesh: BSE_L_K2! in its local form (src/BSEa/BSEa_K2.jl:1-40), bubbles! with
+                                        the 1/nu tail (src/bubble.jl:9-36).  Needs nq = LG = 1. */ };
 int  fdga_set_option(fdga_ctx* ctx, int opt, int value);
 /* one process per GPU; `unique_id` = the 128-byte ncclUniqueId obtained on rank 0 by
  * fdga_comm_unique_id and broadcast by the host (MPI in Julia, torch.distributed in tests). */
@@ -129,6 +134,8 @@ int  fdga_dyson(fdga_ctx*);
 int  fdga_occupation(fdga_ctx*, int which, double* occ);
 /* bubbles_real_space!(Pipp, Piph, G): src/nonlocal_2/bubble.jl:42-122; reference != 0 -> (Pi0, G0) */
 int  fdga_bubbles_real_space(fdga_ctx*, int reference);
+/* bubbles!(Pipp, Piph, G) of the local solver: src/bubble.jl:9-36 (nq = LG = 1) */
+int  fdga_bubbles_local(fdga_ctx*, int reference);
 /* bubbles_momentum_space!: src/nonlocal_2/bubble.jl:1-37 (cross-check; needs LG % nq == 0) */
 int  fdga_bubbles_momentum_space(fdga_ctx*, int reference);
 /* build_K3_cache!(S): src/nonlocal_2/build_K3_cache.jl:18-94; mfrg != 0 -> build_K3_cache_mfRG!(S, first) :97-164 */
