@@ -245,12 +245,137 @@ __global__ void loc_table_kernel(const __grid_constant__ DevChain V, ColJob job,
     if (i < n) T[i] = loc_table_entry<KIND, CH>(V, job, g, i);
 }
 
+// ---- own-channel pieces, hoisted out of the column kernel ------------------------------------------------------
+// For every job the own-channel gamma of a level, summed against R over (win, q), splits exactly into
+//     sum_{win,q} A'(win,q) R[win,q]  +  B(nu,k) * Rtot  +  sum_win K3(nu,win) Rq[win]
+// (Rq[win] = sum_q R[win,q], Rtot = sum_win Rq[win]) with the same box logic as chan_off / chan_off_diff_v:
+//   K2 jobs (nu -> inf difference):  A' = 0,  B = K2[W,nu|P,k],  K3 = K3[W,nu,w(win)|P]
+//   SDE pp  gamma_p(W, W-w, nu; P, P-q, k):  A' = K1[W|P] + K2[W,W-w|P,P-q],  B = K2[W,nu|P,k],  K3 = K3[W,W-w,nu|P]
+//   SDE ph  gamma_f(W, nu, w; P, k, q):      A' = K1[W|P] + K2[W,w|P,q],      B = K2[W,nu|P,k],  K3 = K3[W,nu,w|P]
+// Only B depends on the column momentum k; everything else is a per-slab quantity computed once by slab_own_kernel.
+template <int KIND, int CH>
+FDGA_HD C own_A_term(const DevChain& V, const ColJob& job, const Grid& g, int W, int iP, int win, int iq) {
+    typedef Forms<KIND, CH> FM;
+    C val = zeroC();
+    if (!(KIND == JOB_SDE_PP || KIND == JOB_SDE_PH)) return val;
+    const int L = g.L, NP = g.NP;
+#pragma unroll
+    for (int f = 0; f < FM::n; ++f) {
+        const int form = FM::ch(f);
+        C x = zeroC();
+        for (int l = job.lev_first; l < job.n_nl2; ++l) {
+            const DevLevel& lv = V.lev[l];
+            const DevChan& c = lv.ch[form];
+            if (!inB(W, lv.nK1)) continue;
+            x += ldg(c.K1 + (posB(W, lv.nK1) + (2 * lv.nK1 - 1) * iP));
+            if (!inB(W, lv.nK2b)) continue;
+            const int nB = 2 * lv.nK2b - 1, nF = 2 * lv.nK2f;
+            int vv, kq;
+            if (KIND == JOB_SDE_PP) { vv = W - win - 1; kq = foldidx(iP % L - iq % L, iP / L - iq / L, L); }   // K2[W, W-w | P, P-q]
+            else { vv = win; kq = iq; }                                                                      // K2[W, w | P, q]
+            if (inF(vv, lv.nK2f)) x += ldg(c.K2 + (posB(W, lv.nK2b) + nB * posF(vv, lv.nK2f) + nB * nF * (iP + NP * kq)));
+        }
+        val += x * FM::coef(f);
+    }
+    return val;
+}
+template <int KIND, int CH>
+FDGA_HD C own_K3_term(const DevChain& V, const ColJob& job, const Grid& g, int W, int iP, int nu, int win) {
+    typedef Forms<KIND, CH> FM;
+    C val = zeroC();
+    if (KIND == JOB_LK2 || KIND == JOB_LK2_LOC) return val;
+    int v, w; job_freq_args<KIND, CH>(W, nu, win, v, w);
+#pragma unroll
+    for (int f = 0; f < FM::n; ++f) {
+        const int form = FM::ch(f);
+        C x = zeroC();
+        for (int l = job.lev_first; l < job.n_nl2; ++l) {
+            const DevLevel& lv = V.lev[l];
+            if (inB(W, lv.nK2b) && inF(v, lv.nK2f) && inF(w, lv.nK2f) && inB(W, lv.nK3b) && inF(v, lv.nK3f) && inF(w, lv.nK3f)) {
+                const int nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
+                x += ldg(lv.ch[form].K3 + (posB(W, lv.nK3b) + nB3 * (posF(v, lv.nK3f) + nF3 * (posF(w, lv.nK3f) + nF3 * iP))));
+            }
+        }
+        val += x * FM::coef(f);
+    }
+    return val;
+}
+template <int KIND, int CH>
+FDGA_HD C own_B_term(const DevChain& V, const ColJob& job, const Grid& g, int W, int iP, int ik, int nu) {
+    typedef Forms<KIND, CH> FM;
+    C val = zeroC();
+    if (KIND == JOB_LK2 || KIND == JOB_LK2_LOC) return val;
+#pragma unroll
+    for (int f = 0; f < FM::n; ++f) {
+        const int form = FM::ch(f);
+        C x = zeroC();
+        for (int l = job.lev_first; l < job.n_nl2; ++l) {
+            const DevLevel& lv = V.lev[l];
+            if (inB(W, lv.nK2b) && inF(nu, lv.nK2f)) {
+                const int nB = 2 * lv.nK2b - 1, nF = 2 * lv.nK2f;
+                x += ldg(lv.ch[form].K2 + (posB(W, lv.nK2b) + nB * posF(nu, lv.nK2f) + nB * nF * (iP + g.NP * ik)));
+            }
+        }
+        val += x * FM::coef(f);
+    }
+    return val;
+}
+// k-independent part for one (W, nu, P): own A' and K3 pieces plus the pre-tabulated local/core levels (straightforward
+// form, used by the host unit test; slab_own_kernel computes the same numbers with Rq staged in shared memory)
+template <int KIND, int CH>
+FDGA_HD C slab_own_entry(const DevChain& V, const ColJob& job, const Grid& g, const C* Rs, const C* T, int iW, int iP, int inu) {
+    const int W = iW - (g.nK2b - 1), nu = inu - g.nK2f, nw = job.nw, nF2 = 2 * g.nK2f;
+    C o = zeroC();
+    for (int iq = 0; iq < g.NP; ++iq) for (int iw = 0; iw < nw; ++iw) {
+        C t = own_A_term<KIND, CH>(V, job, g, W, iP, iw - job.Ninner, iq) + own_K3_term<KIND, CH>(V, job, g, W, iP, nu, iw - job.Ninner);
+        if (T != nullptr) t += T[iw + nw * (inu + nF2 * iW)];
+        o += t * Rs[iw + (size_t)nw * iq];
+    }
+    return o;
+}
+// one CTA per active slab (W on the K2 mesh, P): OwnTab[nu | W, P] and Rtot[W, P]
+template <int KIND, int CH>
+__global__ void __launch_bounds__(128)
+slab_own_kernel(const __grid_constant__ DevChain V, ColJob job, const int2* __restrict__ slabs, const C* __restrict__ R,
+                const C* __restrict__ T, C* __restrict__ OwnTab, C* __restrict__ Rtot, Grid g) {
+    extern __shared__ double sm_raw[];
+    C* Rq = reinterpret_cast<C*>(sm_raw);                 // [nw]
+    __shared__ C s_sa;
+    const int iW = slabs[blockIdx.x].x, iP = slabs[blockIdx.x].y;
+    const int W = iW - (g.nK2b - 1), nw = job.nw, NP = g.NP, nF2 = 2 * g.nK2f, nB2 = 2 * g.nK2b - 1;
+    const C* Rs = R + (size_t)nw * NP * (posB(W, job.slabW_N) + (size_t)(2 * job.slabW_N - 1) * iP);
+    for (int iw = threadIdx.x; iw < nw; iw += blockDim.x) {
+        C s = zeroC();
+        for (int iq = 0; iq < NP; ++iq) s += Rs[iw + (size_t)nw * iq];
+        Rq[iw] = s;
+    }
+    C sa = zeroC();
+    if (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH)
+        for (int t = threadIdx.x; t < nw * NP; t += blockDim.x) sa += own_A_term<KIND, CH>(V, job, g, W, iP, t % nw - job.Ninner, t / nw) * Rs[t];
+    sa = block_reduce(sa);
+    if (threadIdx.x == 0) s_sa = sa;
+    __syncthreads();
+    C rt = zeroC();
+    for (int iw = threadIdx.x; iw < nw; iw += blockDim.x) rt += Rq[iw];
+    rt = block_reduce(rt);
+    if (threadIdx.x == 0) Rtot[iW + nB2 * iP] = rt;
+    for (int inu = threadIdx.x; inu < nF2; inu += blockDim.x) {
+        C o = s_sa;
+        for (int iw = 0; iw < nw; ++iw) {
+            C t = own_K3_term<KIND, CH>(V, job, g, W, iP, inu - g.nK2f, iw - job.Ninner);
+            if (T != nullptr) t += ldg(T + iw + nw * (inu + nF2 * iW));
+            o += t * Rq[iw];
+        }
+        OwnTab[inu + nF2 * (iW + nB2 * iP)] = o;
+    }
+}
+
 // ---- the column kernel -----------------------------------------------------------------------------------------
 // thread <-> (representative nu, inner momentum slot): lanes with consecutive nu gather neighbouring table entries,
 // the R slab element is a warp broadcast, and every thread carries a single accumulator.
 // per-thread part (host-callable for CPU unit tests): contribution of thread `tid` of `nthreads` to column `col`
 template <int KIND, int CH>
-FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols, const C* __restrict__ R, const C* __restrict__ T,
+FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols, const C* __restrict__ R,
                         const Grid& g, int col, int tid, int nthreads) {
     typedef Forms<KIND, CH> FM;
     const int iW = cols.iW[col], iP = cols.iP[col], ik = cols.ik[col];
@@ -259,7 +384,6 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
     const int L = g.L, NP = g.NP;
     const int Px = iP % L, Py = iP / L, kx = ik % L, ky = ik / L;
     const int nw = job.nw;
-    const int nF2 = 2 * g.nK2f;
     int NVc = 1;
     while (NVc < nrep) NVc <<= 1;                         // 1, 2, 4, 8 (<= FDGA_NV)
     const int n = tid & (NVc - 1);
@@ -267,7 +391,6 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
     const bool active = n < nrep;
     const int nu = active ? cols.rep_inu[r0 + n] - g.nK2f : 0;
     const C* slab = R + (size_t)nw * NP * (posB(W, job.slabW_N) + (size_t)(2 * job.slabW_N - 1) * iP);
-    const C* Tw = (T != nullptr) ? T + (size_t)nw * (nu + g.nK2f + (size_t)nF2 * iW) : nullptr;
     C acc = zeroC();
 
     // w is split in WS chunks so that small momentum meshes still fill the CTA
@@ -288,25 +411,19 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
         else if (KIND == JOB_K2_MF || KIND == JOB_LK2) { akx = kx; aky = ky; aqx = (CH == CH_P) ? Px - qx : qx; aqy = (CH == CH_P) ? Py - qy : qy; }
         else { akx = Px - qx; aky = Py - qy; aqx = kx; aqy = ky; }              // SDE pp: (P, P - q, k)
         const C* Rq = slab + (size_t)nw * iq;
-        C rs_chunk = zeroC();                                   // sum of R over this chunk (constant table entries use it)
-#pragma unroll 4
-        for (int iw = w_lo; iw < w_hi; ++iw) rs_chunk += Rq[iw];
+        const C rs_chunk = zeroC();                             // cross-channel arguments are never constant in win
 
 #pragma unroll
         for (int f = 0; f < FM::n; ++f) {
             const int form = FM::ch(f);
             const double cf = FM::coef(f);
-            // which pieces come from which NL2 level:
-            //   K2 jobs : every leading NL2 level of the left chain: cross channels + own-channel (nu - inf) difference
-            //   L_K2    : level l0 only, cross channels only (F0 = false, own gamma off)
-            //   SDE     : all levels l >= l0 of the recursion SDE!(..., F.F0) fused: own gamma of level l in full, plus
-            //             ("as coded") the cross channels of every level l > l0
+            // cross-channel pieces (own-channel pieces and local / core levels live in slab_own_kernel + the epilogue):
+            //   K2 jobs : every leading NL2 level of the left chain
+            //   L_K2    : level l0 only (F0 = false)
+            //   SDE     : ("as coded") every level l > l0 of the fused recursion SDE!(..., F.F0)
             for (int l = l0; l < l_end; ++l) {
+                if ((KIND == JOB_SDE_PP || KIND == JOB_SDE_PH) && (job.own_only || l == l0)) continue;
                 const DevLevel& lv = V.lev[l];
-                bool do_own_full = false, do_own_diff = false, do_cross = false;
-                if (KIND == JOB_K2 || KIND == JOB_K2_MF) { do_own_diff = true; do_cross = true; }
-                else if (KIND == JOB_LK2 || KIND == JOB_LK2_LOC) { do_cross = true; }
-                else { do_own_full = true; do_cross = (!job.own_only && l > l0); }
                 MomOff mo[3];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) mo[r] = mom_offsets(lv, form, r, L, NP, Px, Py, akx, aky, aqx, aqy);
@@ -314,30 +431,16 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
                 int v_a, w_a, v_b, w_b;
                 job_freq_args<KIND, CH>(W, nu, 0, v_a, w_a); job_freq_args<KIND, CH>(W, nu, 1, v_b, w_b);
                 C part = zeroC();
-                if (do_cross) {
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        if (r == form) continue;
-                        int W0, v0, w0, W1, v1, w1;
-                        convert_freq(W, v_a, w_a, form, r, W0, v0, w0); convert_freq(W, v_b, w_b, form, r, W1, v1, w1);
-                        Lin lW = {W0, W1 - W0}, lv2 = {v0, v1 - v0}, lw2 = {w0, w1 - w0};
-                        part += chan_lin_sum(lv, r, mo[r], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi, rs_chunk);
-                    }
-                }
-                if (do_own_diff || do_own_full) {
-                    Lin lW = {W, 0}, lv2 = {v_a, v_b - v_a}, lw2 = {w_a, w_b - w_a};
-                    if (do_own_diff) part += chan_lin_sum_diff_v(lv, form, mo[form], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi, rs_chunk);
-                    else part += chan_lin_sum(lv, form, mo[form], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi, rs_chunk);
+                for (int r = 0; r < 3; ++r) {
+                    if (r == form) continue;
+                    int W0, v0, w0, W1, v1, w1;
+                    convert_freq(W, v_a, w_a, form, r, W0, v0, w0); convert_freq(W, v_b, w_b, form, r, W1, v1, w1);
+                    Lin lW = {W0, W1 - W0}, lv2 = {v0, v1 - v0}, lw2 = {w0, w1 - w0};
+                    part += chan_lin_sum(lv, r, mo[r], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi, rs_chunk);
                 }
                 acc += part * cf;
             }
-        }
-        // momentum-independent levels (pre-tabulated, forms and weights already folded in)
-        if (Tw != nullptr) {
-            C part = zeroC();
-#pragma unroll 4
-            for (int iw = w_lo; iw < w_hi; ++iw) part += ldg(Tw + iw) * Rq[iw];
-            acc += part;
         }
     }
 
@@ -349,13 +452,13 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
 #endif
 template <int KIND, int CH>
 __global__ void __launch_bounds__(128, FDGA_COL_MINB)
-column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const C* __restrict__ R, const C* __restrict__ T,
-              C* __restrict__ repvals, Grid g) {
+column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const C* __restrict__ R,
+              const C* __restrict__ OwnTab, const C* __restrict__ Rtot, C* __restrict__ repvals, Grid g) {
     const int col = blockIdx.x;
     const int r0 = cols.start[col], nrep = cols.start[col + 1] - r0;
     int NVc = 1;
     while (NVc < nrep) NVc <<= 1;
-    const C acc = column_thread<KIND, CH>(V, job, cols, R, T, g, col, threadIdx.x, blockDim.x);
+    const C acc = column_thread<KIND, CH>(V, job, cols, R, g, col, threadIdx.x, blockDim.x);
     // reduction over the momentum slots of each representative
     __shared__ double redx[128], redy[128];
     redx[threadIdx.x] = acc.x; redy[threadIdx.x] = acc.y;
@@ -363,8 +466,15 @@ column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const
     if (threadIdx.x < nrep) {
         double x = 0.0, y = 0.0;
         for (int i = threadIdx.x; i < (int)blockDim.x; i += NVc) { x += redx[i]; y += redy[i]; }
+        C val = mkC(x, y);
+        if (OwnTab != nullptr) {      // hoisted own-channel / local-level pieces
+            const int iW = cols.iW[col], iP = cols.iP[col], ik = cols.ik[col], inu = cols.rep_inu[r0 + threadIdx.x];
+            const int nF2 = 2 * g.nK2f, nB2 = 2 * g.nK2b - 1;
+            val += OwnTab[inu + nF2 * (iW + nB2 * iP)]
+                 + own_B_term<KIND, CH>(V, job, g, iW - (g.nK2b - 1), iP, ik, inu - g.nK2f) * Rtot[iW + nB2 * iP];
+        }
         C s = mkC(job.scale_re, job.scale_im);
-        repvals[cols.rep_cls[r0 + threadIdx.x]] = mkC(x, y) * s;
+        repvals[cols.rep_cls[r0 + threadIdx.x]] = val * s;
     }
 }
 

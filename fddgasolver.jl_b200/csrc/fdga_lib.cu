@@ -91,6 +91,7 @@ struct fdga_ctx {
     bool defer; std::vector<struct Pending> pending;   // batched SG finishes (one NCCL group per BSE stage)
     int n_nl2;               // leading NL2 levels of the F chain
     C* Ttab;                 // momentum-independent left-factor table [nw, nF2, nB2]
+    C* OwnTab; C* RtotBuf;   // per-slab hoisted pieces: OwnTab[nu | W, P], Rtot[W, P] (W on the K2 mesh)
     C* twL; C* twLG;         // DFT twiddles exp(2 pi i j / n) for n = L, LG
     LevelBuf Fsum; bool has_fsum, fsum_dirty;   // K tables of lev[0] + lev[1] when both are NL2 on identical meshes
     int2* d_slabs[4]; int n_slabs[4]; bool slabs_dirty;   // active (W,P) slabs: [pp|ph] x [bubble mesh | K2 mesh]
@@ -450,6 +451,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     twiddle_kernel<<<nblk(g.LG, 64), 64, 0, ctx->stream>>>(ctx->twLG, g.LG);
     for (int i = 0; i < 3; i++) { CKC(cudaMalloc(&ctx->Rt3[i], ctx->lenPi * sizeof(C))); ctx->rt_kind[i] = -1; }
     for (int i = 0; i < 4; i++) { ctx->d_slabs[i] = nullptr; ctx->n_slabs[i] = 0; } ctx->slabs_dirty = true;
+    CKC(cudaMalloc(&ctx->OwnTab, (size_t)(2 * g.nK2f) * (2 * g.nK2b - 1) * g.NP * sizeof(C))); CKC(cudaMalloc(&ctx->RtotBuf, (size_t)(2 * g.nK2b - 1) * g.NP * sizeof(C)));
     CKC(cudaMalloc(&ctx->Ttab, (size_t)(2 * g.nPiF) * (2 * g.nK2f) * (2 * g.nK2b - 1) * sizeof(C)));
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; s.d_rep[0] = s.d_rep[1] = s.d_rep[2] = nullptr; s.ncol = 0; s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = nullptr; }
     CKC(cudaStreamSynchronize(ctx->stream));
@@ -469,7 +471,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
     cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->Rt); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB);
     cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
-    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); cudaFree(ctx->Ttab); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) cudaFree(ctx->d_slabs[i]);
+    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); cudaFree(ctx->Ttab); cudaFree(ctx->OwnTab); cudaFree(ctx->RtotBuf); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) cudaFree(ctx->d_slabs[i]);
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); for (int k = 0; k < 3; k++) cudaFree(s.d_rep[k]);
         cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); }
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
@@ -789,17 +791,30 @@ static int launch_right(fdga_ctx* ctx, int ch, const DevChain& F0, const DevChai
     return 0;
 }
 
+template <int KIND, int CH>
+static void kernel_slab_own(fdga_ctx* ctx, const DevChain& V, const ColJob& job, int kind, const C* R, int cat) {
+    size_t smem = (size_t)job.nw * sizeof(C);
+    slab_own_kernel<KIND, CH><<<ctx->n_slabs[kind], 128, smem, ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->Ttab, ctx->OwnTab, ctx->RtotBuf, ctx->g);
+    ctx->n_launch[cat]++; ctx->total_launches++;
+}
 // column path (fdga_column.cuh): momentum-independent table + one CTA per output column
 template <int KIND, int CH>
 static int launch_column_t(fdga_ctx* ctx, const DevChain& V, ColJob job, SymGroup& s, const C* R, int cat) {
+    if (ensure_slabs(ctx)) return 1;
     Scope sc(ctx, cat);
-    const C* T = nullptr;
+    const C* own = nullptr; const C* rtot = nullptr;
     if (KIND != JOB_LK2 && KIND != JOB_LK2_LOC) {
+        // prologue: momentum-independent levels tabulated per (W, nu, w), then everything that does not depend on the
+        // column momentum k reduced per slab (W, P): OwnTab[nu | W, P], Rtot[W, P]
         long long n = (long long)job.nw * (2 * ctx->g.nK2f) * (2 * ctx->g.nK2b - 1);
         LAUNCH(cat, (loc_table_kernel<KIND, CH>), nblk(n, 128), 128, V, job, ctx->g, ctx->Ttab);
-        T = ctx->Ttab;
+        const bool pp = (KIND == JOB_SDE_PP) || ((KIND == JOB_K2 || KIND == JOB_K2_MF) && CH == CH_P);
+        const int kind = (pp ? 0 : 1) + 2;
+        if (ctx->n_slabs[kind] > 0)
+            kernel_slab_own<KIND, CH>(ctx, V, job, kind, R, cat);
+        own = ctx->OwnTab; rtot = ctx->RtotBuf;
     }
-    if (s.ncol > 0) LAUNCH(cat, (column_kernel<KIND, CH>), (unsigned)s.ncol, 128, V, job, col_dev(s), R, T, s.d_repvals, ctx->g);
+    if (s.ncol > 0) LAUNCH(cat, (column_kernel<KIND, CH>), (unsigned)s.ncol, 128, V, job, col_dev(s), R, own, rtot, s.d_repvals, ctx->g);
     CK(cudaGetLastError());
     return 0;
 }

@@ -19,7 +19,7 @@ static const C* rnd_array(size_t n, double scale = 1.0) {
 }
 template <int KIND, int CH>
 __global__ void dev_run(DevChain V, ColJob job, ColDev cols, const C* R, const C* T, Grid g, C* out) {
-    out[threadIdx.x] = column_thread<KIND, CH>(V, job, cols, R, T, g, 0, threadIdx.x, blockDim.x);
+    out[threadIdx.x] = column_thread<KIND, CH>(V, job, cols, R, g, 0, threadIdx.x, blockDim.x);
 }
 #else
 static const C* rnd_array(size_t n, double scale = 1.0) {
@@ -34,7 +34,7 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
     const int NP = g.NP, L = g.L, nw = 2 * Nin, nB2 = 2 * g.nK2b - 1, nF2 = 2 * g.nK2f;
     const bool is_sde = (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH);
-    const int slabN = is_sde ? g.nPiB : g.nK2b, nBs = 2 * slabN - 1;
+    const int slabN = is_sde ? g.nPiB : g.nK2b, nBs = 2 * slabN - 1;     // (the K2 jobs are tested with W on the K2 mesh)
     ColJob job; job.lev_first = lev_first; job.n_nl2 = 0; while (job.n_nl2 < V.nlev && V.lev[job.n_nl2].type == LV_NL2) job.n_nl2++;
     job.own_only = own_only; job.nw = nw; job.Ninner = Nin; job.slabW_N = slabN; job.scale_re = 1.0; job.scale_im = 0.0;
     const C* R = rnd_array((size_t)nw * NP * nBs * NP);
@@ -46,7 +46,7 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
 #else
     std::vector<C> T((size_t)nw * nF2 * nB2);
 #endif
-    for (size_t i = 0; i < T.size(); ++i) T[i] = loc_table_entry<KIND, CH>(V, job, g, (long long)i);
+    for (size_t i = 0; i < T.size(); ++i) T[i] = (KIND == JOB_LK2 || KIND == JOB_LK2_LOC) ? zeroC() : loc_table_entry<KIND, CH>(V, job, g, (long long)i);
     double maxerr = 0.0, maxval = 0.0;
     for (int trial = 0; trial < 12; ++trial) {
         int iW = rand() % nB2, iP = rand() % NP, ik = rand() % NP;
@@ -59,7 +59,7 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
         std::vector<C> got(nrep, zeroC());
         const int nthreads = 128;
         for (int tid = 0; tid < nthreads; ++tid) {
-            C a = column_thread<KIND, CH>(V, job, cols, R, (KIND == JOB_LK2) ? nullptr : T.data(), g, 0, tid, nthreads);
+            C a = column_thread<KIND, CH>(V, job, cols, R, g, 0, tid, nthreads);
             int n = tid & (NVc - 1);
             if (n < nrep) got[n] += a;
         }
@@ -80,6 +80,15 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
             }
         }
 #endif
+        {   // hoisted own-channel / local-level pieces (slab_own_kernel + column epilogue)
+            const int Wv = iW - (g.nK2b - 1);
+            const C* Rs = R + (size_t)nw * NP * (posB(Wv, slabN) + (size_t)nBs * iP);
+            C rtot = zeroC(); for (int i = 0; i < nw * NP; ++i) rtot += Rs[i];
+            for (int n = 0; n < nrep; ++n)
+                if (KIND != JOB_LK2 && KIND != JOB_LK2_LOC)
+                    got[n] += slab_own_entry<KIND, CH>(V, job, g, Rs, T.data(), iW, iP, inu[n])
+                            + own_B_term<KIND, CH>(V, job, g, Wv, iP, ik, inu[n] - g.nK2f) * rtot;
+        }
         // brute force with the per-term evaluator (the arithmetic of bse_k2_kernel / bse_lk2_kernel / sde_L_kernel)
         const int W = iW - (g.nK2b - 1), Px = iP % L, Py = iP / L, kx = ik % L, ky = ik / L;
         const C* slab = R + (size_t)nw * NP * (posB(W, slabN) + (size_t)nBs * iP);
@@ -96,9 +105,10 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
                     else { a.w = w; a.qx = qx; a.qy = qy; }
                     C f1 = eval_vertex<false>(V, lev_first, CH, SP, a, FL_ALL); a.v = FDGA_INF;
                     d = f1 - eval_vertex<false>(V, lev_first, CH, SP, a, FL_ALL);
-                } else if (KIND == JOB_LK2) {
+                } else if (KIND == JOB_LK2 || KIND == JOB_LK2_LOC) {
                     const unsigned FLG = (CH == CH_P ? 0u : FL_GP) | (CH == CH_T ? 0u : FL_GT) | (CH == CH_A ? 0u : FL_GA);
-                    a.v = nu; a.kx = kx; a.ky = ky; a.w = (CH == CH_P) ? W - w - 1 : w; a.qx = (CH == CH_P) ? Px - qx : qx; a.qy = (CH == CH_P) ? Py - qy : qy;
+                    const bool cross = (KIND == JOB_LK2) && (CH == CH_P);
+                    a.v = nu; a.kx = kx; a.ky = ky; a.w = cross ? W - w - 1 : w; a.qx = cross ? Px - qx : qx; a.qy = cross ? Py - qy : qy;
                     d = eval_vertex<false>(V, 0, CH, SP, a, FLG);
                 } else {
                     // fused recursion: sum over levels l >= lev_first of the per-level integrand of sde_L_kernel (core level / 3)
@@ -164,6 +174,7 @@ int main() {
         RUN(JOB_K2, CH_P, 0, 0, g.nPiF) RUN(JOB_K2, CH_T, 0, 0, g.nPiF) RUN(JOB_K2, CH_A, 0, 0, g.nPiF)
         RUN(JOB_K2_MF, CH_P, 1, 0, g.nPiF) RUN(JOB_K2_MF, CH_T, 1, 0, g.nPiF) RUN(JOB_K2_MF, CH_A, 1, 0, g.nPiF)
         RUN(JOB_LK2, CH_P, 0, 0, g.nK2f) RUN(JOB_LK2, CH_T, 0, 0, g.nK2f) RUN(JOB_LK2, CH_A, 0, 0, g.nK2f)
+        RUN(JOB_LK2_LOC, CH_P, 0, 0, g.nPiF) RUN(JOB_LK2_LOC, CH_T, 0, 0, g.nPiF) RUN(JOB_LK2_LOC, CH_A, 0, 0, g.nPiF)
         for (int lf = 0; lf < 4; ++lf) for (int oo = 0; oo < 2; ++oo) { RUN(JOB_SDE_PP, CH_P, lf, oo, g.nPiF) RUN(JOB_SDE_PH, CH_A, lf, oo, g.nPiF) }
         worst = std::max(worst, e);
     }
