@@ -21,7 +21,9 @@ static thread_local std::string g_create_error;
 // ------------------------------------------------------------------------------------------------
 struct LevelBuf {
     fdga_level_desc d;
-    C* K[3][3];          // [channel][class]
+    C* block;            // one allocation per level, laid out [p: K1,K2,K3][t: ...][a: ...] = the order of flatten(F)
+    size_t blocklen;
+    C* K[3][3];          // [channel][class] (pointers into block)
     size_t len[3];
     C* sw[3][4];         // [channel][K1sw, K2swk, K2sww, K3sw]
     C* core[4];
@@ -145,8 +147,13 @@ static int alloc_level(fdga_ctx* ctx, LevelBuf& lb, const fdga_level_desc& d) {
     }
     bool nl2 = d.type == FDGA_LV_NL2;
     for (int cls = 0; cls < 3; cls++) lb.len[cls] = lenK(d, cls, NP, nl2);
+    lb.blocklen = 3 * (lb.len[0] + lb.len[1] + lb.len[2]);
+    CK(cudaMalloc(&lb.block, lb.blocklen * sizeof(C))); CK(cudaMemsetAsync(lb.block, 0, lb.blocklen * sizeof(C), ctx->stream));
+    {
+        size_t off = 0;
+        for (int ch = 0; ch < 3; ch++) for (int cls = 0; cls < 3; cls++) { lb.K[ch][cls] = lb.block + off; off += lb.len[cls]; }
+    }
     for (int ch = 0; ch < 3; ch++) {
-        for (int cls = 0; cls < 3; cls++) { CK(cudaMalloc(&lb.K[ch][cls], lb.len[cls] * sizeof(C))); CK(cudaMemsetAsync(lb.K[ch][cls], 0, lb.len[cls] * sizeof(C), ctx->stream)); }
         if (nl2) {
             size_t n[4] = { (size_t)(2 * d.nK1 - 1), (size_t)(2 * d.nK2[0] - 1) * (2 * d.nK2[1]) * NP,
                             (size_t)(2 * d.nK2[0] - 1) * (2 * d.nK2[1]), (size_t)(2 * d.nK3[0] - 1) * (2 * d.nK3[1]) * (2 * d.nK3[1]) };
@@ -156,7 +163,8 @@ static int alloc_level(fdga_ctx* ctx, LevelBuf& lb, const fdga_level_desc& d) {
     return 0;
 }
 static void free_level(LevelBuf& lb) {
-    for (int ch = 0; ch < 3; ch++) { for (int cls = 0; cls < 3; cls++) cudaFree(lb.K[ch][cls]); for (int j = 0; j < 4; j++) cudaFree(lb.sw[ch][j]); }
+    cudaFree(lb.block);
+    for (int ch = 0; ch < 3; ch++) for (int j = 0; j < 4; j++) cudaFree(lb.sw[ch][j]);
     for (int i = 0; i < 4; i++) cudaFree(lb.core[i]);
 }
 
@@ -224,11 +232,7 @@ static int refresh_swave(fdga_ctx* ctx) {
 static int refresh_fsum(fdga_ctx* ctx) {
     if (!ctx->has_fsum || !ctx->fsum_dirty) return 0;
     Scope sc(ctx, FDGA_T_MISC);
-    for (int ch = 0; ch < 3; ch++) for (int cls = 0; cls < 3; cls++) {
-        size_t n = ctx->Fsum.len[cls];
-        axpby_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->Fsum.K[ch][cls], ctx->lev[0].K[ch][cls], 1.0, ctx->lev[1].K[ch][cls], 1.0, (long long)n);
-        ctx->n_launch[FDGA_T_MISC]++; ctx->total_launches++;
-    }
+    LAUNCH(FDGA_T_MISC, axpby_kernel, nblk(ctx->Fsum.blocklen, 256), 256, ctx->Fsum.block, ctx->lev[0].block, 1.0, ctx->lev[1].block, 1.0, (long long)ctx->Fsum.blocklen);
     CK(cudaGetLastError());
     ctx->fsum_dirty = false;
     return 0;
@@ -652,26 +656,17 @@ int fdga_build_symmetry_group(int which_sg, int n0, int n1, int nq, int64_t* off
 
 int64_t fdga_length_F(fdga_ctx* ctx) { return (int64_t)ctx->lenFlat; }
 static int flatten_dev(fdga_ctx* ctx, const LevelBuf& lb, C* dst) {
-    size_t off = 0;
-    for (int ch = 0; ch < 3; ch++) for (int cls = 0; cls < 3; cls++) {
-        CK(cudaMemcpyAsync(dst + off, lb.K[ch][cls], lb.len[cls] * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
-        off += lb.len[cls];
-    }
+    CK(cudaMemcpyAsync(dst, lb.block, lb.blocklen * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
     return 0;
 }
 int fdga_flatten_F(fdga_ctx* ctx, fdga_c64* host_y) {
     CK(cudaSetDevice(ctx->device));
-    if (flatten_dev(ctx, ctx->lev[0], ctx->flat)) return 1;
-    CK(cudaMemcpyAsync(host_y, ctx->flat, ctx->lenFlat * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(host_y, ctx->lev[0].block, ctx->lenFlat * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));   // the level block IS flatten(S.F)
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 static int unflatten_dev(fdga_ctx* ctx, LevelBuf& lb, const C* src, double scale) {
-    size_t off = 0;
-    for (int ch = 0; ch < 3; ch++) for (int cls = 0; cls < 3; cls++) {
-        LAUNCH(FDGA_T_MISC, scale_copy_kernel, nblk(lb.len[cls], 256), 256, lb.K[ch][cls], src + off, scale, (long long)lb.len[cls]);
-        off += lb.len[cls];
-    }
+    LAUNCH(FDGA_T_MISC, scale_copy_kernel, nblk(lb.blocklen, 256), 256, lb.block, src, scale, (long long)lb.blocklen);
     CK(cudaGetLastError());
     lb.sw_dirty = true; ctx->fsum_dirty = true;
     return 0;
@@ -1048,8 +1043,7 @@ int fdga_bse_K3(fdga_ctx* ctx, int ch, int mfrg) {
 
 int fdga_set_F_from_Fbuff(fdga_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
-    for (int ch = 0; ch < 3; ch++) for (int cls = 0; cls < 3; cls++)
-        CK(cudaMemcpyAsync(ctx->lev[0].K[ch][cls], ctx->Fbuff.K[ch][cls], ctx->Fbuff.len[cls] * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->lev[0].block, ctx->Fbuff.block, ctx->Fbuff.blocklen * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->lev[0].sw_dirty = true; ctx->fsum_dirty = true;
     return 0;
 }
