@@ -37,6 +37,7 @@ struct ColJob {
     int lev_first;              // K2 / LK2: first level of the left chain; SDE: the level l of the recursion
     int n_nl2;                  // number of leading NL2 levels in the chain
     int own_only;               // SDE: SURVEY-E2 toggle
+    int k1_direct;              // 1: cross-channel K1 terms summed inside the column kernel; 0: by slab_conv_kernel (momentum convolution)
     int nw, Ninner;             // inner frequency mesh (count, N)
     int slabW_N;                // bosonic mesh N used to index the R slab ([w + nw*(q + NP*(posB(W) + nB*iP))])
     double scale_re, scale_im;  // complex prefactor applied at the end
@@ -132,11 +133,11 @@ FDGA_HD C stream_sum(const C* __restrict__ tab, int o, int st, int a, int b, con
 // Same box logic as chan_off: every term is a streaming correlation over its analytically clipped in-box interval; only the
 // (rare) K3 term is evaluated term by term inside the K2 band.  rs_chunk = sum of Rq over the chunk.
 FDGA_HD C chan_lin_sum(const DevLevel& lv, int r, const MomOff& m, Lin W2, Lin v2, Lin w2,
-                       const C* __restrict__ Rq, int Nin, int w_lo, int w_hi, C rs_chunk) {
+                       const C* __restrict__ Rq, int Nin, int w_lo, int w_hi, C rs_chunk, bool withK1) {
     const DevChan& c = lv.ch[r];
     const int a0 = w_lo - Nin, b0 = w_hi - 1 - Nin;      // inclusive win range of this chunk
-    C part;
-    {
+    C part = zeroC();
+    if (withK1) {
         int a = a0, b = b0; clip_interval(W2, -(lv.nK1 - 1), lv.nK1 - 1, a, b);
         part = stream_sum(c.K1, m.oK1 + posB(W2.x0, lv.nK1), W2.s, a, b, Rq, Nin, a0, b0, rs_chunk);
     }
@@ -196,6 +197,14 @@ FDGA_HD void job_freq_args(int W, int nu, int win, int& v, int& w) {
     if (KIND == JOB_K2 || KIND == JOB_SDE_PH || KIND == JOB_LK2_LOC) { v = nu; w = win; }
     else if (KIND == JOB_K2_MF || KIND == JOB_LK2) { v = nu; w = (CH == CH_P) ? W - win - 1 : win; }
     else { v = W - win - 1; w = nu; }                                   // JOB_SDE_PP: F(W, W - w, nu, ...)
+}
+
+// momentum arguments (k, q) of the vertex in the form-channel parametrisation, from the column momentum k and the inner q
+template <int KIND, int CH>
+FDGA_HD void job_mom_args(int Px, int Py, int kx, int ky, int qx, int qy, int& akx, int& aky, int& aqx, int& aqy) {
+    if (KIND == JOB_K2 || KIND == JOB_SDE_PH || KIND == JOB_LK2_LOC) { akx = kx; aky = ky; aqx = qx; aqy = qy; }
+    else if (KIND == JOB_K2_MF || KIND == JOB_LK2) { akx = kx; aky = ky; aqx = (CH == CH_P) ? Px - qx : qx; aqy = (CH == CH_P) ? Py - qy : qy; }
+    else { akx = Px - qx; aky = Py - qy; aqx = kx; aqy = ky; }              // SDE pp: (P, P - q, k)
 }
 
 // ---- momentum-independent part of the left factor, tabulated per (W, nu, w) -----------------------------------
@@ -335,11 +344,11 @@ FDGA_HD C slab_own_entry(const DevChain& V, const ColJob& job, const Grid& g, co
 }
 // one CTA per active slab (W on the K2 mesh, P): OwnTab[nu | W, P] and Rtot[W, P]
 template <int KIND, int CH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 slab_own_kernel(const __grid_constant__ DevChain V, ColJob job, const int2* __restrict__ slabs, const C* __restrict__ R,
-                const C* __restrict__ T, C* __restrict__ OwnTab, C* __restrict__ Rtot, Grid g) {
+                const C* __restrict__ T, C* __restrict__ OwnTab, C* __restrict__ Rtot, Grid g, int PC) {
     extern __shared__ double sm_raw[];
-    C* Rq = reinterpret_cast<C*>(sm_raw);                 // [nw]
+    C* Rq = reinterpret_cast<C*>(sm_raw);                 // [nw], then part[nF2 * nw]
     __shared__ C s_sa;
     const int iW = slabs[blockIdx.x].x, iP = slabs[blockIdx.x].y;
     const int W = iW - (g.nK2b - 1), nw = job.nw, NP = g.NP, nF2 = 2 * g.nK2f, nB2 = 2 * g.nK2b - 1;
@@ -351,6 +360,7 @@ slab_own_kernel(const __grid_constant__ DevChain V, ColJob job, const int2* __re
     }
     C sa = zeroC();
     if (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH)
+#pragma unroll 4
         for (int t = threadIdx.x; t < nw * NP; t += blockDim.x) sa += own_A_term<KIND, CH>(V, job, g, W, iP, t % nw - job.Ninner, t / nw) * Rs[t];
     sa = block_reduce(sa);
     if (threadIdx.x == 0) s_sa = sa;
@@ -359,14 +369,208 @@ slab_own_kernel(const __grid_constant__ DevChain V, ColJob job, const int2* __re
     for (int iw = threadIdx.x; iw < nw; iw += blockDim.x) rt += Rq[iw];
     rt = block_reduce(rt);
     if (threadIdx.x == 0) Rtot[iW + nB2 * iP] = rt;
-    for (int inu = threadIdx.x; inu < nF2; inu += blockDim.x) {
-        C o = s_sa;
-        for (int iw = 0; iw < nw; ++iw) {
-            C t = own_K3_term<KIND, CH>(V, job, g, W, iP, inu - g.nK2f, iw - job.Ninner);
-            if (T != nullptr) t += ldg(T + iw + nw * (inu + nF2 * iW));
-            o += t * Rq[iw];
+    C* part = Rq + nw;                                    // [PC * nw]: PC values of nu at a time
+    for (int nu0 = 0; nu0 < nF2; nu0 += PC) {
+        const int nc = min(PC, nF2 - nu0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nc * nw; t += blockDim.x) {
+            const int j = t / nw, iw = t - j * nw, inu = nu0 + j;
+            C x = own_K3_term<KIND, CH>(V, job, g, W, iP, inu - g.nK2f, iw - job.Ninner);
+            if (T != nullptr) x += ldg(T + iw + nw * (inu + nF2 * iW));
+            part[t] = x * Rq[iw];
         }
-        OwnTab[inu + nF2 * (iW + nB2 * iP)] = o;
+        __syncthreads();
+        for (int j = threadIdx.x; j < nc; j += blockDim.x) {
+            C o0 = s_sa, o1 = zeroC();
+            int iw = 0;
+            for (; iw + 1 < nw; iw += 2) { o0 += part[j * nw + iw]; o1 += part[j * nw + iw + 1]; }
+            if (iw < nw) o0 += part[j * nw + iw];
+            OwnTab[nu0 + j + nF2 * (iW + nB2 * iP)] = o0 + o1;
+        }
+    }
+}
+
+// ---- cross-channel K1 pieces as a momentum convolution ---------------------------------------------------------
+// After channel conversion the K1 argument of a cross channel r is
+//     K1_r[ W'(nu, win) | P'(k, q) ],   W' = W0(W, nu) + sW * win,   P' = c(P) + sk * k + sq * q   (sk, sq = +-1),
+// so its contribution  X[nu, k] = sum_{win, q} K1_r[W' | P'] R[win, q]  is a correlation in the frequency AND in the
+// momentum.  With hat f[kappa] = sum_x f[x] exp(-2 pi i kappa.x / L):
+//     X[nu, k] = 1/NP sum_kappa exp(+2 pi i kappa.k / L) Z[nu, kappa],
+//     Z[nu, kappa] = sum_win hatK1_r[W' | sk kappa] * exp(2 pi i sk kappa.c / L) * hatR[win | -sq sk kappa],
+// i.e. O(NP) instead of O(NP^2) work per (slab, nu, win).  One CTA per active slab (W, P) transforms its R slab in shared
+// memory, accumulates Z over all (form, level, r) pieces and transforms back: ConvTab[k, nu | W, P].
+struct ConvPiece { int W0, sW, cx, cy, sk, sq; };
+template <int KIND, int CH>
+FDGA_HD ConvPiece conv_piece(int form, int r, int W, int nu, int Px, int Py) {
+    ConvPiece pc;
+    int v_a, w_a, v_b, w_b, W0, v0, w0, W1, v1, w1;
+    job_freq_args<KIND, CH>(W, nu, 0, v_a, w_a); job_freq_args<KIND, CH>(W, nu, 1, v_b, w_b);
+    convert_freq(W, v_a, w_a, form, r, W0, v0, w0); convert_freq(W, v_b, w_b, form, r, W1, v1, w1);
+    pc.W0 = W0; pc.sW = W1 - W0;
+    Arg a; a.W = a.v = a.w = 0; a.Px = Px; a.Py = Py;
+    job_mom_args<KIND, CH>(Px, Py, 0, 0, 0, 0, a.kx, a.ky, a.qx, a.qy);
+    Arg b0 = convert(a, form, r);
+    job_mom_args<KIND, CH>(Px, Py, 1, 0, 0, 0, a.kx, a.ky, a.qx, a.qy);
+    Arg bk = convert(a, form, r);
+    job_mom_args<KIND, CH>(Px, Py, 0, 0, 1, 0, a.kx, a.ky, a.qx, a.qy);
+    Arg bq = convert(a, form, r);
+    pc.cx = b0.Px; pc.cy = b0.Py; pc.sk = bk.Px - b0.Px; pc.sq = bq.Px - b0.Px;
+    return pc;
+}
+// levels whose cross channels enter the column sum (same selection as column_thread)
+template <int KIND>
+FDGA_HD bool conv_level_on(const ColJob& job, int l) {
+    if ((KIND == JOB_SDE_PP || KIND == JOB_SDE_PH) && (job.own_only || l == job.lev_first)) return false;
+    return true;
+}
+template <int KIND>
+FDGA_HD int conv_level_end(const ColJob& job) { return (KIND == JOB_LK2 || KIND == JOB_LK2_LOC) ? job.lev_first + 1 : job.n_nl2; }
+
+// straightforward form of the same numbers (host unit test / A-B reference)
+template <int KIND, int CH>
+FDGA_HD C k1_cross_direct(const DevChain& V, const ColJob& job, const Grid& g, const C* Rs, int W, int iP, int ik, int nu) {
+    typedef Forms<KIND, CH> FM;
+    const int L = g.L, NP = g.NP, nw = job.nw;
+    const int Px = iP % L, Py = iP / L, kx = ik % L, ky = ik / L;
+    C acc = zeroC();
+    for (int f = 0; f < FM::n; ++f) {
+        const int form = FM::ch(f);
+        for (int l = job.lev_first; l < conv_level_end<KIND>(job); ++l) {
+            if (!conv_level_on<KIND>(job, l)) continue;
+            const DevLevel& lv = V.lev[l];
+            for (int r = 0; r < 3; ++r) {
+                if (r == form) continue;
+                const ConvPiece pc = conv_piece<KIND, CH>(form, r, W, nu, Px, Py);
+                C part = zeroC();
+                for (int iq = 0; iq < NP; ++iq) {
+                    const int qx = iq % L, qy = iq / L;
+                    const int iPp = foldidx(pc.cx + pc.sk * kx + pc.sq * qx, pc.cy + pc.sk * ky + pc.sq * qy, L);
+                    for (int iw = 0; iw < nw; ++iw) {
+                        const int Wc = pc.W0 + pc.sW * (iw - job.Ninner);
+                        if (inB(Wc, lv.nK1)) part += ldg(lv.ch[r].K1 + (posB(Wc, lv.nK1) + (2 * lv.nK1 - 1) * iPp)) * Rs[iw + (size_t)nw * iq];
+                    }
+                }
+                acc += part * FM::coef(f);
+            }
+        }
+    }
+    return acc;
+}
+
+// hatK1[kappa + NP * iW] = sum_P K1[iW + nB1 * P] exp(-2 pi i kappa.P / L) for the three channels of one level
+struct K1hOut { C* p[3]; };
+__global__ void k1_dft_kernel(DevLevel lv, int L, int NP, const C* __restrict__ tw, K1hOut out) {
+    extern __shared__ double sm_raw[];
+    C* row = reinterpret_cast<C*>(sm_raw);                // [NP] K1[iW | .]
+    C* stw = row + NP;                                    // [L]
+    const int nB1 = 2 * lv.nK1 - 1, iW = blockIdx.x;
+    const C* K1 = lv.ch[blockIdx.y].K1;
+    for (int iP = threadIdx.x; iP < NP; iP += blockDim.x) row[iP] = K1[iW + nB1 * iP];
+    for (int j = threadIdx.x; j < L; j += blockDim.x) stw[j] = tw[j];
+    __syncthreads();
+    for (int kap = threadIdx.x; kap < NP; kap += blockDim.x) {
+        const int kx = kap % L, ky = kap / L;
+        C s0 = zeroC(), s1 = zeroC();
+        for (int y = 0; y < L; ++y) {
+            C t = zeroC();
+            for (int x = 0; x < L; ++x) t += row[x + L * y] * conjC(stw[(kx * x) % L]);
+            if (y & 1) s1 += t * conjC(stw[(ky * y) % L]); else s0 += t * conjC(stw[(ky * y) % L]);
+        }
+        out.p[blockIdx.y][kap + (size_t)NP * iW] = s0 + s1;
+    }
+}
+
+template <int KIND, int CH>
+__global__ void __launch_bounds__(512)
+slab_conv_kernel(const __grid_constant__ DevChain V, ColJob job, const int2* __restrict__ slabs, const C* __restrict__ R,
+                 const C* __restrict__ tw, C* __restrict__ ConvTab, Grid g, int TW) {
+    typedef Forms<KIND, CH> FM;
+    extern __shared__ double sm_raw[];
+    const int L = g.L, NP = g.NP, nF2 = 2 * g.nK2f, nB2 = 2 * g.nK2b - 1, nw = job.nw, Nin = job.Ninner;
+    const int TWp = TW | 1;                               // odd row stride: conflict-free column gathers
+    C* A = reinterpret_cast<C*>(sm_raw);                  // [NP][TWp]
+    C* B = A + (size_t)NP * TWp;                          // [NP][TWp]
+    C* Z = B + (size_t)NP * TWp;                          // [nF2][NP]
+    C* stw = Z + (size_t)nF2 * NP;                        // [L]  exp(+2 pi i j / L)
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int iW = slabs[blockIdx.x].x, iP = slabs[blockIdx.x].y;
+    const int W = iW - (g.nK2b - 1), Px = iP % L, Py = iP / L;
+    const C* Rs = R + (size_t)nw * NP * (posB(W, job.slabW_N) + (size_t)(2 * job.slabW_N - 1) * iP);
+    for (int j = tid; j < L; j += nthr) stw[j] = tw[j];
+    for (int o = tid; o < nF2 * NP; o += nthr) Z[o] = zeroC();
+    const int l_end = conv_level_end<KIND>(job);
+
+    for (int t0 = 0; t0 < nw; t0 += TW) {
+        const int tn = min(TW, nw - t0);
+        __syncthreads();
+        for (int e = tid; e < tn * NP; e += nthr) { const int j = e % tn, q = e / tn; A[q * TWp + j] = Rs[t0 + j + (size_t)nw * q]; }
+        __syncthreads();
+        for (int e = tid; e < tn * NP; e += nthr) {       // x axis
+            const int j = e % tn, kq = e / tn, kx = kq % L, qy = kq / L;
+            C s = zeroC();
+            for (int qx = 0; qx < L; ++qx) s += A[(qx + L * qy) * TWp + j] * conjC(stw[(kx * qx) % L]);
+            B[kq * TWp + j] = s;
+        }
+        __syncthreads();
+        for (int e = tid; e < tn * NP; e += nthr) {       // y axis
+            const int j = e % tn, kq = e / tn, kx = kq % L, ky = kq / L;
+            C s = zeroC();
+            for (int qy = 0; qy < L; ++qy) s += B[(kx + L * qy) * TWp + j] * conjC(stw[(ky * qy) % L]);
+            A[kq * TWp + j] = s;
+        }
+        __syncthreads();
+        for (int o = tid; o < nF2 * NP; o += nthr) {
+            const int inu = o / NP, ko = o % NP, kox = ko % L, koy = ko / L, nu = inu - g.nK2f;
+            C z = zeroC();
+#pragma unroll
+            for (int f = 0; f < FM::n; ++f) {
+                const int form = FM::ch(f);
+                for (int l = job.lev_first; l < l_end; ++l) {
+                    if (!conv_level_on<KIND>(job, l)) continue;
+                    const DevLevel& lv = V.lev[l];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        if (r == form) continue;
+                        const ConvPiece pc = conv_piece<KIND, CH>(form, r, W, nu, Px, Py);
+                        const int kx = fold1(pc.sk * kox, L), ky = fold1(pc.sk * koy, L);
+                        const int rx = fold1(-pc.sq * kx, L), ry = fold1(-pc.sq * ky, L);
+                        Lin lW = {pc.W0, pc.sW};
+                        int a = t0 - Nin, b = t0 + tn - 1 - Nin;
+                        clip_interval(lW, -(lv.nK1 - 1), lv.nK1 - 1, a, b);
+                        const C* Kh = lv.ch[r].K1h + (kx + L * ky) + (size_t)NP * posB(pc.W0, lv.nK1);
+                        const C* Ar = A + (size_t)(rx + L * ry) * TWp + (Nin - t0);
+                        const int stepK = NP * pc.sW;
+                        C s0 = zeroC(), s1 = zeroC();
+#pragma unroll 4
+                        for (int win = a; win <= b; win += 2) {
+                            const bool two = win + 1 <= b;
+                            const C k0 = ldg(Kh + (ptrdiff_t)stepK * win);
+                            const C k1 = two ? ldg(Kh + (ptrdiff_t)stepK * (win + 1)) : zeroC();
+                            s0 += k0 * Ar[win];
+                            s1 += k1 * Ar[two ? win + 1 : win];
+                        }
+                        const int ph = (kx * fold1(pc.cx, L) + ky * fold1(pc.cy, L)) % L;
+                        z += (s0 + s1) * stw[ph] * FM::coef(f);
+                    }
+                }
+            }
+            Z[o] += z;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nF2 * NP; e += nthr) {          // back transform, x axis
+        const int inu = e / NP, kq = e % NP, kx = kq % L, ky = kq / L;
+        C s = zeroC();
+        for (int x = 0; x < L; ++x) s += Z[inu * NP + x + L * ky] * stw[(kx * x) % L];
+        A[e] = s;
+    }
+    __syncthreads();
+    const double inv = 1.0 / (double)NP;
+    for (int e = tid; e < nF2 * NP; e += nthr) {          // y axis
+        const int inu = e / NP, kq = e % NP, kx = kq % L, ky = kq / L;
+        C s = zeroC();
+        for (int y = 0; y < L; ++y) s += A[inu * NP + kx + L * y] * stw[(ky * y) % L];
+        ConvTab[kq + (size_t)NP * (inu + nF2 * (iW + (size_t)nB2 * iP))] = s * inv;
     }
 }
 
@@ -399,6 +603,7 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
     const int wchunk = (nw + WS - 1) / WS;
     const int l0 = job.lev_first;
     const int l_end = (KIND == JOB_LK2 || KIND == JOB_LK2_LOC) ? l0 + 1 : job.n_nl2;
+    const bool withK1 = (KIND == JOB_LK2_LOC) || job.k1_direct;   // otherwise the K1 pieces come from slab_conv_kernel
 
     if (active)
     for (int item = qs; item < NP * WS; item += nqs) {
@@ -407,9 +612,7 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
         const int w_lo = ws * wchunk, w_hi = min(nw, w_lo + wchunk);
         // momentum arguments of the vertex for this (k, q)
         int akx, aky, aqx, aqy;
-        if (KIND == JOB_K2 || KIND == JOB_SDE_PH || KIND == JOB_LK2_LOC) { akx = kx; aky = ky; aqx = qx; aqy = qy; }
-        else if (KIND == JOB_K2_MF || KIND == JOB_LK2) { akx = kx; aky = ky; aqx = (CH == CH_P) ? Px - qx : qx; aqy = (CH == CH_P) ? Py - qy : qy; }
-        else { akx = Px - qx; aky = Py - qy; aqx = kx; aqy = ky; }              // SDE pp: (P, P - q, k)
+        job_mom_args<KIND, CH>(Px, Py, kx, ky, qx, qy, akx, aky, aqx, aqy);
         const C* Rq = slab + (size_t)nw * iq;
         const C rs_chunk = zeroC();                             // cross-channel arguments are never constant in win
 
@@ -437,7 +640,7 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
                     int W0, v0, w0, W1, v1, w1;
                     convert_freq(W, v_a, w_a, form, r, W0, v0, w0); convert_freq(W, v_b, w_b, form, r, W1, v1, w1);
                     Lin lW = {W0, W1 - W0}, lv2 = {v0, v1 - v0}, lw2 = {w0, w1 - w0};
-                    part += chan_lin_sum(lv, r, mo[r], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi, rs_chunk);
+                    part += chan_lin_sum(lv, r, mo[r], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi, rs_chunk, withK1);
                 }
                 acc += part * cf;
             }
@@ -453,7 +656,8 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
 template <int KIND, int CH>
 __global__ void __launch_bounds__(128, FDGA_COL_MINB)
 column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const C* __restrict__ R,
-              const C* __restrict__ OwnTab, const C* __restrict__ Rtot, C* __restrict__ repvals, Grid g) {
+              const C* __restrict__ OwnTab, const C* __restrict__ Rtot, const C* __restrict__ ConvTab,
+              C* __restrict__ repvals, Grid g) {
     const int col = blockIdx.x;
     const int r0 = cols.start[col], nrep = cols.start[col + 1] - r0;
     int NVc = 1;
@@ -467,9 +671,11 @@ column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const
         double x = 0.0, y = 0.0;
         for (int i = threadIdx.x; i < (int)blockDim.x; i += NVc) { x += redx[i]; y += redy[i]; }
         C val = mkC(x, y);
+        const int iW = cols.iW[col], iP = cols.iP[col], ik = cols.ik[col], inu = cols.rep_inu[r0 + threadIdx.x];
+        const int nF2 = 2 * g.nK2f, nB2 = 2 * g.nK2b - 1;
+        if (ConvTab != nullptr)       // cross-channel K1 pieces (momentum convolution per slab)
+            val += ConvTab[ik + (size_t)g.NP * (inu + nF2 * (iW + (size_t)nB2 * iP))];
         if (OwnTab != nullptr) {      // hoisted own-channel / local-level pieces
-            const int iW = cols.iW[col], iP = cols.iP[col], ik = cols.ik[col], inu = cols.rep_inu[r0 + threadIdx.x];
-            const int nF2 = 2 * g.nK2f, nB2 = 2 * g.nK2b - 1;
             val += OwnTab[inu + nF2 * (iW + nB2 * iP)]
                  + own_B_term<KIND, CH>(V, job, g, iW - (g.nK2b - 1), iP, ik, inu - g.nK2f) * Rtot[iW + nB2 * iP];
         }

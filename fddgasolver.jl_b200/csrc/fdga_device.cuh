@@ -65,6 +65,7 @@ struct DevChan {
     const C *K2swk;   // [W,v,P]    mean_k K2[W,v,P,k]
     const C *K2sww;   // [W,v]      mean_{P,k} K2
     const C *K3sw;    // [W,v,w]    mean_P K3[W,v,w,P]
+    const C *K1h;     // [kappa,W]  sum_P K1[W,P] exp(-2 pi i kappa.P / L)  (kappa fast; fdga_column.cuh: slab_conv_kernel)
 };
 struct DevLevel {
     int type, nK1, nK2b, nK2f, nK3b, nK3f, pad0, pad1;

@@ -569,20 +569,25 @@ __global__ void hartree_kernel(C* __restrict__ Sigma, const double* occ, C U, do
 // ---- real-space contraction of SDE_compute!: src/nonlocal_2/SDE.jl:200-250 -----------------------------
 // SigR[v, tx, ty] (nSf x LS x LS, pre-zeroed) = T * sum_{R,Rp in [-h,h]^2} w(R,Rp) *
 //     ( [R+Rp == t mod LS] G_R(W-v; -R) Lpp_R[W,v,R,Rp] + [-R+Rp == t mod LS] G_R(W+v; -R) Lph_R[W,v,R,Rp] )
-// One thread per (v on the K2 mesh, t); Rp enumerated by congruence instead of scanning all (R, Rp) pairs.
+// One WARP per (v on the K2 mesh, t): lanes split the R sum, Rp is enumerated by congruence instead of scanning all
+// (R, Rp) pairs.  Only t inside the window [-2h, 2h]^2 (mod LS) can be reached by R + Rp / -R + Rp, so only those
+// warps are launched (SigR is pre-zeroed): grid = nF * tw * tw warps with tw = min(LS, 4h + 1).
 __global__ void sde_rs_kernel(const C* __restrict__ GR, const C* __restrict__ LppR, const C* __restrict__ LphR,
-                              C* __restrict__ SigR, Grid g, int nSig, int LS) {
+                              C* __restrict__ SigR, Grid g, int nSig, int LS, int tw) {
     const int L = g.L, h = L / 2, LG = g.LG, nB = 2 * g.nK2b - 1, nF = 2 * g.nK2f, nSf = 2 * nSig;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long n = (long long)nF * LS * LS;
-    if (i >= n) return;
-    int iv = i % nF; int tx = (i / nF) % LS, ty = (i / nF) / LS;
-    int v = iv - g.nK2f;
+    const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= (long long)nF * tw * tw) return;
+    const int iv = wid % nF, wx = (wid / nF) % tw, wy = (wid / nF) / tw;
+    const int tx = (tw == LS) ? wx : modL(wx - 2 * h, LS), ty = (tw == LS) ? wy : modL(wy - 2 * h, LS);
+    const int v = iv - g.nK2f;
     if (!inF(v, nSig)) return;
     C acc = zeroC();
     const size_t pre = (size_t)nB * nF;
     const bool even = (L % 2 == 0);
-    for (int R2 = -h; R2 <= h; ++R2) for (int R1 = -h; R1 <= h; ++R1) {
+    const int nR = 2 * h + 1;
+    for (int r = lane; r < nR * nR; r += 32) {
+        const int R1 = r % nR - h, R2 = r / nR - h;
         const int gx = modL(-R1, LG), gy = modL(-R2, LG);
         const int iRL = modL(R1, L) + L * modL(R2, L);
         double wR = 1.0;
@@ -601,31 +606,45 @@ __global__ void sde_rs_kernel(const C* __restrict__ GR, const C* __restrict__ Lp
                 const int iRpL = modL(Rp1, L) + L * modL(Rp2, L);
                 const size_t lbase = pre * (iRL + (size_t)g.NP * iRpL) + (size_t)nB * iv;
                 const C* Lr = ph ? LphR : LppR;
+                C part = zeroC();
                 for (int iW = 0; iW < nB; ++iW) {
                     const int W = iW - (g.nK2b - 1);
-                    acc += gr_call(GR, g.nG, LG, ph ? W + v : W - v - 1, gx, gy) * Lr[lbase + iW] * wgt;
+                    part += gr_call(GR, g.nG, LG, ph ? W + v : W - v - 1, gx, gy) * Lr[lbase + iW];
                 }
+                acc += part * wgt;
             }
         }
     }
-    SigR[posF(v, nSig) + (size_t)nSf * (tx + (size_t)LS * ty)] = acc * g.T;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o); }
+    if (lane == 0) SigR[posF(v, nSig) + (size_t)nSf * (tx + (size_t)LS * ty)] = acc * g.T;
 }
 
-// ---- SDE_U2_using_G: src/nonlocal/SDE.jl:421-438.  One thread per (nu, R) ----------------------------
+// ---- SDE_U2_using_G: src/nonlocal/SDE.jl:421-438 ---------------------------------------------------------
+// SR[v, R] = fac * sum_{n1, n2} Gm[n1, R] Gp[n2, R] Gp[n1 - n2 + v, R].  One CTA per R: the correlation
+// c[d] = sum_{n1} Gm[n1] Gp[n1 + d] is formed once in shared memory, then SR[v] = fac * sum_{n2} Gp[n2] c[v - n2].
 __global__ void sde_u2_kernel(const C* __restrict__ Gp, const C* __restrict__ Gm, C* __restrict__ SR, int nG, int LG, C fac) {
-    const int nGf = 2 * nG;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long n = (long long)nGf * LG * LG;
-    if (i >= n) return;
-    int iv = i % nGf; long long iR = i / nGf;
-    int v = iv - nG;
-    const C* gp = Gp + (size_t)nGf * iR; const C* gm = Gm + (size_t)nGf * iR;
-    C acc = zeroC();
-    for (int i2 = 0; i2 < nGf; ++i2) for (int i1 = 0; i1 < nGf; ++i1) {
-        int n3 = (i1 - nG) - (i2 - nG) + v;
-        if (inF(n3, nG)) acc += gm[i1] * gp[i2] * gp[posF(n3, nG)];
+    extern __shared__ double sm_raw[];
+    const int nGf = 2 * nG, nd = 2 * nGf - 1;
+    C* gp = reinterpret_cast<C*>(sm_raw);     // [nGf]
+    C* gm = gp + nGf;                         // [nGf]
+    C* c = gm + nGf;                          // [nd]   d = -(nGf-1) .. nGf-1
+    const size_t iR = blockIdx.x;
+    for (int i = threadIdx.x; i < nGf; i += blockDim.x) { gp[i] = Gp[(size_t)nGf * iR + i]; gm[i] = Gm[(size_t)nGf * iR + i]; }
+    __syncthreads();
+    for (int j = threadIdx.x; j < nd; j += blockDim.x) {
+        const int d = j - (nGf - 1);
+        const int lo = max(0, -d), hi = min(nGf - 1, nGf - 1 - d);
+        C s = zeroC();
+        for (int i1 = lo; i1 <= hi; ++i1) s += gm[i1] * gp[i1 + d];
+        c[j] = s;
     }
-    SR[i] = acc * fac;
+    __syncthreads();
+    for (int iv = threadIdx.x; iv < nGf; iv += blockDim.x) {
+        C acc = zeroC();
+        for (int i2 = 0; i2 < nGf; ++i2) acc += gp[i2] * c[iv - i2 + (nGf - 1)];
+        SR[(size_t)nGf * iR + iv] = acc * fac;
+    }
 }
 
 }  // namespace fdga

@@ -26,6 +26,8 @@ struct LevelBuf {
     C* K[3][3];          // [channel][class] (pointers into block)
     size_t len[3];
     C* sw[3][4];         // [channel][K1sw, K2swk, K2sww, K3sw]
+    C* K1h[3];           // [channel] momentum DFT of K1 (slab_conv_kernel)
+    bool k1h_dirty;
     C* core[4];
     size_t corelen;
     bool sw_dirty;
@@ -72,7 +74,13 @@ struct fdga_ctx {
     C* Pi[4]; C* PiT[4]; C* Pisw[4]; size_t lenPi, lenPisw; bool pi_dirty[4];
     C* cache[10]; size_t lenK3;
     C* L[2];              // Lpp, Lph (K2-shaped)
-    C* Rt;                // hoisted right factor, bubble-sized
+    C* Rt;                // hoisted right factor, bubble-sized (= RtL[0])
+    // concurrency lanes: the three channels of a BSE stage (and the pp / ph / U^2 parts of the SDE) are independent, so
+    // they are issued on three streams forked from / joined into the main stream; every lane owns its scratch tables
+    cudaStream_t main_stream; cudaStream_t lane[3]; cudaEvent_t ev_fork, ev_join[3];
+    int cur_lane; bool forked; int opt_serial;
+    C* RtL[3]; C* TtabL[3]; C* OwnTabL[3]; C* RtotL[3]; C* ConvTabL[3];
+    C* SigR2;             // scratch of the U^2 term (its lane runs beside the real-space contraction)
     C* scratchA; C* scratchB; size_t lenScratch;   // bubble-sized ping-pong (DFTs)
     C* GR; C* GRm; C* SigR; C* SigTmp; C* SigAcc;  // G-sized scratch
     C* flat; size_t lenFlat;                       // flatten staging (device)
@@ -92,8 +100,9 @@ struct fdga_ctx {
     int opt_local;           // FDGA_OPT_LOCAL_SOLVER
     bool defer; std::vector<struct Pending> pending;   // batched SG finishes (one NCCL group per BSE stage)
     int n_nl2;               // leading NL2 levels of the F chain
-    C* Ttab;                 // momentum-independent left-factor table [nw, nF2, nB2]
-    C* OwnTab; C* RtotBuf;   // per-slab hoisted pieces: OwnTab[nu | W, P], Rtot[W, P] (W on the K2 mesh)
+    int opt_direct_k1;       // FDGA_OPT_DIRECT_K1
+    // per lane: TtabL = momentum-independent left-factor table [nw, nF2, nB2]; OwnTabL[nu | W, P], RtotL[W, P] = per-slab hoisted
+    // pieces (W on the K2 mesh); ConvTabL[k, nu | W, P] = cross-channel K1 pieces (slab_conv_kernel)
     C* twL; C* twLG;         // DFT twiddles exp(2 pi i j / n) for n = L, LG
     LevelBuf Fsum; bool has_fsum, fsum_dirty;   // K tables of lev[0] + lev[1] when both are NL2 on identical meshes
     int2* d_slabs[4]; int n_slabs[4]; bool slabs_dirty;   // active (W,P) slabs: [pp|ph] x [bubble mesh | K2 mesh]
@@ -137,7 +146,7 @@ static size_t lenK(const fdga_level_desc& d, int cls, int NP, bool nl2) {
 
 static int alloc_level(fdga_ctx* ctx, LevelBuf& lb, const fdga_level_desc& d) {
     memset(&lb, 0, sizeof(lb));
-    lb.d = d; lb.sw_dirty = true;
+    lb.d = d; lb.sw_dirty = true; lb.k1h_dirty = true;
     int NP = ctx->g.NP;
     if (d.type == FDGA_LV_CORE) {
         lb.corelen = (size_t)(2 * d.nK3[0] - 1) * (2 * d.nK3[1]) * (2 * d.nK3[1]);
@@ -158,6 +167,7 @@ static int alloc_level(fdga_ctx* ctx, LevelBuf& lb, const fdga_level_desc& d) {
             size_t n[4] = { (size_t)(2 * d.nK1 - 1), (size_t)(2 * d.nK2[0] - 1) * (2 * d.nK2[1]) * NP,
                             (size_t)(2 * d.nK2[0] - 1) * (2 * d.nK2[1]), (size_t)(2 * d.nK3[0] - 1) * (2 * d.nK3[1]) * (2 * d.nK3[1]) };
             for (int j = 0; j < 4; j++) CK(cudaMalloc(&lb.sw[ch][j], n[j] * sizeof(C)));
+            CK(cudaMalloc(&lb.K1h[ch], n[0] * NP * sizeof(C)));
         }
     }
     return 0;
@@ -165,6 +175,7 @@ static int alloc_level(fdga_ctx* ctx, LevelBuf& lb, const fdga_level_desc& d) {
 static void free_level(LevelBuf& lb) {
     cudaFree(lb.block);
     for (int ch = 0; ch < 3; ch++) for (int j = 0; j < 4; j++) cudaFree(lb.sw[ch][j]);
+    for (int ch = 0; ch < 3; ch++) cudaFree(lb.K1h[ch]);
     for (int i = 0; i < 4; i++) cudaFree(lb.core[i]);
 }
 
@@ -175,6 +186,7 @@ static DevLevel dev_level(const LevelBuf& lb) {
     for (int ch = 0; ch < 3; ch++) {
         d.ch[ch].K1 = lb.K[ch][0]; d.ch[ch].K2 = lb.K[ch][1]; d.ch[ch].K3 = lb.K[ch][2];
         d.ch[ch].K1sw = lb.sw[ch][0]; d.ch[ch].K2swk = lb.sw[ch][1]; d.ch[ch].K2sww = lb.sw[ch][2]; d.ch[ch].K3sw = lb.sw[ch][3];
+        d.ch[ch].K1h = lb.K1h[ch];
     }
     for (int i = 0; i < 4; i++) d.core[i] = lb.core[i];
     if (lb.d.type == FDGA_LV_CORE && lb.corelen == 0) { d.nK3b = 0; d.nK3f = 0; }
@@ -234,7 +246,25 @@ static int refresh_fsum(fdga_ctx* ctx) {
     Scope sc(ctx, FDGA_T_MISC);
     LAUNCH(FDGA_T_MISC, axpby_kernel, nblk(ctx->Fsum.blocklen, 256), 256, ctx->Fsum.block, ctx->lev[0].block, 1.0, ctx->lev[1].block, 1.0, (long long)ctx->Fsum.blocklen);
     CK(cudaGetLastError());
-    ctx->fsum_dirty = false;
+    ctx->fsum_dirty = false; ctx->Fsum.k1h_dirty = true;
+    return 0;
+}
+// momentum DFT of the K1 tables of every NL2 level a column job may read (and of the merged level)
+static int refresh_k1h(fdga_ctx* ctx) {
+    for (int l = -1; l < ctx->nlev; l++) {
+        if (l < 0 && !ctx->has_fsum) continue;
+        LevelBuf& lb = l < 0 ? ctx->Fsum : ctx->lev[l];
+        if (lb.d.type != FDGA_LV_NL2 || !lb.k1h_dirty) continue;
+        if (l < 0 && ctx->fsum_dirty) continue;
+        Scope sc(ctx, FDGA_T_SWAVE);
+        K1hOut out; for (int ch = 0; ch < 3; ch++) out.p[ch] = lb.K1h[ch];
+        long long n = (long long)(2 * lb.d.nK1 - 1) * ctx->g.NP;
+        (void)n;
+        k1_dft_kernel<<<dim3(2 * lb.d.nK1 - 1, 3), std::min(ctx->g.NP, 256), (size_t)(ctx->g.NP + ctx->g.L) * sizeof(C), ctx->stream>>>(dev_level(lb), ctx->g.L, ctx->g.NP, ctx->twL, out);
+        ctx->n_launch[FDGA_T_SWAVE]++; ctx->total_launches++;
+        lb.k1h_dirty = false;
+    }
+    CK(cudaGetLastError());
     return 0;
 }
 static int refresh_pi(fdga_ctx* ctx, int which) {
@@ -412,7 +442,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     fdga_ctx* ctx = new fdga_ctx();
     ctx->dims = *dims; ctx->device = device; ctx->nlev = dims->nlev;
     ctx->nranks = 1; ctx->rank = 0; ctx->comm = nullptr; memset(&ctx->nccl, 0, sizeof(ctx->nccl));
-    ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0; ctx->opt_generic = 0; ctx->opt_hartree_once = 0; ctx->opt_local = 0; ctx->defer = false;
+    ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0; ctx->opt_generic = 0; ctx->opt_hartree_once = 0; ctx->opt_local = 0; ctx->opt_direct_k1 = 0; ctx->defer = false;
     memset(ctx->t_ms, 0, sizeof(ctx->t_ms)); memset(ctx->n_launch, 0, sizeof(ctx->n_launch));
     Grid& g = ctx->g;
     g.T = dims->T; g.L = dims->nq; g.NP = dims->nq * dims->nq; g.nPiB = dims->nPiB; g.nPiF = dims->nPiF;
@@ -420,6 +450,10 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_create_error = std::string(#call) + ": " + cudaGetErrorString(e_); delete ctx; return 1; } } while (0)
     CKC(cudaSetDevice(device));
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->main_stream = ctx->stream; ctx->lane[0] = ctx->stream; ctx->cur_lane = 0; ctx->forked = false; ctx->opt_serial = 0;
+    for (int i = 1; i < 3; i++) CKC(cudaStreamCreateWithFlags(&ctx->lane[i], cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 3; i++) CKC(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
     for (int l = 0; l < ctx->nlev; l++) if (alloc_level(ctx, ctx->lev[l], dims->lev[l])) { g_create_error = ctx->err; delete ctx; return 1; }
     fdga_level_desc dz = d0; dz.type = FDGA_LV_NL2;
     if (alloc_level(ctx, ctx->FL, dz) || alloc_level(ctx, ctx->Fbuff, dz)) { g_create_error = ctx->err; delete ctx; return 1; }
@@ -436,6 +470,12 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     for (int i = 0; i < 10; i++) { CKC(cudaMalloc(&ctx->cache[i], ctx->lenK3 * sizeof(C))); CKC(cudaMemsetAsync(ctx->cache[i], 0, ctx->lenK3 * sizeof(C), ctx->stream)); }
     for (int i = 0; i < 2; i++) { CKC(cudaMalloc(&ctx->L[i], ctx->lev[0].len[1] * sizeof(C))); CKC(cudaMemsetAsync(ctx->L[i], 0, ctx->lev[0].len[1] * sizeof(C), ctx->stream)); }
     CKC(cudaMalloc(&ctx->Rt, ctx->lenPi * sizeof(C)));
+    ctx->RtL[0] = ctx->Rt;
+    {   // lanes 1, 2 only ever hold right factors with W on the K2 mesh (BSE_L_K2!)
+        size_t n = (size_t)2 * std::max(g.nPiF, g.nK2f) * (2 * g.nK2b - 1) * g.NP * g.NP;
+        for (int i = 1; i < 3; i++) CKC(cudaMalloc(&ctx->RtL[i], n * sizeof(C)));
+    }
+    CKC(cudaMalloc(&ctx->SigR2, ctx->lenG * sizeof(C)));
     ctx->lenScratch = ctx->lenPi;
     CKC(cudaMalloc(&ctx->scratchA, ctx->lenScratch * sizeof(C))); CKC(cudaMalloc(&ctx->scratchB, ctx->lenScratch * sizeof(C)));
     CKC(cudaMalloc(&ctx->GR, ctx->lenG * sizeof(C))); CKC(cudaMalloc(&ctx->GRm, ctx->lenG * sizeof(C)));
@@ -443,6 +483,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     ctx->lenFlat = 3 * (ctx->lev[0].len[0] + ctx->lev[0].len[1] + ctx->lev[0].len[2]);
     CKC(cudaMalloc(&ctx->flat, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->flat2, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->stash, ctx->lenFlat * sizeof(C)));
     CKC(cudaMalloc(&ctx->d_occ, sizeof(double)));
+    for (int i = 0; i < 3; i++) CKC(cudaMalloc(&ctx->ConvTabL[i], ctx->lev[0].len[1] * sizeof(C)));
     {   // merged level (S.F + S.F0) for the K2 left factor
         const fdga_level_desc& a = dims->lev[0]; const fdga_level_desc& b = dims->lev[1];
         ctx->has_fsum = dims->nlev >= 3 && b.type == FDGA_LV_NL2 && a.nK1 == b.nK1 && a.nK2[0] == b.nK2[0] && a.nK2[1] == b.nK2[1] && a.nK3[0] == b.nK3[0] && a.nK3[1] == b.nK3[1];
@@ -455,8 +496,10 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     twiddle_kernel<<<nblk(g.LG, 64), 64, 0, ctx->stream>>>(ctx->twLG, g.LG);
     for (int i = 0; i < 3; i++) { CKC(cudaMalloc(&ctx->Rt3[i], ctx->lenPi * sizeof(C))); ctx->rt_kind[i] = -1; }
     for (int i = 0; i < 4; i++) { ctx->d_slabs[i] = nullptr; ctx->n_slabs[i] = 0; } ctx->slabs_dirty = true;
-    CKC(cudaMalloc(&ctx->OwnTab, (size_t)(2 * g.nK2f) * (2 * g.nK2b - 1) * g.NP * sizeof(C))); CKC(cudaMalloc(&ctx->RtotBuf, (size_t)(2 * g.nK2b - 1) * g.NP * sizeof(C)));
-    CKC(cudaMalloc(&ctx->Ttab, (size_t)(2 * g.nPiF) * (2 * g.nK2f) * (2 * g.nK2b - 1) * sizeof(C)));
+    for (int i = 0; i < 3; i++) {
+        CKC(cudaMalloc(&ctx->OwnTabL[i], (size_t)(2 * g.nK2f) * (2 * g.nK2b - 1) * g.NP * sizeof(C))); CKC(cudaMalloc(&ctx->RtotL[i], (size_t)(2 * g.nK2b - 1) * g.NP * sizeof(C)));
+        CKC(cudaMalloc(&ctx->TtabL[i], (size_t)(2 * g.nPiF) * (2 * g.nK2f) * (2 * g.nK2b - 1) * sizeof(C)));
+    }
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; s.d_rep[0] = s.d_rep[1] = s.d_rep[2] = nullptr; s.ncol = 0; s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = nullptr; }
     CKC(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
@@ -475,11 +518,13 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
     cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->Rt); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB);
     cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
-    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); cudaFree(ctx->Ttab); cudaFree(ctx->OwnTab); cudaFree(ctx->RtotBuf); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) cudaFree(ctx->d_slabs[i]);
+    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); for (int i = 0; i < 3; i++) { cudaFree(ctx->TtabL[i]); cudaFree(ctx->OwnTabL[i]); cudaFree(ctx->RtotL[i]); cudaFree(ctx->ConvTabL[i]); if (i) cudaFree(ctx->RtL[i]); } cudaFree(ctx->SigR2); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) cudaFree(ctx->d_slabs[i]);
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); for (int k = 0; k < 3; k++) cudaFree(s.d_rep[k]);
         cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); }
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
-    cudaStreamDestroy(ctx->stream);
+    for (int i = 1; i < 3; i++) cudaStreamDestroy(ctx->lane[i]);
+    cudaEventDestroy(ctx->ev_fork); for (int i = 0; i < 3; i++) cudaEventDestroy(ctx->ev_join[i]);
+    cudaStreamDestroy(ctx->main_stream);
     delete ctx;
     return 0;
 }
@@ -492,6 +537,8 @@ int fdga_set_option(fdga_ctx* ctx, int opt, int value) {
         if (value && (ctx->g.L != 1 || ctx->g.LG != 1)) FAIL("FDGA_OPT_LOCAL_SOLVER needs nq = LG = 1");
         ctx->opt_local = value != 0; invalidate_rt(ctx); return 0;
     }
+    if (opt == FDGA_OPT_DIRECT_K1) { ctx->opt_direct_k1 = value != 0; return 0; }
+    if (opt == FDGA_OPT_SERIAL) { ctx->opt_serial = value != 0; return 0; }
     FAIL("fdga_set_option: unknown option");
 }
 int fdga_sync(fdga_ctx* ctx) { CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
@@ -562,7 +609,7 @@ int fdga_set_vertex(fdga_ctx* ctx, int which, int channel, int cls, const fdga_c
     if ((size_t)n != lb->len[cls]) FAIL("fdga_set_vertex: length mismatch");
     CK(cudaMemcpyAsync(lb->K[channel][cls], host, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    lb->sw_dirty = true; ctx->fsum_dirty = true;
+    lb->sw_dirty = true; lb->k1h_dirty = true; ctx->fsum_dirty = true;
     invalidate_rt(ctx);
     return 0;
 }
@@ -668,7 +715,7 @@ int fdga_flatten_F(fdga_ctx* ctx, fdga_c64* host_y) {
 static int unflatten_dev(fdga_ctx* ctx, LevelBuf& lb, const C* src, double scale) {
     LAUNCH(FDGA_T_MISC, scale_copy_kernel, nblk(lb.blocklen, 256), 256, lb.block, src, scale, (long long)lb.blocklen);
     CK(cudaGetLastError());
-    lb.sw_dirty = true; ctx->fsum_dirty = true;
+    lb.sw_dirty = true; lb.k1h_dirty = true; ctx->fsum_dirty = true;
     return 0;
 }
 int fdga_stash_F(fdga_ctx* ctx) { CK(cudaSetDevice(ctx->device)); return flatten_dev(ctx, ctx->lev[0], ctx->stash); }
@@ -771,7 +818,7 @@ static int pi_kind(int ch, bool reference) { return ch == FDGA_PCH ? (reference 
 extern "C++" {
 template <int KIND>
 static int launch_right(fdga_ctx* ctx, int ch, const DevChain& F0, const DevChain& FL, int No, int Ninner, C* Rdst = nullptr) {
-    if (!Rdst) Rdst = ctx->Rt;
+    if (!Rdst) Rdst = ctx->RtL[ctx->cur_lane];
     if (ensure_slabs(ctx)) return 1;
     Scope sc(ctx, FDGA_T_RIGHT);
     const C* p0 = ctx->PiT[pi_kind(ch, true)]; const C* p1 = ctx->PiT[pi_kind(ch, false)];
@@ -788,28 +835,54 @@ static int launch_right(fdga_ctx* ctx, int ch, const DevChain& F0, const DevChai
 
 template <int KIND, int CH>
 static void kernel_slab_own(fdga_ctx* ctx, const DevChain& V, const ColJob& job, int kind, const C* R, int cat) {
-    size_t smem = (size_t)job.nw * sizeof(C);
-    slab_own_kernel<KIND, CH><<<ctx->n_slabs[kind], 128, smem, ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->Ttab, ctx->OwnTab, ctx->RtotBuf, ctx->g);
+    const int PC = std::max(1, std::min(2 * ctx->g.nK2f, 2048 / job.nw));
+    size_t smem = (size_t)job.nw * (1 + PC) * sizeof(C);
+    slab_own_kernel<KIND, CH><<<ctx->n_slabs[kind], 256, smem, ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->TtabL[ctx->cur_lane], ctx->OwnTabL[ctx->cur_lane], ctx->RtotL[ctx->cur_lane], ctx->g, PC);
     ctx->n_launch[cat]++; ctx->total_launches++;
+}
+// column path (fdga_column.cuh): momentum-independent table + one CTA per output column
+// cross-channel K1 pieces of a column job as a per-slab momentum convolution; returns the table (or null when the job
+// has no such piece / the slab does not fit in shared memory, in which case job.k1_direct is switched on)
+template <int KIND, int CH>
+static int launch_slab_conv(fdga_ctx* ctx, const DevChain& V, ColJob& job, int kind, const C* R, int cat, const C** tab) {
+    *tab = nullptr;
+    if (KIND == JOB_LK2_LOC || job.k1_direct) return 0;
+    bool any = false;
+    for (int l = job.lev_first; l < conv_level_end<KIND>(job); ++l) any = any || conv_level_on<KIND>(job, l);
+    if (!any || ctx->n_slabs[kind] == 0) return 0;
+    const Grid& g = ctx->g;
+    const int nF2 = 2 * g.nK2f;
+    const size_t budget = 200 * 1024;
+    auto bytes = [&](int tw) { return ((size_t)2 * g.NP * (tw | 1) + (size_t)nF2 * g.NP + g.L) * sizeof(C); };
+    int TW = std::max(job.nw, nF2);
+    while (TW > nF2 && bytes(TW) > budget) TW = std::max(nF2, (TW + 1) / 2);
+    if (bytes(TW) > budget) { job.k1_direct = 1; return 0; }
+    if (refresh_k1h(ctx)) return 1;
+    CK(cudaFuncSetAttribute(slab_conv_kernel<KIND, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(TW)));
+    slab_conv_kernel<KIND, CH><<<ctx->n_slabs[kind], 512, bytes(TW), ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->twL, ctx->ConvTabL[ctx->cur_lane], g, TW);
+    ctx->n_launch[cat]++; ctx->total_launches++;
+    *tab = ctx->ConvTabL[ctx->cur_lane];
+    return 0;
 }
 // column path (fdga_column.cuh): momentum-independent table + one CTA per output column
 template <int KIND, int CH>
 static int launch_column_t(fdga_ctx* ctx, const DevChain& V, ColJob job, SymGroup& s, const C* R, int cat) {
     if (ensure_slabs(ctx)) return 1;
     Scope sc(ctx, cat);
-    const C* own = nullptr; const C* rtot = nullptr;
+    const C* own = nullptr; const C* rtot = nullptr; const C* conv = nullptr;
+    const bool pp = (KIND == JOB_SDE_PP) || ((KIND == JOB_K2 || KIND == JOB_K2_MF || KIND == JOB_LK2 || KIND == JOB_LK2_LOC) && CH == CH_P);
+    const int kind = (pp ? 0 : 1) + 2;
     if (KIND != JOB_LK2 && KIND != JOB_LK2_LOC) {
         // prologue: momentum-independent levels tabulated per (W, nu, w), then everything that does not depend on the
         // column momentum k reduced per slab (W, P): OwnTab[nu | W, P], Rtot[W, P]
         long long n = (long long)job.nw * (2 * ctx->g.nK2f) * (2 * ctx->g.nK2b - 1);
-        LAUNCH(cat, (loc_table_kernel<KIND, CH>), nblk(n, 128), 128, V, job, ctx->g, ctx->Ttab);
-        const bool pp = (KIND == JOB_SDE_PP) || ((KIND == JOB_K2 || KIND == JOB_K2_MF) && CH == CH_P);
-        const int kind = (pp ? 0 : 1) + 2;
+        LAUNCH(cat, (loc_table_kernel<KIND, CH>), nblk(n, 32), 32, V, job, ctx->g, ctx->TtabL[ctx->cur_lane]);
         if (ctx->n_slabs[kind] > 0)
             kernel_slab_own<KIND, CH>(ctx, V, job, kind, R, cat);
-        own = ctx->OwnTab; rtot = ctx->RtotBuf;
+        own = ctx->OwnTabL[ctx->cur_lane]; rtot = ctx->RtotL[ctx->cur_lane];
     }
-    if (s.ncol > 0) LAUNCH(cat, (column_kernel<KIND, CH>), (unsigned)s.ncol, 128, V, job, col_dev(s), R, own, rtot, s.d_repvals, ctx->g);
+    if (launch_slab_conv<KIND, CH>(ctx, V, job, kind, R, cat, &conv)) return 1;
+    if (s.ncol > 0) LAUNCH(cat, (column_kernel<KIND, CH>), (unsigned)s.ncol, 128, V, job, col_dev(s), R, own, rtot, conv, s.d_repvals, ctx->g);
     CK(cudaGetLastError());
     return 0;
 }
@@ -821,7 +894,7 @@ static int launch_column(fdga_ctx* ctx, int ch, const DevChain& V, ColJob job, S
 }
 }  // extern "C++"
 static ColJob make_job(fdga_ctx* ctx, int lev_first, int nw, int Ninner, int slabN, C scale) {
-    ColJob j; j.lev_first = lev_first; j.n_nl2 = ctx->n_nl2; j.own_only = ctx->opt_sde_own_gamma; j.nw = nw; j.Ninner = Ninner;
+    ColJob j; j.lev_first = lev_first; j.n_nl2 = ctx->n_nl2; j.own_only = ctx->opt_sde_own_gamma; j.k1_direct = ctx->opt_direct_k1; j.nw = nw; j.Ninner = Ninner;
     j.slabW_N = slabN; j.scale_re = scale.x; j.scale_im = scale.y;
     return j;
 }
@@ -896,6 +969,27 @@ static int flush_pending(fdga_ctx* ctx) {
     return 0;
 }
 
+// ---- concurrency lanes -------------------------------------------------------------------------------------
+// (profiling and the straightforward A/B kernels run serially on the main stream so that their times stay attributable)
+static bool lanes_enabled(fdga_ctx* ctx) { return !ctx->profile && !ctx->opt_generic && !ctx->opt_serial; }
+// everything the lanes read but do not own must be current before the fork
+static int lanes_fork(fdga_ctx* ctx) {
+    if (!lanes_enabled(ctx) || ctx->forked) return 0;
+    for (int ch = 0; ch < 3; ch++) if (ensure_pi(ctx, ch)) return 1;
+    if (refresh_fsum(ctx) || refresh_k1h(ctx) || ensure_slabs(ctx)) return 1;
+    CK(cudaEventRecord(ctx->ev_fork, ctx->main_stream));
+    for (int i = 1; i < 3; i++) CK(cudaStreamWaitEvent(ctx->lane[i], ctx->ev_fork, 0));
+    ctx->forked = true;
+    return 0;
+}
+static void lane_use(fdga_ctx* ctx, int i) { if (ctx->forked) { ctx->cur_lane = i; ctx->stream = ctx->lane[i]; } }
+static int lanes_join(fdga_ctx* ctx) {
+    if (!ctx->forked) return 0;
+    ctx->forked = false; ctx->cur_lane = 0; ctx->stream = ctx->main_stream;
+    for (int i = 1; i < 3; i++) { CK(cudaEventRecord(ctx->ev_join[i], ctx->lane[i])); CK(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_join[i], 0)); }
+    return 0;
+}
+
 int fdga_bse_K1(fdga_ctx* ctx, int ch, int mfrg) {
     CK(cudaSetDevice(ctx->device));
     if (ch < 0 || ch > 2) FAIL("fdga_bse_K1: bad channel");
@@ -932,13 +1026,13 @@ int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
     if (ctx->opt_local) {       // local solver: omega over the bubble mesh, crossing on the right vertex
         if (launch_right<RK_LK2_LOC>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1;
         ColJob job = make_job(ctx, 0, 2 * ctx->g.nPiF, ctx->g.nPiF, ctx->g.nK2b, mkC(scale, 0.0));
-        if (launch_column<JOB_LK2_LOC>(ctx, ch, F, job, s, ctx->Rt, FDGA_T_L_K2)) return 1;
+        if (launch_column<JOB_LK2_LOC>(ctx, ch, F, job, s, ctx->RtL[ctx->cur_lane], FDGA_T_L_K2)) return 1;
         return finish_or_defer(ctx, s, ctx->FL.K[ch][1], PK_LK2, ch);
     }
     if (launch_right<RK_LK2>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nK2f)) return 1;
     if (!ctx->opt_generic) {
         ColJob job = make_job(ctx, 0, 2 * ctx->g.nK2f, ctx->g.nK2f, ctx->g.nK2b, mkC(scale, 0.0));
-        if (launch_column<JOB_LK2>(ctx, ch, F, job, s, ctx->Rt, FDGA_T_L_K2)) return 1;
+        if (launch_column<JOB_LK2>(ctx, ch, F, job, s, ctx->RtL[ctx->cur_lane], FDGA_T_L_K2)) return 1;
     } else {
         Scope sc(ctx, FDGA_T_L_K2);
         if (c1 > c0) {
@@ -1044,7 +1138,7 @@ int fdga_bse_K3(fdga_ctx* ctx, int ch, int mfrg) {
 int fdga_set_F_from_Fbuff(fdga_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->lev[0].block, ctx->Fbuff.block, ctx->Fbuff.blocklen * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
-    ctx->lev[0].sw_dirty = true; ctx->fsum_dirty = true;
+    ctx->lev[0].sw_dirty = true; ctx->lev[0].k1h_dirty = true; ctx->fsum_dirty = true;
     return 0;
 }
 
@@ -1064,8 +1158,11 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
     CK(cudaMemsetAsync(ctx->L[0], 0, nK2 * sizeof(C), ctx->stream));
     CK(cudaMemsetAsync(ctx->L[1], 0, nK2 * sizeof(C), ctx->stream));
     if (!ctx->opt_generic) {
-        // fused recursion: one column launch per bubble kind covers every level of the chain (fdga_column.cuh)
+        // fused recursion: one column launch per bubble kind covers every level of the chain (fdga_column.cuh);
+        // lanes: pp on 0, ph on 1, (G transforms + U^2 term) on 2
+        if (lanes_fork(ctx)) return 1;
         for (int pp = 1; pp >= 0; pp--) {
+            lane_use(ctx, pp ? 0 : 1);
             SymGroup& s = ctx->sg[pp ? FDGA_SG_PP2 : FDGA_SG_PH2];
             const C* PiT = ctx->PiT[pp ? (reference ? FDGA_PI0PP : FDGA_PIPP) : (reference ? FDGA_PI0PH : FDGA_PIPH)];
             ColJob job = make_job(ctx, from, 2 * g.nPiF, g.nPiF, g.nPiB, U * scale);
@@ -1100,21 +1197,18 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
         }
     }
     C* Sout = ctx->SigAcc;
+    const long long pre = (long long)(2 * g.nK2b - 1) * (2 * g.nK2f);
+    const double nrm = 1.0 / ((double)g.L * g.L * g.L * g.L);
+    // L arrays are transformed in place (clobbered, as in the reference: SURVEY E4)
+    for (int pp = 1; pp >= 0; pp--) {
+        lane_use(ctx, pp ? 0 : 1);
+        Scope sc(ctx, FDGA_T_SDE_RS);
+        if (dft4(ctx, ctx->L[pp ? 0 : 1], pp ? ctx->scratchA : ctx->scratchB, pre, -1, nrm, FDGA_T_SDE_RS)) return 1;
+    }
+    lane_use(ctx, 2);
     {
         Scope sc(ctx, FDGA_T_SDE_RS);
         if (dft2_G(ctx, ctx->G[gwhich], ctx->GR, ctx->SigTmp, -1, 1.0 / ((double)g.LG * g.LG), FDGA_T_SDE_RS)) return 1;
-        long long pre = (long long)(2 * g.nK2b - 1) * (2 * g.nK2f);
-        double nrm = 1.0 / ((double)g.L * g.L * g.L * g.L);
-        // L arrays are transformed in place (clobbered, as in the reference: SURVEY E4)
-        if (dft4(ctx, ctx->L[0], ctx->scratchA, pre, -1, nrm, FDGA_T_SDE_RS)) return 1;
-        if (dft4(ctx, ctx->L[1], ctx->scratchA, pre, -1, nrm, FDGA_T_SDE_RS)) return 1;
-        CK(cudaMemsetAsync(ctx->SigR, 0, ctx->lenG * sizeof(C), ctx->stream));
-        LAUNCH(FDGA_T_SDE_RS, sde_rs_kernel, nblk((long long)(2 * g.nK2f) * g.LG * g.LG, 64), 64, ctx->GR, ctx->L[0], ctx->L[1], ctx->SigR, g, g.nG, g.LG);
-        CK(cudaGetLastError());
-        if (dft2_G(ctx, ctx->SigR, Sout, ctx->SigTmp, +1, 1.0, FDGA_T_SDE_RS)) return 1;
-        SymGroup& ss = ctx->sg[FDGA_SG_SIGMA];
-        LAUNCH(FDGA_T_SDE_RS, symmetrize_kernel, nblk(ss.nmem, 256), 256, Sout, sym_dev(ss));
-        CK(cudaGetLastError());
     }
     if (include_U2) {
         Scope sc(ctx, FDGA_T_SDE_U2);
@@ -1122,11 +1216,24 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
         // GR already holds fft(G)/LG^2 ; GRm = bfft(G)/LG^2
         if (dft2_G(ctx, ctx->G[gwhich], ctx->GRm, ctx->SigTmp, +1, inv, FDGA_T_SDE_U2)) return 1;
         C fac = (U * U) * (g.T * g.T);
-        LAUNCH(FDGA_T_SDE_U2, sde_u2_kernel, nblk(ctx->lenG, 64), 64, ctx->GR, ctx->GRm, ctx->SigR, g.nG, g.LG, fac);
-        if (dft2_G(ctx, ctx->SigR, ctx->GRm, ctx->SigTmp, +1, 1.0, FDGA_T_SDE_U2)) return 1;
+        sde_u2_kernel<<<(unsigned)(g.LG * g.LG), 64, (size_t)(8 * g.nG - 1) * sizeof(C), ctx->stream>>>(ctx->GR, ctx->GRm, ctx->SigR2, g.nG, g.LG, fac);
+        ctx->n_launch[FDGA_T_SDE_U2]++; ctx->total_launches++;
+        if (dft2_G(ctx, ctx->SigR2, ctx->GRm, ctx->SigTmp, +1, 1.0, FDGA_T_SDE_U2)) return 1;
         SymGroup& ss = ctx->sg[FDGA_SG_SIGMA];
         LAUNCH(FDGA_T_SDE_U2, symmetrize_kernel, nblk(ss.nmem, 256), 256, ctx->GRm, sym_dev(ss));
-        LAUNCH(FDGA_T_SDE_U2, add_axpby_kernel, nblk(ctx->lenG, 256), 256, Sout, ctx->GRm, 1.0, (const C*)nullptr, 0.0, (long long)ctx->lenG);
+        CK(cudaGetLastError());
+    }
+    if (lanes_join(ctx)) return 1;
+    {
+        Scope sc(ctx, FDGA_T_SDE_RS);
+        CK(cudaMemsetAsync(ctx->SigR, 0, ctx->lenG * sizeof(C), ctx->stream));
+        const int twin = std::min(g.LG, 4 * (g.L / 2) + 1);
+        LAUNCH(FDGA_T_SDE_RS, sde_rs_kernel, nblk((long long)(2 * g.nK2f) * twin * twin * 32, 128), 128, ctx->GR, ctx->L[0], ctx->L[1], ctx->SigR, g, g.nG, g.LG, twin);
+        CK(cudaGetLastError());
+        if (dft2_G(ctx, ctx->SigR, Sout, ctx->SigTmp, +1, 1.0, FDGA_T_SDE_RS)) return 1;
+        SymGroup& ss = ctx->sg[FDGA_SG_SIGMA];
+        LAUNCH(FDGA_T_SDE_RS, symmetrize_kernel, nblk(ss.nmem, 256), 256, Sout, sym_dev(ss));
+        if (include_U2) LAUNCH(FDGA_T_SDE_RS, add_axpby_kernel, nblk(ctx->lenG, 256), 256, Sout, ctx->GRm, 1.0, (const C*)nullptr, 0.0, (long long)ctx->lenG);
         CK(cudaGetLastError());
     }
     if (include_Hartree) {
@@ -1157,26 +1264,37 @@ int fdga_sde(fdga_ctx* ctx, int strategy, int include_U2, int include_Hartree) {
 }
 
 // ---- drivers ---------------------------------------------------------------------------------------------
+// the BSE stages of one iteration: [L_K2, L_K3] | [K1, K2] | [K3].  The three channels of a stage are independent up to
+// their post-fixes: each runs on its own lane, and the stage ends with one batched SG finish (one NCCL group).
+static int bse_stages(fdga_ctx* ctx, bool with_L, int mfrg) {
+    const int order[3] = {FDGA_PCH, FDGA_ACH, FDGA_TCH};      // p, a, t (BSE_templates.jl:35-38 needs a before t)
+    ctx->defer = true;
+    int rc = 0;
+    if (with_L) {
+        rc = lanes_fork(ctx);
+        for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_L_K2(ctx, order[i]); }
+        for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_L_K3(ctx, order[i]); }   // reads caches and bubbles only
+        if (lanes_join(ctx)) rc = 1;
+        if (!rc) rc = flush_pending(ctx);
+    }
+    if (!rc) rc = lanes_fork(ctx);
+    for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_K1(ctx, order[i], mfrg); }
+    for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_K2(ctx, order[i], mfrg); }    // K1 and K2 share inputs (FL, right factor)
+    if (lanes_join(ctx)) rc = 1;
+    if (!rc) rc = flush_pending(ctx);
+    if (!rc) rc = lanes_fork(ctx);
+    for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_K3(ctx, order[i], mfrg); }
+    if (lanes_join(ctx)) rc = 1;
+    if (!rc) rc = flush_pending(ctx);
+    ctx->defer = false; ctx->pending.clear();
+    return rc;
+}
+
 int fdga_iterate_solver(fdga_ctx* ctx, int strategy, int update_sigma) {
     if (strategy != FDGA_SCPA && strategy != FDGA_FDPA) FAIL("fdga_iterate_solver: strategy must be scPA or fdPA");
     if (update_sigma) { if (fdga_dyson(ctx) || (ctx->opt_local ? fdga_bubbles_local(ctx, 0) : fdga_bubbles_real_space(ctx, 0))) return 1; }
     if (fdga_build_K3_cache(ctx, 0, 0)) return 1;
-    const int order[3] = {FDGA_PCH, FDGA_ACH, FDGA_TCH};      // p, a, t (BSE_templates.jl:35-38 needs a before t)
-    // the three channels of a stage are independent up to their post-fixes: one batched SG finish per stage
-    ctx->defer = true;
-    int rc = 0;
-    if (strategy == FDGA_FDPA) {
-        for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_L_K2(ctx, order[i]);
-        for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_L_K3(ctx, order[i]);      // reads caches and bubbles only
-        if (!rc) rc = flush_pending(ctx);
-    }
-    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_K1(ctx, order[i], 0);
-    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_K2(ctx, order[i], 0);         // K1 and K2 share inputs (FL, right factor)
-    if (!rc) rc = flush_pending(ctx);
-    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_K3(ctx, order[i], 0);
-    if (!rc) rc = flush_pending(ctx);
-    ctx->defer = false; ctx->pending.clear();
-    if (rc) return 1;
+    if (bse_stages(ctx, strategy == FDGA_FDPA, 0)) return 1;
     if (fdga_set_F_from_Fbuff(ctx)) return 1;
     if (update_sigma) { if (fdga_sde(ctx, strategy, 1, 1)) return 1; }
     return 0;
@@ -1188,19 +1306,7 @@ int fdga_mfrg_matvec(fdga_ctx* ctx, const fdga_c64* host_x, fdga_c64* host_y, in
     CK(cudaMemcpyAsync(ctx->flat2, host_x, ctx->lenFlat * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
     if (unflatten_dev(ctx, ctx->lev[0], ctx->flat2, factor)) return 1;
     if (fdga_build_K3_cache(ctx, 1, first)) return 1;
-    const int order[3] = {FDGA_PCH, FDGA_ACH, FDGA_TCH};
-    ctx->defer = true;
-    int rc = 0;
-    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_L_K2(ctx, order[i]);
-    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_L_K3(ctx, order[i]);
-    if (!rc) rc = flush_pending(ctx);
-    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_K1(ctx, order[i], 1);
-    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_K2(ctx, order[i], 1);
-    if (!rc) rc = flush_pending(ctx);
-    for (int i = 0; i < 3 && !rc; i++) rc = fdga_bse_K3(ctx, order[i], 1);
-    if (!rc) rc = flush_pending(ctx);
-    ctx->defer = false; ctx->pending.clear();
-    if (rc) return 1;
+    if (bse_stages(ctx, true, 1)) return 1;
     if (fdga_set_F_from_Fbuff(ctx)) return 1;
     if (flatten_dev(ctx, ctx->lev[0], ctx->flat)) return 1;
     LAUNCH(FDGA_T_MISC, mfrg_residual_kernel, nblk(ctx->lenFlat, 256), 256, ctx->flat, ctx->flat2, ctx->flat, factor, (long long)ctx->lenFlat);

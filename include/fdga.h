@@ -88,7 +88,11 @@ enum { FDGA_OPT_SDE_OWN_GAMMA = 0,
                                         subtracted twice); 1 = subtracted once (reproduces test/test_siam_fdPA.jl:84) */
        FDGA_OPT_LOCAL_SOLVER = 3     /* 1 = the context models the local ParquetSolver (src/ParquetSolver.jl) on a 1 x 1
                                         momentum mesh: BSE_L_K2! in its local form (src/BSEa/BSEa_K2.jl:1-40), bubbles! with
-                                        the 1/nu tail (src/bubble.jl:9-36).  Needs nq = LG = 1. */ };
+                                        the 1/nu tail (src/bubble.jl:9-36).  Needs nq = LG = 1. */,
+       FDGA_OPT_DIRECT_K1 = 4        /* 1 = sum the cross-channel K1 terms of the column kernels term by term instead of
+                                        through the per-slab momentum convolution (A/B check of slab_conv_kernel) */,
+       FDGA_OPT_SERIAL = 5           /* 1 = issue every kernel on the main stream (by default the three channels of a BSE
+                                        stage and the pp / ph / U^2 parts of the SDE run on concurrent streams) */ };
 int  fdga_set_option(fdga_ctx* ctx, int opt, int value);
 /* one process per GPU; `unique_id` = the 128-byte ncclUniqueId obtained on rank 0 by
  * fdga_comm_unique_id and broadcast by the host (MPI in Julia, torch.distributed in tests). */

@@ -29,6 +29,53 @@ static const C* rnd_array(size_t n, double scale = 1.0) {
 }
 #endif
 
+// host restatement of slab_conv_kernel (same formulas, plain loops): X[k + NP * inu] for one slab
+template <int KIND, int CH>
+static std::vector<C> conv_host(const DevChain& V, const ColJob& job, const Grid& g, const C* Rs, int W, int iP) {
+    typedef Forms<KIND, CH> FM;
+    const int L = g.L, NP = g.NP, nF2 = 2 * g.nK2f, nw = job.nw, Nin = job.Ninner;
+    const double tau = 6.283185307179586476925286766559;
+    auto ph = [&](int j) { j = ((j % L) + L) % L; return mkC(std::cos(tau * j / L), std::sin(tau * j / L)); };
+    std::vector<C> Rh((size_t)nw * NP), X((size_t)nF2 * NP, zeroC()), Z((size_t)nF2 * NP, zeroC());
+    for (int iw = 0; iw < nw; ++iw) for (int kap = 0; kap < NP; ++kap) {
+        C s = zeroC();
+        for (int q = 0; q < NP; ++q) s += Rs[iw + (size_t)nw * q] * ph(-((kap % L) * (q % L) + (kap / L) * (q / L)));
+        Rh[iw + (size_t)nw * kap] = s;
+    }
+    const int Px = iP % L, Py = iP / L;
+    for (int f = 0; f < FM::n; ++f) for (int l = job.lev_first; l < conv_level_end<KIND>(job); ++l) {
+        if (!conv_level_on<KIND>(job, l)) continue;
+        const DevLevel& lv = V.lev[l];
+        const int nB1 = 2 * lv.nK1 - 1;
+        for (int r = 0; r < 3; ++r) {
+            if (r == FM::ch(f)) continue;
+            std::vector<C> Kh((size_t)nB1 * NP);
+            for (int i = 0; i < nB1; ++i) for (int kap = 0; kap < NP; ++kap) {
+                C s = zeroC();
+                for (int P = 0; P < NP; ++P) s += lv.ch[r].K1[i + nB1 * P] * ph(-((kap % L) * (P % L) + (kap / L) * (P / L)));
+                Kh[kap + (size_t)NP * i] = s;
+            }
+            for (int inu = 0; inu < nF2; ++inu) for (int ko = 0; ko < NP; ++ko) {
+                const ConvPiece pc = conv_piece<KIND, CH>(FM::ch(f), r, W, inu - g.nK2f, Px, Py);
+                const int kx = fold1(pc.sk * (ko % L), L), ky = fold1(pc.sk * (ko / L), L);
+                const int rx = fold1(-pc.sq * kx, L), ry = fold1(-pc.sq * ky, L);
+                C s = zeroC();
+                for (int iw = 0; iw < nw; ++iw) {
+                    const int Wc = pc.W0 + pc.sW * (iw - Nin);
+                    if (inB(Wc, lv.nK1)) s += Kh[kx + L * ky + (size_t)NP * posB(Wc, lv.nK1)] * Rh[iw + (size_t)nw * (rx + L * ry)];
+                }
+                Z[ko + (size_t)NP * inu] += s * ph(kx * pc.cx + ky * pc.cy) * FM::coef(f);
+            }
+        }
+    }
+    for (int inu = 0; inu < nF2; ++inu) for (int k = 0; k < NP; ++k) {
+        C s = zeroC();
+        for (int ko = 0; ko < NP; ++ko) s += Z[ko + (size_t)NP * inu] * ph((ko % L) * (k % L) + (ko / L) * (k / L));
+        X[k + (size_t)NP * inu] = s * (1.0 / NP);
+    }
+    return X;
+}
+
 template <int KIND, int CH>
 static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_only, int Nin) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
@@ -36,7 +83,7 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
     const bool is_sde = (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH);
     const int slabN = is_sde ? g.nPiB : g.nK2b, nBs = 2 * slabN - 1;     // (the K2 jobs are tested with W on the K2 mesh)
     ColJob job; job.lev_first = lev_first; job.n_nl2 = 0; while (job.n_nl2 < V.nlev && V.lev[job.n_nl2].type == LV_NL2) job.n_nl2++;
-    job.own_only = own_only; job.nw = nw; job.Ninner = Nin; job.slabW_N = slabN; job.scale_re = 1.0; job.scale_im = 0.0;
+    job.own_only = own_only; job.nw = nw; job.Ninner = Nin; job.slabW_N = slabN; job.scale_re = 1.0; job.scale_im = 0.0; job.k1_direct = 0;
     const C* R = rnd_array((size_t)nw * NP * nBs * NP);
 #ifdef DEVICE_CHECK
     C* Tm; cudaMallocManaged(&Tm, (size_t)nw * nF2 * nB2 * sizeof(C));
@@ -83,6 +130,44 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
         {   // hoisted own-channel / local-level pieces (slab_own_kernel + column epilogue)
             const int Wv = iW - (g.nK2b - 1);
             const C* Rs = R + (size_t)nw * NP * (posB(Wv, slabN) + (size_t)nBs * iP);
+            if (KIND != JOB_LK2_LOC) {   // cross-channel K1 pieces: term by term, and through the momentum convolution
+                std::vector<C> X = conv_host<KIND, CH>(V, job, g, Rs, Wv, iP);
+#ifdef DEVICE_CHECK
+                {   // slab_conv_kernel (and k1_dft_kernel) on the device against the host restatement, two tile sizes
+                    DevChain Vd = V;
+                    C* tw; cudaMallocManaged(&tw, L * sizeof(C));
+                    for (int j = 0; j < L; ++j) tw[j] = mkC(std::cos(6.283185307179586 * j / L), std::sin(6.283185307179586 * j / L));
+                    for (int l = 0; l < job.n_nl2; ++l) {
+                        K1hOut o; const int nB1 = 2 * V.lev[l].nK1 - 1;
+                        for (int r = 0; r < 3; ++r) { cudaMallocManaged(&o.p[r], (size_t)nB1 * NP * sizeof(C)); Vd.lev[l].ch[r].K1h = o.p[r]; }
+                        k1_dft_kernel<<<dim3(nB1, 3), std::min(NP, 256), (size_t)(NP + L) * sizeof(C)>>>(V.lev[l], L, NP, tw, o);
+                    }
+                    int2* sl; cudaMallocManaged(&sl, sizeof(int2)); sl[0].x = iW; sl[0].y = iP;
+                    C* tab; cudaMallocManaged(&tab, (size_t)NP * nF2 * nB2 * NP * sizeof(C));
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const int TW = pass == 0 ? std::max(nw, nF2) : nF2;
+                        const size_t bytes = ((size_t)2 * NP * (TW | 1) + (size_t)nF2 * NP + L) * sizeof(C);
+                        cudaFuncSetAttribute(slab_conv_kernel<KIND, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+                        slab_conv_kernel<KIND, CH><<<1, 512, bytes>>>(Vd, job, sl, R, tw, tab, g, TW);
+                        cudaError_t e = cudaDeviceSynchronize();
+                        if (e != cudaSuccess) { printf("CUDA error (slab_conv) %s\n", cudaGetErrorString(e)); exit(2); }
+                        for (int inu2 = 0; inu2 < nF2; ++inu2) for (int k2 = 0; k2 < NP; ++k2) {
+                            C dv = tab[k2 + (size_t)NP * (inu2 + nF2 * (iW + (size_t)nB2 * iP))], hv = X[k2 + (size_t)NP * inu2];
+                            double d = std::max(std::fabs(dv.x - hv.x), std::fabs(dv.y - hv.y));
+                            if (d > 1e-10) printf("    DEVICE CONV != HOST pass %d inu %d k %d: dev (%g,%g) host (%g,%g)\n", pass, inu2, k2, dv.x, dv.y, hv.x, hv.y);
+                            maxdev = std::max(maxdev, d);
+                        }
+                    }
+                }
+#endif
+                for (int n = 0; n < nrep; ++n) {
+                    C d = k1_cross_direct<KIND, CH>(V, job, g, Rs, Wv, iP, ik, inu[n] - g.nK2f);
+                    C x = X[ik + (size_t)NP * inu[n]];
+                    double e = std::max(std::fabs(d.x - x.x), std::fabs(d.y - x.y));
+                    if (e > 1e-11) { printf("    CONV != DIRECT trial %d rep %d: conv (%g,%g) direct (%g,%g)\n", trial, n, x.x, x.y, d.x, d.y); maxerr = std::max(maxerr, e); }
+                    got[n] += x;
+                }
+            }
             C rtot = zeroC(); for (int i = 0; i < nw * NP; ++i) rtot += Rs[i];
             for (int n = 0; n < nrep; ++n)
                 if (KIND != JOB_LK2 && KIND != JOB_LK2_LOC)

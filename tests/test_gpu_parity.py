@@ -282,3 +282,26 @@ def test_column_kernels_match_generic_kernels(orc, sym):
         S.close()
     for a, b in zip(*res):
         assert rel(a, b) < TOL
+
+
+@pytest.mark.parametrize("opt", ["direct_k1", "serial"])
+def test_convolution_and_lanes_match_plain_path(orc, opt):
+    """A/B on the device: (a) cross-channel K1 terms through the per-slab momentum convolution (slab_conv_kernel) vs summed
+    term by term in the column kernels (FDGA_OPT_DIRECT_K1); (b) concurrent lanes vs everything on one stream (FDGA_OPT_SERIAL)"""
+    import fddgasolver_jl_b200 as fd
+    res = []
+    for value in (0, 1):
+        S, _ = make_pair(orc, nmax=3, nq=4, LG=8, sym=True)
+        S.set_option(opt, value)
+        for _ in range(2):
+            fd.iterate_solver(S, "fdPA", True)
+        A = fd.mfRGLinearMap(S)
+        y = A.matvec(S.F.flatten())
+        S.pull("F", "Σ", "FL")
+        res.append((S.F.flatten(), S.FL.flatten(), S.Σ.copy(), y))
+        S.close()
+    for a, b in zip(*res):
+        if opt == "serial":
+            assert np.array_equal(a, b)
+        else:
+            assert rel(a, b) < TOL
