@@ -31,6 +31,8 @@ struct ColDev {                 // columns of class representatives, built on th
     const int* start;           // ncol + 1
     const int* rep_inu;         // position of nu in the K2 fermionic mesh
     const int* rep_cls;         // class id (slot in repvals)
+    int ngrp;                   // groups of <= FDGA_WGROUP consecutive columns sharing (P, k): one CTA each
+    const int* grp_start;       // ngrp + 1 (column index)
 };
 
 struct ColJob {
@@ -345,7 +347,7 @@ FDGA_HD C slab_own_entry(const DevChain& V, const ColJob& job, const Grid& g, co
 // one CTA per active slab (W on the K2 mesh, P): OwnTab[nu | W, P] and Rtot[W, P]
 template <int KIND, int CH>
 __global__ void __launch_bounds__(256)
-slab_own_kernel(const __grid_constant__ DevChain V, ColJob job, const int2* __restrict__ slabs, const C* __restrict__ R,
+slab_own_kernel(const __grid_constant__ DevChain V, ColJob job, const int4* __restrict__ slabs, const C* __restrict__ R,
                 const C* __restrict__ T, C* __restrict__ OwnTab, C* __restrict__ Rtot, Grid g, int PC) {
     extern __shared__ double sm_raw[];
     C* Rq = reinterpret_cast<C*>(sm_raw);                 // [nw], then part[nF2 * nw]
@@ -480,12 +482,18 @@ __global__ void k1_dft_kernel(DevLevel lv, int L, int NP, const C* __restrict__ 
     }
 }
 
+// per-CTA piece table: conv_piece at nu = 0 plus its slope in nu (W0 is linear in nu), level / channel / weight
+struct ConvPieceS { int W0, dW0, sW, cx, cy, sk, sq, lev, r, nK1; double cf; };
+#define FDGA_CONV_MAXP 24     // 2 forms x 6 levels x 2 cross channels
 template <int KIND, int CH>
-__global__ void __launch_bounds__(512)
-slab_conv_kernel(const __grid_constant__ DevChain V, ColJob job, const int2* __restrict__ slabs, const C* __restrict__ R,
+__global__ void __launch_bounds__(256)
+slab_conv_kernel(const __grid_constant__ DevChain V, ColJob job, const int4* __restrict__ slabs, const C* __restrict__ R,
                  const C* __restrict__ tw, C* __restrict__ ConvTab, Grid g, int TW) {
     typedef Forms<KIND, CH> FM;
     extern __shared__ double sm_raw[];
+    __shared__ ConvPieceS pcs[FDGA_CONV_MAXP];
+    __shared__ int s_npc, s_cnt;
+    __shared__ unsigned char nuList[64];
     const int L = g.L, NP = g.NP, nF2 = 2 * g.nK2f, nB2 = 2 * g.nK2b - 1, nw = job.nw, Nin = job.Ninner;
     const int TWp = TW | 1;                               // odd row stride: conflict-free column gathers
     C* A = reinterpret_cast<C*>(sm_raw);                  // [NP][TWp]
@@ -493,109 +501,162 @@ slab_conv_kernel(const __grid_constant__ DevChain V, ColJob job, const int2* __r
     C* Z = B + (size_t)NP * TWp;                          // [nF2][NP]
     C* stw = Z + (size_t)nF2 * NP;                        // [L]  exp(+2 pi i j / L)
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int iW = slabs[blockIdx.x].x, iP = slabs[blockIdx.x].y;
+    const int4 sl = slabs[blockIdx.x];
+    const int iW = sl.x, iP = sl.y;
     const int W = iW - (g.nK2b - 1), Px = iP % L, Py = iP / L;
     const C* Rs = R + (size_t)nw * NP * (posB(W, job.slabW_N) + (size_t)(2 * job.slabW_N - 1) * iP);
     for (int j = tid; j < L; j += nthr) stw[j] = tw[j];
-    for (int o = tid; o < nF2 * NP; o += nthr) Z[o] = zeroC();
-    const int l_end = conv_level_end<KIND>(job);
+    if (tid < FDGA_CONV_MAXP) {        // piece table, one thread per (form, level, cross channel) slot
+        const int nl = conv_level_end<KIND>(job) - job.lev_first;
+        const int rr = tid & 1, fl = tid >> 1, f = nl > 0 ? fl / nl : FM::n, l = job.lev_first + (nl > 0 ? fl % nl : 0);
+        ConvPieceS q; q.cf = 0.0; q.lev = -1;
+        if (f < FM::n && conv_level_on<KIND>(job, l)) {
+            const int form = FM::ch(f);
+            const int r = (form == 0) ? 1 + rr : (form == 1 ? 2 * rr : rr);      // the two channels != form
+            const ConvPiece p0 = conv_piece<KIND, CH>(form, r, W, 0, Px, Py), p1 = conv_piece<KIND, CH>(form, r, W, 1, Px, Py);
+            q.W0 = p0.W0; q.dW0 = p1.W0 - p0.W0; q.sW = p0.sW; q.cx = fold1(p0.cx, L); q.cy = fold1(p0.cy, L);
+            q.sk = p0.sk; q.sq = p0.sq; q.lev = l; q.r = r; q.nK1 = V.lev[l].nK1; q.cf = FM::coef(f);
+        }
+        pcs[tid] = q;
+    }
+    if (tid == 32) {
+        // nu values some column of this slab needs (bit mask built on the host; more than 64 values: all of them)
+        int c = 0;
+        const unsigned long long m = ((unsigned long long)(unsigned)sl.w << 32) | (unsigned)sl.z;
+        if (nF2 <= 64) { for (int i = 0; i < nF2; ++i) if ((m >> i) & 1ULL) nuList[c++] = (unsigned char)i; }
+        s_cnt = (nF2 <= 64) ? c : nF2;
+        s_npc = min(FDGA_CONV_MAXP, 2 * FM::n * max(0, conv_level_end<KIND>(job) - job.lev_first));
+    }
+    __syncthreads();
+    const int npc = s_npc, cnt = s_cnt;
+    for (int o = tid; o < cnt * NP; o += nthr) Z[o] = zeroC();
 
     for (int t0 = 0; t0 < nw; t0 += TW) {
         const int tn = min(TW, nw - t0);
         __syncthreads();
-        for (int e = tid; e < tn * NP; e += nthr) { const int j = e % tn, q = e / tn; A[q * TWp + j] = Rs[t0 + j + (size_t)nw * q]; }
+        for (int e = tid; e < tn * NP; e += nthr) { const int q = e / tn, j = e - q * tn; A[q * TWp + j] = Rs[t0 + j + (size_t)nw * q]; }
         __syncthreads();
         for (int e = tid; e < tn * NP; e += nthr) {       // x axis
-            const int j = e % tn, kq = e / tn, kx = kq % L, qy = kq / L;
-            C s = zeroC();
-            for (int qx = 0; qx < L; ++qx) s += A[(qx + L * qy) * TWp + j] * conjC(stw[(kx * qx) % L]);
-            B[kq * TWp + j] = s;
+            const int kq = e / tn, j = e - kq * tn, qy = kq / L, kx = kq - qy * L;
+            const C* a = A + (size_t)(L * qy) * TWp + j;
+            C s0 = zeroC(), s1 = zeroC();
+            int ph = 0;
+            for (int qx = 0; qx < L; qx += 2) {
+                s0 += a[qx * TWp] * conjC(stw[ph]); ph += kx; ph -= (ph >= L) ? L : 0;
+                if (qx + 1 < L) { s1 += a[(qx + 1) * TWp] * conjC(stw[ph]); ph += kx; ph -= (ph >= L) ? L : 0; }
+            }
+            B[kq * TWp + j] = s0 + s1;
         }
         __syncthreads();
         for (int e = tid; e < tn * NP; e += nthr) {       // y axis
-            const int j = e % tn, kq = e / tn, kx = kq % L, ky = kq / L;
-            C s = zeroC();
-            for (int qy = 0; qy < L; ++qy) s += B[(kx + L * qy) * TWp + j] * conjC(stw[(ky * qy) % L]);
-            A[kq * TWp + j] = s;
+            const int kq = e / tn, j = e - kq * tn, ky = kq / L, kx = kq - ky * L;
+            const C* b = B + (size_t)kx * TWp + j;
+            C s0 = zeroC(), s1 = zeroC();
+            int ph = 0;
+            for (int qy = 0; qy < L; qy += 2) {
+                s0 += b[(L * qy) * TWp] * conjC(stw[ph]); ph += ky; ph -= (ph >= L) ? L : 0;
+                if (qy + 1 < L) { s1 += b[(L * (qy + 1)) * TWp] * conjC(stw[ph]); ph += ky; ph -= (ph >= L) ? L : 0; }
+            }
+            A[kq * TWp + j] = s0 + s1;
         }
         __syncthreads();
-        for (int o = tid; o < nF2 * NP; o += nthr) {
-            const int inu = o / NP, ko = o % NP, kox = ko % L, koy = ko / L, nu = inu - g.nK2f;
+        for (int o = tid; o < cnt * NP; o += nthr) {
+            const int in = o / NP, ko = o - in * NP, koy = ko / L, kox = ko - koy * L;
+            const int inu = (nF2 <= 64) ? nuList[in] : in, nu = inu - g.nK2f;
             C z = zeroC();
-#pragma unroll
-            for (int f = 0; f < FM::n; ++f) {
-                const int form = FM::ch(f);
-                for (int l = job.lev_first; l < l_end; ++l) {
-                    if (!conv_level_on<KIND>(job, l)) continue;
-                    const DevLevel& lv = V.lev[l];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        if (r == form) continue;
-                        const ConvPiece pc = conv_piece<KIND, CH>(form, r, W, nu, Px, Py);
-                        const int kx = fold1(pc.sk * kox, L), ky = fold1(pc.sk * koy, L);
-                        const int rx = fold1(-pc.sq * kx, L), ry = fold1(-pc.sq * ky, L);
-                        Lin lW = {pc.W0, pc.sW};
-                        int a = t0 - Nin, b = t0 + tn - 1 - Nin;
-                        clip_interval(lW, -(lv.nK1 - 1), lv.nK1 - 1, a, b);
-                        const C* Kh = lv.ch[r].K1h + (kx + L * ky) + (size_t)NP * posB(pc.W0, lv.nK1);
-                        const C* Ar = A + (size_t)(rx + L * ry) * TWp + (Nin - t0);
-                        const int stepK = NP * pc.sW;
-                        C s0 = zeroC(), s1 = zeroC();
+            for (int p = 0; p < npc; ++p) {
+                const ConvPieceS pc = pcs[p];
+                if (pc.lev < 0) continue;
+                const int kx = (pc.sk > 0 || kox == 0) ? kox : L - kox, ky = (pc.sk > 0 || koy == 0) ? koy : L - koy;
+                const int rx = (pc.sq < 0 || kx == 0) ? kx : L - kx, ry = (pc.sq < 0 || ky == 0) ? ky : L - ky;
+                const int W0 = pc.W0 + pc.dW0 * nu;
+                Lin lW = {W0, pc.sW};
+                int a = t0 - Nin, b = t0 + tn - 1 - Nin;
+                clip_interval(lW, -(pc.nK1 - 1), pc.nK1 - 1, a, b);
+                const C* Kh = V.lev[pc.lev].ch[pc.r].K1h + (kx + L * ky) + (size_t)NP * posB(W0, pc.nK1);
+                const C* Ar = A + (size_t)(rx + L * ry) * TWp + (Nin - t0);
+                const int stepK = NP * pc.sW;
+                C s0 = zeroC(), s1 = zeroC();
 #pragma unroll 4
-                        for (int win = a; win <= b; win += 2) {
-                            const bool two = win + 1 <= b;
-                            const C k0 = ldg(Kh + (ptrdiff_t)stepK * win);
-                            const C k1 = two ? ldg(Kh + (ptrdiff_t)stepK * (win + 1)) : zeroC();
-                            s0 += k0 * Ar[win];
-                            s1 += k1 * Ar[two ? win + 1 : win];
-                        }
-                        const int ph = (kx * fold1(pc.cx, L) + ky * fold1(pc.cy, L)) % L;
-                        z += (s0 + s1) * stw[ph] * FM::coef(f);
-                    }
+                for (int win = a; win <= b; win += 2) {
+                    const bool two = win + 1 <= b;
+                    const C k0 = ldg(Kh + (ptrdiff_t)stepK * win);
+                    const C k1 = two ? ldg(Kh + (ptrdiff_t)stepK * (win + 1)) : zeroC();
+                    s0 += k0 * Ar[win];
+                    s1 += k1 * Ar[two ? win + 1 : win];
                 }
+                const int ph = (kx * pc.cx + ky * pc.cy) % L;
+                z += (s0 + s1) * stw[ph] * pc.cf;
             }
             Z[o] += z;
         }
     }
     __syncthreads();
-    for (int e = tid; e < nF2 * NP; e += nthr) {          // back transform, x axis
-        const int inu = e / NP, kq = e % NP, kx = kq % L, ky = kq / L;
-        C s = zeroC();
-        for (int x = 0; x < L; ++x) s += Z[inu * NP + x + L * ky] * stw[(kx * x) % L];
-        A[e] = s;
+    for (int e = tid; e < cnt * NP; e += nthr) {          // back transform, x axis
+        const int in = e / NP, kq = e - in * NP, ky = kq / L, kx = kq - ky * L;
+        const C* zr = Z + (size_t)in * NP + L * ky;
+        C s0 = zeroC(), s1 = zeroC();
+        int ph = 0;
+        for (int x = 0; x < L; x += 2) {
+            s0 += zr[x] * stw[ph]; ph += kx; ph -= (ph >= L) ? L : 0;
+            if (x + 1 < L) { s1 += zr[x + 1] * stw[ph]; ph += kx; ph -= (ph >= L) ? L : 0; }
+        }
+        A[e] = s0 + s1;
     }
     __syncthreads();
     const double inv = 1.0 / (double)NP;
-    for (int e = tid; e < nF2 * NP; e += nthr) {          // y axis
-        const int inu = e / NP, kq = e % NP, kx = kq % L, ky = kq / L;
-        C s = zeroC();
-        for (int y = 0; y < L; ++y) s += A[inu * NP + kx + L * y] * stw[(ky * y) % L];
-        ConvTab[kq + (size_t)NP * (inu + nF2 * (iW + (size_t)nB2 * iP))] = s * inv;
+    for (int e = tid; e < cnt * NP; e += nthr) {          // y axis
+        const int in = e / NP, kq = e - in * NP, ky = kq / L, kx = kq - ky * L;
+        const int inu = (nF2 <= 64) ? nuList[in] : in;
+        const C* ar = A + (size_t)in * NP + kx;
+        C s0 = zeroC(), s1 = zeroC();
+        int ph = 0;
+        for (int y = 0; y < L; y += 2) {
+            s0 += ar[L * y] * stw[ph]; ph += ky; ph -= (ph >= L) ? L : 0;
+            if (y + 1 < L) { s1 += ar[L * (y + 1)] * stw[ph]; ph += ky; ph -= (ph >= L) ? L : 0; }
+        }
+        ConvTab[kq + (size_t)NP * (inu + nF2 * (iW + (size_t)nB2 * iP))] = (s0 + s1) * inv;
     }
 }
 
 // ---- the column kernel -----------------------------------------------------------------------------------------
-// thread <-> (representative nu, inner momentum slot): lanes with consecutive nu gather neighbouring table entries,
-// the R slab element is a warp broadcast, and every thread carries a single accumulator.
-// per-thread part (host-callable for CPU unit tests): contribution of thread `tid` of `nthreads` to column `col`
+// One CTA per GROUP of up to FDGA_WGROUP columns that share (P, k) and differ in W.  thread <-> (representative nu, inner
+// momentum slot): the momentum conversions / table base offsets of a (k, q) pair are computed once and reused for every
+// W of the group, and the table blocks fetched for one W are still in L1 when the next W gathers from them.  Lanes with
+// consecutive nu gather neighbouring table entries; the R slab element is a broadcast inside a q-slot.
+// per-thread part (host-callable for CPU unit tests): contribution of thread `tid` of `nthreads` to the columns of group `grp`
+#ifndef FDGA_WGROUP
+#define FDGA_WGROUP 1
+#endif
 template <int KIND, int CH>
-FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols, const C* __restrict__ R,
-                        const Grid& g, int col, int tid, int nthreads) {
+FDGA_HD void column_thread(const DevChain& V, const ColJob& job, const ColDev& cols, const C* __restrict__ R,
+                           const Grid& g, int grp, int tid, int nthreads, C* __restrict__ acc /* [FDGA_WGROUP] */) {
     typedef Forms<KIND, CH> FM;
-    const int iW = cols.iW[col], iP = cols.iP[col], ik = cols.ik[col];
-    const int r0 = cols.start[col], nrep = cols.start[col + 1] - r0;
-    const int W = iW - (g.nK2b - 1);
+    const int c0 = cols.grp_start[grp], ng = cols.grp_start[grp + 1] - c0;
+    const int iP = cols.iP[c0], ik = cols.ik[c0];
     const int L = g.L, NP = g.NP;
     const int Px = iP % L, Py = iP / L, kx = ik % L, ky = ik / L;
     const int nw = job.nw;
+    int maxrep = 1;
+    for (int i = 0; i < ng; ++i) maxrep = max(maxrep, cols.start[c0 + i + 1] - cols.start[c0 + i]);
     int NVc = 1;
-    while (NVc < nrep) NVc <<= 1;                         // 1, 2, 4, 8 (<= FDGA_NV)
+    while (NVc < maxrep) NVc <<= 1;                       // 1, 2, 4, 8 (<= FDGA_NV)
     const int n = tid & (NVc - 1);
     const int qs = tid / NVc, nqs = nthreads / NVc;
-    const bool active = n < nrep;
-    const int nu = active ? cols.rep_inu[r0 + n] - g.nK2f : 0;
-    const C* slab = R + (size_t)nw * NP * (posB(W, job.slabW_N) + (size_t)(2 * job.slabW_N - 1) * iP);
-    C acc = zeroC();
+    int Wg[FDGA_WGROUP], nug[FDGA_WGROUP]; bool actg[FDGA_WGROUP]; bool any = false;
+#pragma unroll
+    for (int i = 0; i < FDGA_WGROUP; ++i) {
+        acc[i] = zeroC(); Wg[i] = 0; nug[i] = 0; actg[i] = false;
+        if (i < ng) {
+            const int r0 = cols.start[c0 + i];
+            Wg[i] = cols.iW[c0 + i] - (g.nK2b - 1);
+            actg[i] = n < cols.start[c0 + i + 1] - r0;
+            nug[i] = actg[i] ? cols.rep_inu[r0 + n] - g.nK2f : 0;
+            any = any || actg[i];
+        }
+    }
+    const size_t slab_stride = (size_t)nw * NP;
+    const C* Rp = R + slab_stride * (size_t)(2 * job.slabW_N - 1) * iP;
 
     // w is split in WS chunks so that small momentum meshes still fill the CTA
     int WS = 1;
@@ -605,7 +666,7 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
     const int l_end = (KIND == JOB_LK2 || KIND == JOB_LK2_LOC) ? l0 + 1 : job.n_nl2;
     const bool withK1 = (KIND == JOB_LK2_LOC) || job.k1_direct;   // otherwise the K1 pieces come from slab_conv_kernel
 
-    if (active)
+    if (any)
     for (int item = qs; item < NP * WS; item += nqs) {
         const int iq = item / WS, ws = item - iq * WS;
         const int qx = iq % L, qy = iq / L;
@@ -613,7 +674,6 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
         // momentum arguments of the vertex for this (k, q)
         int akx, aky, aqx, aqy;
         job_mom_args<KIND, CH>(Px, Py, kx, ky, qx, qy, akx, aky, aqx, aqy);
-        const C* Rq = slab + (size_t)nw * iq;
         const C rs_chunk = zeroC();                             // cross-channel arguments are never constant in win
 
 #pragma unroll
@@ -627,27 +687,25 @@ FDGA_HD C column_thread(const DevChain& V, const ColJob& job, const ColDev& cols
             for (int l = l0; l < l_end; ++l) {
                 if ((KIND == JOB_SDE_PP || KIND == JOB_SDE_PH) && (job.own_only || l == l0)) continue;
                 const DevLevel& lv = V.lev[l];
-                MomOff mo[3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) mo[r] = mom_offsets(lv, form, r, L, NP, Px, Py, akx, aky, aqx, aqy);
-                // vertex frequency arguments are linear in win: v(win), w(win)
-                int v_a, w_a, v_b, w_b;
-                job_freq_args<KIND, CH>(W, nu, 0, v_a, w_a); job_freq_args<KIND, CH>(W, nu, 1, v_b, w_b);
-                C part = zeroC();
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     if (r == form) continue;
-                    int W0, v0, w0, W1, v1, w1;
-                    convert_freq(W, v_a, w_a, form, r, W0, v0, w0); convert_freq(W, v_b, w_b, form, r, W1, v1, w1);
-                    Lin lW = {W0, W1 - W0}, lv2 = {v0, v1 - v0}, lw2 = {w0, w1 - w0};
-                    part += chan_lin_sum(lv, r, mo[r], lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi, rs_chunk, withK1);
+                    const MomOff mo = mom_offsets(lv, form, r, L, NP, Px, Py, akx, aky, aqx, aqy);
+#pragma unroll
+                    for (int i = 0; i < FDGA_WGROUP; ++i) {
+                        if (!actg[i]) continue;
+                        // vertex frequency arguments are linear in win: v(win), w(win)
+                        int v_a, w_a, v_b, w_b, W0, v0, w0, W1, v1, w1;
+                        job_freq_args<KIND, CH>(Wg[i], nug[i], 0, v_a, w_a); job_freq_args<KIND, CH>(Wg[i], nug[i], 1, v_b, w_b);
+                        convert_freq(Wg[i], v_a, w_a, form, r, W0, v0, w0); convert_freq(Wg[i], v_b, w_b, form, r, W1, v1, w1);
+                        Lin lW = {W0, W1 - W0}, lv2 = {v0, v1 - v0}, lw2 = {w0, w1 - w0};
+                        const C* Rq = Rp + slab_stride * posB(Wg[i], job.slabW_N) + (size_t)nw * iq;
+                        acc[i] += chan_lin_sum(lv, r, mo, lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi, rs_chunk, withK1) * cf;
+                    }
                 }
-                acc += part * cf;
             }
         }
     }
-
-    return acc;
 }
 
 #ifndef FDGA_COL_MINB
@@ -658,20 +716,27 @@ __global__ void __launch_bounds__(128, FDGA_COL_MINB)
 column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const C* __restrict__ R,
               const C* __restrict__ OwnTab, const C* __restrict__ Rtot, const C* __restrict__ ConvTab,
               C* __restrict__ repvals, Grid g) {
-    const int col = blockIdx.x;
-    const int r0 = cols.start[col], nrep = cols.start[col + 1] - r0;
+    const int grp = blockIdx.x;
+    const int c0 = cols.grp_start[grp], ng = cols.grp_start[grp + 1] - c0;
+    int maxrep = 1;
+    for (int i = 0; i < ng; ++i) maxrep = max(maxrep, cols.start[c0 + i + 1] - cols.start[c0 + i]);
     int NVc = 1;
-    while (NVc < nrep) NVc <<= 1;
-    const C acc = column_thread<KIND, CH>(V, job, cols, R, g, col, threadIdx.x, blockDim.x);
-    // reduction over the momentum slots of each representative
-    __shared__ double redx[128], redy[128];
-    redx[threadIdx.x] = acc.x; redy[threadIdx.x] = acc.y;
+    while (NVc < maxrep) NVc <<= 1;
+    C acc[FDGA_WGROUP];
+    column_thread<KIND, CH>(V, job, cols, R, g, grp, threadIdx.x, blockDim.x, acc);
+    // reduction over the momentum slots of each representative, one column of the group at a time
+    __shared__ double redx[FDGA_WGROUP][128], redy[FDGA_WGROUP][128];
+#pragma unroll
+    for (int i = 0; i < FDGA_WGROUP; ++i) { redx[i][threadIdx.x] = acc[i].x; redy[i][threadIdx.x] = acc[i].y; }
     __syncthreads();
-    if (threadIdx.x < nrep) {
+    for (int t = threadIdx.x; t < ng * NVc; t += blockDim.x) {
+        const int i = t / NVc, nn = t - i * NVc, col = c0 + i;
+        const int r0 = cols.start[col], nrep = cols.start[col + 1] - r0;
+        if (nn >= nrep) continue;
         double x = 0.0, y = 0.0;
-        for (int i = threadIdx.x; i < (int)blockDim.x; i += NVc) { x += redx[i]; y += redy[i]; }
+        for (int j = nn; j < (int)blockDim.x; j += NVc) { x += redx[i][j]; y += redy[i][j]; }
         C val = mkC(x, y);
-        const int iW = cols.iW[col], iP = cols.iP[col], ik = cols.ik[col], inu = cols.rep_inu[r0 + threadIdx.x];
+        const int iW = cols.iW[col], iP = cols.iP[col], ik = cols.ik[col], inu = cols.rep_inu[r0 + nn];
         const int nF2 = 2 * g.nK2f, nB2 = 2 * g.nK2b - 1;
         if (ConvTab != nullptr)       // cross-channel K1 pieces (momentum convolution per slab)
             val += ConvTab[ik + (size_t)g.NP * (inu + nF2 * (iW + (size_t)nB2 * iP))];
@@ -680,7 +745,7 @@ column_kernel(const __grid_constant__ DevChain V, ColJob job, ColDev cols, const
                  + own_B_term<KIND, CH>(V, job, g, iW - (g.nK2b - 1), iP, ik, inu - g.nK2f) * Rtot[iW + nB2 * iP];
         }
         C s = mkC(job.scale_re, job.scale_im);
-        repvals[cols.rep_cls[r0 + threadIdx.x]] = val * s;
+        repvals[cols.rep_cls[r0 + nn]] = val * s;
     }
 }
 

@@ -173,7 +173,7 @@ enum { RK_FD = 0, RK_MF_K1 = 1, RK_MF_K2 = 2, RK_LK2 = 3, RK_LK2_LOC = 4 };
 template <int CH, int KIND>
 __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ DevChain FL,
                                     const C* __restrict__ Pi0T, const C* __restrict__ PiT, C* __restrict__ Rt,
-                                    Grid g, int No, int Ninner, const int2* __restrict__ slabs, int nslabs) {
+                                    Grid g, int No, int Ninner, const int4* __restrict__ slabs, int nslabs) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
     const int nw = 2 * Ninner, nBo = 2 * No - 1, nFP = 2 * g.nPiF, nBP = 2 * g.nPiB - 1;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -181,7 +181,7 @@ __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const _
     if (i >= n) return;
     long long t = i;
     int iw = t % nw; t /= nw; int iq = t % g.NP; int sl = (int)(t / g.NP);
-    const int2 s2 = slabs[sl];
+    const int4 s2 = slabs[sl];
     const int iWo = s2.x, iP = s2.y;
     int W = iWo - (No - 1), w = iw - Ninner;
     int Px = iP % g.L, Py = iP / g.L, qx = iq % g.L, qy = iq / g.L;

@@ -43,10 +43,10 @@ struct SymGroup {
     long long chunk;
     std::vector<long long> h_offsets, h_index;
     // columns (W, P, k) of this rank's class representatives (K2-shaped groups only)
-    int ncol; int *d_col_iW, *d_col_iP, *d_col_ik, *d_col_start, *d_rep_inu, *d_rep_cls;
+    int ncol; int *d_col_iW, *d_col_iP, *d_col_ik, *d_col_start, *d_rep_inu, *d_rep_cls; int ngrp; int* d_grp_start;
 };
 struct TimedEvent { cudaEvent_t a, b; int cat; };
-struct Pending { SymGroup* s; C* rep; C* out; int kind, ch; };
+struct Pending { SymGroup* s; C* rep; C* out; int kind, ch; bool expanded; };
 enum { PK_K1 = 0, PK_LK2 = 1, PK_K2 = 2, PK_LK3 = 3, PK_K3 = 4 };
 
 // NCCL through dlopen (no link-time dependency; the process may already hold torch's libnccl)
@@ -105,7 +105,7 @@ struct fdga_ctx {
     // pieces (W on the K2 mesh); ConvTabL[k, nu | W, P] = cross-channel K1 pieces (slab_conv_kernel)
     C* twL; C* twLG;         // DFT twiddles exp(2 pi i j / n) for n = L, LG
     LevelBuf Fsum; bool has_fsum, fsum_dirty;   // K tables of lev[0] + lev[1] when both are NL2 on identical meshes
-    int2* d_slabs[4]; int n_slabs[4]; bool slabs_dirty;   // active (W,P) slabs: [pp|ph] x [bubble mesh | K2 mesh]
+    int4* d_slabs[4]; int n_slabs[4]; bool slabs_dirty;   // active (W,P) slabs: [pp|ph] x [bubble mesh | K2 mesh]
     C* Rt3[3]; int rt_kind[3]; // per-channel right factors (W on the bubble mesh) reused between BSE_K1! and BSE_K2!
     std::string err;
 };
@@ -341,8 +341,8 @@ static int dft4(fdga_ctx* ctx, C* a, C* b, long long pre, int sgn, double scale,
 
 // group this rank's class representatives of a K2-shaped symmetry group into columns (W, P, k) of <= FDGA_NV reps
 static int build_columns(fdga_ctx* ctx, SymGroup& s) {
-    cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls);
-    s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = nullptr; s.ncol = 0;
+    cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); cudaFree(s.d_grp_start);
+    s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = s.d_grp_start = nullptr; s.ncol = 0; s.ngrp = 0;
     long long c0 = (long long)ctx->rank * s.chunk, c1 = c0 + s.chunk;
     if (c0 > s.ncls) c0 = s.ncls; if (c1 > s.ncls) c1 = s.ncls;
     const int nB2 = 2 * ctx->g.nK2b - 1, nF2 = 2 * ctx->g.nK2f, NP = ctx->g.NP;
@@ -368,13 +368,22 @@ static int build_columns(fdga_ctx* ctx, SymGroup& s) {
     for (auto& r : reps) { rinu.push_back(r.inu); rcls.push_back(r.cls); }
     s.ncol = (int)ciW.size();
     if (s.ncol == 0) return 0;
+    // groups of <= FDGA_WGROUP consecutive columns with the same (P, k) (the sort key makes them adjacent)
+    std::vector<int> gstart;
+    for (int c = 0; c < s.ncol;) {
+        int e = c;
+        while (e < s.ncol && e - c < FDGA_WGROUP && ciP[e] == ciP[c] && cik[e] == cik[c]) e++;
+        gstart.push_back(c); c = e;
+    }
+    gstart.push_back(s.ncol);
+    s.ngrp = (int)gstart.size() - 1;
     auto up = [&](int*& d, const std::vector<int>& h) -> int {
         CK(cudaMalloc(&d, h.size() * sizeof(int))); CK(cudaMemcpy(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice)); return 0; };
-    if (up(s.d_col_iW, ciW) || up(s.d_col_iP, ciP) || up(s.d_col_ik, cik) || up(s.d_col_start, cstart) || up(s.d_rep_inu, rinu) || up(s.d_rep_cls, rcls)) return 1;
+    if (up(s.d_col_iW, ciW) || up(s.d_col_iP, ciP) || up(s.d_col_ik, cik) || up(s.d_col_start, cstart) || up(s.d_rep_inu, rinu) || up(s.d_rep_cls, rcls) || up(s.d_grp_start, gstart)) return 1;
     return 0;
 }
 static ColDev col_dev(const SymGroup& s) {
-    ColDev c; c.ncol = s.ncol; c.iW = s.d_col_iW; c.iP = s.d_col_iP; c.ik = s.d_col_ik; c.start = s.d_col_start; c.rep_inu = s.d_rep_inu; c.rep_cls = s.d_rep_cls;
+    ColDev c; c.ncol = s.ncol; c.iW = s.d_col_iW; c.iP = s.d_col_iP; c.ik = s.d_col_ik; c.start = s.d_col_start; c.rep_inu = s.d_rep_inu; c.rep_cls = s.d_rep_cls; c.ngrp = s.ngrp; c.grp_start = s.d_grp_start;
     return c;
 }
 
@@ -388,14 +397,16 @@ static int ensure_slabs(fdga_ctx* ctx) {
         const bool pp = (kind % 2 == 0), bubble_mesh = kind < 2;
         const int nBo = bubble_mesh ? 2 * g.nPiB - 1 : nB2;
         std::vector<unsigned char> mark((size_t)nBo * NP, 0);
+        std::vector<unsigned long long> numask((size_t)nBo * NP, 0ULL);   // nu values of this rank's representatives per slab
         const SymGroup& s2 = ctx->sg[pp ? FDGA_SG_PP2 : FDGA_SG_PH2];
         if (s2.set) {
             long long c0 = std::min((long long)ctx->rank * s2.chunk, s2.ncls), c1 = std::min(c0 + s2.chunk, s2.ncls);
             for (long long c = c0; c < c1; c++) {
                 long long idx = s2.h_index[s2.h_offsets[c]];
-                int iW = idx % nB2; idx /= nB2; idx /= nF2; int iP = idx % NP;
+                int iW = idx % nB2; idx /= nB2; int inu = idx % nF2; idx /= nF2; int iP = idx % NP;
                 int iWo = bubble_mesh ? posB(iW - (g.nK2b - 1), g.nPiB) : iW;
                 mark[iWo + (size_t)nBo * iP] = 1;
+                numask[iWo + (size_t)nBo * iP] |= (nF2 <= 64) ? (1ULL << inu) : ~0ULL;
             }
         }
         const SymGroup& s1 = ctx->sg[FDGA_SG_K1];
@@ -407,12 +418,15 @@ static int ensure_slabs(fdga_ctx* ctx) {
                 mark[posB(iW - (g.nK1 - 1), g.nPiB) + (size_t)nBo * iP] = 1;
             }
         }
-        std::vector<int2> list;
-        for (int iP = 0; iP < NP; iP++) for (int iW = 0; iW < nBo; iW++) if (mark[iW + (size_t)nBo * iP]) list.push_back(make_int2(iW, iP));
+        std::vector<int4> list;     // (iW, iP, nu mask low, nu mask high)
+        for (int iP = 0; iP < NP; iP++) for (int iW = 0; iW < nBo; iW++) if (mark[iW + (size_t)nBo * iP]) {
+            unsigned long long m = numask[iW + (size_t)nBo * iP];
+            list.push_back(make_int4(iW, iP, (int)(unsigned)(m & 0xffffffffULL), (int)(unsigned)(m >> 32)));
+        }
         cudaFree(ctx->d_slabs[kind]); ctx->d_slabs[kind] = nullptr; ctx->n_slabs[kind] = (int)list.size();
         if (!list.empty()) {
-            CK(cudaMalloc(&ctx->d_slabs[kind], list.size() * sizeof(int2)));
-            CK(cudaMemcpy(ctx->d_slabs[kind], list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&ctx->d_slabs[kind], list.size() * sizeof(int4)));
+            CK(cudaMemcpy(ctx->d_slabs[kind], list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice));
         }
     }
     ctx->slabs_dirty = false;
@@ -450,8 +464,13 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_create_error = std::string(#call) + ": " + cudaGetErrorString(e_); delete ctx; return 1; } } while (0)
     CKC(cudaSetDevice(device));
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    ctx->main_stream = ctx->stream; ctx->lane[0] = ctx->stream; ctx->cur_lane = 0; ctx->forked = false; ctx->opt_serial = 0;
-    for (int i = 1; i < 3; i++) CKC(cudaStreamCreateWithFlags(&ctx->lane[i], cudaStreamNonBlocking));
+    ctx->main_stream = ctx->stream; ctx->lane[0] = ctx->stream; ctx->cur_lane = 0; ctx->forked = false;
+    { const char* e = getenv("FDGA_SERIAL"); ctx->opt_serial = (e && e[0] == '1') ? 1 : 0; }     // debugging aid, same as FDGA_OPT_SERIAL
+    {   // lane 1 carries the heaviest jobs (t channel, ph bubble): highest priority so that its CTAs are placed first
+        int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CKC(cudaStreamCreateWithPriority(&ctx->lane[1], cudaStreamNonBlocking, hi));
+        CKC(cudaStreamCreateWithFlags(&ctx->lane[2], cudaStreamNonBlocking));
+    }
     CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < 3; i++) CKC(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
     for (int l = 0; l < ctx->nlev; l++) if (alloc_level(ctx, ctx->lev[l], dims->lev[l])) { g_create_error = ctx->err; delete ctx; return 1; }
@@ -500,7 +519,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
         CKC(cudaMalloc(&ctx->OwnTabL[i], (size_t)(2 * g.nK2f) * (2 * g.nK2b - 1) * g.NP * sizeof(C))); CKC(cudaMalloc(&ctx->RtotL[i], (size_t)(2 * g.nK2b - 1) * g.NP * sizeof(C)));
         CKC(cudaMalloc(&ctx->TtabL[i], (size_t)(2 * g.nPiF) * (2 * g.nK2f) * (2 * g.nK2b - 1) * sizeof(C)));
     }
-    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; s.d_rep[0] = s.d_rep[1] = s.d_rep[2] = nullptr; s.ncol = 0; s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = nullptr; }
+    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; s.d_rep[0] = s.d_rep[1] = s.d_rep[2] = nullptr; s.ncol = 0; s.ngrp = 0; s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = s.d_grp_start = nullptr; }
     CKC(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return 0;
@@ -520,7 +539,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
     cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); for (int i = 0; i < 3; i++) { cudaFree(ctx->TtabL[i]); cudaFree(ctx->OwnTabL[i]); cudaFree(ctx->RtotL[i]); cudaFree(ctx->ConvTabL[i]); if (i) cudaFree(ctx->RtL[i]); } cudaFree(ctx->SigR2); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) cudaFree(ctx->d_slabs[i]);
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); for (int k = 0; k < 3; k++) cudaFree(s.d_rep[k]);
-        cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); }
+        cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); cudaFree(s.d_grp_start); }
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (int i = 1; i < 3; i++) cudaStreamDestroy(ctx->lane[i]);
     cudaEventDestroy(ctx->ev_fork); for (int i = 0; i < 3; i++) cudaEventDestroy(ctx->ev_join[i]);
@@ -823,7 +842,7 @@ static int launch_right(fdga_ctx* ctx, int ch, const DevChain& F0, const DevChai
     Scope sc(ctx, FDGA_T_RIGHT);
     const C* p0 = ctx->PiT[pi_kind(ch, true)]; const C* p1 = ctx->PiT[pi_kind(ch, false)];
     const int kind = (ch == FDGA_PCH ? 0 : 1) + (No == ctx->g.nPiB ? 0 : 2);
-    const int nsl = ctx->n_slabs[kind]; const int2* sl = ctx->d_slabs[kind];
+    const int nsl = ctx->n_slabs[kind]; const int4* sl = ctx->d_slabs[kind];
     long long n = (long long)(2 * Ninner) * ctx->g.NP * nsl;
     if (n == 0) return 0;
     if (ch == FDGA_PCH)      LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_P, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl);
@@ -859,7 +878,7 @@ static int launch_slab_conv(fdga_ctx* ctx, const DevChain& V, ColJob& job, int k
     if (bytes(TW) > budget) { job.k1_direct = 1; return 0; }
     if (refresh_k1h(ctx)) return 1;
     CK(cudaFuncSetAttribute(slab_conv_kernel<KIND, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(TW)));
-    slab_conv_kernel<KIND, CH><<<ctx->n_slabs[kind], 512, bytes(TW), ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->twL, ctx->ConvTabL[ctx->cur_lane], g, TW);
+    slab_conv_kernel<KIND, CH><<<ctx->n_slabs[kind], 256, bytes(TW), ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->twL, ctx->ConvTabL[ctx->cur_lane], g, TW);
     ctx->n_launch[cat]++; ctx->total_launches++;
     *tab = ctx->ConvTabL[ctx->cur_lane];
     return 0;
@@ -882,7 +901,7 @@ static int launch_column_t(fdga_ctx* ctx, const DevChain& V, ColJob job, SymGrou
         own = ctx->OwnTabL[ctx->cur_lane]; rtot = ctx->RtotL[ctx->cur_lane];
     }
     if (launch_slab_conv<KIND, CH>(ctx, V, job, kind, R, cat, &conv)) return 1;
-    if (s.ncol > 0) LAUNCH(cat, (column_kernel<KIND, CH>), (unsigned)s.ncol, 128, V, job, col_dev(s), R, own, rtot, conv, s.d_repvals, ctx->g);
+    if (s.ncol > 0) LAUNCH(cat, (column_kernel<KIND, CH>), (unsigned)s.ngrp, 128, V, job, col_dev(s), R, own, rtot, conv, s.d_repvals, ctx->g);
     CK(cudaGetLastError());
     return 0;
 }
@@ -939,7 +958,16 @@ static int post_fix(fdga_ctx* ctx, int kind, int ch) {
     return 0;
 }
 static int finish_or_defer(fdga_ctx* ctx, SymGroup& s, C* out, int kind, int ch) {
-    if (ctx->defer) { Pending p; p.s = &s; p.rep = s.d_repvals; p.out = out; p.kind = kind; p.ch = ch; ctx->pending.push_back(p); return 0; }
+    if (ctx->defer) {
+        Pending p; p.s = &s; p.rep = s.d_repvals; p.out = out; p.kind = kind; p.ch = ch; p.expanded = false;
+        if (ctx->nranks == 1) {     // nothing to gather: expand right away on this lane, only the post-fix waits for the join
+            Scope sc(ctx, FDGA_T_EXPAND);
+            LAUNCH(FDGA_T_EXPAND, expand_kernel, nblk(s.nmem, 256), 256, out, s.d_repvals, sym_dev(s));
+            CK(cudaGetLastError());
+            p.expanded = true;
+        }
+        ctx->pending.push_back(p); return 0;
+    }
     if (sg_finish(ctx, s, out)) return 1;
     return post_fix(ctx, kind, ch);
 }
@@ -958,8 +986,12 @@ static int flush_pending(fdga_ctx* ctx) {
         ctx->n_launch[FDGA_T_COMM]++;
     }
     std::vector<Pending> todo; todo.swap(ctx->pending);
+    // the post-fixes need the order (kernel class, then p, a, t) whatever order the lanes were issued in
+    std::stable_sort(todo.begin(), todo.end(), [](const Pending& a, const Pending& b) {
+        auto rank = [](int ch) { return ch == FDGA_PCH ? 0 : (ch == FDGA_ACH ? 1 : 2); };
+        return a.kind != b.kind ? a.kind < b.kind : rank(a.ch) < rank(b.ch); });
     for (auto& p : todo) {
-        {
+        if (!p.expanded) {
             Scope sc(ctx, FDGA_T_EXPAND);
             LAUNCH(FDGA_T_EXPAND, expand_kernel, nblk(p.s->nmem, 256), 256, p.out, p.rep, sym_dev(*p.s));
             CK(cudaGetLastError());
@@ -1267,7 +1299,9 @@ int fdga_sde(fdga_ctx* ctx, int strategy, int include_U2, int include_Hartree) {
 // the BSE stages of one iteration: [L_K2, L_K3] | [K1, K2] | [K3].  The three channels of a stage are independent up to
 // their post-fixes: each runs on its own lane, and the stage ends with one batched SG finish (one NCCL group).
 static int bse_stages(fdga_ctx* ctx, bool with_L, int mfrg) {
-    const int order[3] = {FDGA_PCH, FDGA_ACH, FDGA_TCH};      // p, a, t (BSE_templates.jl:35-38 needs a before t)
+    // issue order: the t channel carries two spin forms (twice the work), so it goes first on the high-priority lane;
+    // the post-fixes, which need p, a, t (BSE_templates.jl:35-38: a before t), are ordered by flush_pending
+    const int order[3] = {FDGA_TCH, FDGA_PCH, FDGA_ACH};
     ctx->defer = true;
     int rc = 0;
     if (with_L) {

@@ -19,7 +19,9 @@ static const C* rnd_array(size_t n, double scale = 1.0) {
 }
 template <int KIND, int CH>
 __global__ void dev_run(DevChain V, ColJob job, ColDev cols, const C* R, const C* T, Grid g, C* out) {
-    out[threadIdx.x] = column_thread<KIND, CH>(V, job, cols, R, g, 0, threadIdx.x, blockDim.x);
+    C acc[FDGA_WGROUP];
+    column_thread<KIND, CH>(V, job, cols, R, g, 0, threadIdx.x, blockDim.x, acc);
+    for (int i = 0; i < FDGA_WGROUP; ++i) out[threadIdx.x + blockDim.x * i] = acc[i];
 }
 #else
 static const C* rnd_array(size_t n, double scale = 1.0) {
@@ -88,7 +90,7 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
 #ifdef DEVICE_CHECK
     C* Tm; cudaMallocManaged(&Tm, (size_t)nw * nF2 * nB2 * sizeof(C));
     struct { C* p; size_t n; C* data() { return p; } size_t size() { return n; } C& operator[](size_t i) { return p[i]; } } T = {Tm, (size_t)nw * nF2 * nB2};
-    int* mi; cudaMallocManaged(&mi, 64 * sizeof(int)); C* dout; cudaMallocManaged(&dout, 128 * sizeof(C));
+    int* mi; cudaMallocManaged(&mi, 128 * sizeof(int)); C* dout; cudaMallocManaged(&dout, 128 * FDGA_WGROUP * sizeof(C));
     double maxdev = 0.0;
 #else
     std::vector<C> T((size_t)nw * nF2 * nB2);
@@ -96,44 +98,61 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
     for (size_t i = 0; i < T.size(); ++i) T[i] = (KIND == JOB_LK2 || KIND == JOB_LK2_LOC) ? zeroC() : loc_table_entry<KIND, CH>(V, job, g, (long long)i);
     double maxerr = 0.0, maxval = 0.0;
     for (int trial = 0; trial < 12; ++trial) {
-        int iW = rand() % nB2, iP = rand() % NP, ik = rand() % NP;
-        int nrep = 1 + rand() % std::min(FDGA_NV, nF2);
-        std::vector<int> inu(nrep), cls(nrep);
-        for (int n = 0; n < nrep; ++n) { inu[n] = (n * 3 + trial) % nF2; cls[n] = n; }
-        int start[2] = {0, nrep};
-        ColDev cols; cols.ncol = 1; cols.iW = &iW; cols.iP = &iP; cols.ik = &ik; cols.start = start; cols.rep_inu = inu.data(); cols.rep_cls = cls.data();
-        int NVc = 1; while (NVc < nrep) NVc <<= 1;
-        std::vector<C> got(nrep, zeroC());
+        // one group: ng columns sharing (P, k), distinct W, each with its own representatives
+        const int iP = rand() % NP, ik = rand() % NP;
+        const int ng = 1 + rand() % std::min(FDGA_WGROUP, nB2);
+        std::vector<int> iWv(ng), iPv(ng, iP), ikv(ng, ik), start(ng + 1, 0), inu, cls;
+        {
+            std::vector<int> perm(nB2); for (int i = 0; i < nB2; ++i) perm[i] = i;
+            for (int i = 0; i < ng; ++i) { int j = i + rand() % (nB2 - i); std::swap(perm[i], perm[j]); iWv[i] = perm[i]; }
+        }
+        for (int i = 0; i < ng; ++i) {
+            const int nrep = 1 + rand() % std::min(FDGA_NV, nF2);
+            for (int n = 0; n < nrep; ++n) { inu.push_back((n * 3 + trial + i) % nF2); cls.push_back((int)cls.size()); }
+            start[i + 1] = start[i] + nrep;
+        }
+        int gs[2] = {0, ng};
+        ColDev cols; cols.ncol = ng; cols.iW = iWv.data(); cols.iP = iPv.data(); cols.ik = ikv.data(); cols.start = start.data();
+        cols.rep_inu = inu.data(); cols.rep_cls = cls.data(); cols.ngrp = 1; cols.grp_start = gs;
+        int maxrep = 1; for (int i = 0; i < ng; ++i) maxrep = std::max(maxrep, start[i + 1] - start[i]);
+        int NVc = 1; while (NVc < maxrep) NVc <<= 1;
+        const int ntot = start[ng];
+        std::vector<C> got(ntot, zeroC());
         const int nthreads = 128;
         for (int tid = 0; tid < nthreads; ++tid) {
-            C a = column_thread<KIND, CH>(V, job, cols, R, g, 0, tid, nthreads);
+            C a[FDGA_WGROUP];
+            column_thread<KIND, CH>(V, job, cols, R, g, 0, tid, nthreads, a);
             int n = tid & (NVc - 1);
-            if (n < nrep) got[n] += a;
+            for (int i = 0; i < ng; ++i) if (n < start[i + 1] - start[i]) got[start[i] + n] += a[i];
         }
 #ifdef DEVICE_CHECK
         {   // the same column_thread on the device
-            mi[0] = iW; mi[1] = iP; mi[2] = ik; mi[3] = 0; mi[4] = nrep;
-            for (int n = 0; n < nrep; ++n) { mi[8 + n] = inu[n]; mi[24 + n] = cls[n]; }
-            ColDev dc; dc.ncol = 1; dc.iW = mi; dc.iP = mi + 1; dc.ik = mi + 2; dc.start = mi + 3; dc.rep_inu = mi + 8; dc.rep_cls = mi + 24;
+            for (int i = 0; i < ng; ++i) { mi[i] = iWv[i]; mi[8 + i] = iP; mi[16 + i] = ik; }
+            for (int i = 0; i <= ng; ++i) mi[24 + i] = start[i];
+            for (int n = 0; n < ntot; ++n) { mi[32 + n] = inu[n]; mi[64 + n] = cls[n]; }
+            mi[100] = 0; mi[101] = ng;
+            ColDev dc; dc.ncol = ng; dc.iW = mi; dc.iP = mi + 8; dc.ik = mi + 16; dc.start = mi + 24; dc.rep_inu = mi + 32; dc.rep_cls = mi + 64; dc.ngrp = 1; dc.grp_start = mi + 100;
             dev_run<KIND, CH><<<1, nthreads>>>(V, job, dc, R, (KIND == JOB_LK2) ? nullptr : T.data(), g, dout);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); exit(2); }
-            std::vector<C> dgot(nrep, zeroC());
-            for (int tid = 0; tid < nthreads; ++tid) { int n = tid & (NVc - 1); if (n < nrep) dgot[n] += dout[tid]; }
-            for (int n = 0; n < nrep; ++n) {
+            std::vector<C> dgot(ntot, zeroC());
+            for (int tid = 0; tid < nthreads; ++tid) { int n = tid & (NVc - 1); for (int i = 0; i < ng; ++i) if (n < start[i + 1] - start[i]) dgot[start[i] + n] += dout[tid + nthreads * i]; }
+            for (int n = 0; n < ntot; ++n) {
                 double d = std::max(std::fabs(dgot[n].x - got[n].x), std::fabs(dgot[n].y - got[n].y));
-                if (d > 1e-10) printf("    DEVICE != HOST trial %d rep %d (iW %d iP %d ik %d inu %d nrep %d): dev (%g,%g) host (%g,%g)\n", trial, n, iW, iP, ik, inu[n], nrep, dgot[n].x, dgot[n].y, got[n].x, got[n].y);
+                if (d > 1e-10) printf("    DEVICE != HOST trial %d rep %d (iP %d ik %d ng %d): dev (%g,%g) host (%g,%g)\n", trial, n, iP, ik, ng, dgot[n].x, dgot[n].y, got[n].x, got[n].y);
                 maxdev = std::max(maxdev, d);
             }
         }
 #endif
+        for (int gi = 0; gi < ng; ++gi) {
+        const int iW = iWv[gi], nrep = start[gi + 1] - start[gi], off = start[gi];
         {   // hoisted own-channel / local-level pieces (slab_own_kernel + column epilogue)
             const int Wv = iW - (g.nK2b - 1);
             const C* Rs = R + (size_t)nw * NP * (posB(Wv, slabN) + (size_t)nBs * iP);
             if (KIND != JOB_LK2_LOC) {   // cross-channel K1 pieces: term by term, and through the momentum convolution
                 std::vector<C> X = conv_host<KIND, CH>(V, job, g, Rs, Wv, iP);
 #ifdef DEVICE_CHECK
-                {   // slab_conv_kernel (and k1_dft_kernel) on the device against the host restatement, two tile sizes
+                if (gi == 0) {   // slab_conv_kernel (and k1_dft_kernel) on the device against the host restatement, two tile sizes
                     DevChain Vd = V;
                     C* tw; cudaMallocManaged(&tw, L * sizeof(C));
                     for (int j = 0; j < L; ++j) tw[j] = mkC(std::cos(6.283185307179586 * j / L), std::sin(6.283185307179586 * j / L));
@@ -142,13 +161,13 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
                         for (int r = 0; r < 3; ++r) { cudaMallocManaged(&o.p[r], (size_t)nB1 * NP * sizeof(C)); Vd.lev[l].ch[r].K1h = o.p[r]; }
                         k1_dft_kernel<<<dim3(nB1, 3), std::min(NP, 256), (size_t)(NP + L) * sizeof(C)>>>(V.lev[l], L, NP, tw, o);
                     }
-                    int2* sl; cudaMallocManaged(&sl, sizeof(int2)); sl[0].x = iW; sl[0].y = iP;
+                    int4* sl; cudaMallocManaged(&sl, sizeof(int4)); sl[0].x = iW; sl[0].y = iP; sl[0].z = sl[0].w = -1;
                     C* tab; cudaMallocManaged(&tab, (size_t)NP * nF2 * nB2 * NP * sizeof(C));
                     for (int pass = 0; pass < 2; ++pass) {
                         const int TW = pass == 0 ? std::max(nw, nF2) : nF2;
                         const size_t bytes = ((size_t)2 * NP * (TW | 1) + (size_t)nF2 * NP + L) * sizeof(C);
                         cudaFuncSetAttribute(slab_conv_kernel<KIND, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-                        slab_conv_kernel<KIND, CH><<<1, 512, bytes>>>(Vd, job, sl, R, tw, tab, g, TW);
+                        slab_conv_kernel<KIND, CH><<<1, 256, bytes>>>(Vd, job, sl, R, tw, tab, g, TW);
                         cudaError_t e = cudaDeviceSynchronize();
                         if (e != cudaSuccess) { printf("CUDA error (slab_conv) %s\n", cudaGetErrorString(e)); exit(2); }
                         for (int inu2 = 0; inu2 < nF2; ++inu2) for (int k2 = 0; k2 < NP; ++k2) {
@@ -158,27 +177,28 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
                             maxdev = std::max(maxdev, d);
                         }
                     }
+                    cudaFree(tab); cudaFree(sl); cudaFree(tw);
                 }
 #endif
                 for (int n = 0; n < nrep; ++n) {
-                    C d = k1_cross_direct<KIND, CH>(V, job, g, Rs, Wv, iP, ik, inu[n] - g.nK2f);
-                    C x = X[ik + (size_t)NP * inu[n]];
+                    C d = k1_cross_direct<KIND, CH>(V, job, g, Rs, Wv, iP, ik, inu[off + n] - g.nK2f);
+                    C x = X[ik + (size_t)NP * inu[off + n]];
                     double e = std::max(std::fabs(d.x - x.x), std::fabs(d.y - x.y));
                     if (e > 1e-11) { printf("    CONV != DIRECT trial %d rep %d: conv (%g,%g) direct (%g,%g)\n", trial, n, x.x, x.y, d.x, d.y); maxerr = std::max(maxerr, e); }
-                    got[n] += x;
+                    got[off + n] += x;
                 }
             }
             C rtot = zeroC(); for (int i = 0; i < nw * NP; ++i) rtot += Rs[i];
             for (int n = 0; n < nrep; ++n)
                 if (KIND != JOB_LK2 && KIND != JOB_LK2_LOC)
-                    got[n] += slab_own_entry<KIND, CH>(V, job, g, Rs, T.data(), iW, iP, inu[n])
-                            + own_B_term<KIND, CH>(V, job, g, Wv, iP, ik, inu[n] - g.nK2f) * rtot;
+                    got[off + n] += slab_own_entry<KIND, CH>(V, job, g, Rs, T.data(), iW, iP, inu[off + n])
+                            + own_B_term<KIND, CH>(V, job, g, Wv, iP, ik, inu[off + n] - g.nK2f) * rtot;
         }
         // brute force with the per-term evaluator (the arithmetic of bse_k2_kernel / bse_lk2_kernel / sde_L_kernel)
         const int W = iW - (g.nK2b - 1), Px = iP % L, Py = iP / L, kx = ik % L, ky = ik / L;
         const C* slab = R + (size_t)nw * NP * (posB(W, slabN) + (size_t)nBs * iP);
         for (int n = 0; n < nrep; ++n) {
-            const int nu = inu[n] - g.nK2f;
+            const int nu = inu[off + n] - g.nK2f;
             C ref = zeroC();
             for (int iq = 0; iq < NP; ++iq) for (int iw = 0; iw < nw; ++iw) {
                 const int w = iw - Nin, qx = iq % L, qy = iq / L;
@@ -218,8 +238,9 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
                 }
                 ref += d * slab[iw + (size_t)nw * iq];
             }
-            maxerr = std::max(maxerr, std::max(std::fabs(ref.x - got[n].x), std::fabs(ref.y - got[n].y)));
+            maxerr = std::max(maxerr, std::max(std::fabs(ref.x - got[off + n].x), std::fabs(ref.y - got[off + n].y)));
             maxval = std::max(maxval, std::max(std::fabs(ref.x), std::fabs(ref.y)));
+        }
         }
     }
     return maxerr / std::max(maxval, 1e-300);
@@ -241,12 +262,12 @@ int main() {
     setvbuf(stdout, NULL, _IONBF, 0);
     srand(4242);
     double worst = 0.0;
-    for (int cfg = 0; cfg < 3; ++cfg) {
+    for (int cfg = 0; cfg < 4; ++cfg) {
         g_store.clear(); g_store.reserve(4096);
-        const int L = (cfg == 0) ? 3 : (cfg == 1 ? 4 : 2), NP = L * L;
+        const int L = (cfg == 0) ? 3 : (cfg == 1 ? 4 : (cfg == 2 ? 2 : 1)), NP = L * L;      // cfg 3: the local solver's 1 x 1 mesh
         Grid g; memset(&g, 0, sizeof(g));
         g.T = 0.3; g.L = L; g.NP = NP; g.nK1 = (cfg == 1) ? 6 : 5; g.nPiB = g.nK1; g.nPiF = g.nK1;
-        g.nK2b = 3; g.nK2f = (cfg == 1) ? 4 : 2; g.nK3b = 2; g.nK3f = 2;
+        g.nK2b = 3; g.nK2f = (cfg == 1) ? 4 : (cfg == 3 ? 5 : 2); g.nK3b = 2; g.nK3f = 2;
         DevChain V; memset(&V, 0, sizeof(V)); V.L = L; V.NP = NP; V.nlev = 4;
         V.lev[0] = make_level(LV_NL2, g.nK1, g.nK2b, g.nK2f, g.nK3b, g.nK3f, NP);
         V.lev[1] = (cfg == 2) ? make_level(LV_NL2, 7, 4, 3, 2, 1, NP) : make_level(LV_NL2, g.nK1, g.nK2b, g.nK2f, g.nK3b, g.nK3f, NP);
