@@ -22,14 +22,14 @@ PI0PP, PI0PH, PIPP, PIPH = 0, 1, 2, 3
 SG_SIGMA, SG_K1, SG_PP2, SG_PH2, SG_PP3, SG_PH3, SG_PPL3, SG_PHL3 = range(8)
 SCPA, FDPA = 0, 1
 T_NAMES = ["cache", "L_K2", "L_K3", "K1", "K2", "K3", "sde_L", "sde_rs", "sde_U2", "bubble",
-           "right", "swave", "expand", "misc", "comm"]
+           "right", "swave", "expand", "misc", "comm", "column_K2"]
 
 # every symbol include/fdga.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
     "fdga_create", "fdga_destroy", "fdga_last_error", "fdga_sync", "fdga_set_option", "fdga_comm_unique_id", "fdga_comm_init", "fdga_partition",
     "fdga_set_vertex", "fdga_get_vertex", "fdga_set_core", "fdga_set_green", "fdga_get_green",
     "fdga_set_bubble", "fdga_get_bubble", "fdga_set_cache", "fdga_get_cache", "fdga_get_L",
-    "fdga_set_symmetry_classes", "fdga_build_symmetry_group", "fdga_length_F", "fdga_flatten_F",
+    "fdga_set_symmetry_classes", "fdga_build_symmetry_group", "fdga_length_F", "fdga_flatten_F", "fdga_flatten_F_async",
     "fdga_unflatten_F", "fdga_stash_F", "fdga_unstash_F", "fdga_dyson", "fdga_occupation", "fdga_bubbles_real_space",
     "fdga_bubbles_momentum_space", "fdga_bubbles_local", "fdga_build_K3_cache", "fdga_bse_L_K2", "fdga_bse_L_K3", "fdga_bse_K1",
     "fdga_bse_K2", "fdga_bse_K3", "fdga_set_F_from_Fbuff", "fdga_sde", "fdga_iterate_solver",
@@ -87,6 +87,7 @@ def load():
     lib.fdga_length_F.restype = i64
     lib.fdga_length_F.argtypes = [vp]
     lib.fdga_flatten_F.argtypes = [vp, vp]
+    lib.fdga_flatten_F_async.argtypes = [vp, vp]
     lib.fdga_unflatten_F.argtypes = [vp, vp, dbl]
     lib.fdga_stash_F.argtypes = [vp]
     lib.fdga_unstash_F.argtypes = [vp]

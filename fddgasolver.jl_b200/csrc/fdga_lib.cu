@@ -80,6 +80,7 @@ struct fdga_ctx {
     cudaStream_t main_stream; cudaStream_t lane[3]; cudaEvent_t ev_fork, ev_join[3];
     int cur_lane; bool forked; int opt_serial;
     C* RtL[3]; C* TtabL[3]; C* OwnTabL[3]; C* RtotL[3]; C* ConvTabL[3];
+    cudaStream_t copy_stream; cudaEvent_t ev_copy_ready, ev_copy_done; bool copy_pending;   // fdga_flatten_F_async
     C* SigR2;             // scratch of the U^2 term (its lane runs beside the real-space contraction)
     C* scratchA; C* scratchB; size_t lenScratch;   // bubble-sized ping-pong (DFTs)
     C* GR; C* GRm; C* SigR; C* SigTmp; C* SigAcc;  // G-sized scratch
@@ -119,18 +120,19 @@ static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) 
 
 // profiling scope: CUDA events on the launching stream around a group of launches
 struct Scope {
-    fdga_ctx* c; int cat; bool on;
-    Scope(fdga_ctx* c_, int cat_) : c(c_), cat(cat_), on(false) {
+    fdga_ctx* c; int cat; bool on; size_t idx;
+    Scope(fdga_ctx* c_, int cat_) : c(c_), cat(cat_), on(false), idx(0) {
         if (c->profile && c->cur_cat < 0) {
             on = true; c->cur_cat = cat;
             TimedEvent ev; ev.cat = cat;
             cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
             cudaEventRecord(ev.a, c->stream);
+            idx = c->events.size();
             c->events.push_back(ev);
         }
     }
     ~Scope() {
-        if (on) { cudaEventRecord(c->events.back().b, c->stream); c->cur_cat = -1; }
+        if (on) { cudaEventRecord(c->events[idx].b, c->stream); c->cur_cat = -1; }
     }
 };
 #define LAUNCH(cat, kernel, grid, block, ...) do { \
@@ -471,6 +473,8 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
         CKC(cudaStreamCreateWithPriority(&ctx->lane[1], cudaStreamNonBlocking, hi));
         CKC(cudaStreamCreateWithFlags(&ctx->lane[2], cudaStreamNonBlocking));
     }
+    CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)); ctx->copy_pending = false;
+    CKC(cudaEventCreateWithFlags(&ctx->ev_copy_ready, cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < 3; i++) CKC(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
     for (int l = 0; l < ctx->nlev; l++) if (alloc_level(ctx, ctx->lev[l], dims->lev[l])) { g_create_error = ctx->err; delete ctx; return 1; }
@@ -541,6 +545,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); for (int k = 0; k < 3; k++) cudaFree(s.d_rep[k]);
         cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); cudaFree(s.d_grp_start); }
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_copy_ready); cudaEventDestroy(ctx->ev_copy_done);
     for (int i = 1; i < 3; i++) cudaStreamDestroy(ctx->lane[i]);
     cudaEventDestroy(ctx->ev_fork); for (int i = 0; i < 3; i++) cudaEventDestroy(ctx->ev_join[i]);
     cudaStreamDestroy(ctx->main_stream);
@@ -560,7 +565,11 @@ int fdga_set_option(fdga_ctx* ctx, int opt, int value) {
     if (opt == FDGA_OPT_SERIAL) { ctx->opt_serial = value != 0; return 0; }
     FAIL("fdga_set_option: unknown option");
 }
-int fdga_sync(fdga_ctx* ctx) { CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+int fdga_sync(fdga_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_pending) { CK(cudaStreamSynchronize(ctx->copy_stream)); ctx->copy_pending = false; }
+    return 0;
+}
 void* fdga_stream(fdga_ctx* ctx) { return (void*)ctx->stream; }
 
 // ---- NCCL ----------------------------------------------------------------------------------------
@@ -626,6 +635,7 @@ int fdga_set_vertex(fdga_ctx* ctx, int which, int channel, int cls, const fdga_c
     LevelBuf* lb = which_level(ctx, which);
     if (!lb || lb->d.type == FDGA_LV_CORE || channel < 0 || channel > 2 || cls < 0 || cls > 2) FAIL("fdga_set_vertex: bad selector");
     if ((size_t)n != lb->len[cls]) FAIL("fdga_set_vertex: length mismatch");
+    if (lb == &ctx->lev[0] && ctx->copy_pending) CK(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_copy_done, 0));
     CK(cudaMemcpyAsync(lb->K[channel][cls], host, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     lb->sw_dirty = true; lb->k1h_dirty = true; ctx->fsum_dirty = true;
@@ -731,7 +741,22 @@ int fdga_flatten_F(fdga_ctx* ctx, fdga_c64* host_y) {
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+// an asynchronous flatten may still be reading S.F: writers of the level-0 block wait for it (stream order, no host sync)
+static int wait_copy(fdga_ctx* ctx) {
+    if (ctx->copy_pending) CK(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_copy_done, 0));
+    return 0;
+}
+int fdga_flatten_F_async(fdga_ctx* ctx, fdga_c64* host_y) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev_copy_ready, ctx->main_stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_ready, 0));
+    CK(cudaMemcpyAsync(host_y, ctx->lev[0].block, ctx->lenFlat * sizeof(C), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
+    ctx->copy_pending = true;
+    return 0;
+}
 static int unflatten_dev(fdga_ctx* ctx, LevelBuf& lb, const C* src, double scale) {
+    if (&lb == &ctx->lev[0] && wait_copy(ctx)) return 1;
     LAUNCH(FDGA_T_MISC, scale_copy_kernel, nblk(lb.blocklen, 256), 256, lb.block, src, scale, (long long)lb.blocklen);
     CK(cudaGetLastError());
     lb.sw_dirty = true; lb.k1h_dirty = true; ctx->fsum_dirty = true;
@@ -901,7 +926,11 @@ static int launch_column_t(fdga_ctx* ctx, const DevChain& V, ColJob job, SymGrou
         own = ctx->OwnTabL[ctx->cur_lane]; rtot = ctx->RtotL[ctx->cur_lane];
     }
     if (launch_slab_conv<KIND, CH>(ctx, V, job, kind, R, cat, &conv)) return 1;
+    const bool sub = ctx->profile && (KIND == JOB_K2 || KIND == JOB_K2_MF) && s.ncol > 0;   // sub-timer: the column kernel alone
+    TimedEvent ev; ev.cat = FDGA_T_COLUMN_K2;
+    if (sub) { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); cudaEventRecord(ev.a, ctx->stream); }
     if (s.ncol > 0) LAUNCH(cat, (column_kernel<KIND, CH>), (unsigned)s.ngrp, 128, V, job, col_dev(s), R, own, rtot, conv, s.d_repvals, ctx->g);
+    if (sub) { cudaEventRecord(ev.b, ctx->stream); ctx->events.push_back(ev); ctx->n_launch[FDGA_T_COLUMN_K2]++; }
     CK(cudaGetLastError());
     return 0;
 }
@@ -1169,6 +1198,7 @@ int fdga_bse_K3(fdga_ctx* ctx, int ch, int mfrg) {
 
 int fdga_set_F_from_Fbuff(fdga_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
+    if (wait_copy(ctx)) return 1;
     CK(cudaMemcpyAsync(ctx->lev[0].block, ctx->Fbuff.block, ctx->Fbuff.blocklen * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->lev[0].sw_dirty = true; ctx->lev[0].k1h_dirty = true; ctx->fsum_dirty = true;
     return 0;

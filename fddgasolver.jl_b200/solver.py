@@ -239,6 +239,11 @@ class NL2_ParquetSolver:
         self._call("fdga_flatten_F", L.ptr(out))
         return out
 
+    def flatten_F_async(self, out):
+        """flatten(S.F) into `out` (ideally pinned) on a side stream, overlapping whatever is issued next; valid after sync()"""
+        assert out.dtype == np.complex128 and out.size == self.length_F()
+        self._call("fdga_flatten_F_async", L.ptr(out))
+
     def unflatten_F(self, x, scale=1.0):
         x = np.ascontiguousarray(x, dtype=np.complex128)
         assert x.size == self.length_F()

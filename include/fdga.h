@@ -126,6 +126,9 @@ int  fdga_build_symmetry_group(int which_sg, int n0, int n1, int nq, int64_t* of
 /* flatten(S.F) / unflatten!(S.F, x*scale): src/vertex.jl:153-195, src/channel.jl:155-210 */
 int64_t fdga_length_F(fdga_ctx*);
 int  fdga_flatten_F(fdga_ctx*, fdga_c64* host_y);
+/* same copy on a side stream, ordered after everything issued so far and overlapping what is issued next (e.g. SDE!
+ * after iterate_solver!); host_y (ideally pinned) is valid after the next fdga_sync.  Later writers of S.F wait for it. */
+int  fdga_flatten_F_async(fdga_ctx*, fdga_c64* host_y);
 int  fdga_unflatten_F(fdga_ctx*, const fdga_c64* host_x, double scale);   /* asynchronous on the context stream */
 /* device-resident copy of S.F (copy(S.F) / set!(S.F, copy)): lets a caller restart iterations without host traffic */
 int  fdga_stash_F(fdga_ctx*);
@@ -167,7 +170,9 @@ int  fdga_mfrg_matvec(fdga_ctx*, const fdga_c64* host_x, fdga_c64* host_y, int f
 /* accumulated device time (CUDA events on the launching stream) and launch counts per kernel id */
 enum { FDGA_T_CACHE = 0, FDGA_T_L_K2 = 1, FDGA_T_L_K3 = 2, FDGA_T_K1 = 3, FDGA_T_K2 = 4, FDGA_T_K3 = 5,
        FDGA_T_SDE_L = 6, FDGA_T_SDE_RS = 7, FDGA_T_SDE_U2 = 8, FDGA_T_BUBBLE = 9, FDGA_T_RIGHT = 10,
-       FDGA_T_SWAVE = 11, FDGA_T_EXPAND = 12, FDGA_T_MISC = 13, FDGA_T_COMM = 14, FDGA_T_COUNT = 15 };
+       FDGA_T_SWAVE = 11, FDGA_T_EXPAND = 12, FDGA_T_MISC = 13, FDGA_T_COMM = 14,
+       FDGA_T_COLUMN_K2 = 15,   /* the column_kernel launches of BSE_K2! alone (a sub-interval of FDGA_T_K2) */
+       FDGA_T_COUNT = 16 };
 int  fdga_profile_enable(fdga_ctx*, int on);
 int  fdga_profile_reset(fdga_ctx*);
 int  fdga_kernel_time_ms(fdga_ctx*, int kernel_id, double* ms, int64_t* launches);

@@ -305,3 +305,24 @@ def test_convolution_and_lanes_match_plain_path(orc, opt):
             assert np.array_equal(a, b)
         else:
             assert rel(a, b) < TOL
+
+
+def test_flatten_async_matches_flatten(orc):
+    """fdga_flatten_F_async: the copy overlaps later work (SDE!) and lands the same bytes as the synchronous flatten"""
+    import fddgasolver_jl_b200 as fd
+    S, _ = make_pair(orc, nmax=2, nq=3, LG=6, sym=True)
+    fd.iterate_solver(S, "fdPA", False)
+    y = np.zeros(S.length_F(), dtype=np.complex128)
+    S.flatten_F_async(y)
+    fd.SDE(S, "scPA")
+    S.unstash_F() if False else None
+    S.sync()
+    assert np.array_equal(y, S.flatten_F())
+    # a writer of S.F issued right after the async copy must not overtake it
+    fd.iterate_solver(S, "fdPA", False)
+    ref = S.flatten_F().copy()
+    S.flatten_F_async(y)
+    S.unflatten_F_async(np.zeros_like(ref))
+    S.sync()
+    assert np.array_equal(y, ref)
+    S.close()
