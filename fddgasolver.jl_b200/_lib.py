@@ -20,7 +20,7 @@ V_FL, V_FBUFF = 100, 101
 G, G0, GBARE, SIGMA, SIGMA0 = 0, 1, 2, 3, 4
 PI0PP, PI0PH, PIPP, PIPH = 0, 1, 2, 3
 SG_SIGMA, SG_K1, SG_PP2, SG_PH2, SG_PP3, SG_PH3, SG_PPL3, SG_PHL3 = range(8)
-SCPA, FDPA = 0, 1
+SCPA, FDPA, SCPA_NEW, FDPA_NEW, FDPA_1LOOP = 0, 1, 2, 3, 4
 T_NAMES = ["cache", "L_K2", "L_K3", "K1", "K2", "K3", "sde_L", "sde_rs", "sde_U2", "bubble",
            "right", "swave", "expand", "misc", "comm", "column_K2"]
 
@@ -32,7 +32,8 @@ EXPORTS = [
     "fdga_set_symmetry_classes", "fdga_build_symmetry_group", "fdga_length_F", "fdga_flatten_F", "fdga_flatten_F_async",
     "fdga_unflatten_F", "fdga_stash_F", "fdga_unstash_F", "fdga_dyson", "fdga_occupation", "fdga_bubbles_real_space",
     "fdga_bubbles_momentum_space", "fdga_bubbles_local", "fdga_build_K3_cache", "fdga_bse_L_K2", "fdga_bse_L_K3", "fdga_bse_K1",
-    "fdga_bse_K2", "fdga_bse_K3", "fdga_set_F_from_Fbuff", "fdga_sde", "fdga_iterate_solver",
+    "fdga_bse_K2", "fdga_bse_K3", "fdga_bse_K1_new", "fdga_bse_K2_new", "fdga_bse_K1_1loop", "fdga_bse_K2_1loop", "fdga_bse_K3_1loop",
+    "fdga_set_F_from_Fbuff", "fdga_sde", "fdga_iterate_solver",
     "fdga_mfrg_matvec", "fdga_profile_enable", "fdga_profile_reset", "fdga_kernel_time_ms",
     "fdga_total_launches", "fdga_stream",
 ]
@@ -102,6 +103,8 @@ def load():
     lib.fdga_bse_K1.argtypes = [vp, i32, i32]
     lib.fdga_bse_K2.argtypes = [vp, i32, i32]
     lib.fdga_bse_K3.argtypes = [vp, i32, i32]
+    for _n in ("fdga_bse_K1_new", "fdga_bse_K2_new", "fdga_bse_K1_1loop", "fdga_bse_K2_1loop", "fdga_bse_K3_1loop"):
+        getattr(lib, _n).argtypes = [vp, i32, i32]
     lib.fdga_set_F_from_Fbuff.argtypes = [vp]
     lib.fdga_sde.argtypes = [vp, i32, i32, i32]
     lib.fdga_iterate_solver.argtypes = [vp, i32, i32]

@@ -167,7 +167,8 @@ __global__ void pi_swave_kernel(const C* __restrict__ Pi, C* __restrict__ Pisw, 
 //  RK_LK2   : Pi0 * F0(W, w, inf; P, q, k0), w on the K2 nu-mesh                        BSEa_K2.jl:38-41
 // Rt layout: [iw + nw*(iq + NP*(iWo + nBo*iP))], W on the OUTPUT bosonic mesh (N = No).
 //  RK_LK2_LOC : Pi0 * F0(W, w~, inf), w on the bubble nu-mesh (local solver)                src/BSEa/BSEa_K2.jl:27-30
-enum { RK_FD = 0, RK_MF_K1 = 1, RK_MF_K2 = 2, RK_LK2 = 3, RK_LK2_LOC = 4 };
+//  RK_1L    : (Pi - Pi0) * F0(W, w~, inf; P, q~, k0)  (fd branch of the 1-loop variants)   BSE_1loop.jl:41-46,104-109
+enum { RK_FD = 0, RK_MF_K1 = 1, RK_MF_K2 = 2, RK_LK2 = 3, RK_LK2_LOC = 4, RK_1L = 5 };
 
 // Only the slabs (W, P) that hold class representatives of this rank are filled: `slabs` lists (iWo, iP) pairs.
 template <int CH, int KIND>
@@ -188,7 +189,7 @@ __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const _
     size_t pidx = posF(w, g.nPiF) + (size_t)nFP * (iq + (size_t)g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP));
     Arg a;
     a.W = W; a.w = FDGA_INF; a.Px = Px; a.Py = Py; a.qx = 0; a.qy = 0;
-    if (KIND == RK_FD || KIND == RK_MF_K1 || KIND == RK_LK2_LOC) {   // crossed arguments (_crossing, BSE_templates.jl:4-6)
+    if (KIND == RK_FD || KIND == RK_MF_K1 || KIND == RK_LK2_LOC || KIND == RK_1L) {   // crossed arguments (_crossing, BSE_templates.jl:4-6)
         a.v = (CH == CH_P) ? W - w - 1 : w;
         a.kx = (CH == CH_P) ? Px - qx : qx; a.ky = (CH == CH_P) ? Py - qy : qy;
     } else {
@@ -200,6 +201,8 @@ __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const _
         C FLr = eval_vertex<false>(FL, 0, CH, SP, a, FL_ALL);
         C p = PiT[pidx], p0 = Pi0T[pidx];
         r = (p - p0) * F0r + p * FLr;
+    } else if (KIND == RK_1L) {
+        r = (PiT[pidx] - Pi0T[pidx]) * eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
     } else if (KIND == RK_LK2 || KIND == RK_LK2_LOC) {
         r = Pi0T[pidx] * eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
     } else {
@@ -289,6 +292,63 @@ __global__ void bse_k2_kernel(const __grid_constant__ DevChain Fleft, const C* _
     if (threadIdx.x == 0) repvals[cls] = acc * scale;
 }
 
+// ---- BSE_K1_new!: src/nonlocal_2/BSEa/BSEa_K1.jl:62-113, K1 = (U + K1 + K2') Pi U.  One CTA per representative (W, P).
+//  fd   : [F(W,inf,w;P,k0,q) Pi - F0(W,inf,w;P,k0,q) Pi0] U          mfRG : [F - F0] Pi U
+//  PiT / Pi0T are the transposed bubbles [w, q | W, P] (W on the bubble mesh, which is the K1 mesh).
+template <int CH>
+__global__ void bse_k1_new_kernel(const __grid_constant__ DevChain F, const __grid_constant__ DevChain F0,
+                                  const C* __restrict__ Pi0T, const C* __restrict__ PiT, C* __restrict__ repvals,
+                                  SymDev sg, long long c0, Grid g, C scaleU, int mfrg) {
+    constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
+    long long cls = c0 + blockIdx.x;
+    long long idx = sg.index[sg.offsets[cls]];
+    const int nB1 = 2 * g.nK1 - 1, nw = 2 * g.nPiF, nBP = 2 * g.nPiB - 1;
+    int iW = idx % nB1, iP = idx / nB1;
+    int W = iW - (g.nK1 - 1), Px = iP % g.L, Py = iP / g.L;
+    const size_t off = (size_t)nw * g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP);
+    C acc = zeroC();
+    for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
+        int iw = t % nw, iq = t / nw;
+        Arg a; a.W = W; a.v = FDGA_INF; a.w = iw - g.nPiF; a.Px = Px; a.Py = Py; a.kx = 0; a.ky = 0; a.qx = iq % g.L; a.qy = iq / g.L;
+        C Fl = eval_vertex<false>(F, 0, CH, SP, a, FL_ALL);
+        C F0l = eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
+        if (mfrg) acc += (Fl - F0l) * PiT[off + t];
+        else      acc += Fl * PiT[off + t] - F0l * Pi0T[off + t];
+    }
+    acc = block_reduce(acc);
+    if (threadIdx.x == 0) repvals[cls] = acc * scaleU;
+}
+
+// ---- BSE_K2_new!: src/nonlocal_2/BSEa/BSEa_K2.jl:142-216.  One CTA per representative (W, v, P, k); the inner
+// frequency runs over the K2 nu-mesh only (BSEa_K2.jl:189-193).
+template <int CH>
+__global__ void bse_k2_new_kernel(const __grid_constant__ DevChain F, const __grid_constant__ DevChain F0,
+                                  const C* __restrict__ Pi0T, const C* __restrict__ PiT, C* __restrict__ repvals,
+                                  SymDev sg, long long c0, Grid g, C scaleU, int mfrg) {
+    constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
+    long long cls = c0 + blockIdx.x;
+    long long idx = sg.index[sg.offsets[cls]];
+    const int nB2 = 2 * g.nK2b - 1, nF2 = 2 * g.nK2f, nFP = 2 * g.nPiF, nBP = 2 * g.nPiB - 1;
+    long long t0 = idx;
+    int iW = t0 % nB2; t0 /= nB2; int iv = t0 % nF2; t0 /= nF2; int iP = t0 % g.NP; int ik = t0 / g.NP;
+    int W = iW - (g.nK2b - 1), v = iv - g.nK2f, Px = iP % g.L, Py = iP / g.L, kx = ik % g.L, ky = ik / g.L;
+    const size_t off = (size_t)nFP * g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP);
+    C acc = zeroC();
+    for (int t = threadIdx.x; t < nF2 * g.NP; t += blockDim.x) {
+        int iw = t % nF2, iq = t / nF2;
+        int w = iw - g.nK2f;
+        Arg a; a.W = W; a.v = v; a.w = w; a.Px = Px; a.Py = Py; a.kx = kx; a.ky = ky; a.qx = iq % g.L; a.qy = iq / g.L;
+        C Fl = eval_vertex<false>(F, 0, CH, SP, a, FL_ALL), F0l = eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
+        a.v = FDGA_INF;
+        Fl = Fl - eval_vertex<false>(F, 0, CH, SP, a, FL_ALL); F0l = F0l - eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
+        size_t pidx = off + posF(w, g.nPiF) + (size_t)nFP * iq;
+        if (mfrg) acc += (Fl - F0l) * PiT[pidx];
+        else      acc += Fl * PiT[pidx] - F0l * Pi0T[pidx];
+    }
+    acc = block_reduce(acc);
+    if (threadIdx.x == 0) repvals[cls] = acc * scaleU;
+}
+
 // ---- K3 index helper -----------------------------------------------------------------------------
 __device__ __forceinline__ size_t k3at(const Grid& g, int W, int v, int w, int iP) {
     int nB = 2 * g.nK3b - 1, nF = 2 * g.nK3f;
@@ -317,7 +377,9 @@ __global__ void bse_lk3_kernel(const C* __restrict__ cache_G, const C* __restric
 }
 
 // ---- BSE_K3!: src/nonlocal_2/BSEa/BSEa_K3.jl:62-121.  One thread per representative -----------------
-template <int CH, bool MF>
+// ONELOOP: BSE_K3_1loop! (src/nonlocal_2/BSEa/BSE_1loop.jl:123-199): fd branch keeps the (Pi - Pi0) F0 term only;
+// neither branch adds FL.K3 to the result.
+template <int CH, bool MF, bool ONELOOP = false>
 __global__ void bse_k3_kernel(const C* __restrict__ FLown, const C* __restrict__ FLt, const C* __restrict__ FLa,
                               const C* __restrict__ cache_G, const C* __restrict__ cache_F, const C* __restrict__ cache_F0,
                               const C* __restrict__ Pi0sw, const C* __restrict__ Pisw, C* __restrict__ repvals,
@@ -338,6 +400,10 @@ __global__ void bse_k3_kernel(const C* __restrict__ FLown, const C* __restrict__
         if (MF) {
             val += Fs * P0 * Gs * sign1;
             if (cin) val += Fs * P0 * cen * sign2;
+        } else if (ONELOOP) {
+            C P1 = Pisw[piswat(g, W, w, iP)];
+            C F0s = cache_F0[k3at(g, W, w, vp, iP)];
+            val += Fs * (P1 - P0) * F0s * sign1;
         } else {
             C P1 = Pisw[piswat(g, W, w, iP)];
             C F0s = cache_F0[k3at(g, W, w, vp, iP)];
@@ -345,6 +411,7 @@ __global__ void bse_k3_kernel(const C* __restrict__ FLown, const C* __restrict__
             if (cin) val += Fs * P1 * cen * sign2;
         }
     }
+    if (ONELOOP) { repvals[cls] = val * g.T; return; }
     C add = (CH == CH_T) ? (2.0 * FLt[k3at(g, W, v, vp, iP)] - FLa[k3at(g, W, v, vp, iP)]) : FLown[k3at(g, W, v, vp, iP)];
     repvals[cls] = val * g.T + add;
 }

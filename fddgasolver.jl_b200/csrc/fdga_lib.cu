@@ -47,7 +47,7 @@ struct SymGroup {
 };
 struct TimedEvent { cudaEvent_t a, b; int cat; };
 struct Pending { SymGroup* s; C* rep; C* out; int kind, ch; bool expanded; };
-enum { PK_K1 = 0, PK_LK2 = 1, PK_K2 = 2, PK_LK3 = 3, PK_K3 = 4 };
+enum { PK_K1 = 0, PK_LK2 = 1, PK_K2 = 2, PK_LK3 = 3, PK_K3 = 4, PK_K2_NOFL = 5 };
 
 // NCCL through dlopen (no link-time dependency; the process may already hold torch's libnccl)
 struct NcclApi {
@@ -954,6 +954,7 @@ static int cached_right(fdga_ctx* ctx, int ch, int kind, const DevChain& F0, con
     int rc;
     if (kind == RK_FD) rc = launch_right<RK_FD>(ctx, ch, F0, FL, ctx->g.nPiB, ctx->g.nPiF, ctx->Rt3[ch]);
     else if (kind == RK_MF_K1) rc = launch_right<RK_MF_K1>(ctx, ch, F0, FL, ctx->g.nPiB, ctx->g.nPiF, ctx->Rt3[ch]);
+    else if (kind == RK_1L) rc = launch_right<RK_1L>(ctx, ch, F0, FL, ctx->g.nPiB, ctx->g.nPiF, ctx->Rt3[ch]);
     else rc = launch_right<RK_MF_K2>(ctx, ch, F0, FL, ctx->g.nPiB, ctx->g.nPiF, ctx->Rt3[ch]);
     if (rc) return rc;
     ctx->rt_kind[ch] = tag;
@@ -980,6 +981,7 @@ static int post_fix(fdga_ctx* ctx, int kind, int ch) {
         }
         return add_axpby(ctx, out, ctx->FL.K[ch][1], 1.0, nullptr, 0.0, n);
     }
+    case PK_K2_NOFL: if (ch == FDGA_TCH) return tfix(ctx, ctx->Fbuff.K[FDGA_TCH][1], ctx->Fbuff.K[FDGA_ACH][1], ctx->Fbuff.len[1]); return 0;
     case PK_LK3: ctx->FL.sw_dirty = true; invalidate_rt(ctx);
                  if (ch == FDGA_TCH) return tfix(ctx, ctx->FL.K[FDGA_TCH][2], ctx->FL.K[FDGA_ACH][2], ctx->FL.len[2]); return 0;
     case PK_K3:  if (ch == FDGA_TCH) return tfix(ctx, ctx->Fbuff.K[FDGA_TCH][2], ctx->Fbuff.K[FDGA_ACH][2], ctx->Fbuff.len[2]); return 0;
@@ -1051,13 +1053,14 @@ static int lanes_join(fdga_ctx* ctx) {
     return 0;
 }
 
-int fdga_bse_K1(fdga_ctx* ctx, int ch, int mfrg) {
+// BSE_K1! and the fd branch of BSE_K1_1loop! differ in the right factor only (rk_fd = RK_FD resp. RK_1L)
+static int bse_K1_impl(fdga_ctx* ctx, int ch, int mfrg, int rk_fd) {
     CK(cudaSetDevice(ctx->device));
     if (ch < 0 || ch > 2) FAIL("fdga_bse_K1: bad channel");
     NEED_SG(FDGA_SG_K1);
     if (ensure_pi(ctx, ch)) return 1;
     DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0), FL = chain_FL(ctx);
-    if (cached_right(ctx, ch, mfrg ? RK_MF_K1 : RK_FD, F0, FL)) return 1;
+    if (cached_right(ctx, ch, mfrg ? RK_MF_K1 : rk_fd, F0, FL)) return 1;
     SymGroup& s = ctx->sg[FDGA_SG_K1]; s.d_repvals = s.d_rep[ch];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
     double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
@@ -1073,6 +1076,40 @@ int fdga_bse_K1(fdga_ctx* ctx, int ch, int mfrg) {
     }
     return finish_or_defer(ctx, s, ctx->Fbuff.K[ch][0], PK_K1, ch);
 }
+int fdga_bse_K1(fdga_ctx* ctx, int ch, int mfrg) { return bse_K1_impl(ctx, ch, mfrg, RK_FD); }
+// BSE_K1_1loop!: src/nonlocal_2/BSEa/BSE_1loop.jl:2-56 (its mfRG branch is BSE_K1!'s)
+int fdga_bse_K1_1loop(fdga_ctx* ctx, int ch, int mfrg) { return bse_K1_impl(ctx, ch, mfrg, RK_1L); }
+
+// BSE_K1_new! / BSE_K2_new!: src/nonlocal_2/BSEa/BSEa_K1.jl:62-113, BSEa_K2.jl:142-216 (term-by-term kernels)
+static int bse_new_impl(fdga_ctx* ctx, int ch, int mfrg, int cls) {
+    CK(cudaSetDevice(ctx->device));
+    if (ch < 0 || ch > 2) FAIL("fdga_bse_K*_new: bad channel");
+    int which = cls == 0 ? FDGA_SG_K1 : (ch == FDGA_PCH ? FDGA_SG_PP2 : FDGA_SG_PH2);
+    NEED_SG(which);
+    if (ctx->opt_local) FAIL("fdga_bse_K*_new: not available for the local solver context");
+    if (ensure_pi(ctx, ch)) return 1;
+    DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0);
+    SymGroup& s = ctx->sg[which]; s.d_repvals = s.d_rep[ch];
+    long long c0, c1; sg_class_range(ctx, s, c0, c1);
+    const C* p0 = ctx->PiT[pi_kind(ch, true)]; const C* p1 = ctx->PiT[pi_kind(ch, false)];
+    C scaleU = bareU(ctx) * (ctx->g.T / (double)ctx->g.NP * chsign(ch));      // bare_vertex(F, Sp) = +U for pSp and dSp
+    const int cat = cls == 0 ? FDGA_T_K1 : FDGA_T_K2;
+    {
+        Scope sc(ctx, cat);
+        unsigned nb = (unsigned)(c1 - c0);
+        if (c1 > c0) {
+#define NEWL(KER, CHT) LAUNCH(cat, KER<CHT>, nb, 256, F, F0, p0, p1, s.d_repvals, sym_dev(s), c0, ctx->g, scaleU, mfrg)
+            if (cls == 0) { if (ch == FDGA_PCH) NEWL(bse_k1_new_kernel, CH_P); else if (ch == FDGA_TCH) NEWL(bse_k1_new_kernel, CH_T); else NEWL(bse_k1_new_kernel, CH_A); }
+            else          { if (ch == FDGA_PCH) NEWL(bse_k2_new_kernel, CH_P); else if (ch == FDGA_TCH) NEWL(bse_k2_new_kernel, CH_T); else NEWL(bse_k2_new_kernel, CH_A); }
+#undef NEWL
+        }
+        CK(cudaGetLastError());
+    }
+    // post-fix: only the d -> p spin fix of the t channel (BSE_templates.jl:209-215, 244-250); no FL add
+    return finish_or_defer(ctx, s, ctx->Fbuff.K[ch][cls], cls == 0 ? PK_K1 : PK_K2_NOFL, ch);
+}
+int fdga_bse_K1_new(fdga_ctx* ctx, int ch, int mfrg) { return bse_new_impl(ctx, ch, mfrg, 0); }
+int fdga_bse_K2_new(fdga_ctx* ctx, int ch, int mfrg) { return bse_new_impl(ctx, ch, mfrg, 1); }
 
 int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
     CK(cudaSetDevice(ctx->device));
@@ -1106,15 +1143,17 @@ int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
     return finish_or_defer(ctx, s, ctx->FL.K[ch][1], PK_LK2, ch);
 }
 
-int fdga_bse_K2(fdga_ctx* ctx, int ch, int mfrg) {
+// BSE_K2! and the fd branch of BSE_K2_1loop! differ in the right factor only (rk_fd = RK_FD resp. RK_1L)
+static int bse_K2_impl(fdga_ctx* ctx, int ch, int mfrg, int rk_fd) {
     CK(cudaSetDevice(ctx->device));
     if (ch < 0 || ch > 2) FAIL("fdga_bse_K2: bad channel");
     int which = ch == FDGA_PCH ? FDGA_SG_PP2 : FDGA_SG_PH2;
     NEED_SG(which);
     if (ensure_pi(ctx, ch)) return 1;
     DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0), FL = chain_FL(ctx);
-    if (!ctx->opt_generic) { if (cached_right(ctx, ch, mfrg ? RK_MF_K2 : RK_FD, F0, FL)) return 1; }
+    if (!ctx->opt_generic) { if (cached_right(ctx, ch, mfrg ? RK_MF_K2 : rk_fd, F0, FL)) return 1; }
     else if (mfrg) { if (launch_right<RK_MF_K2>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1; }
+    else if (rk_fd == RK_1L) { if (launch_right<RK_1L>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1; }
     else           { if (launch_right<RK_FD>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1; }
     SymGroup& s = ctx->sg[which]; s.d_repvals = s.d_rep[ch];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
@@ -1146,6 +1185,9 @@ int fdga_bse_K2(fdga_ctx* ctx, int ch, int mfrg) {
     }
     return finish_or_defer(ctx, s, ctx->Fbuff.K[ch][1], PK_K2, ch);
 }
+int fdga_bse_K2(fdga_ctx* ctx, int ch, int mfrg) { return bse_K2_impl(ctx, ch, mfrg, RK_FD); }
+// BSE_K2_1loop!: src/nonlocal_2/BSEa/BSE_1loop.jl:59-124 (its mfRG branch and its FL.K2 post-add are BSE_K2!'s)
+int fdga_bse_K2_1loop(fdga_ctx* ctx, int ch, int mfrg) { return bse_K2_impl(ctx, ch, mfrg, RK_1L); }
 
 int fdga_bse_L_K3(fdga_ctx* ctx, int ch) {
     CK(cudaSetDevice(ctx->device));
@@ -1167,7 +1209,7 @@ int fdga_bse_L_K3(fdga_ctx* ctx, int ch) {
     return finish_or_defer(ctx, s, ctx->FL.K[ch][2], PK_LK3, ch);
 }
 
-int fdga_bse_K3(fdga_ctx* ctx, int ch, int mfrg) {
+static int bse_K3_impl(fdga_ctx* ctx, int ch, int mfrg, bool oneloop) {
     CK(cudaSetDevice(ctx->device));
     if (ch < 0 || ch > 2) FAIL("fdga_bse_K3: bad channel");
     int which = ch == FDGA_PCH ? FDGA_SG_PP3 : FDGA_SG_PH3;
@@ -1185,16 +1227,22 @@ int fdga_bse_K3(fdga_ctx* ctx, int ch, int mfrg) {
     {
         Scope sc(ctx, FDGA_T_K3);
         unsigned nb = nblk(c1 - c0, 64);
-#define K3L(CHT, MFT) LAUNCH(FDGA_T_K3, (bse_k3_kernel<CHT, MFT>), nb, 64, FLo, FLt, FLa, ctx->cache[cg], ctx->cache[cf], ctx->cache[cf0], Pi0sw, Pisw, s.d_repvals, sym_dev(s), c0, c1, ctx->g, s1, s2)
-        if (c1 > c0) {
-            if (mfrg) { if (ch == FDGA_PCH) K3L(CH_P, true); else if (ch == FDGA_TCH) K3L(CH_T, true); else K3L(CH_A, true); }
-            else      { if (ch == FDGA_PCH) K3L(CH_P, false); else if (ch == FDGA_TCH) K3L(CH_T, false); else K3L(CH_A, false); }
+#define K3L(CHT, MFT, OL) LAUNCH(FDGA_T_K3, (bse_k3_kernel<CHT, MFT, OL>), nb, 64, FLo, FLt, FLa, ctx->cache[cg], ctx->cache[cf], ctx->cache[cf0], Pi0sw, Pisw, s.d_repvals, sym_dev(s), c0, c1, ctx->g, s1, s2)
+        if (c1 > c0 && !oneloop) {
+            if (mfrg) { if (ch == FDGA_PCH) K3L(CH_P, true, false); else if (ch == FDGA_TCH) K3L(CH_T, true, false); else K3L(CH_A, true, false); }
+            else      { if (ch == FDGA_PCH) K3L(CH_P, false, false); else if (ch == FDGA_TCH) K3L(CH_T, false, false); else K3L(CH_A, false, false); }
+        } else if (c1 > c0) {
+            if (mfrg) { if (ch == FDGA_PCH) K3L(CH_P, true, true); else if (ch == FDGA_TCH) K3L(CH_T, true, true); else K3L(CH_A, true, true); }
+            else      { if (ch == FDGA_PCH) K3L(CH_P, false, true); else if (ch == FDGA_TCH) K3L(CH_T, false, true); else K3L(CH_A, false, true); }
         }
 #undef K3L
         CK(cudaGetLastError());
     }
     return finish_or_defer(ctx, s, ctx->Fbuff.K[ch][2], PK_K3, ch);
 }
+int fdga_bse_K3(fdga_ctx* ctx, int ch, int mfrg) { return bse_K3_impl(ctx, ch, mfrg, false); }
+// BSE_K3_1loop!: src/nonlocal_2/BSEa/BSE_1loop.jl:123-199
+int fdga_bse_K3_1loop(fdga_ctx* ctx, int ch, int mfrg) { return bse_K3_impl(ctx, ch, mfrg, true); }
 
 int fdga_set_F_from_Fbuff(fdga_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
@@ -1313,7 +1361,8 @@ int fdga_sde(fdga_ctx* ctx, int strategy, int include_U2, int include_Hartree) {
     C* S = ctx->G[FDGA_SIGMA];
     CK(cudaMemsetAsync(S, 0, ctx->lenG * sizeof(C), ctx->stream));
     if (sde_chain(ctx, S, 1.0, FDGA_G, false, 0, include_U2, include_Hartree)) return 1;
-    if (strategy == FDGA_FDPA) {      // src/SDE.jl:13-24
+    if (strategy < FDGA_SCPA || strategy > FDGA_FDPA_1LOOP) FAIL("fdga_sde: Calculation strategy unknown");
+    if (strategy == FDGA_FDPA || strategy == FDGA_FDPA_NEW || strategy == FDGA_FDPA_1LOOP) {      // src/SDE.jl:4,8,13-24
         if (sde_chain(ctx, S, -1.0, FDGA_G0, true, 1, include_U2, include_Hartree)) return 1;
         LAUNCH(FDGA_T_MISC, add_axpby_kernel, nblk(ctx->lenG, 256), 256, S, ctx->G[FDGA_SIGMA0], 1.0, (const C*)nullptr, 0.0, (long long)ctx->lenG);
         if (include_Hartree && !ctx->opt_hartree_once) {
@@ -1321,7 +1370,7 @@ int fdga_sde(fdga_ctx* ctx, int strategy, int include_U2, int include_Hartree) {
             LAUNCH(FDGA_T_MISC, hartree_kernel, nblk(ctx->lenG, 256), 256, S, ctx->d_occ, bareU(ctx), -1.0, (long long)ctx->lenG);
         }
         CK(cudaGetLastError());
-    } else if (strategy != FDGA_SCPA) FAIL("fdga_sde: unknown strategy");
+    }
     return 0;
 }
 
@@ -1354,11 +1403,40 @@ static int bse_stages(fdga_ctx* ctx, bool with_L, int mfrg) {
     return rc;
 }
 
+// one stage = the same entry point for the three channels on concurrent lanes + one batched SG finish
+static int bse_stage(fdga_ctx* ctx, int (*fn)(fdga_ctx*, int, int), int mfrg) {
+    const int order[3] = {FDGA_TCH, FDGA_PCH, FDGA_ACH};
+    int rc = lanes_fork(ctx);
+    for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fn(ctx, order[i], mfrg); }
+    if (lanes_join(ctx)) rc = 1;
+    if (!rc) rc = flush_pending(ctx);
+    return rc;
+}
+static int bse_L_K3_stage_fn(fdga_ctx* ctx, int ch, int) { return fdga_bse_L_K3(ctx, ch); }
+// the stage lists of the variant strategies, src/solve.jl:26-58
+static int bse_stages_variant(fdga_ctx* ctx, int strategy) {
+    ctx->defer = true;
+    int rc = 0;
+    if (strategy == FDGA_FDPA_1LOOP) {
+        rc = bse_stage(ctx, fdga_bse_K3_1loop, 0);
+        if (!rc) rc = bse_stage(ctx, fdga_bse_K1_1loop, 0);
+        if (!rc) rc = bse_stage(ctx, fdga_bse_K2_1loop, 0);
+    } else {
+        if (strategy == FDGA_FDPA_NEW) rc = bse_stage(ctx, bse_L_K3_stage_fn, 0);
+        if (!rc) rc = bse_stage(ctx, fdga_bse_K3, 0);
+        if (!rc) rc = bse_stage(ctx, fdga_bse_K1_new, 0);
+        if (!rc) rc = bse_stage(ctx, fdga_bse_K2_new, 0);
+    }
+    ctx->defer = false; ctx->pending.clear();
+    return rc;
+}
+
 int fdga_iterate_solver(fdga_ctx* ctx, int strategy, int update_sigma) {
-    if (strategy != FDGA_SCPA && strategy != FDGA_FDPA) FAIL("fdga_iterate_solver: strategy must be scPA or fdPA");
+    if (strategy < FDGA_SCPA || strategy > FDGA_FDPA_1LOOP) FAIL("fdga_iterate_solver: Calculation strategy unknown");
     if (update_sigma) { if (fdga_dyson(ctx) || (ctx->opt_local ? fdga_bubbles_local(ctx, 0) : fdga_bubbles_real_space(ctx, 0))) return 1; }
     if (fdga_build_K3_cache(ctx, 0, 0)) return 1;
-    if (bse_stages(ctx, strategy == FDGA_FDPA, 0)) return 1;
+    if (strategy >= FDGA_SCPA_NEW) { if (bse_stages_variant(ctx, strategy)) return 1; }
+    else if (bse_stages(ctx, strategy == FDGA_FDPA, 0)) return 1;
     if (fdga_set_F_from_Fbuff(ctx)) return 1;
     if (update_sigma) { if (fdga_sde(ctx, strategy, 1, 1)) return 1; }
     return 0;

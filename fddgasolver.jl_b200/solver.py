@@ -21,7 +21,7 @@ import numpy as np
 from . import _lib as L
 from .types import (CH_NAME, CHANNELS, NL2_Vertex, RefVertex, Vertex, aCh, nB, nF, pCh, tCh, vertex_chain, zeros)
 
-STRATEGY = {"scPA": L.SCPA, "fdPA": L.FDPA}
+STRATEGY = {"scPA": L.SCPA, "fdPA": L.FDPA, "scPA_new": L.SCPA_NEW, "fdPA_new": L.FDPA_NEW, "fdPA_1loop": L.FDPA_1LOOP}
 _G_NAMES = {"G": L.G, "G0": L.G0, "Gbare": L.GBARE, "Σ": L.SIGMA, "Σ0": L.SIGMA0}
 _PI_NAMES = {"Π0pp": L.PI0PP, "Π0ph": L.PI0PH, "Πpp": L.PIPP, "Πph": L.PIPH}
 _CACHE_NAMES = ["cache_Γpx", "cache_F0p", "cache_F0a", "cache_F0t", "cache_Γpp", "cache_Γa", "cache_Γt",
@@ -379,12 +379,40 @@ def BSE_K3(S, Ch, is_mfRG=False):
     S._call("fdga_bse_K3", Ch, int(is_mfRG))
 
 
+def BSE_K1_new(S, Ch, is_mfRG=False):
+    """BSE_K1_new!(S, Ch, is_mfRG): src/BSE_templates.jl:188-218"""
+    S._call("fdga_bse_K1_new", Ch, int(is_mfRG))
+
+
+def BSE_K2_new(S, Ch, is_mfRG=False):
+    """BSE_K2_new!(S, Ch, is_mfRG): src/BSE_templates.jl:223-253"""
+    S._call("fdga_bse_K2_new", Ch, int(is_mfRG))
+
+
+def BSE_K1_1loop(S, Ch, is_mfRG=False):
+    """BSE_K1_1loop!(S, Ch, is_mfRG): src/BSE_templates.jl:261-291"""
+    S._call("fdga_bse_K1_1loop", Ch, int(is_mfRG))
+
+
+def BSE_K2_1loop(S, Ch, is_mfRG=False):
+    """BSE_K2_1loop!(S, Ch, is_mfRG): src/BSE_templates.jl:297-327"""
+    S._call("fdga_bse_K2_1loop", Ch, int(is_mfRG))
+
+
+def BSE_K3_1loop(S, Ch, is_mfRG=False):
+    """BSE_K3_1loop!(S, Ch, is_mfRG): src/BSE_templates.jl:332-358"""
+    S._call("fdga_bse_K3_1loop", Ch, int(is_mfRG))
+
+
 def SDE(S, strategy="scPA", include_U2=True, include_Hartree=True):
+    if strategy not in STRATEGY:
+        raise ValueError(f"Calculation strategy {strategy} unknown")      # src/SDE.jl:31
     S._call("fdga_sde", STRATEGY[strategy], int(include_U2), int(include_Hartree))
 
 
 def iterate_solver(S, strategy="fdPA", update_Σ=True):
     """iterate_solver!(S; strategy, update_Σ): src/solve.jl:4-116 (fused inside the library)"""
+    assert strategy in STRATEGY, "Calculation strategy unknown"      # src/solve.jl:10
     S._call("fdga_iterate_solver", STRATEGY[strategy], int(update_Σ))
 
 
@@ -395,17 +423,15 @@ def iterate_solver_stepwise(S, strategy="fdPA", update_Σ=True):
         bubbles(S)
     build_K3_cache(S)
     order = (pCh, aCh, tCh)
-    if strategy == "fdPA":
+    if strategy in ("fdPA_new", "scPA_new"):
+        stages = ([BSE_L_K3] if strategy == "fdPA_new" else []) + [BSE_K3, BSE_K1_new, BSE_K2_new]
+    elif strategy == "fdPA_1loop":
+        stages = [BSE_K3_1loop, BSE_K1_1loop, BSE_K2_1loop]
+    else:
+        stages = ([BSE_L_K2, BSE_L_K3] if strategy == "fdPA" else []) + [BSE_K1, BSE_K2, BSE_K3]
+    for stage in stages:
         for ch in order:
-            BSE_L_K2(S, ch)
-        for ch in order:
-            BSE_L_K3(S, ch)
-    for ch in order:
-        BSE_K1(S, ch)
-    for ch in order:
-        BSE_K2(S, ch)
-    for ch in order:
-        BSE_K3(S, ch)
+            stage(S, ch)
     S._call("fdga_set_F_from_Fbuff")
     if update_Σ:
         SDE(S, strategy)

@@ -72,7 +72,8 @@ enum { FDGA_C_GPX = 0, FDGA_C_F0P = 1, FDGA_C_F0A = 2, FDGA_C_F0T = 3, FDGA_C_GP
 /* symmetry groups, src/nonlocal_2/ParquetSolver.jl:200-291 (SGxx[i] -> K(i) class) */
 enum { FDGA_SG_SIGMA = 0, FDGA_SG_K1 = 1, FDGA_SG_PP2 = 2, FDGA_SG_PH2 = 3, FDGA_SG_PP3 = 4,
        FDGA_SG_PH3 = 5, FDGA_SG_PPL3 = 6, FDGA_SG_PHL3 = 7, FDGA_SG_COUNT = 8 };
-enum { FDGA_SCPA = 0, FDGA_FDPA = 1 };   /* strategies of src/solve.jl:10, src/SDE.jl:3-33 */
+/* strategies of src/solve.jl:10, src/SDE.jl:3-33 (:scPA, :fdPA, :scPA_new, :fdPA_new, :fdPA_1loop) */
+enum { FDGA_SCPA = 0, FDGA_FDPA = 1, FDGA_SCPA_NEW = 2, FDGA_FDPA_NEW = 3, FDGA_FDPA_1LOOP = 4 };
 
 /* ---- lifecycle ------------------------------------------------------------------------ */
 int  fdga_create(const fdga_dims* dims, int device, fdga_ctx** out);
@@ -157,11 +158,21 @@ int  fdga_bse_K1(fdga_ctx*, int ch, int mfrg);
 int  fdga_bse_K2(fdga_ctx*, int ch, int mfrg);
 /* BSE_K3!(S, Ch, is_mfRG): src/BSE_templates.jl:151-180 -> src/nonlocal_2/BSEa/BSEa_K3.jl:43-128 */
 int  fdga_bse_K3(fdga_ctx*, int ch, int mfrg);
+/* BSE_K1_new!(S, Ch, is_mfRG): src/BSE_templates.jl:188-218 -> src/nonlocal_2/BSEa/BSEa_K1.jl:62-113  (K1 = (U + K1 + K2') Pi U) */
+int  fdga_bse_K1_new(fdga_ctx*, int ch, int mfrg);
+/* BSE_K2_new!(S, Ch, is_mfRG): src/BSE_templates.jl:223-253 -> src/nonlocal_2/BSEa/BSEa_K2.jl:142-216 */
+int  fdga_bse_K2_new(fdga_ctx*, int ch, int mfrg);
+/* BSE_K1_1loop!(S, Ch, is_mfRG): src/BSE_templates.jl:261-291 -> src/nonlocal_2/BSEa/BSE_1loop.jl:2-56 */
+int  fdga_bse_K1_1loop(fdga_ctx*, int ch, int mfrg);
+/* BSE_K2_1loop!(S, Ch, is_mfRG): src/BSE_templates.jl:297-327 -> src/nonlocal_2/BSEa/BSE_1loop.jl:59-124 */
+int  fdga_bse_K2_1loop(fdga_ctx*, int ch, int mfrg);
+/* BSE_K3_1loop!(S, Ch, is_mfRG): src/BSE_templates.jl:332-358 -> src/nonlocal_2/BSEa/BSE_1loop.jl:123-199 */
+int  fdga_bse_K3_1loop(fdga_ctx*, int ch, int mfrg);
 /* set!(S.F, S.Fbuff): src/solve.jl:87 */
 int  fdga_set_F_from_Fbuff(fdga_ctx*);
 /* SDE!(S; strategy, include_U2, include_Hartree): src/SDE.jl:3-48 -> src/nonlocal_2/SDE.jl:154-324 */
 int  fdga_sde(fdga_ctx*, int strategy, int include_U2, int include_Hartree);
-/* iterate_solver!(S; strategy, update_Sigma): src/solve.jl:4-116 (strategies scPA, fdPA) */
+/* iterate_solver!(S; strategy, update_Sigma): src/solve.jl:4-116 (all five strategies) */
 int  fdga_iterate_solver(fdga_ctx*, int strategy, int update_sigma);
 /* mfRGLinearMap matvec: src/mfRG.jl:34-89 (strategy fdPA); first = is_first_iteration */
 int  fdga_mfrg_matvec(fdga_ctx*, const fdga_c64* host_x, fdga_c64* host_y, int first);

@@ -543,6 +543,133 @@ void orc_bse_K2(cplx* K2, int nK2b, int nK2f, const orc_vertex* F0, const orc_ve
     sg_apply(K2, SG, diagram, c0, c1);
 }
 
+// ---- BSE_K1_new!, src/nonlocal_2/BSEa/BSEa_K1.jl:62-113: K1 = (U + K1 + K2') Pi U ------
+// U = bare_vertex(F, Sp) = +U for pSp and dSp (src/refvertex.jl:213-215, src/vertex.jl:340)
+void orc_bse_K1_new(cplx* K1, int nK1, const orc_vertex* F0, const orc_vertex* F,
+                    const cplx* Pi0, const cplx* Pi, const orc_sg* SG, int sign, int Ch, int Sp, int is_mfRG,
+                    const orc_grid* g, int64_t c0, int64_t c1) {
+    int L = g->L, NP = L * L;
+    VertexEval EF0 = {F0, L, NP}, EF = {F, L, NP};
+    int nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF, nB1 = 2 * nK1 - 1;
+    double T = g->T;
+    const orc_level& core = F->lev[F->nlev - 1];
+    cplx U = cplx(core.U_re, core.U_im) * (Sp == xSp ? -1.0 : 1.0);
+    Mom k0 = mk(0, 0);
+    auto diagram = [&](int64_t idx) -> cplx {
+        int W = (int)(idx % nB1) - (nK1 - 1); int iP = (int)(idx / nB1); Mom P = mk(iP % L, iP / L);
+        int iW = posB(W, g->nPiB);
+        cplx val = 0;
+        for (int iq = 0; iq < NP; iq++) for (int iw = 0; iw < nFP; iw++) {
+            int w = iw - g->nPiF; Mom q = mk(iq % L, iq / L);
+            size_t pidx = iW + (size_t)nBP * (iw + (size_t)nFP * (iP + (size_t)NP * iq));
+            cplx Fl  = EF.eval(0, W, INF, w, P, k0, q, Ch, Sp, ALLF());
+            cplx F0l = EF0.eval(0, W, INF, w, P, k0, q, Ch, Sp, ALLF());
+            if (is_mfRG) val += (Fl - F0l) * Pi[pidx] * U;
+            else         val += (Fl * Pi[pidx] - F0l * Pi0[pidx]) * U;
+        }
+        return T * val / (double)NP * (double)sign;
+    };
+    sg_apply(K1, SG, diagram, c0, c1);
+}
+
+// ---- BSE_K2_new!, src/nonlocal_2/BSEa/BSEa_K2.jl:142-216: K2 = (K2 + K3 + ...) Pi U; omega runs over the K2 nu-mesh
+void orc_bse_K2_new(cplx* K2, int nK2b, int nK2f, const orc_vertex* F0, const orc_vertex* F,
+                    const cplx* Pi0, const cplx* Pi, const orc_sg* SG, int sign, int Ch, int Sp, int is_mfRG,
+                    const orc_grid* g, int64_t c0, int64_t c1) {
+    int L = g->L, NP = L * L;
+    VertexEval EF0 = {F0, L, NP}, EF = {F, L, NP};
+    int nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF;
+    K2Shape s = {nK2b, nK2f, NP};
+    double T = g->T;
+    const orc_level& core = F->lev[F->nlev - 1];
+    cplx U = cplx(core.U_re, core.U_im) * (Sp == xSp ? -1.0 : 1.0);
+    auto diagram = [&](int64_t idx) -> cplx {
+        int W, v; Mom P, k; decodeK2(idx, s, L, W, v, P, k);
+        int iW = posB(W, g->nPiB), iP = kidx(P, L);
+        cplx val = 0;
+        for (int iq = 0; iq < NP; iq++) {
+            Mom q = mk(iq % L, iq / L);
+            for (int iw = 0; iw < 2 * nK2f; iw++) {
+                int w = iw - nK2f;
+                size_t pidx = iW + (size_t)nBP * (posF(w, g->nPiF) + (size_t)nFP * (iP + (size_t)NP * iq));
+                cplx Fl  = EF.eval(0, W, v, w, P, k, q, Ch, Sp, ALLF())  - EF.eval(0, W, INF, w, P, k, q, Ch, Sp, ALLF());
+                cplx F0l = EF0.eval(0, W, v, w, P, k, q, Ch, Sp, ALLF()) - EF0.eval(0, W, INF, w, P, k, q, Ch, Sp, ALLF());
+                if (is_mfRG) val += (Fl - F0l) * Pi[pidx] * U;
+                else         val += (Fl * Pi[pidx] - F0l * Pi0[pidx]) * U;
+            }
+        }
+        return T * val / (double)NP * (double)sign;
+    };
+    sg_apply(K2, SG, diagram, c0, c1);
+}
+
+// ---- BSE_K1_1loop!, src/nonlocal_2/BSEa/BSE_1loop.jl:2-56 -------------------------------
+void orc_bse_K1_1loop(cplx* K1, int nK1, const orc_vertex* F0, const orc_vertex* F, const orc_vertex* FL,
+                      const cplx* Pi0, const cplx* Pi, const orc_sg* SG, int sign, int Ch, int Sp, int is_mfRG,
+                      const orc_grid* g, int64_t c0, int64_t c1) {
+    int L = g->L, NP = L * L;
+    VertexEval EF0 = {F0, L, NP}, EF = {F, L, NP}, EFL = {FL, L, NP};
+    int nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF, nB1 = 2 * nK1 - 1;
+    double T = g->T;
+    Mom k0 = mk(0, 0);
+    auto diagram = [&](int64_t idx) -> cplx {
+        int W = (int)(idx % nB1) - (nK1 - 1); int iP = (int)(idx / nB1); Mom P = mk(iP % L, iP / L);
+        int iW = posB(W, g->nPiB);
+        cplx val = 0;
+        for (int iq = 0; iq < NP; iq++) for (int iw = 0; iw < nFP; iw++) {
+            int w = iw - g->nPiF; Mom q = mk(iq % L, iq / L);
+            size_t pidx = iW + (size_t)nBP * (iw + (size_t)nFP * (iP + (size_t)NP * iq));
+            if (is_mfRG) {
+                cplx Fl  = EF0.eval(0, W, INF, w, P, k0, q, Ch, Sp, ALLF());
+                cplx FLr = EFL.eval(0, W, crossingF(W, w, Ch), INF, P, crossingK(P, q, Ch), k0, Ch, Sp, ALLF());
+                val += Fl * Pi0[pidx] * FLr;
+            } else {
+                cplx Fl  = EF.eval(0, W, INF, w, P, k0, q, Ch, Sp, ALLF());
+                cplx F0r = EF0.eval(0, W, crossingF(W, w, Ch), INF, P, crossingK(P, q, Ch), k0, Ch, Sp, ALLF());
+                val += Fl * (Pi[pidx] - Pi0[pidx]) * F0r;
+            }
+        }
+        return T * val / (double)NP * (double)sign;
+    };
+    sg_apply(K1, SG, diagram, c0, c1);
+}
+
+// ---- BSE_K2_1loop!, src/nonlocal_2/BSEa/BSE_1loop.jl:59-124 (SG part only; FL add done by the caller) ----
+void orc_bse_K2_1loop(cplx* K2, int nK2b, int nK2f, const orc_vertex* F0, const orc_vertex* F, const orc_vertex* FL,
+                      const cplx* Pi0, const cplx* Pi, const orc_sg* SG, int sign, int Ch, int Sp, int is_mfRG,
+                      const orc_grid* g, int64_t c0, int64_t c1) {
+    int L = g->L, NP = L * L;
+    VertexEval EF0 = {F0, L, NP}, EF = {F, L, NP}, EFL = {FL, L, NP};
+    int nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF;
+    K2Shape s = {nK2b, nK2f, NP};
+    double T = g->T;
+    Mom k0 = mk(0, 0);
+    auto diagram = [&](int64_t idx) -> cplx {
+        int W, v; Mom P, k; decodeK2(idx, s, L, W, v, P, k);
+        int iW = posB(W, g->nPiB), iP = kidx(P, L);
+        cplx val = 0;
+        for (int iq = 0; iq < NP; iq++) {
+            Mom q = mk(iq % L, iq / L);
+            for (int iw = 0; iw < nFP; iw++) {
+                int w = iw - g->nPiF;
+                size_t pidx = iW + (size_t)nBP * (iw + (size_t)nFP * (iP + (size_t)NP * iq));
+                if (is_mfRG) {
+                    int wc = crossingF(W, w, Ch); Mom qc = crossingK(P, q, Ch);
+                    cplx Fl  = EF0.eval(0, W, v, wc, P, k, qc, Ch, Sp, ALLF()) - EF0.eval(0, W, INF, wc, P, k, qc, Ch, Sp, ALLF());
+                    cplx FLr = EFL.eval(0, W, w, INF, P, q, k0, Ch, Sp, ALLF());
+                    val += Fl * Pi0[pidx] * FLr;
+                } else {
+                    cplx Fl  = EF.eval(0, W, v, w, P, k, q, Ch, Sp, ALLF()) - EF.eval(0, W, INF, w, P, k, q, Ch, Sp, ALLF());
+                    cplx F0r = EF0.eval(0, W, crossingF(W, w, Ch), INF, P, crossingK(P, q, Ch), k0, Ch, Sp, ALLF());
+                    val += Fl * (Pi[pidx] - Pi0[pidx]) * F0r;
+                }
+            }
+        }
+        return T * val / (double)NP * (double)sign;
+    };
+    sg_apply(K2, SG, diagram, c0, c1);
+}
+
 // Pi[W, w, P, kSW] -> mean over the 4th axis (src/nonlocal/swave.jl:91-105)
 static inline cplx pi_sw(const cplx* Pi, const orc_grid* g, int W, int w, int iP) {
     int NP = g->L * g->L, nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF;
@@ -615,6 +742,40 @@ void orc_bse_K3(cplx* K3, int nK3b, int nK3f, const cplx* FLown, const cplx* FLt
         }
         if (Ch == aCh || Ch == pCh) return T * val + FLown[s.at(W, v, vp, iP)];
         return T * val + 2.0 * FLt[s.at(W, v, vp, iP)] - FLa[s.at(W, v, vp, iP)];
+    };
+    sg_apply(K3, SG, diagram);
+}
+
+// ---- BSE_K3_1loop!, src/nonlocal_2/BSEa/BSE_1loop.jl:123-199: no FL.K3 added to the result -----
+void orc_bse_K3_1loop(cplx* K3, int nK3b, int nK3f, const cplx* FLown, const cplx* FLt, const cplx* FLa,
+                      const cplx* cache_G, const cplx* cache_F, const cplx* cache_F0,
+                      const cplx* Pi0, const cplx* Pi, const orc_sg* SG, int sign1, int sign2, int Ch, int is_mfRG,
+                      const orc_grid* g) {
+    int NP = g->L * g->L;
+    K3Shape s = {nK3b, nK3f, NP};
+    double T = g->T;
+    auto diagram = [&](int64_t idx) -> cplx {
+        int W, v, vp, iP; decodeK3(idx, s, W, v, vp, iP);
+        cplx val = 0;
+        for (int iw = 0; iw < s.nF(); iw++) {
+            int w = iw - nK3f;
+            cplx Gs = (Ch == pCh) ? cache_G[s.at(W, w, vp, iP)] : cache_G[s.at(W, vp, w, iP)];
+            cplx Fs = cache_F[s.at(W, v, w, iP)];
+            cplx F0s = cache_F0[s.at(W, w, vp, iP)];
+            cplx P0 = pi_sw(Pi0, g, W, w, iP);
+            cplx P1 = pi_sw(Pi, g, W, w, iP);
+            if (is_mfRG) {
+                val += Fs * P0 * Gs * (double)sign1;
+                int wc = crossingF(W, w, Ch);
+                if (inF(wc, nK3f)) {
+                    if (Ch == aCh || Ch == pCh) val += Fs * P0 * FLown[s.at(W, wc, vp, iP)] * (double)sign2;
+                    else val += Fs * P0 * (2.0 * FLt[s.at(W, wc, vp, iP)] - FLa[s.at(W, wc, vp, iP)]) * (double)sign2;
+                }
+            } else {
+                val += Fs * (P1 - P0) * F0s * (double)sign1;
+            }
+        }
+        return T * val;
     };
     sg_apply(K3, SG, diagram);
 }

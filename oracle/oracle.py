@@ -309,6 +309,68 @@ def BSE_K3(S, ch, is_mfRG=False):
         _tfix(S.Fbuff.γt.K3, S.Fbuff.γa.K3)
 
 
+def BSE_K1_new(S, ch, is_mfRG=False, c0=0, c1=-1):
+    """BSE_K1_new!(S, Ch, is_mfRG): src/BSE_templates.jl:188-218 -> src/nonlocal_2/BSEa/BSEa_K1.jl:62-113"""
+    sign, Sp = _sign_sp(ch)
+    K1 = S.Fbuff.channel(ch).K1
+    lib().orc_bse_K1_new(_p(K1), S.nK1, C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)),
+                         _p(_pi(S, ch, True)), _p(_pi(S, ch, False)), C.byref(sg_struct(S.sg[SG_K1])), sign, ch, Sp, int(is_mfRG),
+                         C.byref(S.grid), C.c_int64(c0), C.c_int64(c1))
+    if ch == tCh:
+        _tfix(S.Fbuff.γt.K1, S.Fbuff.γa.K1)
+
+
+def BSE_K2_new(S, ch, is_mfRG=False, c0=0, c1=-1):
+    """BSE_K2_new!(S, Ch, is_mfRG): src/BSE_templates.jl:223-253 -> src/nonlocal_2/BSEa/BSEa_K2.jl:142-216"""
+    sign, Sp = _sign_sp(ch)
+    K2 = S.Fbuff.channel(ch).K2
+    sg = S.sg[SG_PP2 if ch == pCh else SG_PH2]
+    lib().orc_bse_K2_new(_p(K2), S.nK2[0], S.nK2[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)),
+                         _p(_pi(S, ch, True)), _p(_pi(S, ch, False)), C.byref(sg_struct(sg)), sign, ch, Sp, int(is_mfRG),
+                         C.byref(S.grid), C.c_int64(c0), C.c_int64(c1))
+    if ch == tCh:
+        _tfix(S.Fbuff.γt.K2, S.Fbuff.γa.K2)
+
+
+def BSE_K1_1loop(S, ch, is_mfRG=False, c0=0, c1=-1):
+    """BSE_K1_1loop!(S, Ch, is_mfRG): src/BSE_templates.jl:261-291 -> src/nonlocal_2/BSEa/BSE_1loop.jl:2-56"""
+    sign, Sp = _sign_sp(ch)
+    K1 = S.Fbuff.channel(ch).K1
+    lib().orc_bse_K1_1loop(_p(K1), S.nK1, C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)), C.byref(vertex_struct(S.FL)),
+                           _p(_pi(S, ch, True)), _p(_pi(S, ch, False)), C.byref(sg_struct(S.sg[SG_K1])), sign, ch, Sp, int(is_mfRG),
+                           C.byref(S.grid), C.c_int64(c0), C.c_int64(c1))
+    if ch == tCh:
+        _tfix(S.Fbuff.γt.K1, S.Fbuff.γa.K1)
+
+
+def BSE_K2_1loop(S, ch, is_mfRG=False, c0=0, c1=-1):
+    """BSE_K2_1loop!(S, Ch, is_mfRG): src/BSE_templates.jl:297-327 -> src/nonlocal_2/BSEa/BSE_1loop.jl:59-124"""
+    sign, Sp = _sign_sp(ch)
+    K2 = S.Fbuff.channel(ch).K2
+    sg = S.sg[SG_PP2 if ch == pCh else SG_PH2]
+    lib().orc_bse_K2_1loop(_p(K2), S.nK2[0], S.nK2[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)), C.byref(vertex_struct(S.FL)),
+                           _p(_pi(S, ch, True)), _p(_pi(S, ch, False)), C.byref(sg_struct(sg)), sign, ch, Sp, int(is_mfRG),
+                           C.byref(S.grid), C.c_int64(c0), C.c_int64(c1))
+    if ch == tCh:       # BSE_1loop.jl:114-119
+        K2 += 2 * S.FL.γt.K2
+        K2 += -1 * S.FL.γa.K2
+        _tfix(S.Fbuff.γt.K2, S.Fbuff.γa.K2)
+    else:
+        K2 += S.FL.channel(ch).K2
+
+
+def BSE_K3_1loop(S, ch, is_mfRG=False):
+    """BSE_K3_1loop!(S, Ch, is_mfRG): src/BSE_templates.jl:332-358 -> src/nonlocal_2/BSEa/BSE_1loop.jl:123-199"""
+    cG, cF, cF0, s1, s2 = {aCh: (S.cache_Γa, S.cache_Fa, S.cache_F0a, +1, +1), pCh: (S.cache_Γpx, S.cache_Fp, S.cache_F0p, -1, +1),
+                           tCh: (S.cache_Γt, S.cache_Ft, S.cache_F0t, -1, -1)}[ch]
+    sg = S.sg[SG_PP3 if ch == pCh else SG_PH3]
+    K3 = S.Fbuff.channel(ch).K3
+    lib().orc_bse_K3_1loop(_p(K3), S.nK3[0], S.nK3[1], _p(S.FL.channel(ch).K3), _p(S.FL.γt.K3), _p(S.FL.γa.K3), _p(cG), _p(cF), _p(cF0),
+                           _p(_pi(S, ch, True)), _p(_pi(S, ch, False)), C.byref(sg_struct(sg)), s1, s2, ch, int(is_mfRG), C.byref(S.grid))
+    if ch == tCh:
+        _tfix(S.Fbuff.γt.K3, S.Fbuff.γa.K3)
+
+
 def SDE_channel_L(S, Lout, Π, V, level, is_pp, c0=0, c1=-1):
     sg = S.sg[SG_PP2 if is_pp else SG_PH2]
     lib().orc_sde_L(_p(Lout), S.nK2[0], S.nK2[1], C.byref(vertex_struct(V)), level, _p(Π), C.byref(sg_struct(sg)), int(is_pp),
@@ -355,7 +417,7 @@ def SDE(S, strategy="scPA", include_U2=True, include_Hartree=True):
     """SDE!(S; strategy): src/SDE.jl:3-33"""
     S.Σ[...] = 0
     _SDE_chain(S, S.Σ, S.G, S.Πpp, S.Πph, S.F, 0, include_U2, include_Hartree)
-    if strategy == "fdPA":
+    if strategy in ("fdPA", "fdPA_new", "fdPA_1loop"):
         Σ0part = _SDE_chain(S, zeros(S.Σ.shape), S.G0, S.Π0pp, S.Π0ph, S.F, 1, include_U2, include_Hartree)
         S.Σ += -1 * Σ0part
         S.Σ += S.Σ0
@@ -366,21 +428,41 @@ def SDE(S, strategy="scPA", include_U2=True, include_Hartree=True):
 
 def iterate_solver(S, strategy="fdPA", update_Σ=True):
     """iterate_solver!(S; strategy, update_Σ): src/solve.jl:4-116"""
+    assert strategy in ("fdPA", "scPA", "scPA_new", "fdPA_new", "fdPA_1loop"), "Calculation strategy unknown"
+    order = (pCh, aCh, tCh)
     if update_Σ:
         Dyson(S)
         bubbles(S)
     build_K3_cache(S)
-    if strategy == "fdPA":
-        for ch in (pCh, aCh, tCh):
-            BSE_L_K2(S, ch)
-        for ch in (pCh, aCh, tCh):
-            BSE_L_K3(S, ch)
-    for ch in (pCh, aCh, tCh):
-        BSE_K1(S, ch)
-    for ch in (pCh, aCh, tCh):
-        BSE_K2(S, ch)
-    for ch in (pCh, aCh, tCh):
-        BSE_K3(S, ch)
+    if strategy in ("fdPA_new", "scPA_new"):          # src/solve.jl:26-45
+        if strategy == "fdPA_new":
+            for ch in order:
+                BSE_L_K3(S, ch)
+        for ch in order:
+            BSE_K3(S, ch)
+        for ch in order:
+            BSE_K1_new(S, ch)
+        for ch in order:
+            BSE_K2_new(S, ch)
+    elif strategy == "fdPA_1loop":                    # src/solve.jl:47-58
+        for ch in order:
+            BSE_K3_1loop(S, ch)
+        for ch in order:
+            BSE_K1_1loop(S, ch)
+        for ch in order:
+            BSE_K2_1loop(S, ch)
+    else:
+        if strategy == "fdPA":
+            for ch in order:
+                BSE_L_K2(S, ch)
+            for ch in order:
+                BSE_L_K3(S, ch)
+        for ch in order:
+            BSE_K1(S, ch)
+        for ch in order:
+            BSE_K2(S, ch)
+        for ch in order:
+            BSE_K3(S, ch)
     S.F.set(S.Fbuff)
     if update_Σ:
         SDE(S, strategy)

@@ -165,6 +165,56 @@ def test_iterate_solver_fused(orc, strategy):
     S.close()
 
 
+@pytest.mark.parametrize("sym,pa,mfrg", [(True, False, False), (False, False, False), (True, True, False), (True, False, True)])
+def test_bse_variant_kernels_stepwise(orc, sym, pa, mfrg):
+    """BSE_K{1,2}_new!, BSE_K{1,2,3}_1loop! (src/solve.jl:26-58 order), each compared with the oracle after the call;
+    FL is non-trivial (left by a preceding L stage) so that the 1-loop FL adds and the mfRG branches are exercised."""
+    import fddgasolver_jl_b200 as fd
+    S, R = make_pair(orc, nmax=2, nq=3, LG=6, sym=sym, pa=pa)
+    order = (fd.pCh, fd.aCh, fd.tCh)
+    if mfrg:
+        fd.build_K3_cache_mfRG(S, True); orc.build_K3_cache_mfRG(R, True)
+    else:
+        fd.build_K3_cache(S); orc.build_K3_cache(R)
+    for ch in order:
+        fd.BSE_L_K2(S, ch); orc.BSE_L_K2(R, ch)
+    for ch in order:
+        fd.BSE_L_K3(S, ch); orc.BSE_L_K3(R, ch)
+    for fg, fo in ((fd.BSE_K3_1loop, orc.BSE_K3_1loop), (fd.BSE_K1_1loop, orc.BSE_K1_1loop), (fd.BSE_K2_1loop, orc.BSE_K2_1loop)):
+        for ch in order:
+            fg(S, ch, mfrg); fo(R, ch, mfrg)
+    S.pull("Fbuff")
+    compare_vertex(S.Fbuff, R.Fbuff, "Fbuff(1loop)")
+    for fg, fo in ((fd.BSE_K1_new, orc.BSE_K1_new), (fd.BSE_K2_new, orc.BSE_K2_new)):
+        for ch in order:
+            fg(S, ch, mfrg); fo(R, ch, mfrg)
+    S.pull("Fbuff")
+    compare_vertex(S.Fbuff, R.Fbuff, "Fbuff(new)", ("K1", "K2"))
+    S.close()
+
+
+@pytest.mark.parametrize("strategy", ["scPA_new", "fdPA_new", "fdPA_1loop"])
+def test_iterate_solver_variant_strategies(orc, strategy):
+    """iterate_solver!(S; strategy = :scPA_new / :fdPA_new / :fdPA_1loop) fused in the library, two iterations with Σ update"""
+    import fddgasolver_jl_b200 as fd
+    S, R = make_pair(orc, nmax=2, nq=3, LG=6)
+    for _ in range(2):
+        fd.iterate_solver(S, strategy, True); orc.iterate_solver(R, strategy, True)
+    S.pull("F", "Σ", "G")
+    compare_vertex(S.F, R.F, "F")
+    assert rel(S.Σ, R.Σ) < TOL and rel(S.G, R.G) < TOL
+    # the call-by-call sequence gives the same state as the fused driver
+    S2, _ = make_pair(orc, nmax=2, nq=3, LG=6)
+    for _ in range(2):
+        fd.iterate_solver_stepwise(S2, strategy, True)
+    S2.pull("F", "Σ")
+    compare_vertex(S2.F, S.F, "stepwise vs fused")
+    assert rel(S2.Σ, S.Σ) < TOL
+    with pytest.raises(AssertionError):
+        fd.iterate_solver(S, "no_such_strategy", True)
+    S.close(); S2.close()
+
+
 def test_flatten_unflatten_roundtrip(orc):
     import fddgasolver_jl_b200 as fd
     S, R = make_pair(orc, nmax=2, nq=3, LG=6)
