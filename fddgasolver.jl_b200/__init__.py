@@ -10,6 +10,7 @@ from .types import (pCh, tCh, aCh, pSp, xSp, dSp, Channel, NL2_Channel, RefVerte
 from .models import hubbard_bare_Green, hubbard_band, siam_bare_Green  # noqa: F401
 from .solver import (NL2_ParquetSolver, ParquetSolver, init_sym_grp, Dyson, compute_occupation, bubbles, bubbles_real_space,  # noqa: F401
                      bubbles_momentum_space, build_K3_cache, build_K3_cache_mfRG, BSE_L_K2, BSE_L_K3, BSE_K1,
-                     BSE_K2, BSE_K3, BSE_K1_new, BSE_K2_new, BSE_K1_1loop, BSE_K2_1loop, BSE_K3_1loop, SDE, iterate_solver, iterate_solver_stepwise, fixed_point, mfRGLinearMap)
+                     BSE_K2, BSE_K3, BSE_K1_new, BSE_K2_new, BSE_K1_1loop, BSE_K2_1loop, BSE_K3_1loop, SDE, iterate_solver, iterate_solver_stepwise, fixed_point, mfRGLinearMap,
+                     dqgmres, symmetrize_solver, fixed_point_preconditioned)
 from .synthetic import (parquet_solver_hubbard_parquet_approximation_NL2, parquet_solver_siam_parquet_approximation, synthetic_local_vertex,  # noqa: F401
                         wu_point_solver, wu_point_inputs, randomize_vertex)

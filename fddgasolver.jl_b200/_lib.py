@@ -22,7 +22,7 @@ PI0PP, PI0PH, PIPP, PIPH = 0, 1, 2, 3
 SG_SIGMA, SG_K1, SG_PP2, SG_PH2, SG_PP3, SG_PH3, SG_PPL3, SG_PHL3 = range(8)
 SCPA, FDPA, SCPA_NEW, FDPA_NEW, FDPA_1LOOP = 0, 1, 2, 3, 4
 T_NAMES = ["cache", "L_K2", "L_K3", "K1", "K2", "K3", "sde_L", "sde_rs", "sde_U2", "bubble",
-           "right", "swave", "expand", "misc", "comm", "column_K2"]
+           "right", "swave", "expand", "misc", "comm", "column_K2", "krylov"]
 
 # every symbol include/fdga.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
@@ -34,7 +34,8 @@ EXPORTS = [
     "fdga_bubbles_momentum_space", "fdga_bubbles_local", "fdga_build_K3_cache", "fdga_bse_L_K2", "fdga_bse_L_K3", "fdga_bse_K1",
     "fdga_bse_K2", "fdga_bse_K3", "fdga_bse_K1_new", "fdga_bse_K2_new", "fdga_bse_K1_1loop", "fdga_bse_K2_1loop", "fdga_bse_K3_1loop",
     "fdga_set_F_from_Fbuff", "fdga_sde", "fdga_iterate_solver",
-    "fdga_mfrg_matvec", "fdga_profile_enable", "fdga_profile_reset", "fdga_kernel_time_ms",
+    "fdga_mfrg_matvec", "fdga_mfrg_matvec_strategy", "fdga_mfrg_dqgmres", "fdga_symmetrize_solver", "fdga_fixed_point_preconditioned",
+    "fdga_profile_enable", "fdga_profile_reset", "fdga_kernel_time_ms",
     "fdga_total_launches", "fdga_stream",
 ]
 
@@ -109,6 +110,10 @@ def load():
     lib.fdga_sde.argtypes = [vp, i32, i32, i32]
     lib.fdga_iterate_solver.argtypes = [vp, i32, i32]
     lib.fdga_mfrg_matvec.argtypes = [vp, vp, vp, i32]
+    lib.fdga_mfrg_matvec_strategy.argtypes = [vp, vp, vp, i32, i32]
+    lib.fdga_mfrg_dqgmres.argtypes = [vp, vp, vp, i32, i32, dbl, dbl, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(dbl), i32]
+    lib.fdga_symmetrize_solver.argtypes = [vp]
+    lib.fdga_fixed_point_preconditioned.argtypes = [vp, vp, vp, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.fdga_profile_enable.argtypes = [vp, i32]
     lib.fdga_profile_reset.argtypes = [vp]
     lib.fdga_kernel_time_ms.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(i64)]

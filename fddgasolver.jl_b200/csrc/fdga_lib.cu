@@ -3,6 +3,7 @@
 // SDE! (src/SDE.jl:3-48), mfRGLinearMap (src/mfRG.jl:34-89).
 #include "../../include/fdga.h"
 #include "fdga_column.cuh"
+#include "fdga_krylov.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -107,6 +108,8 @@ struct fdga_ctx {
     C* twL; C* twLG;         // DFT twiddles exp(2 pi i j / n) for n = L, LG
     LevelBuf Fsum; bool has_fsum, fsum_dirty;   // K tables of lev[0] + lev[1] when both are NL2 on identical meshes
     int4* d_slabs[4]; int n_slabs[4]; bool slabs_dirty;   // active (W,P) slabs: [pp|ph] x [bubble mesh | K2 mesh]
+    // device-resident DQGMRES workspace (fdga_mfrg_dqgmres): rings of `kry_mem` basis / direction vectors, work vector, iterate
+    C* kryV; C* kryP; C* kryW; C* kryX; C* kryH; C* kryPart; unsigned int* kryTicket; C* kryHhost; int kry_mem;
     C* Rt3[3]; int rt_kind[3]; // per-channel right factors (W on the bubble mesh) reused between BSE_K1! and BSE_K2!
     std::string err;
 };
@@ -541,6 +544,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
     cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->Rt); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB);
     cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
+    cudaFree(ctx->kryV); cudaFree(ctx->kryP); cudaFree(ctx->kryW); cudaFree(ctx->kryX); cudaFree(ctx->kryH); cudaFree(ctx->kryPart); cudaFree(ctx->kryTicket); if (ctx->kryHhost) cudaFreeHost(ctx->kryHhost);
     cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); for (int i = 0; i < 3; i++) { cudaFree(ctx->TtabL[i]); cudaFree(ctx->OwnTabL[i]); cudaFree(ctx->RtotL[i]); cudaFree(ctx->ConvTabL[i]); if (i) cudaFree(ctx->RtL[i]); } cudaFree(ctx->SigR2); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) cudaFree(ctx->d_slabs[i]);
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); for (int k = 0; k < 3; k++) cudaFree(s.d_rep[k]);
         cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); cudaFree(s.d_grp_start); }
@@ -1442,19 +1446,244 @@ int fdga_iterate_solver(fdga_ctx* ctx, int strategy, int update_sigma) {
     return 0;
 }
 
-int fdga_mfrg_matvec(fdga_ctx* ctx, const fdga_c64* host_x, fdga_c64* host_y, int first) {
-    CK(cudaSetDevice(ctx->device));
+// mfRGLinearMap(S, strategy) * x on DEVICE vectors (src/mfRG.jl:34-89): y = x - flatten(BSE_lin(factor * x)) / factor.
+// x_dev and y_dev may alias.  strategy: fdPA / fdPA_1loop (identical maps, src/mfRG.jl:51) or fdPA_new.
+static int mfrg_matvec_dev(fdga_ctx* ctx, const C* x_dev, C* y_dev, int first, int strategy) {
     const double factor = 1e-2;                                  // src/mfRG.jl:37
-    CK(cudaMemcpyAsync(ctx->flat2, host_x, ctx->lenFlat * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
-    if (unflatten_dev(ctx, ctx->lev[0], ctx->flat2, factor)) return 1;
+    if (strategy != FDGA_FDPA && strategy != FDGA_FDPA_NEW && strategy != FDGA_FDPA_1LOOP)
+        FAIL("mfRGLinearMap: Invalid strategy. Must be fdPA or fdPA_new or fdPA_1loop.");      // src/mfRG.jl:26-28
+    if (unflatten_dev(ctx, ctx->lev[0], x_dev, factor)) return 1;
     if (fdga_build_K3_cache(ctx, 1, first)) return 1;
-    if (bse_stages(ctx, true, 1)) return 1;
+    if (strategy == FDGA_FDPA_NEW) {                             // src/mfRG.jl:65-83; L_K3 only reads caches and bubbles
+        ctx->defer = true;
+        int rc = bse_stage(ctx, bse_L_K3_stage_fn, 0);
+        if (!rc) rc = bse_stage(ctx, fdga_bse_K1_new, 1);
+        if (!rc) rc = bse_stage(ctx, fdga_bse_K2_new, 1);
+        if (!rc) rc = bse_stage(ctx, fdga_bse_K3, 1);
+        ctx->defer = false; ctx->pending.clear();
+        if (rc) return 1;
+    } else if (bse_stages(ctx, true, 1)) return 1;
     if (fdga_set_F_from_Fbuff(ctx)) return 1;
-    if (flatten_dev(ctx, ctx->lev[0], ctx->flat)) return 1;
-    LAUNCH(FDGA_T_MISC, mfrg_residual_kernel, nblk(ctx->lenFlat, 256), 256, ctx->flat, ctx->flat2, ctx->flat, factor, (long long)ctx->lenFlat);
+    LAUNCH(FDGA_T_MISC, mfrg_residual_kernel, nblk(ctx->lenFlat, 256), 256, y_dev, x_dev, ctx->lev[0].block, factor, (long long)ctx->lenFlat);
     CK(cudaGetLastError());
+    return 0;
+}
+int fdga_mfrg_matvec_strategy(fdga_ctx* ctx, const fdga_c64* host_x, fdga_c64* host_y, int first, int strategy) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->flat2, host_x, ctx->lenFlat * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    if (mfrg_matvec_dev(ctx, ctx->flat2, ctx->flat, first, strategy)) return 1;
     CK(cudaMemcpyAsync(host_y, ctx->flat, ctx->lenFlat * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int fdga_mfrg_matvec(fdga_ctx* ctx, const fdga_c64* host_x, fdga_c64* host_y, int first) {
+    return fdga_mfrg_matvec_strategy(ctx, host_x, host_y, first, FDGA_FDPA);
+}
+
+// ---- DQGMRES on the device (Saad & Wu 1996; the reference calls Krylov.dqgmres, src/mfRG.jl:147-151) ----------------
+static int kry_alloc(fdga_ctx* ctx, int memory) {
+    const size_t n = ctx->lenFlat;
+    if (!ctx->kryW) {
+        CK(cudaMalloc(&ctx->kryW, n * sizeof(C))); CK(cudaMalloc(&ctx->kryX, n * sizeof(C)));
+        CK(cudaMalloc(&ctx->kryPart, FDGA_KRY_BLOCKS * sizeof(C))); CK(cudaMalloc(&ctx->kryTicket, sizeof(unsigned int)));
+        CK(cudaMemset(ctx->kryTicket, 0, sizeof(unsigned int)));
+    }
+    if (memory > ctx->kry_mem) {
+        cudaFree(ctx->kryV); cudaFree(ctx->kryP); cudaFree(ctx->kryH); if (ctx->kryHhost) cudaFreeHost(ctx->kryHhost);
+        ctx->kryV = ctx->kryP = ctx->kryH = ctx->kryHhost = nullptr; ctx->kry_mem = 0;
+        CK(cudaMalloc(&ctx->kryV, (size_t)memory * n * sizeof(C)));
+        CK(cudaMalloc(&ctx->kryP, (size_t)memory * n * sizeof(C)));
+        CK(cudaMalloc(&ctx->kryH, (size_t)(memory + 2) * sizeof(C)));
+        CK(cudaMallocHost(&ctx->kryHhost, (size_t)(memory + 2) * sizeof(C)));
+        ctx->kry_mem = memory;
+    }
+    return 0;
+}
+struct cd { double re, im; };
+static inline cd cmul(cd a, cd b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+static inline cd cadd(cd a, cd b) { return {a.re + b.re, a.im + b.im}; }
+static inline cd cconj(cd a) { return {a.re, -a.im}; }
+static inline cd cscale(cd a, double s) { return {a.re * s, a.im * s}; }
+static inline double cabs_(cd a) { return hypot(a.re, a.im); }
+// complex Givens rotation [c s; -conj(s) c] [a; b] = [rho; 0], c real, b real >= 0
+static void sym_givens(cd a, double b, double& c, cd& s, cd& rho) {
+    if (b == 0.0) { c = 1.0; s = {0.0, 0.0}; rho = a; return; }
+    const double aa = cabs_(a);
+    if (aa == 0.0) { c = 0.0; s = {1.0, 0.0}; rho = {b, 0.0}; return; }
+    const double t = hypot(aa, b);
+    const cd ph = cscale(a, 1.0 / aa);
+    c = aa / t; s = cscale(ph, b / t); rho = cscale(ph, t);
+}
+#define KRY_MGS(vsub, hsub, vdot, outp) do { \
+    kry_mgs_kernel<<<FDGA_KRY_BLOCKS, FDGA_KRY_THREADS, 0, ctx->stream>>>(ctx->kryW, vsub, hsub, vdot, outp, ctx->kryPart, ctx->kryTicket, (long long)n); \
+    ctx->n_launch[FDGA_T_KRYLOV]++; ctx->total_launches++; } while (0)
+
+// x_dev <- approximate solution of A x = b_dev (x0 = 0); b_dev is overwritten.  Vectors never leave the device.
+static int dqgmres_dev(fdga_ctx* ctx, C* b_dev, C* x_dev, int strategy, int memory, double atol, double rtol, int itmax,
+                       int* niter, int* solved, double* residuals, int nres) {
+    const size_t n = ctx->lenFlat;
+    if (memory < 1) FAIL("fdga_mfrg_dqgmres: memory must be >= 1");
+    if (itmax <= 0) itmax = 2 * (int)std::min<size_t>(n, 1u << 20);
+    if (kry_alloc(ctx, memory)) return 1;
+    const int k = memory;
+    C* V = ctx->kryV; C* P = ctx->kryP; C* Hd = ctx->kryH; cd* Hh = reinterpret_cast<cd*>(ctx->kryHhost);
+    auto Vs = [&](int m) { return V + (size_t)((m - 1) % k) * n; };     // v_m, m = 1, 2, ...
+    auto Ps = [&](int m) { return P + (size_t)((m - 1) % k) * n; };
+    std::vector<double> cs(k); std::vector<cd> sn(k);                    // rotation i in slot (i - 1) % k
+    *niter = 0; *solved = 0;
+    CK(cudaMemsetAsync(x_dev, 0, n * sizeof(C), ctx->stream));
+    // beta = ||b||
+    CK(cudaMemcpyAsync(ctx->kryW, b_dev, n * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+    {
+        Scope sc(ctx, FDGA_T_KRYLOV);
+        KRY_MGS(nullptr, nullptr, nullptr, Hd);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(Hh, Hd, sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double beta = sqrt(Hh[0].re);
+    int nr = 0;
+    if (residuals && nr < nres) residuals[nr++] = beta;
+    if (beta == 0.0) { *solved = 1; return 0; }
+    const double eps = atol + rtol * beta;
+    {
+        Scope sc(ctx, FDGA_T_KRYLOV);
+        LAUNCH(FDGA_T_KRYLOV, scale_copy_kernel, nblk(n, 256), 256, Vs(1), ctx->kryW, 1.0 / beta, (long long)n);
+        CK(cudaGetLastError());
+    }
+    cd gamma = {beta, 0.0};
+    std::vector<cd> t(k + 3);
+    bool first = true;
+    for (int m = 1; m <= itmax; ++m) {
+        if (mfrg_matvec_dev(ctx, Vs(m), ctx->kryW, first ? 1 : 0, strategy)) return 1;     // w = A v_m
+        first = false;
+        const int lo = std::max(1, m - k + 1), cnt = m - lo + 1;
+        {   // incomplete modified Gram-Schmidt against v_lo .. v_m, then ||w||^2: cnt + 1 fused launches, no host sync
+            Scope sc(ctx, FDGA_T_KRYLOV);
+            KRY_MGS(nullptr, nullptr, Vs(lo), Hd);
+            for (int j = 1; j < cnt; ++j) KRY_MGS(Vs(lo + j - 1), Hd + (j - 1), Vs(lo + j), Hd + j);
+            KRY_MGS(Vs(m), Hd + (cnt - 1), nullptr, Hd + cnt);
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemcpyAsync(Hh, Hd, (size_t)(cnt + 1) * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const double hnext = sqrt(std::max(0.0, Hh[cnt].re));
+        // column m of the Hessenberg matrix: rows plo .. m (+ hnext at m + 1); row m - k lies outside the window (zero)
+        const int plo = std::max(1, m - k);
+        int off = 0;
+        if (plo < lo) { t[0] = {0.0, 0.0}; off = 1; }
+        for (int j = 0; j < cnt; ++j) t[off + j] = Hh[j];                  // t[i - plo], i = plo .. m
+        for (int i = plo; i < m; ++i) {                                    // previous rotations on rows (i, i + 1)
+            const cd ti = t[i - plo], tj = t[i + 1 - plo];
+            const double c = cs[(i - 1) % k]; const cd s = sn[(i - 1) % k];
+            t[i - plo] = cadd(cscale(ti, c), cmul(s, tj));
+            t[i + 1 - plo] = cadd(cscale(cmul(cconj(s), ti), -1.0), cscale(tj, c));
+        }
+        double c; cd s, rmm;
+        sym_givens(t[m - plo], hnext, c, s, rmm);
+        cs[(m - 1) % k] = c; sn[(m - 1) % k] = s;
+        const cd gamma_next = cscale(cmul(cconj(s), gamma), -1.0);
+        gamma = cscale(gamma, c);
+        {   // p_m = (v_m - sum_{i = plo}^{m-1} t_i p_i) / r_mm ;  x += gamma_m p_m.  p_m takes the ring slot of p_{m-k}, which is
+            // still an input: the kernel is elementwise (each thread reads its element of every slot before writing), and
+            // p_{m-k} is the first coefficient of the first chunk, so later chunks only see the accumulated value.
+            Scope sc(ctx, FDGA_T_KRYLOV);
+            const double r2 = rmm.re * rmm.re + rmm.im * rmm.im;
+            const C inv_r = mkC(rmm.re / r2, -rmm.im / r2), gm = mkC(gamma.re, gamma.im);
+            const int np = m - plo;                                        // number of previous directions
+            C* dst = Ps(m);
+            int done = 0;
+            do {
+                KryCoefs cf; cf.nc = std::min(FDGA_KRY_CHUNK, np - done);
+                for (int j = 0; j < cf.nc; ++j) { const int i = plo + done + j; cf.slot[j] = (i - 1) % k; cf.t[j] = mkC(t[i - plo].re, t[i - plo].im); }
+                const int last = (done + cf.nc >= np) ? 1 : 0;
+                LAUNCH(FDGA_T_KRYLOV, kry_direction_kernel, FDGA_KRY_BLOCKS, FDGA_KRY_THREADS, dst, done == 0 ? (const C*)Vs(m) : (const C*)dst, (const C*)P, (long long)n, cf, last, inv_r, gm, x_dev);
+                done += cf.nc;
+            } while (done < np);
+            CK(cudaGetLastError());
+        }
+        gamma = gamma_next;
+        const double rnorm = cabs_(gamma);
+        *niter = m;
+        if (residuals && nr < nres) residuals[nr++] = rnorm;
+        if (rnorm <= eps) { *solved = 1; break; }
+        if (hnext == 0.0 || m == itmax) break;
+        {   // v_{m+1} = w / h_{m+1,m} into the ring slot of v_{m-k+1} (outside the next window)
+            Scope sc(ctx, FDGA_T_KRYLOV);
+            LAUNCH(FDGA_T_KRYLOV, scale_copy_kernel, nblk(n, 256), 256, Vs(m + 1), ctx->kryW, 1.0 / hnext, (long long)n);
+            CK(cudaGetLastError());
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+// Krylov.dqgmres(mfRGLinearMap(S, strategy), b; atol, rtol, itmax, memory): src/mfRG.jl:147-151.  b and x are host vectors of
+// length(S.F); they cross PCIe once each.  residuals (may be NULL) receives ||b|| and the residual estimate of every iteration.
+int fdga_mfrg_dqgmres(fdga_ctx* ctx, const fdga_c64* host_b, fdga_c64* host_x, int strategy, int memory, double atol, double rtol,
+                      int itmax, int* niter, int* solved, double* residuals, int nres) {
+    CK(cudaSetDevice(ctx->device));
+    int it = 0, ok = 0;
+    if (kry_alloc(ctx, memory)) return 1;
+    CK(cudaMemcpyAsync(ctx->flat2, host_b, ctx->lenFlat * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    if (dqgmres_dev(ctx, ctx->flat2, ctx->kryX, strategy, memory, atol, rtol, itmax, &it, &ok, residuals, nres)) return 1;
+    CK(cudaMemcpyAsync(host_x, ctx->kryX, ctx->lenFlat * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (niter) *niter = it;
+    if (solved) *solved = ok;
+    return 0;
+}
+
+// symmetrize_solver!(S): src/ParquetSolver.jl:246-259 (Sigma with SG_Sigma, every channel's K1 / K2 / K3 with its group)
+int fdga_symmetrize_solver(fdga_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    if (wait_copy(ctx)) return 1;
+    Scope sc(ctx, FDGA_T_MISC);
+    auto sym = [&](int which, C* f) -> int {
+        SymGroup& g = ctx->sg[which];
+        if (!g.nmem) return 0;
+        LAUNCH(FDGA_T_MISC, symmetrize_kernel, nblk(g.nmem, 256), 256, f, sym_dev(g));
+        return 0;
+    };
+    sym(FDGA_SG_SIGMA, ctx->G[FDGA_SIGMA]);
+    for (int ch = 0; ch < 3; ch++) {
+        const bool pp = ch == FDGA_PCH;
+        sym(FDGA_SG_K1, ctx->lev[0].K[ch][0]);
+        sym(pp ? FDGA_SG_PP2 : FDGA_SG_PH2, ctx->lev[0].K[ch][1]);
+        sym(pp ? FDGA_SG_PP3 : FDGA_SG_PH3, ctx->lev[0].K[ch][2]);
+    }
+    CK(cudaGetLastError());
+    ctx->lev[0].sw_dirty = true; ctx->lev[0].k1h_dirty = true; ctx->fsum_dirty = true;
+    return 0;
+}
+
+// fixed_point_preconditioned!(R, x, S; strategy, update_Sigma = false, use_preconditioner, krylov_maxiter): src/mfRG.jl:93-171
+//   unflatten!(S.F, x); symmetrize_solver!(S); iterate_solver!(S; strategy, update_Sigma = false);
+//   R_F = flatten(S.F) - x;  R = use_preconditioner ? dqgmres(mfRGLinearMap(S, strategy), R_F; atol = rtol = 1e-6, memory) : R_F
+// As in the reference, S.F is left holding the last Krylov vector (the caller unflattens its own iterate next).
+int fdga_fixed_point_preconditioned(fdga_ctx* ctx, const fdga_c64* host_x, fdga_c64* host_R, int strategy, int use_preconditioner,
+                                    int krylov_maxiter, int memory, int* niter, int* solved) {
+    CK(cudaSetDevice(ctx->device));
+    if (strategy != FDGA_FDPA && strategy != FDGA_FDPA_NEW && strategy != FDGA_FDPA_1LOOP)
+        FAIL("fdga_fixed_point_preconditioned: strategy must be fdPA, fdPA_new or fdPA_1loop");
+    const size_t n = ctx->lenFlat;
+    int it = 0, ok = 1;
+    if (kry_alloc(ctx, std::max(1, memory))) return 1;
+    CK(cudaMemcpyAsync(ctx->flat2, host_x, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    if (unflatten_dev(ctx, ctx->lev[0], ctx->flat2, 1.0)) return 1;
+    if (fdga_symmetrize_solver(ctx)) return 1;
+    if (fdga_iterate_solver(ctx, strategy, 0)) return 1;
+    // R_F = flatten(S.F) - x   (flat2 <- R_F)
+    LAUNCH(FDGA_T_MISC, axpby_kernel, nblk(n, 256), 256, ctx->flat2, (const C*)ctx->lev[0].block, 1.0, (const C*)ctx->flat2, -1.0, (long long)n);
+    CK(cudaGetLastError());
+    const C* result = ctx->flat2;
+    if (use_preconditioner) {
+        if (dqgmres_dev(ctx, ctx->flat2, ctx->kryX, strategy, memory, 1e-6, 1e-6, krylov_maxiter, &it, &ok, nullptr, 0)) return 1;
+        result = ctx->kryX;
+    }
+    CK(cudaMemcpyAsync(host_R, result, n * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (niter) *niter = it;
+    if (solved) *solved = ok;
     return 0;
 }
 

@@ -454,12 +454,13 @@ def fixed_point(R, x, S, strategy="fdPA", update_Σ=True):
 
 
 class mfRGLinearMap:
-    """mfRGLinearMap(S, :fdPA): y = x - BSE_lin(1e-2 x)/1e-2 (src/mfRG.jl:20-89)"""
+    """mfRGLinearMap(S, strategy): y = x - BSE_lin(1e-2 x)/1e-2 (src/mfRG.jl:20-89)"""
 
     def __init__(self, S, strategy="fdPA"):
-        if strategy != "fdPA":
-            raise ValueError("only strategy fdPA is implemented")
+        if strategy not in ("fdPA", "fdPA_new", "fdPA_1loop"):
+            raise ValueError(f"Invalid strategy {strategy}. Must be fdPA or fdPA_new or fdPA_1loop.")    # src/mfRG.jl:26-28
         self.S = S
+        self.strategy = strategy
         self.is_first_iteration = True
         n = S.length_F()
         self.shape = (n, n)
@@ -470,6 +471,39 @@ class mfRGLinearMap:
     def matvec(self, x):
         x = np.ascontiguousarray(x, dtype=np.complex128)
         y = np.empty_like(x)
-        self.S._call("fdga_mfrg_matvec", L.ptr(x), L.ptr(y), int(self.is_first_iteration))
+        self.S._call("fdga_mfrg_matvec_strategy", L.ptr(x), L.ptr(y), int(self.is_first_iteration), STRATEGY[self.strategy])
         self.is_first_iteration = False
         return y
+
+
+def dqgmres(A, b, *, memory=20, atol=1e-6, rtol=1e-6, itmax=0, history=True):
+    """Krylov.dqgmres(A::mfRGLinearMap, b; atol, rtol, itmax, memory) as called at src/mfRG.jl:147-151, device resident:
+    returns (x, stats) with stats = dict(niter, solved, residuals)."""
+    if not isinstance(A, mfRGLinearMap):
+        raise TypeError("dqgmres: A must be an mfRGLinearMap (the device-resident Krylov solver is tied to this operator)")
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    x = np.empty_like(b)
+    niter, solved = C.c_int(0), C.c_int(0)
+    nres = (itmax if itmax > 0 else 4096) + 1
+    res = np.zeros(nres, dtype=np.float64)
+    A.S._call("fdga_mfrg_dqgmres", L.ptr(b), L.ptr(x), STRATEGY[A.strategy], int(memory), float(atol), float(rtol), int(itmax),
+              C.byref(niter), C.byref(solved), res.ctypes.data_as(C.POINTER(C.c_double)), nres)
+    A.is_first_iteration = False
+    return x, {"niter": niter.value, "solved": bool(solved.value), "residuals": res[: min(nres, niter.value + 1)].tolist()}
+
+
+def symmetrize_solver(S):
+    """symmetrize_solver!(S): src/ParquetSolver.jl:246-259 (on the device state)"""
+    S._call("fdga_symmetrize_solver")
+
+
+def fixed_point_preconditioned(R, x, S, *, strategy="fdPA", use_preconditioner=True, krylov_maxiter=400, memory=100):
+    """fixed_point_preconditioned!(R, x, S; strategy, update_Σ = false): src/mfRG.jl:93-171.  One call: unflatten, symmetrise,
+    iterate_solver!, residual and the DQGMRES preconditioning all stay on the device.  Returns (niter, solved) of the Krylov solve."""
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    out = np.empty_like(x)
+    niter, solved = C.c_int(0), C.c_int(0)
+    S._call("fdga_fixed_point_preconditioned", L.ptr(x), L.ptr(out), STRATEGY[strategy], int(use_preconditioner), int(krylov_maxiter), int(memory),
+            C.byref(niter), C.byref(solved))
+    R[: x.size] = out
+    return niter.value, bool(solved.value)

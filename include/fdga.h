@@ -177,13 +177,30 @@ int  fdga_iterate_solver(fdga_ctx*, int strategy, int update_sigma);
 /* mfRGLinearMap matvec: src/mfRG.jl:34-89 (strategy fdPA); first = is_first_iteration */
 int  fdga_mfrg_matvec(fdga_ctx*, const fdga_c64* host_x, fdga_c64* host_y, int first);
 
+/* mfRGLinearMap(S, strategy) matvec: src/mfRG.jl:20-89; strategy FDGA_FDPA, FDGA_FDPA_1LOOP (same map) or FDGA_FDPA_NEW */
+int  fdga_mfrg_matvec_strategy(fdga_ctx*, const fdga_c64* host_x, fdga_c64* host_y, int first, int strategy);
+/* Krylov.dqgmres(mfRGLinearMap(S, strategy), b; atol, rtol, itmax, memory) as called at src/mfRG.jl:147-151, with the Krylov
+ * basis, the direction vectors and the iterate resident in HBM: b and x cross PCIe once.  x0 = 0, no
+ * preconditioner, modified Gram-Schmidt over the last `memory` vectors; stop when the quasi-residual estimate
+ * <= atol + rtol ||b|| (solved = 1) or after itmax iterations (itmax <= 0: 2 n).  residuals may be NULL; otherwise it receives
+ * ||b|| and then one estimate per iteration (at most nres entries). */
+int  fdga_mfrg_dqgmres(fdga_ctx*, const fdga_c64* host_b, fdga_c64* host_x, int strategy, int memory, double atol, double rtol,
+                       int itmax, int* niter, int* solved, double* residuals, int nres);
+/* symmetrize_solver!(S): src/ParquetSolver.jl:246-259 */
+int  fdga_symmetrize_solver(fdga_ctx*);
+/* fixed_point_preconditioned!(R, x, S; strategy, update_Sigma = false, use_preconditioner, krylov_maxiter): src/mfRG.jl:93-171
+ * (the function nlsolve iterates in solve_using_mfRG!, src/mfRG.jl:287); memory = 100 and atol = rtol = 1e-6 in the reference */
+int  fdga_fixed_point_preconditioned(fdga_ctx*, const fdga_c64* host_x, fdga_c64* host_R, int strategy, int use_preconditioner,
+                                     int krylov_maxiter, int memory, int* niter, int* solved);
+
 /* ---- introspection --------------------------------------------------------------------- */
 /* accumulated device time (CUDA events on the launching stream) and launch counts per kernel id */
 enum { FDGA_T_CACHE = 0, FDGA_T_L_K2 = 1, FDGA_T_L_K3 = 2, FDGA_T_K1 = 3, FDGA_T_K2 = 4, FDGA_T_K3 = 5,
        FDGA_T_SDE_L = 6, FDGA_T_SDE_RS = 7, FDGA_T_SDE_U2 = 8, FDGA_T_BUBBLE = 9, FDGA_T_RIGHT = 10,
        FDGA_T_SWAVE = 11, FDGA_T_EXPAND = 12, FDGA_T_MISC = 13, FDGA_T_COMM = 14,
        FDGA_T_COLUMN_K2 = 15,   /* the column_kernel launches of BSE_K2! alone (a sub-interval of FDGA_T_K2) */
-       FDGA_T_COUNT = 16 };
+       FDGA_T_KRYLOV = 16,      /* vector kernels of fdga_mfrg_dqgmres (orthogonalisation sweep, direction / iterate update) */
+       FDGA_T_COUNT = 17 };
 int  fdga_profile_enable(fdga_ctx*, int on);
 int  fdga_profile_reset(fdga_ctx*);
 int  fdga_kernel_time_ms(fdga_ctx*, int kernel_id, double* ms, int64_t* launches);

@@ -468,12 +468,45 @@ def iterate_solver(S, strategy="fdPA", update_Σ=True):
         SDE(S, strategy)
 
 
+def symmetrize_solver(S):
+    """symmetrize_solver!(S): src/ParquetSolver.jl:246-259"""
+    def sym(which, a):
+        lib().orc_symmetrize(_p(a), C.byref(sg_struct(S.sg[which])))
+    sym(SG_SIGMA, S.Σ)
+    for ch in (aCh, pCh, tCh):
+        g = S.F.channel(ch)
+        sym(SG_K1, g.K1)
+        sym(SG_PP2 if ch == pCh else SG_PH2, g.K2)
+        sym(SG_PP3 if ch == pCh else SG_PH3, g.K3)
+
+
+def fixed_point_preconditioned(R, x, S, *, strategy="fdPA", use_preconditioner=True, krylov_maxiter=400, memory=100):
+    """fixed_point_preconditioned!(R, x, S; strategy, update_Σ = false): src/mfRG.jl:93-171"""
+    nF_ = len(S.F)
+    S.F.unflatten(np.asarray(x[:nF_]))
+    symmetrize_solver(S)
+    iterate_solver(S, strategy, False)
+    R_F = S.F.flatten() - x[:nF_]
+    stats = {"niter": 0, "solved": True}
+    if use_preconditioner:
+        xsol, stats = dqgmres(mfRGLinearMap(S, strategy), R_F, atol=1e-6, rtol=1e-6, itmax=krylov_maxiter, memory=memory)
+        R[:nF_] = xsol
+    else:
+        R[:nF_] = R_F
+    return stats["niter"], stats["solved"]
+
+
 class mfRGLinearMap:
     """src/mfRG.jl:20-89"""
 
-    def __init__(self, S):
+    def __init__(self, S, strategy="fdPA"):
+        if strategy not in ("fdPA", "fdPA_new", "fdPA_1loop"):
+            raise ValueError(f"Invalid strategy {strategy}. Must be fdPA or fdPA_new or fdPA_1loop.")      # src/mfRG.jl:26-28
         self.S = S
+        self.strategy = strategy
         self.is_first_iteration = True
+        n = len(S.F)
+        self.shape = (n, n)
 
     def matvec(self, x):
         S = self.S
@@ -481,19 +514,99 @@ class mfRGLinearMap:
         S.F.unflatten(np.asarray(x) * factor)
         build_K3_cache_mfRG(S, self.is_first_iteration)
         self.is_first_iteration = False
-        for ch in (pCh, aCh, tCh):
-            BSE_L_K2(S, ch)
-        for ch in (pCh, aCh, tCh):
-            BSE_K1(S, ch, True)
-        for ch in (pCh, aCh, tCh):
-            BSE_K2(S, ch, True)
-        for ch in (pCh, aCh, tCh):
+        order = (pCh, aCh, tCh)
+        if self.strategy in ("fdPA", "fdPA_1loop"):        # src/mfRG.jl:51-64
+            for ch in order:
+                BSE_L_K2(S, ch)
+            for ch in order:
+                BSE_K1(S, ch, True)
+            for ch in order:
+                BSE_K2(S, ch, True)
+        else:                                              # :fdPA_new, src/mfRG.jl:65-74
+            for ch in order:
+                BSE_K1_new(S, ch, True)
+            for ch in order:
+                BSE_K2_new(S, ch, True)
+        for ch in order:
             BSE_L_K3(S, ch)
-        for ch in (pCh, aCh, tCh):
+        for ch in order:
             BSE_K3(S, ch, True)
         S.F.set(S.Fbuff)
         y = S.F.flatten()
         return x - y / factor
+
+    __matmul__ = matvec
+
+
+def sym_givens(a, b):
+    """Complex Givens rotation [c s; -conj(s) c] [a; b] = [rho; 0] with real c (b real, >= 0)."""
+    if b == 0:
+        return 1.0, 0.0 + 0.0j, a
+    if a == 0:
+        return 0.0, 1.0 + 0.0j, b + 0.0j
+    t = np.hypot(abs(a), b)
+    ph = a / abs(a)
+    return abs(a) / t, ph * b / t, ph * t
+
+
+def dqgmres(A, b, *, memory=20, atol=1e-6, rtol=1e-6, itmax=0):
+    """DQGMRES (Saad & Wu, "DQGMRES: a direct quasi-minimal residual algorithm based on incomplete orthogonalization",
+    Numer. Linear Algebra Appl. 3 (1996) 329): the solver the reference calls as Krylov.dqgmres(mfRGLinearMap(S, strategy), R_F;
+    atol = 1e-6, rtol = 1e-6, itmax, memory = 100) (src/mfRG.jl:147-151; Krylov.jl is a dependency, not in the tree).
+    No preconditioner, x0 = 0, modified Gram-Schmidt over the last `memory` Krylov vectors; the residual estimate of the
+    stopping test |gamma_{m+1}| <= atol + rtol * ||b|| is the quasi-residual norm.  Returns (x, stats)."""
+    b = np.asarray(b, dtype=np.complex128)
+    n = b.size
+    itmax = itmax if itmax > 0 else 2 * n
+    x = np.zeros(n, dtype=np.complex128)
+    beta = float(np.linalg.norm(b))
+    stats = {"niter": 0, "solved": beta == 0.0, "residuals": [beta]}
+    if beta == 0.0:
+        return x, stats
+    eps = atol + rtol * beta
+    k = int(memory)
+    V, P, c, s = {}, {}, {}, {}
+    V[1] = b / beta
+    gamma = beta + 0.0j
+    for m in range(1, itmax + 1):
+        w = np.asarray(A.matvec(V[m]), dtype=np.complex128).copy()
+        lo = max(1, m - k + 1)
+        t = {}
+        for i in range(lo, m + 1):
+            t[i] = np.vdot(V[i], w)
+            w -= t[i] * V[i]
+        hnext = float(np.linalg.norm(w))
+        plo = max(1, m - k)
+        if plo < lo:
+            t[plo] = 0.0 + 0.0j
+        tn = {m + 1: hnext + 0.0j}
+        for i in range(plo, m):                   # previous rotations on rows (i, i + 1)
+            ti, tj = t[i], t[i + 1]
+            t[i] = c[i] * ti + s[i] * tj
+            t[i + 1] = -np.conj(s[i]) * ti + c[i] * tj
+        c[m], s[m], rmm = sym_givens(t[m], hnext)
+        gamma_next = -np.conj(s[m]) * gamma
+        gamma = c[m] * gamma
+        p = V[m].copy()
+        for i in range(plo, m):
+            p -= t[i] * P[i]
+        p /= rmm
+        P[m] = p
+        x += gamma * p
+        gamma = gamma_next
+        rnorm = abs(gamma)
+        stats["niter"] = m
+        stats["residuals"].append(rnorm)
+        if rnorm <= eps:
+            stats["solved"] = True
+            break
+        if hnext == 0.0:
+            break
+        V[m + 1] = w / hnext
+        V.pop(m - k + 1, None)                    # iteration m + 1 orthogonalises against V[m-k+2 .. m+1] ...
+        for d in (P, c, s):                       # ... and uses P, c, s of m-k+1 .. m
+            d.pop(m - k, None)
+    return x, stats
 
 
 # ================================================================================================ local solver
