@@ -903,6 +903,10 @@ static int launch_slab_conv(fdga_ctx* ctx, const DevChain& V, ColJob& job, int k
     const size_t budget = 200 * 1024;
     auto bytes = [&](int tw) { return ((size_t)2 * g.NP * (tw | 1) + (size_t)nF2 * g.NP + g.L) * sizeof(C); };
     int TW = std::max(job.nw, nF2);
+    // narrow win tiles keep the slab's shared memory small, so that every slab CTA of the launch is resident at once (config 3:
+    // 404 slabs, 76 KB -> 2 CTAs/SM = 1.36 waves with one 32-wide tile; 8-wide tiles -> 6 CTAs/SM, one wave, +4 % per step)
+    static const int tw_cap = getenv("FDGA_CONV_TW") ? atoi(getenv("FDGA_CONV_TW")) : 8;      // tuning knob (tile width in win)
+    if (tw_cap > 0) TW = std::min(TW, std::max(nF2, tw_cap));
     while (TW > nF2 && bytes(TW) > budget) TW = std::max(nF2, (TW + 1) / 2);
     if (bytes(TW) > budget) { job.k1_direct = 1; return 0; }
     if (refresh_k1h(ctx)) return 1;
