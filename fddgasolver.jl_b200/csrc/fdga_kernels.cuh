@@ -625,6 +625,37 @@ __global__ void occupation_kernel(const C* __restrict__ G, long long n, double T
     acc = block_reduce(acc);
     if (threadIdx.x == 0) *occ = 0.5 + acc.y * T / Nk;
 }
+// ---- hubbard_bare_Green: src/models/hubbard.jl:8-44.  Stored quantity is i*G0 = i / (i nu + mu - eps_k) ----------------
+__device__ __forceinline__ C hubbard_bare_entry(int n, int ik, int LG, double T, double mu, double t1, double t2, double t3) {
+    const int ix = ik % LG, iy = ik / LG;
+    const double k1 = 2.0 * M_PI * ix / LG, k2 = 2.0 * M_PI * iy / LG;
+    double ek = -2.0 * t1 * (cos(k1) + cos(k2)); ek += -4.0 * t2 * cos(k1) * cos(k2); ek += -2.0 * t3 * (cos(2.0 * k1) + cos(2.0 * k2));
+    const double nu = (2 * n + 1) * M_PI * T, re = mu - ek;        // 1 / (re + i nu) * i = (nu + i re) / (re^2 + nu^2)
+    const double d = re * re + nu * nu;
+    return mkC(nu / d, re / d);
+}
+__global__ void hubbard_bare_green_kernel(C* __restrict__ G, int nG, int LG, double T, double mu, double t1, double t2, double t3) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n = (long long)2 * nG * LG * LG;
+    if (i >= n) return;
+    G[i] = hubbard_bare_entry((int)(i % (2 * nG)) - nG, (int)(i / (2 * nG)), LG, T, mu, t1, t2, t3);
+}
+// occupation(mu) of compute_hubbard_chemical_potential (src/dyson.jl:45-57): Gbare(mu) -> Dyson -> compute_occupation, fused;
+// single CTA, deterministic
+__global__ void occupation_mu_kernel(const C* __restrict__ Sigma, int nG, int LG, double T, double mu, double t1, double t2, double t3,
+                                     double* occ) {
+    const long long n = (long long)2 * nG * LG * LG;
+    C acc = zeroC();
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const C gb = hubbard_bare_entry((int)(i % (2 * nG)) - nG, (int)(i / (2 * nG)), LG, T, mu, t1, t2, t3);
+        const double d = gb.x * gb.x + gb.y * gb.y;
+        const C inv = mkC(gb.x / d, -gb.y / d) + Sigma[i];
+        const double e = inv.x * inv.x + inv.y * inv.y;
+        acc += mkC(inv.x / e, -inv.y / e);
+    }
+    acc = block_reduce(acc);
+    if (threadIdx.x == 0) *occ = 0.5 + acc.y * T / ((double)LG * LG);
+}
 // Sigma += sgn * i (n - 1/2) U    (Hartree, src/nonlocal_2/SDE.jl:317-321, src/SDE.jl:19-23)
 __global__ void hartree_kernel(C* __restrict__ Sigma, const double* occ, C U, double sgn, long long n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;

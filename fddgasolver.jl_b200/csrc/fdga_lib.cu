@@ -110,6 +110,7 @@ struct fdga_ctx {
     int4* d_slabs[4]; int n_slabs[4]; bool slabs_dirty;   // active (W,P) slabs: [pp|ph] x [bubble mesh | K2 mesh]
     // device-resident DQGMRES workspace (fdga_mfrg_dqgmres): rings of `kry_mem` basis / direction vectors, work vector, iterate
     C* kryV; C* kryP; C* kryW; C* kryX; C* kryH; C* kryPart; unsigned int* kryTicket; C* kryHhost; int kry_mem;
+    C* PiMixed[2];           // Pipp_mixed, Piph_mixed of solve_using_mfRG! (fdga_mix_bubbles / fdga_update_reference)
     C* Rt3[3]; int rt_kind[3]; // per-channel right factors (W on the bubble mesh) reused between BSE_K1! and BSE_K2!
     std::string err;
 };
@@ -544,6 +545,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
     cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->Rt); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB);
     cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
+    cudaFree(ctx->PiMixed[0]); cudaFree(ctx->PiMixed[1]);
     cudaFree(ctx->kryV); cudaFree(ctx->kryP); cudaFree(ctx->kryW); cudaFree(ctx->kryX); cudaFree(ctx->kryH); cudaFree(ctx->kryPart); cudaFree(ctx->kryTicket); if (ctx->kryHhost) cudaFreeHost(ctx->kryHhost);
     cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); for (int i = 0; i < 3; i++) { cudaFree(ctx->TtabL[i]); cudaFree(ctx->OwnTabL[i]); cudaFree(ctx->RtotL[i]); cudaFree(ctx->ConvTabL[i]); if (i) cudaFree(ctx->RtL[i]); } cudaFree(ctx->SigR2); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) cudaFree(ctx->d_slabs[i]);
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); for (int k = 0; k < 3; k++) cudaFree(s.d_rep[k]);
@@ -791,6 +793,45 @@ int fdga_occupation(fdga_ctx* ctx, int which, double* occ) {
     if (occupation_dev(ctx, which)) return 1;
     CK(cudaMemcpyAsync(occ, ctx->d_occ, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+// set!(S.Gbare, hubbard_bare_Green(meshes(S.Gbare)...; mu, t1, t2, t3)): src/models/hubbard.jl:8-29
+int fdga_set_hubbard_bare_green(fdga_ctx* ctx, double mu, double t1, double t2, double t3) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->opt_local) FAIL("fdga_set_hubbard_bare_green: lattice model only (the local solver uses siam_bare_Green on the host)");
+    Scope sc(ctx, FDGA_T_MISC);
+    LAUNCH(FDGA_T_MISC, hubbard_bare_green_kernel, nblk(ctx->lenG, 256), 256, ctx->G[FDGA_GBARE], ctx->dims.nG, ctx->g.LG, ctx->g.T, mu, t1, t2, t3);
+    CK(cudaGetLastError());
+    return 0;
+}
+// compute_hubbard_chemical_potential(occ_target, S.Sigma, (; t1, t2, t3)): src/dyson.jl:45-57.  Roots.find_zero on the bracket
+// (-4|t1|, 4|t1|) = bisection down to neighbouring floating-point numbers; occupation(mu) is one fused kernel per evaluation.
+int fdga_hubbard_chemical_potential(fdga_ctx* ctx, double occ_target, double t1, double t2, double t3, double* mu_out) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->opt_local) FAIL("fdga_hubbard_chemical_potential: lattice model only");
+    auto f = [&](double mu, double& val) -> int {
+        double occ = 0.0;
+        LAUNCH(FDGA_T_MISC, occupation_mu_kernel, 1, 1024, ctx->G[FDGA_SIGMA], ctx->dims.nG, ctx->g.LG, ctx->g.T, mu, t1, t2, t3, ctx->d_occ);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&occ, ctx->d_occ, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        val = occ - occ_target;
+        return 0;
+    };
+    double a = -4.0 * fabs(t1), b = 4.0 * fabs(t1), fa, fb;
+    if (f(a, fa) || f(b, fb)) return 1;
+    if (fa == 0.0) { *mu_out = a; return 0; }
+    if (fb == 0.0) { *mu_out = b; return 0; }
+    if ((fa < 0.0) == (fb < 0.0) || fa != fa || fb != fb)
+        FAIL("fdga_hubbard_chemical_potential: the interval [-4|t1|, 4|t1|] is not a bracketing interval (occupation target out of reach)");
+    for (int it = 0; it < 200; ++it) {
+        const double m = a + 0.5 * (b - a);
+        if (m <= a || m >= b) break;                  // a and b are neighbouring floats
+        double fm; if (f(m, fm)) return 1;
+        if (fm == 0.0) { a = b = m; break; }
+        if ((fm < 0.0) == (fa < 0.0)) { a = m; fa = fm; } else { b = m; fb = fm; }
+    }
+    *mu_out = (fabs(fa) <= fabs(fb)) ? a : b;
     return 0;
 }
 int fdga_bubbles_real_space(fdga_ctx* ctx, int reference) {
@@ -1688,6 +1729,49 @@ int fdga_fixed_point_preconditioned(fdga_ctx* ctx, const fdga_c64* host_x, fdga_
     CK(cudaStreamSynchronize(ctx->stream));
     if (niter) *niter = it;
     if (solved) *solved = ok;
+    return 0;
+}
+
+// ---- outer loop of solve_using_mfRG! (src/mfRG.jl:217-372): the state updates between two vertex solves, on the device ----
+// Pi_mixed = mixing * Pi + (1 - mixing) * Pi0 ; set!(S.Pi, Pi_mixed)   (src/mfRG.jl:271-276).  The mixed bubbles are kept for
+// fdga_update_reference.
+int fdga_mix_bubbles(fdga_ctx* ctx, double mixing) {
+    CK(cudaSetDevice(ctx->device));
+    for (int i = 0; i < 2; i++) if (!ctx->PiMixed[i]) CK(cudaMalloc(&ctx->PiMixed[i], ctx->lenPi * sizeof(C)));
+    Scope sc(ctx, FDGA_T_MISC);
+    const int pi[2] = {FDGA_PIPP, FDGA_PIPH}, pi0[2] = {FDGA_PI0PP, FDGA_PI0PH};
+    for (int i = 0; i < 2; i++) {
+        LAUNCH(FDGA_T_MISC, axpby_kernel, nblk(ctx->lenPi, 256), 256, ctx->PiMixed[i], (const C*)ctx->Pi[pi[i]], mixing, (const C*)ctx->Pi[pi0[i]], 1.0 - mixing, (long long)ctx->lenPi);
+        CK(cudaMemcpyAsync(ctx->Pi[pi[i]], ctx->PiMixed[i], ctx->lenPi * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->pi_dirty[pi[i]] = true;
+    }
+    CK(cudaGetLastError());
+    invalidate_rt(ctx);
+    return 0;
+}
+// "Update reference Green function, bubble, and self-energy; update reference vertex and reset target vertex" (src/mfRG.jl:336-347):
+//   set!(S.Pi0pp, Pipp_mixed); set!(S.Pi0ph, Piph_mixed); set!(S.G0, S.G); set!(S.Sigma0, S.Sigma); add!(S.F0, S.F); set!(S.F, 0)
+int fdga_update_reference(fdga_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->PiMixed[0]) FAIL("fdga_update_reference: call fdga_mix_bubbles first");
+    if (ctx->nlev < 2 || ctx->lev[1].d.type != FDGA_LV_NL2 || ctx->lev[1].blocklen != ctx->lev[0].blocklen)
+        FAIL("fdga_update_reference: add!(S.F0, S.F) needs S.F0 to be an NL2_Vertex on the meshes of S.F");
+    if (wait_copy(ctx)) return 1;
+    Scope sc(ctx, FDGA_T_MISC);
+    const int pi0[2] = {FDGA_PI0PP, FDGA_PI0PH};
+    for (int i = 0; i < 2; i++) {
+        CK(cudaMemcpyAsync(ctx->Pi[pi0[i]], ctx->PiMixed[i], ctx->lenPi * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->pi_dirty[pi0[i]] = true;
+    }
+    CK(cudaMemcpyAsync(ctx->G[FDGA_G0], ctx->G[FDGA_G], ctx->lenG * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->G[FDGA_SIGMA0], ctx->G[FDGA_SIGMA], ctx->lenG * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+    const long long n = (long long)ctx->lev[0].blocklen;
+    LAUNCH(FDGA_T_MISC, add_axpby_kernel, nblk(n, 256), 256, ctx->lev[1].block, (const C*)ctx->lev[0].block, 1.0, (const C*)nullptr, 0.0, n);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(ctx->lev[0].block, 0, (size_t)n * sizeof(C), ctx->stream));
+    for (int l = 0; l < 2; l++) { ctx->lev[l].sw_dirty = true; ctx->lev[l].k1h_dirty = true; }
+    ctx->fsum_dirty = true;
+    invalidate_rt(ctx);
     return 0;
 }
 

@@ -171,6 +171,10 @@ class NL2_ParquetSolver:
         for n in names:
             if n == "F":
                 self._vertex_io(0, self.F, False)
+            elif n == "F0":            # K tables of the reference chain (e.g. after add!(S.F0, S.F)); the core never changes
+                for i, V in enumerate(self._chain[1:], start=1):
+                    if not isinstance(V, RefVertex):
+                        self._vertex_io(i, V, False)
             elif n == "FL":
                 self._vertex_io(L.V_FL, self.FL, False)
             elif n == "Fbuff":
@@ -336,6 +340,19 @@ def compute_occupation(S, which="G"):
     occ = C.c_double(0)
     S._call("fdga_occupation", _G_NAMES[which], C.byref(occ))
     return occ.value
+
+
+def set_hubbard_bare_Green(S, *, μ, t1, t2=0.0, t3=0.0):
+    """set!(S.Gbare, hubbard_bare_Green(meshes(S.Gbare)...; μ, hubbard_params...)) on the device (src/mfRG.jl:113, 355)"""
+    S._call("fdga_set_hubbard_bare_green", float(μ), float(t1), float(t2), float(t3))
+
+
+def compute_hubbard_chemical_potential(occ_target, S, hubbard_params):
+    """compute_hubbard_chemical_potential(occ_target, S.Σ, hubbard_params): src/dyson.jl:45-57, Σ = the device copy of S.Σ"""
+    mu = C.c_double(0.0)
+    S._call("fdga_hubbard_chemical_potential", float(occ_target), float(hubbard_params["t1"]), float(hubbard_params.get("t2", 0.0)),
+            float(hubbard_params.get("t3", 0.0)), C.byref(mu))
+    return mu.value
 
 
 def bubbles(S):
@@ -507,3 +524,62 @@ def fixed_point_preconditioned(R, x, S, *, strategy="fdPA", use_preconditioner=T
             C.byref(niter), C.byref(solved))
     R[: x.size] = out
     return niter.value, bool(solved.value)
+
+
+def mix_bubbles(S, mixing):
+    S._call("fdga_mix_bubbles", float(mixing))
+
+
+def update_reference(S):
+    S._call("fdga_update_reference")
+
+
+def solve_using_mfRG(S, *, maxiter=100, verbose=False, occ_target=None, hubbard_params=None, mixing_init=1.0, tol=1e-4,
+                     strategy="fdPA", anderson_iterations=40, anderson_m=50, krylov_maxiter=400, memory=100, debug_single_iter=False):
+    """solve_using_mfRG!(S; maxiter, occ_target, hubbard_params, mixing_init, tol, strategy): src/mfRG.jl:217-372 (adaptive mixing of
+    the target bubble, vertex solve by Anderson iteration of the DQGMRES-preconditioned fixed point, SDE, reference update).
+    Everything between two vertex solves stays on the device; checkpoint files / restart are not mirrored.  Returns a dict with the
+    history (mixing, Σ error, μ per accepted iteration)."""
+    from .nlsolve import anderson
+    mixing, it = float(mixing_init), 0
+    hist = {"mixing": [], "Σ_err": [], "μ": [], "anderson_iterations": [], "converged": False}
+    for _ in range(maxiter):
+        it += 1
+        mix_bubbles(S, mixing)                                                   # :271-276
+        nF_ = S.length_F()
+
+        def fp(x):
+            R = np.empty(nF_, dtype=np.complex128)
+            fixed_point_preconditioned(R, x, S, strategy=strategy, krylov_maxiter=krylov_maxiter, memory=memory)
+            return R
+        res = anderson(fp, S.flatten_F(), m=anderson_m, beta=0.85, ftol=tol, iterations=anderson_iterations, show_trace=verbose)   # :287-294
+        hist["anderson_iterations"].append(res.iterations)
+        if debug_single_iter:
+            S.unflatten_F(res.zero)
+            return hist
+        if not res.f_converged:                                                  # :300-308
+            mixing /= 2.0
+            it -= 1
+            bubbles(S)
+            continue
+        used = mixing
+        mixing = min(1.0, mixing * 1.2)                                          # :310
+        S.unflatten_F(res.zero)
+        S._call("fdga_bubbles_real_space", 1)                                    # restore the unmixed bubbles for the SDE, :318-319
+        S._call("fdga_bubbles_real_space", 0)
+        SDE(S, "scPA")                                                           # :323
+        S.pull("Σ", "Σ0")
+        Σ_err = float(np.max(np.abs(S.Σ - S.Σ0))) / mixing                       # :324 (the reference divides by the UPDATED mixing)
+        update_reference(S)                                                      # :328-347
+        if occ_target is not None:                                               # :350-355
+            μ = compute_hubbard_chemical_potential(occ_target, S, hubbard_params)
+            set_hubbard_bare_Green(S, μ=μ, **hubbard_params)
+            hist["μ"].append(μ)
+        Dyson(S)                                                                 # :357-358
+        bubbles(S)
+        hist["mixing"].append(used)
+        hist["Σ_err"].append(Σ_err)
+        if Σ_err < tol:                                                          # :377-379
+            hist["converged"] = True
+            break
+    return hist

@@ -140,6 +140,12 @@ int  fdga_unstash_F(fdga_ctx*);
 int  fdga_dyson(fdga_ctx*);
 /* compute_occupation(G): src/dyson.jl:39-41; which = FDGA_G or FDGA_G0 */
 int  fdga_occupation(fdga_ctx*, int which, double* occ);
+/* set!(S.Gbare, hubbard_bare_Green(meshes(S.Gbare)...; mu, t1, t2, t3)) evaluated on the device: src/models/hubbard.jl:8-44 */
+int  fdga_set_hubbard_bare_green(fdga_ctx*, double mu, double t1, double t2, double t3);
+/* compute_hubbard_chemical_potential(occ_target, S.Sigma, hubbard_params): src/dyson.jl:45-57 (bracket -4|t1| .. 4|t1|, bisection to
+ * neighbouring floats as Roots.find_zero does; one fused Gbare(mu) -> Dyson -> occupation kernel per evaluation).  Fails when the
+ * bracket does not contain the target occupation. */
+int  fdga_hubbard_chemical_potential(fdga_ctx*, double occ_target, double t1, double t2, double t3, double* mu);
 /* bubbles_real_space!(Pipp, Piph, G): src/nonlocal_2/bubble.jl:42-122; reference != 0 -> (Pi0, G0) */
 int  fdga_bubbles_real_space(fdga_ctx*, int reference);
 /* bubbles!(Pipp, Piph, G) of the local solver: src/bubble.jl:9-36 (nq = LG = 1) */
@@ -192,6 +198,12 @@ int  fdga_symmetrize_solver(fdga_ctx*);
  * (the function nlsolve iterates in solve_using_mfRG!, src/mfRG.jl:287); memory = 100 and atol = rtol = 1e-6 in the reference */
 int  fdga_fixed_point_preconditioned(fdga_ctx*, const fdga_c64* host_x, fdga_c64* host_R, int strategy, int use_preconditioner,
                                      int krylov_maxiter, int memory, int* niter, int* solved);
+
+/* State updates of the outer loop of solve_using_mfRG! (src/mfRG.jl:217-372), device resident:
+ * fdga_mix_bubbles:      Pi_mixed = mixing * Pi + (1 - mixing) * Pi0;  set!(S.Pi, Pi_mixed)                       (:271-276)
+ * fdga_update_reference: set!(S.Pi0, Pi_mixed); set!(S.G0, S.G); set!(S.Sigma0, S.Sigma); add!(S.F0, S.F); set!(S.F, 0) (:336-347) */
+int  fdga_mix_bubbles(fdga_ctx*, double mixing);
+int  fdga_update_reference(fdga_ctx*);
 
 /* ---- introspection --------------------------------------------------------------------- */
 /* accumulated device time (CUDA events on the launching stream) and launch counts per kernel id */

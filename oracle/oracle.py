@@ -206,6 +206,42 @@ def hubbard_bare_Green(T, nG, LG, *, μ, t1, t2=0.0, t3=0.0):
     return G
 
 
+def compute_hubbard_chemical_potential(occ_target, S, hubbard_params):
+    """compute_hubbard_chemical_potential(occ_target, Σ, hubbard_params): src/dyson.jl:45-57; Roots.find_zero on a bracket =
+    bisection down to neighbouring floating-point numbers."""
+    t1, t2, t3 = hubbard_params["t1"], hubbard_params.get("t2", 0.0), hubbard_params.get("t3", 0.0)
+
+    class Tmp:
+        pass
+    tmp = Tmp()
+    tmp.Σ, tmp.G = S.Σ, np.zeros_like(S.Σ)
+
+    def f(μ):
+        tmp.Gbare = hubbard_bare_Green(S.T, S.nG, S.LG, μ=μ, t1=t1, t2=t2, t3=t3)
+        Dyson(tmp)
+        return compute_occupation(S, tmp.G) - occ_target
+    a, b = -4 * abs(t1), 4 * abs(t1)
+    fa, fb = f(a), f(b)
+    if fa == 0:
+        return a
+    if fb == 0:
+        return b
+    if (fa < 0) == (fb < 0):
+        raise ValueError("The interval [a,b] is not a bracketing interval")
+    for _ in range(200):
+        m = a + 0.5 * (b - a)
+        if m <= a or m >= b:
+            break
+        fm = f(m)
+        if fm == 0:
+            return m
+        if (fm < 0) == (fa < 0):
+            a, fa = m, fm
+        else:
+            b, fb = m, fm
+    return a if abs(fa) <= abs(fb) else b
+
+
 def bubbles_real_space(S, Πpp, Πph, G):
     lib().orc_bubbles_real_space(_p(Πpp), _p(Πph), _p(G), S.nG, S.LG, C.byref(S.grid))
 
@@ -494,6 +530,82 @@ def fixed_point_preconditioned(R, x, S, *, strategy="fdPA", use_preconditioner=T
     else:
         R[:nF_] = R_F
     return stats["niter"], stats["solved"]
+
+
+def _anderson(fixed_point, x0, *, m=50, beta=0.85, ftol=1e-4, iterations=40):
+    """nlsolve(...; method = :anderson) stand-in (same update rule as the product's host driver, written out independently)"""
+    x = np.array(x0, dtype=np.complex128, copy=True)
+    Xs, Rs = [], []
+    err = np.inf
+    for it in range(1, iterations + 1):
+        R = np.asarray(fixed_point(x))
+        err = float(np.max(np.abs(R)))
+        if err <= ftol:
+            return x, True, it
+        Xs.append(x.copy()); Rs.append(R.copy())
+        if len(Xs) > m + 1:
+            Xs.pop(0); Rs.pop(0)
+        if len(Xs) == 1:
+            x = x + beta * R
+        else:
+            dR = np.stack([Rs[i + 1] - Rs[i] for i in range(len(Rs) - 1)], axis=1)
+            dX = np.stack([Xs[i + 1] - Xs[i] for i in range(len(Xs) - 1)], axis=1)
+            gamma, *_ = np.linalg.lstsq(dR, R, rcond=None)
+            x = x + beta * R - (dX + beta * dR) @ gamma
+    return x, False, iterations
+
+
+def solve_using_mfRG(S, *, maxiter=100, occ_target=None, hubbard_params=None, mixing_init=1.0, tol=1e-4, strategy="fdPA",
+                     anderson_iterations=40, anderson_m=50, krylov_maxiter=400, memory=100):
+    """solve_using_mfRG!(S; ...): src/mfRG.jl:217-372 on the oracle's host arrays (no checkpoint files)"""
+    mixing, it = float(mixing_init), 0
+    hist = {"mixing": [], "Σ_err": [], "μ": [], "anderson_iterations": [], "converged": False}
+    for _ in range(maxiter):
+        it += 1
+        Πpp_mixed = S.Πpp * mixing + S.Π0pp * (1 - mixing)
+        Πph_mixed = S.Πph * mixing + S.Π0ph * (1 - mixing)
+        S.Πpp[...] = Πpp_mixed
+        S.Πph[...] = Πph_mixed
+        nF_ = len(S.F)
+
+        def fp(x):
+            R = np.empty(nF_, dtype=np.complex128)
+            fixed_point_preconditioned(R, x, S, strategy=strategy, krylov_maxiter=krylov_maxiter, memory=memory)
+            return R
+        zero, ok, nit = _anderson(fp, S.F.flatten(), m=anderson_m, beta=0.85, ftol=tol, iterations=anderson_iterations)
+        hist["anderson_iterations"].append(nit)
+        if not ok:
+            mixing /= 2.0
+            it -= 1
+            bubbles(S)
+            continue
+        used = mixing
+        mixing = min(1.0, mixing * 1.2)
+        S.F.unflatten(zero)
+        bubbles_real_space(S, S.Π0pp, S.Π0ph, S.G0)
+        bubbles_real_space(S, S.Πpp, S.Πph, S.G)
+        SDE(S, "scPA")
+        Σ_err = float(np.max(np.abs(S.Σ - S.Σ0))) / mixing
+        S.Π0pp[...] = Πpp_mixed
+        S.Π0ph[...] = Πph_mixed
+        S.G0[...] = S.G
+        S.Σ0[...] = S.Σ
+        for g0, g in zip(S.F0.channels(), S.F.channels()):        # add!(S.F0, S.F); set!(S.F, 0)
+            for a0, a in zip(g0.arrays(), g.arrays()):
+                a0 += a
+                a[...] = 0
+        if occ_target is not None:
+            μ = compute_hubbard_chemical_potential(occ_target, S, hubbard_params)
+            S.Gbare[...] = hubbard_bare_Green(S.T, S.nG, S.LG, μ=μ, **hubbard_params)
+            hist["μ"].append(μ)
+        Dyson(S)
+        bubbles(S)
+        hist["mixing"].append(used)
+        hist["Σ_err"].append(Σ_err)
+        if Σ_err < tol:
+            hist["converged"] = True
+            break
+    return hist
 
 
 class mfRGLinearMap:

@@ -70,3 +70,40 @@ def test_fixed_point_preconditioned(orc, use_preconditioner):
     assert (ng, okg) == (no, oko)
     assert rel(Rg, Ro) < 1e-8
     S.close()
+
+
+def test_solve_using_mfRG_outer_loop(orc):
+    """solve_using_mfRG! (src/mfRG.jl:217-372): three accepted outer iterations with adaptive bubble mixing, occupation-fixing
+    chemical potential, DQGMRES-preconditioned Anderson vertex solves, SDE and reference update -- device state vs the oracle's.
+    Weak-coupling start as in production: S.F0 = NL2_Vertex(bare U) with zero K's, S.F = 0 (the synthetic Wu-point state at
+    U = 5.6 does not converge without a physical reference vertex)."""
+    import fddgasolver_jl_b200 as fd
+    T, U, nG, LG, L = 0.5, 2.0, 8, 6, 3
+    hp = {"t1": 1.0, "t2": -0.3}
+    Gb = fd.hubbard_bare_Green(T, nG, LG, μ=0.3, **hp)
+    G0 = fd.hubbard_bare_Green(T, nG, LG, μ=0.1, **hp)
+    mk = lambda: fd.NL2_Vertex(fd.RefVertex(T, U), T, 8, (2, 2), (2, 2), L)
+    S = fd.NL2_ParquetSolver(8, (2, 2), (2, 2), L, Gb, G0, np.zeros_like(G0), mk(), T=T)
+    S.init_sym_grp()
+    R = orc.OracleSolver(8, (2, 2), (2, 2), L, Gb, G0, np.zeros_like(G0), mk(), T=T)
+    R.init_sym_grp()
+    kw = dict(occ_target=0.45, hubbard_params=hp, mixing_init=0.5, tol=1e-5, strategy="fdPA", anderson_iterations=30,
+              krylov_maxiter=40, memory=10)
+    hg = fd.solve_using_mfRG(S, maxiter=2, **kw)
+    ho = orc.solve_using_mfRG(R, maxiter=2, **kw)
+    # the Krylov preconditioner is solved to rtol = 1e-6 (src/mfRG.jl:148), so the two Anderson trajectories agree to that level,
+    # not to rounding: iteration counts may differ by a step at the ftol boundary
+    assert len(hg["Σ_err"]) == len(ho["Σ_err"]) == 2 and hg["mixing"] == ho["mixing"] == [0.5, 0.6]
+    assert hg["anderson_iterations"][0] == ho["anderson_iterations"][0] and abs(hg["anderson_iterations"][1] - ho["anderson_iterations"][1]) <= 2
+    assert np.allclose(hg["Σ_err"], ho["Σ_err"], rtol=1e-4) and np.allclose(hg["μ"], ho["μ"], rtol=0, atol=1e-5)
+    S.pull("F", "F0", "Σ", "Σ0", "G", "G0", "Π")
+    assert rel(S.Σ0, R.Σ0) < 1e-4 and rel(S.G, R.G) < 1e-4 and rel(S.G0, R.G0) < 1e-4
+    assert rel(S.Π0pp, R.Π0pp) < 1e-4 and rel(S.Πph, R.Πph) < 1e-4
+    for a, b in zip(S.F0.channels(), R.F0.channels()):
+        for x, y in zip(a.arrays(), b.arrays()):
+            assert rel(x, y) < 1e-4
+    assert np.max(np.abs(S.F0.flatten())) > 0.05 and not np.any(S.F.flatten())          # add!(S.F0, S.F); set!(S.F, 0)
+    # carried on, the outer loop converges (Σ error drops by more than an order of magnitude with the next accepted iteration)
+    h2 = fd.solve_using_mfRG(S, maxiter=1, **{**kw, "mixing_init": 0.72})
+    assert len(h2["Σ_err"]) == 1 and h2["Σ_err"][0] < 0.1 * hg["Σ_err"][0]
+    S.close()

@@ -376,3 +376,28 @@ def test_flatten_async_matches_flatten(orc):
     S.sync()
     assert np.array_equal(y, ref)
     S.close()
+
+
+def test_hubbard_chemical_potential_and_bare_green(orc):
+    """compute_hubbard_chemical_potential + set!(S.Gbare, hubbard_bare_Green(...; μ)) on the device (src/dyson.jl:45-57,
+    src/mfRG.jl:110-114): golden occupations of test/test_hubbard.jl:84-88 inverted, random Σ vs the oracle, error behaviour."""
+    import fddgasolver_jl_b200 as fd
+    S, R = make_pair(orc, nmax=2, nq=3, LG=6)
+    hp = {"t1": 1.0, "t2": -0.3}
+    fd.SDE(S, "scPA"); orc.SDE(R, "scPA")
+    for occ in (0.3, 0.48, 0.61):
+        mg, mo = fd.compute_hubbard_chemical_potential(occ, S, hp), orc.compute_hubbard_chemical_potential(occ, R, hp)
+        assert abs(mg - mo) < 1e-11, (occ, mg, mo)
+    fd.set_hubbard_bare_Green(S, μ=mg, **hp)
+    S.pull("Gbare")
+    assert rel(S.Gbare, fd.hubbard_bare_Green(S.T, S.nG, S.LG, μ=mg, **hp)) < 1e-14
+    fd.Dyson(S)
+    assert abs(fd.compute_occupation(S) - 0.61) < 1e-11
+    with pytest.raises(fd.FdgaError):
+        fd.compute_hubbard_chemical_potential(1.7, S, hp)
+    S.close()
+    # Σ = 0 on the mesh of test/test_hubbard.jl:84-88: μ = -2 <-> n = 0.2057188296739284
+    Gb = fd.hubbard_bare_Green(0.5, 20, 8, μ=0.0, t1=1.0)
+    S2 = fd.NL2_ParquetSolver(4, (2, 2), (2, 2), 2, Gb, Gb, np.zeros_like(Gb), fd.RefVertex(0.5, 1.0), T=0.5)
+    assert abs(fd.compute_hubbard_chemical_potential(0.2057188296739284, S2, {"t1": 1.0}) + 2.0) < 1e-11
+    S2.close()

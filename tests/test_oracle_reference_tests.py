@@ -210,3 +210,15 @@ def test_converged_fdPA_matches_scPA_of_target(orc, converged_reference):
     Sfd2.init_sym_grp()
     _solve(orc, Sfd2, "fdPA")
     assert np.max(np.abs(Sfd2.Σ - S.Σ)) > 1e-2
+
+
+def test_chemical_potential_inverts_golden_occupations(orc):
+    """compute_hubbard_chemical_potential (src/dyson.jl:45-57) must invert the golden occupations of test/test_hubbard.jl:84-88"""
+    class S:
+        nG, LG, T = 20, 8, 0.5
+    S.Σ = np.zeros((40, 64), dtype=np.complex128, order="F")
+    for mu, occ in [(-2.0, 0.2057188296739284), (0.0, 0.5), (2.0, 1 - 0.2057188296739284)]:
+        got = orc.compute_hubbard_chemical_potential(occ, S, {"t1": 1.0})
+        assert abs(got - mu) < 1e-11, (mu, got)
+    with pytest.raises(ValueError):
+        orc.compute_hubbard_chemical_potential(1.5, S, {"t1": 1.0})
