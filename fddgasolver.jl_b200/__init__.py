@@ -12,6 +12,7 @@ from .solver import (NL2_ParquetSolver, ParquetSolver, init_sym_grp, Dyson, comp
                      bubbles_momentum_space, build_K3_cache, build_K3_cache_mfRG, BSE_L_K2, BSE_L_K3, BSE_K1,
                      BSE_K2, BSE_K3, BSE_K1_new, BSE_K2_new, BSE_K1_1loop, BSE_K2_1loop, BSE_K3_1loop, SDE, iterate_solver, iterate_solver_stepwise, fixed_point, mfRGLinearMap,
                      dqgmres, symmetrize_solver, fixed_point_preconditioned,
-                     set_hubbard_bare_Green, compute_hubbard_chemical_potential, mix_bubbles, update_reference, solve_using_mfRG)
+                     set_hubbard_bare_Green, compute_hubbard_chemical_potential, mix_bubbles, update_reference, solve_using_mfRG,
+                     interpolate_vertex, interpolate_solver)
 from .synthetic import (parquet_solver_hubbard_parquet_approximation_NL2, parquet_solver_siam_parquet_approximation, synthetic_local_vertex,  # noqa: F401
                         wu_point_solver, wu_point_inputs, randomize_vertex)

@@ -625,6 +625,44 @@ __global__ void occupation_kernel(const C* __restrict__ G, long long n, double T
     acc = block_reduce(acc);
     if (threadIdx.x == 0) *occ = 0.5 + acc.y * T / Nk;
 }
+// ---- Fourier interpolation between momentum meshes: src/interpolate.jl:1-165 -------------------------------------------
+// The reference transforms to real space (fft / Li^d), copies the coefficients R in [-Li/2, Li/2]^d to the output mesh (half
+// weights at |R_c| = Li/2 for even Li) and transforms back (bfft).  All three steps are linear and factorise over the momentum
+// components, so per component it is ONE small matrix  M[xo, xi] = 1/Li sum_R w(R) exp(2 pi i R (xo/Lo - xi/Li))  applied along
+// that axis (built on the host in double precision, fdga_lib.cu: interp_matrix).
+// Step 1: re-box the frequency axes (values outside the input meshes: 0, or clamped to the edge for the self-energy,
+// src/interpolate.jl:176-186).  Frequency index maps are shifts: i_in = i_out + (N_in - N_out) for bosonic and fermionic meshes.
+struct InterpBox { int nd; int no[3]; int ni[3]; int shift[3]; };
+__global__ void interp_rebox_kernel(const C* __restrict__ in, C* __restrict__ out, InterpBox b, long long M, int clamp) {
+    long long Fo = (long long)b.no[0] * b.no[1] * b.no[2], Fi = (long long)b.ni[0] * b.ni[1] * b.ni[2];
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= Fo * M) return;
+    long long fo = i % Fo, m = i / Fo;
+    int io[3]; io[0] = (int)(fo % b.no[0]); io[1] = (int)((fo / b.no[0]) % b.no[1]); io[2] = (int)(fo / ((long long)b.no[0] * b.no[1]));
+    long long fi = 0, stride = 1; bool ok = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        int j = io[d] + b.shift[d];
+        if (j < 0 || j >= b.ni[d]) { if (clamp) j = j < 0 ? 0 : b.ni[d] - 1; else ok = false; }
+        fi += stride * j; stride *= b.ni[d];
+    }
+    out[i] = ok ? in[fi + Fi * m] : zeroC();
+}
+// Step 2 (once per momentum component): out[pre, xo, post] = sum_xi M[xo + Lo * xi] in[pre, xi, post]
+__global__ void interp_axis_kernel(const C* __restrict__ in, C* __restrict__ out, long long pre, int Li, int Lo, long long post,
+                                   const C* __restrict__ M) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= pre * Lo * post) return;
+    const long long ip = i % pre, r = i / pre; const int xo = (int)(r % Lo); const long long q = r / Lo;
+    C s0 = zeroC(), s1 = zeroC();
+    const C* src = in + ip + pre * (size_t)Li * q;
+    for (int xi = 0; xi < Li; xi += 2) {
+        s0 += M[xo + Lo * xi] * src[pre * xi];
+        if (xi + 1 < Li) s1 += M[xo + Lo * (xi + 1)] * src[pre * (xi + 1)];
+    }
+    out[i] = s0 + s1;
+}
+
 // ---- hubbard_bare_Green: src/models/hubbard.jl:8-44.  Stored quantity is i*G0 = i / (i nu + mu - eps_k) ----------------
 __device__ __forceinline__ C hubbard_bare_entry(int n, int ik, int LG, double T, double mu, double t1, double t2, double t3) {
     const int ix = ik % LG, iy = ik / LG;

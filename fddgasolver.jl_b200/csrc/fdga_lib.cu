@@ -110,6 +110,7 @@ struct fdga_ctx {
     int4* d_slabs[4]; int n_slabs[4]; bool slabs_dirty;   // active (W,P) slabs: [pp|ph] x [bubble mesh | K2 mesh]
     // device-resident DQGMRES workspace (fdga_mfrg_dqgmres): rings of `kry_mem` basis / direction vectors, work vector, iterate
     C* kryV; C* kryP; C* kryW; C* kryX; C* kryH; C* kryPart; unsigned int* kryTicket; C* kryHhost; int kry_mem;
+    C* itpA; C* itpB; size_t lenItp;   // ping-pong of fdga_interpolate_* when the bubble-sized scratch is too small (coarsening)
     C* PiMixed[2];           // Pipp_mixed, Piph_mixed of solve_using_mfRG! (fdga_mix_bubbles / fdga_update_reference)
     C* Rt3[3]; int rt_kind[3]; // per-channel right factors (W on the bubble mesh) reused between BSE_K1! and BSE_K2!
     std::string err;
@@ -545,7 +546,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
     cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->Rt); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB);
     cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
-    cudaFree(ctx->PiMixed[0]); cudaFree(ctx->PiMixed[1]);
+    cudaFree(ctx->PiMixed[0]); cudaFree(ctx->PiMixed[1]); cudaFree(ctx->itpA); cudaFree(ctx->itpB);
     cudaFree(ctx->kryV); cudaFree(ctx->kryP); cudaFree(ctx->kryW); cudaFree(ctx->kryX); cudaFree(ctx->kryH); cudaFree(ctx->kryPart); cudaFree(ctx->kryTicket); if (ctx->kryHhost) cudaFreeHost(ctx->kryHhost);
     cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); for (int i = 0; i < 3; i++) { cudaFree(ctx->TtabL[i]); cudaFree(ctx->OwnTabL[i]); cudaFree(ctx->RtotL[i]); cudaFree(ctx->ConvTabL[i]); if (i) cudaFree(ctx->RtL[i]); } cudaFree(ctx->SigR2); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) cudaFree(ctx->d_slabs[i]);
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); for (int k = 0; k < 3; k++) cudaFree(s.d_rep[k]);
@@ -1730,6 +1731,95 @@ int fdga_fixed_point_preconditioned(fdga_ctx* ctx, const fdga_c64* host_x, fdga_
     if (niter) *niter = it;
     if (solved) *solved = ok;
     return 0;
+}
+
+// ---- interpolate_vertex! / interpolate_solver!: src/interpolate.jl:1-191 ------------------------------------------------
+// dst (device, frequency count Fo, D momentum components of size Lo) <- Fourier interpolation of host_in (frequency boxes
+// box.ni, D components of size Li).  Memory order: frequencies fastest, then the momentum components (x fastest).
+static int interp_run(fdga_ctx* ctx, C* dst, const fdga_c64* host_in, InterpBox box, int D, int Li, int Lo, int clamp) {
+    if (Li < 1 || Li > 64 || Lo > 64) FAIL("fdga_interpolate: momentum mesh sizes must be in 1..64");
+    const long long Fo = (long long)box.no[0] * box.no[1] * box.no[2], Fi = (long long)box.ni[0] * box.ni[1] * box.ni[2];
+    long long Mi = 1, big = Fo;
+    for (int d = 0; d < D; ++d) Mi *= Li;
+    { long long cur = Fo * Mi; big = cur; for (int d = 0; d < D; ++d) { cur = cur / Li * Lo; big = std::max(big, cur); } }
+    big = std::max(big, Fi * Mi);
+    C* bufA = ctx->scratchA; C* bufB = ctx->scratchB;
+    if ((size_t)big > ctx->lenScratch) {      // e.g. coarsening from a finer mesh: dedicated buffers, grown on demand
+        if ((size_t)big > ctx->lenItp) {
+            cudaFree(ctx->itpA); cudaFree(ctx->itpB); ctx->itpA = ctx->itpB = nullptr; ctx->lenItp = 0;
+            CK(cudaMalloc(&ctx->itpA, (size_t)big * sizeof(C))); CK(cudaMalloc(&ctx->itpB, (size_t)big * sizeof(C)));
+            ctx->lenItp = (size_t)big;
+        }
+        bufA = ctx->itpA; bufB = ctx->itpB;
+    }
+    // M[xo + Lo * xi] = 1/Li sum_{R = -Li/2}^{Li/2} w(R) exp(2 pi i R (xo / Lo - xi / Li)), w = 1/2 at |R| = Li/2 for even Li
+    std::vector<C> M((size_t)Lo * Li);
+    for (int xi = 0; xi < Li; ++xi) for (int xo = 0; xo < Lo; ++xo) {
+        double re = 0.0, im = 0.0;
+        for (int R = -(Li / 2); R <= Li / 2; ++R) {
+            const double w = (Li % 2 == 0 && std::abs(R) == Li / 2) ? 0.5 : 1.0;
+            // exact phase reduction: R * (xo * Li - xi * Lo) / (Lo * Li) turns
+            const long long num = (long long)R * ((long long)xo * Li - (long long)xi * Lo), den = (long long)Lo * Li;
+            const long long rem = ((num % den) + den) % den;
+            const double ph = 2.0 * M_PI * (double)rem / (double)den;
+            re += w * cos(ph); im += w * sin(ph);
+        }
+        M[xo + (size_t)Lo * xi] = mkC(re / Li, im / Li);
+    }
+    C* dM = ctx->SigR2;     // G-sized scratch, at least 2 nG LG^2 >= 64 * 64 entries for any realistic mesh; checked:
+    if ((size_t)Lo * Li > ctx->lenG) FAIL("fdga_interpolate: interpolation matrix does not fit its scratch");
+    Scope sc(ctx, FDGA_T_MISC);
+    CK(cudaMemcpyAsync(dM, M.data(), M.size() * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(bufB, host_in, (size_t)(Fi * Mi) * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));          // M is a stack-lifetime vector, host_in belongs to the caller
+    LAUNCH(FDGA_T_MISC, interp_rebox_kernel, nblk(Fo * Mi, 256), 256, (const C*)bufB, bufA, box, Mi, clamp);
+    C* cur = bufA; C* other = bufB;
+    long long pre = Fo, post = Mi;
+    for (int d = 0; d < D; ++d) {
+        post /= Li;
+        C* out = (d == D - 1) ? dst : other;
+        LAUNCH(FDGA_T_MISC, interp_axis_kernel, nblk(pre * Lo * post, 256), 256, (const C*)cur, out, pre, Li, Lo, post, (const C*)dM);
+        pre *= Lo;
+        other = cur; cur = out;
+    }
+    CK(cudaGetLastError());
+    if (D == 0) CK(cudaMemcpyAsync(dst, bufA, (size_t)Fo * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+// interpolate_vertex!(Ko, Ki): Ko = class `cls` of channel `channel` of the NL2 vertex `which` of this context, Ki = host array on
+// an Li x Li momentum mesh with frequency meshes nKi (cls 0: {N_K1}; 1: {N_K2 bosonic, N_K2 fermionic}; 2: {N_K3 bosonic, N_K3 fermionic})
+int fdga_interpolate_vertex(fdga_ctx* ctx, int which, int channel, int cls, const fdga_c64* host_Ki, const int32_t* nKi, int Li) {
+    CK(cudaSetDevice(ctx->device));
+    LevelBuf* lb = which_level(ctx, which);
+    if (!lb || lb->d.type != FDGA_LV_NL2 || channel < 0 || channel > 2 || cls < 0 || cls > 2) FAIL("fdga_interpolate_vertex: bad selector (needs an NL2 level)");
+    if (lb == &ctx->lev[0] && wait_copy(ctx)) return 1;
+    const fdga_level_desc& d = lb->d;
+    InterpBox b; b.nd = 1; for (int i = 0; i < 3; ++i) { b.no[i] = 1; b.ni[i] = 1; b.shift[i] = 0; }
+    int D = 2;
+    if (cls == 0) { b.no[0] = 2 * d.nK1 - 1; b.ni[0] = 2 * nKi[0] - 1; b.shift[0] = nKi[0] - d.nK1; }
+    else if (cls == 1) {
+        b.nd = 2; D = 4;
+        b.no[0] = 2 * d.nK2[0] - 1; b.ni[0] = 2 * nKi[0] - 1; b.shift[0] = nKi[0] - d.nK2[0];
+        b.no[1] = 2 * d.nK2[1];     b.ni[1] = 2 * nKi[1];     b.shift[1] = nKi[1] - d.nK2[1];
+    } else {
+        b.nd = 3;
+        b.no[0] = 2 * d.nK3[0] - 1; b.ni[0] = 2 * nKi[0] - 1; b.shift[0] = nKi[0] - d.nK3[0];
+        b.no[1] = b.no[2] = 2 * d.nK3[1]; b.ni[1] = b.ni[2] = 2 * nKi[1]; b.shift[1] = b.shift[2] = nKi[1] - d.nK3[1];
+    }
+    for (int i = 0; i < 3; ++i) if (b.ni[i] < 1) FAIL("fdga_interpolate_vertex: bad input mesh sizes");
+    if (interp_run(ctx, lb->K[channel][cls], host_Ki, b, D, Li, ctx->g.L, 0)) return 1;
+    lb->sw_dirty = true; lb->k1h_dirty = true; ctx->fsum_dirty = true;
+    invalidate_rt(ctx);
+    return 0;
+}
+// interpolate_vertex!(Go, Gi) for G-shaped arrays [nu, k] (NL_MF_G, src/interpolate.jl:62-80); clamp != 0: frequencies outside the
+// input mesh take the value at its edge, as interpolate_solver! does for the self-energy (src/interpolate.jl:176-186)
+int fdga_interpolate_green(fdga_ctx* ctx, int which, const fdga_c64* host_in, int nG_in, int Li, int clamp) {
+    CK(cudaSetDevice(ctx->device));
+    if (which < 0 || which >= 5 || nG_in < 1) FAIL("fdga_interpolate_green: bad selector");
+    InterpBox b; b.nd = 1; for (int i = 0; i < 3; ++i) { b.no[i] = 1; b.ni[i] = 1; b.shift[i] = 0; }
+    b.no[0] = 2 * ctx->dims.nG; b.ni[0] = 2 * nG_in; b.shift[0] = nG_in - ctx->dims.nG;
+    return interp_run(ctx, ctx->G[which], host_in, b, 2, Li, ctx->g.LG, clamp);
 }
 
 // ---- outer loop of solve_using_mfRG! (src/mfRG.jl:217-372): the state updates between two vertex solves, on the device ----

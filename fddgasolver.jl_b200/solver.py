@@ -583,3 +583,29 @@ def solve_using_mfRG(S, *, maxiter=100, verbose=False, occ_target=None, hubbard_
             hist["converged"] = True
             break
     return hist
+
+
+def interpolate_vertex(So, Fi, which=0):
+    """interpolate_vertex!(γo.K, γi.K) for the three channels and classes of an NL2 vertex (src/interpolate.jl:62-165, 199-206):
+    Fourier interpolation of the host vertex Fi (its own momentum mesh and frequency boxes) into vertex `which` of So's context."""
+    Li = Fi.L
+    for ch in CHANNELS:
+        g = Fi.channel(ch)
+        for cls, (a, n) in enumerate(((g.K1, (Fi.numK1,)), (g.K2, Fi.numK2), (g.K3, Fi.numK3))):
+            nk = (C.c_int32 * 2)(*(tuple(n) + (0,))[:2])
+            So._call("fdga_interpolate_vertex", which, ch, cls, L.ptr(a), nk, Li)
+
+
+def interpolate_solver(So, Si, *, occ_target=None, hubbard_params=None):
+    """interpolate_solver!(So, Si; occ_target, hubbard_params): src/interpolate.jl:168-213.  Si only provides HOST arrays (Si.Σ,
+    Si.F: pull them first if Si is a device solver); everything is evaluated in So's context."""
+    nGi = Si.Σ.shape[0] // 2
+    LGi = int(round(np.sqrt(Si.Σ.shape[1])))
+    So._call("fdga_interpolate_green", L.SIGMA, L.ptr(np.asfortranarray(Si.Σ)), nGi, LGi, 1)
+    if occ_target is not None:
+        μ = compute_hubbard_chemical_potential(occ_target, So, hubbard_params)
+        set_hubbard_bare_Green(So, μ=μ, **hubbard_params)
+    Dyson(So)
+    bubbles(So)
+    interpolate_vertex(So, Si.F, 0)
+    symmetrize_solver(So)

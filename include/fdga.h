@@ -199,6 +199,14 @@ int  fdga_symmetrize_solver(fdga_ctx*);
 int  fdga_fixed_point_preconditioned(fdga_ctx*, const fdga_c64* host_x, fdga_c64* host_R, int strategy, int use_preconditioner,
                                      int krylov_maxiter, int memory, int* niter, int* solved);
 
+/* interpolate_vertex!(Ko, Ki): src/interpolate.jl:1-165 -- Fourier interpolation between momentum meshes.  Ko = class `cls` of
+ * channel `channel` of the NL2 vertex `which` of this context (its own meshes); Ki = host array on an Li x Li momentum mesh with
+ * frequency meshes nKi (cls K1: {N}; K2: {N bosonic, N fermionic}; K3: {N bosonic, N fermionic}).  Frequencies outside Ki's
+ * meshes are set to 0 (set!(Ko, 0) + is_inbounds || continue). */
+int  fdga_interpolate_vertex(fdga_ctx*, int which, int channel, int cls, const fdga_c64* host_Ki, const int32_t* nKi, int Li);
+/* the NL_MF_G method [nu, k] (src/interpolate.jl:62-80) into G / G0 / Gbare / Sigma / Sigma0 of this context; clamp != 0 extends
+ * the input beyond its frequency mesh by its edge values as interpolate_solver! does for Sigma (src/interpolate.jl:176-186) */
+int  fdga_interpolate_green(fdga_ctx*, int which, const fdga_c64* host_in, int nG_in, int Li, int clamp);
 /* State updates of the outer loop of solve_using_mfRG! (src/mfRG.jl:217-372), device resident:
  * fdga_mix_bubbles:      Pi_mixed = mixing * Pi + (1 - mixing) * Pi0;  set!(S.Pi, Pi_mixed)                       (:271-276)
  * fdga_update_reference: set!(S.Pi0, Pi_mixed); set!(S.G0, S.G); set!(S.Sigma0, S.Sigma); add!(S.F0, S.F); set!(S.F, 0) (:336-347) */

@@ -504,6 +504,65 @@ def iterate_solver(S, strategy="fdPA", update_Σ=True):
         SDE(S, strategy)
 
 
+def _fourier_interpolate(yi, Lo, Li):
+    """_fourier_interpolate!(yi, Lo, Li): src/interpolate.jl:1-58, vector (Li^2) and matrix (Li^2 x Li^2) methods, restated
+    literally: fft / Li^d, coefficients R in [-Li/2, Li/2] copied with half weights at |R_c| = Li/2 (even Li), bfft."""
+    d = 2 * yi.ndim
+    yR = np.fft.fftn(yi.reshape((Li,) * d, order="F")) / Li ** d
+    yo = np.zeros((Lo,) * d, dtype=np.complex128)
+    Rs = range(-(Li // 2), Li // 2 + 1)
+    import itertools
+    for R in itertools.product(Rs, repeat=d):
+        w = 1.0
+        if Li % 2 == 0:
+            for c in R:
+                if abs(c) == Li // 2:
+                    w /= 2
+        yo[tuple(c % Lo for c in R)] += yR[tuple(c % Li for c in R)] * w
+    yo = np.fft.ifftn(yo) * Lo ** d
+    return yo.reshape((Lo * Lo,) * yi.ndim, order="F")
+
+
+def interpolate_array(Ko, Ki, nfreq, Lo, Li, shifts, clamp=False):
+    """interpolate_vertex!(Ko, Ki) for any class: the first `nfreq` axes are Matsubara meshes (index shift i_in = i_out + shift),
+    the rest momentum axes (src/interpolate.jl:62-165).  clamp: edge values outside the input box (Σ in interpolate_solver!)."""
+    Ko[...] = 0
+    import itertools
+    for io in itertools.product(*[range(n) for n in Ko.shape[:nfreq]]):
+        ii = []
+        ok = True
+        for d, i in enumerate(io):
+            j = i + shifts[d]
+            if j < 0 or j >= Ki.shape[d]:
+                if clamp:
+                    j = 0 if j < 0 else Ki.shape[d] - 1
+                else:
+                    ok = False
+            ii.append(j)
+        if ok:
+            Ko[io] = _fourier_interpolate(np.ascontiguousarray(Ki[tuple(ii)]), Lo, Li)
+
+
+def interpolate_vertex(Fo, Fi):
+    """the channel / class loop of interpolate_solver! (src/interpolate.jl:199-206) on host NL2 vertices"""
+    for go, gi in zip(Fo.channels(), Fi.channels()):
+        interpolate_array(go.K1, gi.K1, 1, Fo.L, Fi.L, (Fi.numK1 - Fo.numK1,))
+        interpolate_array(go.K2, gi.K2, 2, Fo.L, Fi.L, (Fi.numK2[0] - Fo.numK2[0], Fi.numK2[1] - Fo.numK2[1]))
+        interpolate_array(go.K3, gi.K3, 3, Fo.L, Fi.L, (Fi.numK3[0] - Fo.numK3[0],) + (Fi.numK3[1] - Fo.numK3[1],) * 2)
+
+
+def interpolate_solver(So, Si, *, occ_target=None, hubbard_params=None):
+    """interpolate_solver!(So, Si; occ_target, hubbard_params): src/interpolate.jl:168-213"""
+    interpolate_array(So.Σ, Si.Σ, 1, So.LG, Si.LG, (Si.nG - So.nG,), clamp=True)
+    if occ_target is not None:
+        μ = compute_hubbard_chemical_potential(occ_target, So, hubbard_params)
+        So.Gbare[...] = hubbard_bare_Green(So.T, So.nG, So.LG, μ=μ, **hubbard_params)
+    Dyson(So)
+    bubbles(So)
+    interpolate_vertex(So.F, Si.F)
+    symmetrize_solver(So)
+
+
 def symmetrize_solver(S):
     """symmetrize_solver!(S): src/ParquetSolver.jl:246-259"""
     def sym(which, a):
