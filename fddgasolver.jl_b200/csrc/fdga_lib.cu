@@ -472,7 +472,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     CKC(cudaSetDevice(device));
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->main_stream = ctx->stream; ctx->lane[0] = ctx->stream; ctx->cur_lane = 0; ctx->forked = false;
-    { const char* e = getenv("FDGA_SERIAL"); ctx->opt_serial = (e && e[0] == '1') ? 1 : 0; }     // debugging aid, same as FDGA_OPT_SERIAL
+    { const char* e = getenv("FDGA_SERIAL"); ctx->opt_serial = e ? atoi(e) : 0; }     // debugging aid, same as FDGA_OPT_SERIAL
     {   // lane 1 carries the heaviest jobs (t channel, ph bubble): highest priority so that its CTAs are placed first
         int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
         CKC(cudaStreamCreateWithPriority(&ctx->lane[1], cudaStreamNonBlocking, hi));
@@ -569,7 +569,7 @@ int fdga_set_option(fdga_ctx* ctx, int opt, int value) {
         ctx->opt_local = value != 0; invalidate_rt(ctx); return 0;
     }
     if (opt == FDGA_OPT_DIRECT_K1) { ctx->opt_direct_k1 = value != 0; return 0; }
-    if (opt == FDGA_OPT_SERIAL) { ctx->opt_serial = value != 0; return 0; }
+    if (opt == FDGA_OPT_SERIAL) { ctx->opt_serial = value; return 0; }
     FAIL("fdga_set_option: unknown option");
 }
 int fdga_sync(fdga_ctx* ctx) {
@@ -1084,7 +1084,16 @@ static int flush_pending(fdga_ctx* ctx) {
 
 // ---- concurrency lanes -------------------------------------------------------------------------------------
 // (profiling and the straightforward A/B kernels run serially on the main stream so that their times stay attributable)
-static bool lanes_enabled(fdga_ctx* ctx) { return !ctx->profile && !ctx->opt_generic && !ctx->opt_serial; }
+// Concurrent lanes pay when the kernels of a stage cannot fill the GPU on their own and the right factors of the three channels
+// stay L2 resident together (config 3: 65 MB each, 1.75 ms with lanes vs 2.26 ms without).  For big meshes every kernel fills the
+// GPU anyway and three of them at once evict each other's slabs from L2 (nq = 16, 1 GB per right factor: 94 ms with lanes,
+// 58 ms without), so the default (FDGA_OPT_SERIAL = 0) decides by the size of one bubble-shaped array.
+static bool lanes_enabled(fdga_ctx* ctx) {
+    if (ctx->profile || ctx->opt_generic || ctx->opt_serial == 1) return false;
+    if (ctx->opt_serial == 2) return true;
+    static const double lim_mb = getenv("FDGA_LANES_MAX_MB") ? atof(getenv("FDGA_LANES_MAX_MB")) : 160.0;
+    return (double)ctx->lenPi * sizeof(C) <= lim_mb * 1e6;
+}
 // everything the lanes read but do not own must be current before the fork
 static int lanes_fork(fdga_ctx* ctx) {
     if (!lanes_enabled(ctx) || ctx->forked) return 0;

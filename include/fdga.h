@@ -92,8 +92,10 @@ enum { FDGA_OPT_SDE_OWN_GAMMA = 0,
                                         the 1/nu tail (src/bubble.jl:9-36).  Needs nq = LG = 1. */,
        FDGA_OPT_DIRECT_K1 = 4        /* 1 = sum the cross-channel K1 terms of the column kernels term by term instead of
                                         through the per-slab momentum convolution (A/B check of slab_conv_kernel) */,
-       FDGA_OPT_SERIAL = 5           /* 1 = issue every kernel on the main stream (by default the three channels of a BSE
-                                        stage and the pp / ph / U^2 parts of the SDE run on concurrent streams) */ };
+       FDGA_OPT_SERIAL = 5           /* concurrency of the three channels of a BSE stage and of the pp / ph / U^2 parts of the SDE:
+                                        0 (default) = concurrent streams when one bubble-shaped array is <= 160 MB (the right
+                                        factors of the channels then share the L2), one stream otherwise; 1 = always one stream;
+                                        2 = always concurrent */ };
 int  fdga_set_option(fdga_ctx* ctx, int opt, int value);
 /* one process per GPU; `unique_id` = the 128-byte ncclUniqueId obtained on rank 0 by
  * fdga_comm_unique_id and broadcast by the host (MPI in Julia, torch.distributed in tests). */
