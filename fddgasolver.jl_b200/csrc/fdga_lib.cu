@@ -113,11 +113,15 @@ struct fdga_ctx {
     C* itpA; C* itpB; size_t lenItp;   // ping-pong of fdga_interpolate_* when the bubble-sized scratch is too small (coarsening)
     C* PiMixed[2];           // Pipp_mixed, Piph_mixed of solve_using_mfRG! (fdga_mix_bubbles / fdga_update_reference)
     C* Rt3[3]; int rt_kind[3]; // per-channel right factors (W on the bubble mesh) reused between BSE_K1! and BSE_K2!
-    std::string err;
+    std::string err, launch_err;
 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
-    ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } } while (0)
+    ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_) + (ctx->launch_err.empty() ? "" : " [first failed launch: " + ctx->launch_err + "]"); \
+    ctx->launch_err.clear(); return 1; } } while (0)
+// remember the first kernel whose launch was rejected (bad configuration / shared memory request), for the error text
+#define NOTE_LAUNCH(name) do { if (cudaPeekAtLastError() != cudaSuccess && ctx->launch_err.empty()) \
+    ctx->launch_err = std::string(name) + ": " + cudaGetErrorString(cudaPeekAtLastError()); } while (0)
 #define FAIL(msg) do { ctx->err = (msg); return 1; } while (0)
 
 static void invalidate_rt(fdga_ctx* ctx) { ctx->rt_kind[0] = ctx->rt_kind[1] = ctx->rt_kind[2] = -1; }
@@ -142,6 +146,7 @@ struct Scope {
 };
 #define LAUNCH(cat, kernel, grid, block, ...) do { \
     kernel<<<grid, block, 0, ctx->stream>>>(__VA_ARGS__); \
+    NOTE_LAUNCH(#kernel); \
     ctx->n_launch[cat]++; ctx->total_launches++; } while (0)
 
 static size_t lenK(const fdga_level_desc& d, int cls, int NP, bool nl2) {
@@ -927,7 +932,11 @@ template <int KIND, int CH>
 static void kernel_slab_own(fdga_ctx* ctx, const DevChain& V, const ColJob& job, int kind, const C* R, int cat) {
     const int PC = std::max(1, std::min(2 * ctx->g.nK2f, 2048 / job.nw));
     size_t smem = (size_t)job.nw * (1 + PC) * sizeof(C);
+    // long inner meshes (local solver, m_Pi_nu_factor = 6: nw = 3072 at BASELINE config 2) need the opt-in shared memory carve-out
+    if (smem + 2048 > 48 * 1024) cudaFuncSetAttribute(slab_own_kernel<KIND, CH>,     // static + dynamic must stay under 48 KB without the opt-in
+        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(smem, 227 * 1024));
     slab_own_kernel<KIND, CH><<<ctx->n_slabs[kind], 256, smem, ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->TtabL[ctx->cur_lane], ctx->OwnTabL[ctx->cur_lane], ctx->RtotL[ctx->cur_lane], ctx->g, PC);
+    NOTE_LAUNCH("slab_own_kernel");
     ctx->n_launch[cat]++; ctx->total_launches++;
 }
 // column path (fdga_column.cuh): momentum-independent table + one CTA per output column
@@ -954,6 +963,7 @@ static int launch_slab_conv(fdga_ctx* ctx, const DevChain& V, ColJob& job, int k
     if (refresh_k1h(ctx)) return 1;
     CK(cudaFuncSetAttribute(slab_conv_kernel<KIND, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(TW)));
     slab_conv_kernel<KIND, CH><<<ctx->n_slabs[kind], 256, bytes(TW), ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->twL, ctx->ConvTabL[ctx->cur_lane], g, TW);
+    NOTE_LAUNCH("slab_conv_kernel");
     ctx->n_launch[cat]++; ctx->total_launches++;
     *tab = ctx->ConvTabL[ctx->cur_lane];
     return 0;

@@ -1211,7 +1211,7 @@ int64_t orc_build_symmetry_group(int kind, int n0, int n1, int L, int64_t* offse
 
 // ---- BSE_L_K2! local, src/BSEa/BSEa_K2.jl:1-40: omega over the BUBBLE mesh, crossing on the right vertex ----
 void orc_bse_L_K2_local(cplx* K2, int nK2b, int nK2f, const orc_vertex* F0, const orc_vertex* F,
-                        const cplx* Pi0, const orc_sg* SG, int sign, int Ch, int Sp, const orc_grid* g) {
+                        const cplx* Pi0, const orc_sg* SG, int sign, int Ch, int Sp, const orc_grid* g, int64_t c0, int64_t c1) {
     VertexEval EF0 = {F0, 1, 1}, EF = {F, 1, 1};
     int nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF;
     K2Shape s = {nK2b, nK2f, 1};
@@ -1230,7 +1230,7 @@ void orc_bse_L_K2_local(cplx* K2, int nK2b, int nK2f, const orc_vertex* F0, cons
         }
         return T * val * (double)sign;
     };
-    sg_apply(K2, SG, diagram);
+    sg_apply(K2, SG, diagram, c0, c1);
 }
 
 // ---- bubbles! local, src/bubble.jl:9-36 (use_G_tail = true: 1/nu outside the G mesh) ------------------------

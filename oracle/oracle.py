@@ -804,13 +804,13 @@ def bubbles_local(S, Πpp, Πph, G):
     lib().orc_bubbles_local(_p(Πpp), _p(Πph), _p(G), S.nG, C.byref(S.grid))
 
 
-def BSE_L_K2_local(S, ch):
+def BSE_L_K2_local(S, ch, c0=0, c1=-1):
     sign, Sp = _sign_sp(ch)
     K2 = S.FL.channel(ch).K2
     sg = S.sg[SG_PP2 if ch == pCh else SG_PH2]
     lib().orc_bse_L_K2_local(_p(K2), S.nK2[0], S.nK2[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)),
-                             _p(_pi(S, ch, True)), C.byref(sg_struct(sg)), sign, ch, Sp, C.byref(S.grid))
-    if ch == tCh:
+                             _p(_pi(S, ch, True)), C.byref(sg_struct(sg)), sign, ch, Sp, C.byref(S.grid), C.c_int64(c0), C.c_int64(c1))
+    if ch == tCh and c1 < 0:
         _tfix(S.FL.γt.K2, S.FL.γa.K2)
 
 

@@ -115,3 +115,66 @@ def test_siam_fdPA_golden_sigma_on_gpu(orc):
     S2.init_sym_grp(); solve(S2, "fdPA")
     assert abs(S2.Σ[nG, 0] - (0.024643001835742997 - 0.17494219707558506j)) < 5e-5
     S0.close(); S2.close()
+
+
+def test_local_hubbard_config2_sizes(orc):
+    """BASELINE configs[1]: local Hubbard fdΓA iteration on the grid sizes of data/high_temperature_U2.0*.h5 (T = 0.5; G N = 128;
+    K1 N = 128; K2 N = (74, 50); core (24, 16); mΠν_factor = 6 => Π 255 x 1536).  The device runs the full iteration; the oracle
+    recomputes K1 / K3 / caches in full and sampled class representatives of L_K2 / K2 (inputs taken from the device state), plus
+    the exact symmetry of every output."""
+    import ctypes
+    import fddgasolver_jl_b200 as fd
+    T, U, nG = 0.5, 2.0, 128
+    F0 = fd.synthetic_local_vertex(T, U, numK1=128, numK2=(74, 50), numK3=(1, 1), core=(24, 16), seed=2)
+    for g in F0.channels():
+        for a in g.arrays():
+            a *= 0.05
+    Gb = fd.siam_bare_Green(T, nG, e=0.1, Δ=0.6, D=10.0)
+    S = fd.ParquetSolver(128, (74, 50), (24, 16), Gb, 0.9 * Gb, 0.02 * Gb, F0, T=T, mΠν_factor=6)
+    fd.randomize_vertex(S.F, 3, 0.05); S.push("F"); S.init_sym_grp()
+    fd.symmetrize_solver(S); S.pull("F")
+    R = orc.OracleLocalSolver(128, (74, 50), (24, 16), Gb, 0.9 * Gb, 0.02 * Gb, F0, T=T, mΠν_factor=6)
+    R.init_sym_grp(); R.F.set(S.F)
+    S.pull("Π", "G")
+    for n in ("Π0pp", "Π0ph", "Πpp", "Πph"):
+        assert rel(getattr(S, n), getattr(R, n)) < TOL, n
+    fd.iterate_solver(S, "fdPA", True)
+    S.pull("FL", "Fbuff", "cache", "Σ")
+    assert np.isfinite(S.Σ).all() and np.isfinite(S.Fbuff.flatten()).all()
+    orc.build_K3_cache(R)
+    for n in ("cache_Γpx", "cache_F0p", "cache_F0a", "cache_F0t", "cache_Γpp", "cache_Γa", "cache_Γt", "cache_Fp", "cache_Fa", "cache_Ft"):
+        assert rel(getattr(S, n), getattr(R, n)) < TOL, n
+    rng = np.random.default_rng(5)
+    order = (fd.pCh, fd.aCh)
+    for ch in order:                                  # L_K2 samples (inputs: S.F, S.F0)
+        sg = S._sg[fd._lib.SG_PP2 if ch == fd.pCh else fd._lib.SG_PH2]
+        for c in rng.integers(0, len(sg[0]) - 1, size=6):
+            orc.BSE_L_K2_local(R, ch, c0=int(c), c1=int(c) + 1)
+            idx = sg[1][sg[0][c]:sg[0][c + 1]]
+            assert rel(S.FL.channel(ch).K2.ravel(order="F")[idx], R.FL.channel(ch).K2.ravel(order="F")[idx]) < TOL, ("L_K2", ch, c)
+    R.FL.set(S.FL)
+    for ch in (fd.pCh, fd.aCh, fd.tCh):
+        orc.BSE_L_K3(R, ch)
+    for a, b in zip(S.FL.channels(), R.FL.channels()):
+        assert rel(a.K3, b.K3) < TOL
+    for ch in (fd.pCh, fd.aCh, fd.tCh):
+        orc.BSE_K1(R, ch)
+    for ch in (fd.pCh, fd.aCh, fd.tCh):
+        orc.BSE_K3(R, ch)
+    for a, b in zip(S.Fbuff.channels(), R.Fbuff.channels()):
+        assert rel(a.K1, b.K1) < TOL and rel(a.K3, b.K3) < TOL
+    for ch in order:                                  # K2 samples
+        sg = S._sg[fd._lib.SG_PP2 if ch == fd.pCh else fd._lib.SG_PH2]
+        for c in rng.integers(0, len(sg[0]) - 1, size=6):
+            R.Fbuff.channel(ch).K2[...] = 0
+            orc.BSE_K2(R, ch, c0=int(c), c1=int(c) + 1)
+            idx = sg[1][sg[0][c]:sg[0][c + 1]]
+            assert rel(S.Fbuff.channel(ch).K2.ravel(order="F")[idx], R.Fbuff.channel(ch).K2.ravel(order="F")[idx]) < TOL, ("K2", ch, c)
+    for ch in order:                                  # outputs are exactly class-constant
+        for cls, which in (("K1", fd._lib.SG_K1), ("K2", fd._lib.SG_PP2 if ch == fd.pCh else fd._lib.SG_PH2),
+                           ("K3", fd._lib.SG_PP3 if ch == fd.pCh else fd._lib.SG_PH3)):
+            flat = getattr(S.Fbuff.channel(ch), cls).ravel(order="F").copy()
+            sym = flat.copy()
+            orc.lib().orc_symmetrize(orc._p(sym), ctypes.byref(orc.sg_struct(S._sg[which])))
+            assert np.array_equal(sym, flat), (ch, cls)
+    S.close()
