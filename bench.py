@@ -294,12 +294,13 @@ def run_ours(a):
     ach = bytes_per_launch / (k2_ms_launch * 1e-3) / 1e9
     roofline = {"kernel": "column_kernel<JOB_K2> (BSE_K2!, src/nonlocal_2/BSEa/BSEa_K2.jl:55-138), mean over the p, t, a launches", "bound": "hbm", "achieved": ach, "peak": peak_hbm,
                 "unit": "GB/s", "frac": ach / peak_hbm,
-                # dram__bytes_read.sum + dram__bytes_write.sum of column_kernel<JOB_K2, pCh> at config 3, world 1, from
-                # profiles/r01_final_column_kernel_ncu_full.txt (ncu --set full); None for other workloads
-                "traffic": 22.93e6 if (a.nmax, a.nq, a.LG, world) == (4, 8, 48, 1) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of column_kernel<JOB_K2, tCh> (the heaviest of the three launches the
+                # line averages over) at config 3, world 1, from profiles/r01_s2_column_slab_kernels_ncu_full.txt (ncu --set full);
+                # None for other workloads
+                "traffic": 19.78e6 if (a.nmax, a.nq, a.LG, world) == (4, 8, 48, 1) else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": k2_ms_launch,
-                "note": "gather/issue-bound FP64 kernel, not HBM-bound: see fp64",
+                "note": "not HBM-bound: the L1 data pipe (LSU wavefronts 74 % of peak, ncu) and the index arithmetic bound this gather kernel; see fp64 and DESIGN.md section 4",
                 "fp64": {"algorithmic_gflop_per_launch": flop_per_launch / 1e9, "achieved_tflops": flop_per_launch / (k2_ms_launch * 1e-3) / 1e12}}
 
     # second hot entry of the reference: the mfRG linear map y = A x (src/mfRG.jl:34-89, script/benchmark_Wu.jl:60-64),

@@ -19,6 +19,12 @@ for serial in (2, 1):
         step()
     S.sync(); out["ms_per_step_%s" % {1: "one_stream", 2: "lanes"}[serial]] = round((time.perf_counter() - t0) / 4 * 1e3, 3)
 S.set_option("serial", 0)
+# host-side enqueue time (no synchronisation inside the loop): if it approaches the step time the CPU, not the GPU, is the limit
+S.sync(); t0 = time.perf_counter()
+for _ in range(10):
+    step()
+t_enq = (time.perf_counter() - t0) / 10
+S.sync(); out["enqueue_ms_per_step"] = round(t_enq * 1e3, 3); out["ms_per_step_default"] = round((time.perf_counter() - t0) / 10 * 1e3, 3)
 S.profile(True); S.profile_reset()
 S.sync(); t0 = time.perf_counter()
 step(); S.sync(); out["ms_profiled_step_wall"] = round((time.perf_counter() - t0) * 1e3, 3)
