@@ -31,8 +31,8 @@ UNIT = "iterations/s"
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=10)
-    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=10)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--nmax", type=int, default=4)
     p.add_argument("--nq", type=int, default=8)
@@ -169,7 +169,8 @@ def run_reference(a):
     inp = fd.wu_point_inputs(a.nmax, a.nq, a.LG, F0_scale=0.02)
     R = make_oracle_solver(o, inp)
     cores = o.lib().orc_num_threads()
-    frac = a.cpu_fraction
+    # keep the whole run within minutes whatever K is, but never sample fewer than ~4 class representatives per host thread
+    frac = a.cpu_fraction * max(min(1.0, 60.0 / max(a.steps, 1)), 0.3)
     for _ in range(a.warmup):
         cpu_iteration_seconds(o, R, frac / 4)
     ts = []

@@ -1444,7 +1444,7 @@ int fdga_sde(fdga_ctx* ctx, int strategy, int include_U2, int include_Hartree) {
 }
 
 // ---- drivers ---------------------------------------------------------------------------------------------
-// the BSE stages of one iteration: [L_K2, L_K3] | [K1, K2] | [K3].  The three channels of a stage are independent up to
+// the BSE stages of one iteration: [L_K2, L_K3] | [K1, K2, K3].  The three channels of a stage are independent up to
 // their post-fixes: each runs on its own lane, and the stage ends with one batched SG finish (one NCCL group).
 static int bse_stages(fdga_ctx* ctx, bool with_L, int mfrg) {
     // issue order: the t channel carries two spin forms (twice the work), so it goes first on the high-priority lane;
@@ -1462,9 +1462,7 @@ static int bse_stages(fdga_ctx* ctx, bool with_L, int mfrg) {
     if (!rc) rc = lanes_fork(ctx);
     for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_K1(ctx, order[i], mfrg); }
     for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_K2(ctx, order[i], mfrg); }    // K1 and K2 share inputs (FL, right factor)
-    if (lanes_join(ctx)) rc = 1;
-    if (!rc) rc = flush_pending(ctx);
-    if (!rc) rc = lanes_fork(ctx);
+    // BSE_K3! only reads the caches, the s-wave bubbles and FL.K3 (all final after the L stage): same stage, one SG finish fewer
     for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_K3(ctx, order[i], mfrg); }
     if (lanes_join(ctx)) rc = 1;
     if (!rc) rc = flush_pending(ctx);
