@@ -42,7 +42,8 @@ struct SymGroup {
     C* d_repvals;         // current slot (= d_rep[channel]); padded to chunk * nranks
     C* d_rep[3];          // one slot per channel so that the all-gathers of p, a, t can be issued as one NCCL group
     long long chunk;
-    std::vector<long long> h_offsets, h_index;
+    std::vector<long long> h_offsets, h_index;            // internal class order (see rebuild_sg)
+    std::vector<long long> o_offsets, o_index; std::vector<unsigned char> o_ops;   // as registered by the caller
     // columns (W, P, k) of this rank's class representatives (K2-shaped groups only)
     int ncol; int *d_col_iW, *d_col_iP, *d_col_ik, *d_col_start, *d_rep_inu, *d_rep_cls; int ngrp; int* d_grp_start;
 };
@@ -607,6 +608,7 @@ int fdga_comm_unique_id(void* unique_id_128B) {
     if (rc) { g_create_error = std::string("ncclGetUniqueId: ") + a.GetErrorString(rc); return 1; }
     return 0;
 }
+static int rebuild_sg(fdga_ctx* ctx, int which);
 int fdga_comm_init(fdga_ctx* ctx, int nranks, int rank, const void* unique_id_128B) {
     if (nranks < 1 || rank < 0 || rank >= nranks) FAIL("fdga_comm_init: bad nranks/rank");
     CK(cudaSetDevice(ctx->device));
@@ -619,19 +621,8 @@ int fdga_comm_init(fdga_ctx* ctx, int nranks, int rank, const void* unique_id_12
         if (rc) FAIL(std::string("ncclCommInitRank: ") + ctx->nccl.GetErrorString(rc));
     }
     ctx->nranks = nranks; ctx->rank = rank; ctx->slabs_dirty = true;
-    // re-chunk already registered symmetry groups
-    for (int i = 0; i < FDGA_SG_COUNT; i++) {
-        SymGroup& s = ctx->sg[i];
-        if (!s.set) continue;
-        s.chunk = (s.ncls + nranks - 1) / nranks;
-        for (int k = 0; k < 3; k++) {
-            cudaFree(s.d_rep[k]);
-            CK(cudaMalloc(&s.d_rep[k], (size_t)s.chunk * nranks * sizeof(C)));
-            CK(cudaMemset(s.d_rep[k], 0, (size_t)s.chunk * nranks * sizeof(C)));
-        }
-        s.d_repvals = s.d_rep[0];
-        if ((i == FDGA_SG_PP2 || i == FDGA_SG_PH2) && build_columns(ctx, s)) return 1;
-    }
+    // re-order / re-chunk already registered symmetry groups for the new rank count
+    for (int i = 0; i < FDGA_SG_COUNT; i++) if (ctx->sg[i].set && rebuild_sg(ctx, i)) return 1;
     return 0;
 }
 
@@ -701,26 +692,38 @@ static size_t sg_target_len(fdga_ctx* ctx, int which) {
     if (which == FDGA_SG_PP2 || which == FDGA_SG_PH2) return ctx->lev[0].len[1];
     return ctx->lev[0].len[2];
 }
-int fdga_set_symmetry_classes(fdga_ctx* ctx, int which, int64_t nclasses, const int64_t* offsets, const int64_t* index, const uint8_t* ops) {
-    CK(cudaSetDevice(ctx->device));
-    if (which < 0 || which >= FDGA_SG_COUNT) FAIL("fdga_set_symmetry_classes: bad selector");
-    size_t len = sg_target_len(ctx, which);
-    long long nmem = offsets[nclasses];
-    if (nclasses <= 0 || offsets[0] != 0 || (size_t)nmem > len) FAIL("fdga_set_symmetry_classes: malformed class table");
-    std::vector<int> mclass(nmem);
-    std::vector<unsigned char> seen(len, 0);
-    for (int64_t c = 0; c < nclasses; c++) {
-        if (offsets[c + 1] <= offsets[c]) FAIL("fdga_set_symmetry_classes: empty class");
-        for (int64_t j = offsets[c]; j < offsets[c + 1]; j++) {
-            if (index[j] < 0 || (size_t)index[j] >= len || seen[index[j]]) FAIL("fdga_set_symmetry_classes: index out of range or repeated");
-            seen[index[j]] = 1; mclass[j] = (int)c;
-        }
-    }
+// (Re)build the device tables of a registered symmetry group.  The class ORDER is internal to the library (callers only see
+// class members), and it decides what a rank has to touch: ranks own contiguous blocks of classes, and every slab-level kernel
+// (right factor, slab_own, slab_conv) runs on the (W, P) slabs that hold a representative of the rank.  In the caller's order
+// (ascending linear index: k slowest for K2) every rank touches every slab; with more than one rank the K1 / K2 classes are
+// therefore sorted by the slab (P, W) of their representative, so that the slab-level work is sharded like the column work.
+static int rebuild_sg(fdga_ctx* ctx, int which) {
     SymGroup& s = ctx->sg[which];
+    const long long nclasses = (long long)s.o_offsets.size() - 1, nmem = s.o_offsets[nclasses];
+    std::vector<long long> perm(nclasses);
+    for (long long c = 0; c < nclasses; c++) perm[c] = c;
+    if (ctx->nranks > 1 && (which == FDGA_SG_K1 || which == FDGA_SG_PP2 || which == FDGA_SG_PH2)) {
+        const Grid& g = ctx->g;
+        const long long nB = which == FDGA_SG_K1 ? 2 * g.nK1 - 1 : 2 * g.nK2b - 1, nF = which == FDGA_SG_K1 ? 1 : 2 * g.nK2f;
+        std::vector<long long> key(nclasses);
+        for (long long c = 0; c < nclasses; c++) {
+            long long idx = s.o_index[s.o_offsets[c]];
+            const long long iW = idx % nB; idx /= nB; idx /= nF; const long long iP = idx % g.NP;
+            key[c] = iW + nB * iP;
+        }
+        std::stable_sort(perm.begin(), perm.end(), [&](long long a, long long b) { return key[a] < key[b]; });
+    }
+    std::vector<long long> offs(nclasses + 1), idx(nmem); std::vector<unsigned char> ops(nmem); std::vector<int> mclass(nmem);
+    long long pos = 0;
+    for (long long c = 0; c < nclasses; c++) {
+        offs[c] = pos;
+        for (long long j = s.o_offsets[perm[c]]; j < s.o_offsets[perm[c] + 1]; j++) { idx[pos] = s.o_index[j]; ops[pos] = s.o_ops[j]; mclass[pos] = (int)c; pos++; }
+    }
+    offs[nclasses] = pos;
     cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); for (int k = 0; k < 3; k++) cudaFree(s.d_rep[k]);
+    s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; for (int k = 0; k < 3; k++) s.d_rep[k] = nullptr;
     s.ncls = nclasses; s.nmem = nmem; s.chunk = (nclasses + ctx->nranks - 1) / ctx->nranks;
-    s.h_offsets.assign(offsets, offsets + nclasses + 1);
-    s.h_index.assign(index, index + nmem);
+    s.h_offsets = offs; s.h_index = idx;
     CK(cudaMalloc(&s.d_offsets, (nclasses + 1) * sizeof(long long))); CK(cudaMalloc(&s.d_index, nmem * sizeof(long long)));
     CK(cudaMalloc(&s.d_ops, nmem)); CK(cudaMalloc(&s.d_member_class, nmem * sizeof(int)));
     for (int k = 0; k < 3; k++) {
@@ -728,13 +731,33 @@ int fdga_set_symmetry_classes(fdga_ctx* ctx, int which, int64_t nclasses, const 
         CK(cudaMemset(s.d_rep[k], 0, (size_t)s.chunk * ctx->nranks * sizeof(C)));
     }
     s.d_repvals = s.d_rep[0];
-    CK(cudaMemcpy(s.d_offsets, offsets, (nclasses + 1) * sizeof(long long), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s.d_index, index, nmem * sizeof(long long), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s.d_ops, ops, nmem, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.d_offsets, offs.data(), (nclasses + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.d_index, idx.data(), nmem * sizeof(long long), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.d_ops, ops.data(), nmem, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s.d_member_class, mclass.data(), nmem * sizeof(int), cudaMemcpyHostToDevice));
     s.set = true; ctx->slabs_dirty = true;
     if (which == FDGA_SG_PP2 || which == FDGA_SG_PH2) return build_columns(ctx, s);
     return 0;
+}
+int fdga_set_symmetry_classes(fdga_ctx* ctx, int which, int64_t nclasses, const int64_t* offsets, const int64_t* index, const uint8_t* ops) {
+    CK(cudaSetDevice(ctx->device));
+    if (which < 0 || which >= FDGA_SG_COUNT) FAIL("fdga_set_symmetry_classes: bad selector");
+    size_t len = sg_target_len(ctx, which);
+    long long nmem = offsets[nclasses];
+    if (nclasses <= 0 || offsets[0] != 0 || (size_t)nmem > len) FAIL("fdga_set_symmetry_classes: malformed class table");
+    std::vector<unsigned char> seen(len, 0);
+    for (int64_t c = 0; c < nclasses; c++) {
+        if (offsets[c + 1] <= offsets[c]) FAIL("fdga_set_symmetry_classes: empty class");
+        for (int64_t j = offsets[c]; j < offsets[c + 1]; j++) {
+            if (index[j] < 0 || (size_t)index[j] >= len || seen[index[j]]) FAIL("fdga_set_symmetry_classes: index out of range or repeated");
+            seen[index[j]] = 1;
+        }
+    }
+    SymGroup& s = ctx->sg[which];
+    s.o_offsets.assign(offsets, offsets + nclasses + 1);
+    s.o_index.assign(index, index + nmem);
+    s.o_ops.assign(ops, ops + nmem);
+    return rebuild_sg(ctx, which);
 }
 int fdga_build_symmetry_group(int which_sg, int n0, int n1, int nq, int64_t* offsets, int64_t* index, uint8_t* ops, int64_t* nclasses) {
     if (which_sg < 0 || which_sg >= FDGA_SG_COUNT) return 1;
