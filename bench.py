@@ -292,6 +292,7 @@ def run_ours(a):
     except Exception:
         pass
     peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+    fp64_peak = S.measure_fp64_peak()                     # DFMA micro-benchmark, measured live on this device
     ach = bytes_per_launch / (k2_ms_launch * 1e-3) / 1e9
     roofline = {"kernel": "column_kernel<JOB_K2> (BSE_K2!, src/nonlocal_2/BSEa/BSEa_K2.jl:55-138), mean over the p, t, a launches", "bound": "hbm", "achieved": ach, "peak": peak_hbm,
                 "unit": "GB/s", "frac": ach / peak_hbm,
@@ -302,7 +303,9 @@ def run_ours(a):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": k2_ms_launch,
                 "note": "not HBM-bound: the L1 data pipe (LSU wavefronts 74 % of peak, ncu) and the index arithmetic bound this gather kernel; see fp64 and DESIGN.md section 4",
-                "fp64": {"algorithmic_gflop_per_launch": flop_per_launch / 1e9, "achieved_tflops": flop_per_launch / (k2_ms_launch * 1e-3) / 1e12}}
+                "fp64": {"algorithmic_gflop_per_launch": flop_per_launch / 1e9, "achieved_tflops": flop_per_launch / (k2_ms_launch * 1e-3) / 1e12,
+                         "peak_tflops": fp64_peak, "peak_source": "DFMA micro-benchmark in libfdga (fdga_measure_fp64_peak), measured in this run",
+                         "frac": flop_per_launch / (k2_ms_launch * 1e-3) / 1e12 / fp64_peak}}
 
     # second hot entry of the reference: the mfRG linear map y = A x (src/mfRG.jl:34-89, script/benchmark_Wu.jl:60-64),
     # host vectors in and out exactly as Krylov.dqgmres calls it

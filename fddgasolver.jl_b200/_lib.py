@@ -35,7 +35,7 @@ EXPORTS = [
     "fdga_bse_K2", "fdga_bse_K3", "fdga_bse_K1_new", "fdga_bse_K2_new", "fdga_bse_K1_1loop", "fdga_bse_K2_1loop", "fdga_bse_K3_1loop",
     "fdga_set_F_from_Fbuff", "fdga_sde", "fdga_iterate_solver",
     "fdga_mfrg_matvec", "fdga_mfrg_matvec_strategy", "fdga_mfrg_dqgmres", "fdga_symmetrize_solver", "fdga_fixed_point_preconditioned", "fdga_mix_bubbles", "fdga_update_reference", "fdga_interpolate_vertex", "fdga_interpolate_green",
-    "fdga_profile_enable", "fdga_profile_reset", "fdga_kernel_time_ms",
+    "fdga_measure_fp64_peak", "fdga_profile_enable", "fdga_profile_reset", "fdga_kernel_time_ms",
     "fdga_total_launches", "fdga_stream",
 ]
 
@@ -117,6 +117,7 @@ def load():
     lib.fdga_symmetrize_solver.argtypes = [vp]
     lib.fdga_interpolate_vertex.argtypes = [vp, i32, i32, i32, vp, C.POINTER(C.c_int32), i32]
     lib.fdga_interpolate_green.argtypes = [vp, i32, vp, i32, i32, i32]
+    lib.fdga_measure_fp64_peak.argtypes = [vp, C.POINTER(dbl)]
     lib.fdga_mix_bubbles.argtypes = [vp, dbl]
     lib.fdga_update_reference.argtypes = [vp]
     lib.fdga_fixed_point_preconditioned.argtypes = [vp, vp, vp, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]

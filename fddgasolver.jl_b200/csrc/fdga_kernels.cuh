@@ -625,6 +625,17 @@ __global__ void occupation_kernel(const C* __restrict__ G, long long n, double T
     acc = block_reduce(acc);
     if (threadIdx.x == 0) *occ = 0.5 + acc.y * T / Nk;
 }
+// ---- FP64 FMA micro-benchmark (roofline denominator of the contraction kernels) ---------------------------------
+// 8 independent DFMA chains per thread; the result is written so that the loop cannot be removed.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 // ---- Fourier interpolation between momentum meshes: src/interpolate.jl:1-165 -------------------------------------------
 // The reference transforms to real space (fft / Li^d), copies the coefficients R in [-Li/2, Li/2]^d to the output mesh (half
 // weights at |R_c| = Li/2 for even Li) and transforms back (bfft).  All three steps are linear and factorise over the momentum

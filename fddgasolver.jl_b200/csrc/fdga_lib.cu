@@ -1425,6 +1425,10 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
         LAUNCH(FDGA_T_SDE_U2, symmetrize_kernel, nblk(ss.nmem, 256), 256, ctx->GRm, sym_dev(ss));
         CK(cudaGetLastError());
     }
+    if (include_Hartree) {      // occupation of G for the Hartree term: single-CTA reduction, hidden on lane 2 beside the L transforms
+        Scope sc(ctx, FDGA_T_MISC);
+        if (occupation_dev(ctx, gwhich)) return 1;
+    }
     if (lanes_join(ctx)) return 1;
     {
         Scope sc(ctx, FDGA_T_SDE_RS);
@@ -1440,7 +1444,6 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
     }
     if (include_Hartree) {
         Scope sc(ctx, FDGA_T_MISC);
-        if (occupation_dev(ctx, gwhich)) return 1;
         LAUNCH(FDGA_T_MISC, hartree_kernel, nblk(ctx->lenG, 256), 256, Sout, ctx->d_occ, U, 1.0, (long long)ctx->lenG);
         CK(cudaGetLastError());
     }
@@ -1906,6 +1909,27 @@ int fdga_update_reference(fdga_ctx* ctx) {
 }
 
 // ---- introspection -----------------------------------------------------------------------------------------
+// measured FP64 FMA throughput of this device (2 flop per DFMA), the denominator of the `fp64` roofline entry of bench.py
+int fdga_measure_fp64_peak(fdga_ctx* ctx, double* tflops) {
+    CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double* d_out = nullptr; CK(cudaMalloc(&d_out, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 0.999999, 1e-6);
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    CK(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+    return 0;
+}
 int fdga_profile_enable(fdga_ctx* ctx, int on) { ctx->profile = on != 0; return 0; }
 static int profile_collect(fdga_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));

@@ -298,6 +298,12 @@ class NL2_ParquetSolver:
             out[n] = (ms.value, cnt.value)
         return out
 
+    def measure_fp64_peak(self):
+        """FP64 FMA throughput of the device in TFLOP/s (DFMA micro-benchmark inside the library)"""
+        v = C.c_double(0.0)
+        self._call("fdga_measure_fp64_peak", C.byref(v))
+        return v.value
+
     def total_launches(self):
         return int(self._lib.fdga_total_launches(self._ctx))
 

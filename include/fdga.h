@@ -223,6 +223,8 @@ enum { FDGA_T_CACHE = 0, FDGA_T_L_K2 = 1, FDGA_T_L_K3 = 2, FDGA_T_K1 = 3, FDGA_T
        FDGA_T_COLUMN_K2 = 15,   /* the column_kernel launches of BSE_K2! alone (a sub-interval of FDGA_T_K2) */
        FDGA_T_KRYLOV = 16,      /* vector kernels of fdga_mfrg_dqgmres (orthogonalisation sweep, direction / iterate update) */
        FDGA_T_COUNT = 17 };
+/* FP64 FMA throughput of the device measured with a DFMA micro-benchmark (TFLOP/s, 2 flop per FMA): roofline denominator */
+int  fdga_measure_fp64_peak(fdga_ctx*, double* tflops);
 int  fdga_profile_enable(fdga_ctx*, int on);
 int  fdga_profile_reset(fdga_ctx*);
 int  fdga_kernel_time_ms(fdga_ctx*, int kernel_id, double* ms, int64_t* launches);
