@@ -44,6 +44,75 @@ kry_mgs_kernel(C* __restrict__ w, const C* __restrict__ v_sub, const C* __restri
     if (threadIdx.x == 0) { *out = tot; *ticket = 0u; }
 }
 
+// Blocked form of the same sweep: up to FDGA_KRY_B basis vectors per launch.  For the new block {v_j} the kernel accumulates
+// d_j = <v_j, w'> (w' = w minus the previous block, subtracted on the fly) AND the Gram entries G_jl = <v_j, v_l>, l < j; the last
+// CTA then runs the modified Gram-Schmidt recurrence on the coefficients,  h_j = d_j - sum_{l<j} h_l G_jl  (= <v_j, w' - sum_{l<j}
+// h_l v_l> exactly), so the algebra is MGS while w is read and written once per block instead of once per vector:
+// 2.5 vector passes per basis vector instead of 4, a quarter of the launches.
+#define FDGA_KRY_B 4
+struct KryBlk { int nprev, nnew, norm; int prev_slot[FDGA_KRY_B], new_slot[FDGA_KRY_B]; };
+__global__ void __launch_bounds__(FDGA_KRY_THREADS)
+kry_bmgs_kernel(C* __restrict__ w, const C* __restrict__ Vbase, long long n, const __grid_constant__ KryBlk blk,
+                const C* __restrict__ h_prev, C* __restrict__ h_new, C* __restrict__ part, unsigned int* __restrict__ ticket) {
+    constexpr int B = FDGA_KRY_B, NACC = B + B * (B - 1) / 2 + 1;
+    __shared__ bool is_last;
+    __shared__ C tot[NACC];
+    C hp[B];
+#pragma unroll
+    for (int p = 0; p < B; ++p) hp[p] = p < blk.nprev ? h_prev[p] : zeroC();
+    C acc[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc[a] = zeroC();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        C wi = w[i];
+        if (blk.nprev > 0) {
+#pragma unroll
+            for (int p = 0; p < B; ++p) if (p < blk.nprev) wi = wi - hp[p] * Vbase[(size_t)blk.prev_slot[p] * n + i];
+            w[i] = wi;
+        }
+        C v[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) v[j] = j < blk.nnew ? Vbase[(size_t)blk.new_slot[j] * n + i] : zeroC();
+        int g = B;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            acc[j] += conjC(v[j]) * wi;
+#pragma unroll
+            for (int l = 0; l < j; ++l) { acc[g] += conjC(v[j]) * v[l]; ++g; }
+        }
+        if (blk.norm) acc[NACC - 1] += conjC(wi) * wi;
+    }
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        C r = block_reduce(acc[a]);
+        if (threadIdx.x == 0) part[(size_t)blockIdx.x * NACC + a] = r;
+    }
+    if (threadIdx.x == 0) { __threadfence(); is_last = atomicAdd(ticket, 1u) == gridDim.x - 1; }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        C t = zeroC();
+        for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) t += part[(size_t)j * NACC + a];
+        t = block_reduce(t);
+        if (threadIdx.x == 0) tot[a] = t;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        C h[B];
+        int g = B;
+        for (int j = 0; j < B; ++j) {
+            C x = tot[j];
+            for (int l = 0; l < j; ++l) { x = x - h[l] * tot[g]; ++g; }
+            h[j] = x;
+            if (j < blk.nnew) h_new[j] = x;
+        }
+        if (blk.norm) h_new[blk.nnew] = tot[NACC - 1];
+        *ticket = 0u;
+    }
+}
+
 struct KryCoefs { int nc; int slot[FDGA_KRY_CHUNK]; C t[FDGA_KRY_CHUNK]; };
 // p_new = (src - sum_j t_j P[slot_j]) ; on the last chunk: p_new *= inv_r and x += gamma * p_new
 // (p_m = (v_m - sum_i r_{i,m} p_i) / r_{m,m},  x_m = x_{m-1} + gamma_m p_m)

@@ -1574,7 +1574,7 @@ static int kry_alloc(fdga_ctx* ctx, int memory) {
     const size_t n = ctx->lenFlat;
     if (!ctx->kryW) {
         CK(cudaMalloc(&ctx->kryW, n * sizeof(C))); CK(cudaMalloc(&ctx->kryX, n * sizeof(C)));
-        CK(cudaMalloc(&ctx->kryPart, FDGA_KRY_BLOCKS * sizeof(C))); CK(cudaMalloc(&ctx->kryTicket, sizeof(unsigned int)));
+        CK(cudaMalloc(&ctx->kryPart, (size_t)FDGA_KRY_BLOCKS * 16 * sizeof(C))); CK(cudaMalloc(&ctx->kryTicket, sizeof(unsigned int)));
         CK(cudaMemset(ctx->kryTicket, 0, sizeof(unsigned int)));
     }
     if (memory > ctx->kry_mem) {
@@ -1649,9 +1649,25 @@ static int dqgmres_dev(fdga_ctx* ctx, C* b_dev, C* x_dev, int strategy, int memo
         const int lo = std::max(1, m - k + 1), cnt = m - lo + 1;
         {   // incomplete modified Gram-Schmidt against v_lo .. v_m, then ||w||^2: cnt + 1 fused launches, no host sync
             Scope sc(ctx, FDGA_T_KRYLOV);
-            KRY_MGS(nullptr, nullptr, Vs(lo), Hd);
-            for (int j = 1; j < cnt; ++j) KRY_MGS(Vs(lo + j - 1), Hd + (j - 1), Vs(lo + j), Hd + j);
-            KRY_MGS(Vs(m), Hd + (cnt - 1), nullptr, Hd + cnt);
+            // blocks of FDGA_KRY_B vectors: launch b subtracts block b - 1 and produces the coefficients of block b; the last
+            // launch subtracts the last block and returns ||w||^2 in Hd[cnt]
+            static const bool blocked = getenv("FDGA_KRY_BLOCKED") ? atoi(getenv("FDGA_KRY_BLOCKED")) != 0 : false;
+            if (!blocked) {       // one fused launch per basis vector
+                KRY_MGS(nullptr, nullptr, Vs(lo), Hd);
+                for (int j = 1; j < cnt; ++j) KRY_MGS(Vs(lo + j - 1), Hd + (j - 1), Vs(lo + j), Hd + j);
+                KRY_MGS(Vs(m), Hd + (cnt - 1), nullptr, Hd + cnt);
+            }
+            const int nb = blocked ? (cnt + FDGA_KRY_B - 1) / FDGA_KRY_B : -1;
+            for (int b = 0; b <= nb; ++b) {
+                KryBlk blk; blk.nprev = 0; blk.nnew = 0; blk.norm = (b == nb) ? 1 : 0;
+                for (int p = 0; p < FDGA_KRY_B; ++p) { blk.prev_slot[p] = 0; blk.new_slot[p] = 0; }
+                if (b > 0) for (int j = (b - 1) * FDGA_KRY_B; j < std::min(cnt, b * FDGA_KRY_B); ++j) blk.prev_slot[blk.nprev++] = (lo + j - 1) % k;
+                if (b < nb) for (int j = b * FDGA_KRY_B; j < std::min(cnt, (b + 1) * FDGA_KRY_B); ++j) blk.new_slot[blk.nnew++] = (lo + j - 1) % k;
+                kry_bmgs_kernel<<<FDGA_KRY_BLOCKS, FDGA_KRY_THREADS, 0, ctx->stream>>>(ctx->kryW, V, (long long)n, blk,
+                    Hd + std::max(0, (b - 1) * FDGA_KRY_B), Hd + std::min(cnt, b * FDGA_KRY_B), ctx->kryPart, ctx->kryTicket);
+                NOTE_LAUNCH("kry_bmgs_kernel");
+                ctx->n_launch[FDGA_T_KRYLOV]++; ctx->total_launches++;
+            }
             CK(cudaGetLastError());
         }
         CK(cudaMemcpyAsync(Hh, Hd, (size_t)(cnt + 1) * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
