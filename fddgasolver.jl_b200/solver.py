@@ -476,6 +476,26 @@ def fixed_point(R, x, S, strategy="fdPA", update_Σ=True):
     return R
 
 
+def solve(S, *, maxiter=100, tol=1e-4, δ=0.85, mem=8, verbose=False, strategy="fdPA", update_Σ=True):
+    """solve!(S; maxiter, tol, δ, mem, strategy, update_Σ): src/solve.jl:160-196 -- nlsolve(:anderson) on fixed_point! over the
+    flattened [F; Σ] (or F alone).  Returns the nlsolve-like result (zero, f_converged, iterations, residual_norm); the solver holds
+    the last iterate."""
+    from .nlsolve import anderson
+    nF_ = S.length_F()
+    x0 = S.flatten_F()
+    if update_Σ:
+        S.pull("Σ")
+        x0 = np.concatenate([x0, S.Σ.ravel(order="F")])
+    res = anderson(lambda x: fixed_point(np.empty_like(x), x, S, strategy, update_Σ), x0, m=mem, beta=δ, ftol=tol, iterations=maxiter,
+                   show_trace=verbose)
+    S.unflatten_F(res.zero[:nF_])
+    S.F.unflatten(res.zero[:nF_])
+    if update_Σ:
+        S.Σ[...] = res.zero[nF_:].reshape(S.Σ.shape, order="F")
+        S.push("Σ")
+    return res
+
+
 class mfRGLinearMap:
     """mfRGLinearMap(S, strategy): y = x - BSE_lin(1e-2 x)/1e-2 (src/mfRG.jl:20-89)"""
 

@@ -178,3 +178,20 @@ def test_local_hubbard_config2_sizes(orc):
             orc.lib().orc_symmetrize(orc._p(sym), ctypes.byref(orc.sg_struct(S._sg[which])))
             assert np.array_equal(sym, flat), (ch, cls)
     S.close()
+
+
+def test_solve_mirror_reproduces_siam_golden_sigma(orc):
+    """solve!(S; strategy = :scPA, tol) (src/solve.jl:160-196) as mirrored by fd.solve: the reference's own call sequence of
+    test/test_siam_scPA.jl:20-31 end to end on the device."""
+    import fddgasolver_jl_b200 as fd
+    T, nmax = 0.1, 6
+    nG, nK1 = 6 * nmax, 4 * nmax
+    g = GOLD[0.0]
+    S = fd.parquet_solver_siam_parquet_approximation(nG, nK1, g["nK2"], g["nK2"], e=0.0, Δ=np.pi / 5, D=10.0, T=T, U=1.0, mΠν_factor=1)
+    S.init_sym_grp()
+    res = fd.solve(S, strategy="scPA", tol=1e-9, maxiter=100)
+    assert res.f_converged and res.iterations < 60
+    S.pull("Σ")
+    Σ = S.Σ.ravel(order="F")
+    assert np.max(np.abs(np.array([Σ[n + nG] for n in (-2, -1, 0, 1)]) - np.array(g["Σ"]))) < 1e-4
+    S.close()
