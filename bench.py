@@ -232,11 +232,16 @@ def run_ours(a):
         fd.SDE(S, "scPA")
 
     def step_e2e():
-        S.unflatten_F_async(x_np)                       # H2D of this step's input vertex
+        if world == 1:
+            S.unflatten_F_async(x_np)                   # H2D of this step's input vertex
+        else:
+            S.unflatten_F_from_root(x_np, 1.0, 0, rank)  # one PCIe upload on rank 0, NVLink broadcast to the other ranks
         fd.iterate_solver(S, "fdPA", update_Σ=False)
-        S.flatten_F_async(y_np)                         # D2H of the updated vertex, overlapping the SDE below
-        fd.SDE(S, "scPA")
-        S.get_green_into("Σ", s_np)                     # D2H of the self-energy
+        if rank == 0:
+            S.flatten_F_async(y_np)                     # D2H of the updated vertex (the job's result leaves through rank 0),
+        fd.SDE(S, "scPA")                               # ... overlapping the SDE
+        if rank == 0:
+            S.get_green_into("Σ", s_np)                 # D2H of the self-energy
         S.sync()                                        # both copies have landed
 
     def timed(step, K, W):

@@ -30,7 +30,7 @@ EXPORTS = [
     "fdga_set_vertex", "fdga_get_vertex", "fdga_set_core", "fdga_set_green", "fdga_get_green",
     "fdga_set_bubble", "fdga_get_bubble", "fdga_set_cache", "fdga_get_cache", "fdga_get_L",
     "fdga_set_symmetry_classes", "fdga_build_symmetry_group", "fdga_length_F", "fdga_flatten_F", "fdga_flatten_F_async",
-    "fdga_unflatten_F", "fdga_stash_F", "fdga_unstash_F", "fdga_dyson", "fdga_occupation", "fdga_bubbles_real_space",
+    "fdga_unflatten_F", "fdga_unflatten_F_from_root", "fdga_stash_F", "fdga_unstash_F", "fdga_dyson", "fdga_occupation", "fdga_bubbles_real_space",
     "fdga_set_hubbard_bare_green", "fdga_hubbard_chemical_potential", "fdga_bubbles_momentum_space", "fdga_bubbles_local", "fdga_build_K3_cache", "fdga_bse_L_K2", "fdga_bse_L_K3", "fdga_bse_K1",
     "fdga_bse_K2", "fdga_bse_K3", "fdga_bse_K1_new", "fdga_bse_K2_new", "fdga_bse_K1_1loop", "fdga_bse_K2_1loop", "fdga_bse_K3_1loop",
     "fdga_set_F_from_Fbuff", "fdga_sde", "fdga_iterate_solver",
@@ -118,6 +118,7 @@ def load():
     lib.fdga_interpolate_vertex.argtypes = [vp, i32, i32, i32, vp, C.POINTER(C.c_int32), i32]
     lib.fdga_interpolate_green.argtypes = [vp, i32, vp, i32, i32, i32]
     lib.fdga_measure_fp64_peak.argtypes = [vp, C.POINTER(dbl)]
+    lib.fdga_unflatten_F_from_root.argtypes = [vp, vp, dbl, i32]
     lib.fdga_mix_bubbles.argtypes = [vp, dbl]
     lib.fdga_update_reference.argtypes = [vp]
     lib.fdga_fixed_point_preconditioned.argtypes = [vp, vp, vp, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]

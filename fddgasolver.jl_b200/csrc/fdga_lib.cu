@@ -58,6 +58,7 @@ struct NcclApi {
     void* CommInitRank;                                  // bound with the by-value ncclUniqueId signature at the call site
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t);
     int (*CommDestroy)(void*);
     int (*GroupStart)(); int (*GroupEnd)();
     const char* (*GetErrorString)(int);
@@ -595,6 +596,7 @@ static int load_nccl(NcclApi& a, std::string& err) {
     a.CommInitRank = dlsym(a.h, "ncclCommInitRank");
     a.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(a.h, "ncclAllGather");
     a.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(a.h, "ncclAllReduce");
+    a.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(a.h, "ncclBroadcast");
     a.CommDestroy = (int (*)(void*))dlsym(a.h, "ncclCommDestroy");
     a.GroupStart = (int (*)())dlsym(a.h, "ncclGroupStart"); a.GroupEnd = (int (*)())dlsym(a.h, "ncclGroupEnd");
     a.GetErrorString = (const char* (*)(int))dlsym(a.h, "ncclGetErrorString");
@@ -802,6 +804,26 @@ int fdga_unstash_F(fdga_ctx* ctx) { CK(cudaSetDevice(ctx->device)); return unfla
 int fdga_unflatten_F(fdga_ctx* ctx, const fdga_c64* host_x, double scale) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->flat, host_x, ctx->lenFlat * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    return unflatten_dev(ctx, ctx->lev[0], ctx->flat, scale);
+}
+
+// unflatten!(S.F, x * scale) for a multi-rank job whose input lives on ONE host: the root rank copies x over PCIe once, the other
+// ranks receive it over NVLink (ncclBroadcast) -- instead of every rank pulling its own copy of the same vector through PCIe.
+// host_x is read on the root only (may be NULL elsewhere).  Collective: every rank of the communicator must call it.
+int fdga_unflatten_F_from_root(fdga_ctx* ctx, const fdga_c64* host_x, double scale, int root) {
+    CK(cudaSetDevice(ctx->device));
+    if (root < 0 || root >= ctx->nranks) FAIL("fdga_unflatten_F_from_root: bad root");
+    if (ctx->rank == root) {
+        if (!host_x) FAIL("fdga_unflatten_F_from_root: the root needs the host vector");
+        CK(cudaMemcpyAsync(ctx->flat, host_x, ctx->lenFlat * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (ctx->nranks > 1) {
+        if (!ctx->nccl.Broadcast) FAIL("fdga_unflatten_F_from_root: ncclBroadcast not available");
+        Scope sc(ctx, FDGA_T_COMM);
+        int rc = ctx->nccl.Broadcast(ctx->flat, ctx->flat, ctx->lenFlat * 2, /*ncclDouble*/ 8, root, ctx->comm, ctx->stream);
+        if (rc != 0) FAIL(std::string("ncclBroadcast: ") + ctx->nccl.GetErrorString(rc));
+        ctx->n_launch[FDGA_T_COMM]++;
+    }
     return unflatten_dev(ctx, ctx->lev[0], ctx->flat, scale);
 }
 

@@ -259,6 +259,10 @@ class NL2_ParquetSolver:
         assert x.dtype == np.complex128 and x.size == self.length_F()
         self._call("fdga_unflatten_F", L.ptr(x), float(scale))
 
+    def unflatten_F_from_root(self, x, scale=1.0, root=0, rank=0):
+        """collective unflatten!(S.F, x * scale): x crosses PCIe on the root only, the other ranks get it over NVLink"""
+        self._call("fdga_unflatten_F_from_root", L.ptr(x) if rank == root else None, float(scale), int(root))
+
     def stash_F(self):
         self._call("fdga_stash_F")
 

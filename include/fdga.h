@@ -133,6 +133,9 @@ int  fdga_flatten_F(fdga_ctx*, fdga_c64* host_y);
  * after iterate_solver!); host_y (ideally pinned) is valid after the next fdga_sync.  Later writers of S.F wait for it. */
 int  fdga_flatten_F_async(fdga_ctx*, fdga_c64* host_y);
 int  fdga_unflatten_F(fdga_ctx*, const fdga_c64* host_x, double scale);   /* asynchronous on the context stream */
+/* collective form for a multi-rank job whose vector lives on one host: the root copies over PCIe once, the other ranks receive
+ * over NVLink (ncclBroadcast); host_x is read on the root only */
+int  fdga_unflatten_F_from_root(fdga_ctx*, const fdga_c64* host_x, double scale, int root);
 /* device-resident copy of S.F (copy(S.F) / set!(S.F, copy)): lets a caller restart iterations without host traffic */
 int  fdga_stash_F(fdga_ctx*);
 int  fdga_unstash_F(fdga_ctx*);
