@@ -355,10 +355,26 @@ slab_own_kernel(const __grid_constant__ DevChain V, ColJob job, const int4* __re
     const int iW = slabs[blockIdx.x].x, iP = slabs[blockIdx.x].y;
     const int W = iW - (g.nK2b - 1), nw = job.nw, NP = g.NP, nF2 = 2 * g.nK2f, nB2 = 2 * g.nK2b - 1;
     const C* Rs = R + (size_t)nw * NP * (posB(W, job.slabW_N) + (size_t)(2 * job.slabW_N - 1) * iP);
-    for (int iw = threadIdx.x; iw < nw; iw += blockDim.x) {
-        C s = zeroC();
-        for (int iq = 0; iq < NP; ++iq) s += Rs[iw + (size_t)nw * iq];
-        Rq[iw] = s;
+    {   // Rq[iw] = sum_q Rs[iw, q]: all threads stream the slab (G momentum groups per frequency), partial sums meet in shared memory
+        C* part0 = Rq + nw;
+        const int G = (nw < (int)blockDim.x) ? min((int)blockDim.x / nw, PC) : 1;
+        if ((int)threadIdx.x < G * nw) {
+            const int gq = threadIdx.x / nw, iw = threadIdx.x - gq * nw;
+            C s = zeroC();
+            for (int iq = gq; iq < NP; iq += G) s += Rs[iw + (size_t)nw * iq];
+            part0[gq * nw + iw] = s;
+        }
+        if (G == 1) for (int iw = threadIdx.x + blockDim.x; iw < nw; iw += blockDim.x) {      // nw > blockDim.x: remaining frequencies
+            C s = zeroC();
+            for (int iq = 0; iq < NP; ++iq) s += Rs[iw + (size_t)nw * iq];
+            part0[iw] = s;
+        }
+        __syncthreads();
+        for (int iw = threadIdx.x; iw < nw; iw += blockDim.x) {
+            C s = zeroC();
+            for (int gq = 0; gq < G; ++gq) s += part0[gq * nw + iw];
+            Rq[iw] = s;
+        }
     }
     C sa = zeroC();
     if (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH)
