@@ -515,9 +515,12 @@ class mfRGLinearMap:
     def __matmul__(self, x):
         return self.matvec(x)
 
-    def matvec(self, x):
+    def matvec(self, x, out=None):
+        """y = A x.  `out` (optional) receives y: pass pinned host buffers for x and out to move them at full PCIe speed
+        (pageable numpy arrays are staged by the driver at a fraction of it)."""
         x = np.ascontiguousarray(x, dtype=np.complex128)
-        y = np.empty_like(x)
+        y = np.empty_like(x) if out is None else out
+        assert y.dtype == np.complex128 and y.size == x.size and y.flags["C_CONTIGUOUS"]
         self.S._call("fdga_mfrg_matvec_strategy", L.ptr(x), L.ptr(y), int(self.is_first_iteration), STRATEGY[self.strategy])
         self.is_first_iteration = False
         return y
