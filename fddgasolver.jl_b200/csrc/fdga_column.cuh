@@ -498,21 +498,45 @@ __global__ void k1_dft_kernel(DevLevel lv, int L, int NP, const C* __restrict__ 
     }
 }
 
+// ---- TMA (bulk asynchronous copy) staging of one contiguous R slab into shared memory, completion on an mbarrier ------------
+// The slab [w, q | W, P] is ONE contiguous run (nw * NP * 16 bytes, 16-byte aligned), so a single cp.async.bulk issued by one
+// thread brings it in while the CTA builds its piece table; the tiles are then cut out of shared memory.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ unsigned fdga_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fdga_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(fdga_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fdga_tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(fdga_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(fdga_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(fdga_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fdga_mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(fdga_smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
 // per-CTA piece table: conv_piece at nu = 0 plus its slope in nu (W0 is linear in nu), level / channel / weight
 struct ConvPieceS { int W0, dW0, sW, cx, cy, sk, sq, lev, r, nK1; double cf; };
 #define FDGA_CONV_MAXP 24     // 2 forms x 6 levels x 2 cross channels
 template <int KIND, int CH>
 __global__ void __launch_bounds__(256)
 slab_conv_kernel(const __grid_constant__ DevChain V, ColJob job, const int4* __restrict__ slabs, const C* __restrict__ R,
-                 const C* __restrict__ tw, C* __restrict__ ConvTab, Grid g, int TW) {
+                 const C* __restrict__ tw, C* __restrict__ ConvTab, Grid g, int TW, int use_tma) {
     typedef Forms<KIND, CH> FM;
-    extern __shared__ double sm_raw[];
+    extern __shared__ __align__(128) double sm_raw[];
+    __shared__ __align__(8) unsigned long long slab_bar;
     __shared__ ConvPieceS pcs[FDGA_CONV_MAXP];
     __shared__ int s_npc, s_cnt;
     __shared__ unsigned char nuList[64];
     const int L = g.L, NP = g.NP, nF2 = 2 * g.nK2f, nB2 = 2 * g.nK2b - 1, nw = job.nw, Nin = job.Ninner;
     const int TWp = TW | 1;                               // odd row stride: conflict-free column gathers
-    C* A = reinterpret_cast<C*>(sm_raw);                  // [NP][TWp]
+    C* Rsm = reinterpret_cast<C*>(sm_raw);                // [nw][NP] the whole R slab (TMA staging; absent when !use_tma)
+    C* A = Rsm + (use_tma ? (size_t)nw * NP : 0);         // [NP][TWp]
     C* B = A + (size_t)NP * TWp;                          // [NP][TWp]
     C* Z = B + (size_t)NP * TWp;                          // [nF2][NP]
     C* stw = Z + (size_t)nF2 * NP;                        // [L]  exp(+2 pi i j / L)
@@ -521,6 +545,13 @@ slab_conv_kernel(const __grid_constant__ DevChain V, ColJob job, const int4* __r
     const int iW = sl.x, iP = sl.y;
     const int W = iW - (g.nK2b - 1), Px = iP % L, Py = iP / L;
     const C* Rs = R + (size_t)nw * NP * (posB(W, job.slabW_N) + (size_t)(2 * job.slabW_N - 1) * iP);
+#if defined(__CUDA_ARCH__)
+    if (use_tma) {
+        if (tid == 0) fdga_mbar_init(&slab_bar, 1);
+        __syncthreads();
+        if (tid == 0) fdga_tma_load_1d(Rsm, Rs, (unsigned)((size_t)nw * NP * sizeof(C)), &slab_bar);
+    }
+#endif
     for (int j = tid; j < L; j += nthr) stw[j] = tw[j];
     if (tid < FDGA_CONV_MAXP) {        // piece table, one thread per (form, level, cross channel) slot
         const int nl = conv_level_end<KIND>(job) - job.lev_first;
@@ -546,11 +577,15 @@ slab_conv_kernel(const __grid_constant__ DevChain V, ColJob job, const int4* __r
     __syncthreads();
     const int npc = s_npc, cnt = s_cnt;
     for (int o = tid; o < cnt * NP; o += nthr) Z[o] = zeroC();
+    const C* Rsrc = Rs;
+#if defined(__CUDA_ARCH__)
+    if (use_tma) { fdga_mbar_wait(&slab_bar, 0); Rsrc = Rsm; }      // the slab has landed in shared memory
+#endif
 
     for (int t0 = 0; t0 < nw; t0 += TW) {
         const int tn = min(TW, nw - t0);
         __syncthreads();
-        for (int e = tid; e < tn * NP; e += nthr) { const int q = e / tn, j = e - q * tn; A[q * TWp + j] = Rs[t0 + j + (size_t)nw * q]; }
+        for (int e = tid; e < tn * NP; e += nthr) { const int q = e / tn, j = e - q * tn; A[q * TWp + j] = Rsrc[t0 + j + (size_t)nw * q]; }
         __syncthreads();
         for (int e = tid; e < tn * NP; e += nthr) {       // x axis
             const int kq = e / tn, j = e - kq * tn, qy = kq / L, kx = kq - qy * L;

@@ -1006,8 +1006,13 @@ static int launch_slab_conv(fdga_ctx* ctx, const DevChain& V, ColJob& job, int k
     while (TW > nF2 && bytes(TW) > budget) TW = std::max(nF2, (TW + 1) / 2);
     if (bytes(TW) > budget) { job.k1_direct = 1; return 0; }
     if (refresh_k1h(ctx)) return 1;
-    CK(cudaFuncSetAttribute(slab_conv_kernel<KIND, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(TW)));
-    slab_conv_kernel<KIND, CH><<<ctx->n_slabs[kind], 256, bytes(TW), ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->twL, ctx->ConvTabL[ctx->cur_lane], g, TW);
+    // TMA staging of the whole R slab (one cp.async.bulk per CTA) when it keeps >= 3 CTAs per SM resident; opt-in until measured
+    static const int tma_on = getenv("FDGA_CONV_TMA") ? atoi(getenv("FDGA_CONV_TMA")) : 0;
+    const size_t slab_bytes = (size_t)job.nw * g.NP * sizeof(C);
+    const int use_tma = (tma_on && slab_bytes % 16 == 0 && bytes(TW) + slab_bytes <= 72 * 1024) ? 1 : 0;
+    const size_t smem = bytes(TW) + (use_tma ? slab_bytes : 0);
+    CK(cudaFuncSetAttribute(slab_conv_kernel<KIND, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    slab_conv_kernel<KIND, CH><<<ctx->n_slabs[kind], 256, smem, ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->twL, ctx->ConvTabL[ctx->cur_lane], g, TW, use_tma);
     NOTE_LAUNCH("slab_conv_kernel");
     ctx->n_launch[cat]++; ctx->total_launches++;
     *tab = ctx->ConvTabL[ctx->cur_lane];

@@ -167,7 +167,7 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
                         const int TW = pass == 0 ? std::max(nw, nF2) : nF2;
                         const size_t bytes = ((size_t)2 * NP * (TW | 1) + (size_t)nF2 * NP + L) * sizeof(C);
                         cudaFuncSetAttribute(slab_conv_kernel<KIND, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-                        slab_conv_kernel<KIND, CH><<<1, 256, bytes>>>(Vd, job, sl, R, tw, tab, g, TW);
+                        slab_conv_kernel<KIND, CH><<<1, 256, bytes>>>(Vd, job, sl, R, tw, tab, g, TW, 0);
                         cudaError_t e = cudaDeviceSynchronize();
                         if (e != cudaSuccess) { printf("CUDA error (slab_conv) %s\n", cudaGetErrorString(e)); exit(2); }
                         for (int inu2 = 0; inu2 < nF2; ++inu2) for (int k2 = 0; k2 < NP; ++k2) {
