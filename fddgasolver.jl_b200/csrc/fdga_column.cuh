@@ -344,17 +344,50 @@ FDGA_HD C slab_own_entry(const DevChain& V, const ColJob& job, const Grid& g, co
     }
     return o;
 }
+// ---- TMA (bulk asynchronous copy) staging of one contiguous R slab into shared memory, completion on an mbarrier ------------
+// The slab [w, q | W, P] is ONE contiguous run (nw * NP * 16 bytes, 16-byte aligned), so a single cp.async.bulk issued by one
+// thread brings it in while the CTA builds its piece table; the tiles are then cut out of shared memory.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ unsigned fdga_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fdga_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(fdga_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fdga_tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(fdga_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(fdga_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(fdga_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fdga_mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(fdga_smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
 // one CTA per active slab (W on the K2 mesh, P): OwnTab[nu | W, P] and Rtot[W, P]
 template <int KIND, int CH>
 __global__ void __launch_bounds__(256)
 slab_own_kernel(const __grid_constant__ DevChain V, ColJob job, const int4* __restrict__ slabs, const C* __restrict__ R,
-                const C* __restrict__ T, C* __restrict__ OwnTab, C* __restrict__ Rtot, Grid g, int PC) {
-    extern __shared__ double sm_raw[];
-    C* Rq = reinterpret_cast<C*>(sm_raw);                 // [nw], then part[nF2 * nw]
+                const C* __restrict__ T, C* __restrict__ OwnTab, C* __restrict__ Rtot, Grid g, int PC, int use_tma) {
+    extern __shared__ __align__(128) double sm_raw[];
+    __shared__ __align__(8) unsigned long long slab_bar;
     __shared__ C s_sa;
     const int iW = slabs[blockIdx.x].x, iP = slabs[blockIdx.x].y;
     const int W = iW - (g.nK2b - 1), nw = job.nw, NP = g.NP, nF2 = 2 * g.nK2f, nB2 = 2 * g.nK2b - 1;
+    C* Rsm = reinterpret_cast<C*>(sm_raw);                // [nw][NP] TMA-staged slab (absent when !use_tma)
+    C* Rq = Rsm + (use_tma ? (size_t)nw * NP : 0);        // [nw], then part[PC * nw]
     const C* Rs = R + (size_t)nw * NP * (posB(W, job.slabW_N) + (size_t)(2 * job.slabW_N - 1) * iP);
+#if defined(__CUDA_ARCH__)
+    if (use_tma) {       // the slab is read twice (momentum sums, own-channel A' terms): one bulk copy, both passes from shared memory
+        if (threadIdx.x == 0) fdga_mbar_init(&slab_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) fdga_tma_load_1d(Rsm, Rs, (unsigned)((size_t)nw * NP * sizeof(C)), &slab_bar);
+        fdga_mbar_wait(&slab_bar, 0);
+        Rs = Rsm;
+    }
+#endif
     {   // Rq[iw] = sum_q Rs[iw, q]: all threads stream the slab (G momentum groups per frequency), partial sums meet in shared memory
         C* part0 = Rq + nw;
         const int G = (nw < (int)blockDim.x) ? min((int)blockDim.x / nw, PC) : 1;
@@ -497,28 +530,6 @@ __global__ void k1_dft_kernel(DevLevel lv, int L, int NP, const C* __restrict__ 
         out.p[blockIdx.y][kap + (size_t)NP * iW] = s0 + s1;
     }
 }
-
-// ---- TMA (bulk asynchronous copy) staging of one contiguous R slab into shared memory, completion on an mbarrier ------------
-// The slab [w, q | W, P] is ONE contiguous run (nw * NP * 16 bytes, 16-byte aligned), so a single cp.async.bulk issued by one
-// thread brings it in while the CTA builds its piece table; the tiles are then cut out of shared memory.
-#if defined(__CUDA_ARCH__)
-__device__ __forceinline__ unsigned fdga_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void fdga_mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(fdga_smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fdga_tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(fdga_smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(fdga_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(fdga_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fdga_mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned done = 0;
-    while (!done)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(fdga_smem_u32(bar)), "r"(parity) : "memory");
-}
-#endif
 
 // per-CTA piece table: conv_piece at nu = 0 plus its slope in nu (W0 is linear in nu), level / channel / weight
 struct ConvPieceS { int W0, dW0, sW, cx, cy, sk, sq, lev, r, nK1; double cf; };

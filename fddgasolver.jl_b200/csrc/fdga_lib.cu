@@ -977,10 +977,15 @@ template <int KIND, int CH>
 static void kernel_slab_own(fdga_ctx* ctx, const DevChain& V, const ColJob& job, int kind, const C* R, int cat) {
     const int PC = std::max(1, std::min(2 * ctx->g.nK2f, 2048 / job.nw));
     size_t smem = (size_t)job.nw * (1 + PC) * sizeof(C);
+    // TMA staging of the slab (read twice by the SDE jobs) while it keeps the kernel's residency: opt-in until measured
+    static const int tma_on = getenv("FDGA_OWN_TMA") ? atoi(getenv("FDGA_OWN_TMA")) : 0;
+    const size_t slab_bytes = (size_t)job.nw * ctx->g.NP * sizeof(C);
+    const int use_tma = (tma_on && slab_bytes <= 64 * 1024) ? 1 : 0;
+    if (use_tma) smem += slab_bytes;
     // long inner meshes (local solver, m_Pi_nu_factor = 6: nw = 3072 at BASELINE config 2) need the opt-in shared memory carve-out
     if (smem + 2048 > 48 * 1024) cudaFuncSetAttribute(slab_own_kernel<KIND, CH>,     // static + dynamic must stay under 48 KB without the opt-in
         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(smem, 227 * 1024));
-    slab_own_kernel<KIND, CH><<<ctx->n_slabs[kind], 256, smem, ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->TtabL[ctx->cur_lane], ctx->OwnTabL[ctx->cur_lane], ctx->RtotL[ctx->cur_lane], ctx->g, PC);
+    slab_own_kernel<KIND, CH><<<ctx->n_slabs[kind], 256, smem, ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->TtabL[ctx->cur_lane], ctx->OwnTabL[ctx->cur_lane], ctx->RtotL[ctx->cur_lane], ctx->g, PC, use_tma);
     NOTE_LAUNCH("slab_own_kernel");
     ctx->n_launch[cat]++; ctx->total_launches++;
 }
