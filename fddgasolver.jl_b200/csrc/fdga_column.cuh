@@ -115,9 +115,10 @@ FDGA_HD void clip_interval(const Lin& x, int lo, int hi, int& a, int& b) {   // 
     else if (x.s < 0) { a = max(a, x.x0 - hi); b = min(b, x.x0 - lo); }
     else if (x.x0 < lo || x.x0 > hi) { b = a - 1; }
 }
-// streaming correlation  sum_{win in [a, b]} tab[o + st * win] * Rq[win + Nin]  with two independent accumulators;
+// streaming correlation  sum_{win in [a, b]} tab[o + st * win] * Rq[(win + Nin) * rst]  with two independent accumulators
+// (rst = NP: the slab is stored with the inner momentum fastest, slab_at);
 // a constant table entry (st == 0) over the full chunk uses the pre-summed R of the chunk instead of a loop
-FDGA_HD C stream_sum(const C* __restrict__ tab, int o, int st, int a, int b, const C* __restrict__ Rq, int Nin,
+FDGA_HD C stream_sum(const C* __restrict__ tab, int o, int st, int a, int b, const C* __restrict__ Rq, int Nin, int rst,
                      int a0, int b0, C rs_chunk) {
     if (a > b) return zeroC();
     if (st == 0 && a == a0 && b == b0) return ldg(tab + o) * rs_chunk;
@@ -125,48 +126,48 @@ FDGA_HD C stream_sum(const C* __restrict__ tab, int o, int st, int a, int b, con
     int win = a;
 #pragma unroll 4
     for (; win + 1 <= b; win += 2) {
-        p0 += ldg(tab + (o + st * win)) * Rq[win + Nin];
-        p1 += ldg(tab + (o + st * (win + 1))) * Rq[win + 1 + Nin];
+        p0 += ldg(tab + (o + st * win)) * Rq[(size_t)(win + Nin) * rst];
+        p1 += ldg(tab + (o + st * (win + 1))) * Rq[(size_t)(win + 1 + Nin) * rst];
     }
-    if (win <= b) p0 += ldg(tab + (o + st * win)) * Rq[win + Nin];
+    if (win <= b) p0 += ldg(tab + (o + st * win)) * Rq[(size_t)(win + Nin) * rst];
     return p0 + p1;
 }
 // sum over iw in [w_lo, w_hi) of gamma_r(W2, v2, w2) * Rq[iw] at fixed momenta (all K switches on), W2/v2/w2 linear in win = iw - Nin.
 // Same box logic as chan_off: every term is a streaming correlation over its analytically clipped in-box interval; only the
 // (rare) K3 term is evaluated term by term inside the K2 band.  rs_chunk = sum of Rq over the chunk.
 FDGA_HD C chan_lin_sum(const DevLevel& lv, int r, const MomOff& m, Lin W2, Lin v2, Lin w2,
-                       const C* __restrict__ Rq, int Nin, int w_lo, int w_hi, C rs_chunk, bool withK1) {
+                       const C* __restrict__ Rq, int Nin, int rst, int w_lo, int w_hi, C rs_chunk, bool withK1) {
     const DevChan& c = lv.ch[r];
     const int a0 = w_lo - Nin, b0 = w_hi - 1 - Nin;      // inclusive win range of this chunk
     C part = zeroC();
     if (withK1) {
         int a = a0, b = b0; clip_interval(W2, -(lv.nK1 - 1), lv.nK1 - 1, a, b);
-        part = stream_sum(c.K1, m.oK1 + posB(W2.x0, lv.nK1), W2.s, a, b, Rq, Nin, a0, b0, rs_chunk);
+        part = stream_sum(c.K1, m.oK1 + posB(W2.x0, lv.nK1), W2.s, a, b, Rq, Nin, rst, a0, b0, rs_chunk);
     }
     int a = a0, b = b0; clip_interval(W2, -(lv.nK2b - 1), lv.nK2b - 1, a, b);
     if (a > b) return part;
     const int nB = 2 * lv.nK2b - 1, nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
     {
         int aa = a, bb = b; clip_interval(v2, -lv.nK2f, lv.nK2f - 1, aa, bb);
-        part += stream_sum(c.K2, m.oK2A + posB(W2.x0, lv.nK2b) + nB * posF(v2.x0, lv.nK2f), W2.s + nB * v2.s, aa, bb, Rq, Nin, a0, b0, rs_chunk);
+        part += stream_sum(c.K2, m.oK2A + posB(W2.x0, lv.nK2b) + nB * posF(v2.x0, lv.nK2f), W2.s + nB * v2.s, aa, bb, Rq, Nin, rst, a0, b0, rs_chunk);
     }
     {
         int aa = a, bb = b; clip_interval(w2, -lv.nK2f, lv.nK2f - 1, aa, bb);
-        part += stream_sum(c.K2, m.oK2B + posB(W2.x0, lv.nK2b) + nB * posF(w2.x0, lv.nK2f), W2.s + nB * w2.s, aa, bb, Rq, Nin, a0, b0, rs_chunk);
+        part += stream_sum(c.K2, m.oK2B + posB(W2.x0, lv.nK2b) + nB * posF(w2.x0, lv.nK2f), W2.s + nB * w2.s, aa, bb, Rq, Nin, rst, a0, b0, rs_chunk);
     }
     {   // K3: short loop inside the K3 Omega-box band, explicit box tests (see DESIGN.md "toolchain pitfall")
         int aa = a, bb = b; clip_interval(W2, -(lv.nK3b - 1), lv.nK3b - 1, aa, bb);
         for (int win = aa; win <= bb; ++win) {
             const int Wc = W2.x0 + W2.s * win, vc = v2.x0 + v2.s * win, wc = w2.x0 + w2.s * win;
             if (inF(vc, lv.nK2f) && inF(wc, lv.nK2f) && inF(vc, lv.nK3f) && inF(wc, lv.nK3f))
-                part += ldg(c.K3 + (m.oK3 + posB(Wc, lv.nK3b) + nB3 * (posF(vc, lv.nK3f) + nF3 * posF(wc, lv.nK3f)))) * Rq[win + Nin];
+                part += ldg(c.K3 + (m.oK3 + posB(Wc, lv.nK3b) + nB3 * (posF(vc, lv.nK3f) + nF3 * posF(wc, lv.nK3f)))) * Rq[(size_t)(win + Nin) * rst];
         }
     }
     return part;
 }
 // same for gamma_r(W, v, w) - gamma_r(W, inf, w): K2[W, v | P, k] + K3[W, v, w | P] inside the boxes
 FDGA_HD C chan_lin_sum_diff_v(const DevLevel& lv, int r, const MomOff& m, Lin W2, Lin v2, Lin w2,
-                              const C* __restrict__ Rq, int Nin, int w_lo, int w_hi, C rs_chunk) {
+                              const C* __restrict__ Rq, int Nin, int rst, int w_lo, int w_hi, C rs_chunk) {
     const DevChan& c = lv.ch[r];
     const int a0 = w_lo - Nin, b0 = w_hi - 1 - Nin;
     int a = a0, b = b0;
@@ -174,12 +175,12 @@ FDGA_HD C chan_lin_sum_diff_v(const DevLevel& lv, int r, const MomOff& m, Lin W2
     clip_interval(v2, -lv.nK2f, lv.nK2f - 1, a, b);
     if (a > b) return zeroC();
     const int nB = 2 * lv.nK2b - 1, nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
-    C part = stream_sum(c.K2, m.oK2A + posB(W2.x0, lv.nK2b) + nB * posF(v2.x0, lv.nK2f), W2.s + nB * v2.s, a, b, Rq, Nin, a0, b0, rs_chunk);
+    C part = stream_sum(c.K2, m.oK2A + posB(W2.x0, lv.nK2b) + nB * posF(v2.x0, lv.nK2f), W2.s + nB * v2.s, a, b, Rq, Nin, rst, a0, b0, rs_chunk);
     int aa = a, bb = b; clip_interval(W2, -(lv.nK3b - 1), lv.nK3b - 1, aa, bb);
     for (int win = aa; win <= bb; ++win) {
         const int Wc = W2.x0 + W2.s * win, vc = v2.x0 + v2.s * win, wc = w2.x0 + w2.s * win;
         if (inF(wc, lv.nK2f) && inF(vc, lv.nK3f) && inF(wc, lv.nK3f))
-            part += ldg(c.K3 + (m.oK3 + posB(Wc, lv.nK3b) + nB3 * (posF(vc, lv.nK3f) + nF3 * posF(wc, lv.nK3f)))) * Rq[win + Nin];
+            part += ldg(c.K3 + (m.oK3 + posB(Wc, lv.nK3b) + nB3 * (posF(vc, lv.nK3f) + nF3 * posF(wc, lv.nK3f)))) * Rq[(size_t)(win + Nin) * rst];
     }
     return part;
 }
@@ -340,12 +341,12 @@ FDGA_HD C slab_own_entry(const DevChain& V, const ColJob& job, const Grid& g, co
     for (int iq = 0; iq < g.NP; ++iq) for (int iw = 0; iw < nw; ++iw) {
         C t = own_A_term<KIND, CH>(V, job, g, W, iP, iw - job.Ninner, iq) + own_K3_term<KIND, CH>(V, job, g, W, iP, nu, iw - job.Ninner);
         if (T != nullptr) t += T[iw + nw * (inu + nF2 * iW)];
-        o += t * Rs[iw + (size_t)nw * iq];
+        o += t * Rs[slab_at(iw, iq, g.NP)];
     }
     return o;
 }
 // ---- TMA (bulk asynchronous copy) staging of one contiguous R slab into shared memory, completion on an mbarrier ------------
-// The slab [w, q | W, P] is ONE contiguous run (nw * NP * 16 bytes, 16-byte aligned), so a single cp.async.bulk issued by one
+// The slab [q, w | W, P] is ONE contiguous run (nw * NP * 16 bytes, 16-byte aligned), so a single cp.async.bulk issued by one
 // thread brings it in while the CTA builds its piece table; the tiles are then cut out of shared memory.
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ unsigned fdga_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -388,31 +389,24 @@ slab_own_kernel(const __grid_constant__ DevChain V, ColJob job, const int4* __re
         Rs = Rsm;
     }
 #endif
-    {   // Rq[iw] = sum_q Rs[iw, q]: all threads stream the slab (G momentum groups per frequency), partial sums meet in shared memory
-        C* part0 = Rq + nw;
-        const int G = (nw < (int)blockDim.x) ? min((int)blockDim.x / nw, PC) : 1;
-        if ((int)threadIdx.x < G * nw) {
-            const int gq = threadIdx.x / nw, iw = threadIdx.x - gq * nw;
-            C s = zeroC();
-            for (int iq = gq; iq < NP; iq += G) s += Rs[iw + (size_t)nw * iq];
-            part0[gq * nw + iw] = s;
-        }
-        if (G == 1) for (int iw = threadIdx.x + blockDim.x; iw < nw; iw += blockDim.x) {      // nw > blockDim.x: remaining frequencies
-            C s = zeroC();
-            for (int iq = 0; iq < NP; ++iq) s += Rs[iw + (size_t)nw * iq];
-            part0[iw] = s;
+    {   // Rq[iw] = sum_q Rs[q, iw]: one warp per inner frequency at a time, lanes over the (contiguous) inner momentum
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+        for (int iw = wid; iw < nw; iw += nwarp) {
+            C s0 = zeroC(), s1 = zeroC();
+            const C* row = Rs + (size_t)NP * iw;
+            int iq = lane;
+            for (; iq + 32 < NP; iq += 64) { s0 += row[iq]; s1 += row[iq + 32]; }
+            if (iq < NP) s0 += row[iq];
+            s0 += s1;
+            for (int o = 16; o > 0; o >>= 1) { s0.x += __shfl_xor_sync(0xffffffffu, s0.x, o); s0.y += __shfl_xor_sync(0xffffffffu, s0.y, o); }
+            if (lane == 0) Rq[iw] = s0;
         }
         __syncthreads();
-        for (int iw = threadIdx.x; iw < nw; iw += blockDim.x) {
-            C s = zeroC();
-            for (int gq = 0; gq < G; ++gq) s += part0[gq * nw + iw];
-            Rq[iw] = s;
-        }
     }
     C sa = zeroC();
     if (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH)
 #pragma unroll 4
-        for (int t = threadIdx.x; t < nw * NP; t += blockDim.x) sa += own_A_term<KIND, CH>(V, job, g, W, iP, t % nw - job.Ninner, t / nw) * Rs[t];
+        for (int t = threadIdx.x; t < nw * NP; t += blockDim.x) sa += own_A_term<KIND, CH>(V, job, g, W, iP, t / NP - job.Ninner, t % NP) * Rs[t];
     sa = block_reduce(sa);
     if (threadIdx.x == 0) s_sa = sa;
     __syncthreads();
@@ -498,7 +492,7 @@ FDGA_HD C k1_cross_direct(const DevChain& V, const ColJob& job, const Grid& g, c
                     const int iPp = foldidx(pc.cx + pc.sk * kx + pc.sq * qx, pc.cy + pc.sk * ky + pc.sq * qy, L);
                     for (int iw = 0; iw < nw; ++iw) {
                         const int Wc = pc.W0 + pc.sW * (iw - job.Ninner);
-                        if (inB(Wc, lv.nK1)) part += ldg(lv.ch[r].K1 + (posB(Wc, lv.nK1) + (2 * lv.nK1 - 1) * iPp)) * Rs[iw + (size_t)nw * iq];
+                        if (inB(Wc, lv.nK1)) part += ldg(lv.ch[r].K1 + (posB(Wc, lv.nK1) + (2 * lv.nK1 - 1) * iPp)) * Rs[slab_at(iw, iq, NP)];
                     }
                 }
                 acc += part * FM::coef(f);
@@ -596,7 +590,7 @@ slab_conv_kernel(const __grid_constant__ DevChain V, ColJob job, const int4* __r
     for (int t0 = 0; t0 < nw; t0 += TW) {
         const int tn = min(TW, nw - t0);
         __syncthreads();
-        for (int e = tid; e < tn * NP; e += nthr) { const int q = e / tn, j = e - q * tn; A[q * TWp + j] = Rsrc[t0 + j + (size_t)nw * q]; }
+        for (int e = tid; e < tn * NP; e += nthr) { const int j = e / NP, q = e - j * NP; A[q * TWp + j] = Rsrc[slab_at(t0 + j, q, NP)]; }
         __syncthreads();
         for (int e = tid; e < tn * NP; e += nthr) {       // x axis
             const int kq = e / tn, j = e - kq * tn, qy = kq / L, kx = kq - qy * L;
@@ -761,8 +755,8 @@ FDGA_HD void column_thread(const DevChain& V, const ColJob& job, const ColDev& c
                         job_freq_args<KIND, CH>(Wg[i], nug[i], 0, v_a, w_a); job_freq_args<KIND, CH>(Wg[i], nug[i], 1, v_b, w_b);
                         convert_freq(Wg[i], v_a, w_a, form, r, W0, v0, w0); convert_freq(Wg[i], v_b, w_b, form, r, W1, v1, w1);
                         Lin lW = {W0, W1 - W0}, lv2 = {v0, v1 - v0}, lw2 = {w0, w1 - w0};
-                        const C* Rq = Rp + slab_stride * posB(Wg[i], job.slabW_N) + (size_t)nw * iq;
-                        acc[i] += chan_lin_sum(lv, r, mo, lW, lv2, lw2, Rq, job.Ninner, w_lo, w_hi, rs_chunk, withK1) * cf;
+                        const C* Rq = Rp + slab_stride * posB(Wg[i], job.slabW_N) + iq;      // element win of this q: Rq[(win + Nin) * NP]
+                        acc[i] += chan_lin_sum(lv, r, mo, lW, lv2, lw2, Rq, job.Ninner, NP, w_lo, w_hi, rs_chunk, withK1) * cf;
                     }
                 }
             }

@@ -66,6 +66,9 @@ struct DevChan {
     const C *K2sww;   // [W,v]      mean_{P,k} K2
     const C *K3sw;    // [W,v,w]    mean_P K3[W,v,w,P]
     const C *K1h;     // [kappa,W]  sum_P K1[W,P] exp(-2 pi i kappa.P / L)  (kappa fast; fdga_column.cuh: slab_conv_kernel)
+    const C *K2m[4];  // K2 in the four momentum-fastest layouts ML_P, ML_K, ML_S, ML_D (fdga_qlane.cuh); null until built
+    const C *K3m;     // [P,W,v,w]  K3 with the transfer momentum fastest
+    const C *K1m;     // [P,W]      K1 with the transfer momentum fastest
 };
 struct DevLevel {
     int type, nK1, nK2b, nK2f, nK3b, nK3f, pad0, pad1;

@@ -141,14 +141,17 @@ __global__ void swave_tables2_kernel(DevLevel lv, int NP, SwOut out) {
     out.p[r][2][i] = s / (double)NP;
 }
 
-// ---- bubble auxiliaries: PiT[w,q,W,P] (slab-contiguous copy) and Pisw[W,w,P] = mean_k Pi[W,w,P,k] ----
+// ---- bubble auxiliaries: PiT[q,w,W,P] (slab-contiguous copy, inner momentum fastest) and Pisw[W,w,P] = mean_k Pi[W,w,P,k] ----
+// Slab layout used by every contraction kernel: element (w, q) of the slab (W, P) sits at  q + NP * w  (q fastest), so that a
+// warp whose lanes run over the inner momentum q reads one contiguous run per inner frequency.
+FDGA_HD size_t slab_at(int iw, int iq, int NP) { return (size_t)iq + (size_t)NP * iw; }
 __global__ void pi_transpose_kernel(const C* __restrict__ Pi, C* __restrict__ PiT, int nB, int nF, int NP) {
     // one thread per output element, output index contiguous
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long n = (long long)nB * nF * NP * NP;
     if (i >= n) return;
     long long t = i;
-    int iw = t % nF; t /= nF; int iq = t % NP; t /= NP; int iW = t % nB; int iP = t / nB;
+    int iq = t % NP; t /= NP; int iw = t % nF; t /= nF; int iW = t % nB; int iP = t / nB;
     PiT[i] = Pi[iW + (size_t)nB * (iw + (size_t)nF * (iP + (size_t)NP * iq))];
 }
 __global__ void pi_swave_kernel(const C* __restrict__ Pi, C* __restrict__ Pisw, int nB, int nF, int NP) {
@@ -165,7 +168,7 @@ __global__ void pi_swave_kernel(const C* __restrict__ Pi, C* __restrict__ Pisw, 
 //  RK_MF_K1 : Pi0 * FL(W, w~, inf; P, q~, k0)                                           BSEa_K1.jl:33-37
 //  RK_MF_K2 : Pi0 * FL(W, w, inf; P, q, k0)                                             BSEa_K2.jl:100-104
 //  RK_LK2   : Pi0 * F0(W, w, inf; P, q, k0), w on the K2 nu-mesh                        BSEa_K2.jl:38-41
-// Rt layout: [iw + nw*(iq + NP*(iWo + nBo*iP))], W on the OUTPUT bosonic mesh (N = No).
+// Rt layout: [iq + NP*(iw + nw*(iWo + nBo*iP))] (slab_at), W on the OUTPUT bosonic mesh (N = No).
 //  RK_LK2_LOC : Pi0 * F0(W, w~, inf), w on the bubble nu-mesh (local solver)                src/BSEa/BSEa_K2.jl:27-30
 //  RK_1L    : (Pi - Pi0) * F0(W, w~, inf; P, q~, k0)  (fd branch of the 1-loop variants)   BSE_1loop.jl:41-46,104-109
 enum { RK_FD = 0, RK_MF_K1 = 1, RK_MF_K2 = 2, RK_LK2 = 3, RK_LK2_LOC = 4, RK_1L = 5 };
@@ -181,12 +184,12 @@ __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const _
     long long n = (long long)nw * g.NP * nslabs;
     if (i >= n) return;
     long long t = i;
-    int iw = t % nw; t /= nw; int iq = t % g.NP; int sl = (int)(t / g.NP);
+    int iq = t % g.NP; t /= g.NP; int iw = t % nw; int sl = (int)(t / nw);
     const int4 s2 = slabs[sl];
     const int iWo = s2.x, iP = s2.y;
     int W = iWo - (No - 1), w = iw - Ninner;
     int Px = iP % g.L, Py = iP / g.L, qx = iq % g.L, qy = iq / g.L;
-    size_t pidx = posF(w, g.nPiF) + (size_t)nFP * (iq + (size_t)g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP));
+    size_t pidx = slab_at(posF(w, g.nPiF), iq, g.NP) + (size_t)nFP * g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP);
     Arg a;
     a.W = W; a.w = FDGA_INF; a.Px = Px; a.Py = Py; a.qx = 0; a.qy = 0;
     if (KIND == RK_FD || KIND == RK_MF_K1 || KIND == RK_LK2_LOC || KIND == RK_1L) {   // crossed arguments (_crossing, BSE_templates.jl:4-6)
@@ -208,7 +211,7 @@ __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const _
     } else {
         r = Pi0T[pidx] * eval_vertex<false>(FL, 0, CH, SP, a, FL_ALL);
     }
-    Rt[iw + (size_t)nw * (iq + (size_t)g.NP * (iWo + (size_t)nBo * iP))] = r;
+    Rt[slab_at(iw, iq, g.NP) + (size_t)nw * g.NP * (iWo + (size_t)nBo * iP)] = r;
 }
 
 // ---- BSE_K1!: src/nonlocal_2/BSEa/BSEa_K1.jl:19-52.  One CTA per class representative (W, P) ------
@@ -224,7 +227,7 @@ __global__ void bse_k1_kernel(const __grid_constant__ DevChain Fleft, const C* _
     const C* slab = Rt + (size_t)nw * g.NP * (iW + (size_t)nB1 * iP);
     C acc = zeroC();
     for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
-        int iw = t % nw, iq = t / nw;
+        int iq = t % g.NP, iw = t / g.NP;
         Arg a; a.W = W; a.v = FDGA_INF; a.w = iw - g.nPiF; a.Px = Px; a.Py = Py; a.kx = 0; a.ky = 0; a.qx = iq % g.L; a.qy = iq / g.L;
         C Fl = eval_vertex<false>(Fleft, 0, CH, SP, a, FL_ALL);
         acc += Fl * slab[t];
@@ -248,7 +251,7 @@ __global__ void bse_lk2_kernel(const __grid_constant__ DevChain F, const C* __re
     const C* slab = Rt + (size_t)nw * g.NP * (iW + (size_t)nB2 * iP);
     C acc = zeroC();
     for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
-        int iw = t % nw, iq = t / nw;
+        int iq = t % g.NP, iw = t / g.NP;
         int w = iw - g.nK2f, qx = iq % g.L, qy = iq / g.L;
         Arg a; a.W = W; a.v = v; a.Px = Px; a.Py = Py; a.kx = kx; a.ky = ky;
         a.w = (CH == CH_P) ? W - w - 1 : w;
@@ -276,7 +279,7 @@ __global__ void bse_k2_kernel(const __grid_constant__ DevChain Fleft, const C* _
     const C* slab = Rt + (size_t)nw * g.NP * (iW + (size_t)nB2 * iP);
     C acc = zeroC();
     for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
-        int iw = t % nw, iq = t / nw;
+        int iq = t % g.NP, iw = t / g.NP;
         int w = iw - g.nPiF, qx = iq % g.L, qy = iq / g.L;
         Arg a; a.W = W; a.v = v; a.Px = Px; a.Py = Py; a.kx = kx; a.ky = ky;
         if (MF) {
@@ -294,7 +297,7 @@ __global__ void bse_k2_kernel(const __grid_constant__ DevChain Fleft, const C* _
 
 // ---- BSE_K1_new!: src/nonlocal_2/BSEa/BSEa_K1.jl:62-113, K1 = (U + K1 + K2') Pi U.  One CTA per representative (W, P).
 //  fd   : [F(W,inf,w;P,k0,q) Pi - F0(W,inf,w;P,k0,q) Pi0] U          mfRG : [F - F0] Pi U
-//  PiT / Pi0T are the transposed bubbles [w, q | W, P] (W on the bubble mesh, which is the K1 mesh).
+//  PiT / Pi0T are the transposed bubbles [q, w | W, P] (W on the bubble mesh, which is the K1 mesh).
 template <int CH>
 __global__ void bse_k1_new_kernel(const __grid_constant__ DevChain F, const __grid_constant__ DevChain F0,
                                   const C* __restrict__ Pi0T, const C* __restrict__ PiT, C* __restrict__ repvals,
@@ -308,7 +311,7 @@ __global__ void bse_k1_new_kernel(const __grid_constant__ DevChain F, const __gr
     const size_t off = (size_t)nw * g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP);
     C acc = zeroC();
     for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
-        int iw = t % nw, iq = t / nw;
+        int iq = t % g.NP, iw = t / g.NP;
         Arg a; a.W = W; a.v = FDGA_INF; a.w = iw - g.nPiF; a.Px = Px; a.Py = Py; a.kx = 0; a.ky = 0; a.qx = iq % g.L; a.qy = iq / g.L;
         C Fl = eval_vertex<false>(F, 0, CH, SP, a, FL_ALL);
         C F0l = eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
@@ -335,13 +338,13 @@ __global__ void bse_k2_new_kernel(const __grid_constant__ DevChain F, const __gr
     const size_t off = (size_t)nFP * g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP);
     C acc = zeroC();
     for (int t = threadIdx.x; t < nF2 * g.NP; t += blockDim.x) {
-        int iw = t % nF2, iq = t / nF2;
+        int iq = t % g.NP, iw = t / g.NP;
         int w = iw - g.nK2f;
         Arg a; a.W = W; a.v = v; a.w = w; a.Px = Px; a.Py = Py; a.kx = kx; a.ky = ky; a.qx = iq % g.L; a.qy = iq / g.L;
         C Fl = eval_vertex<false>(F, 0, CH, SP, a, FL_ALL), F0l = eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
         a.v = FDGA_INF;
         Fl = Fl - eval_vertex<false>(F, 0, CH, SP, a, FL_ALL); F0l = F0l - eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
-        size_t pidx = off + posF(w, g.nPiF) + (size_t)nFP * iq;
+        size_t pidx = off + slab_at(posF(w, g.nPiF), iq, g.NP);
         if (mfrg) acc += (Fl - F0l) * PiT[pidx];
         else      acc += Fl * PiT[pidx] - F0l * Pi0T[pidx];
     }
@@ -486,7 +489,7 @@ __global__ void sde_L_kernel(const __grid_constant__ DevChain V, int level, cons
     const bool is_core = V.lev[level].type == LV_CORE;
     C acc = zeroC();
     for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
-        int iw = t % nw, iq = t / nw;
+        int iq = t % g.NP, iw = t / g.NP;
         int w = iw - g.nPiF, qx = iq % g.L, qy = iq / g.L;
         C d;
         Arg a; a.W = W; a.Px = Px; a.Py = Py;

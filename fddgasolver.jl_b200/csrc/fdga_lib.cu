@@ -2,7 +2,7 @@
 // Reference call structure being replaced: iterate_solver! (src/solve.jl:4-116), BSE_templates.jl:12-180,
 // SDE! (src/SDE.jl:3-48), mfRGLinearMap (src/mfRG.jl:34-89).
 #include "../../include/fdga.h"
-#include "fdga_column.cuh"
+#include "fdga_qlane.cuh"
 #include "fdga_krylov.cuh"
 
 #include <cstdio>
@@ -29,6 +29,8 @@ struct LevelBuf {
     C* sw[3][4];         // [channel][K1sw, K2swk, K2sww, K3sw]
     C* K1h[3];           // [channel] momentum DFT of K1 (slab_conv_kernel)
     bool k1h_dirty;
+    C* mom[3][ML_COUNT];  // [channel][layout] momentum-fastest copies of K2 / K3 / K1 (fdga_qlane.cuh), allocated by alloc_mom
+    unsigned mom_valid[3]; // bit = layout whose copy is current
     C* core[4];
     size_t corelen;
     bool sw_dirty;
@@ -46,6 +48,7 @@ struct SymGroup {
     std::vector<long long> o_offsets, o_index; std::vector<unsigned char> o_ops;   // as registered by the caller
     // columns (W, P, k) of this rank's class representatives (K2-shaped groups only)
     int ncol; int *d_col_iW, *d_col_iP, *d_col_ik, *d_col_start, *d_rep_inu, *d_rep_cls; int ngrp; int* d_grp_start;
+    int nrep; int4* d_reps;   // the same representatives, slab-major, one per warp of qlane_kernel
 };
 struct TimedEvent { cudaEvent_t a, b; int cat; };
 struct Pending { SymGroup* s; C* rep; C* out; int kind, ch; bool expanded; };
@@ -105,6 +108,8 @@ struct fdga_ctx {
     bool defer; std::vector<struct Pending> pending;   // batched SG finishes (one NCCL group per BSE stage)
     int n_nl2;               // leading NL2 levels of the F chain
     int opt_direct_k1;       // FDGA_OPT_DIRECT_K1
+    int opt_qlane;           // FDGA_OPT_QLANE
+    unsigned mom_mask[3];    // momentum layouts (per table channel) any q-lane job reads
     // per lane: TtabL = momentum-independent left-factor table [nw, nF2, nB2]; OwnTabL[nu | W, P], RtotL[W, P] = per-slab hoisted
     // pieces (W on the K2 mesh); ConvTabL[k, nu | W, P] = cross-channel K1 pieces (slab_conv_kernel)
     C* twL; C* twLG;         // DFT twiddles exp(2 pi i j / n) for n = L, LG
@@ -160,7 +165,7 @@ static size_t lenK(const fdga_level_desc& d, int cls, int NP, bool nl2) {
 
 static int alloc_level(fdga_ctx* ctx, LevelBuf& lb, const fdga_level_desc& d) {
     memset(&lb, 0, sizeof(lb));
-    lb.d = d; lb.sw_dirty = true; lb.k1h_dirty = true;
+    lb.d = d; lb.sw_dirty = true; lb.k1h_dirty = true; lb.mom_valid[0] = lb.mom_valid[1] = lb.mom_valid[2] = 0;
     int NP = ctx->g.NP;
     if (d.type == FDGA_LV_CORE) {
         lb.corelen = (size_t)(2 * d.nK3[0] - 1) * (2 * d.nK3[1]) * (2 * d.nK3[1]);
@@ -190,6 +195,7 @@ static void free_level(LevelBuf& lb) {
     cudaFree(lb.block);
     for (int ch = 0; ch < 3; ch++) for (int j = 0; j < 4; j++) cudaFree(lb.sw[ch][j]);
     for (int ch = 0; ch < 3; ch++) cudaFree(lb.K1h[ch]);
+    for (int ch = 0; ch < 3; ch++) for (int j = 0; j < ML_COUNT; j++) cudaFree(lb.mom[ch][j]);
     for (int i = 0; i < 4; i++) cudaFree(lb.core[i]);
 }
 
@@ -201,6 +207,8 @@ static DevLevel dev_level(const LevelBuf& lb) {
         d.ch[ch].K1 = lb.K[ch][0]; d.ch[ch].K2 = lb.K[ch][1]; d.ch[ch].K3 = lb.K[ch][2];
         d.ch[ch].K1sw = lb.sw[ch][0]; d.ch[ch].K2swk = lb.sw[ch][1]; d.ch[ch].K2sww = lb.sw[ch][2]; d.ch[ch].K3sw = lb.sw[ch][3];
         d.ch[ch].K1h = lb.K1h[ch];
+        for (int j = 0; j < 4; j++) d.ch[ch].K2m[j] = lb.mom[ch][j];
+        d.ch[ch].K3m = lb.mom[ch][ML_K3]; d.ch[ch].K1m = lb.mom[ch][ML_K1];
     }
     for (int i = 0; i < 4; i++) d.core[i] = lb.core[i];
     if (lb.d.type == FDGA_LV_CORE && lb.corelen == 0) { d.nK3b = 0; d.nK3f = 0; }
@@ -260,7 +268,7 @@ static int refresh_fsum(fdga_ctx* ctx) {
     Scope sc(ctx, FDGA_T_MISC);
     LAUNCH(FDGA_T_MISC, axpby_kernel, nblk(ctx->Fsum.blocklen, 256), 256, ctx->Fsum.block, ctx->lev[0].block, 1.0, ctx->lev[1].block, 1.0, (long long)ctx->Fsum.blocklen);
     CK(cudaGetLastError());
-    ctx->fsum_dirty = false; ctx->Fsum.k1h_dirty = true;
+    ctx->fsum_dirty = false; ctx->Fsum.k1h_dirty = true; ctx->Fsum.mom_valid[0] = ctx->Fsum.mom_valid[1] = ctx->Fsum.mom_valid[2] = 0;
     return 0;
 }
 // momentum DFT of the K1 tables of every NL2 level a column job may read (and of the merged level)
@@ -279,6 +287,49 @@ static int refresh_k1h(fdga_ctx* ctx) {
         lb.k1h_dirty = false;
     }
     CK(cudaGetLastError());
+    return 0;
+}
+// ---- q-lane kernel: momentum-fastest copies of the vertex tables -------------------------------------------------------
+static bool qlane_enabled(fdga_ctx* ctx) {
+    if (ctx->opt_local || ctx->opt_generic || ctx->opt_qlane == 0) return false;
+    if (ctx->opt_qlane == 1) return true;
+    return ctx->g.NP >= 16;
+}
+// buffers are allocated once (device pointers inside DevChain copies must stay valid); contents are refreshed lazily
+static int alloc_mom(fdga_ctx* ctx, LevelBuf& lb) {
+    if (lb.d.type != FDGA_LV_NL2) return 0;
+    for (int ch = 0; ch < 3; ch++) for (int j = 0; j < ML_COUNT; j++) {
+        if (!(ctx->mom_mask[ch] & (1u << j)) || lb.mom[ch][j]) continue;
+        const size_t n = j == ML_K1 ? lb.len[0] : (j == ML_K3 ? lb.len[2] : lb.len[1]);
+        CK(cudaMalloc(&lb.mom[ch][j], n * sizeof(C)));
+    }
+    return 0;
+}
+static int alloc_mom_all(fdga_ctx* ctx) {
+    for (int l = 0; l < ctx->n_nl2; l++) if (alloc_mom(ctx, ctx->lev[l])) return 1;
+    if (ctx->has_fsum && alloc_mom(ctx, ctx->Fsum)) return 1;
+    return 0;
+}
+static int ensure_mom(fdga_ctx* ctx, LevelBuf& lb) {
+    if (lb.d.type != FDGA_LV_NL2) return 0;
+    MomOut out; bool any = false;
+    for (int ch = 0; ch < 3; ch++) for (int j = 0; j < ML_COUNT; j++) {
+        const bool need = (ctx->mom_mask[ch] & (1u << j)) && !(lb.mom_valid[ch] & (1u << j));
+        out.p[ch][j] = need ? lb.mom[ch][j] : nullptr;
+        if (need && !lb.mom[ch][j]) FAIL("q-lane kernel: momentum layouts not allocated");
+        any = any || need;
+    }
+    if (!any) return 0;
+    Scope sc(ctx, FDGA_T_SWAVE);
+    LAUNCH(FDGA_T_SWAVE, mom_layout_kernel, dim3(nblk((long long)std::max(lb.len[0], std::max(lb.len[1], lb.len[2])), 256), 3 * ML_COUNT), 256, dev_level(lb), ctx->g.L, ctx->g.NP, out);
+    CK(cudaGetLastError());
+    for (int ch = 0; ch < 3; ch++) lb.mom_valid[ch] = ctx->mom_mask[ch];
+    return 0;
+}
+static int refresh_mom_all(fdga_ctx* ctx) {
+    if (!qlane_enabled(ctx)) return 0;
+    for (int l = 0; l < ctx->n_nl2; l++) if (ensure_mom(ctx, ctx->lev[l])) return 1;
+    if (ctx->has_fsum && !ctx->fsum_dirty && ensure_mom(ctx, ctx->Fsum)) return 1;
     return 0;
 }
 static int refresh_pi(fdga_ctx* ctx, int which) {
@@ -355,8 +406,8 @@ static int dft4(fdga_ctx* ctx, C* a, C* b, long long pre, int sgn, double scale,
 
 // group this rank's class representatives of a K2-shaped symmetry group into columns (W, P, k) of <= FDGA_NV reps
 static int build_columns(fdga_ctx* ctx, SymGroup& s) {
-    cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); cudaFree(s.d_grp_start);
-    s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = s.d_grp_start = nullptr; s.ncol = 0; s.ngrp = 0;
+    cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); cudaFree(s.d_grp_start); cudaFree(s.d_reps);
+    s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = s.d_grp_start = nullptr; s.ncol = 0; s.ngrp = 0; s.d_reps = nullptr; s.nrep = 0;
     long long c0 = (long long)ctx->rank * s.chunk, c1 = c0 + s.chunk;
     if (c0 > s.ncls) c0 = s.ncls; if (c1 > s.ncls) c1 = s.ncls;
     const int nB2 = 2 * ctx->g.nK2b - 1, nF2 = 2 * ctx->g.nK2f, NP = ctx->g.NP;
@@ -367,6 +418,18 @@ static int build_columns(fdga_ctx* ctx, SymGroup& s) {
         int iW = idx % nB2; idx /= nB2; int inu = idx % nF2; idx /= nF2; int iP = idx % NP; int ik = (int)(idx / NP);
         Rep r; r.key = ((long long)ik * NP + iP) * nB2 + iW; r.inu = inu; r.cls = (int)c;
         reps.push_back(r);
+    }
+    {   // q-lane kernel: one warp per representative, slab-major (P, W, k, nu) so that the warps of a CTA share their R rows
+        std::vector<int4> list; list.reserve(reps.size());
+        for (auto& r : reps) {
+            long long key = r.key; const int iW = (int)(key % nB2); key /= nB2; const int iP = (int)(key % NP), ik = (int)(key / NP);
+            list.push_back(make_int4(iW | (r.inu << 16), iP, ik, r.cls));
+        }
+        std::stable_sort(list.begin(), list.end(), [&](const int4& a, const int4& b) {
+            const long long ka = (((long long)a.y * nB2 + (a.x & 0xffff)) * NP + a.z) * nF2 + (a.x >> 16), kb = (((long long)b.y * nB2 + (b.x & 0xffff)) * NP + b.z) * nF2 + (b.x >> 16);
+            return ka < kb; });
+        s.nrep = (int)list.size();
+        if (s.nrep) { CK(cudaMalloc(&s.d_reps, list.size() * sizeof(int4))); CK(cudaMemcpy(s.d_reps, list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice)); }
     }
     std::stable_sort(reps.begin(), reps.end(), [](const Rep& a, const Rep& b) { return a.key < b.key; });
     std::vector<int> ciW, ciP, cik, cstart, rinu, rcls;
@@ -470,7 +533,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     fdga_ctx* ctx = new fdga_ctx();
     ctx->dims = *dims; ctx->device = device; ctx->nlev = dims->nlev;
     ctx->nranks = 1; ctx->rank = 0; ctx->comm = nullptr; memset(&ctx->nccl, 0, sizeof(ctx->nccl));
-    ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0; ctx->opt_generic = 0; ctx->opt_hartree_once = 0; ctx->opt_local = 0; ctx->opt_direct_k1 = 0; ctx->defer = false;
+    ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0; ctx->opt_generic = 0; ctx->opt_hartree_once = 0; ctx->opt_local = 0; ctx->opt_direct_k1 = 0; ctx->opt_qlane = getenv("FDGA_QLANE") ? atoi(getenv("FDGA_QLANE")) : -1; ctx->defer = false;
     memset(ctx->t_ms, 0, sizeof(ctx->t_ms)); memset(ctx->n_launch, 0, sizeof(ctx->n_launch));
     Grid& g = ctx->g;
     g.T = dims->T; g.L = dims->nq; g.NP = dims->nq * dims->nq; g.nPiB = dims->nPiB; g.nPiF = dims->nPiF;
@@ -526,6 +589,14 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
         if (ctx->has_fsum && alloc_level(ctx, ctx->Fsum, d0)) { g_create_error = ctx->err; delete ctx; return 1; }
     }
     ctx->n_nl2 = 0; while (ctx->n_nl2 < ctx->nlev && dims->lev[ctx->n_nl2].type == FDGA_LV_NL2) ctx->n_nl2++;
+    {   // momentum layouts read by any q-lane job (fdga_qlane.cuh); K1 copies are tiny and always kept (FDGA_OPT_DIRECT_K1)
+        unsigned* m = ctx->mom_mask; m[0] = m[1] = m[2] = 0;
+        qlane_needed_layouts<JOB_K2, CH_P>(m, true); qlane_needed_layouts<JOB_K2, CH_T>(m, true); qlane_needed_layouts<JOB_K2, CH_A>(m, true);
+        qlane_needed_layouts<JOB_K2_MF, CH_P>(m, true); qlane_needed_layouts<JOB_K2_MF, CH_T>(m, true); qlane_needed_layouts<JOB_K2_MF, CH_A>(m, true);
+        qlane_needed_layouts<JOB_LK2, CH_P>(m, true); qlane_needed_layouts<JOB_LK2, CH_T>(m, true); qlane_needed_layouts<JOB_LK2, CH_A>(m, true);
+        qlane_needed_layouts<JOB_SDE_PP, CH_P>(m, true); qlane_needed_layouts<JOB_SDE_PH, CH_A>(m, true);
+        if (qlane_enabled(ctx) && alloc_mom_all(ctx)) { g_create_error = ctx->err; delete ctx; return 1; }
+    }
     CKC(cudaMalloc(&ctx->twL, g.L * sizeof(C))); CKC(cudaMalloc(&ctx->twLG, g.LG * sizeof(C)));
     twiddle_kernel<<<nblk(g.L, 64), 64, 0, ctx->stream>>>(ctx->twL, g.L);
     twiddle_kernel<<<nblk(g.LG, 64), 64, 0, ctx->stream>>>(ctx->twLG, g.LG);
@@ -535,7 +606,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
         CKC(cudaMalloc(&ctx->OwnTabL[i], (size_t)(2 * g.nK2f) * (2 * g.nK2b - 1) * g.NP * sizeof(C))); CKC(cudaMalloc(&ctx->RtotL[i], (size_t)(2 * g.nK2b - 1) * g.NP * sizeof(C)));
         CKC(cudaMalloc(&ctx->TtabL[i], (size_t)(2 * g.nPiF) * (2 * g.nK2f) * (2 * g.nK2b - 1) * sizeof(C)));
     }
-    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; s.d_rep[0] = s.d_rep[1] = s.d_rep[2] = nullptr; s.ncol = 0; s.ngrp = 0; s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = s.d_grp_start = nullptr; }
+    for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; s.set = false; s.d_offsets = s.d_index = nullptr; s.d_ops = nullptr; s.d_member_class = nullptr; s.d_repvals = nullptr; s.d_rep[0] = s.d_rep[1] = s.d_rep[2] = nullptr; s.ncol = 0; s.ngrp = 0; s.nrep = 0; s.d_reps = nullptr; s.d_col_iW = s.d_col_iP = s.d_col_ik = s.d_col_start = s.d_rep_inu = s.d_rep_cls = s.d_grp_start = nullptr; }
     CKC(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return 0;
@@ -557,7 +628,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     cudaFree(ctx->kryV); cudaFree(ctx->kryP); cudaFree(ctx->kryW); cudaFree(ctx->kryX); cudaFree(ctx->kryH); cudaFree(ctx->kryPart); cudaFree(ctx->kryTicket); if (ctx->kryHhost) cudaFreeHost(ctx->kryHhost);
     cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); for (int i = 0; i < 3; i++) { cudaFree(ctx->TtabL[i]); cudaFree(ctx->OwnTabL[i]); cudaFree(ctx->RtotL[i]); cudaFree(ctx->ConvTabL[i]); if (i) cudaFree(ctx->RtL[i]); } cudaFree(ctx->SigR2); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) cudaFree(ctx->d_slabs[i]);
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); for (int k = 0; k < 3; k++) cudaFree(s.d_rep[k]);
-        cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); cudaFree(s.d_grp_start); }
+        cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); cudaFree(s.d_grp_start); cudaFree(s.d_reps); }
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_copy_ready); cudaEventDestroy(ctx->ev_copy_done);
     for (int i = 1; i < 3; i++) cudaStreamDestroy(ctx->lane[i]);
@@ -577,6 +648,13 @@ int fdga_set_option(fdga_ctx* ctx, int opt, int value) {
     }
     if (opt == FDGA_OPT_DIRECT_K1) { ctx->opt_direct_k1 = value != 0; return 0; }
     if (opt == FDGA_OPT_SERIAL) { ctx->opt_serial = value; return 0; }
+    if (opt == FDGA_OPT_QLANE) {
+        if (value < -1 || value > 1) FAIL("fdga_set_option: FDGA_OPT_QLANE takes -1, 0 or 1");
+        ctx->opt_qlane = value;
+        CK(cudaSetDevice(ctx->device));
+        if (qlane_enabled(ctx) && alloc_mom_all(ctx)) return 1;
+        return 0;
+    }
     FAIL("fdga_set_option: unknown option");
 }
 int fdga_sync(fdga_ctx* ctx) {
@@ -643,7 +721,7 @@ int fdga_set_vertex(fdga_ctx* ctx, int which, int channel, int cls, const fdga_c
     if (lb == &ctx->lev[0] && ctx->copy_pending) CK(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_copy_done, 0));
     CK(cudaMemcpyAsync(lb->K[channel][cls], host, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    lb->sw_dirty = true; lb->k1h_dirty = true; ctx->fsum_dirty = true;
+    lb->sw_dirty = true; lb->k1h_dirty = true; lb->mom_valid[0] = lb->mom_valid[1] = lb->mom_valid[2] = 0; ctx->fsum_dirty = true;
     invalidate_rt(ctx);
     return 0;
 }
@@ -796,7 +874,7 @@ static int unflatten_dev(fdga_ctx* ctx, LevelBuf& lb, const C* src, double scale
     if (&lb == &ctx->lev[0] && wait_copy(ctx)) return 1;
     LAUNCH(FDGA_T_MISC, scale_copy_kernel, nblk(lb.blocklen, 256), 256, lb.block, src, scale, (long long)lb.blocklen);
     CK(cudaGetLastError());
-    lb.sw_dirty = true; lb.k1h_dirty = true; ctx->fsum_dirty = true;
+    lb.sw_dirty = true; lb.k1h_dirty = true; lb.mom_valid[0] = lb.mom_valid[1] = lb.mom_valid[2] = 0; ctx->fsum_dirty = true;
     return 0;
 }
 int fdga_stash_F(fdga_ctx* ctx) { CK(cudaSetDevice(ctx->device)); return flatten_dev(ctx, ctx->lev[0], ctx->stash); }
@@ -1044,6 +1122,12 @@ static int launch_column_t(fdga_ctx* ctx, const DevChain& V, ColJob job, SymGrou
     const bool sub = ctx->profile && (KIND == JOB_K2 || KIND == JOB_K2_MF) && s.ncol > 0;   // sub-timer: the column kernel alone
     TimedEvent ev; ev.cat = FDGA_T_COLUMN_K2;
     if (sub) { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); cudaEventRecord(ev.a, ctx->stream); }
+    if (KIND != JOB_LK2_LOC && qlane_enabled(ctx)) {
+        // the momentum-fastest table copies are made current before the lanes fork; on one stream, right here
+        if (!ctx->forked && refresh_mom_all(ctx)) return 1;
+        RepDev rd; rd.nrep = s.nrep; rd.rep = s.d_reps;
+        if (s.nrep > 0) LAUNCH(cat, (qlane_kernel<KIND, CH>), nblk(s.nrep, FDGA_QL_WARPS), 32 * FDGA_QL_WARPS, V, job, rd, R, own, rtot, conv, s.d_repvals, ctx->g);
+    } else
     if (s.ncol > 0) LAUNCH(cat, (column_kernel<KIND, CH>), (unsigned)s.ngrp, 128, V, job, col_dev(s), R, own, rtot, conv, s.d_repvals, ctx->g);
     if (sub) { cudaEventRecord(ev.b, ctx->stream); ctx->events.push_back(ev); ctx->n_launch[FDGA_T_COLUMN_K2]++; }
     CK(cudaGetLastError());
@@ -1163,7 +1247,7 @@ static bool lanes_enabled(fdga_ctx* ctx) {
 static int lanes_fork(fdga_ctx* ctx) {
     if (!lanes_enabled(ctx) || ctx->forked) return 0;
     for (int ch = 0; ch < 3; ch++) if (ensure_pi(ctx, ch)) return 1;
-    if (refresh_fsum(ctx) || refresh_k1h(ctx) || ensure_slabs(ctx)) return 1;
+    if (refresh_fsum(ctx) || refresh_k1h(ctx) || refresh_mom_all(ctx) || ensure_slabs(ctx)) return 1;
     CK(cudaEventRecord(ctx->ev_fork, ctx->main_stream));
     for (int i = 1; i < 3; i++) CK(cudaStreamWaitEvent(ctx->lane[i], ctx->ev_fork, 0));
     ctx->forked = true;
@@ -1372,7 +1456,7 @@ int fdga_set_F_from_Fbuff(fdga_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     if (wait_copy(ctx)) return 1;
     CK(cudaMemcpyAsync(ctx->lev[0].block, ctx->Fbuff.block, ctx->Fbuff.blocklen * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
-    ctx->lev[0].sw_dirty = true; ctx->lev[0].k1h_dirty = true; ctx->fsum_dirty = true;
+    ctx->lev[0].sw_dirty = true; ctx->lev[0].k1h_dirty = true; ctx->lev[0].mom_valid[0] = ctx->lev[0].mom_valid[1] = ctx->lev[0].mom_valid[2] = 0; ctx->fsum_dirty = true;
     return 0;
 }
 
@@ -1789,7 +1873,7 @@ int fdga_symmetrize_solver(fdga_ctx* ctx) {
         sym(pp ? FDGA_SG_PP3 : FDGA_SG_PH3, ctx->lev[0].K[ch][2]);
     }
     CK(cudaGetLastError());
-    ctx->lev[0].sw_dirty = true; ctx->lev[0].k1h_dirty = true; ctx->fsum_dirty = true;
+    ctx->lev[0].sw_dirty = true; ctx->lev[0].k1h_dirty = true; ctx->lev[0].mom_valid[0] = ctx->lev[0].mom_valid[1] = ctx->lev[0].mom_valid[2] = 0; ctx->fsum_dirty = true;
     return 0;
 }
 
@@ -1899,7 +1983,7 @@ int fdga_interpolate_vertex(fdga_ctx* ctx, int which, int channel, int cls, cons
     }
     for (int i = 0; i < 3; ++i) if (b.ni[i] < 1) FAIL("fdga_interpolate_vertex: bad input mesh sizes");
     if (interp_run(ctx, lb->K[channel][cls], host_Ki, b, D, Li, ctx->g.L, 0)) return 1;
-    lb->sw_dirty = true; lb->k1h_dirty = true; ctx->fsum_dirty = true;
+    lb->sw_dirty = true; lb->k1h_dirty = true; lb->mom_valid[0] = lb->mom_valid[1] = lb->mom_valid[2] = 0; ctx->fsum_dirty = true;
     invalidate_rt(ctx);
     return 0;
 }
@@ -1950,7 +2034,7 @@ int fdga_update_reference(fdga_ctx* ctx) {
     LAUNCH(FDGA_T_MISC, add_axpby_kernel, nblk(n, 256), 256, ctx->lev[1].block, (const C*)ctx->lev[0].block, 1.0, (const C*)nullptr, 0.0, n);
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->lev[0].block, 0, (size_t)n * sizeof(C), ctx->stream));
-    for (int l = 0; l < 2; l++) { ctx->lev[l].sw_dirty = true; ctx->lev[l].k1h_dirty = true; }
+    for (int l = 0; l < 2; l++) { ctx->lev[l].sw_dirty = true; ctx->lev[l].k1h_dirty = true; ctx->lev[l].mom_valid[0] = ctx->lev[l].mom_valid[1] = ctx->lev[l].mom_valid[2] = 0; }
     ctx->fsum_dirty = true;
     invalidate_rt(ctx);
     return 0;

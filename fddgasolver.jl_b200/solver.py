@@ -125,7 +125,7 @@ class NL2_ParquetSolver:
 
     def set_option(self, name, value):
         """options of include/fdga.h; 'sde_own_gamma' toggles the SURVEY-E2 reading of the NL2 SDE L kernels"""
-        self._call("fdga_set_option", {"sde_own_gamma": 0, "generic_kernels": 1, "fd_hartree_once": 2, "local_solver": 3, "direct_k1": 4, "serial": 5}[name], int(value))
+        self._call("fdga_set_option", {"sde_own_gamma": 0, "generic_kernels": 1, "fd_hartree_once": 2, "local_solver": 3, "direct_k1": 4, "serial": 5, "qlane": 6}[name], int(value))
 
     def sync(self):
         self._call("fdga_sync")

@@ -95,7 +95,11 @@ enum { FDGA_OPT_SDE_OWN_GAMMA = 0,
        FDGA_OPT_SERIAL = 5           /* concurrency of the three channels of a BSE stage and of the pp / ph / U^2 parts of the SDE:
                                         0 (default) = concurrent streams when one bubble-shaped array is <= 160 MB (the right
                                         factors of the channels then share the L2), one stream otherwise; 1 = always one stream;
-                                        2 = always concurrent */ };
+                                        2 = always concurrent */,
+       FDGA_OPT_QLANE = 6            /* contraction kernel of BSE_K2! / BSE_L_K2! / the SDE L arrays: -1 (default) = the q-lane
+                                        kernel (one warp per class representative, lanes over the inner momentum, vertex tables
+                                        in momentum-fastest layouts) when nq * nq >= 16, the column kernel otherwise;
+                                        0 = always the column kernel; 1 = always the q-lane kernel (A/B check) */ };
 int  fdga_set_option(fdga_ctx* ctx, int opt, int value);
 /* one process per GPU; `unique_id` = the 128-byte ncclUniqueId obtained on rank 0 by
  * fdga_comm_unique_id and broadcast by the host (MPI in Julia, torch.distributed in tests). */

@@ -2,7 +2,7 @@
 // (eval_vertex) for every job kind / channel on a random nested chain NL2 -> NL2 -> LOCAL -> CORE with ragged boxes.
 // Built and run by tests/test_host_eval.py (nvcc, no GPU needed).
 #include <cstdio>
-#include "../fddgasolver.jl_b200/csrc/fdga_column.cuh"
+#include "../fddgasolver.jl_b200/csrc/fdga_qlane.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -23,6 +23,12 @@ __global__ void dev_run(DevChain V, ColJob job, ColDev cols, const C* R, const C
     column_thread<KIND, CH>(V, job, cols, R, g, 0, threadIdx.x, blockDim.x, acc);
     for (int i = 0; i < FDGA_WGROUP; ++i) out[threadIdx.x + blockDim.x * i] = acc[i];
 }
+// the q-lane contraction on the device: one warp per representative, lane partial sums written out
+template <int KIND, int CH>
+__global__ void dev_run_q(DevChain V, ColJob job, const int* rep4, int nrep, const C* R, Grid g, C* out) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (w < nrep) out[threadIdx.x] = qlane_lane<KIND, CH>(V, job, g, R, rep4[4 * w], rep4[4 * w + 1], rep4[4 * w + 2], rep4[4 * w + 3], lane);
+}
 #else
 static const C* rnd_array(size_t n, double scale = 1.0) {
     g_store.emplace_back(n);
@@ -30,6 +36,35 @@ static const C* rnd_array(size_t n, double scale = 1.0) {
     return g_store.back().data();
 }
 #endif
+
+static C* raw_array(size_t n) {
+#ifdef DEVICE_CHECK
+    C* p; cudaMallocManaged(&p, n * sizeof(C)); return p;
+#else
+    g_store.emplace_back(n); return g_store.back().data();
+#endif
+}
+// momentum-fastest layouts of an NL2 level (what mom_layout_kernel builds on the device), via the same index map
+static void build_mom_layouts(DevLevel& lv, int L, int NP) {
+    const int nB1 = 2 * lv.nK1 - 1; const size_t n2 = (size_t)(2 * lv.nK2b - 1) * (2 * lv.nK2f), n3 = (size_t)(2 * lv.nK3b - 1) * (2 * lv.nK3f) * (2 * lv.nK3f);
+    for (int r = 0; r < 3; ++r) {
+        DevChan& c = lv.ch[r];
+        for (int lay = 0; lay < 4; ++lay) {
+            C* d = raw_array(n2 * NP * NP);
+            for (int blk = 0; blk < NP; ++blk) for (size_t row = 0; row < n2; ++row) for (int m = 0; m < NP; ++m) {
+                int iP, ik; mom_layout_source(lay, m, blk, L, iP, ik);
+                d[m + (size_t)NP * (row + n2 * blk)] = c.K2[row + n2 * (iP + (size_t)NP * ik)];
+            }
+            c.K2m[lay] = d;
+        }
+        C* d3 = raw_array(n3 * NP);
+        for (size_t row = 0; row < n3; ++row) for (int iP = 0; iP < NP; ++iP) d3[iP + (size_t)NP * row] = c.K3[row + n3 * iP];
+        c.K3m = d3;
+        C* d1 = raw_array((size_t)nB1 * NP);
+        for (int pW = 0; pW < nB1; ++pW) for (int iP = 0; iP < NP; ++iP) d1[iP + (size_t)NP * pW] = c.K1[pW + (size_t)nB1 * iP];
+        c.K1m = d1;
+    }
+}
 
 // host restatement of slab_conv_kernel (same formulas, plain loops): X[k + NP * inu] for one slab
 template <int KIND, int CH>
@@ -41,7 +76,7 @@ static std::vector<C> conv_host(const DevChain& V, const ColJob& job, const Grid
     std::vector<C> Rh((size_t)nw * NP), X((size_t)nF2 * NP, zeroC()), Z((size_t)nF2 * NP, zeroC());
     for (int iw = 0; iw < nw; ++iw) for (int kap = 0; kap < NP; ++kap) {
         C s = zeroC();
-        for (int q = 0; q < NP; ++q) s += Rs[iw + (size_t)nw * q] * ph(-((kap % L) * (q % L) + (kap / L) * (q / L)));
+        for (int q = 0; q < NP; ++q) s += Rs[slab_at(iw, q, NP)] * ph(-((kap % L) * (q % L) + (kap / L) * (q / L)));
         Rh[iw + (size_t)nw * kap] = s;
     }
     const int Px = iP % L, Py = iP / L;
@@ -124,6 +159,38 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
             column_thread<KIND, CH>(V, job, cols, R, g, 0, tid, nthreads, a);
             int n = tid & (NVc - 1);
             for (int i = 0; i < ng; ++i) if (n < start[i + 1] - start[i]) got[start[i] + n] += a[i];
+        }
+        if (KIND != JOB_LK2_LOC) for (int pass = 0; pass < 2; ++pass) {   // q-lane contraction (one warp per representative) against column_thread
+            ColJob jq = job; jq.k1_direct = pass;
+            std::vector<C> ref(ntot, zeroC());
+            if (pass == 0) ref = got;
+            else for (int tid = 0; tid < nthreads; ++tid) {
+                C a[FDGA_WGROUP];
+                column_thread<KIND, CH>(V, jq, cols, R, g, 0, tid, nthreads, a);
+                int n = tid & (NVc - 1);
+                for (int i = 0; i < ng; ++i) if (n < start[i + 1] - start[i]) ref[start[i] + n] += a[i];
+            }
+            for (int i = 0; i < ng; ++i) for (int n = start[i]; n < start[i + 1]; ++n) {
+                C sq = zeroC();
+                for (int lane = 0; lane < 32; ++lane) sq += qlane_lane<KIND, CH>(V, jq, g, R, iWv[i], inu[n], iP, ik, lane);
+                const double d = std::max(std::fabs(sq.x - ref[n].x), std::fabs(sq.y - ref[n].y));
+                if (d > 1e-11) printf("    QLANE != COLUMN pass %d trial %d rep %d: qlane (%g,%g) column (%g,%g)\n", pass, trial, n, sq.x, sq.y, ref[n].x, ref[n].y);
+                maxerr = std::max(maxerr, d);
+#ifdef DEVICE_CHECK
+                if (pass == 0) {
+                    int* r4; cudaMallocManaged(&r4, 4 * sizeof(int)); r4[0] = iWv[i]; r4[1] = inu[n]; r4[2] = iP; r4[3] = ik;
+                    C* qo; cudaMallocManaged(&qo, 32 * sizeof(C));
+                    dev_run_q<KIND, CH><<<1, 32>>>(V, jq, r4, 1, R, g, qo);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    if (e != cudaSuccess) { printf("CUDA error (qlane) %s\n", cudaGetErrorString(e)); exit(2); }
+                    C dq = zeroC(); for (int lane = 0; lane < 32; ++lane) dq += qo[lane];
+                    const double dd = std::max(std::fabs(dq.x - sq.x), std::fabs(dq.y - sq.y));
+                    if (dd > 1e-10) printf("    DEVICE QLANE != HOST trial %d rep %d: dev (%g,%g) host (%g,%g)\n", trial, n, dq.x, dq.y, sq.x, sq.y);
+                    maxdev = std::max(maxdev, dd);
+                    cudaFree(r4); cudaFree(qo);
+                }
+#endif
+            }
         }
 #ifdef DEVICE_CHECK
         {   // the same column_thread on the device
@@ -236,13 +303,16 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
                         d += dl;
                     }
                 }
-                ref += d * slab[iw + (size_t)nw * iq];
+                ref += d * slab[slab_at(iw, iq, NP)];
             }
             maxerr = std::max(maxerr, std::max(std::fabs(ref.x - got[off + n].x), std::fabs(ref.y - got[off + n].y)));
             maxval = std::max(maxval, std::max(std::fabs(ref.x), std::fabs(ref.y)));
         }
         }
     }
+#ifdef DEVICE_CHECK
+    maxerr = std::max(maxerr, maxdev);
+#endif
     return maxerr / std::max(maxval, 1e-300);
 }
 
@@ -255,6 +325,7 @@ static DevLevel make_level(int type, int nK1, int nK2b, int nK2f, int nK3b, int 
         lv.ch[r].K2 = rnd_array((size_t)(2 * nK2b - 1) * (2 * nK2f) * np * np);
         lv.ch[r].K3 = rnd_array((size_t)(2 * nK3b - 1) * (2 * nK3f) * (2 * nK3f) * np);
     }
+    if (type == LV_NL2) { int L = 1; while (L * L < NP) ++L; build_mom_layouts(lv, L, NP); }
     return lv;
 }
 

@@ -51,11 +51,11 @@ static double check(const DevLevel& lv, int L, int Nin, int nw, int nK2b_out, in
                     int W0, v0, w0, W1, v1, w1;
                     convert_freq(W, v_a, w_a, form, r, W0, v0, w0); convert_freq(W, v_b, w_b, form, r, W1, v1, w1);
                     Lin lW = {W0, W1 - W0}, lv2 = {v0, v1 - v0}, lw2 = {w0, w1 - w0};
-                    l_cross += chan_lin_sum(lv, r, mo[r], lW, lv2, lw2, R.data(), Nin, w_lo, w_hi, rs, true);
+                    l_cross += chan_lin_sum(lv, r, mo[r], lW, lv2, lw2, R.data(), Nin, 1, w_lo, w_hi, rs, true);
                 }
                 Lin lW = {W, 0}, lv2 = {v_a, v_b - v_a}, lw2 = {w_a, w_b - w_a};
-                C l_diff = chan_lin_sum_diff_v(lv, form, mo[form], lW, lv2, lw2, R.data(), Nin, w_lo, w_hi, rs);
-                C l_full = chan_lin_sum(lv, form, mo[form], lW, lv2, lw2, R.data(), Nin, w_lo, w_hi, rs, true);
+                C l_diff = chan_lin_sum_diff_v(lv, form, mo[form], lW, lv2, lw2, R.data(), Nin, 1, w_lo, w_hi, rs);
+                C l_full = chan_lin_sum(lv, form, mo[form], lW, lv2, lw2, R.data(), Nin, 1, w_lo, w_hi, rs, true);
                 auto err = [](C a, C b) { return std::max(std::fabs(a.x - b.x), std::fabs(a.y - b.y)); };
                 maxerr = std::max(maxerr, std::max(err(b_cross, l_cross), std::max(err(b_diff, l_diff), err(b_full, l_full))));
             }

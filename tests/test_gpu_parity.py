@@ -357,6 +357,62 @@ def test_convolution_and_lanes_match_plain_path(orc, opt):
             assert rel(a, b) < TOL
 
 
+@pytest.mark.parametrize("nq,LG,qlane", [(3, 6, 1), (5, 10, 1), (4, 8, 1), (4, 8, 0)])
+def test_qlane_and_column_kernels_vs_oracle(orc, nq, LG, qlane):
+    """Both contraction kernels of BSE_K2! / BSE_L_K2! / the SDE L arrays against the oracle: the q-lane kernel (one warp per
+    class representative, lanes over the inner momentum; forced on for momentum meshes that do not fill a warp, NP = 9, 25, and
+    on its default mesh NP = 16) and the column kernel (forced on at NP = 16): one fused fdPA iteration with the self-energy
+    update, then two mfRG matvecs (FDGA_OPT_QLANE)."""
+    import fddgasolver_jl_b200 as fd
+    S, R = make_pair(orc, nmax=2, nq=nq, LG=LG)
+    S.set_option("qlane", qlane)
+    fd.iterate_solver(S, "fdPA", True); orc.iterate_solver(R, "fdPA", True)
+    S.pull("F", "Σ", "FL")
+    compare_vertex(S.FL, R.FL, "FL", ("K2", "K3"))
+    compare_vertex(S.F, R.F, "F")
+    assert rel(S.Σ, R.Σ) < TOL
+    x = S.F.flatten() * 3.0
+    A, B = fd.mfRGLinearMap(S), orc.mfRGLinearMap(R)
+    for _ in range(2):
+        yg, yo = A.matvec(x), B.matvec(x)
+        assert rel(yg, yo) < TOL
+        x = yo * 0.5
+    S.close()
+
+
+def test_qlane_matches_column_kernel_bitwise_inputs(orc):
+    """A/B on the device at a mesh where both kernels are natural (nq = 6, NP = 36): q-lane vs column kernel, direct K1 in both"""
+    import fddgasolver_jl_b200 as fd
+    res = []
+    for qlane, dk1 in ((0, 0), (1, 0), (1, 1)):
+        S, _ = make_pair(orc, nmax=3, nq=6, LG=12, sym=True)
+        S.set_option("qlane", qlane); S.set_option("direct_k1", dk1)
+        fd.iterate_solver(S, "fdPA", True)
+        y = fd.mfRGLinearMap(S).matvec(S.F.flatten())
+        S.pull("F", "Σ", "FL")
+        res.append((S.F.flatten(), S.FL.flatten(), S.Σ.copy(), y))
+        S.close()
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert rel(a, b) < TOL
+
+
+def test_device_kernels_match_host_restatement(tmp_path):
+    """tests/host_column_test.cu compiled with -DDEVICE_CHECK: column_thread, qlane_lane and slab_conv_kernel executed on the
+    device against the same functions executed on the host (guards against miscompiled index loops)"""
+    import os, shutil, subprocess
+    nvcc = shutil.which("nvcc")
+    if nvcc is None:
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "dev_column_test")
+    subprocess.check_call([nvcc, "-std=c++17", "-O3", "-DDEVICE_CHECK", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                           os.path.join(root, "tests", "host_column_test.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "WORST" in out.stdout and "!=" not in out.stdout, out.stdout[-3000:]
+
+
 def test_flatten_async_matches_flatten(orc):
     """fdga_flatten_F_async: the copy overlaps later work (SDE!) and lands the same bytes as the synchronous flatten"""
     import fddgasolver_jl_b200 as fd
