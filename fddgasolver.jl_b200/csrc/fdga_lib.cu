@@ -291,7 +291,7 @@ static int refresh_k1h(fdga_ctx* ctx) {
 }
 // ---- q-lane kernel: momentum-fastest copies of the vertex tables -------------------------------------------------------
 static bool qlane_enabled(fdga_ctx* ctx) {
-    if (ctx->opt_local || ctx->opt_generic || ctx->opt_qlane == 0) return false;
+    if (ctx->opt_local || ctx->opt_generic || ctx->opt_qlane == 0 || ctx->g.L > 64) return false;      // rep descriptors pack momenta in 8 / 16 bits
     if (ctx->opt_qlane == 1) return true;
     return ctx->g.NP >= 16;
 }
@@ -301,7 +301,9 @@ static int alloc_mom(fdga_ctx* ctx, LevelBuf& lb) {
     for (int ch = 0; ch < 3; ch++) for (int j = 0; j < ML_COUNT; j++) {
         if (!(ctx->mom_mask[ch] & (1u << j)) || lb.mom[ch][j]) continue;
         const size_t n = j == ML_K1 ? lb.len[0] : (j == ML_K3 ? lb.len[2] : lb.len[1]);
-        CK(cudaMalloc(&lb.mom[ch][j], n * sizeof(C)));
+        if (n + ctx->g.NP >= (size_t)1 << 31) FAIL("q-lane kernel: vertex table too large for 32-bit element offsets");
+        CK(cudaMalloc(&lb.mom[ch][j], (n + ctx->g.NP) * sizeof(C)));      // + NP zeros: the row read by terms outside their Matsubara box
+        CK(cudaMemsetAsync(lb.mom[ch][j] + n, 0, (size_t)ctx->g.NP * sizeof(C), ctx->stream));
     }
     return 0;
 }
@@ -423,11 +425,12 @@ static int build_columns(fdga_ctx* ctx, SymGroup& s) {
         std::vector<int4> list; list.reserve(reps.size());
         for (auto& r : reps) {
             long long key = r.key; const int iW = (int)(key % nB2); key /= nB2; const int iP = (int)(key % NP), ik = (int)(key / NP);
-            list.push_back(make_int4(iW | (r.inu << 16), iP, ik, r.cls));
+            const int L = ctx->g.L;
+            list.push_back(make_int4(iW | (r.inu << 16), iP | (ik << 16), (iP % L) | ((iP / L) << 8) | ((ik % L) << 16) | ((ik / L) << 24), r.cls));
         }
         std::stable_sort(list.begin(), list.end(), [&](const int4& a, const int4& b) {
-            const long long ka = (((long long)a.y * nB2 + (a.x & 0xffff)) * NP + a.z) * nF2 + (a.x >> 16), kb = (((long long)b.y * nB2 + (b.x & 0xffff)) * NP + b.z) * nF2 + (b.x >> 16);
-            return ka < kb; });
+            auto key = [&](const int4& t) { return ((((long long)(t.y & 0xffff)) * nB2 + (t.x & 0xffff)) * NP + ((t.y >> 16) & 0xffff)) * nF2 + (t.x >> 16); };
+            return key(a) < key(b); });
         s.nrep = (int)list.size();
         if (s.nrep) { CK(cudaMalloc(&s.d_reps, list.size() * sizeof(int4))); CK(cudaMemcpy(s.d_reps, list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice)); }
     }

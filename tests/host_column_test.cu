@@ -50,14 +50,14 @@ static void build_mom_layouts(DevLevel& lv, int L, int NP) {
     for (int r = 0; r < 3; ++r) {
         DevChan& c = lv.ch[r];
         for (int lay = 0; lay < 4; ++lay) {
-            C* d = raw_array(n2 * NP * NP);
+            C* d = raw_array(n2 * NP * NP + NP); for (int z = 0; z < NP; ++z) d[n2 * NP * NP + z] = zeroC();     // zero padding read by out-of-box terms
             for (int blk = 0; blk < NP; ++blk) for (size_t row = 0; row < n2; ++row) for (int m = 0; m < NP; ++m) {
                 int iP, ik; mom_layout_source(lay, m, blk, L, iP, ik);
                 d[m + (size_t)NP * (row + n2 * blk)] = c.K2[row + n2 * (iP + (size_t)NP * ik)];
             }
             c.K2m[lay] = d;
         }
-        C* d3 = raw_array(n3 * NP);
+        C* d3 = raw_array(n3 * NP + NP); for (int z = 0; z < NP; ++z) d3[n3 * NP + z] = zeroC();
         for (size_t row = 0; row < n3; ++row) for (int iP = 0; iP < NP; ++iP) d3[iP + (size_t)NP * row] = c.K3[row + n3 * iP];
         c.K3m = d3;
         C* d1 = raw_array((size_t)nB1 * NP);
