@@ -328,10 +328,12 @@ static int ensure_mom(fdga_ctx* ctx, LevelBuf& lb) {
     for (int ch = 0; ch < 3; ch++) lb.mom_valid[ch] = ctx->mom_mask[ch];
     return 0;
 }
-static int refresh_mom_all(fdga_ctx* ctx) {
+// `need`: bit l = level l of the S.F chain, MOM_FSUM = the merged level; only tables a coming job reads are re-laid out
+enum : unsigned { MOM_FSUM = 1u << 30, MOM_ALL = ~0u };
+static int refresh_mom_all(fdga_ctx* ctx, unsigned need = MOM_ALL) {
     if (!qlane_enabled(ctx)) return 0;
-    for (int l = 0; l < ctx->n_nl2; l++) if (ensure_mom(ctx, ctx->lev[l])) return 1;
-    if (ctx->has_fsum && !ctx->fsum_dirty && ensure_mom(ctx, ctx->Fsum)) return 1;
+    for (int l = 0; l < ctx->n_nl2; l++) if ((need & (1u << l)) && ensure_mom(ctx, ctx->lev[l])) return 1;
+    if ((need & MOM_FSUM) && ctx->has_fsum && !ctx->fsum_dirty && ensure_mom(ctx, ctx->Fsum)) return 1;
     return 0;
 }
 static int refresh_pi(fdga_ctx* ctx, int which) {
@@ -421,7 +423,7 @@ static int build_columns(fdga_ctx* ctx, SymGroup& s) {
         Rep r; r.key = ((long long)ik * NP + iP) * nB2 + iW; r.inu = inu; r.cls = (int)c;
         reps.push_back(r);
     }
-    {   // q-lane kernel: one warp per representative, slab-major (P, W, k, nu) so that the warps of a CTA share their R rows
+    {   // q-lane kernel: one warp per representative, slab-major
         std::vector<int4> list; list.reserve(reps.size());
         for (auto& r : reps) {
             long long key = r.key; const int iW = (int)(key % nB2); key /= nB2; const int iP = (int)(key % NP), ik = (int)(key / NP);
@@ -429,7 +431,11 @@ static int build_columns(fdga_ctx* ctx, SymGroup& s) {
             list.push_back(make_int4(iW | (r.inu << 16), iP | (ik << 16), (iP % L) | ((iP / L) << 8) | ((ik % L) << 16) | ((ik / L) << 24), r.cls));
         }
         std::stable_sort(list.begin(), list.end(), [&](const int4& a, const int4& b) {
-            auto key = [&](const int4& t) { return ((((long long)(t.y & 0xffff)) * nB2 + (t.x & 0xffff)) * NP + ((t.y >> 16) & 0xffff)) * nF2 + (t.x >> 16); };
+            // (P, W, nu, k): the warps of a CTA share their R rows and their K3 rows (both independent of the column momentum k)
+            static const int order = getenv("FDGA_QL_ORDER") ? atoi(getenv("FDGA_QL_ORDER")) : 1;
+            auto key = [&](const int4& t) {
+                const long long iP = t.y & 0xffff, iW = t.x & 0xffff, ik = (t.y >> 16) & 0xffff, inu = t.x >> 16;
+                return order == 0 ? ((iP * nB2 + iW) * NP + ik) * nF2 + inu : ((iP * nB2 + iW) * nF2 + inu) * NP + ik; };
             return key(a) < key(b); });
         s.nrep = (int)list.size();
         if (s.nrep) { CK(cudaMalloc(&s.d_reps, list.size() * sizeof(int4))); CK(cudaMemcpy(s.d_reps, list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice)); }
@@ -1247,10 +1253,10 @@ static bool lanes_enabled(fdga_ctx* ctx) {
     return (double)ctx->lenPi * sizeof(C) <= lim_mb * 1e6;
 }
 // everything the lanes read but do not own must be current before the fork
-static int lanes_fork(fdga_ctx* ctx) {
+static int lanes_fork(fdga_ctx* ctx, unsigned mom_need = MOM_ALL) {
     if (!lanes_enabled(ctx) || ctx->forked) return 0;
     for (int ch = 0; ch < 3; ch++) if (ensure_pi(ctx, ch)) return 1;
-    if (refresh_fsum(ctx) || refresh_k1h(ctx) || refresh_mom_all(ctx) || ensure_slabs(ctx)) return 1;
+    if (refresh_fsum(ctx) || refresh_k1h(ctx) || refresh_mom_all(ctx, mom_need) || ensure_slabs(ctx)) return 1;
     CK(cudaEventRecord(ctx->ev_fork, ctx->main_stream));
     for (int i = 1; i < 3; i++) CK(cudaStreamWaitEvent(ctx->lane[i], ctx->ev_fork, 0));
     ctx->forked = true;
@@ -1481,7 +1487,7 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
     if (!ctx->opt_generic) {
         // fused recursion: one column launch per bubble kind covers every level of the chain (fdga_column.cuh);
         // lanes: pp on 0, ph on 1, (G transforms + U^2 term) on 2
-        if (lanes_fork(ctx)) return 1;
+        if (lanes_fork(ctx, ctx->opt_sde_own_gamma ? 0u : (MOM_ALL & ~MOM_FSUM) & ~((2u << from) - 1u))) return 1;      // cross channels of the levels > from
         for (int pp = 1; pp >= 0; pp--) {
             lane_use(ctx, pp ? 0 : 1);
             SymGroup& s = ctx->sg[pp ? FDGA_SG_PP2 : FDGA_SG_PH2];
@@ -1598,13 +1604,14 @@ static int bse_stages(fdga_ctx* ctx, bool with_L, int mfrg) {
     ctx->defer = true;
     int rc = 0;
     if (with_L) {
-        rc = lanes_fork(ctx);
+        rc = lanes_fork(ctx, 1u);      // BSE_L_K2!: cross channels of S.F itself
         for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_L_K2(ctx, order[i]); }
         for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_L_K3(ctx, order[i]); }   // reads caches and bubbles only
         if (lanes_join(ctx)) rc = 1;
         if (!rc) rc = flush_pending(ctx);
     }
-    if (!rc) rc = lanes_fork(ctx);
+    // BSE_K2!: left vertex S.F + S.F0 (merged level when available), mfRG: S.F0 only
+    if (!rc) rc = lanes_fork(ctx, mfrg ? (MOM_ALL & ~MOM_FSUM & ~1u) : (ctx->has_fsum ? (MOM_ALL & ~3u) : (MOM_ALL & ~MOM_FSUM)));
     for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_K1(ctx, order[i], mfrg); }
     for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_K2(ctx, order[i], mfrg); }    // K1 and K2 share inputs (FL, right factor)
     // BSE_K3! only reads the caches, the s-wave bubbles and FL.K3 (all final after the L stage): same stage, one SG finish fewer

@@ -161,13 +161,13 @@ FDGA_HD void qlane_piece(const DevLevel& lv, const ColJob& job, const Grid& g, i
     pc.wa = -Nin; pc.wb = nw - 1 - Nin; clip_interval(pc.lW, -(lv.nK2b - 1), lv.nK2b - 1, pc.wa, pc.wb);
 }
 // entry of inner frequency win: element offsets (rowA, rowB, row3, R row)
-FDGA_HD int4 qlane_entry(const QPiece& pc, const DevLevel& lv, int NP, int Nin, int win) {
+FDGA_HD uint4 qlane_entry(const QPiece& pc, const DevLevel& lv, int NP, int Nin, int win) {
     const int nB = 2 * lv.nK2b - 1, nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
     const int Wc = pc.lW.x0 + pc.lW.s * win, vc = pc.lv2.x0 + pc.lv2.s * win, wc = pc.lw2.x0 + pc.lw2.s * win;
     const bool inA = inF(vc, lv.nK2f), inBt = inF(wc, lv.nK2f);
     const bool in3 = inA && inBt && inB(Wc, lv.nK3b) && inF(vc, lv.nK3f) && inF(wc, lv.nK3f);
     const int pW = posB(Wc, lv.nK2b);
-    int4 e;
+    uint4 e;
     e.x = inA ? NP * (pW + nB * posF(vc, lv.nK2f)) : pc.zA;
     e.y = inBt ? NP * (pW + nB * posF(wc, lv.nK2f)) : pc.zB;
     e.z = in3 ? NP * (posB(Wc, lv.nK3b) + nB3 * (posF(vc, lv.nK3f) + nF3 * posF(wc, lv.nK3f))) : pc.z3;
@@ -175,7 +175,7 @@ FDGA_HD int4 qlane_entry(const QPiece& pc, const DevLevel& lv, int NP, int Nin, 
     return e;
 }
 // one lane's share of a piece: momentum slots q0 = (q0x, q0y) and q1 (q1 == q0 with has1 == false: second slot idle)
-FDGA_HD C qlane_consume(const QPiece& pc, const int4* __restrict__ ent, int n, const C* __restrict__ r0, const C* __restrict__ r1,
+FDGA_HD C qlane_consume(const QPiece& pc, const uint4* __restrict__ ent, int n, const C* __restrict__ r0, const C* __restrict__ r1,
                         int q0x, int q0y, int q1x, int q1y, bool has1, int L) {
     const C* __restrict__ a0 = pc.tA + mom_lane(pc.mA, q0x, q0y, L); const C* __restrict__ a1 = pc.tA + mom_lane(pc.mA, q1x, q1y, L);
     const C* __restrict__ b0 = pc.tB + mom_lane(pc.mB, q0x, q0y, L); const C* __restrict__ b1 = pc.tB + mom_lane(pc.mB, q1x, q1y, L);
@@ -183,7 +183,7 @@ FDGA_HD C qlane_consume(const QPiece& pc, const int4* __restrict__ ent, int n, c
     C p0 = zeroC(), p1 = zeroC();
 #pragma unroll QL_UNROLL
     for (int i = 0; i < n; ++i) {
-        const int4 e = ent[i];
+        const uint4 e = ent[i];
         const C va0 = ldg(a0 + e.x), va1 = ldg(a1 + e.x), vb0 = ldg(b0 + e.y), vb1 = ldg(b1 + e.y), vc0 = ldg(c0 + e.z), vc1 = ldg(c1 + e.z);
         const C x0 = r0[e.w], x1 = r1[e.w];
         p0 += ((va0 + vb0) + vc0) * x0; p1 += ((va1 + vb1) + vc1) * x1;
@@ -211,7 +211,7 @@ FDGA_HD C qlane_k1_direct(const QPiece& pc, const DevLevel& lv, const C* __restr
 // with __syncwarp; SYNC = false: the host restatement of ONE lane with a private entry array (tests/host_column_test.cu sums it
 // over the 32 lanes).  Same building blocks either way.
 template <int KIND, int CH, bool SYNC>
-FDGA_HD C qlane_rep(const DevChain& V, const ColJob& job, const Grid& g, const C* __restrict__ R, int4* ent,
+FDGA_HD C qlane_rep(const DevChain& V, const ColJob& job, const Grid& g, const C* __restrict__ R, uint4* ent,
                     int iW, int inu, int iP, int Px, int Py, int kx, int ky, int lane) {
     typedef Forms<KIND, CH> FM;
     const int L = g.L, NP = g.NP, nw = job.nw, Nin = job.Ninner;
@@ -264,7 +264,7 @@ FDGA_HD C qlane_rep(const DevChain& V, const ColJob& job, const Grid& g, const C
 template <int KIND, int CH>
 FDGA_HD C qlane_lane(const DevChain& V, const ColJob& job, const Grid& g, const C* __restrict__ R,
                      int iW, int inu, int iP, int ik, int lane) {
-    int4 ent[FDGA_QL_ENT];
+    uint4 ent[FDGA_QL_ENT];
     return qlane_rep<KIND, CH, false>(V, job, g, R, ent, iW, inu, iP, iP % g.L, iP / g.L, ik % g.L, ik / g.L, lane);
 }
 
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(32 * FDGA_QL_WARPS, FDGA_QL_MINB)
 qlane_kernel(const __grid_constant__ DevChain V, ColJob job, RepDev reps, const C* __restrict__ R,
              const C* __restrict__ OwnTab, const C* __restrict__ Rtot, const C* __restrict__ ConvTab,
              C* __restrict__ repvals, Grid g) {
-    __shared__ int4 s_ent[FDGA_QL_WARPS][FDGA_QL_ENT];
+    __shared__ uint4 s_ent[FDGA_QL_WARPS][FDGA_QL_ENT];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * FDGA_QL_WARPS + wid;
     if (w >= reps.nrep) return;                     // whole warps leave together; only __syncwarp below
