@@ -10,7 +10,7 @@ from .types import (pCh, tCh, aCh, pSp, xSp, dSp, Channel, NL2_Channel, RefVerte
 from .models import hubbard_bare_Green, hubbard_band, siam_bare_Green  # noqa: F401
 from .solver import (NL2_ParquetSolver, ParquetSolver, init_sym_grp, Dyson, compute_occupation, bubbles, bubbles_real_space,  # noqa: F401
                      bubbles_momentum_space, build_K3_cache, build_K3_cache_mfRG, BSE_L_K2, BSE_L_K3, BSE_K1,
-                     BSE_K2, BSE_K3, BSE_K1_new, BSE_K2_new, BSE_K1_1loop, BSE_K2_1loop, BSE_K3_1loop, SDE, iterate_solver, iterate_solver_stepwise, fixed_point, solve, mfRGLinearMap,
+                     BSE_K2, BSE_K3, BSE_K1_new, BSE_K2_new, BSE_K1_1loop, BSE_K2_1loop, BSE_K3_1loop, SDE, SDE_channel_L, iterate_solver, iterate_solver_stepwise, fixed_point, solve, mfRGLinearMap,
                      dqgmres, symmetrize_solver, fixed_point_preconditioned,
                      set_hubbard_bare_Green, compute_hubbard_chemical_potential, mix_bubbles, update_reference, solve_using_mfRG,
                      interpolate_vertex, interpolate_solver)

@@ -1474,7 +1474,7 @@ int fdga_set_F_from_Fbuff(fdga_ctx* ctx) {
 // The real-space contraction, the back transform and SG_Sigma are linear in (Lpp, Lph), so the L arrays of all levels
 // of the F0 chain are accumulated first (weight 1/3 for the RefVertex level, SDE.jl:305-309) and transformed ONCE:
 // identical to the reference's per-level sum up to rounding.  acc += sgn * result.
-static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool reference, int from, bool include_U2, bool include_Hartree) {
+static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool reference, int from, bool include_U2, bool include_Hartree, bool L_only = false) {
     NEED_SG(FDGA_SG_SIGMA); NEED_SG(FDGA_SG_PP2); NEED_SG(FDGA_SG_PH2);
     const Grid& g = ctx->g;
     if (refresh_pi(ctx, reference ? FDGA_PI0PP : FDGA_PIPP) || refresh_pi(ctx, reference ? FDGA_PI0PH : FDGA_PIPH)) return 1;
@@ -1523,6 +1523,7 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
             CK(cudaGetLastError());
         }
     }
+    if (L_only) return lanes_join(ctx);
     C* Sout = ctx->SigAcc;
     const long long pre = (long long)(2 * g.nK2b - 1) * (2 * g.nK2f);
     const double nrm = 1.0 / ((double)g.L * g.L * g.L * g.L);
@@ -1576,12 +1577,17 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
     CK(cudaGetLastError());
     return 0;
 }
+int fdga_sde_channel_L(fdga_ctx* ctx, int reference, int from) {
+    CK(cudaSetDevice(ctx->device));
+    if (from < 0 || from >= ctx->nlev) FAIL("fdga_sde_channel_L: bad level");
+    return sde_chain(ctx, nullptr, 0.0, reference ? FDGA_G0 : FDGA_G, reference != 0, from, false, false, true);
+}
 int fdga_sde(fdga_ctx* ctx, int strategy, int include_U2, int include_Hartree) {
     CK(cudaSetDevice(ctx->device));
+    if (strategy < FDGA_SCPA || strategy > FDGA_FDPA_1LOOP) FAIL("fdga_sde: Calculation strategy unknown");      // before S.Sigma is touched (src/SDE.jl:31)
     C* S = ctx->G[FDGA_SIGMA];
     CK(cudaMemsetAsync(S, 0, ctx->lenG * sizeof(C), ctx->stream));
     if (sde_chain(ctx, S, 1.0, FDGA_G, false, 0, include_U2, include_Hartree)) return 1;
-    if (strategy < FDGA_SCPA || strategy > FDGA_FDPA_1LOOP) FAIL("fdga_sde: Calculation strategy unknown");
     if (strategy == FDGA_FDPA || strategy == FDGA_FDPA_NEW || strategy == FDGA_FDPA_1LOOP) {      // src/SDE.jl:4,8,13-24
         if (sde_chain(ctx, S, -1.0, FDGA_G0, true, 1, include_U2, include_Hartree)) return 1;
         LAUNCH(FDGA_T_MISC, add_axpby_kernel, nblk(ctx->lenG, 256), 256, S, ctx->G[FDGA_SIGMA0], 1.0, (const C*)nullptr, 0.0, (long long)ctx->lenG);
@@ -1650,14 +1656,14 @@ static int bse_stages_variant(fdga_ctx* ctx, int strategy) {
     return rc;
 }
 
-int fdga_iterate_solver(fdga_ctx* ctx, int strategy, int update_sigma) {
+int fdga_iterate_solver(fdga_ctx* ctx, int strategy, int update_sigma, int compute_hartree) {
     if (strategy < FDGA_SCPA || strategy > FDGA_FDPA_1LOOP) FAIL("fdga_iterate_solver: Calculation strategy unknown");
     if (update_sigma) { if (fdga_dyson(ctx) || (ctx->opt_local ? fdga_bubbles_local(ctx, 0) : fdga_bubbles_real_space(ctx, 0))) return 1; }
     if (fdga_build_K3_cache(ctx, 0, 0)) return 1;
     if (strategy >= FDGA_SCPA_NEW) { if (bse_stages_variant(ctx, strategy)) return 1; }
     else if (bse_stages(ctx, strategy == FDGA_FDPA, 0)) return 1;
     if (fdga_set_F_from_Fbuff(ctx)) return 1;
-    if (update_sigma) { if (fdga_sde(ctx, strategy, 1, 1)) return 1; }
+    if (update_sigma) { if (fdga_sde(ctx, strategy, 1, compute_hartree ? 1 : 0)) return 1; }      // SDE!(S; strategy, include_Hartree = compute_Hartree), src/solve.jl:99
     return 0;
 }
 
@@ -1902,7 +1908,7 @@ int fdga_fixed_point_preconditioned(fdga_ctx* ctx, const fdga_c64* host_x, fdga_
     CK(cudaMemcpyAsync(ctx->flat2, host_x, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
     if (unflatten_dev(ctx, ctx->lev[0], ctx->flat2, 1.0)) return 1;
     if (fdga_symmetrize_solver(ctx)) return 1;
-    if (fdga_iterate_solver(ctx, strategy, 0)) return 1;
+    if (fdga_iterate_solver(ctx, strategy, 0, 1)) return 1;
     // R_F = flatten(S.F) - x   (flat2 <- R_F)
     LAUNCH(FDGA_T_MISC, axpby_kernel, nblk(n, 256), 256, ctx->flat2, (const C*)ctx->lev[0].block, 1.0, (const C*)ctx->flat2, -1.0, (long long)n);
     CK(cudaGetLastError());

@@ -9,8 +9,10 @@ class Result:
         self.zero, self.f_converged, self.iterations, self.residual_norm = zero, f_converged, iterations, residual_norm
 
 
-def anderson(fixed_point, x0, *, m=50, beta=0.85, ftol=1e-4, iterations=40, show_trace=False):
-    """Solve R(x) = 0 where fixed_point(x) returns the residual R(x) = g(x) - x.  Converged when |R|_inf <= ftol."""
+def anderson(fixed_point, x0, *, m=50, beta=0.85, ftol=1e-4, iterations=40, show_trace=False, droptol=1e10):
+    """Solve R(x) = 0 where fixed_point(x) returns the residual R(x) = g(x) - x.  Converged when |R|_inf <= ftol.
+    droptol (NLsolve default 1e10): while the least-squares matrix of residual differences has a condition number above it, the
+    OLDEST history column is dropped, as NLsolve's anderson does on its QR factor."""
     x = np.array(x0, dtype=np.complex128, copy=True)
     Xs, Rs = [], []
     err = np.inf
@@ -29,6 +31,13 @@ def anderson(fixed_point, x0, *, m=50, beta=0.85, ftol=1e-4, iterations=40, show
         if len(Xs) == 1:
             x = x + beta * R
         else:
+            if droptol is not None:
+                while len(Xs) > 2:
+                    Rfac = np.linalg.qr(np.stack([Rs[i + 1] - Rs[i] for i in range(len(Rs) - 1)], axis=1), mode="r")
+                    if np.linalg.cond(Rfac) <= droptol:
+                        break
+                    Xs.pop(0)
+                    Rs.pop(0)
             dR = np.stack([Rs[i + 1] - Rs[i] for i in range(len(Rs) - 1)], axis=1)
             dX = np.stack([Xs[i + 1] - Xs[i] for i in range(len(Xs) - 1)], axis=1)
             gamma, *_ = np.linalg.lstsq(dR, R, rcond=None)

@@ -437,13 +437,19 @@ def SDE(S, strategy="scPA", include_U2=True, include_Hartree=True):
     S._call("fdga_sde", STRATEGY[strategy], int(include_U2), int(include_Hartree))
 
 
-def iterate_solver(S, strategy="fdPA", update_Σ=True):
-    """iterate_solver!(S; strategy, update_Σ): src/solve.jl:4-116 (fused inside the library)"""
+def SDE_channel_L(S, reference=False, level=0):
+    """SDE_channel_L_pp! / SDE_channel_L_ph! (src/nonlocal_2/SDE.jl:16-33, 54-73) for the chain starting at `level`, summed over
+    its levels with SDE!'s weights; S.pull("L") fetches S.Lpp, S.Lph"""
+    S._call("fdga_sde_channel_L", int(reference), int(level))
+
+
+def iterate_solver(S, strategy="fdPA", update_Σ=True, compute_Hartree=True):
+    """iterate_solver!(S; strategy, update_Σ, compute_Hartree): src/solve.jl:4-116 (fused inside the library)"""
     assert strategy in STRATEGY, "Calculation strategy unknown"      # src/solve.jl:10
-    S._call("fdga_iterate_solver", STRATEGY[strategy], int(update_Σ))
+    S._call("fdga_iterate_solver", STRATEGY[strategy], int(update_Σ), int(compute_Hartree))
 
 
-def iterate_solver_stepwise(S, strategy="fdPA", update_Σ=True):
+def iterate_solver_stepwise(S, strategy="fdPA", update_Σ=True, compute_Hartree=True):
     """Same sequence as iterate_solver, issued call by call (used by the tests to check the fused driver)."""
     if update_Σ:
         Dyson(S)
@@ -461,17 +467,17 @@ def iterate_solver_stepwise(S, strategy="fdPA", update_Σ=True):
             stage(S, ch)
     S._call("fdga_set_F_from_Fbuff")
     if update_Σ:
-        SDE(S, strategy)
+        SDE(S, strategy, include_Hartree=compute_Hartree)
 
 
-def fixed_point(R, x, S, strategy="fdPA", update_Σ=True):
+def fixed_point(R, x, S, strategy="fdPA", update_Σ=True, compute_Hartree=True):
     """fixed_point!(R, x, S): R = iterate(x) - x on the flattened [F; Σ] (src/solve.jl:119-157, src/ParquetSolver.jl:277-306)"""
     nF_ = S.length_F()
     S.unflatten_F(x[:nF_])
     if update_Σ:
         S.Σ[...] = np.asarray(x[nF_:]).reshape(S.Σ.shape, order="F")
         S.push("Σ")
-    iterate_solver(S, strategy, update_Σ)
+    iterate_solver(S, strategy, update_Σ, compute_Hartree)
     S.flatten_F(R[:nF_])
     if update_Σ:
         S.pull("Σ")
@@ -480,23 +486,22 @@ def fixed_point(R, x, S, strategy="fdPA", update_Σ=True):
     return R
 
 
-def solve(S, *, maxiter=100, tol=1e-4, δ=0.85, mem=8, verbose=False, strategy="fdPA", update_Σ=True):
-    """solve!(S; maxiter, tol, δ, mem, strategy, update_Σ): src/solve.jl:160-196 -- nlsolve(:anderson) on fixed_point! over the
-    flattened [F; Σ] (or F alone).  Returns the nlsolve-like result (zero, f_converged, iterations, residual_norm); the solver holds
-    the last iterate."""
+def solve(S, *, maxiter=100, tol=1e-4, δ=0.85, mem=8, verbose=False, strategy="fdPA", update_Σ=True, compute_Hartree=True):
+    """solve!(S; maxiter, tol, δ, mem, kwargs_solver...): src/solve.jl:160-196 -- nlsolve(:anderson) on fixed_point! over the
+    flattened [F; Σ] (or F alone).  Returns the nlsolve-like result (zero, f_converged, iterations, residual_norm).  As in the
+    reference, S is left in the state of the LAST iterate_solver! call (F, Σ = its outputs; G, Π = its inputs' Dyson / bubbles):
+    nothing is restored from res.zero."""
     from .nlsolve import anderson
     nF_ = S.length_F()
     x0 = S.flatten_F()
     if update_Σ:
         S.pull("Σ")
         x0 = np.concatenate([x0, S.Σ.ravel(order="F")])
-    res = anderson(lambda x: fixed_point(np.empty_like(x), x, S, strategy, update_Σ), x0, m=mem, beta=δ, ftol=tol, iterations=maxiter,
-                   show_trace=verbose)
-    S.unflatten_F(res.zero[:nF_])
-    S.F.unflatten(res.zero[:nF_])
+    res = anderson(lambda x: fixed_point(np.empty_like(x), x, S, strategy, update_Σ, compute_Hartree), x0, m=mem, beta=δ, ftol=tol,
+                   iterations=maxiter, show_trace=verbose)
+    S.pull("F")
     if update_Σ:
-        S.Σ[...] = res.zero[nF_:].reshape(S.Σ.shape, order="F")
-        S.push("Σ")
+        S.pull("Σ")
     return res
 
 

@@ -185,10 +185,17 @@ int  fdga_bse_K2_1loop(fdga_ctx*, int ch, int mfrg);
 int  fdga_bse_K3_1loop(fdga_ctx*, int ch, int mfrg);
 /* set!(S.F, S.Fbuff): src/solve.jl:87 */
 int  fdga_set_F_from_Fbuff(fdga_ctx*);
-/* SDE!(S; strategy, include_U2, include_Hartree): src/SDE.jl:3-48 -> src/nonlocal_2/SDE.jl:154-324 */
+/* SDE!(S; strategy, include_U2, include_Hartree): src/SDE.jl:3-48 -> src/nonlocal_2/SDE.jl:154-324.  An unknown strategy is
+ * rejected before S.Sigma is touched (src/SDE.jl:31). */
 int  fdga_sde(fdga_ctx*, int strategy, int include_U2, int include_Hartree);
-/* iterate_solver!(S; strategy, update_Sigma): src/solve.jl:4-116 (all five strategies) */
-int  fdga_iterate_solver(fdga_ctx*, int strategy, int update_sigma);
+/* SDE_channel_L_pp! and SDE_channel_L_ph! (src/nonlocal_2/SDE.jl:16-33, 54-73) for the vertex chain starting at level `from`
+ * (0 = S.F, 1 = S.F0, ...), summed over the levels of the chain with the weights SDE! gives them (1/3 for the RefVertex level,
+ * src/nonlocal_2/SDE.jl:305-309), against the bubbles of S (reference = 0) or the reference bubbles (reference = 1).
+ * Results: fdga_get_L.  (fdga_sde transforms these arrays in place afterwards, as the reference does: SURVEY E4.) */
+int  fdga_sde_channel_L(fdga_ctx*, int reference, int from);
+/* iterate_solver!(S; strategy, update_Sigma, compute_Hartree): src/solve.jl:4-116 (all five strategies); compute_hartree is
+ * forwarded to SDE! as include_Hartree (src/solve.jl:99; false for DGammaA runs whose Sigma0 already holds the Hartree term) */
+int  fdga_iterate_solver(fdga_ctx*, int strategy, int update_sigma, int compute_hartree);
 /* mfRGLinearMap matvec: src/mfRG.jl:34-89 (strategy fdPA); first = is_first_iteration */
 int  fdga_mfrg_matvec(fdga_ctx*, const fdga_c64* host_x, fdga_c64* host_y, int first);
 

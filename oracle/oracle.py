@@ -12,12 +12,12 @@ import sys
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_ROOT = os.path.dirname(_HERE)
-if _ROOT not in sys.path:
-    sys.path.insert(0, _ROOT)
-import fddgasolver_jl_b200  # noqa: E402,F401  (data containers only; no device code is touched)
-from fddgasolver_jl_b200.types import (NL2_Vertex, RefVertex, Vertex, aCh, dSp, nB, nF, pCh, pSp, tCh,  # noqa: E402
-                                       vertex_chain, xSp, zeros)
+if _HERE not in sys.path:
+    sys.path.insert(0, _HERE)
+# the oracle keeps its OWN data model (mesh lengths, shapes, flatten order restated from the reference): oracle/otypes.py.
+# Vertices handed in by tests in the product's containers are copied into it (otypes.adopt), never used in place.
+from otypes import (NL2_Vertex, RefVertex, Vertex, aCh, adopt, dSp, nB, nF, pCh, pSp, tCh,  # noqa: E402,F401
+                    vertex_chain, xSp, zeros)
 
 LIB = os.path.join(_HERE, "_build", "libfdga_oracle.so")
 INF = (2 ** 31 - 1) // 4
@@ -71,7 +71,7 @@ def _p(a):
 def vertex_struct(V):
     """ctypes descriptor of the nested vertex chain V -> V.F0 -> ... (arrays are referenced, not copied)"""
     out = _Vertex()
-    chain = vertex_chain(V)
+    chain = vertex_chain(adopt(V))
     out.nlev = len(chain)
     for i, X in enumerate(chain):
         lv = out.lev[i]
@@ -154,8 +154,8 @@ class OracleSolver:
         self.Σ0 = np.array(Σ0, dtype=np.complex128, order="F")
         self.G = self.G0.copy(order="F")
         self.Σ = self.Σ0.copy(order="F")
-        self.F0 = F0
-        self.F = NL2_Vertex(F0, self.T, nK1, nK2, nK3, self.L)
+        self.F0 = adopt(F0)
+        self.F = NL2_Vertex(self.F0, self.T, nK1, nK2, nK3, self.L)
         self.Fbuff = NL2_Vertex(RefVertex(self.T, 0.0), self.T, nK1, nK2, nK3, self.L)
         self.FL = NL2_Vertex(RefVertex(self.T, 0.0), self.T, nK1, nK2, nK3, self.L)
         shpΠ = (nB(self.nΠB), nF(self.nΠF), self.NP, self.NP)
@@ -462,8 +462,8 @@ def SDE(S, strategy="scPA", include_U2=True, include_Hartree=True):
             S.Σ -= (n0 - 1 / 2) * S.F.bare_vertex() * 1j
 
 
-def iterate_solver(S, strategy="fdPA", update_Σ=True):
-    """iterate_solver!(S; strategy, update_Σ): src/solve.jl:4-116"""
+def iterate_solver(S, strategy="fdPA", update_Σ=True, compute_Hartree=True):
+    """iterate_solver!(S; strategy, update_Σ, compute_Hartree): src/solve.jl:4-116"""
     assert strategy in ("fdPA", "scPA", "scPA_new", "fdPA_new", "fdPA_1loop"), "Calculation strategy unknown"
     order = (pCh, aCh, tCh)
     if update_Σ:
@@ -501,7 +501,7 @@ def iterate_solver(S, strategy="fdPA", update_Σ=True):
             BSE_K3(S, ch)
     S.F.set(S.Fbuff)
     if update_Σ:
-        SDE(S, strategy)
+        SDE(S, strategy, include_Hartree=compute_Hartree)      # src/solve.jl:99
 
 
 def _fourier_interpolate(yi, Lo, Li):

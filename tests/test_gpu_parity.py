@@ -457,3 +457,42 @@ def test_hubbard_chemical_potential_and_bare_green(orc):
     S2 = fd.NL2_ParquetSolver(4, (2, 2), (2, 2), 2, Gb, Gb, np.zeros_like(Gb), fd.RefVertex(0.5, 1.0), T=0.5)
     assert abs(fd.compute_hubbard_chemical_potential(0.2057188296739284, S2, {"t1": 1.0}) + 2.0) < 1e-11
     S2.close()
+
+
+def test_iterate_solver_compute_hartree_false(orc):
+    """iterate_solver!(S; compute_Hartree = false) forwards include_Hartree = false to SDE! (src/solve.jl:7,99): the DΓA case
+    whose Σ0 already contains the Hartree term.  Fused driver and call-by-call sequence against the oracle."""
+    import fddgasolver_jl_b200 as fd
+    S, R = make_pair(orc, nmax=2, nq=3, LG=6)
+    S2, _ = make_pair(orc, nmax=2, nq=3, LG=6)
+    for _ in range(2):
+        fd.iterate_solver(S, "fdPA", True, compute_Hartree=False)
+        fd.iterate_solver_stepwise(S2, "fdPA", True, compute_Hartree=False)
+        orc.iterate_solver(R, "fdPA", True, compute_Hartree=False)
+    S.pull("F", "Σ"); S2.pull("F", "Σ")
+    compare_vertex(S.F, R.F, "F")
+    assert rel(S.Σ, R.Σ) < TOL and rel(S2.Σ, R.Σ) < TOL
+    # and it differs from the default by exactly the Hartree shift i (n - 1/2) U of the last SDE! (both branches of fdPA)
+    S3, R3 = make_pair(orc, nmax=2, nq=3, LG=6)
+    fd.iterate_solver(S3, "fdPA", True)
+    S3.pull("Σ")
+    S4, _ = make_pair(orc, nmax=2, nq=3, LG=6)
+    fd.iterate_solver(S4, "fdPA", True, compute_Hartree=False)
+    S4.pull("Σ")
+    d = S3.Σ - S4.Σ
+    assert np.max(np.abs(d - d.flat[0])) < 1e-12 * max(1.0, abs(d.flat[0])) and abs(d.flat[0]) > 1e-6
+    for s in (S, S2, S3, S4):
+        s.close()
+
+
+def test_sde_rejects_unknown_strategy_before_touching_sigma(orc):
+    """src/SDE.jl:31 throws before S.Σ is modified"""
+    import fddgasolver_jl_b200 as fd
+    S, _ = make_pair(orc, nmax=2, nq=3, LG=6)
+    S.pull("Σ")
+    before = S.Σ.copy()
+    with pytest.raises(fd.FdgaError):
+        S._call("fdga_sde", 17, 1, 1)
+    S.pull("Σ")
+    assert np.array_equal(S.Σ, before)
+    S.close()
