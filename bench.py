@@ -37,7 +37,6 @@ def parse():
     p.add_argument("--nmax", type=int, default=4)
     p.add_argument("--nq", type=int, default=8)
     p.add_argument("--LG", type=int, default=48)
-    p.add_argument("--cpu-fraction", type=float, default=1.0 / 48, help="fraction of class representatives timed on the CPU per step")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
 
@@ -90,59 +89,28 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_iteration_seconds(o, R, frac):
-    """Time the oracle (reference loop structure, OpenMP over class representatives = the reference's
-    Threads.@threads over SG classes) on a contiguous sample of `frac` of the class representatives of every
-    kernel, and extrapolate each kernel linearly in the number of representatives to one full iteration."""
-    import fddgasolver_jl_b200 as fd
-    t_total, parts = 0.0, {}
+def host_threads(o):
+    """Use every host core whatever the launcher exported: torch.distributed.run sets OMP_NUM_THREADS=1 for its workers, which
+    silently pinned the CPU arm to one core in round 1."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    o.lib().orc_set_num_threads(int(n))
+    used = int(o.lib().orc_num_threads())
+    if used == 1 and n > 1:
+        raise SystemExit(f"bench.py: the CPU arm would run on 1 of {n} host cores; refusing to print a line")
+    return used
 
-    def timed(name, fn, n_total, n_sample):
-        nonlocal t_total
-        t0 = time.perf_counter()
-        fn(n_sample)
-        dt = (time.perf_counter() - t0) * n_total / max(n_sample, 1)
-        parts[name] = parts.get(name, 0.0) + dt
-        t_total += dt
 
-    ns = lambda n: max(1, int(round(n * frac)))
-    n3 = R.F.γp.K3.size
-    timed("cache", lambda n: o.build_K3_cache(R, 0, n), n3, ns(n3))
-    order = (fd.pCh, fd.aCh, fd.tCh)
-    for ch in order:
-        n2 = len(R.sg[o.SG_PP2 if ch == fd.pCh else o.SG_PH2][0]) - 1
-        timed("L_K2", lambda n: o.BSE_L_K2(R, ch, c0=0, c1=n), n2, ns(n2))
+def cpu_full_iteration(o, R, F_start):
+    """ONE complete, un-sampled pass of the hot path on the host: iterate_solver!(fdPA, update_Σ = false) + SDE!(scPA) of the
+    oracle restatement (reference loop structure, OpenMP over class representatives = the reference's Threads.@threads over the
+    symmetry classes).  Returns the measured wall time and its split."""
+    R.F.set(F_start)
     t0 = time.perf_counter()
-    for ch in order:
-        o.BSE_L_K3(R, ch)
-    parts["L_K3"] = time.perf_counter() - t0; t_total += parts["L_K3"]
-    for ch in order:
-        n1 = len(R.sg[o.SG_K1][0]) - 1
-        timed("K1", lambda n: o.BSE_K1(R, ch, c0=0, c1=n), n1, max(1, min(n1, int(round(n1 * frac * 4)))))
-    for ch in order:
-        n2 = len(R.sg[o.SG_PP2 if ch == fd.pCh else o.SG_PH2][0]) - 1
-        timed("K2", lambda n: o.BSE_K2(R, ch, c0=0, c1=n), n2, ns(n2))
-    t0 = time.perf_counter()
-    for ch in order:
-        o.BSE_K3(R, ch)
-    parts["K3"] = time.perf_counter() - t0; t_total += parts["K3"]
-    # SDE!(scPA): L kernels for every level of the F0 chain (sampled), real-space contraction and U^2 term (full, once)
-    nlev = len(fd.vertex_chain(R.F))
-    for lvl in range(nlev):
-        n2 = len(R.sg[o.SG_PP2][0]) - 1
-        timed("sde_L", lambda n: o.SDE_channel_L(R, R.Lpp, R.Πpp, R.F, lvl, True, 0, n), n2, ns(n2))
-        timed("sde_L", lambda n: o.SDE_channel_L(R, R.Lph, R.Πph, R.F, lvl, False, 0, n), n2, ns(n2))
-    t0 = time.perf_counter()
-    import ctypes as C
-    Σ = np.zeros_like(R.Σ)
-    sgΣ = o.sg_struct(R.sg[o.SG_SIGMA])
-    o.lib().orc_sde_real_space(o._p(Σ), R.nG, R.LG, o._p(R.G), R.nG, R.LG, o._p(R.Lpp), o._p(R.Lph), R.nK2[0], R.nK2[1], C.byref(sgΣ), C.byref(R.grid))
-    dt_rs = time.perf_counter() - t0
-    parts["sde_rs"] = dt_rs * nlev; t_total += dt_rs * nlev
-    t0 = time.perf_counter()
-    o.lib().orc_sde_U2(o._p(Σ), o._p(R.G), R.nG, R.LG, C.c_double(5.6), C.c_double(0.0), C.c_double(R.T), C.byref(sgΣ))
-    parts["sde_U2"] = time.perf_counter() - t0; t_total += parts["sde_U2"]
-    return t_total, parts
+    o.iterate_solver(R, "fdPA", False)
+    t1 = time.perf_counter()
+    o.SDE(R, "scPA")
+    t2 = time.perf_counter()
+    return t2 - t0, {"iterate_solver": round(t1 - t0, 3), "SDE": round(t2 - t1, 3)}
 
 
 def make_oracle_solver(o, inp, share_bubbles_from=None):
@@ -154,11 +122,13 @@ def make_oracle_solver(o, inp, share_bubbles_from=None):
         R.Π0pp, R.Π0ph, R.Πpp, R.Πph, R.G = S.Π0pp, S.Π0ph, S.Πpp, S.Πph, S.G.copy(order="F")
     R.init_sym_grp()
     R.F.set(inp["F"])
-    R.FL.set(inp["F"])     # any non-trivial FL: timing only
     return R
 
 
 def run_reference(a):
+    """--impl reference: the reference's CPU path (its restatement under oracle/; Julia + MatsubaraFunctions.jl are not installed on
+    any box) on all host cores.  Every timed step is one COMPLETE iteration, nothing is sampled or extrapolated; because a step
+    takes seconds, the number of timed steps is capped by a wall-clock budget and the line reports the steps actually run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -166,26 +136,26 @@ def run_reference(a):
     import fddgasolver_jl_b200 as fd
     import oracle as o
     o.build()
+    cores = host_threads(o)
     inp = fd.wu_point_inputs(a.nmax, a.nq, a.LG, F0_scale=0.02)
     R = make_oracle_solver(o, inp)
-    cores = o.lib().orc_num_threads()
-    # keep the whole run within minutes whatever K is, but never sample fewer than ~4 class representatives per host thread
-    frac = a.cpu_fraction * max(min(1.0, 60.0 / max(a.steps, 1)), 0.3)
-    for _ in range(a.warmup):
-        cpu_iteration_seconds(o, R, frac / 4)
-    ts = []
-    for _ in range(a.steps):
-        t, parts = cpu_iteration_seconds(o, R, frac)
+    budget = float(os.environ.get("FDGA_REF_BUDGET_S", "150"))
+    t_warm, _ = cpu_full_iteration(o, R, inp["F"]) if a.warmup > 0 else (0.0, None)      # one full warm-up pass (threads, page faults)
+    ts, parts = [], None
+    while len(ts) < max(a.steps, 1) and (not ts or sum(ts) + ts[-1] <= budget):
+        t, parts = cpu_full_iteration(o, R, inp["F"])
         ts.append(t)
     sec = float(np.mean(ts))
     val = 1.0 / sec
-    sample = f"{frac:.4f} of the class representatives of every BSE/SDE-L kernel per step, extrapolated linearly; K3 kernels, real-space SDE and U^2 term in full"
-    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-           "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex)",
-           "data": "synthetic", "config": {"workload": workload_name(a), "timing": "host wall clock of the CPU restatement (oracle/) of the reference algorithm; Julia + MatsubaraFunctions.jl are not installed"},
+    sample = (f"{len(ts)} complete un-sampled iteration(s) (iterate_solver!(fdPA, update_Σ=false) + SDE!(scPA)), measured wall time; "
+              f"{a.steps} requested, capped by a {budget:.0f} s budget")
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": len(ts), "steps_requested": a.steps,
+           "warmup": 1 if a.warmup > 0 else 0, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64 (complex)", "data": "synthetic",
+           "config": {"workload": workload_name(a), "timing": "host wall clock of complete iterations of the CPU restatement (oracle/) of the reference algorithm; Julia + MatsubaraFunctions.jl are not installed"},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "parts_s": {k: round(v, 3) for k, v in parts.items()}}
+           "seconds_per_step": [round(t, 3) for t in ts], "parts_s": parts, "timed_wall_s": round(sum(ts), 3), "warmup_wall_s": round(t_warm, 3)}
     print(json.dumps(out))
 
 
@@ -199,7 +169,10 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("FDGA_NCCL_DEBUG", "NONE")     # keep stdout to the one JSON line
+        # NCCL's communicator lines go to stderr (stdout carries the one JSON line): the driver counts the ranks from them
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     inp = fd.wu_point_inputs(a.nmax, a.nq, a.LG, F0_scale=0.02)
@@ -351,11 +324,12 @@ def run_ours(a):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as o
         o.build()
+        cores = host_threads(o)
         R = make_oracle_solver(o, inp, share_bubbles_from=S)
-        sec, parts = cpu_iteration_seconds(o, R, a.cpu_fraction)
-        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": o.lib().orc_num_threads(), "kind": "port",
-               "sample": f"{a.cpu_fraction:.4f} of the class representatives of every BSE/SDE-L kernel, extrapolated linearly; K3, real-space SDE, U^2 in full",
-               "s_per_iteration": sec, "parts_s": {k: round(v, 3) for k, v in parts.items()}}
+        sec, parts = cpu_full_iteration(o, R, inp["F"])
+        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "ONE complete un-sampled iteration (iterate_solver!(fdPA, update_Σ=false) + SDE!(scPA)) of the oracle restatement, measured wall time",
+               "s_per_iteration": sec, "parts_s": parts}
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W, "ms_per_step": ms / a.steps,

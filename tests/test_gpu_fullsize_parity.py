@@ -22,6 +22,8 @@ CACHES = ("cache_Γpx", "cache_F0p", "cache_F0a", "cache_F0t", "cache_Γpp", "ca
 def oracle_twin(orc, fd, S, inp, compute_bubbles):
     R = orc.OracleSolver(inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"], T=inp["T"],
                          compute_bubbles=compute_bubbles)
+    if not compute_bubbles:
+        orc.Dyson(R)            # G from (Gbare, Σ0), as the constructor does between the two bubble evaluations
     R.init_sym_grp()
     for which in range(8):      # index / symmetry tables: bit exact
         for a, b in zip(S._sg[which], R.sg[which]):
