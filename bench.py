@@ -255,15 +255,16 @@ def run_ours(a):
     S.profile(False)
     kernels = {k: {"ms_per_step": v[0] / PS, "launches_per_step": v[1] / PS} for k, v in kt.items() if v[1]}
 
-    # roofline of the dominant kernel (BSE_K2!, one launch per channel; DESIGN.md "Roofline")
+    # roofline of the dominant kernel: the contraction kernel of BSE_K2! (qlane_kernel<JOB_K2>; column_kernel on small meshes), one
+    # launch per channel, timed alone with CUDA events on the library's stream
     n2cls = [S.num_classes(fd._lib.SG_PP2), S.num_classes(fd._lib.SG_PH2), S.num_classes(fd._lib.SG_PH2)]
     nB2, nF2, NP, nFΠ = 2 * S.nK2[0] - 1, 2 * S.nK2[1], S.NP, 2 * S.nΠF
     chunk = [(-(-n // world)) for n in n2cls]           # representatives per rank
     tables = sum(sum(arr.size for arr in V.γp.arrays()) * 3 * 16 for V in fd.vertex_chain(S.F)[:-1]) + 4 * fd.vertex_chain(S.F)[-1].Fp_p.size * 16
-    bytes_per_launch = nB2 * NP * nFΠ * NP * 16 / world + tables + np.mean(chunk) * 16
-    flop_per_launch = 26.0 * np.mean(chunk) * nFΠ * NP
+    bytes_per_launch = nB2 * NP * nFΠ * NP * 16 / world + tables + np.mean(chunk) * 16      # R slabs of the K2 bosonic box + vertex tables + outputs
+    flop_per_launch = 26.0 * np.mean(chunk) * nFΠ * NP                                       # 26 flop per (representative, w, q) term
     k2 = kernels.get("column_K2", {"ms_per_step": float("nan"), "launches_per_step": 3})
-    k2_ms_launch = k2["ms_per_step"] / max(k2["launches_per_step"], 1)   # CUDA events around the column_kernel launches alone
+    k2_ms_launch = k2["ms_per_step"] / max(k2["launches_per_step"], 1)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -271,16 +272,19 @@ def run_ours(a):
         pass
     peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
     fp64_peak = S.measure_fp64_peak()                     # DFMA micro-benchmark, measured live on this device
+    traffic = None                                        # measured DRAM bytes per launch, from the committed ncu capture of this workload
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"nmax{a.nmax}_nq{a.nq}_LG{a.LG}_world{world}")
+        traffic = None if tr is None else {"dram_bytes_per_launch": tr["dram_bytes_per_launch"], "l2_to_l1_bytes_per_launch": tr.get("l2_to_l1_bytes_per_launch"), "source": tr["source"]}
+    except Exception:
+        pass
     ach = bytes_per_launch / (k2_ms_launch * 1e-3) / 1e9
-    roofline = {"kernel": "column_kernel<JOB_K2> (BSE_K2!, src/nonlocal_2/BSEa/BSEa_K2.jl:55-138), mean over the p, t, a launches", "bound": "hbm", "achieved": ach, "peak": peak_hbm,
+    roofline = {"kernel": "qlane_kernel<JOB_K2> (BSE_K2!, src/nonlocal_2/BSEa/BSEa_K2.jl:55-138), mean over the p, t, a launches", "bound": "hbm", "achieved": ach, "peak": peak_hbm,
                 "unit": "GB/s", "frac": ach / peak_hbm,
-                # dram__bytes_read.sum + dram__bytes_write.sum of column_kernel<JOB_K2, tCh> (the heaviest of the three launches the
-                # line averages over) at config 3, world 1, from profiles/r01_s2_column_slab_kernels_ncu_full.txt (ncu --set full);
-                # None for other workloads
-                "traffic": 19.78e6 if (a.nmax, a.nq, a.LG, world) == (4, 8, 48, 1) else None,
+                "traffic": None if traffic is None else traffic["dram_bytes_per_launch"], "traffic_detail": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": k2_ms_launch,
-                "note": "not HBM-bound: the L1 data pipe (LSU wavefronts 74 % of peak, ncu) and the index arithmetic bound this gather kernel; see fp64 and DESIGN.md section 4",
+                "note": "not HBM-bound: a gather contraction whose tables and slabs are L2-resident (DRAM traffic below the algorithmic bytes); bounded by L2 -> L1 latency at the occupancy its registers allow, see fp64 and DESIGN.md section 4",
                 "fp64": {"algorithmic_gflop_per_launch": flop_per_launch / 1e9, "achieved_tflops": flop_per_launch / (k2_ms_launch * 1e-3) / 1e12,
                          "peak_tflops": fp64_peak, "peak_source": "DFMA micro-benchmark in libfdga (fdga_measure_fp64_peak), measured in this run",
                          "frac": flop_per_launch / (k2_ms_launch * 1e-3) / 1e12 / fp64_peak}}
