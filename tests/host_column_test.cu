@@ -333,12 +333,13 @@ int main() {
     setvbuf(stdout, NULL, _IONBF, 0);
     srand(4242);
     double worst = 0.0;
-    for (int cfg = 0; cfg < 4; ++cfg) {
+    for (int cfg = 0; cfg < 5; ++cfg) {
         g_store.clear(); g_store.reserve(4096);
-        const int L = (cfg == 0) ? 3 : (cfg == 1 ? 4 : (cfg == 2 ? 2 : 1)), NP = L * L;      // cfg 3: the local solver's 1 x 1 mesh
+        const int L = (cfg == 0) ? 3 : (cfg == 1 ? 4 : (cfg == 2 ? 2 : (cfg == 3 ? 1 : 9))), NP = L * L;      // cfg 3: the local solver's 1 x 1 mesh; cfg 4: NP = 81, two momentum passes of the q-lane kernel
         Grid g; memset(&g, 0, sizeof(g));
-        g.T = 0.3; g.L = L; g.NP = NP; g.nK1 = (cfg == 1) ? 6 : 5; g.nPiB = g.nK1; g.nPiF = g.nK1;
-        g.nK2b = 3; g.nK2f = (cfg == 1) ? 4 : (cfg == 3 ? 5 : 2); g.nK3b = 2; g.nK3f = 2;
+        g.T = 0.3; g.L = L; g.NP = NP; g.nK1 = (cfg == 1) ? 6 : (cfg == 4 ? 8 : 5); g.nPiB = g.nK1; g.nPiF = g.nK1;
+        g.nK2b = (cfg == 4) ? 6 : 3;      // cfg 4: 11-wide K2 bosonic box = two entry rounds of the q-lane kernel
+        g.nK2f = (cfg == 1) ? 4 : (cfg == 3 ? 5 : 2); g.nK3b = 2; g.nK3f = 2;
         DevChain V; memset(&V, 0, sizeof(V)); V.L = L; V.NP = NP; V.nlev = 4;
         V.lev[0] = make_level(LV_NL2, g.nK1, g.nK2b, g.nK2f, g.nK3b, g.nK3f, NP);
         V.lev[1] = (cfg == 2) ? make_level(LV_NL2, 7, 4, 3, 2, 1, NP) : make_level(LV_NL2, g.nK1, g.nK2b, g.nK2f, g.nK3b, g.nK3f, NP);
