@@ -578,6 +578,46 @@ __global__ void bubbles_rs_kernel(const C* __restrict__ GR, C* __restrict__ Pipp
     PippR[i] = spp; PiphR[i] = sph;
 }
 
+// ---- bubbles_real_space! in product form --------------------------------------------------------------------------------
+// The reference fills Pi_R[W, v, R, R' -+ R] += G_R(W -+ v) G_R'(v) w(R) w(R') for R, R' in [-h, h]^2 (h = L / 2) and transforms
+// the four momentum axes back (src/nonlocal_2/bubble.jl:68-119).  Both the fill and the weights factorise, so
+//     Pipp[W, v, P, k] = Ghat(W - v - 1, P - k) * Ghat(v, k),      Piph[W, v, P, k] = Ghat(W + v, P + k) * Ghat(v, k),
+//     Ghat(n, p) = sum_{R in [-h, h]^2} w(R) G_R(n; R mod LG) exp(+2 pi i p.R / L)
+// with the COARSE-GRAINED Green function Ghat on the vertex mesh (0 outside the fermionic mesh, use_G_tail = false).  One
+// pointwise product per element, for any subset of the bubble: no 4-d transform, no bubble-sized intermediate.
+// w(R) = 1/2 per component with |R_c| = LG / 2 (LG even): as coded, the test is against the G mesh.
+__global__ void coarse_green_kernel(const C* __restrict__ GR, C* __restrict__ Ghat, int nG, int LG, int L, const C* __restrict__ twL) {
+    const int nGf = 2 * nG, NP = L * L, h = L / 2;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)nGf * NP) return;
+    const int n = (int)(i % nGf), p = (int)(i / nGf), px = p % L, py = p / L;
+    const bool even = (LG % 2 == 0);
+    C s = zeroC();
+    for (int R2 = -h; R2 <= h; ++R2) for (int R1 = -h; R1 <= h; ++R1) {
+        double w = 1.0;
+        if (even) { if (abs(R1) == LG / 2) w *= 0.5; if (abs(R2) == LG / 2) w *= 0.5; }
+        const C gr = GR[n + (size_t)nGf * (modL(R1, LG) + (size_t)LG * modL(R2, LG))];
+        s += gr * twL[modL(px * R1 + py * R2, L)] * w;
+    }
+    Ghat[i] = s;
+}
+FDGA_HD C ghat_call(const C* __restrict__ Ghat, int nG, int n, int ip) {
+    return inF(n, nG) ? Ghat[posF(n, nG) + (size_t)(2 * nG) * ip] : zeroC();
+}
+// the whole bubbles in the reference's layout [W, v, P, k]
+__global__ void bubbles_product_kernel(const C* __restrict__ Ghat, C* __restrict__ Pipp, C* __restrict__ Piph, Grid g) {
+    const int nBP = 2 * g.nPiB - 1, nFP = 2 * g.nPiF, L = g.L;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)nBP * nFP * g.NP * g.NP) return;
+    long long t = i;
+    const int iW = t % nBP; t /= nBP; const int iv = t % nFP; t /= nFP; const int iP = t % g.NP; const int ik = (int)(t / g.NP);
+    const int W = iW - (g.nPiB - 1), v = iv - g.nPiF;
+    const int Px = iP % L, Py = iP / L, kx = ik % L, ky = ik / L;
+    const C gk = ghat_call(Ghat, g.nG, v, ik);
+    Pipp[i] = ghat_call(Ghat, g.nG, W - v - 1, kidx(Px - kx, Py - ky, L)) * gk;
+    Piph[i] = ghat_call(Ghat, g.nG, W + v, kidx(Px + kx, Py + ky, L)) * gk;
+}
+
 // ---- bubbles_momentum_space!: src/nonlocal_2/bubble.jl:1-37 -----------------------------------------
 __global__ void bubbles_ms_kernel(const C* __restrict__ G, C* __restrict__ Pipp, C* __restrict__ Piph, Grid g) {
     const int nBP = 2 * g.nPiB - 1, nFP = 2 * g.nPiF, L = g.L, LG = g.LG, ratio = LG / L, nGf = 2 * g.nG;

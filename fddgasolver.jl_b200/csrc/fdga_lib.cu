@@ -90,6 +90,7 @@ struct fdga_ctx {
     C* SigR2;             // scratch of the U^2 term (its lane runs beside the real-space contraction)
     C* scratchA; C* scratchB; size_t lenScratch;   // bubble-sized ping-pong (DFTs)
     C* GR; C* GRm; C* SigR; C* SigTmp; C* SigAcc;  // G-sized scratch
+    C* Ghat[2];           // coarse-grained G / G0 on the vertex momentum mesh [nu, p] (bubbles in product form)
     C* flat; size_t lenFlat;                       // flatten staging (device)
     C* flat2;
     C* stash;                                      // fdga_stash_F / fdga_unstash_F
@@ -586,6 +587,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     ctx->lenScratch = ctx->lenPi;
     CKC(cudaMalloc(&ctx->scratchA, ctx->lenScratch * sizeof(C))); CKC(cudaMalloc(&ctx->scratchB, ctx->lenScratch * sizeof(C)));
     CKC(cudaMalloc(&ctx->GR, ctx->lenG * sizeof(C))); CKC(cudaMalloc(&ctx->GRm, ctx->lenG * sizeof(C)));
+    for (int i = 0; i < 2; i++) CKC(cudaMalloc(&ctx->Ghat[i], (size_t)2 * g.nG * g.NP * sizeof(C)));
     CKC(cudaMalloc(&ctx->SigR, ctx->lenG * sizeof(C))); CKC(cudaMalloc(&ctx->SigTmp, ctx->lenG * sizeof(C))); CKC(cudaMalloc(&ctx->SigAcc, ctx->lenG * sizeof(C)));
     ctx->lenFlat = 3 * (ctx->lev[0].len[0] + ctx->lev[0].len[1] + ctx->lev[0].len[2]);
     CKC(cudaMalloc(&ctx->flat, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->flat2, ctx->lenFlat * sizeof(C))); CKC(cudaMalloc(&ctx->stash, ctx->lenFlat * sizeof(C)));
@@ -632,7 +634,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (int i = 0; i < 4; i++) { cudaFree(ctx->Pi[i]); cudaFree(ctx->PiT[i]); cudaFree(ctx->Pisw[i]); }
     for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
     cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->Rt); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB);
-    cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
+    cudaFree(ctx->Ghat[0]); cudaFree(ctx->Ghat[1]); cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
     cudaFree(ctx->PiMixed[0]); cudaFree(ctx->PiMixed[1]); cudaFree(ctx->itpA); cudaFree(ctx->itpB);
     cudaFree(ctx->kryV); cudaFree(ctx->kryP); cudaFree(ctx->kryW); cudaFree(ctx->kryX); cudaFree(ctx->kryH); cudaFree(ctx->kryPart); cudaFree(ctx->kryTicket); if (ctx->kryHhost) cudaFreeHost(ctx->kryHhost);
     cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); for (int i = 0; i < 3; i++) { cudaFree(ctx->TtabL[i]); cudaFree(ctx->OwnTabL[i]); cudaFree(ctx->RtotL[i]); cudaFree(ctx->ConvTabL[i]); if (i) cudaFree(ctx->RtL[i]); } cudaFree(ctx->SigR2); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) cudaFree(ctx->d_slabs[i]);
@@ -979,11 +981,19 @@ int fdga_bubbles_real_space(fdga_ctx* ctx, int reference) {
     int ipp = reference ? FDGA_PI0PP : FDGA_PIPP, iph = reference ? FDGA_PI0PH : FDGA_PIPH;
     const C* Gsrc = ctx->G[reference ? FDGA_G0 : FDGA_G];
     if (dft2_G(ctx, Gsrc, ctx->GR, ctx->SigTmp, -1, 1.0 / ((double)g.LG * g.LG), FDGA_T_BUBBLE)) return 1;
-    LAUNCH(FDGA_T_BUBBLE, bubbles_rs_kernel, nblk(ctx->lenPi, 128), 128, ctx->GR, ctx->Pi[ipp], ctx->Pi[iph], g);
-    CK(cudaGetLastError());
-    long long pre = (long long)(2 * g.nPiB - 1) * (2 * g.nPiF);
-    if (dft4(ctx, ctx->Pi[ipp], ctx->scratchA, pre, +1, 1.0, FDGA_T_BUBBLE)) return 1;
-    if (dft4(ctx, ctx->Pi[iph], ctx->scratchA, pre, +1, 1.0, FDGA_T_BUBBLE)) return 1;
+    static const bool legacy = getenv("FDGA_BUBBLES_RS") ? atoi(getenv("FDGA_BUBBLES_RS")) != 0 : false;
+    if (!legacy) {      // product form on the coarse-grained Green function (fdga_kernels.cuh)
+        C* Ghat = ctx->Ghat[reference ? 1 : 0];
+        LAUNCH(FDGA_T_BUBBLE, coarse_green_kernel, nblk((long long)2 * g.nG * g.NP, 128), 128, ctx->GR, Ghat, g.nG, g.LG, g.L, ctx->twL);
+        LAUNCH(FDGA_T_BUBBLE, bubbles_product_kernel, nblk(ctx->lenPi, 256), 256, Ghat, ctx->Pi[ipp], ctx->Pi[iph], g);
+        CK(cudaGetLastError());
+    } else {            // the reference's own route: real-space fill + 4-d back transform (A/B check)
+        LAUNCH(FDGA_T_BUBBLE, bubbles_rs_kernel, nblk(ctx->lenPi, 128), 128, ctx->GR, ctx->Pi[ipp], ctx->Pi[iph], g);
+        CK(cudaGetLastError());
+        long long pre = (long long)(2 * g.nPiB - 1) * (2 * g.nPiF);
+        if (dft4(ctx, ctx->Pi[ipp], ctx->scratchA, pre, +1, 1.0, FDGA_T_BUBBLE)) return 1;
+        if (dft4(ctx, ctx->Pi[iph], ctx->scratchA, pre, +1, 1.0, FDGA_T_BUBBLE)) return 1;
+    }
     ctx->pi_dirty[ipp] = ctx->pi_dirty[iph] = true;
     invalidate_rt(ctx);
     return 0;
