@@ -43,6 +43,7 @@ struct ColJob {
     int nw, Ninner;             // inner frequency mesh (count, N)
     int slabW_N;                // bosonic mesh N used to index the R slab ([w + nw*(q + NP*(posB(W) + nB*iP))])
     double scale_re, scale_im;  // complex prefactor applied at the end
+    const int* slabmap;         // (position of W in the slab mesh, P) -> slab number of R (compact storage; null: natural order)
 };
 
 struct MomOff { int oK1, oK2A, oK2B, oK3; };
@@ -379,7 +380,7 @@ slab_own_kernel(const __grid_constant__ DevChain V, ColJob job, const int4* __re
     const int W = iW - (g.nK2b - 1), nw = job.nw, NP = g.NP, nF2 = 2 * g.nK2f, nB2 = 2 * g.nK2b - 1;
     C* Rsm = reinterpret_cast<C*>(sm_raw);                // [nw][NP] TMA-staged slab (absent when !use_tma)
     C* Rq = Rsm + (use_tma ? (size_t)nw * NP : 0);        // [nw], then part[PC * nw]
-    const C* Rs = R + (size_t)nw * NP * (posB(W, job.slabW_N) + (size_t)(2 * job.slabW_N - 1) * iP);
+    const C* Rs = R + (size_t)nw * NP * slab_index(job.slabmap, posB(W, job.slabW_N), 2 * job.slabW_N - 1, iP);
 #if defined(__CUDA_ARCH__)
     if (use_tma) {       // the slab is read twice (momentum sums, own-channel A' terms): one bulk copy, both passes from shared memory
         if (threadIdx.x == 0) fdga_mbar_init(&slab_bar, 1);
@@ -549,7 +550,7 @@ slab_conv_kernel(const __grid_constant__ DevChain V, ColJob job, const int4* __r
     const int4 sl = slabs[blockIdx.x];
     const int iW = sl.x, iP = sl.y;
     const int W = iW - (g.nK2b - 1), Px = iP % L, Py = iP / L;
-    const C* Rs = R + (size_t)nw * NP * (posB(W, job.slabW_N) + (size_t)(2 * job.slabW_N - 1) * iP);
+    const C* Rs = R + (size_t)nw * NP * slab_index(job.slabmap, posB(W, job.slabW_N), 2 * job.slabW_N - 1, iP);
 #if defined(__CUDA_ARCH__)
     if (use_tma) {
         if (tid == 0) fdga_mbar_init(&slab_bar, 1);
@@ -712,7 +713,6 @@ FDGA_HD void column_thread(const DevChain& V, const ColJob& job, const ColDev& c
         }
     }
     const size_t slab_stride = (size_t)nw * NP;
-    const C* Rp = R + slab_stride * (size_t)(2 * job.slabW_N - 1) * iP;
 
     // w is split in WS chunks so that small momentum meshes still fill the CTA
     int WS = 1;
@@ -755,7 +755,7 @@ FDGA_HD void column_thread(const DevChain& V, const ColJob& job, const ColDev& c
                         job_freq_args<KIND, CH>(Wg[i], nug[i], 0, v_a, w_a); job_freq_args<KIND, CH>(Wg[i], nug[i], 1, v_b, w_b);
                         convert_freq(Wg[i], v_a, w_a, form, r, W0, v0, w0); convert_freq(Wg[i], v_b, w_b, form, r, W1, v1, w1);
                         Lin lW = {W0, W1 - W0}, lv2 = {v0, v1 - v0}, lw2 = {w0, w1 - w0};
-                        const C* Rq = Rp + slab_stride * posB(Wg[i], job.slabW_N) + iq;      // element win of this q: Rq[(win + Nin) * NP]
+                        const C* Rq = R + slab_stride * slab_index(job.slabmap, posB(Wg[i], job.slabW_N), 2 * job.slabW_N - 1, iP) + iq;      // element win of this q: Rq[(win + Nin) * NP]
                         acc[i] += chan_lin_sum(lv, r, mo, lW, lv2, lw2, Rq, job.Ninner, NP, w_lo, w_hi, rs_chunk, withK1) * cf;
                     }
                 }

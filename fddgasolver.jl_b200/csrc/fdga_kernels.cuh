@@ -145,13 +145,22 @@ __global__ void swave_tables2_kernel(DevLevel lv, int NP, SwOut out) {
 // Slab layout used by every contraction kernel: element (w, q) of the slab (W, P) sits at  q + NP * w  (q fastest), so that a
 // warp whose lanes run over the inner momentum q reads one contiguous run per inner frequency.
 FDGA_HD size_t slab_at(int iw, int iq, int NP) { return (size_t)iq + (size_t)NP * iw; }
-__global__ void pi_transpose_kernel(const C* __restrict__ Pi, C* __restrict__ PiT, int nB, int nF, int NP) {
+// Slab storage is COMPACT: a rank only holds the (W, P) slabs that carry one of its class representatives, in the order of its
+// slab list; `map` translates (position of W in the bosonic mesh, P) into the position in that list (null: all slabs, natural order).
+FDGA_HD size_t slab_index(const int* __restrict__ map, int iWo, int nBo, int iP) {
+    const int j = iWo + nBo * iP;
+    return map ? (size_t)map[j] : (size_t)j;
+}
+// slabs (list entries (iW, iP)) of a bubble given in the reference's layout [W, v, P, k]
+__global__ void pi_gather_slabs_kernel(const C* __restrict__ Pi, C* __restrict__ PiT, int nB, int nF, int NP,
+                                       const int4* __restrict__ slabs, int nslabs) {
     // one thread per output element, output index contiguous
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long n = (long long)nB * nF * NP * NP;
+    long long n = (long long)nF * NP * nslabs;
     if (i >= n) return;
     long long t = i;
-    int iq = t % NP; t /= NP; int iw = t % nF; t /= nF; int iW = t % nB; int iP = t / nB;
+    int iq = t % NP; t /= NP; int iw = t % nF; int sl = (int)(t / nF);
+    const int iW = slabs[sl].x, iP = slabs[sl].y;
     PiT[i] = Pi[iW + (size_t)nB * (iw + (size_t)nF * (iP + (size_t)NP * iq))];
 }
 __global__ void pi_swave_kernel(const C* __restrict__ Pi, C* __restrict__ Pisw, int nB, int nF, int NP) {
@@ -168,7 +177,7 @@ __global__ void pi_swave_kernel(const C* __restrict__ Pi, C* __restrict__ Pisw, 
 //  RK_MF_K1 : Pi0 * FL(W, w~, inf; P, q~, k0)                                           BSEa_K1.jl:33-37
 //  RK_MF_K2 : Pi0 * FL(W, w, inf; P, q, k0)                                             BSEa_K2.jl:100-104
 //  RK_LK2   : Pi0 * F0(W, w, inf; P, q, k0), w on the K2 nu-mesh                        BSEa_K2.jl:38-41
-// Rt layout: [iq + NP*(iw + nw*(iWo + nBo*iP))] (slab_at), W on the OUTPUT bosonic mesh (N = No).
+// Rt layout: [iq + NP*(iw + nw*slab)] (slab_at), slab = position of (W, P) in the list; W on the OUTPUT bosonic mesh (N = No).
 //  RK_LK2_LOC : Pi0 * F0(W, w~, inf), w on the bubble nu-mesh (local solver)                src/BSEa/BSEa_K2.jl:27-30
 //  RK_1L    : (Pi - Pi0) * F0(W, w~, inf; P, q~, k0)  (fd branch of the 1-loop variants)   BSE_1loop.jl:41-46,104-109
 enum { RK_FD = 0, RK_MF_K1 = 1, RK_MF_K2 = 2, RK_LK2 = 3, RK_LK2_LOC = 4, RK_1L = 5 };
@@ -177,7 +186,7 @@ enum { RK_FD = 0, RK_MF_K1 = 1, RK_MF_K2 = 2, RK_LK2 = 3, RK_LK2_LOC = 4, RK_1L 
 template <int CH, int KIND>
 __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ DevChain FL,
                                     const C* __restrict__ Pi0T, const C* __restrict__ PiT, C* __restrict__ Rt,
-                                    Grid g, int No, int Ninner, const int4* __restrict__ slabs, int nslabs) {
+                                    Grid g, int No, int Ninner, const int4* __restrict__ slabs, int nslabs, const int* __restrict__ pimap) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
     const int nw = 2 * Ninner, nBo = 2 * No - 1, nFP = 2 * g.nPiF, nBP = 2 * g.nPiB - 1;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -189,7 +198,7 @@ __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const _
     const int iWo = s2.x, iP = s2.y;
     int W = iWo - (No - 1), w = iw - Ninner;
     int Px = iP % g.L, Py = iP / g.L, qx = iq % g.L, qy = iq / g.L;
-    size_t pidx = slab_at(posF(w, g.nPiF), iq, g.NP) + (size_t)nFP * g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP);
+    size_t pidx = slab_at(posF(w, g.nPiF), iq, g.NP) + (size_t)nFP * g.NP * slab_index(pimap, posB(W, g.nPiB), nBP, iP);
     Arg a;
     a.W = W; a.w = FDGA_INF; a.Px = Px; a.Py = Py; a.qx = 0; a.qy = 0;
     if (KIND == RK_FD || KIND == RK_MF_K1 || KIND == RK_LK2_LOC || KIND == RK_1L) {   // crossed arguments (_crossing, BSE_templates.jl:4-6)
@@ -211,20 +220,21 @@ __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const _
     } else {
         r = Pi0T[pidx] * eval_vertex<false>(FL, 0, CH, SP, a, FL_ALL);
     }
-    Rt[slab_at(iw, iq, g.NP) + (size_t)nw * g.NP * (iWo + (size_t)nBo * iP)] = r;
+    (void)nBo;
+    Rt[slab_at(iw, iq, g.NP) + (size_t)nw * g.NP * sl] = r;      // compact: slab number = position in the list
 }
 
 // ---- BSE_K1!: src/nonlocal_2/BSEa/BSEa_K1.jl:19-52.  One CTA per class representative (W, P) ------
 template <int CH>
 __global__ void bse_k1_kernel(const __grid_constant__ DevChain Fleft, const C* __restrict__ Rt, C* __restrict__ repvals,
-                              SymDev sg, long long c0, Grid g, double scale) {
+                              SymDev sg, long long c0, Grid g, double scale, const int* __restrict__ map) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
     long long cls = c0 + blockIdx.x;
     long long idx = sg.index[sg.offsets[cls]];
     const int nB1 = 2 * g.nK1 - 1, nw = 2 * g.nPiF;
     int iW = idx % nB1, iP = idx / nB1;
     int W = iW - (g.nK1 - 1), Px = iP % g.L, Py = iP / g.L;
-    const C* slab = Rt + (size_t)nw * g.NP * (iW + (size_t)nB1 * iP);
+    const C* slab = Rt + (size_t)nw * g.NP * slab_index(map, iW, nB1, iP);
     C acc = zeroC();
     for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
         int iq = t % g.NP, iw = t / g.NP;
@@ -239,7 +249,7 @@ __global__ void bse_k1_kernel(const __grid_constant__ DevChain Fleft, const C* _
 // ---- BSE_L_K2!: src/nonlocal_2/BSEa/BSEa_K2.jl:17-43.  One CTA per representative (W, v, P, k) -----
 template <int CH>
 __global__ void bse_lk2_kernel(const __grid_constant__ DevChain F, const C* __restrict__ Rt, C* __restrict__ repvals,
-                               SymDev sg, long long c0, Grid g, double scale) {
+                               SymDev sg, long long c0, Grid g, double scale, const int* __restrict__ map) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
     constexpr unsigned FLG = (CH == CH_P ? 0u : FL_GP) | (CH == CH_T ? 0u : FL_GT) | (CH == CH_A ? 0u : FL_GA);
     long long cls = c0 + blockIdx.x;
@@ -248,7 +258,7 @@ __global__ void bse_lk2_kernel(const __grid_constant__ DevChain F, const C* __re
     long long t0 = idx;
     int iW = t0 % nB2; t0 /= nB2; int iv = t0 % nF2; t0 /= nF2; int iP = t0 % g.NP; int ik = t0 / g.NP;
     int W = iW - (g.nK2b - 1), v = iv - g.nK2f, Px = iP % g.L, Py = iP / g.L, kx = ik % g.L, ky = ik / g.L;
-    const C* slab = Rt + (size_t)nw * g.NP * (iW + (size_t)nB2 * iP);
+    const C* slab = Rt + (size_t)nw * g.NP * slab_index(map, iW, nB2, iP);
     C acc = zeroC();
     for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
         int iq = t % g.NP, iw = t / g.NP;
@@ -268,7 +278,7 @@ __global__ void bse_lk2_kernel(const __grid_constant__ DevChain F, const C* __re
 //  mfRG : [F0(W,v,w~;P,k,q~) - F0(W,inf,w~;P,k,q~)] * Rt           (Fleft = S.F0)
 template <int CH, bool MF>
 __global__ void bse_k2_kernel(const __grid_constant__ DevChain Fleft, const C* __restrict__ Rt, C* __restrict__ repvals,
-                              SymDev sg, long long c0, Grid g, double scale) {
+                              SymDev sg, long long c0, Grid g, double scale, const int* __restrict__ map) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
     long long cls = c0 + blockIdx.x;
     long long idx = sg.index[sg.offsets[cls]];
@@ -276,7 +286,7 @@ __global__ void bse_k2_kernel(const __grid_constant__ DevChain Fleft, const C* _
     long long t0 = idx;
     int iW = t0 % nB2; t0 /= nB2; int iv = t0 % nF2; t0 /= nF2; int iP = t0 % g.NP; int ik = t0 / g.NP;
     int W = iW - (g.nK2b - 1), v = iv - g.nK2f, Px = iP % g.L, Py = iP / g.L, kx = ik % g.L, ky = ik / g.L;
-    const C* slab = Rt + (size_t)nw * g.NP * (iW + (size_t)nB2 * iP);
+    const C* slab = Rt + (size_t)nw * g.NP * slab_index(map, iW, nB2, iP);
     C acc = zeroC();
     for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
         int iq = t % g.NP, iw = t / g.NP;
@@ -301,14 +311,14 @@ __global__ void bse_k2_kernel(const __grid_constant__ DevChain Fleft, const C* _
 template <int CH>
 __global__ void bse_k1_new_kernel(const __grid_constant__ DevChain F, const __grid_constant__ DevChain F0,
                                   const C* __restrict__ Pi0T, const C* __restrict__ PiT, C* __restrict__ repvals,
-                                  SymDev sg, long long c0, Grid g, C scaleU, int mfrg) {
+                                  SymDev sg, long long c0, Grid g, C scaleU, int mfrg, const int* __restrict__ map) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
     long long cls = c0 + blockIdx.x;
     long long idx = sg.index[sg.offsets[cls]];
     const int nB1 = 2 * g.nK1 - 1, nw = 2 * g.nPiF, nBP = 2 * g.nPiB - 1;
     int iW = idx % nB1, iP = idx / nB1;
     int W = iW - (g.nK1 - 1), Px = iP % g.L, Py = iP / g.L;
-    const size_t off = (size_t)nw * g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP);
+    const size_t off = (size_t)nw * g.NP * slab_index(map, posB(W, g.nPiB), nBP, iP);
     C acc = zeroC();
     for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
         int iq = t % g.NP, iw = t / g.NP;
@@ -327,7 +337,7 @@ __global__ void bse_k1_new_kernel(const __grid_constant__ DevChain F, const __gr
 template <int CH>
 __global__ void bse_k2_new_kernel(const __grid_constant__ DevChain F, const __grid_constant__ DevChain F0,
                                   const C* __restrict__ Pi0T, const C* __restrict__ PiT, C* __restrict__ repvals,
-                                  SymDev sg, long long c0, Grid g, C scaleU, int mfrg) {
+                                  SymDev sg, long long c0, Grid g, C scaleU, int mfrg, const int* __restrict__ map) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
     long long cls = c0 + blockIdx.x;
     long long idx = sg.index[sg.offsets[cls]];
@@ -335,7 +345,7 @@ __global__ void bse_k2_new_kernel(const __grid_constant__ DevChain F, const __gr
     long long t0 = idx;
     int iW = t0 % nB2; t0 /= nB2; int iv = t0 % nF2; t0 /= nF2; int iP = t0 % g.NP; int ik = t0 / g.NP;
     int W = iW - (g.nK2b - 1), v = iv - g.nK2f, Px = iP % g.L, Py = iP / g.L, kx = ik % g.L, ky = ik / g.L;
-    const size_t off = (size_t)nFP * g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP);
+    const size_t off = (size_t)nFP * g.NP * slab_index(map, posB(W, g.nPiB), nBP, iP);
     C acc = zeroC();
     for (int t = threadIdx.x; t < nF2 * g.NP; t += blockDim.x) {
         int iq = t % g.NP, iw = t / g.NP;
@@ -478,14 +488,14 @@ __global__ void cache_mfrg_kernel(const __grid_constant__ DevChain F0, const __g
 // ---- SDE_channel_L_pp!/ph!: src/nonlocal_2/SDE.jl:16-33, 54-73, 96-111, 130-145.  CTA per rep --------
 template <bool PP>
 __global__ void sde_L_kernel(const __grid_constant__ DevChain V, int level, const C* __restrict__ PiT,
-                             C* __restrict__ repvals, SymDev sg, long long c0, Grid g, C U, double scale, int own_only) {
+                             C* __restrict__ repvals, SymDev sg, long long c0, Grid g, C U, double scale, int own_only, const int* __restrict__ map) {
     long long cls = c0 + blockIdx.x;
     long long idx = sg.index[sg.offsets[cls]];
     const int nB2 = 2 * g.nK2b - 1, nF2 = 2 * g.nK2f, nw = 2 * g.nPiF, nBP = 2 * g.nPiB - 1;
     long long t0 = idx;
     int iW = t0 % nB2; t0 /= nB2; int iv = t0 % nF2; t0 /= nF2; int iP = t0 % g.NP; int ik = t0 / g.NP;
     int W = iW - (g.nK2b - 1), v = iv - g.nK2f, Px = iP % g.L, Py = iP / g.L, kx = ik % g.L, ky = ik / g.L;
-    const C* slab = PiT + (size_t)nw * g.NP * (posB(W, g.nPiB) + (size_t)nBP * iP);
+    const C* slab = PiT + (size_t)nw * g.NP * slab_index(map, posB(W, g.nPiB), nBP, iP);
     const bool is_core = V.lev[level].type == LV_CORE;
     C acc = zeroC();
     for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
@@ -603,6 +613,33 @@ __global__ void coarse_green_kernel(const C* __restrict__ GR, C* __restrict__ Gh
 }
 FDGA_HD C ghat_call(const C* __restrict__ Ghat, int nG, int n, int ip) {
     return inF(n, nG) ? Ghat[posF(n, nG) + (size_t)(2 * nG) * ip] : zeroC();
+}
+// one bubble on the listed slabs, slab layout [q, w | slab]
+__global__ void bubble_slabs_kernel(const C* __restrict__ Ghat, C* __restrict__ PiT, Grid g, int pp, const int4* __restrict__ slabs, int nslabs) {
+    const int nFP = 2 * g.nPiF, L = g.L, NP = g.NP;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)nFP * NP * nslabs) return;
+    long long t = i;
+    const int iq = t % NP; t /= NP; const int iw = t % nFP; const int sl = (int)(t / nFP);
+    const int W = slabs[sl].x - (g.nPiB - 1), iP = slabs[sl].y, v = iw - g.nPiF;
+    const int Px = iP % L, Py = iP / L, kx = iq % L, ky = iq / L;
+    const C gk = ghat_call(Ghat, g.nG, v, iq);
+    PiT[i] = (pp ? ghat_call(Ghat, g.nG, W - v - 1, kidx(Px - kx, Py - ky, L)) : ghat_call(Ghat, g.nG, W + v, kidx(Px + kx, Py + ky, L))) * gk;
+}
+// Pisw[W, v, P] = mean_k Pi[W, v, P, k] of one bubble
+__global__ void bubble_swave_kernel(const C* __restrict__ Ghat, C* __restrict__ Pisw, Grid g, int pp) {
+    const int nBP = 2 * g.nPiB - 1, nFP = 2 * g.nPiF, L = g.L, NP = g.NP;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)nBP * nFP * NP) return;
+    long long t = i;
+    const int iW = t % nBP; t /= nBP; const int iv = t % nFP; const int iP = (int)(t / nFP);
+    const int W = iW - (g.nPiB - 1), v = iv - g.nPiF, Px = iP % L, Py = iP / L;
+    C s = zeroC();
+    for (int ik = 0; ik < NP; ++ik) {
+        const int kx = ik % L, ky = ik / L;
+        s += (pp ? ghat_call(Ghat, g.nG, W - v - 1, kidx(Px - kx, Py - ky, L)) : ghat_call(Ghat, g.nG, W + v, kidx(Px + kx, Py + ky, L))) * ghat_call(Ghat, g.nG, v, ik);
+    }
+    Pisw[i] = s / (double)NP;
 }
 // the whole bubbles in the reference's layout [W, v, P, k]
 __global__ void bubbles_product_kernel(const C* __restrict__ Ghat, C* __restrict__ Pipp, C* __restrict__ Piph, Grid g) {

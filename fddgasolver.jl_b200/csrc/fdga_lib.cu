@@ -52,6 +52,7 @@ struct SymGroup {
 };
 struct TimedEvent { cudaEvent_t a, b; int cat; };
 struct Pending { SymGroup* s; C* rep; C* out; int kind, ch; bool expanded; };
+enum { PI_NONE = 0, PI_GHAT = 1, PI_FULL = 2 };
 enum { PK_K1 = 0, PK_LK2 = 1, PK_K2 = 2, PK_LK3 = 3, PK_K3 = 4, PK_K2_NOFL = 5 };
 
 // NCCL through dlopen (no link-time dependency; the process may already hold torch's libnccl)
@@ -77,7 +78,10 @@ struct fdga_ctx {
     LevelBuf lev[FDGA_MAX_LEVELS];
     LevelBuf FL, Fbuff;
     C* G[5]; size_t lenG;
-    C* Pi[4]; C* PiT[4]; C* Pisw[4]; size_t lenPi, lenPisw; bool pi_dirty[4];
+    // bubbles.  Pi[i]: the reference's layout [W, v, P, k], allocated only when a caller reads / writes a bubble in that layout
+    // or mixes bubbles; PiT[i]: COMPACT slab storage [q, w | slab] of the slabs this rank reads; Pisw[i] = mean_k.
+    // pi_src: where the truth of bubble i lives (PI_NONE zeros, PI_GHAT product of the coarse-grained G, PI_FULL Pi[i])
+    C* Pi[4]; C* PiT[4]; C* Pisw[4]; size_t lenPi, lenPisw; bool pi_dirty[4]; int pi_src[4]; bool pi_full_valid[4];
     C* cache[10]; size_t lenK3;
     C* L[2];              // Lpp, Lph (K2-shaped)
     C* Rt;                // hoisted right factor, bubble-sized (= RtL[0])
@@ -116,6 +120,9 @@ struct fdga_ctx {
     C* twL; C* twLG;         // DFT twiddles exp(2 pi i j / n) for n = L, LG
     LevelBuf Fsum; bool has_fsum, fsum_dirty;   // K tables of lev[0] + lev[1] when both are NL2 on identical meshes
     int4* d_slabs[4]; int n_slabs[4]; bool slabs_dirty;   // active (W,P) slabs: [pp|ph] x [bubble mesh | K2 mesh]
+    int* d_slabmap[4];    // (iW + nB * iP) -> position in d_slabs[kind] (-1: not held by this rank)
+    size_t lenRtL;        // elements of RtL[i]
+    C* scratchBig;        // bubble-sized scratch of the legacy bubble route (FDGA_BUBBLES_RS=1), allocated on demand
     // device-resident DQGMRES workspace (fdga_mfrg_dqgmres): rings of `kry_mem` basis / direction vectors, work vector, iterate
     C* kryV; C* kryP; C* kryW; C* kryX; C* kryH; C* kryPart; unsigned int* kryTicket; C* kryHhost; int kry_mem;
     C* itpA; C* itpB; size_t lenItp;   // ping-pong of fdga_interpolate_* when the bubble-sized scratch is too small (coarsening)
@@ -337,12 +344,48 @@ static int refresh_mom_all(fdga_ctx* ctx, unsigned need = MOM_ALL) {
     if ((need & MOM_FSUM) && ctx->has_fsum && !ctx->fsum_dirty && ensure_mom(ctx, ctx->Fsum)) return 1;
     return 0;
 }
+static int ensure_slabs(fdga_ctx* ctx);
+// the bubble `which` in the reference's layout, materialised on demand
+static int ensure_pi_full(fdga_ctx* ctx, int which) {
+    if (!ctx->Pi[which]) { CK(cudaMalloc(&ctx->Pi[which], ctx->lenPi * sizeof(C))); ctx->pi_full_valid[which] = false; }
+    if (ctx->pi_full_valid[which]) return 0;
+    if (ctx->pi_src[which] == PI_GHAT) {
+        const int other = which ^ 1;                       // the pp / ph partner of the same Green function is produced alongside
+        if (!ctx->Pi[other]) { CK(cudaMalloc(&ctx->Pi[other], ctx->lenPi * sizeof(C))); ctx->pi_full_valid[other] = false; }
+        const bool fill_other = ctx->pi_src[other] == PI_GHAT && !ctx->pi_full_valid[other];
+        C* tmp = nullptr;
+        if (!fill_other) CK(cudaMalloc(&tmp, ctx->lenPi * sizeof(C)));      // partner holds explicit data: do not overwrite it
+        C* pp = (which % 2 == 0) ? ctx->Pi[which] : (fill_other ? ctx->Pi[other] : tmp);
+        C* ph = (which % 2 == 1) ? ctx->Pi[which] : (fill_other ? ctx->Pi[other] : tmp);
+        LAUNCH(FDGA_T_BUBBLE, bubbles_product_kernel, nblk(ctx->lenPi, 256), 256, ctx->Ghat[which < 2 ? 1 : 0], pp, ph, ctx->g);
+        CK(cudaGetLastError());
+        if (tmp) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(tmp); }
+        if (fill_other) ctx->pi_full_valid[other] = true;
+    } else if (ctx->pi_src[which] == PI_NONE) {
+        CK(cudaMemsetAsync(ctx->Pi[which], 0, ctx->lenPi * sizeof(C), ctx->stream));
+    }
+    ctx->pi_full_valid[which] = true;
+    return 0;
+}
+// compact slabs + s-wave mean of bubble `which`, refreshed lazily
 static int refresh_pi(fdga_ctx* ctx, int which) {
+    if (ensure_slabs(ctx)) return 1;
     if (!ctx->pi_dirty[which]) return 0;
     Scope sc(ctx, FDGA_T_MISC);
-    int nB = 2 * ctx->g.nPiB - 1, nF = 2 * ctx->g.nPiF, NP = ctx->g.NP;
-    LAUNCH(FDGA_T_MISC, pi_transpose_kernel, nblk(ctx->lenPi, 256), 256, ctx->Pi[which], ctx->PiT[which], nB, nF, NP);
-    LAUNCH(FDGA_T_MISC, pi_swave_kernel, nblk(ctx->lenPisw, 256), 256, ctx->Pi[which], ctx->Pisw[which], nB, nF, NP);
+    const int nB = 2 * ctx->g.nPiB - 1, nF = 2 * ctx->g.nPiF, NP = ctx->g.NP;
+    const int pp = (which % 2 == 0) ? 1 : 0, kind = pp ? 0 : 1, nsl = ctx->n_slabs[kind];
+    const long long nel = (long long)nF * NP * nsl;
+    if (ctx->pi_src[which] == PI_GHAT) {
+        const C* Ghat = ctx->Ghat[which < 2 ? 1 : 0];
+        if (nsl) LAUNCH(FDGA_T_MISC, bubble_slabs_kernel, nblk(nel, 256), 256, Ghat, ctx->PiT[which], ctx->g, pp, ctx->d_slabs[kind], nsl);
+        LAUNCH(FDGA_T_MISC, bubble_swave_kernel, nblk(ctx->lenPisw, 128), 128, Ghat, ctx->Pisw[which], ctx->g, pp);
+    } else if (ctx->pi_src[which] == PI_FULL) {
+        if (nsl) LAUNCH(FDGA_T_MISC, pi_gather_slabs_kernel, nblk(nel, 256), 256, ctx->Pi[which], ctx->PiT[which], nB, nF, NP, ctx->d_slabs[kind], nsl);
+        LAUNCH(FDGA_T_MISC, pi_swave_kernel, nblk(ctx->lenPisw, 256), 256, ctx->Pi[which], ctx->Pisw[which], nB, nF, NP);
+    } else {
+        if (nsl) CK(cudaMemsetAsync(ctx->PiT[which], 0, (size_t)nel * sizeof(C), ctx->stream));
+        CK(cudaMemsetAsync(ctx->Pisw[which], 0, ctx->lenPisw * sizeof(C), ctx->stream));
+    }
     CK(cudaGetLastError());
     ctx->pi_dirty[which] = false;
     return 0;
@@ -511,10 +554,37 @@ static int ensure_slabs(fdga_ctx* ctx) {
             list.push_back(make_int4(iW, iP, (int)(unsigned)(m & 0xffffffffULL), (int)(unsigned)(m >> 32)));
         }
         cudaFree(ctx->d_slabs[kind]); ctx->d_slabs[kind] = nullptr; ctx->n_slabs[kind] = (int)list.size();
+        cudaFree(ctx->d_slabmap[kind]); ctx->d_slabmap[kind] = nullptr;
+        std::vector<int> map((size_t)nBo * NP, -1);
+        for (size_t i = 0; i < list.size(); i++) map[list[i].x + (size_t)nBo * list[i].y] = (int)i;
+        CK(cudaMalloc(&ctx->d_slabmap[kind], map.size() * sizeof(int)));
+        CK(cudaMemcpy(ctx->d_slabmap[kind], map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
         if (!list.empty()) {
             CK(cudaMalloc(&ctx->d_slabs[kind], list.size() * sizeof(int4)));
             CK(cudaMemcpy(ctx->d_slabs[kind], list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice));
         }
+    }
+    {   // compact storage of everything slab-shaped: the bubbles' slabs, the per-channel right factors, the lane right factors
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 1; i < 3; i++) CK(cudaStreamSynchronize(ctx->lane[i]));
+        const size_t slab = (size_t)(2 * g.nPiF) * NP;
+        for (int i = 0; i < 4; i++) {
+            cudaFree(ctx->PiT[i]); ctx->PiT[i] = nullptr;
+            const size_t n = slab * ctx->n_slabs[i % 2 == 0 ? 0 : 1];
+            if (n) CK(cudaMalloc(&ctx->PiT[i], n * sizeof(C)));
+            ctx->pi_dirty[i] = true;
+        }
+        for (int ch = 0; ch < 3; ch++) {
+            cudaFree(ctx->Rt3[ch]); ctx->Rt3[ch] = nullptr;
+            const size_t n = slab * ctx->n_slabs[ch == FDGA_PCH ? 0 : 1];
+            if (n) CK(cudaMalloc(&ctx->Rt3[ch], n * sizeof(C)));
+        }
+        ctx->lenRtL = (size_t)2 * std::max(g.nPiF, g.nK2f) * NP * std::max(ctx->n_slabs[2], ctx->n_slabs[3]);
+        for (int i = 0; i < 3; i++) {
+            cudaFree(ctx->RtL[i]); ctx->RtL[i] = nullptr;
+            if (ctx->lenRtL) CK(cudaMalloc(&ctx->RtL[i], ctx->lenRtL * sizeof(C)));
+        }
+        ctx->Rt = ctx->RtL[0];
     }
     ctx->slabs_dirty = false;
     invalidate_rt(ctx);
@@ -569,22 +639,18 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     for (int i = 0; i < 5; i++) { CKC(cudaMalloc(&ctx->G[i], ctx->lenG * sizeof(C))); CKC(cudaMemsetAsync(ctx->G[i], 0, ctx->lenG * sizeof(C), ctx->stream)); }
     ctx->lenPi = (size_t)(2 * g.nPiB - 1) * (2 * g.nPiF) * g.NP * g.NP;
     ctx->lenPisw = (size_t)(2 * g.nPiB - 1) * (2 * g.nPiF) * g.NP;
-    for (int i = 0; i < 4; i++) {
-        CKC(cudaMalloc(&ctx->Pi[i], ctx->lenPi * sizeof(C))); CKC(cudaMemsetAsync(ctx->Pi[i], 0, ctx->lenPi * sizeof(C), ctx->stream));
-        CKC(cudaMalloc(&ctx->PiT[i], ctx->lenPi * sizeof(C))); CKC(cudaMalloc(&ctx->Pisw[i], ctx->lenPisw * sizeof(C)));
+    for (int i = 0; i < 4; i++) {      // Pi[i] (full layout) and PiT[i] (compact slabs) are allocated on demand / by ensure_slabs
+        ctx->Pi[i] = nullptr; ctx->PiT[i] = nullptr; ctx->pi_src[i] = PI_NONE; ctx->pi_full_valid[i] = false;
+        CKC(cudaMalloc(&ctx->Pisw[i], ctx->lenPisw * sizeof(C)));
         ctx->pi_dirty[i] = true;
     }
     ctx->lenK3 = ctx->lev[0].len[2];
     for (int i = 0; i < 10; i++) { CKC(cudaMalloc(&ctx->cache[i], ctx->lenK3 * sizeof(C))); CKC(cudaMemsetAsync(ctx->cache[i], 0, ctx->lenK3 * sizeof(C), ctx->stream)); }
     for (int i = 0; i < 2; i++) { CKC(cudaMalloc(&ctx->L[i], ctx->lev[0].len[1] * sizeof(C))); CKC(cudaMemsetAsync(ctx->L[i], 0, ctx->lev[0].len[1] * sizeof(C), ctx->stream)); }
-    CKC(cudaMalloc(&ctx->Rt, ctx->lenPi * sizeof(C)));
-    ctx->RtL[0] = ctx->Rt;
-    {   // lanes 1, 2 only ever hold right factors with W on the K2 mesh (BSE_L_K2!)
-        size_t n = (size_t)2 * std::max(g.nPiF, g.nK2f) * (2 * g.nK2b - 1) * g.NP * g.NP;
-        for (int i = 1; i < 3; i++) CKC(cudaMalloc(&ctx->RtL[i], n * sizeof(C)));
-    }
+    ctx->Rt = nullptr; for (int i = 0; i < 3; i++) ctx->RtL[i] = nullptr;      // right factors: compact, sized by ensure_slabs
+    ctx->lenRtL = 0; ctx->scratchBig = nullptr;
     CKC(cudaMalloc(&ctx->SigR2, ctx->lenG * sizeof(C)));
-    ctx->lenScratch = ctx->lenPi;
+    ctx->lenScratch = std::max(ctx->lev[0].len[1], ctx->lenG);      // ping-pong of the 4-d transforms of the (K2-shaped) L arrays
     CKC(cudaMalloc(&ctx->scratchA, ctx->lenScratch * sizeof(C))); CKC(cudaMalloc(&ctx->scratchB, ctx->lenScratch * sizeof(C)));
     CKC(cudaMalloc(&ctx->GR, ctx->lenG * sizeof(C))); CKC(cudaMalloc(&ctx->GRm, ctx->lenG * sizeof(C)));
     for (int i = 0; i < 2; i++) CKC(cudaMalloc(&ctx->Ghat[i], (size_t)2 * g.nG * g.NP * sizeof(C)));
@@ -611,8 +677,8 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     CKC(cudaMalloc(&ctx->twL, g.L * sizeof(C))); CKC(cudaMalloc(&ctx->twLG, g.LG * sizeof(C)));
     twiddle_kernel<<<nblk(g.L, 64), 64, 0, ctx->stream>>>(ctx->twL, g.L);
     twiddle_kernel<<<nblk(g.LG, 64), 64, 0, ctx->stream>>>(ctx->twLG, g.LG);
-    for (int i = 0; i < 3; i++) { CKC(cudaMalloc(&ctx->Rt3[i], ctx->lenPi * sizeof(C))); ctx->rt_kind[i] = -1; }
-    for (int i = 0; i < 4; i++) { ctx->d_slabs[i] = nullptr; ctx->n_slabs[i] = 0; } ctx->slabs_dirty = true;
+    for (int i = 0; i < 3; i++) { ctx->Rt3[i] = nullptr; ctx->rt_kind[i] = -1; }
+    for (int i = 0; i < 4; i++) { ctx->d_slabs[i] = nullptr; ctx->d_slabmap[i] = nullptr; ctx->n_slabs[i] = 0; } ctx->slabs_dirty = true;
     for (int i = 0; i < 3; i++) {
         CKC(cudaMalloc(&ctx->OwnTabL[i], (size_t)(2 * g.nK2f) * (2 * g.nK2b - 1) * g.NP * sizeof(C))); CKC(cudaMalloc(&ctx->RtotL[i], (size_t)(2 * g.nK2b - 1) * g.NP * sizeof(C)));
         CKC(cudaMalloc(&ctx->TtabL[i], (size_t)(2 * g.nPiF) * (2 * g.nK2f) * (2 * g.nK2b - 1) * sizeof(C)));
@@ -633,11 +699,11 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (int i = 0; i < 5; i++) cudaFree(ctx->G[i]);
     for (int i = 0; i < 4; i++) { cudaFree(ctx->Pi[i]); cudaFree(ctx->PiT[i]); cudaFree(ctx->Pisw[i]); }
     for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
-    cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->Rt); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB);
+    cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB); cudaFree(ctx->scratchBig);
     cudaFree(ctx->Ghat[0]); cudaFree(ctx->Ghat[1]); cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
     cudaFree(ctx->PiMixed[0]); cudaFree(ctx->PiMixed[1]); cudaFree(ctx->itpA); cudaFree(ctx->itpB);
     cudaFree(ctx->kryV); cudaFree(ctx->kryP); cudaFree(ctx->kryW); cudaFree(ctx->kryX); cudaFree(ctx->kryH); cudaFree(ctx->kryPart); cudaFree(ctx->kryTicket); if (ctx->kryHhost) cudaFreeHost(ctx->kryHhost);
-    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); for (int i = 0; i < 3; i++) { cudaFree(ctx->TtabL[i]); cudaFree(ctx->OwnTabL[i]); cudaFree(ctx->RtotL[i]); cudaFree(ctx->ConvTabL[i]); if (i) cudaFree(ctx->RtL[i]); } cudaFree(ctx->SigR2); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) cudaFree(ctx->d_slabs[i]);
+    cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); for (int i = 0; i < 3; i++) { cudaFree(ctx->TtabL[i]); cudaFree(ctx->OwnTabL[i]); cudaFree(ctx->RtotL[i]); cudaFree(ctx->ConvTabL[i]); cudaFree(ctx->RtL[i]); } cudaFree(ctx->SigR2); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) { cudaFree(ctx->d_slabs[i]); cudaFree(ctx->d_slabmap[i]); }
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); for (int k = 0; k < 3; k++) cudaFree(s.d_rep[k]);
         cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); cudaFree(s.d_grp_start); cudaFree(s.d_reps); }
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
@@ -768,7 +834,25 @@ int fdga_get_##NAME(fdga_ctx* ctx, int which, fdga_c64* host, int64_t n) { \
     CK(cudaMemcpyAsync(host, ctx->ARR[which], n * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream)); \
     CK(cudaStreamSynchronize(ctx->stream)); return 0; }
 SETGET(green, G, 5, ctx->lenG, (void)0)
-SETGET(bubble, Pi, 4, ctx->lenPi, (ctx->pi_dirty[which] = true, invalidate_rt(ctx)))
+int fdga_set_bubble(fdga_ctx* ctx, int which, const fdga_c64* host, int64_t n) {
+    CK(cudaSetDevice(ctx->device));
+    if (which < 0 || which >= 4) FAIL("fdga_set_bubble: bad selector");
+    if ((size_t)n != ctx->lenPi) FAIL("fdga_set_bubble: length mismatch");
+    if (!ctx->Pi[which]) CK(cudaMalloc(&ctx->Pi[which], ctx->lenPi * sizeof(C)));
+    CK(cudaMemcpyAsync(ctx->Pi[which], host, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->pi_src[which] = PI_FULL; ctx->pi_full_valid[which] = true; ctx->pi_dirty[which] = true; invalidate_rt(ctx);
+    return 0;
+}
+int fdga_get_bubble(fdga_ctx* ctx, int which, fdga_c64* host, int64_t n) {
+    CK(cudaSetDevice(ctx->device));
+    if (which < 0 || which >= 4) FAIL("fdga_get_bubble: bad selector");
+    if ((size_t)n != ctx->lenPi) FAIL("fdga_get_bubble: length mismatch");
+    if (ensure_pi_full(ctx, which)) return 1;
+    CK(cudaMemcpyAsync(host, ctx->Pi[which], n * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
 SETGET(cache, cache, 10, ctx->lenK3, (void)0)
 int fdga_get_L(fdga_ctx* ctx, int is_pp, fdga_c64* host, int64_t n) {
     CK(cudaSetDevice(ctx->device));
@@ -982,17 +1066,20 @@ int fdga_bubbles_real_space(fdga_ctx* ctx, int reference) {
     const C* Gsrc = ctx->G[reference ? FDGA_G0 : FDGA_G];
     if (dft2_G(ctx, Gsrc, ctx->GR, ctx->SigTmp, -1, 1.0 / ((double)g.LG * g.LG), FDGA_T_BUBBLE)) return 1;
     static const bool legacy = getenv("FDGA_BUBBLES_RS") ? atoi(getenv("FDGA_BUBBLES_RS")) != 0 : false;
-    if (!legacy) {      // product form on the coarse-grained Green function (fdga_kernels.cuh)
+    if (!legacy) {      // product form on the coarse-grained Green function (fdga_kernels.cuh); the slabs are filled lazily (refresh_pi)
         C* Ghat = ctx->Ghat[reference ? 1 : 0];
         LAUNCH(FDGA_T_BUBBLE, coarse_green_kernel, nblk((long long)2 * g.nG * g.NP, 128), 128, ctx->GR, Ghat, g.nG, g.LG, g.L, ctx->twL);
-        LAUNCH(FDGA_T_BUBBLE, bubbles_product_kernel, nblk(ctx->lenPi, 256), 256, Ghat, ctx->Pi[ipp], ctx->Pi[iph], g);
         CK(cudaGetLastError());
+        ctx->pi_src[ipp] = ctx->pi_src[iph] = PI_GHAT; ctx->pi_full_valid[ipp] = ctx->pi_full_valid[iph] = false;
     } else {            // the reference's own route: real-space fill + 4-d back transform (A/B check)
+        for (int w : {ipp, iph}) if (!ctx->Pi[w]) CK(cudaMalloc(&ctx->Pi[w], ctx->lenPi * sizeof(C)));
+        if (!ctx->scratchBig) CK(cudaMalloc(&ctx->scratchBig, ctx->lenPi * sizeof(C)));
         LAUNCH(FDGA_T_BUBBLE, bubbles_rs_kernel, nblk(ctx->lenPi, 128), 128, ctx->GR, ctx->Pi[ipp], ctx->Pi[iph], g);
         CK(cudaGetLastError());
         long long pre = (long long)(2 * g.nPiB - 1) * (2 * g.nPiF);
-        if (dft4(ctx, ctx->Pi[ipp], ctx->scratchA, pre, +1, 1.0, FDGA_T_BUBBLE)) return 1;
-        if (dft4(ctx, ctx->Pi[iph], ctx->scratchA, pre, +1, 1.0, FDGA_T_BUBBLE)) return 1;
+        if (dft4(ctx, ctx->Pi[ipp], ctx->scratchBig, pre, +1, 1.0, FDGA_T_BUBBLE)) return 1;
+        if (dft4(ctx, ctx->Pi[iph], ctx->scratchBig, pre, +1, 1.0, FDGA_T_BUBBLE)) return 1;
+        ctx->pi_src[ipp] = ctx->pi_src[iph] = PI_FULL; ctx->pi_full_valid[ipp] = ctx->pi_full_valid[iph] = true;
     }
     ctx->pi_dirty[ipp] = ctx->pi_dirty[iph] = true;
     invalidate_rt(ctx);
@@ -1003,6 +1090,7 @@ int fdga_bubbles_local(fdga_ctx* ctx, int reference) {
     if (ctx->g.L != 1 || ctx->g.LG != 1) FAIL("fdga_bubbles_local: needs nq = LG = 1");
     Scope sc(ctx, FDGA_T_BUBBLE);
     int ipp = reference ? FDGA_PI0PP : FDGA_PIPP, iph = reference ? FDGA_PI0PH : FDGA_PIPH;
+    for (int w : {ipp, iph}) { if (!ctx->Pi[w]) CK(cudaMalloc(&ctx->Pi[w], ctx->lenPi * sizeof(C))); ctx->pi_src[w] = PI_FULL; ctx->pi_full_valid[w] = true; }
     LAUNCH(FDGA_T_BUBBLE, bubbles_local_kernel, nblk(ctx->lenPi, 128), 128, ctx->G[reference ? FDGA_G0 : FDGA_G], ctx->Pi[ipp], ctx->Pi[iph], ctx->g);
     CK(cudaGetLastError());
     ctx->pi_dirty[ipp] = ctx->pi_dirty[iph] = true;
@@ -1014,6 +1102,7 @@ int fdga_bubbles_momentum_space(fdga_ctx* ctx, int reference) {
     if (ctx->g.LG % ctx->g.L != 0) FAIL("fdga_bubbles_momentum_space: LG must be a multiple of nq");
     Scope sc(ctx, FDGA_T_BUBBLE);
     int ipp = reference ? FDGA_PI0PP : FDGA_PIPP, iph = reference ? FDGA_PI0PH : FDGA_PIPH;
+    for (int w : {ipp, iph}) { if (!ctx->Pi[w]) CK(cudaMalloc(&ctx->Pi[w], ctx->lenPi * sizeof(C))); ctx->pi_src[w] = PI_FULL; ctx->pi_full_valid[w] = true; }
     LAUNCH(FDGA_T_BUBBLE, bubbles_ms_kernel, nblk(ctx->lenPi, 128), 128, ctx->G[reference ? FDGA_G0 : FDGA_G], ctx->Pi[ipp], ctx->Pi[iph], ctx->g);
     CK(cudaGetLastError());
     ctx->pi_dirty[ipp] = ctx->pi_dirty[iph] = true;
@@ -1055,17 +1144,18 @@ static int pi_kind(int ch, bool reference) { return ch == FDGA_PCH ? (reference 
 extern "C++" {
 template <int KIND>
 static int launch_right(fdga_ctx* ctx, int ch, const DevChain& F0, const DevChain& FL, int No, int Ninner, C* Rdst = nullptr) {
-    if (!Rdst) Rdst = ctx->RtL[ctx->cur_lane];
     if (ensure_slabs(ctx)) return 1;
+    if (!Rdst) Rdst = ctx->RtL[ctx->cur_lane];
     Scope sc(ctx, FDGA_T_RIGHT);
     const C* p0 = ctx->PiT[pi_kind(ch, true)]; const C* p1 = ctx->PiT[pi_kind(ch, false)];
     const int kind = (ch == FDGA_PCH ? 0 : 1) + (No == ctx->g.nPiB ? 0 : 2);
     const int nsl = ctx->n_slabs[kind]; const int4* sl = ctx->d_slabs[kind];
     long long n = (long long)(2 * Ninner) * ctx->g.NP * nsl;
     if (n == 0) return 0;
-    if (ch == FDGA_PCH)      LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_P, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl);
-    else if (ch == FDGA_TCH) LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_T, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl);
-    else                     LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_A, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl);
+    const int* pimap = ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1];      // the bubbles live on the bubble-mesh slab list
+    if (ch == FDGA_PCH)      LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_P, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl, pimap);
+    else if (ch == FDGA_TCH) LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_T, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl, pimap);
+    else                     LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_A, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl, pimap);
     CK(cudaGetLastError());
     return 0;
 }
@@ -1128,6 +1218,7 @@ static int launch_column_t(fdga_ctx* ctx, const DevChain& V, ColJob job, SymGrou
     const C* own = nullptr; const C* rtot = nullptr; const C* conv = nullptr;
     const bool pp = (KIND == JOB_SDE_PP) || ((KIND == JOB_K2 || KIND == JOB_K2_MF || KIND == JOB_LK2 || KIND == JOB_LK2_LOC) && CH == CH_P);
     const int kind = (pp ? 0 : 1) + 2;
+    job.slabmap = ctx->d_slabmap[(pp ? 0 : 1) + (job.slabW_N == ctx->g.nPiB ? 0 : 2)];      // slab numbering of R (bubble mesh or K2 mesh)
     if (KIND != JOB_LK2 && KIND != JOB_LK2_LOC) {
         // prologue: momentum-independent levels tabulated per (W, nu, w), then everything that does not depend on the
         // column momentum k reduced per slab (W, P): OwnTab[nu | W, P], Rtot[W, P]
@@ -1161,7 +1252,7 @@ static int launch_column(fdga_ctx* ctx, int ch, const DevChain& V, ColJob job, S
 }  // extern "C++"
 static ColJob make_job(fdga_ctx* ctx, int lev_first, int nw, int Ninner, int slabN, C scale) {
     ColJob j; j.lev_first = lev_first; j.n_nl2 = ctx->n_nl2; j.own_only = ctx->opt_sde_own_gamma; j.k1_direct = ctx->opt_direct_k1; j.nw = nw; j.Ninner = Ninner;
-    j.slabW_N = slabN; j.scale_re = scale.x; j.scale_im = scale.y;
+    j.slabW_N = slabN; j.scale_re = scale.x; j.scale_im = scale.y; j.slabmap = nullptr;
     return j;
 }
 // right factor of channel ch with W on the bubble mesh, cached per channel (K1 and K2 share it: SURVEY App. C.3)
@@ -1260,7 +1351,9 @@ static bool lanes_enabled(fdga_ctx* ctx) {
     if (ctx->profile || ctx->opt_generic || ctx->opt_serial == 1) return false;
     if (ctx->opt_serial == 2) return true;
     static const double lim_mb = getenv("FDGA_LANES_MAX_MB") ? atof(getenv("FDGA_LANES_MAX_MB")) : 160.0;
-    return (double)ctx->lenPi * sizeof(C) <= lim_mb * 1e6;
+    // size of one slab-shaped array as stored (compact: only the slabs this rank reads)
+    const double bytes = ctx->slabs_dirty ? (double)ctx->lenPi * sizeof(C) : (double)(2 * ctx->g.nPiF) * ctx->g.NP * std::max(ctx->n_slabs[0], ctx->n_slabs[1]) * sizeof(C);
+    return bytes <= lim_mb * 1e6;
 }
 // everything the lanes read but do not own must be current before the fork
 static int lanes_fork(fdga_ctx* ctx, unsigned mom_need = MOM_ALL) {
@@ -1295,9 +1388,9 @@ static int bse_K1_impl(fdga_ctx* ctx, int ch, int mfrg, int rk_fd) {
     {
         Scope sc(ctx, FDGA_T_K1);
         if (c1 > c0) {
-            if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_P>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale);
-            else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_T>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale);
-            else                     LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_A>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+            if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_P>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1]);
+            else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_T>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1]);
+            else                     LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_A>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1]);
         }
         CK(cudaGetLastError());
     }
@@ -1325,7 +1418,7 @@ static int bse_new_impl(fdga_ctx* ctx, int ch, int mfrg, int cls) {
         Scope sc(ctx, cat);
         unsigned nb = (unsigned)(c1 - c0);
         if (c1 > c0) {
-#define NEWL(KER, CHT) LAUNCH(cat, KER<CHT>, nb, 256, F, F0, p0, p1, s.d_repvals, sym_dev(s), c0, ctx->g, scaleU, mfrg)
+#define NEWL(KER, CHT) LAUNCH(cat, KER<CHT>, nb, 256, F, F0, p0, p1, s.d_repvals, sym_dev(s), c0, ctx->g, scaleU, mfrg, ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1])
             if (cls == 0) { if (ch == FDGA_PCH) NEWL(bse_k1_new_kernel, CH_P); else if (ch == FDGA_TCH) NEWL(bse_k1_new_kernel, CH_T); else NEWL(bse_k1_new_kernel, CH_A); }
             else          { if (ch == FDGA_PCH) NEWL(bse_k2_new_kernel, CH_P); else if (ch == FDGA_TCH) NEWL(bse_k2_new_kernel, CH_T); else NEWL(bse_k2_new_kernel, CH_A); }
 #undef NEWL
@@ -1361,9 +1454,9 @@ int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
     } else {
         Scope sc(ctx, FDGA_T_L_K2);
         if (c1 > c0) {
-            if (ch == FDGA_PCH)      LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_P>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
-            else if (ch == FDGA_TCH) LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_T>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
-            else                     LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_A>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+            if (ch == FDGA_PCH)      LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_P>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
+            else if (ch == FDGA_TCH) LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_T>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
+            else                     LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_A>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
         }
         CK(cudaGetLastError());
     }
@@ -1399,13 +1492,13 @@ static int bse_K2_impl(fdga_ctx* ctx, int ch, int mfrg, int rk_fd) {
         unsigned nb = (unsigned)(c1 - c0);
         if (c1 > c0) {
             if (mfrg) {
-                if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_P, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
-                else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_T, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
-                else                     LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_A, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+                if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_P, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
+                else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_T, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
+                else                     LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_A, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
             } else {
-                if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_P, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
-                else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_T, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
-                else                     LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_A, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale);
+                if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_P, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
+                else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_T, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
+                else                     LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_A, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
             }
         }
         CK(cudaGetLastError());
@@ -1517,8 +1610,8 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
             {
                 Scope sc(ctx, FDGA_T_SDE_L);
                 if (c1 > c0) {
-                    if (pp) LAUNCH(FDGA_T_SDE_L, sde_L_kernel<true>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma);
-                    else    LAUNCH(FDGA_T_SDE_L, sde_L_kernel<false>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma);
+                    if (pp) LAUNCH(FDGA_T_SDE_L, sde_L_kernel<true>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma, ctx->d_slabmap[0]);
+                    else    LAUNCH(FDGA_T_SDE_L, sde_L_kernel<false>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma, ctx->d_slabmap[1]);
                 }
                 CK(cudaGetLastError());
             }
@@ -2031,9 +2124,11 @@ int fdga_mix_bubbles(fdga_ctx* ctx, double mixing) {
     for (int i = 0; i < 2; i++) if (!ctx->PiMixed[i]) CK(cudaMalloc(&ctx->PiMixed[i], ctx->lenPi * sizeof(C)));
     Scope sc(ctx, FDGA_T_MISC);
     const int pi[2] = {FDGA_PIPP, FDGA_PIPH}, pi0[2] = {FDGA_PI0PP, FDGA_PI0PH};
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 2; i++) {      // the mixed bubbles are not products of Green functions: they live in the full layout
+        if (ensure_pi_full(ctx, pi[i]) || ensure_pi_full(ctx, pi0[i])) return 1;
         LAUNCH(FDGA_T_MISC, axpby_kernel, nblk(ctx->lenPi, 256), 256, ctx->PiMixed[i], (const C*)ctx->Pi[pi[i]], mixing, (const C*)ctx->Pi[pi0[i]], 1.0 - mixing, (long long)ctx->lenPi);
         CK(cudaMemcpyAsync(ctx->Pi[pi[i]], ctx->PiMixed[i], ctx->lenPi * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->pi_src[pi[i]] = PI_FULL; ctx->pi_full_valid[pi[i]] = true;
         ctx->pi_dirty[pi[i]] = true;
     }
     CK(cudaGetLastError());
@@ -2051,7 +2146,9 @@ int fdga_update_reference(fdga_ctx* ctx) {
     Scope sc(ctx, FDGA_T_MISC);
     const int pi0[2] = {FDGA_PI0PP, FDGA_PI0PH};
     for (int i = 0; i < 2; i++) {
+        if (!ctx->Pi[pi0[i]]) CK(cudaMalloc(&ctx->Pi[pi0[i]], ctx->lenPi * sizeof(C)));
         CK(cudaMemcpyAsync(ctx->Pi[pi0[i]], ctx->PiMixed[i], ctx->lenPi * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->pi_src[pi0[i]] = PI_FULL; ctx->pi_full_valid[pi0[i]] = true;
         ctx->pi_dirty[pi0[i]] = true;
     }
     CK(cudaMemcpyAsync(ctx->G[FDGA_G0], ctx->G[FDGA_G], ctx->lenG * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));

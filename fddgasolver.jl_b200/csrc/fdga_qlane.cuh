@@ -216,7 +216,7 @@ FDGA_HD C qlane_rep(const DevChain& V, const ColJob& job, const Grid& g, const C
     typedef Forms<KIND, CH> FM;
     const int L = g.L, NP = g.NP, nw = job.nw, Nin = job.Ninner;
     const int W = iW - (g.nK2b - 1), nu = inu - g.nK2f;
-    const C* __restrict__ Rs = R + (size_t)nw * NP * (posB(W, job.slabW_N) + (size_t)(2 * job.slabW_N - 1) * iP);
+    const C* __restrict__ Rs = R + (size_t)nw * NP * slab_index(job.slabmap, posB(W, job.slabW_N), 2 * job.slabW_N - 1, iP);
     const int l0 = job.lev_first, l_end = qlane_level_end<KIND>(job);
     C acc = zeroC();
     for (int q0 = lane; q0 < NP || SYNC; q0 += 64) {       // SYNC: every lane runs the loop (warp-wide barriers inside), idle lanes masked

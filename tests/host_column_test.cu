@@ -120,7 +120,7 @@ static double run_job(const DevChain& V, const Grid& g, int lev_first, int own_o
     const bool is_sde = (KIND == JOB_SDE_PP || KIND == JOB_SDE_PH);
     const int slabN = is_sde ? g.nPiB : g.nK2b, nBs = 2 * slabN - 1;     // (the K2 jobs are tested with W on the K2 mesh)
     ColJob job; job.lev_first = lev_first; job.n_nl2 = 0; while (job.n_nl2 < V.nlev && V.lev[job.n_nl2].type == LV_NL2) job.n_nl2++;
-    job.own_only = own_only; job.nw = nw; job.Ninner = Nin; job.slabW_N = slabN; job.scale_re = 1.0; job.scale_im = 0.0; job.k1_direct = 0;
+    job.own_only = own_only; job.nw = nw; job.Ninner = Nin; job.slabW_N = slabN; job.scale_re = 1.0; job.scale_im = 0.0; job.k1_direct = 0; job.slabmap = nullptr;
     const C* R = rnd_array((size_t)nw * NP * nBs * NP);
 #ifdef DEVICE_CHECK
     C* Tm; cudaMallocManaged(&Tm, (size_t)nw * nF2 * nB2 * sizeof(C));

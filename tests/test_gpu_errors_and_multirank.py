@@ -25,7 +25,7 @@ def test_error_paths_return_status_and_message(orc):
         lambda: S._call("fdga_set_vertex", 0, 0, 1, L.ptr(z), 4),                # length mismatch
         lambda: S._call("fdga_set_vertex", 55, 0, 0, L.ptr(z), 4),               # bad vertex selector
         lambda: S._call("fdga_set_bubble", 9, L.ptr(z), 4),                      # bad bubble selector
-        lambda: S._call("fdga_iterate_solver", 17, 0),                           # unknown strategy
+        lambda: S._call("fdga_iterate_solver", 17, 0, 1),                           # unknown strategy
         lambda: S._call("fdga_set_option", 99, 1),                               # unknown option
         lambda: S._call("fdga_interpolate_green", 9, L.ptr(z), 1, 1, 0),         # bad selector
         lambda: S._call("fdga_update_reference"),                                # before fdga_mix_bubbles
