@@ -151,7 +151,7 @@ def run_reference(a):
               f"{a.steps} requested, capped by a {budget:.0f} s budget")
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": len(ts), "steps_requested": a.steps,
            "warmup": 1 if a.warmup > 0 else 0, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "f64 (complex)", "data": "synthetic",
+           "dtype": "f64 (complex)", "data": inp["data"],
            "config": {"workload": workload_name(a), "timing": "host wall clock of complete iterations of the CPU restatement (oracle/) of the reference algorithm; Julia + MatsubaraFunctions.jl are not installed"},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -337,7 +337,7 @@ def run_ours(a):
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W, "ms_per_step": ms / a.steps,
-               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex)", "data": "synthetic",
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex)", "data": inp["data"],
                "config": {"workload": workload_name(a), "l2": "inputs larger than L2: 4 bubbles x %.0f MB + hoisted right factor %.0f MB per channel are streamed every step" % (S.length_F() * 0 + 16e-6 * np.prod(S._shpΠ), 16e-6 * np.prod(S._shpΠ)),
                           "symmetry_classes": {"K1": S.num_classes(fd._lib.SG_K1), "K2pp": n2cls[0], "K2ph": n2cls[1], "K3pp": S.num_classes(fd._lib.SG_PP3), "K3ph": S.num_classes(fd._lib.SG_PH3)},
                           "parallelism": f"class representatives sharded over {world} rank(s), NCCL all-gather per kernel" if world > 1 else "1 GPU"},

@@ -13,6 +13,8 @@ from .solver import (NL2_ParquetSolver, ParquetSolver, init_sym_grp, Dyson, comp
                      BSE_K2, BSE_K3, BSE_K1_new, BSE_K2_new, BSE_K1_1loop, BSE_K2_1loop, BSE_K3_1loop, SDE, SDE_channel_L, iterate_solver, iterate_solver_stepwise, fixed_point, solve, mfRGLinearMap,
                      dqgmres, symmetrize_solver, fixed_point_preconditioned,
                      set_hubbard_bare_Green, compute_hubbard_chemical_potential, mix_bubbles, update_reference, solve_using_mfRG,
-                     interpolate_vertex, interpolate_solver)
+                     interpolate_vertex, interpolate_solver, save_solver, load_solver)
+from . import h5min, io, synthetic, types  # noqa: F401,E402
+from .io import load_triqs_data  # noqa: F401,E402
 from .synthetic import (parquet_solver_hubbard_parquet_approximation_NL2, parquet_solver_siam_parquet_approximation, synthetic_local_vertex,  # noqa: F401
                         wu_point_solver, wu_point_inputs, randomize_vertex)

@@ -572,15 +572,46 @@ def update_reference(S):
     S._call("fdga_update_reference")
 
 
+def save_solver(S, filename, extra=None):
+    """save!(f, "S", S): src/ParquetSolver.jl:309-330 (HDF5 in the reference's MeshFunction layout, fddgasolver.jl_b200/io.py)"""
+    from . import io
+    S.pull("Gbare", "G0", "Σ0", "G", "Σ", "F", "F0", "Π")
+    io.save_solver(filename, S, extra=extra)
+
+
+def load_solver(S, filename):
+    """load_solver!(S, filename): src/nonlocal/ParquetSolver.jl:332-346"""
+    from . import io
+    for n in ("Π0pp", "Π0ph", "Πpp", "Πph"):
+        if getattr(S, n) is None:
+            setattr(S, n, zeros(S._shpΠ))
+    io.load_solver(S, filename)
+    S.push("Gbare", "G0", "Σ0", "G", "Σ", "F0", "F", "Π0pp", "Π0ph", "Πpp", "Πph")
+
+
 def solve_using_mfRG(S, *, maxiter=100, verbose=False, occ_target=None, hubbard_params=None, mixing_init=1.0, tol=1e-4,
-                     strategy="fdPA", anderson_iterations=40, anderson_m=50, krylov_maxiter=400, memory=100, debug_single_iter=False):
-    """solve_using_mfRG!(S; maxiter, occ_target, hubbard_params, mixing_init, tol, strategy): src/mfRG.jl:217-372 (adaptive mixing of
-    the target bubble, vertex solve by Anderson iteration of the DQGMRES-preconditioned fixed point, SDE, reference update).
-    Everything between two vertex solves stays on the device; checkpoint files / restart are not mirrored.  Returns a dict with the
-    history (mixing, Σ error, μ per accepted iteration)."""
+                     strategy="fdPA", anderson_iterations=40, anderson_m=50, krylov_maxiter=400, memory=100, debug_single_iter=False,
+                     filename_log=None, iter_restart=0, auto_restart=False):
+    """solve_using_mfRG!(S; maxiter, occ_target, hubbard_params, mixing_init, tol, strategy, filename_log, iter_restart,
+    auto_restart): src/mfRG.jl:217-372 (adaptive mixing of the target bubble, vertex solve by Anderson iteration of the
+    DQGMRES-preconditioned fixed point, SDE, reference update).  Everything between two vertex solves stays on the device.
+    filename_log: after every accepted iteration the solver and the scalar `mixing` are written to `$filename_log.iter$i.h5`
+    (:363-370); iter_restart / auto_restart resume from such a file (:240-275).  Returns a dict with the history (mixing, Σ error,
+    μ per accepted iteration)."""
     from .nlsolve import anderson
     mixing, it = float(mixing_init), 0
-    hist = {"mixing": [], "Σ_err": [], "μ": [], "anderson_iterations": [], "converged": False}
+    if auto_restart and filename_log is not None:
+        from . import io
+        _, last = io.last_checkpoint(filename_log, 100)
+        if last:
+            iter_restart = last
+    if iter_restart:
+        from . import h5min
+        fn = f"{filename_log}.iter{iter_restart}.h5"
+        load_solver(S, fn)
+        mixing = float(h5min.File(fn)["mixing"].read())
+        it = int(iter_restart)
+    hist = {"mixing": [], "Σ_err": [], "μ": [], "anderson_iterations": [], "converged": False, "iterations": it}
     for _ in range(maxiter):
         it += 1
         mix_bubbles(S, mixing)                                                   # :271-276
@@ -617,6 +648,9 @@ def solve_using_mfRG(S, *, maxiter=100, verbose=False, occ_target=None, hubbard_
         bubbles(S)
         hist["mixing"].append(used)
         hist["Σ_err"].append(Σ_err)
+        hist["iterations"] = it
+        if filename_log is not None:                                             # :363-370
+            save_solver(S, f"{filename_log}.iter{it}.h5", extra={"mixing": mixing})
         if Σ_err < tol:                                                          # :377-379
             hist["converged"] = True
             break

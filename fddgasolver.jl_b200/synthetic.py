@@ -4,6 +4,8 @@ There is no HDF5 reader in this environment, so the DMFT input files of the refe
 replaced by synthetic vertices of the same grid sizes: K1 N=128, K2 N=(64,48), dummy K3 N=(1,1),
 core box N=(24,16) (sizes decoded from data/Wu_point*.h5).
 """
+import os
+
 import numpy as np
 
 from .models import hubbard_bare_Green, siam_bare_Green
@@ -82,7 +84,24 @@ def synthetic_local_sigma(T, nG, U, n=0.48, seed=3):
     return 1j * sig
 
 
-def wu_point_inputs(nmax=4, nq=8, LG=48, *, seed=1, F_scale=1e-2, F0_scale=0.0, small_reference=False):
+DMFT_FIXTURE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "wu_point_dmft.npz")
+
+
+def load_dmft_fixture(path=DMFT_FIXTURE):
+    """The reference's packaged DMFT data of the Wu point (data/Wu_point.h5 as load_triqs_data returns it, src/utility/
+    load_triqs.jl:298-308), from the fixture written by tests/golden/make_wu_point_fixture.py: dict G, G0, Σ (i G, i Σ on the
+    fermionic mesh of size nG), Γ (local Vertex with its RefVertex core), occ, params, T."""
+    z = np.load(path)
+    T, U = float(z["T"]), complex(z["U"])
+    core = RefVertex(T, U, tuple(int(x) for x in z["core_N"]), z["Fp_p"], z["Fp_x"], z["Ft_p"], z["Ft_x"])
+    Γ = Vertex(core, T, int(z["numK1"]), tuple(int(x) for x in z["numK2"]), tuple(int(x) for x in z["numK3"]))
+    for ch, g in zip("pta", Γ.channels()):
+        g.K1[...], g.K2[...], g.K3[...] = z[f"K1_{ch}"], z[f"K2_{ch}"], z[f"K3_{ch}"]
+    return {"G": z["G"], "G0": z["G0"], "Σ": z["Sigma"], "nG": int(z["nG"]), "T": T, "Γ": Γ, "occ": float(z["occ"]),
+            "params": dict(zip([str(k) for k in z["param_names"]], [float(v) for v in z["param_values"]])), "source": str(z["source"])}
+
+
+def wu_point_inputs(nmax=4, nq=8, LG=48, *, seed=1, F_scale=1e-2, F0_scale=0.0, small_reference=False, data="auto"):
     """Pure-numpy inputs of the Wu-point NL2 problem (no device needed): dict with the constructor arguments
     of NL2_ParquetSolver plus the seeded start vertex `F` (an NL2_Vertex whose F0 is the reference vertex).
 
@@ -97,26 +116,37 @@ def wu_point_inputs(nmax=4, nq=8, LG=48, *, seed=1, F_scale=1e-2, F0_scale=0.0, 
     nG = nK1 = 4 * nmax
     nK2 = nK3 = (nmax, nmax)
     Gbare = hubbard_bare_Green(T, nG, LG, μ=μ, t1=t1, t2=t2)
-    Σloc = synthetic_local_sigma(T, nG, U)
-    Σ0 = np.asfortranarray(np.repeat(Σloc[:, None], LG * LG, axis=1))
-    Glat = 1.0 / (1.0 / Gbare + Σ0)
-    G0 = np.asfortranarray(np.repeat(Glat.mean(axis=1)[:, None], LG * LG, axis=1))   # impurity G = local lattice G
-    if small_reference:
-        Γ = synthetic_local_vertex(T, U, numK1=2 * nK1, numK2=(2 * nmax, 2 * nmax), numK3=(1, 1), core=(nmax + 1, nmax), seed=2)
+    use_ref = (data == "reference") or (data == "auto" and not small_reference and os.path.exists(DMFT_FIXTURE))
+    if use_ref:
+        d = load_dmft_fixture()
+        assert abs(d["T"] - T) < 1e-12 and nG <= d["nG"], "the packaged data is on the T = 0.2 mesh with N = 128"
+        sl = slice(d["nG"] - nG, d["nG"] + nG)             # same temperature: the mesh points coincide, data_triqs.G(value(ν)) is exact
+        G0 = np.asfortranarray(np.repeat(d["G"][sl][:, None], LG * LG, axis=1))
+        Σ0 = np.asfortranarray(np.repeat(d["Σ"][sl][:, None], LG * LG, axis=1))
+        Γ = d["Γ"]
     else:
-        Γ = synthetic_local_vertex(T, U, seed=2)
+        Σloc = synthetic_local_sigma(T, nG, U)
+        Σ0 = np.asfortranarray(np.repeat(Σloc[:, None], LG * LG, axis=1))
+        Glat = 1.0 / (1.0 / Gbare + Σ0)
+        G0 = np.asfortranarray(np.repeat(Glat.mean(axis=1)[:, None], LG * LG, axis=1))   # impurity G = local lattice G
+        if small_reference:
+            Γ = synthetic_local_vertex(T, U, numK1=2 * nK1, numK2=(2 * nmax, 2 * nmax), numK3=(1, 1), core=(nmax + 1, nmax), seed=2)
+        else:
+            Γ = synthetic_local_vertex(T, U, seed=2)
     F0 = NL2_Vertex(Γ, T, nK1, nK2, nK3, nq)
     if F0_scale:
         randomize_vertex(F0, seed + 7, scale=F0_scale)
     F = NL2_Vertex(F0, T, nK1, nK2, nK3, nq)
     randomize_vertex(F, seed, scale=F_scale)
-    return dict(T=T, U=U, nK1=nK1, nK2=nK2, nK3=nK3, L=nq, Gbare=Gbare, G0=G0, Σ0=Σ0, F0=F0, F=F)
+    return dict(T=T, U=U, nK1=nK1, nK2=nK2, nK3=nK3, L=nq, Gbare=Gbare, G0=G0, Σ0=Σ0, F0=F0, F=F,
+                data=("reference file data/Wu_point.h5 (local DMFT vertex, impurity G and Σ, via tests/golden/wu_point_dmft.npz) + seeded nonlocal start vertex"
+                      if use_ref else "synthetic"))
 
 
 def wu_point_solver(nmax=4, nq=8, LG=48, *, seed=1, device=0, init_sym=True, F_scale=1e-2, F0_scale=0.0,
-                    small_reference=False):
+                    small_reference=False, data="auto"):
     """NL2_ParquetSolver on the GPU for wu_point_inputs(...) (see there)."""
-    inp = wu_point_inputs(nmax, nq, LG, seed=seed, F_scale=F_scale, F0_scale=F0_scale, small_reference=small_reference)
+    inp = wu_point_inputs(nmax, nq, LG, seed=seed, F_scale=F_scale, F0_scale=F0_scale, small_reference=small_reference, data=data)
     S = NL2_ParquetSolver(inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"],
                           T=inp["T"], device=device)
     S.F.set(inp["F"])

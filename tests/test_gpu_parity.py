@@ -496,3 +496,35 @@ def test_sde_rejects_unknown_strategy_before_touching_sigma(orc):
     S.pull("Σ")
     assert np.array_equal(S.Σ, before)
     S.close()
+
+
+def test_solver_checkpoint_round_trip_on_device(orc, tmp_path):
+    """save!(f, "S", S) / load_solver!(S, filename) through the pure-Python HDF5 layer: a solver restored from its checkpoint
+    continues bit-identically; solve_using_mfRG writes `$log.iter$i.h5` + `mixing` and resumes from it (src/mfRG.jl:240-275, 363-370)"""
+    import fddgasolver_jl_b200 as fd
+    S, _ = make_pair(orc, nmax=2, nq=3, LG=6)
+    fd.iterate_solver(S, "fdPA", True)
+    p = str(tmp_path / "ckpt.h5")
+    fd.save_solver(S, p, extra={"mixing": 0.25})
+    f = fd.h5min.File(p)
+    assert f["mixing"].read() == 0.25 and f["F/γa/K2"].attrs["type"] == "MeshFunction"
+    S2, _ = make_pair(orc, nmax=2, nq=3, LG=6, seed=99)      # different start state
+    fd.load_solver(S2, p)
+    for s in (S, S2):
+        fd.iterate_solver(s, "fdPA", True)
+        s.pull("F", "Σ", "G")
+    assert np.array_equal(S.F.flatten(), S2.F.flatten()) and np.array_equal(S.Σ, S2.Σ) and np.array_equal(S.G, S2.G)
+    S.close(); S2.close()
+    # outer loop with log files, then a restart that picks the last one up
+    hp = {"t1": 1.0, "t2": -0.3}
+    log = str(tmp_path / "run")
+    A, _ = make_pair(orc, nmax=2, nq=3, LG=6)
+    ha = fd.solve_using_mfRG(A, maxiter=2, hubbard_params=hp, mixing_init=0.5, tol=1e-12, filename_log=log, anderson_iterations=4, krylov_maxiter=5, memory=5)
+    path, last = fd.io.last_checkpoint(log)
+    assert last == ha["iterations"] >= 1 and path is not None
+    B, _ = make_pair(orc, nmax=2, nq=3, LG=6, seed=5)
+    hb = fd.solve_using_mfRG(B, maxiter=0, hubbard_params=hp, tol=1e-12, filename_log=log, auto_restart=True)
+    assert hb["iterations"] == last
+    A.pull("F", "Σ", "F0"); B.pull("F", "Σ", "F0")
+    assert np.array_equal(A.Σ, B.Σ) and np.array_equal(A.F0.flatten(), B.F0.flatten())
+    A.close(); B.close()
