@@ -16,5 +16,6 @@ from .solver import (NL2_ParquetSolver, ParquetSolver, init_sym_grp, Dyson, comp
                      interpolate_vertex, interpolate_solver, save_solver, load_solver)
 from . import h5min, io, synthetic, types  # noqa: F401,E402
 from .io import load_triqs_data  # noqa: F401,E402
+from .flow import bare_Green_Ω_flow  # noqa: F401,E402
 from .synthetic import (parquet_solver_hubbard_parquet_approximation_NL2, parquet_solver_siam_parquet_approximation, synthetic_local_vertex,  # noqa: F401
                         wu_point_solver, wu_point_inputs, randomize_vertex)
