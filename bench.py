@@ -38,6 +38,7 @@ def parse():
     p.add_argument("--nq", type=int, default=8)
     p.add_argument("--LG", type=int, default=48)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-extras", action="store_true", help="skip the mfRG matvec / DQGMRES side measurements (large sweep sizes)")
     return p.parse_args()
 
 
@@ -291,25 +292,28 @@ def run_ours(a):
 
     # second hot entry of the reference: the mfRG linear map y = A x (src/mfRG.jl:34-89, script/benchmark_Wu.jl:60-64),
     # host vectors in and out exactly as Krylov.dqgmres calls it
-    A = fd.mfRGLinearMap(S)
-    xm = x_np                                            # pinned host vectors in and out (x_host / y_host above)
-    A.matvec(xm, out=y_np); A.matvec(xm, out=y_np)
-    barrier()
-    t0 = time.perf_counter()
-    nmv = max(3, min(a.steps, 50))
-    for _ in range(nmv):
-        A.matvec(xm, out=y_np)
-    barrier()
-    mfrg_per_s = nmv / (time.perf_counter() - t0)
-    # the same operator inside the device-resident DQGMRES (Krylov.dqgmres(...; memory = 100) of src/mfRG.jl:147-151): one Krylov
-    # iteration = one matvec + the incomplete orthogonalisation and direction update, all vectors in HBM
-    nk = 30
-    fd.dqgmres(A, xm, memory=100, atol=0.0, rtol=0.0, itmax=2)
-    barrier()
-    t0 = time.perf_counter()
-    _, kst = fd.dqgmres(A, xm, memory=100, atol=0.0, rtol=0.0, itmax=nk)
-    barrier()
-    krylov_per_s = kst["niter"] / (time.perf_counter() - t0)
+    mfrg_per_s = krylov_per_s = None
+    if not a.no_extras:
+        A = fd.mfRGLinearMap(S)
+        xm = x_np                                            # pinned host vectors in and out (x_host / y_host above)
+        A.matvec(xm, out=y_np); A.matvec(xm, out=y_np)
+        barrier()
+        t0 = time.perf_counter()
+        nmv = max(3, min(a.steps, 50))
+        for _ in range(nmv):
+            A.matvec(xm, out=y_np)
+        barrier()
+        mfrg_per_s = nmv / (time.perf_counter() - t0)
+        # the same operator inside the device-resident DQGMRES (Krylov.dqgmres(...; memory = 100) of src/mfRG.jl:147-151): one Krylov
+        # iteration = one matvec + the incomplete orthogonalisation and direction update, all vectors in HBM
+        nk = 30
+        kmem = int(max(2, min(100, 8e9 // (2 * nF * 16))))    # the rings of basis / direction vectors stay under 8 GB
+        fd.dqgmres(A, xm, memory=kmem, atol=0.0, rtol=0.0, itmax=2)
+        barrier()
+        t0 = time.perf_counter()
+        _, kst = fd.dqgmres(A, xm, memory=kmem, atol=0.0, rtol=0.0, itmax=nk)
+        barrier()
+        krylov_per_s = kst["niter"] / (time.perf_counter() - t0)
 
     # state fingerprint after one more iteration from the stashed vertex: identical on every rank and for every N
     import hashlib
@@ -322,6 +326,14 @@ def run_ours(a):
         dist.all_gather_object(objs, digest)
         if rank == 0 and len(set(objs)) != 1:
             raise SystemExit(f"bench.py: ranks disagree on the iterated state: {objs}")
+
+    # device memory in use on every rank (the slab-shaped arrays are sharded: each rank holds only the (W, P) slabs it reads)
+    free_b, total_b = torch.cuda.mem_get_info()
+    mem_gb = round((total_b - free_b) / 1e9, 3)
+    mem_all = [mem_gb]
+    if dist is not None:
+        mem_all = [None] * world
+        dist.all_gather_object(mem_all, mem_gb)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -342,7 +354,7 @@ def run_ours(a):
                           "symmetry_classes": {"K1": S.num_classes(fd._lib.SG_K1), "K2pp": n2cls[0], "K2ph": n2cls[1], "K3pp": S.num_classes(fd._lib.SG_PP3), "K3ph": S.num_classes(fd._lib.SG_PH3)},
                           "parallelism": f"class representatives sharded over {world} rank(s), NCCL all-gather per kernel" if world > 1 else "1 GPU"},
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(nF * 16), "d2h_bytes_per_step": int(nF * 16 + S.Σ.size * 16), "ms_per_step": ms_e2e / a.steps},
-               "gpu_launches": int(launches), "mfrg_matvecs_per_sec_e2e": mfrg_per_s, "mfrg_dqgmres_iterations_per_sec_device_resident": krylov_per_s, "state_sha1": digest, "state_checksum": checksum, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
+               "gpu_launches": int(launches), "mfrg_matvecs_per_sec_e2e": mfrg_per_s, "mfrg_dqgmres_iterations_per_sec_device_resident": krylov_per_s, "state_sha1": digest, "state_checksum": checksum, "device_memory_gb_per_rank": mem_all, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
         print(json.dumps(out))
     S.close()
     if dist is not None:

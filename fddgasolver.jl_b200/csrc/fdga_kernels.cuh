@@ -90,6 +90,38 @@ __global__ void expand_add_kernel(C* __restrict__ out, const C* __restrict__ rep
     if (j >= sg.nmem) return;
     out[sg.index[j]] += apply_op(sg.ops[j], repvals[sg.member_class[j]]) * w;
 }
+// ---- batched SG finish of one BSE stage -----------------------------------------------------------------------------------
+// All post-processing that follows the SG(...) fills of a stage (BSE_templates.jl:35-38, 72-73, 107-108, 142-143, 176-177;
+// BSEa_K2.jl:128-135) is linear and commutes with the class expansion (every array involved is symmetric under the SAME group
+// with the same operations), so it is applied to the class REPRESENTATIVES -- a few thousand numbers instead of the full arrays:
+//     a, p :  rep_r += FL_r[index of the representative]                 (K2 only: the FL add)
+//     t    :  rep_t <- ( rep_t + [2 FL_t - FL_a][rep index] + rep_a ) / 2  (spin d -> p with the FINAL a-channel value)
+// One launch handles every kernel class of the stage (blockIdx.y); then ONE launch expands all arrays (expand_multi_kernel).
+struct RepFixJob { C* rep[3]; const C* fl[3]; const long long* offsets[3]; const long long* index[3]; long long ncls[3]; };
+#define FDGA_MAXFIX 4
+struct RepFixJobs { RepFixJob j[FDGA_MAXFIX]; };
+__global__ void repfix_kernel(const __grid_constant__ RepFixJobs jobs) {
+    const RepFixJob& J = jobs.j[blockIdx.y];
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c < J.ncls[CH_P] && J.fl[CH_P])                              // the p channel lives in its own (pp) group
+        J.rep[CH_P][c] += J.fl[CH_P][J.index[CH_P][J.offsets[CH_P][c]]];
+    if (c >= J.ncls[CH_A]) return;                                   // a and t share the ph group
+    const long long idx = J.fl[CH_A] ? J.index[CH_A][J.offsets[CH_A][c]] : 0;
+    C a = J.rep[CH_A][c];
+    if (J.fl[CH_A]) { a += J.fl[CH_A][idx]; J.rep[CH_A][c] = a; }
+    C t = J.rep[CH_T][c];
+    if (J.fl[CH_T]) t += J.fl[CH_T][idx] * 2.0 - J.fl[CH_A][idx];
+    J.rep[CH_T][c] = (t + a) * 0.5;
+}
+struct ExpandJob { C* out; const C* rep; SymDev sg; };
+#define FDGA_MAXEXP 12
+struct ExpandJobs { ExpandJob j[FDGA_MAXEXP]; };
+__global__ void expand_multi_kernel(const __grid_constant__ ExpandJobs jobs) {
+    const ExpandJob& J = jobs.j[blockIdx.y];
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < J.sg.nmem; m += (long long)gridDim.x * blockDim.x)
+        J.out[J.sg.index[m]] = apply_op(J.sg.ops[m], J.rep[J.sg.member_class[m]]);
+}
+
 // SG(f): symmetrise in place from the representatives
 __global__ void symmetrize_kernel(C* __restrict__ f, SymDev sg) {
     long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;

@@ -1298,20 +1298,16 @@ static int post_fix(fdga_ctx* ctx, int kind, int ch) {
     return 0;
 }
 static int finish_or_defer(fdga_ctx* ctx, SymGroup& s, C* out, int kind, int ch) {
-    if (ctx->defer) {
+    if (ctx->defer) {       // fused stage: everything is finished together by flush_pending
         Pending p; p.s = &s; p.rep = s.d_repvals; p.out = out; p.kind = kind; p.ch = ch; p.expanded = false;
-        if (ctx->nranks == 1) {     // nothing to gather: expand right away on this lane, only the post-fix waits for the join
-            Scope sc(ctx, FDGA_T_EXPAND);
-            LAUNCH(FDGA_T_EXPAND, expand_kernel, nblk(s.nmem, 256), 256, out, s.d_repvals, sym_dev(s));
-            CK(cudaGetLastError());
-            p.expanded = true;
-        }
         ctx->pending.push_back(p); return 0;
     }
     if (sg_finish(ctx, s, out)) return 1;
     return post_fix(ctx, kind, ch);
 }
-// one NCCL group for all deferred all-gathers of a stage, then the expansions and post-fixes in call order
+// one NCCL group for all deferred all-gathers of a stage; then, when every kernel class of the stage has its three channels
+// pending (the fused drivers), ONE launch applies the post-fixes to the representatives and ONE launch expands all arrays;
+// otherwise the expansions and post-fixes run one by one in call order
 static int flush_pending(fdga_ctx* ctx) {
     if (ctx->pending.empty()) return 0;
     if (ctx->nranks > 1) {
@@ -1330,8 +1326,45 @@ static int flush_pending(fdga_ctx* ctx) {
     std::stable_sort(todo.begin(), todo.end(), [](const Pending& a, const Pending& b) {
         auto rank = [](int ch) { return ch == FDGA_PCH ? 0 : (ch == FDGA_ACH ? 1 : 2); };
         return a.kind != b.kind ? a.kind < b.kind : rank(a.ch) < rank(b.ch); });
+    // batched form: groups of three consecutive entries (p, a, t) of one kind
+    bool batched = todo.size() % 3 == 0 && todo.size() / 3 <= FDGA_MAXFIX && todo.size() <= FDGA_MAXEXP;
+    for (size_t i = 0; batched && i < todo.size(); i += 3)
+        batched = todo[i].kind == todo[i + 1].kind && todo[i].kind == todo[i + 2].kind &&
+                  todo[i].ch == FDGA_PCH && todo[i + 1].ch == FDGA_ACH && todo[i + 2].ch == FDGA_TCH && todo[i + 1].s == todo[i + 2].s;
+    if (batched) {
+        RepFixJobs fj; ExpandJobs ej; memset(&fj, 0, sizeof(fj)); memset(&ej, 0, sizeof(ej));
+        long long maxcls = 0, maxmem = 0;
+        const int nk = (int)todo.size() / 3;
+        for (int k = 0; k < nk; k++) {
+            RepFixJob& J = fj.j[k];
+            const int order[3] = {FDGA_PCH, FDGA_ACH, FDGA_TCH};
+            for (int i = 0; i < 3; i++) {
+                const Pending& p = todo[3 * k + i];
+                const int ch = order[i];
+                J.rep[ch] = p.rep; J.offsets[ch] = p.s->d_offsets; J.index[ch] = p.s->d_index; J.ncls[ch] = p.s->ncls;
+                J.fl[ch] = (p.kind == PK_K2) ? ctx->FL.K[ch][1] : nullptr;
+                ej.j[3 * k + i].out = p.out; ej.j[3 * k + i].rep = p.rep; ej.j[3 * k + i].sg = sym_dev(*p.s);
+                maxmem = std::max(maxmem, p.s->nmem);
+                maxcls = std::max(maxcls, p.s->ncls);
+            }
+        }
+        if (batched) {
+            {
+                Scope sc(ctx, FDGA_T_MISC);
+                LAUNCH(FDGA_T_MISC, repfix_kernel, dim3(nblk(maxcls, 128), nk), 128, fj);
+            }
+            {
+                Scope sc(ctx, FDGA_T_EXPAND);
+                const unsigned nbx = (unsigned)std::min<long long>(nblk(maxmem, 256), 2048);
+                LAUNCH(FDGA_T_EXPAND, expand_multi_kernel, dim3(nbx, (unsigned)todo.size()), 256, ej);
+            }
+            CK(cudaGetLastError());
+            for (auto& p : todo) if (p.kind == PK_LK2 || p.kind == PK_LK3) { ctx->FL.sw_dirty = true; invalidate_rt(ctx); }
+            return 0;
+        }
+    }
     for (auto& p : todo) {
-        if (!p.expanded) {
+        {
             Scope sc(ctx, FDGA_T_EXPAND);
             LAUNCH(FDGA_T_EXPAND, expand_kernel, nblk(p.s->nmem, 256), 256, p.out, p.rep, sym_dev(*p.s));
             CK(cudaGetLastError());
