@@ -530,7 +530,7 @@ __global__ void k1_dft_kernel(DevLevel lv, int L, int NP, const C* __restrict__ 
 struct ConvPieceS { int W0, dW0, sW, cx, cy, sk, sq, lev, r, nK1; double cf; };
 #define FDGA_CONV_MAXP 24     // 2 forms x 6 levels x 2 cross channels
 template <int KIND, int CH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 slab_conv_kernel(const __grid_constant__ DevChain V, ColJob job, const int4* __restrict__ slabs, const C* __restrict__ R,
                  const C* __restrict__ tw, C* __restrict__ ConvTab, Grid g, int TW, int use_tma) {
     typedef Forms<KIND, CH> FM;

@@ -1204,7 +1204,10 @@ static int launch_slab_conv(fdga_ctx* ctx, const DevChain& V, ColJob& job, int k
     const int use_tma = (tma_on && slab_bytes % 16 == 0 && bytes(TW) + slab_bytes <= 72 * 1024) ? 1 : 0;
     const size_t smem = bytes(TW) + (use_tma ? slab_bytes : 0);
     CK(cudaFuncSetAttribute(slab_conv_kernel<KIND, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    slab_conv_kernel<KIND, CH><<<ctx->n_slabs[kind], 256, smem, ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->twL, ctx->ConvTabL[ctx->cur_lane], g, TW, use_tma);
+    // big momentum meshes: the slab's shared memory limits the SM to two CTAs, so each gets twice the threads
+    static const int conv_thr_env = getenv("FDGA_CONV_THREADS") ? atoi(getenv("FDGA_CONV_THREADS")) : 0;
+    const int conv_thr = conv_thr_env ? conv_thr_env : (smem > 64 * 1024 ? 512 : 256);
+    slab_conv_kernel<KIND, CH><<<ctx->n_slabs[kind], conv_thr, smem, ctx->stream>>>(V, job, ctx->d_slabs[kind], R, ctx->twL, ctx->ConvTabL[ctx->cur_lane], g, TW, use_tma);
     NOTE_LAUNCH("slab_conv_kernel");
     ctx->n_launch[cat]++; ctx->total_launches++;
     *tab = ctx->ConvTabL[ctx->cur_lane];
@@ -1236,7 +1239,16 @@ static int launch_column_t(fdga_ctx* ctx, const DevChain& V, ColJob job, SymGrou
         // the momentum-fastest table copies are made current before the lanes fork; on one stream, right here
         if (!ctx->forked && refresh_mom_all(ctx)) return 1;
         RepDev rd; rd.nrep = s.nrep; rd.rep = s.d_reps;
-        if (s.nrep > 0) LAUNCH(cat, (qlane_kernel<KIND, CH>), nblk(s.nrep, FDGA_QL_WARPS), 32 * FDGA_QL_WARPS, V, job, rd, R, own, rtot, conv, s.d_repvals, ctx->g);
+        if (s.nrep > 0) {
+            const size_t ring = (size_t)FDGA_QL_DEPTH * 4096 * FDGA_QL_WARPS;       // cp.async ring of qlane_consume_async
+            if (ring + 4096 > 48 * 1024) {
+                static bool attr_set = false;       // per template instance
+                if (!attr_set) { CK(cudaFuncSetAttribute(qlane_kernel<KIND, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring)); attr_set = true; }
+            }
+            qlane_kernel<KIND, CH><<<nblk(s.nrep, FDGA_QL_WARPS), 32 * FDGA_QL_WARPS, ring, ctx->stream>>>(V, job, rd, R, own, rtot, conv, s.d_repvals, ctx->g);
+            NOTE_LAUNCH("qlane_kernel");
+            ctx->n_launch[cat]++; ctx->total_launches++;
+        }
     } else
     if (s.ncol > 0) LAUNCH(cat, (column_kernel<KIND, CH>), (unsigned)s.ngrp, 128, V, job, col_dev(s), R, own, rtot, conv, s.d_repvals, ctx->g);
     if (sub) { cudaEventRecord(ev.b, ctx->stream); ctx->events.push_back(ev); ctx->n_launch[FDGA_T_COLUMN_K2]++; }

@@ -191,6 +191,44 @@ FDGA_HD C qlane_consume(const QPiece& pc, const uint4* __restrict__ ent, int n, 
     if (!has1) p1 = zeroC();
     return p0 + p1;
 }
+#ifndef FDGA_QL_DEPTH
+#define FDGA_QL_DEPTH 0        // stages of the cp.async ring of qlane_consume_async (0: plain loads, qlane_consume)
+#endif
+#if defined(__CUDA_ARCH__)
+// The same sum with the loads software-pipelined through shared memory: every lane copies its own eight 16-byte elements of
+// entry i + DEPTH - 1 with cp.async (L1-allocating, so the R rows and zero rows shared with neighbouring warps still hit) into a
+// per-warp ring of DEPTH stages while it consumes entry i.  Loads in flight do not hold registers, and there is no barrier: a
+// lane only ever reads back what it copied itself.  Stage layout: [8 loads][32 lanes] x 16 B = 4 KB.
+template <int DEPTH>
+__device__ __forceinline__ C qlane_consume_async(const QPiece& pc, const uint4* __restrict__ ent, int n, const C* __restrict__ r0, const C* __restrict__ r1,
+                                                 int q0x, int q0y, int q1x, int q1y, bool has1, int L, C* ring_lane) {
+    const C* a0 = pc.tA + mom_lane(pc.mA, q0x, q0y, L); const C* a1 = pc.tA + mom_lane(pc.mA, q1x, q1y, L);
+    const C* b0 = pc.tB + mom_lane(pc.mB, q0x, q0y, L); const C* b1 = pc.tB + mom_lane(pc.mB, q1x, q1y, L);
+    const C* c0 = pc.t3 + mom_lane(pc.m3, q0x, q0y, L); const C* c1 = pc.t3 + mom_lane(pc.m3, q1x, q1y, L);
+    const unsigned sb = (unsigned)__cvta_generic_to_shared(ring_lane);
+    auto cp16 = [](unsigned dst, const C* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory"); };
+    auto issue = [&](int i) {
+        const uint4 e = ent[i];
+        const unsigned d = sb + (unsigned)(i % DEPTH) * 4096u;
+        cp16(d, a0 + e.x); cp16(d + 512u, a1 + e.x); cp16(d + 1024u, b0 + e.y); cp16(d + 1536u, b1 + e.y);
+        cp16(d + 2048u, c0 + e.z); cp16(d + 2560u, c1 + e.z); cp16(d + 3072u, r0 + e.w); cp16(d + 3584u, r1 + e.w);
+    };
+#pragma unroll
+    for (int i = 0; i < DEPTH - 1; ++i) { if (i < n) issue(i); asm volatile("cp.async.commit_group;" ::: "memory"); }
+    C p0 = zeroC(), p1 = zeroC();
+    for (int i = 0; i < n; ++i) {
+        asm volatile("cp.async.wait_group %0;" :: "n"(DEPTH - 2) : "memory");      // entry i has landed
+        const C* st = ring_lane + (size_t)(i % DEPTH) * 256;                         // 4096 B = 256 elements per stage
+        const C va0 = st[0], va1 = st[32], vb0 = st[64], vb1 = st[96], vc0 = st[128], vc1 = st[160], x0 = st[192], x1 = st[224];
+        if (i + DEPTH - 1 < n) issue(i + DEPTH - 1);                                 // into the stage consumed one iteration ago
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        p0 += ((va0 + vb0) + vc0) * x0; p1 += ((va1 + vb1) + vc1) * x1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!has1) p1 = zeroC();
+    return p0 + p1;
+}
+#endif
 // cross-channel K1 term summed inside the kernel (FDGA_OPT_DIRECT_K1, or slabs too large for slab_conv_kernel)
 FDGA_HD C qlane_k1_direct(const QPiece& pc, const DevLevel& lv, const C* __restrict__ r0, const C* __restrict__ r1, int NP, int nw, int Nin,
                           int q0x, int q0y, int q1x, int q1y, bool has1, int L) {
@@ -211,7 +249,7 @@ FDGA_HD C qlane_k1_direct(const QPiece& pc, const DevLevel& lv, const C* __restr
 // with __syncwarp; SYNC = false: the host restatement of ONE lane with a private entry array (tests/host_column_test.cu sums it
 // over the 32 lanes).  Same building blocks either way.
 template <int KIND, int CH, bool SYNC>
-FDGA_HD C qlane_rep(const DevChain& V, const ColJob& job, const Grid& g, const C* __restrict__ R, uint4* ent,
+FDGA_HD C qlane_rep(const DevChain& V, const ColJob& job, const Grid& g, const C* __restrict__ R, uint4* ent, C* ring_lane,
                     int iW, int inu, int iP, int Px, int Py, int kx, int ky, int lane) {
     typedef Forms<KIND, CH> FM;
     const int L = g.L, NP = g.NP, nw = job.nw, Nin = job.Ninner;
@@ -247,7 +285,12 @@ FDGA_HD C qlane_rep(const DevChain& V, const ColJob& job, const Grid& g, const C
                         } else
 #endif
                         for (int i = 0; i < n; ++i) ent[i] = qlane_entry(pc, lv, NP, Nin, e0 + i);
+#if defined(__CUDA_ARCH__) && FDGA_QL_DEPTH >= 2
+                        const C part = SYNC ? qlane_consume_async<FDGA_QL_DEPTH>(pc, ent, n, r0, r1, q0x, q0y, q1x, q1y, has1, L, ring_lane)
+                                            : qlane_consume(pc, ent, n, r0, r1, q0x, q0y, q1x, q1y, has1, L);
+#else
                         const C part = qlane_consume(pc, ent, n, r0, r1, q0x, q0y, q1x, q1y, has1, L);
+#endif
                         if (has0) pf += part;
                     }
                     if (job.k1_direct) {
@@ -265,7 +308,7 @@ template <int KIND, int CH>
 FDGA_HD C qlane_lane(const DevChain& V, const ColJob& job, const Grid& g, const C* __restrict__ R,
                      int iW, int inu, int iP, int ik, int lane) {
     uint4 ent[FDGA_QL_ENT];
-    return qlane_rep<KIND, CH, false>(V, job, g, R, ent, iW, inu, iP, iP % g.L, iP / g.L, ik % g.L, ik / g.L, lane);
+    return qlane_rep<KIND, CH, false>(V, job, g, R, ent, nullptr, iW, inu, iP, iP % g.L, iP / g.L, ik % g.L, ik / g.L, lane);
 }
 
 // class representatives of this rank, sorted by slab: (iW | inu << 16, iP | ik << 16, Px | Py << 8 | kx << 16 | ky << 24, class slot)
@@ -283,13 +326,15 @@ qlane_kernel(const __grid_constant__ DevChain V, ColJob job, RepDev reps, const 
              const C* __restrict__ OwnTab, const C* __restrict__ Rtot, const C* __restrict__ ConvTab,
              C* __restrict__ repvals, Grid g) {
     __shared__ uint4 s_ent[FDGA_QL_WARPS][FDGA_QL_ENT];
+    extern __shared__ __align__(128) double ql_ring[];      // FDGA_QL_DEPTH x 4 KB per warp (cp.async ring), empty when FDGA_QL_DEPTH == 0
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * FDGA_QL_WARPS + wid;
     if (w >= reps.nrep) return;                     // whole warps leave together; only __syncwarp below
     const int4 rp = reps.rep[w];
     const int iW = rp.x & 0xffff, inu = rp.x >> 16, iP = rp.y & 0xffff, ik = (rp.y >> 16) & 0xffff;
     const int Px = rp.z & 0xff, Py = (rp.z >> 8) & 0xff, kx = (rp.z >> 16) & 0xff, ky = (rp.z >> 24) & 0xff;
-    C acc = qlane_rep<KIND, CH, true>(V, job, g, R, s_ent[wid], iW, inu, iP, Px, Py, kx, ky, lane);
+    C* ring_lane = reinterpret_cast<C*>(ql_ring) + (size_t)wid * (FDGA_QL_DEPTH > 0 ? FDGA_QL_DEPTH : 1) * 256 + lane;
+    C acc = qlane_rep<KIND, CH, true>(V, job, g, R, s_ent[wid], ring_lane, iW, inu, iP, Px, Py, kx, ky, lane);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o); }
     if (lane == 0) {
