@@ -350,7 +350,7 @@ def run_ours(a):
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W, "ms_per_step": ms / a.steps,
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex)", "data": inp["data"],
-               "config": {"workload": workload_name(a), "l2": "inputs larger than L2: 4 bubbles x %.0f MB + hoisted right factor %.0f MB per channel are streamed every step" % (S.length_F() * 0 + 16e-6 * np.prod(S._shpΠ), 16e-6 * np.prod(S._shpΠ)),
+               "config": {"workload": workload_name(a), "l2": "inputs larger than L2, nothing flushed between steps: K2 tables of S.F, S.F0, S.F + S.F0, FL, Fbuff and their momentum-fastest copies %.0f MB + compact bubble slabs and right factors (only the (W,P) slabs with class representatives) + scratch tables, against 126 MB of L2" % (16e-6 * S.F.γp.K2.size * 3 * 14),
                           "symmetry_classes": {"K1": S.num_classes(fd._lib.SG_K1), "K2pp": n2cls[0], "K2ph": n2cls[1], "K3pp": S.num_classes(fd._lib.SG_PP3), "K3ph": S.num_classes(fd._lib.SG_PH3)},
                           "parallelism": f"class representatives sharded over {world} rank(s), NCCL all-gather per kernel" if world > 1 else "1 GPU"},
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(nF * 16), "d2h_bytes_per_step": int(nF * 16 + S.Σ.size * 16), "ms_per_step": ms_e2e / a.steps},
