@@ -286,6 +286,10 @@ def run_ours(a):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": k2_ms_launch,
                 "note": "not HBM-bound: a gather contraction whose tables and slabs are L2-resident (DRAM traffic below the algorithmic bytes); bounded by L2 -> L1 latency at the occupancy its registers allow, see fp64 and DESIGN.md section 4",
+                "l2": None if (traffic is None or not traffic.get("l2_to_l1_bytes_per_launch")) else {
+                    "bytes_per_launch": traffic["l2_to_l1_bytes_per_launch"], "achieved_tbs": traffic["l2_to_l1_bytes_per_launch"] / (k2_ms_launch * 1e-3) / 1e12,
+                    "peak_tbs": 6300 * 1.965e9 / 1e12, "frac": traffic["l2_to_l1_bytes_per_launch"] / (k2_ms_launch * 1e-3) / (6300 * 1.965e9),
+                    "peak_source": "LTS throughput cap ~6300 B/clk (B300_MICROARCH.md, measured on B300) x 1.965 GHz; bytes = lts__t_sectors_srcunit_tex_op_read x 32 from the committed ncu capture"},
                 "fp64": {"algorithmic_gflop_per_launch": flop_per_launch / 1e9, "achieved_tflops": flop_per_launch / (k2_ms_launch * 1e-3) / 1e12,
                          "peak_tflops": fp64_peak, "peak_source": "DFMA micro-benchmark in libfdga (fdga_measure_fp64_peak), measured in this run",
                          "frac": flop_per_launch / (k2_ms_launch * 1e-3) / 1e12 / fp64_peak}}
