@@ -41,7 +41,7 @@ static const int INF = INT_MAX / 4;
 
 enum { pCh = 0, tCh = 1, aCh = 2 };
 enum { pSp = 0, xSp = 1, dSp = 2 };
-enum { LV_NL2 = 0, LV_LOCAL = 1, LV_CORE = 2 };
+enum { LV_NL2 = 0, LV_LOCAL = 1, LV_CORE = 2, LV_NL = 3 /* NL_Vertex: bosonic momentum only, src/nonlocal/vertex.jl */ };
 
 // ---------------------------------------------------------------------------------
 // Matsubara index arithmetic (derived from value(nu) = (2n+1) pi T etc.)
@@ -69,7 +69,7 @@ static inline int kidx(Mom k, int L) { return mod_(k.x, L) + L * mod_(k.y, L); }
 // C-layout descriptors filled by the Python adapter (oracle/oracle.py)
 extern "C" {
 typedef struct {
-    int type;                       // LV_NL2 / LV_LOCAL / LV_CORE
+    int type;                       // LV_NL2 / LV_LOCAL / LV_CORE / LV_NL
     int nK1, nK2b, nK2f, nK3b, nK3f; // mesh N's (CORE: nK3b, nK3f = box of the 4 core arrays)
     double U_re, U_im;              // CORE only
     const cplx* K1[3];              // [p, t, a]
@@ -87,6 +87,7 @@ typedef struct {
     double T;
     int L;                          // linear size of the vertex / bubble momentum mesh
     int nPiB, nPiF;                 // N of the bubble's bosonic / fermionic Matsubara meshes
+    int swave;                      // 1: s-wave NL_ParquetSolver (bubbles Pi[W,w,P], K2[W,v,P]); 0: NL2 / local
 } orc_grid;
 
 typedef struct {                    // symmetry classes, CSR; representative = first member
@@ -191,6 +192,58 @@ struct NL2Chan {
     }
 };
 
+// ---- NL_Channel evaluator (K1[W,P], K2[W,v,P], K3[W,v,w,P]), src/nonlocal/channel.jl:68-226; P may be the s-wave point:
+// getindex then averages over the momentum axis (src/nonlocal/swave.jl:32-74)
+struct NLChan {
+    int nK1, nK2b, nK2f, nK3b, nK3f, L, NP;
+    const cplx *K1, *K2, *K3;
+    cplx k1(int W, Mom P) const {
+        int iW = posB(W, nK1), nB = 2 * nK1 - 1;
+        if (!P.sw) return K1[iW + (size_t)nB * kidx(P, L)];
+        cplx s = 0; for (int p = 0; p < NP; p++) s += K1[iW + (size_t)nB * p];
+        return s / (double)NP;
+    }
+    cplx k2(int W, int v, Mom P) const {
+        int nB = 2 * nK2b - 1, nF = 2 * nK2f;
+        size_t base = posB(W, nK2b) + (size_t)nB * posF(v, nK2f), sP = (size_t)nB * nF;
+        if (!P.sw) return K2[base + sP * kidx(P, L)];
+        cplx s = 0; for (int p = 0; p < NP; p++) s += K2[base + sP * p];
+        return s / (double)NP;
+    }
+    cplx k3(int W, int v, int w, Mom P) const {
+        int nB = 2 * nK3b - 1, nF = 2 * nK3f;
+        size_t base = posB(W, nK3b) + (size_t)nB * (posF(v, nK3f) + (size_t)nF * posF(w, nK3f)), sP = (size_t)nB * nF * nF;
+        if (!P.sw) return K3[base + sP * kidx(P, L)];
+        cplx s = 0; for (int p = 0; p < NP; p++) s += K3[base + sP * p];
+        return s / (double)NP;
+    }
+    cplx eval(int W, int v, int w, Mom P, bool fK1 = true, bool fK2 = true, bool fK3 = true) const {
+        cplx val = 0;
+        bool vi = isinf_(v), wi = isinf_(w);
+        if (!vi && !wi) {                                   // :90-130
+            if (inB(W, nK1)) {
+                if (fK1) val += k1(W, P);
+                if (inB(W, nK2b)) {
+                    bool a = inF(v, nK2f), b = inF(w, nK2f);
+                    if (a && b) {
+                        if (fK2) val += k2(W, v, P) + k2(W, w, P);
+                        if (fK3 && inB(W, nK3b) && inF(v, nK3f) && inF(w, nK3f)) val += k3(W, v, w, P);
+                    } else if (a) { if (fK2) val += k2(W, v, P); }
+                    else if (b) { if (fK2) val += k2(W, w, P); }
+                }
+            }
+        } else if (vi != wi) {                              // :133-200 (nu = inf: K2 at nu'; nu' = inf: K2 at nu)
+            int x = vi ? w : v;
+            if (fK1) {
+                if (inB(W, nK1)) { val += k1(W, P); if (fK2 && inB(W, nK2b) && inF(x, nK2f)) val += k2(W, x, P); }
+            } else if (fK2 && inB(W, nK2b) && inF(x, nK2f)) val += k2(W, x, P);
+        } else {                                            // :203-225
+            if (fK1 && inB(W, nK1)) val += k1(W, P);
+        }
+        return val;
+    }
+};
+
 // ---- local Channel evaluator, src/channel.jl:220-339 --------------------------------
 struct LocChan {
     int nK1, nK2b, nK2f, nK3b, nK3f;
@@ -267,6 +320,10 @@ struct VertexEval {
         NL2Chan c; c.nK1 = lv.nK1; c.nK2b = lv.nK2b; c.nK2f = lv.nK2f; c.nK3b = lv.nK3b; c.nK3f = lv.nK3f;
         c.L = L; c.NP = NP; c.K1 = lv.K1[r]; c.K2 = lv.K2[r]; c.K3 = lv.K3[r]; return c;
     }
+    NLChan nl(const orc_level& lv, int r) const {
+        NLChan c; c.nK1 = lv.nK1; c.nK2b = lv.nK2b; c.nK2f = lv.nK2f; c.nK3b = lv.nK3b; c.nK3f = lv.nK3f;
+        c.L = L; c.NP = NP; c.K1 = lv.K1[r]; c.K2 = lv.K2[r]; c.K3 = lv.K3[r]; return c;
+    }
     LocChan loc(const orc_level& lv, int r) const {
         LocChan c; c.nK1 = lv.nK1; c.nK2b = lv.nK2b; c.nK2f = lv.nK2f; c.nK3b = lv.nK3b; c.nK3f = lv.nK3f;
         c.K1 = lv.K1[r]; c.K2 = lv.K2[r]; c.K3 = lv.K3[r]; return c;
@@ -311,7 +368,30 @@ struct VertexEval {
         }
         // ---- pSp ----
         if (lv.type == LV_LOCAL) return eval_local(l, W, v, w, Ch, f);
+        if (lv.type == LV_NL) return eval_nl(l, W, v, w, P, k, q, Ch, f);
         return eval_nl2(l, W, v, w, P, k, q, Ch, f);
+    }
+
+    // NL_Vertex (bosonic momentum dependence only), src/nonlocal/vertex.jl:69-153 (Brillouin points), :213-377 (s-wave points)
+    cplx eval_nl(int l, int W, int v, int w, Mom P, Mom k, Mom q, int Ch, Flags f) const {
+        const orc_level& lv = V->lev[l];
+        cplx val = 0;
+        if (f.F0) val += eval(l + 1, W, v, w, P, k, q, Ch, pSp, ALLF());
+        bool fl[3] = {f.gp, f.gt, f.ga};
+        if (isinf_(v) || isinf_(w)) {                     // :112-153: only the own channel, at P
+            if (fl[Ch]) val += nl(lv, Ch).eval(W, v, w, P);
+            return val;
+        }
+        for (int r = 0; r < 3; r++) if (fl[r]) {
+            int W2, v2, w2; conv_freq(W, v, w, Ch, r, W2, v2, w2);
+            if (!k.sw && !q.sw) {                         // :69-107: converted transfer momentum
+                Mom P2, k2, q2; conv_mom(P, k, q, Ch, r, P2, k2, q2);
+                val += nl(lv, r).eval(W2, v2, w2, P2);
+            } else {                                      // :213-377: own channel at P, other channels averaged over their momentum
+                val += nl(lv, r).eval(W2, v2, w2, r == Ch ? P : SW());
+            }
+        }
+        return val;
     }
 
     // local Vertex, src/vertex.jl:209-284 (momentum args dropped, src/nonlocal/channel.jl:230-256)
@@ -439,6 +519,7 @@ void orc_eval_channel(const orc_vertex* V, int L, int level, int r, int W, int v
     Mom PP = (swbits & 1) ? SW() : mk(P[0], P[1]);
     Mom kk = (swbits & 2) ? SW() : mk(k[0], k[1]);
     Mom qq = (swbits & 4) ? SW() : mk(q[0], q[1]);
+    if (V->lev[level].type == LV_NL) { *out = E.nl(V->lev[level], r).eval(W, v, w, PP, fK1 != 0, fK2 != 0, fK3 != 0); return; }
     *out = E.nl2(V->lev[level], r).eval(W, v, w, PP, kk, qq, fK1 != 0, fK2 != 0, fK3 != 0);
 }
 
@@ -674,6 +755,7 @@ void orc_bse_K2_1loop(cplx* K2, int nK2b, int nK2f, const orc_vertex* F0, const 
 static inline cplx pi_sw(const cplx* Pi, const orc_grid* g, int W, int w, int iP) {
     int NP = g->L * g->L, nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF;
     size_t base = posB(W, g->nPiB) + (size_t)nBP * (posF(w, g->nPiF) + (size_t)nFP * iP);
+    if (g->swave) return Pi[base];          // NL_MF_Pi[W, w, P]: src/nonlocal/BSEa/BSEa_K3.jl:28,80-81
     size_t sk = (size_t)nBP * nFP * NP;
     cplx s = 0; for (int i = 0; i < NP; i++) s += Pi[base + sk * i];
     return s / (double)NP;
@@ -1096,8 +1178,202 @@ void orc_sde_U2(cplx* SigU2, const cplx* G, int nG, int LG, double U_re, double 
     orc_symmetrize(SigU2, SGS);
 }
 
+// =====================================================================================================
+// s-wave NL_ParquetSolver (nl_method = 1 of script/run_Wu_point.jl): vertices with bosonic momentum dependence only,
+// K1[W,P], K2[W,v,P], K3[W,v,w,P], bubbles Pi[W,w,P]; every fermionic momentum is the s-wave point kSW.
+// The K3 kernels and build_K3_cache! are the NL2 ones above (same formulas, src/nonlocal/BSEa/BSEa_K3.jl,
+// src/nonlocal/build_K3_cache.jl:18-94) with g->swave = 1 selecting the three-index bubble.
+static inline void decodeK2nl(int64_t idx, int nb, int nf, int L, int& W, int& v, int& iP, Mom& P) {
+    int nB = 2 * nb - 1, nF = 2 * nf;
+    int iW = idx % nB; idx /= nB; int iv = idx % nF; iP = (int)(idx / nF);
+    W = iW - (nb - 1); v = iv - nf; P = mk(iP % L, iP / L);
+}
+// ---- BSE_K1!, src/nonlocal/BSEa/BSEa_K1.jl:2-58 ----
+void orc_nl_bse_K1(cplx* K1, int nK1, const orc_vertex* F0, const orc_vertex* F, const orc_vertex* FL,
+                   const cplx* Pi0, const cplx* Pi, const orc_sg* SG, int sign, int Ch, int Sp, int is_mfRG,
+                   const orc_grid* g, int64_t c0, int64_t c1) {
+    int L = g->L, NP = L * L;
+    VertexEval EF0 = {F0, L, NP}, EF = {F, L, NP}, EFL = {FL, L, NP};
+    int nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF, nB1 = 2 * nK1 - 1;
+    double T = g->T;
+    auto diagram = [&](int64_t idx) -> cplx {
+        int W = (int)(idx % nB1) - (nK1 - 1); int iP = (int)(idx / nB1); Mom P = mk(iP % L, iP / L);
+        int iW = posB(W, g->nPiB);
+        cplx val = 0;
+        for (int iw = 0; iw < nFP; iw++) {
+            int w = iw - g->nPiF;
+            size_t pidx = iW + (size_t)nBP * (iw + (size_t)nFP * iP);
+            if (is_mfRG) {
+                cplx Fl  = EF0.eval(0, W, INF, w, P, SW(), SW(), Ch, Sp, ALLF());
+                cplx FLr = EFL.eval(0, W, crossingF(W, w, Ch), INF, P, SW(), SW(), Ch, Sp, ALLF());
+                val += Fl * Pi0[pidx] * FLr;
+            } else {
+                cplx Fl  = EF.eval(0, W, INF, w, P, SW(), SW(), Ch, Sp, ALLF());
+                cplx F0r = EF0.eval(0, W, crossingF(W, w, Ch), INF, P, SW(), SW(), Ch, Sp, ALLF());
+                cplx FLr = EFL.eval(0, W, crossingF(W, w, Ch), INF, P, SW(), SW(), Ch, Sp, ALLF());
+                val += Fl * ((Pi[pidx] - Pi0[pidx]) * F0r + Pi[pidx] * FLr);
+            }
+        }
+        return T * val * (double)sign;
+    };
+    sg_apply(K1, SG, diagram, c0, c1);
+}
+// ---- BSE_L_K2!, src/nonlocal/BSEa/BSEa_K2.jl:1-41 (omega over the K2 nu-mesh) ----
+void orc_nl_bse_L_K2(cplx* K2, int nK2b, int nK2f, const orc_vertex* F0, const orc_vertex* F,
+                     const cplx* Pi0, const orc_sg* SG, int sign, int Ch, int Sp,
+                     const orc_grid* g, int64_t c0, int64_t c1) {
+    int L = g->L, NP = L * L;
+    VertexEval EF0 = {F0, L, NP}, EF = {F, L, NP};
+    int nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF;
+    double T = g->T;
+    Flags fl = {false, Ch != pCh, Ch != tCh, Ch != aCh};
+    auto diagram = [&](int64_t idx) -> cplx {
+        int W, v, iP; Mom P; decodeK2nl(idx, nK2b, nK2f, L, W, v, iP, P);
+        int iW = posB(W, g->nPiB);
+        cplx val = 0;
+        for (int iw = 0; iw < 2 * nK2f; iw++) {
+            int w = iw - nK2f;
+            cplx Gl  = EF.eval(0, W, v, crossingF(W, w, Ch), P, SW(), SW(), Ch, Sp, fl);
+            cplx F0r = EF0.eval(0, W, w, INF, P, SW(), SW(), Ch, Sp, ALLF());
+            val += Gl * Pi0[iW + (size_t)nBP * (posF(w, g->nPiF) + (size_t)nFP * iP)] * F0r;
+        }
+        return T * val * (double)sign;
+    };
+    sg_apply(K2, SG, diagram, c0, c1);
+}
+// ---- BSE_K2!, src/nonlocal/BSEa/BSEa_K2.jl:44-106 (SG part; the FL add is done by the caller) ----
+void orc_nl_bse_K2(cplx* K2, int nK2b, int nK2f, const orc_vertex* F0, const orc_vertex* F, const orc_vertex* FL,
+                   const cplx* Pi0, const cplx* Pi, const orc_sg* SG, int sign, int Ch, int Sp, int is_mfRG,
+                   const orc_grid* g, int64_t c0, int64_t c1) {
+    int L = g->L, NP = L * L;
+    VertexEval EF0 = {F0, L, NP}, EF = {F, L, NP}, EFL = {FL, L, NP};
+    int nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF;
+    double T = g->T;
+    auto diagram = [&](int64_t idx) -> cplx {
+        int W, v, iP; Mom P; decodeK2nl(idx, nK2b, nK2f, L, W, v, iP, P);
+        int iW = posB(W, g->nPiB);
+        cplx val = 0;
+        for (int iw = 0; iw < nFP; iw++) {
+            int w = iw - g->nPiF;
+            size_t pidx = iW + (size_t)nBP * (iw + (size_t)nFP * iP);
+            if (is_mfRG) {
+                int wc = crossingF(W, w, Ch);
+                cplx Fl  = EF0.eval(0, W, v, wc, P, SW(), SW(), Ch, Sp, ALLF()) - EF0.eval(0, W, INF, wc, P, SW(), SW(), Ch, Sp, ALLF());
+                cplx FLr = EFL.eval(0, W, w, INF, P, SW(), SW(), Ch, Sp, ALLF());
+                val += Fl * Pi0[pidx] * FLr;
+            } else {
+                cplx Fl  = EF.eval(0, W, v, w, P, SW(), SW(), Ch, Sp, ALLF()) - EF.eval(0, W, INF, w, P, SW(), SW(), Ch, Sp, ALLF());
+                cplx F0r = EF0.eval(0, W, crossingF(W, w, Ch), INF, P, SW(), SW(), Ch, Sp, ALLF());
+                cplx FLr = EFL.eval(0, W, crossingF(W, w, Ch), INF, P, SW(), SW(), Ch, Sp, ALLF());
+                val += Fl * ((Pi[pidx] - Pi0[pidx]) * F0r + Pi[pidx] * FLr);
+            }
+        }
+        return T * val * (double)sign;
+    };
+    sg_apply(K2, SG, diagram, c0, c1);
+}
+// ---- bubbles_real_space! for NL_MF_Pi, src/nonlocal/bubble.jl:86-158:  Pipp(R) = G(R) G(R), Piph(R) = G(R) G(-R), R in
+// [-L/2, L/2]^2 weighted 1/2 per component with |R_c| = LG/2 (LG even), R = 0 with the 1/nu tail outside the G mesh
+// (use_G_tail = true by default), backward transform over the momentum axes ----
+void orc_nl_bubbles_real_space(cplx* Pipp, cplx* Piph, const cplx* G, int nG, int LG, const orc_grid* g, int use_G_tail) {
+    const int L = g->L, NP = L * L, nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF, nGf = 2 * nG, h = L / 2;
+    const double pi = 3.14159265358979323846;
+    std::vector<cplx> GR((size_t)nGf * LG * LG);
+    std::copy(G, G + GR.size(), GR.begin());
+    dft_axis(GR.data(), nGf, LG, LG, -1); dft_axis(GR.data(), (size_t)nGf * LG, LG, 1, -1);
+    for (auto& x : GR) x /= (double)(LG * LG);
+    const size_t pre = (size_t)nBP * nFP;
+    std::fill(Pipp, Pipp + pre * NP, cplx(0)); std::fill(Piph, Piph + pre * NP, cplx(0));
+    auto gat = [&](int n, int rx, int ry, bool tail) -> cplx {
+        if (inF(n, nG)) return GR[posF(n, nG) + (size_t)nGf * (mod_(rx, LG) + (size_t)LG * mod_(ry, LG))];
+        return tail ? cplx(1.0 / ((2 * n + 1) * pi * g->T), 0.0) : cplx(0);
+    };
+    for (int R2 = -h; R2 <= h; R2++) for (int R1 = -h; R1 <= h; R1++) {
+        double weight = 1.0;
+        if (LG % 2 == 0) { if (std::abs(R1) == LG / 2) weight /= 2; if (std::abs(R2) == LG / 2) weight /= 2; }
+        const size_t iR = mod_(R1, L) + (size_t)L * mod_(R2, L);
+        const bool tail = use_G_tail && R1 == 0 && R2 == 0;
+        for (int iw = 0; iw < nFP; iw++) for (int iW = 0; iW < nBP; iW++) {
+            const int W = iW - (g->nPiB - 1), w = iw - g->nPiF;
+            Pipp[iW + (size_t)nBP * iw + pre * iR] += gat(W - w - 1, R1, R2, tail) * gat(w, R1, R2, tail) * weight;
+            Piph[iW + (size_t)nBP * iw + pre * iR] += gat(W + w, R1, R2, tail) * gat(w, -R1, -R2, tail) * weight;
+        }
+    }
+    dft_axis(Pipp, pre, L, L, +1); dft_axis(Pipp, pre * L, L, 1, +1);
+    dft_axis(Piph, pre, L, L, +1); dft_axis(Piph, pre * L, L, 1, +1);
+}
+// ---- SDE_channel_L_pp! / ph!, src/nonlocal/SDE.jl:3-146: own gamma of the level only (NL_Vertex / Vertex), core - bare for the
+// RefVertex level; `level` indexes the chain V ----
+void orc_nl_sde_L(cplx* Lout, int nK2b, int nK2f, const orc_vertex* V, int level, const cplx* Pi, const orc_sg* SG, int is_pp,
+                  const orc_grid* g, int64_t c0, int64_t c1) {
+    int L = g->L, NP = L * L;
+    VertexEval E = {V, L, NP};
+    int nBP = 2 * g->nPiB - 1, nFP = 2 * g->nPiF;
+    double T = g->T;
+    const orc_level& lv = V->lev[level];
+    const orc_level& core = V->lev[V->nlev - 1];
+    cplx U(core.U_re, core.U_im);
+    auto own = [&](int r, int W, int v, int w, Mom P) -> cplx {
+        if (lv.type == LV_NL) return E.nl(lv, r).eval(W, v, w, P);
+        if (lv.type == LV_LOCAL) return E.loc(lv, r).eval(W, v, w, true, true, true);
+        return 0;
+    };
+    auto diagram = [&](int64_t idx) -> cplx {
+        int W, v, iP; Mom P; decodeK2nl(idx, nK2b, nK2f, L, W, v, iP, P);
+        int iW = posB(W, g->nPiB);
+        cplx val = 0;
+        for (int iw = 0; iw < nFP; iw++) {
+            int w = iw - g->nPiF;
+            cplx pi = Pi[iW + (size_t)nBP * (iw + (size_t)nFP * iP)];
+            if (lv.type == LV_CORE) {
+                if (is_pp) val += U * pi * (E.core_eval(lv, W, B_minus_F(W, w), v, pCh, pSp) - U);
+                else val += U * pi * (E.core_eval(lv, W, v, w, tCh, pSp) + E.core_eval(lv, W, v, w, aCh, pSp) - 2.0 * U);
+            } else {
+                if (is_pp) val += U * pi * own(pCh, W, B_minus_F(W, w), v, P);
+                else val += U * pi * (own(tCh, W, v, w, P) + own(aCh, W, v, w, P));
+            }
+        }
+        return T * val;
+    };
+    sg_apply(Lout, SG, diagram, c0, c1);
+}
+// ---- SDE_compute_inner! (use_real_space = true), src/nonlocal/SDE.jl:191-275.  Lpp / Lph are read only here. ----
+void orc_nl_sde_inner(cplx* Sigma, int nSig, int LSig, const cplx* G, int nG, int LG, const cplx* Lpp, const cplx* Lph,
+                      int nK2b, int nK2f, const orc_sg* SGS, const orc_grid* g) {
+    const int L = g->L, nB = 2 * nK2b - 1, nF = 2 * nK2f, nGf = 2 * nG, nSf = 2 * nSig, h = L / 2;
+    const size_t pre = (size_t)nB * nF;
+    std::vector<cplx> GR((size_t)nGf * LG * LG), A(Lpp, Lpp + pre * L * L), B(Lph, Lph + pre * L * L), SR((size_t)nSf * LSig * LSig, cplx(0));
+    std::copy(G, G + GR.size(), GR.begin());
+    dft_axis(GR.data(), nGf, LG, LG, -1); dft_axis(GR.data(), (size_t)nGf * LG, LG, 1, -1);
+    for (auto& x : GR) x /= (double)(LG * LG);
+    dft_axis(A.data(), pre, L, L, -1); dft_axis(A.data(), pre * L, L, 1, -1);
+    dft_axis(B.data(), pre, L, L, -1); dft_axis(B.data(), pre * L, L, 1, -1);
+    for (auto& x : A) x /= (double)(L * L);
+    for (auto& x : B) x /= (double)(L * L);
+    for (int R2 = -h; R2 <= h; R2++) for (int R1 = -h; R1 <= h; R1++) {
+        double weight = 1.0;
+        if (L % 2 == 0) { if (std::abs(R1) == L / 2) weight /= 2; if (std::abs(R2) == L / 2) weight /= 2; }
+        const size_t iRL = mod_(R1, L) + (size_t)L * mod_(R2, L);
+        const size_t imRG = mod_(-R1, LG) + (size_t)LG * mod_(-R2, LG);
+        const size_t ipRS = mod_(R1, LSig) + (size_t)LSig * mod_(R2, LSig), imRS = mod_(-R1, LSig) + (size_t)LSig * mod_(-R2, LSig);
+        for (int iv = 0; iv < nF; iv++) {
+            const int v = iv - nK2f;
+            if (!inF(v, nSig)) continue;
+            for (int iW = 0; iW < nB; iW++) {
+                const int W = iW - (nK2b - 1);
+                if (inF(W - v - 1, nG)) SR[posF(v, nSig) + (size_t)nSf * ipRS] += GR[posF(W - v - 1, nG) + (size_t)nGf * imRG] * A[iW + (size_t)nB * iv + pre * iRL] * weight;
+                if (inF(W + v, nG))     SR[posF(v, nSig) + (size_t)nSf * imRS] += GR[posF(W + v, nG) + (size_t)nGf * imRG] * B[iW + (size_t)nB * iv + pre * iRL] * weight;
+            }
+        }
+    }
+    for (auto& x : SR) x *= g->T;
+    dft_axis(SR.data(), nSf, LSig, LSig, +1); dft_axis(SR.data(), (size_t)nSf * LSig, LSig, 1, +1);
+    std::copy(SR.begin(), SR.end(), Sigma);
+    orc_symmetrize(Sigma, SGS);
+}
+
 // ---- MatsubaraFunctions.SymmetryGroup(symmetries, f) restated ------
-// kind: 0 Sigma(nu,k) 1 K1(W,P) 2 K2pp 3 K2ph 4 K3pp 5 K3ph 6 K3ppL 7 K3phL
+// kind: 0 Sigma(nu,k) 1 K1(W,P) 2 K2pp 3 K2ph 4 K3pp 5 K3ph 6 K3ppL 7 K3phL 8 K2pp[W,v,P] 9 K2ph[W,v,P] (s-wave NL solver)
 // generators in the order of src/nonlocal_2/ParquetSolver.jl:200-291.
 struct SymPt { int f[3]; Mom m[2]; };
 static bool apply_gen(int kind, int gi, const SymPt& a, int L, SymPt& b, uint8_t& op) {
@@ -1132,6 +1408,15 @@ static bool apply_gen(int kind, int gi, const SymPt& a, int L, SymPt& b, uint8_t
         else if (gi == 3) b.m[0] = ref(a.m[0]);
         else b.m[0] = rot(a.m[0]);
         break;
+    case 8: case 9: ngen = 4;   // K2 with s-wave truncation: src/nonlocal/symmetries.jl:47-72, order of src/nonlocal/ParquetSolver.jl:215-250
+        if (gi == 0) { b.f[0] = -a.f[0]; b.f[1] = -a.f[1] - 1; b.m[0] = neg(a.m[0]); op = 2; }
+        else if (gi == 1) {
+            if (kind == 8) b.f[1] = B_minus_F(a.f[0], a.f[1]);
+            else { b.f[0] = -a.f[0]; b.f[1] = B_plus_F(a.f[0], a.f[1]); b.m[0] = neg(a.m[0]); }
+        }
+        else if (gi == 2) b.m[0] = ref(a.m[0]);
+        else b.m[0] = rot(a.m[0]);
+        break;
     case 6: case 7: ngen = 4;   // K3 left: generators 1, 3, ref, rot
         if (gi == 0) { b.f[0] = -a.f[0]; b.f[1] = -a.f[1] - 1; b.f[2] = -a.f[2] - 1; b.m[0] = neg(a.m[0]); op = 2; }
         else if (gi == 1) {
@@ -1149,7 +1434,7 @@ static bool apply_gen(int kind, int gi, const SymPt& a, int L, SymPt& b, uint8_t
 // Outputs sized to the array length; returns the number of classes.
 int64_t orc_build_symmetry_group(int kind, int n0, int n1, int L, int64_t* offsets, int64_t* index, uint8_t* ops) {
     int NP = L * L;
-    int nfreq = (kind <= 1) ? 1 : (kind <= 3 ? 2 : 3);
+    int nfreq = (kind <= 1) ? 1 : ((kind <= 3 || kind >= 8) ? 2 : 3);
     int nmom = (kind == 2 || kind == 3) ? 2 : 1;
     int len0 = (kind == 0) ? 2 * n0 : 2 * n0 - 1, len1 = 2 * n1;
     int dims[5]; int nd = 0;

@@ -16,7 +16,7 @@ if _HERE not in sys.path:
     sys.path.insert(0, _HERE)
 # the oracle keeps its OWN data model (mesh lengths, shapes, flatten order restated from the reference): oracle/otypes.py.
 # Vertices handed in by tests in the product's containers are copied into it (otypes.adopt), never used in place.
-from otypes import (NL2_Vertex, RefVertex, Vertex, aCh, adopt, dSp, nB, nF, pCh, pSp, tCh,  # noqa: E402,F401
+from otypes import (NL2_Vertex, NL_Vertex, RefVertex, Vertex, aCh, adopt, dSp, nB, nF, pCh, pSp, tCh,  # noqa: E402,F401
                     vertex_chain, xSp, zeros)
 
 LIB = os.path.join(_HERE, "_build", "libfdga_oracle.so")
@@ -42,7 +42,7 @@ class _Vertex(C.Structure):
 
 
 class _Grid(C.Structure):
-    _fields_ = [("T", C.c_double), ("L", C.c_int), ("nPiB", C.c_int), ("nPiF", C.c_int)]
+    _fields_ = [("T", C.c_double), ("L", C.c_int), ("nPiB", C.c_int), ("nPiF", C.c_int), ("swave", C.c_int)]
 
 
 class _SG(C.Structure):
@@ -82,7 +82,7 @@ def vertex_struct(V):
             for j, a in enumerate(X.arrays()):
                 lv.core[j] = a.ctypes.data
         else:
-            lv.type = 0 if isinstance(X, NL2_Vertex) else 1
+            lv.type = 0 if isinstance(X, NL2_Vertex) else (3 if isinstance(X, NL_Vertex) else 1)
             lv.nK1 = X.numK1
             lv.nK2b, lv.nK2f = X.numK2
             lv.nK3b, lv.nK3f = X.numK3
@@ -138,6 +138,7 @@ def eval_channel(V, L, r, W, v, w, P, k, q, K1=True, K2=True, K3=True, level=0):
 _CACHE_NAMES = ["cache_Γpx", "cache_F0p", "cache_F0a", "cache_F0t", "cache_Γpp", "cache_Γa", "cache_Γt",
                 "cache_Fp", "cache_Fa", "cache_Ft"]
 SG_SIGMA, SG_K1, SG_PP2, SG_PH2, SG_PP3, SG_PH3, SG_PPL3, SG_PHL3 = range(8)
+SG_NL_PP2, SG_NL_PH2 = 8, 9          # builder kinds of the s-wave solver's K2[Ω, ν, P] groups (stored under SG_PP2 / SG_PH2)
 
 
 class OracleSolver:
@@ -163,7 +164,12 @@ class OracleSolver:
         self.Lpp, self.Lph = zeros(self.F.γp.K2.shape), zeros(self.F.γp.K2.shape)
         for n in _CACHE_NAMES:
             setattr(self, n, zeros(self.F.γp.K3.shape))
-        self.grid = _Grid(self.T, self.L, self.nΠB, self.nΠF)
+        self.grid = _Grid(self.T, self.L, self.nΠB, self.nΠF, 0)
+        self._finish_init(compute_bubbles)
+
+    swave = False
+
+    def _finish_init(self, compute_bubbles):
         self.reset_sym_grp()
         if compute_bubbles:
             bubbles_real_space(self, self.Π0pp, self.Π0ph, self.G0)
@@ -179,8 +185,9 @@ class OracleSolver:
     def init_sym_grp(self):
         n = {SG_SIGMA: (self.nG, 0), SG_K1: (self.nK1, 0), SG_PP2: self.nK2, SG_PH2: self.nK2,
              SG_PP3: self.nK3, SG_PH3: self.nK3, SG_PPL3: self.nK3, SG_PHL3: self.nK3}
+        kind = {SG_PP2: SG_NL_PP2, SG_PH2: SG_NL_PH2} if self.swave else {}
         for w, (n0, n1) in n.items():
-            self.sg[w] = build_symmetry_group(w, n0, n1, self.LG if w == SG_SIGMA else self.L, self._sg_len(w))
+            self.sg[w] = build_symmetry_group(kind.get(w, w), n0, n1, self.LG if w == SG_SIGMA else self.L, self._sg_len(w))
 
     def set_symmetry_classes(self, which, offsets, index, ops):
         self.sg[which] = (np.ascontiguousarray(offsets, dtype=np.int64), np.ascontiguousarray(index, dtype=np.int64),
@@ -188,6 +195,35 @@ class OracleSolver:
 
     def caches(self):
         return [getattr(self, n) for n in _CACHE_NAMES]
+
+
+class OracleNLSolver(OracleSolver):
+    """CPU restatement of NL_ParquetSolver (src/nonlocal/ParquetSolver.jl:1-154): the s-wave solver, vertices with bosonic
+    momentum dependence only (K2[Ω, ν, P]), bubbles Π[Ω, ν, P] (mΠν_factor = 32 by default, :86)."""
+    swave = True
+
+    def __init__(self, nK1, nK2, nK3, L_, Gbare, G0, Σ0, F0, *, T, mΠν_factor=32, compute_bubbles=True):
+        self.T, self.L, self.NP = float(T), int(L_), int(L_) ** 2
+        self.nK1, self.nK2, self.nK3 = int(nK1), tuple(nK2), tuple(nK3)
+        self.Gbare = np.asfortranarray(Gbare, dtype=np.complex128)
+        self.nG = self.Gbare.shape[0] // 2
+        self.LG = int(round(np.sqrt(self.Gbare.shape[1])))
+        self.nΠB, self.nΠF = self.nK1, self.nK1 * int(mΠν_factor)
+        self.G0 = np.array(G0, dtype=np.complex128, order="F")
+        self.Σ0 = np.array(Σ0, dtype=np.complex128, order="F")
+        self.G = self.G0.copy(order="F")
+        self.Σ = self.Σ0.copy(order="F")
+        self.F0 = adopt(F0)
+        self.F = NL_Vertex(self.F0, self.T, nK1, nK2, nK3, self.L)
+        self.Fbuff = NL_Vertex(RefVertex(self.T, 0.0), self.T, nK1, nK2, nK3, self.L)
+        self.FL = NL_Vertex(RefVertex(self.T, 0.0), self.T, nK1, nK2, nK3, self.L)
+        shpΠ = (nB(self.nΠB), nF(self.nΠF), self.NP)
+        self.Π0pp, self.Π0ph, self.Πpp, self.Πph = zeros(shpΠ), zeros(shpΠ), zeros(shpΠ), zeros(shpΠ)
+        self.Lpp, self.Lph = zeros(self.F.γp.K2.shape), zeros(self.F.γp.K2.shape)
+        for n in _CACHE_NAMES:
+            setattr(self, n, zeros(self.F.γp.K3.shape))
+        self.grid = _Grid(self.T, self.L, self.nΠB, self.nΠF, 1)
+        self._finish_init(compute_bubbles)
 
 
 # ------------------------------------------------------------------------------- reference-named operations
@@ -242,11 +278,15 @@ def compute_hubbard_chemical_potential(occ_target, S, hubbard_params):
     return a if abs(fa) <= abs(fb) else b
 
 
-def bubbles_real_space(S, Πpp, Πph, G):
+def bubbles_real_space(S, Πpp, Πph, G, use_G_tail=True):
+    if S.swave:     # src/nonlocal/bubble.jl:87-158
+        lib().orc_nl_bubbles_real_space(_p(Πpp), _p(Πph), _p(G), S.nG, S.LG, C.byref(S.grid), int(use_G_tail))
+        return
     lib().orc_bubbles_real_space(_p(Πpp), _p(Πph), _p(G), S.nG, S.LG, C.byref(S.grid))
 
 
 def bubbles_momentum_space(S, Πpp, Πph, G):
+    assert not S.swave, "the s-wave solver's bubbles! is bubbles_real_space! (src/nonlocal/ParquetSolver.jl:294-297)"
     lib().orc_bubbles_momentum_space(_p(Πpp), _p(Πph), _p(G), S.nG, S.LG, C.byref(S.grid))
 
 
@@ -291,7 +331,7 @@ def build_K3_cache_mfRG(S, is_first_iteration):
 def BSE_K1(S, ch, is_mfRG=False, c0=0, c1=-1):
     sign, Sp = _sign_sp(ch)
     K1 = S.Fbuff.channel(ch).K1
-    lib().orc_bse_K1(_p(K1), S.nK1, C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)), C.byref(vertex_struct(S.FL)),
+    getattr(lib(), "orc_nl_bse_K1" if S.swave else "orc_bse_K1")(_p(K1), S.nK1, C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)), C.byref(vertex_struct(S.FL)),
                      _p(_pi(S, ch, True)), _p(_pi(S, ch, False)), C.byref(sg_struct(S.sg[SG_K1])), sign, ch, Sp, int(is_mfRG),
                      C.byref(S.grid), C.c_int64(c0), C.c_int64(c1))
     if ch == tCh:
@@ -302,7 +342,7 @@ def BSE_L_K2(S, ch, is_mfRG=False, c0=0, c1=-1):
     sign, Sp = _sign_sp(ch)
     K2 = S.FL.channel(ch).K2
     sg = S.sg[SG_PP2 if ch == pCh else SG_PH2]
-    lib().orc_bse_L_K2(_p(K2), S.nK2[0], S.nK2[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)),
+    getattr(lib(), "orc_nl_bse_L_K2" if S.swave else "orc_bse_L_K2")(_p(K2), S.nK2[0], S.nK2[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)),
                        _p(_pi(S, ch, True)), C.byref(sg_struct(sg)), sign, ch, Sp, C.byref(S.grid), C.c_int64(c0), C.c_int64(c1))
     if ch == tCh:
         _tfix(S.FL.γt.K2, S.FL.γa.K2)
@@ -312,7 +352,7 @@ def BSE_K2(S, ch, is_mfRG=False, c0=0, c1=-1):
     sign, Sp = _sign_sp(ch)
     K2 = S.Fbuff.channel(ch).K2
     sg = S.sg[SG_PP2 if ch == pCh else SG_PH2]
-    lib().orc_bse_K2(_p(K2), S.nK2[0], S.nK2[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)), C.byref(vertex_struct(S.FL)),
+    getattr(lib(), "orc_nl_bse_K2" if S.swave else "orc_bse_K2")(_p(K2), S.nK2[0], S.nK2[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)), C.byref(vertex_struct(S.FL)),
                      _p(_pi(S, ch, True)), _p(_pi(S, ch, False)), C.byref(sg_struct(sg)), sign, ch, Sp, int(is_mfRG),
                      C.byref(S.grid), C.c_int64(c0), C.c_int64(c1))
     if ch == tCh:       # BSEa_K2.jl:130-135
@@ -409,7 +449,7 @@ def BSE_K3_1loop(S, ch, is_mfRG=False):
 
 def SDE_channel_L(S, Lout, Π, V, level, is_pp, c0=0, c1=-1):
     sg = S.sg[SG_PP2 if is_pp else SG_PH2]
-    lib().orc_sde_L(_p(Lout), S.nK2[0], S.nK2[1], C.byref(vertex_struct(V)), level, _p(Π), C.byref(sg_struct(sg)), int(is_pp),
+    getattr(lib(), "orc_nl_sde_L" if S.swave else "orc_sde_L")(_p(Lout), S.nK2[0], S.nK2[1], C.byref(vertex_struct(V)), level, _p(Π), C.byref(sg_struct(sg)), int(is_pp),
                     C.byref(S.grid), C.c_int64(c0), C.c_int64(c1))
 
 
@@ -421,7 +461,7 @@ def SDE_compute(S, G, Πpp, Πph, V, level, include_U2=True, include_Hartree=Tru
     SDE_channel_L(S, S.Lph, Πph, V, level, False)
     Σ = zeros(S.Σ.shape)
     sgΣ = sg_struct(S.sg[SG_SIGMA])
-    lib().orc_sde_real_space(_p(Σ), S.nG, S.LG, _p(G), S.nG, S.LG, _p(S.Lpp), _p(S.Lph), S.nK2[0], S.nK2[1], C.byref(sgΣ), C.byref(S.grid))
+    getattr(lib(), "orc_nl_sde_inner" if S.swave else "orc_sde_real_space")(_p(Σ), S.nG, S.LG, _p(G), S.nG, S.LG, _p(S.Lpp), _p(S.Lph), S.nK2[0], S.nK2[1], C.byref(sgΣ), C.byref(S.grid))
     if isinstance(chain[level], RefVertex):
         Σ *= 1 / 3
     if include_U2:
@@ -465,6 +505,7 @@ def SDE(S, strategy="scPA", include_U2=True, include_Hartree=True):
 def iterate_solver(S, strategy="fdPA", update_Σ=True, compute_Hartree=True):
     """iterate_solver!(S; strategy, update_Σ, compute_Hartree): src/solve.jl:4-116"""
     assert strategy in ("fdPA", "scPA", "scPA_new", "fdPA_new", "fdPA_1loop"), "Calculation strategy unknown"
+    assert not S.swave or strategy in ("fdPA", "scPA"), "s-wave solver: only the fdPA / scPA strategies are restated"
     order = (pCh, aCh, tCh)
     if update_Σ:
         Dyson(S)

@@ -45,11 +45,13 @@ def _fill_colmajor(a, x):
 
 
 class OChannel:
-    def __init__(self, T, numK1, numK2, numK3, L=None):
+    def __init__(self, T, numK1, numK2, numK3, L=None, swave=False):
+        # swave: NL_Channel of src/nonlocal/channel.jl:3-51, K2[Ω, ν, P] (bosonic momentum only)
         self.T, self.numK1, self.numK2, self.numK3 = float(T), int(numK1), (int(numK2[0]), int(numK2[1])), (int(numK3[0]), int(numK3[1]))
         self.L = None if L is None else int(L)
+        self.swave = bool(swave)
         mom1 = () if L is None else (self.L ** 2,)
-        mom2 = () if L is None else (self.L ** 2, self.L ** 2)
+        mom2 = () if L is None else ((self.L ** 2,) if swave else (self.L ** 2, self.L ** 2))
         self.K1 = zeros((n_boson(self.numK1),) + mom1)
         self.K2 = zeros((n_boson(self.numK2[0]), n_fermion(self.numK2[1])) + mom2)
         self.K3 = zeros((n_boson(self.numK3[0]), n_fermion(self.numK3[1]), n_fermion(self.numK3[1])) + mom1)
@@ -171,19 +173,29 @@ class ONL2_Vertex(_OVertexBase):
             setattr(self, n, OChannel(T, numK1, numK2, numK3, L))
 
 
+class ONL_Vertex(_OVertexBase):
+    """NL_Vertex (src/nonlocal/vertex.jl:1-37): bosonic momentum dependence only"""
+    def __init__(self, F0, T, numK1, numK2, numK3, L):
+        self.F0 = F0
+        self.L = int(L)
+        for n in self.ORDER:
+            setattr(self, n, OChannel(T, numK1, numK2, numK3, L, swave=True))
+
+
 # the names oracle.py uses
-RefVertex, Vertex, NL2_Vertex = ORefVertex, OVertex, ONL2_Vertex
+RefVertex, Vertex, NL2_Vertex, NL_Vertex = ORefVertex, OVertex, ONL2_Vertex, ONL_Vertex
 
 
 def adopt(V):
     """deep copy of a vertex chain held in foreign containers (same attribute names) into the oracle's own types"""
-    if isinstance(V, (ORefVertex, OVertex, ONL2_Vertex)):
+    if isinstance(V, (ORefVertex, OVertex, ONL2_Vertex, ONL_Vertex)):
         return V
     if hasattr(V, "Fp_p"):
         return ORefVertex(V.T, V.U, V.numK3, V.Fp_p, V.Fp_x, V.Ft_p, V.Ft_x)
     F0 = adopt(V.F0)
     if getattr(V, "L", None) is not None and V.γp.K1.ndim == 2:
-        out = ONL2_Vertex(F0, V.T, V.numK1, V.numK2, V.numK3, V.L)
+        cls = ONL_Vertex if V.γp.K2.ndim == 3 else ONL2_Vertex
+        out = cls(F0, V.T, V.numK1, V.numK2, V.numK3, V.L)
     else:
         out = OVertex(F0, V.T, V.numK1, V.numK2, V.numK3)
     out.set(V)
