@@ -5,10 +5,10 @@ reference's NL2_ParquetSolver interface (solver.py).  Import it as ``fddgasolver
 name contains a dot; the top-level shim ``fddgasolver_jl_b200.py`` registers it under that name).
 """
 from ._lib import FdgaError, LIB_PATH, EXPORTS  # noqa: F401
-from .types import (pCh, tCh, aCh, pSp, xSp, dSp, Channel, NL2_Channel, RefVertex, Vertex, NL2_Vertex,  # noqa: F401
+from .types import (pCh, tCh, aCh, pSp, xSp, dSp, Channel, NL2_Channel, NL_Channel, RefVertex, Vertex, NL2_Vertex, NL_Vertex,  # noqa: F401
                     vertex_chain, nB, nF)
 from .models import hubbard_bare_Green, hubbard_band, siam_bare_Green  # noqa: F401
-from .solver import (NL2_ParquetSolver, ParquetSolver, init_sym_grp, Dyson, compute_occupation, bubbles, bubbles_real_space,  # noqa: F401
+from .solver import (NL2_ParquetSolver, NL_ParquetSolver, ParquetSolver, init_sym_grp, Dyson, compute_occupation, bubbles, bubbles_real_space,  # noqa: F401
                      bubbles_momentum_space, build_K3_cache, build_K3_cache_mfRG, BSE_L_K2, BSE_L_K3, BSE_K1,
                      BSE_K2, BSE_K3, BSE_K1_new, BSE_K2_new, BSE_K1_1loop, BSE_K2_1loop, BSE_K3_1loop, SDE, SDE_channel_L, iterate_solver, iterate_solver_stepwise, fixed_point, solve, mfRGLinearMap,
                      dqgmres, symmetrize_solver, fixed_point_preconditioned,
@@ -17,5 +17,5 @@ from .solver import (NL2_ParquetSolver, ParquetSolver, init_sym_grp, Dyson, comp
 from . import h5min, io, synthetic, types  # noqa: F401,E402
 from .io import load_triqs_data  # noqa: F401,E402
 from .flow import bare_Green_Ω_flow  # noqa: F401,E402
-from .synthetic import (parquet_solver_hubbard_parquet_approximation_NL2, parquet_solver_siam_parquet_approximation, synthetic_local_vertex,  # noqa: F401
+from .synthetic import (parquet_solver_hubbard_parquet_approximation_NL2, parquet_solver_hubbard_parquet_approximation, parquet_solver_siam_parquet_approximation, synthetic_local_vertex,  # noqa: F401
                         wu_point_solver, wu_point_inputs, randomize_vertex)

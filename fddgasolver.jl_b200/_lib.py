@@ -15,11 +15,12 @@ LIB_PATH = os.environ.get("FDGA_LIB_PATH", os.path.join(_HERE, "libfdga.so"))   
 FDGA_MAX_LEVELS = 6
 PCH, TCH, ACH = 0, 1, 2
 K1, K2, K3 = 0, 1, 2
-LV_NL2, LV_LOCAL, LV_CORE = 0, 1, 2
+LV_NL2, LV_LOCAL, LV_CORE, LV_NL = 0, 1, 2, 3
 V_FL, V_FBUFF = 100, 101
 G, G0, GBARE, SIGMA, SIGMA0 = 0, 1, 2, 3, 4
 PI0PP, PI0PH, PIPP, PIPH = 0, 1, 2, 3
 SG_SIGMA, SG_K1, SG_PP2, SG_PH2, SG_PP3, SG_PH3, SG_PPL3, SG_PHL3 = range(8)
+SG_NL_PP2, SG_NL_PH2 = 8, 9       # builder-only ids: K2[Ω, ν, P] groups of the s-wave solver
 SCPA, FDPA, SCPA_NEW, FDPA_NEW, FDPA_1LOOP = 0, 1, 2, 3, 4
 T_NAMES = ["cache", "L_K2", "L_K3", "K1", "K2", "K3", "sde_L", "sde_rs", "sde_U2", "bubble",
            "right", "swave", "expand", "misc", "comm", "column_K2", "krylov"]

@@ -3,6 +3,7 @@
 // SDE! (src/SDE.jl:3-48), mfRGLinearMap (src/mfRG.jl:34-89).
 #include "../../include/fdga.h"
 #include "fdga_qlane.cuh"
+#include "fdga_swave.cuh"
 #include "fdga_krylov.cuh"
 
 #include <cstdio>
@@ -127,6 +128,8 @@ struct fdga_ctx {
     C* kryV; C* kryP; C* kryW; C* kryX; C* kryH; C* kryPart; unsigned int* kryTicket; C* kryHhost; int kry_mem;
     C* itpA; C* itpB; size_t lenItp;   // ping-pong of fdga_interpolate_* when the bubble-sized scratch is too small (coarsening)
     C* PiMixed[2];           // Pipp_mixed, Piph_mixed of solve_using_mfRG! (fdga_mix_bubbles / fdga_update_reference)
+    // s-wave solver (NL_ParquetSolver): lev[0] is an FDGA_LV_NL level; bubbles are Pi[W,w,P] and live in Pisw[] (fdga_swave.cuh)
+    bool swave; C* swScratch[2];
     C* Rt3[3]; int rt_kind[3]; // per-channel right factors (W on the bubble mesh) reused between BSE_K1! and BSE_K2!
     std::string err, launch_err;
 };
@@ -164,11 +167,12 @@ struct Scope {
     NOTE_LAUNCH(#kernel); \
     ctx->n_launch[cat]++; ctx->total_launches++; } while (0)
 
-static size_t lenK(const fdga_level_desc& d, int cls, int NP, bool nl2) {
+static size_t lenK(const fdga_level_desc& d, int cls, int NP) {
     size_t nB1 = 2 * d.nK1 - 1, nB2 = 2 * d.nK2[0] - 1, nF2 = 2 * d.nK2[1], nB3 = 2 * d.nK3[0] - 1, nF3 = 2 * d.nK3[1];
-    if (cls == 0) return nB1 * (nl2 ? NP : 1);
-    if (cls == 1) return nB2 * nF2 * (nl2 ? (size_t)NP * NP : 1);
-    return nB3 * nF3 * nF3 * (nl2 ? NP : 1);
+    const bool mom = d.type == FDGA_LV_NL2 || d.type == FDGA_LV_NL;
+    if (cls == 0) return nB1 * (mom ? NP : 1);
+    if (cls == 1) return nB2 * nF2 * (d.type == FDGA_LV_NL2 ? (size_t)NP * NP : (mom ? (size_t)NP : 1));
+    return nB3 * nF3 * nF3 * (mom ? NP : 1);
 }
 
 static int alloc_level(fdga_ctx* ctx, LevelBuf& lb, const fdga_level_desc& d) {
@@ -182,7 +186,7 @@ static int alloc_level(fdga_ctx* ctx, LevelBuf& lb, const fdga_level_desc& d) {
         return 0;
     }
     bool nl2 = d.type == FDGA_LV_NL2;
-    for (int cls = 0; cls < 3; cls++) lb.len[cls] = lenK(d, cls, NP, nl2);
+    for (int cls = 0; cls < 3; cls++) lb.len[cls] = lenK(d, cls, NP);
     lb.blocklen = 3 * (lb.len[0] + lb.len[1] + lb.len[2]);
     CK(cudaMalloc(&lb.block, lb.blocklen * sizeof(C))); CK(cudaMemsetAsync(lb.block, 0, lb.blocklen * sizeof(C), ctx->stream));
     {
@@ -195,6 +199,10 @@ static int alloc_level(fdga_ctx* ctx, LevelBuf& lb, const fdga_level_desc& d) {
                             (size_t)(2 * d.nK2[0] - 1) * (2 * d.nK2[1]), (size_t)(2 * d.nK3[0] - 1) * (2 * d.nK3[1]) * (2 * d.nK3[1]) };
             for (int j = 0; j < 4; j++) CK(cudaMalloc(&lb.sw[ch][j], n[j] * sizeof(C)));
             CK(cudaMalloc(&lb.K1h[ch], n[0] * NP * sizeof(C)));
+        } else if (d.type == FDGA_LV_NL) {
+            // NL level: the table of fermionic-momentum means K2swk[W,v,P] IS K2 (dev_level aliases it); K1sw, K2sww, K3sw are P-means
+            size_t n[4] = { (size_t)(2 * d.nK1 - 1), 0, (size_t)(2 * d.nK2[0] - 1) * (2 * d.nK2[1]), (size_t)(2 * d.nK3[0] - 1) * (2 * d.nK3[1]) * (2 * d.nK3[1]) };
+            for (int j = 0; j < 4; j++) if (n[j]) CK(cudaMalloc(&lb.sw[ch][j], n[j] * sizeof(C)));
         }
     }
     return 0;
@@ -209,12 +217,14 @@ static void free_level(LevelBuf& lb) {
 
 static DevLevel dev_level(const LevelBuf& lb) {
     DevLevel d; memset(&d, 0, sizeof(d));
-    d.type = lb.d.type; d.nK1 = lb.d.nK1; d.nK2b = lb.d.nK2[0]; d.nK2f = lb.d.nK2[1]; d.nK3b = lb.d.nK3[0]; d.nK3f = lb.d.nK3[1];
+    d.type = lb.d.type == FDGA_LV_NL ? (int)LV_NL2 : lb.d.type;      // evaluated through the kSW forms only (fdga_swave.cuh)
+    d.nK1 = lb.d.nK1; d.nK2b = lb.d.nK2[0]; d.nK2f = lb.d.nK2[1]; d.nK3b = lb.d.nK3[0]; d.nK3f = lb.d.nK3[1];
     d.U = mkC(lb.d.U_re, lb.d.U_im);
     for (int ch = 0; ch < 3; ch++) {
         d.ch[ch].K1 = lb.K[ch][0]; d.ch[ch].K2 = lb.K[ch][1]; d.ch[ch].K3 = lb.K[ch][2];
         d.ch[ch].K1sw = lb.sw[ch][0]; d.ch[ch].K2swk = lb.sw[ch][1]; d.ch[ch].K2sww = lb.sw[ch][2]; d.ch[ch].K3sw = lb.sw[ch][3];
         d.ch[ch].K1h = lb.K1h[ch];
+        if (lb.d.type == FDGA_LV_NL) d.ch[ch].K2swk = lb.K[ch][1];
         for (int j = 0; j < 4; j++) d.ch[ch].K2m[j] = lb.mom[ch][j];
         d.ch[ch].K3m = lb.mom[ch][ML_K3]; d.ch[ch].K1m = lb.mom[ch][ML_K1];
     }
@@ -257,10 +267,17 @@ static C bareU(fdga_ctx* ctx) { const fdga_level_desc& d = ctx->lev[ctx->nlev - 
 static int refresh_swave(fdga_ctx* ctx) {
     for (int l = 0; l < ctx->nlev; l++) {          // S.FL is never evaluated at kSW: its tables are not needed
         LevelBuf& lb = ctx->lev[l];
-        if (lb.d.type != FDGA_LV_NL2 || !lb.sw_dirty) continue;
+        if ((lb.d.type != FDGA_LV_NL2 && lb.d.type != FDGA_LV_NL) || !lb.sw_dirty) continue;
         Scope sc(ctx, FDGA_T_SWAVE);
         DevLevel dl = dev_level(lb);
         SwOut out; for (int ch = 0; ch < 3; ch++) for (int j = 0; j < 4; j++) out.p[ch][j] = lb.sw[ch][j];
+        if (lb.d.type == FDGA_LV_NL) {
+            long long n = (long long)(2 * lb.d.nK1 - 1) + (long long)(2 * lb.d.nK2[0] - 1) * (2 * lb.d.nK2[1])
+                        + (long long)(2 * lb.d.nK3[0] - 1) * (2 * lb.d.nK3[1]) * (2 * lb.d.nK3[1]);
+            LAUNCH(FDGA_T_SWAVE, swave_tables_nl_kernel, dim3(nblk(n, 128), 3), 128, dl, ctx->g.NP, out);
+            lb.sw_dirty = false;
+            continue;
+        }
         long long n = (long long)(2 * lb.d.nK1 - 1) + (long long)(2 * lb.d.nK2[0] - 1) * (2 * lb.d.nK2[1]) * ctx->g.NP
                     + (long long)(2 * lb.d.nK3[0] - 1) * (2 * lb.d.nK3[1]) * (2 * lb.d.nK3[1]);
         long long n2 = (long long)(2 * lb.d.nK2[0] - 1) * (2 * lb.d.nK2[1]);
@@ -299,7 +316,7 @@ static int refresh_k1h(fdga_ctx* ctx) {
 }
 // ---- q-lane kernel: momentum-fastest copies of the vertex tables -------------------------------------------------------
 static bool qlane_enabled(fdga_ctx* ctx) {
-    if (ctx->opt_local || ctx->opt_generic || ctx->opt_qlane == 0 || ctx->g.L > 64) return false;      // rep descriptors pack momenta in 8 / 16 bits
+    if (ctx->swave || ctx->opt_local || ctx->opt_generic || ctx->opt_qlane == 0 || ctx->g.L > 64) return false;      // rep descriptors pack momenta in 8 / 16 bits
     if (ctx->opt_qlane == 1) return true;
     return ctx->g.NP >= 16;
 }
@@ -347,6 +364,7 @@ static int refresh_mom_all(fdga_ctx* ctx, unsigned need = MOM_ALL) {
 static int ensure_slabs(fdga_ctx* ctx);
 // the bubble `which` in the reference's layout, materialised on demand
 static int ensure_pi_full(fdga_ctx* ctx, int which) {
+    if (ctx->swave) FAIL("internal: the s-wave solver has no four-index bubbles");
     if (!ctx->Pi[which]) { CK(cudaMalloc(&ctx->Pi[which], ctx->lenPi * sizeof(C))); ctx->pi_full_valid[which] = false; }
     if (ctx->pi_full_valid[which]) return 0;
     if (ctx->pi_src[which] == PI_GHAT) {
@@ -369,6 +387,7 @@ static int ensure_pi_full(fdga_ctx* ctx, int which) {
 }
 // compact slabs + s-wave mean of bubble `which`, refreshed lazily
 static int refresh_pi(fdga_ctx* ctx, int which) {
+    if (ctx->swave) return 0;       // Pisw[which] is the bubble itself
     if (ensure_slabs(ctx)) return 1;
     if (!ctx->pi_dirty[which]) return 0;
     Scope sc(ctx, FDGA_T_MISC);
@@ -521,6 +540,7 @@ static ColDev col_dev(const SymGroup& s) {
 // K2 columns.  Everything else of Rt stays unwritten (and unread).
 static int ensure_slabs(fdga_ctx* ctx) {
     if (!ctx->slabs_dirty) return 0;
+    if (ctx->swave) { ctx->slabs_dirty = false; return 0; }
     const Grid& g = ctx->g;
     const int nB1 = 2 * g.nK1 - 1, nB2 = 2 * g.nK2b - 1, nF2 = 2 * g.nK2f, NP = g.NP;
     for (int kind = 0; kind < 4; kind++) {
@@ -602,16 +622,22 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) { g_create_error = std::string("no CUDA device available (libfdga has no CPU fallback): ") + cudaGetErrorString(e); return 2; }
     if (device < 0 || device >= ndev) { g_create_error = "invalid device index"; return 2; }
-    if (dims->nlev < 2 || dims->nlev > FDGA_MAX_LEVELS || dims->lev[0].type != FDGA_LV_NL2 || dims->lev[dims->nlev - 1].type != FDGA_LV_CORE) {
-        g_create_error = "dims: need lev[0] = NL2 and lev[nlev-1] = CORE, 2 <= nlev <= FDGA_MAX_LEVELS"; return 2; }
+    const bool swave = dims->lev[0].type == FDGA_LV_NL;
+    if (dims->nlev < 2 || dims->nlev > FDGA_MAX_LEVELS || (dims->lev[0].type != FDGA_LV_NL2 && !swave) || dims->lev[dims->nlev - 1].type != FDGA_LV_CORE) {
+        g_create_error = "dims: need lev[0] = NL2 (or NL for the s-wave solver) and lev[nlev-1] = CORE, 2 <= nlev <= FDGA_MAX_LEVELS"; return 2; }
     for (int l = 1; l < dims->nlev - 1; l++) if (dims->lev[l].type == FDGA_LV_CORE) { g_create_error = "dims: CORE level must be last"; return 2; }
-    for (int l = 1; l < dims->nlev - 1; l++) if (dims->lev[l].type == FDGA_LV_NL2 && dims->lev[l - 1].type != FDGA_LV_NL2) { g_create_error = "dims: NL2 levels must precede LOCAL levels"; return 2; }
+    for (int l = 1; l < dims->nlev - 1; l++) {
+        const int t = dims->lev[l].type;
+        if (t != FDGA_LV_NL2 && t != FDGA_LV_NL && t != FDGA_LV_LOCAL) { g_create_error = "dims: unknown level type"; return 2; }
+        if (t != FDGA_LV_LOCAL && t != dims->lev[0].type) { g_create_error = "dims: the momentum-dependent levels of a chain must all be NL2 (NL2 solver) or all NL (s-wave solver)"; return 2; }
+        if (t != FDGA_LV_LOCAL && dims->lev[l - 1].type == FDGA_LV_LOCAL) { g_create_error = "dims: NL2 / NL levels must precede LOCAL levels"; return 2; }
+    }
     const fdga_level_desc& d0 = dims->lev[0];
     if (dims->nPiB != d0.nK1) { g_create_error = "dims: bubble bosonic mesh must equal the K1 mesh (nPiB == nK1)"; return 2; }
     if (!(d0.nK1 > d0.nK2[0] && d0.nK1 > d0.nK2[1] && d0.nK2[0] >= d0.nK3[0] && d0.nK2[1] >= d0.nK3[1] && dims->nPiF >= d0.nK2[1])) {
         g_create_error = "dims: mesh constraints violated (src/nonlocal_2/channel.jl:26-33)"; return 2; }
     fdga_ctx* ctx = new fdga_ctx();
-    ctx->dims = *dims; ctx->device = device; ctx->nlev = dims->nlev;
+    ctx->dims = *dims; ctx->device = device; ctx->nlev = dims->nlev; ctx->swave = swave; ctx->swScratch[0] = ctx->swScratch[1] = nullptr;
     ctx->nranks = 1; ctx->rank = 0; ctx->comm = nullptr; memset(&ctx->nccl, 0, sizeof(ctx->nccl));
     ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0; ctx->opt_generic = 0; ctx->opt_hartree_once = 0; ctx->opt_local = 0; ctx->opt_direct_k1 = 0; ctx->opt_qlane = getenv("FDGA_QLANE") ? atoi(getenv("FDGA_QLANE")) : -1; ctx->defer = false;
     memset(ctx->t_ms, 0, sizeof(ctx->t_ms)); memset(ctx->n_launch, 0, sizeof(ctx->n_launch));
@@ -633,15 +659,17 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < 3; i++) CKC(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
     for (int l = 0; l < ctx->nlev; l++) if (alloc_level(ctx, ctx->lev[l], dims->lev[l])) { g_create_error = ctx->err; delete ctx; return 1; }
-    fdga_level_desc dz = d0; dz.type = FDGA_LV_NL2;
+    fdga_level_desc dz = d0;
     if (alloc_level(ctx, ctx->FL, dz) || alloc_level(ctx, ctx->Fbuff, dz)) { g_create_error = ctx->err; delete ctx; return 1; }
     ctx->lenG = (size_t)2 * g.nG * g.LG * g.LG;
     for (int i = 0; i < 5; i++) { CKC(cudaMalloc(&ctx->G[i], ctx->lenG * sizeof(C))); CKC(cudaMemsetAsync(ctx->G[i], 0, ctx->lenG * sizeof(C), ctx->stream)); }
     ctx->lenPi = (size_t)(2 * g.nPiB - 1) * (2 * g.nPiF) * g.NP * g.NP;
     ctx->lenPisw = (size_t)(2 * g.nPiB - 1) * (2 * g.nPiF) * g.NP;
+    if (swave) ctx->lenPi = ctx->lenPisw;      // Pi[W, w, P] (NL_MF_Pi, src/types.jl)
     for (int i = 0; i < 4; i++) {      // Pi[i] (full layout) and PiT[i] (compact slabs) are allocated on demand / by ensure_slabs
         ctx->Pi[i] = nullptr; ctx->PiT[i] = nullptr; ctx->pi_src[i] = PI_NONE; ctx->pi_full_valid[i] = false;
         CKC(cudaMalloc(&ctx->Pisw[i], ctx->lenPisw * sizeof(C)));
+        if (swave) CKC(cudaMemsetAsync(ctx->Pisw[i], 0, ctx->lenPisw * sizeof(C), ctx->stream));
         ctx->pi_dirty[i] = true;
     }
     ctx->lenK3 = ctx->lev[0].len[2];
@@ -701,6 +729,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (int i = 0; i < 10; i++) cudaFree(ctx->cache[i]);
     cudaFree(ctx->L[0]); cudaFree(ctx->L[1]); cudaFree(ctx->scratchA); cudaFree(ctx->scratchB); cudaFree(ctx->scratchBig);
     cudaFree(ctx->Ghat[0]); cudaFree(ctx->Ghat[1]); cudaFree(ctx->GR); cudaFree(ctx->GRm); cudaFree(ctx->SigR); cudaFree(ctx->SigTmp); cudaFree(ctx->SigAcc);
+    cudaFree(ctx->swScratch[0]); cudaFree(ctx->swScratch[1]);
     cudaFree(ctx->PiMixed[0]); cudaFree(ctx->PiMixed[1]); cudaFree(ctx->itpA); cudaFree(ctx->itpB);
     cudaFree(ctx->kryV); cudaFree(ctx->kryP); cudaFree(ctx->kryW); cudaFree(ctx->kryX); cudaFree(ctx->kryH); cudaFree(ctx->kryPart); cudaFree(ctx->kryTicket); if (ctx->kryHhost) cudaFreeHost(ctx->kryHhost);
     cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); for (int i = 0; i < 3; i++) { cudaFree(ctx->TtabL[i]); cudaFree(ctx->OwnTabL[i]); cudaFree(ctx->RtotL[i]); cudaFree(ctx->ConvTabL[i]); cudaFree(ctx->RtL[i]); } cudaFree(ctx->SigR2); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) { cudaFree(ctx->d_slabs[i]); cudaFree(ctx->d_slabmap[i]); }
@@ -721,6 +750,7 @@ int fdga_set_option(fdga_ctx* ctx, int opt, int value) {
     if (opt == FDGA_OPT_FD_HARTREE_ONCE) { ctx->opt_hartree_once = value != 0; return 0; }
     if (opt == FDGA_OPT_LOCAL_SOLVER) {
         if (value && (ctx->g.L != 1 || ctx->g.LG != 1)) FAIL("FDGA_OPT_LOCAL_SOLVER needs nq = LG = 1");
+        if (value && ctx->swave) FAIL("FDGA_OPT_LOCAL_SOLVER: not for an s-wave (NL) context");
         ctx->opt_local = value != 0; invalidate_rt(ctx); return 0;
     }
     if (opt == FDGA_OPT_DIRECT_K1) { ctx->opt_direct_k1 = value != 0; return 0; }
@@ -838,6 +868,11 @@ int fdga_set_bubble(fdga_ctx* ctx, int which, const fdga_c64* host, int64_t n) {
     CK(cudaSetDevice(ctx->device));
     if (which < 0 || which >= 4) FAIL("fdga_set_bubble: bad selector");
     if ((size_t)n != ctx->lenPi) FAIL("fdga_set_bubble: length mismatch");
+    if (ctx->swave) {
+        CK(cudaMemcpyAsync(ctx->Pisw[which], host, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
     if (!ctx->Pi[which]) CK(cudaMalloc(&ctx->Pi[which], ctx->lenPi * sizeof(C)));
     CK(cudaMemcpyAsync(ctx->Pi[which], host, n * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -848,6 +883,11 @@ int fdga_get_bubble(fdga_ctx* ctx, int which, fdga_c64* host, int64_t n) {
     CK(cudaSetDevice(ctx->device));
     if (which < 0 || which >= 4) FAIL("fdga_get_bubble: bad selector");
     if ((size_t)n != ctx->lenPi) FAIL("fdga_get_bubble: length mismatch");
+    if (ctx->swave) {
+        CK(cudaMemcpyAsync(host, ctx->Pisw[which], n * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
     if (ensure_pi_full(ctx, which)) return 1;
     CK(cudaMemcpyAsync(host, ctx->Pi[which], n * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -911,7 +951,7 @@ static int rebuild_sg(fdga_ctx* ctx, int which) {
     CK(cudaMemcpy(s.d_ops, ops.data(), nmem, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s.d_member_class, mclass.data(), nmem * sizeof(int), cudaMemcpyHostToDevice));
     s.set = true; ctx->slabs_dirty = true;
-    if (which == FDGA_SG_PP2 || which == FDGA_SG_PH2) return build_columns(ctx, s);
+    if ((which == FDGA_SG_PP2 || which == FDGA_SG_PH2) && !ctx->swave) return build_columns(ctx, s);
     return 0;
 }
 int fdga_set_symmetry_classes(fdga_ctx* ctx, int which, int64_t nclasses, const int64_t* offsets, const int64_t* index, const uint8_t* ops) {
@@ -935,7 +975,7 @@ int fdga_set_symmetry_classes(fdga_ctx* ctx, int which, int64_t nclasses, const 
     return rebuild_sg(ctx, which);
 }
 int fdga_build_symmetry_group(int which_sg, int n0, int n1, int nq, int64_t* offsets, int64_t* index, uint8_t* ops, int64_t* nclasses) {
-    if (which_sg < 0 || which_sg >= FDGA_SG_COUNT) return 1;
+    if (which_sg < 0 || which_sg > FDGA_SG_NL_PH2) return 1;
     *nclasses = fdga_symgroup_build_host(which_sg, n0, n1, nq, offsets, index, ops);
     return 0;
 }
@@ -1065,6 +1105,19 @@ int fdga_bubbles_real_space(fdga_ctx* ctx, int reference) {
     int ipp = reference ? FDGA_PI0PP : FDGA_PIPP, iph = reference ? FDGA_PI0PH : FDGA_PIPH;
     const C* Gsrc = ctx->G[reference ? FDGA_G0 : FDGA_G];
     if (dft2_G(ctx, Gsrc, ctx->GR, ctx->SigTmp, -1, 1.0 / ((double)g.LG * g.LG), FDGA_T_BUBBLE)) return 1;
+    if (ctx->swave) {       // bubbles_real_space!(::NL_MF_Pi; use_G_tail = true): src/nonlocal/bubble.jl:87-158
+        for (int i = 0; i < 2; i++) if (!ctx->swScratch[i]) CK(cudaMalloc(&ctx->swScratch[i], ctx->lenPisw * sizeof(C)));
+        const long long pre = (long long)(2 * g.nPiB - 1) * (2 * g.nPiF), n = pre * g.NP;
+        LAUNCH(FDGA_T_BUBBLE, sw_bubbles_rs_kernel, nblk(n, 128), 128, ctx->GR, ctx->swScratch[0], ctx->swScratch[1], g, 1);
+        for (int i = 0; i < 2; i++) {      // back transform over the two momentum axes; Pisw[] as the intermediate
+            C* dst = ctx->Pisw[i == 0 ? ipp : iph];
+            LAUNCH(FDGA_T_BUBBLE, dft_axis_kernel, nblk(n, 128), 128, ctx->swScratch[i], dst, pre, g.L, (long long)g.L, +1, 1.0, ctx->twL);
+            LAUNCH(FDGA_T_BUBBLE, dft_axis_kernel, nblk(n, 128), 128, dst, ctx->swScratch[i], pre * g.L, g.L, 1LL, +1, 1.0, ctx->twL);
+            CK(cudaMemcpyAsync(dst, ctx->swScratch[i], (size_t)n * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        CK(cudaGetLastError());
+        return 0;
+    }
     static const bool legacy = getenv("FDGA_BUBBLES_RS") ? atoi(getenv("FDGA_BUBBLES_RS")) != 0 : false;
     if (!legacy) {      // product form on the coarse-grained Green function (fdga_kernels.cuh); the slabs are filled lazily (refresh_pi)
         C* Ghat = ctx->Ghat[reference ? 1 : 0];
@@ -1088,6 +1141,7 @@ int fdga_bubbles_real_space(fdga_ctx* ctx, int reference) {
 int fdga_bubbles_local(fdga_ctx* ctx, int reference) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->g.L != 1 || ctx->g.LG != 1) FAIL("fdga_bubbles_local: needs nq = LG = 1");
+    if (ctx->swave) FAIL("fdga_bubbles_local: not for an s-wave (NL) context");
     Scope sc(ctx, FDGA_T_BUBBLE);
     int ipp = reference ? FDGA_PI0PP : FDGA_PIPP, iph = reference ? FDGA_PI0PH : FDGA_PIPH;
     for (int w : {ipp, iph}) { if (!ctx->Pi[w]) CK(cudaMalloc(&ctx->Pi[w], ctx->lenPi * sizeof(C))); ctx->pi_src[w] = PI_FULL; ctx->pi_full_valid[w] = true; }
@@ -1100,6 +1154,7 @@ int fdga_bubbles_local(fdga_ctx* ctx, int reference) {
 int fdga_bubbles_momentum_space(fdga_ctx* ctx, int reference) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->g.LG % ctx->g.L != 0) FAIL("fdga_bubbles_momentum_space: LG must be a multiple of nq");
+    if (ctx->swave) FAIL("fdga_bubbles_momentum_space: the s-wave solver's bubbles! is bubbles_real_space! (src/nonlocal/ParquetSolver.jl:294-297)");
     Scope sc(ctx, FDGA_T_BUBBLE);
     int ipp = reference ? FDGA_PI0PP : FDGA_PIPP, iph = reference ? FDGA_PI0PH : FDGA_PIPH;
     for (int w : {ipp, iph}) { if (!ctx->Pi[w]) CK(cudaMalloc(&ctx->Pi[w], ctx->lenPi * sizeof(C))); ctx->pi_src[w] = PI_FULL; ctx->pi_full_valid[w] = true; }
@@ -1394,6 +1449,7 @@ static int flush_pending(fdga_ctx* ctx) {
 // 58 ms without), so the default (FDGA_OPT_SERIAL = 0) decides by the size of one bubble-shaped array.
 static bool lanes_enabled(fdga_ctx* ctx) {
     if (ctx->profile || ctx->opt_generic || ctx->opt_serial == 1) return false;
+    if (ctx->swave) return ctx->opt_serial == 2 || ctx->opt_serial == 0;      // small kernels: the three channels always overlap
     if (ctx->opt_serial == 2) return true;
     static const double lim_mb = getenv("FDGA_LANES_MAX_MB") ? atof(getenv("FDGA_LANES_MAX_MB")) : 160.0;
     // size of one slab-shaped array as stored (compact: only the slabs this rank reads)
@@ -1403,6 +1459,7 @@ static bool lanes_enabled(fdga_ctx* ctx) {
 // everything the lanes read but do not own must be current before the fork
 static int lanes_fork(fdga_ctx* ctx, unsigned mom_need = MOM_ALL) {
     if (!lanes_enabled(ctx) || ctx->forked) return 0;
+    if (ctx->swave && refresh_swave(ctx)) return 1;
     for (int ch = 0; ch < 3; ch++) if (ensure_pi(ctx, ch)) return 1;
     if (refresh_fsum(ctx) || refresh_k1h(ctx) || refresh_mom_all(ctx, mom_need) || ensure_slabs(ctx)) return 1;
     CK(cudaEventRecord(ctx->ev_fork, ctx->main_stream));
@@ -1425,9 +1482,25 @@ static int bse_K1_impl(fdga_ctx* ctx, int ch, int mfrg, int rk_fd) {
     NEED_SG(FDGA_SG_K1);
     if (ensure_pi(ctx, ch)) return 1;
     DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0), FL = chain_FL(ctx);
-    if (cached_right(ctx, ch, mfrg ? RK_MF_K1 : rk_fd, F0, FL)) return 1;
     SymGroup& s = ctx->sg[FDGA_SG_K1]; s.d_repvals = s.d_rep[ch];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
+    if (ctx->swave) {       // BSE_K1!(::NL_MF_K1, ...): src/nonlocal/BSEa/BSEa_K1.jl:2-58
+        if (rk_fd != RK_FD) FAIL("fdga_bse_K1_1loop: not available for the s-wave (NL) solver");
+        if (!ctx->forked && refresh_swave(ctx)) return 1;
+        Scope sc(ctx, FDGA_T_K1);
+        const double sc1 = ctx->g.T * chsign(ch);
+        const C* p0 = ctx->Pisw[pi_kind(ch, true)]; const C* p1 = ctx->Pisw[pi_kind(ch, false)];
+        const unsigned nb = nblk(c1 - c0, FDGA_SW_WARPS);
+#define SWK1(CHT, MFT) LAUNCH(FDGA_T_K1, (sw_bse_k1_kernel<CHT, MFT>), nb, 32 * FDGA_SW_WARPS, F0, F, FL, p0, p1, s.d_repvals, sym_dev(s), c0, c1, ctx->g, sc1)
+        if (c1 > c0) {
+            if (mfrg) { if (ch == FDGA_PCH) SWK1(CH_P, true); else if (ch == FDGA_TCH) SWK1(CH_T, true); else SWK1(CH_A, true); }
+            else      { if (ch == FDGA_PCH) SWK1(CH_P, false); else if (ch == FDGA_TCH) SWK1(CH_T, false); else SWK1(CH_A, false); }
+        }
+#undef SWK1
+        CK(cudaGetLastError());
+        return finish_or_defer(ctx, s, ctx->Fbuff.K[ch][0], PK_K1, ch);
+    }
+    if (cached_right(ctx, ch, mfrg ? RK_MF_K1 : rk_fd, F0, FL)) return 1;
     double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
     const DevChain& left = mfrg ? F0 : F;
     {
@@ -1452,6 +1525,7 @@ static int bse_new_impl(fdga_ctx* ctx, int ch, int mfrg, int cls) {
     int which = cls == 0 ? FDGA_SG_K1 : (ch == FDGA_PCH ? FDGA_SG_PP2 : FDGA_SG_PH2);
     NEED_SG(which);
     if (ctx->opt_local) FAIL("fdga_bse_K*_new: not available for the local solver context");
+    if (ctx->swave) FAIL("fdga_bse_K*_new: not available for the s-wave (NL) solver");
     if (ensure_pi(ctx, ch)) return 1;
     DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0);
     SymGroup& s = ctx->sg[which]; s.d_repvals = s.d_rep[ch];
@@ -1486,6 +1560,18 @@ int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
     SymGroup& s = ctx->sg[which]; s.d_repvals = s.d_rep[ch];
     long long c0, c1; sg_class_range(ctx, s, c0, c1);
     double scale = ctx->g.T / (double)ctx->g.NP * chsign(ch);
+    if (ctx->swave) {       // BSE_L_K2!(::NL_MF_K2, ...): src/nonlocal/BSEa/BSEa_K2.jl:1-41
+        if (!ctx->forked && refresh_swave(ctx)) return 1;
+        Scope sc(ctx, FDGA_T_L_K2);
+        const double sc1 = ctx->g.T * chsign(ch);
+        const C* p0 = ctx->Pisw[pi_kind(ch, true)];
+        const unsigned nb = nblk(c1 - c0, FDGA_SW_WARPS);
+#define SWLK2(CHT) LAUNCH(FDGA_T_L_K2, sw_bse_lk2_kernel<CHT>, nb, 32 * FDGA_SW_WARPS, F0, F, p0, s.d_repvals, sym_dev(s), c0, c1, ctx->g, sc1)
+        if (c1 > c0) { if (ch == FDGA_PCH) SWLK2(CH_P); else if (ch == FDGA_TCH) SWLK2(CH_T); else SWLK2(CH_A); }
+#undef SWLK2
+        CK(cudaGetLastError());
+        return finish_or_defer(ctx, s, ctx->FL.K[ch][1], PK_LK2, ch);
+    }
     if (ctx->opt_local) {       // local solver: omega over the bubble mesh, crossing on the right vertex
         if (launch_right<RK_LK2_LOC>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1;
         ColJob job = make_job(ctx, 0, 2 * ctx->g.nPiF, ctx->g.nPiF, ctx->g.nK2b, mkC(scale, 0.0));
@@ -1516,6 +1602,26 @@ static int bse_K2_impl(fdga_ctx* ctx, int ch, int mfrg, int rk_fd) {
     NEED_SG(which);
     if (ensure_pi(ctx, ch)) return 1;
     DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0), FL = chain_FL(ctx);
+    if (ctx->swave) {       // BSE_K2!(::NL_MF_K2, ...): src/nonlocal/BSEa/BSEa_K2.jl:44-106
+        if (rk_fd != RK_FD) FAIL("fdga_bse_K2_1loop: not available for the s-wave (NL) solver");
+        if (!ctx->forked && refresh_swave(ctx)) return 1;
+        SymGroup& s = ctx->sg[which]; s.d_repvals = s.d_rep[ch];
+        long long c0, c1; sg_class_range(ctx, s, c0, c1);
+        {
+            Scope sc(ctx, FDGA_T_K2);
+            const double sc1 = ctx->g.T * chsign(ch);
+            const C* p0 = ctx->Pisw[pi_kind(ch, true)]; const C* p1 = ctx->Pisw[pi_kind(ch, false)];
+            const unsigned nb = nblk(c1 - c0, FDGA_SW_WARPS);
+#define SWK2(CHT, MFT) LAUNCH(FDGA_T_K2, (sw_bse_k2_kernel<CHT, MFT>), nb, 32 * FDGA_SW_WARPS, F0, F, FL, p0, p1, s.d_repvals, sym_dev(s), c0, c1, ctx->g, sc1)
+            if (c1 > c0) {
+                if (mfrg) { if (ch == FDGA_PCH) SWK2(CH_P, true); else if (ch == FDGA_TCH) SWK2(CH_T, true); else SWK2(CH_A, true); }
+                else      { if (ch == FDGA_PCH) SWK2(CH_P, false); else if (ch == FDGA_TCH) SWK2(CH_T, false); else SWK2(CH_A, false); }
+            }
+#undef SWK2
+            CK(cudaGetLastError());
+        }
+        return finish_or_defer(ctx, s, ctx->Fbuff.K[ch][1], PK_K2, ch);
+    }
     if (!ctx->opt_generic) { if (cached_right(ctx, ch, mfrg ? RK_MF_K2 : rk_fd, F0, FL)) return 1; }
     else if (mfrg) { if (launch_right<RK_MF_K2>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1; }
     else if (rk_fd == RK_1L) { if (launch_right<RK_1L>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1; }
@@ -1577,6 +1683,7 @@ int fdga_bse_L_K3(fdga_ctx* ctx, int ch) {
 static int bse_K3_impl(fdga_ctx* ctx, int ch, int mfrg, bool oneloop) {
     CK(cudaSetDevice(ctx->device));
     if (ch < 0 || ch > 2) FAIL("fdga_bse_K3: bad channel");
+    if (oneloop && ctx->swave) FAIL("fdga_bse_K3_1loop: not available for the s-wave (NL) solver");
     int which = ch == FDGA_PCH ? FDGA_SG_PP3 : FDGA_SG_PH3;
     NEED_SG(which);
     if (ensure_pi(ctx, ch)) return 1;
@@ -1632,6 +1739,26 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
     size_t nK2 = ctx->lev[0].len[1];
     CK(cudaMemsetAsync(ctx->L[0], 0, nK2 * sizeof(C), ctx->stream));
     CK(cudaMemsetAsync(ctx->L[1], 0, nK2 * sizeof(C), ctx->stream));
+    if (ctx->swave) {       // SDE_channel_L_pp! / ph!(::NL_MF_K2, ...), src/nonlocal/SDE.jl:3-146; every level of the chain in one pass
+        if (refresh_swave(ctx)) return 1;
+        if (lanes_fork(ctx)) return 1;
+        for (int pp = 1; pp >= 0; pp--) {
+            lane_use(ctx, pp ? 0 : 1);
+            SymGroup& s = ctx->sg[pp ? FDGA_SG_PP2 : FDGA_SG_PH2];
+            long long c0, c1; sg_class_range(ctx, s, c0, c1);
+            const C* Pi = ctx->Pisw[pp ? (reference ? FDGA_PI0PP : FDGA_PIPP) : (reference ? FDGA_PI0PH : FDGA_PIPH)];
+            {
+                Scope sc(ctx, FDGA_T_SDE_L);
+                const unsigned nb = nblk(c1 - c0, FDGA_SW_WARPS);
+                if (c1 > c0) {
+                    if (pp) LAUNCH(FDGA_T_SDE_L, sw_sde_L_kernel<true>, nb, 32 * FDGA_SW_WARPS, V, from, Pi, s.d_repvals, sym_dev(s), c0, c1, g, U, g.T);
+                    else    LAUNCH(FDGA_T_SDE_L, sw_sde_L_kernel<false>, nb, 32 * FDGA_SW_WARPS, V, from, Pi, s.d_repvals, sym_dev(s), c0, c1, g, U, g.T);
+                }
+                CK(cudaGetLastError());
+            }
+            if (sg_finish(ctx, s, ctx->L[pp ? 0 : 1])) return 1;
+        }
+    } else
     if (!ctx->opt_generic) {
         // fused recursion: one column launch per bubble kind covers every level of the chain (fdga_column.cuh);
         // lanes: pp on 0, ph on 1, (G transforms + U^2 term) on 2
@@ -1679,6 +1806,14 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
     for (int pp = 1; pp >= 0; pp--) {
         lane_use(ctx, pp ? 0 : 1);
         Scope sc(ctx, FDGA_T_SDE_RS);
+        if (ctx->swave) {       // fft(L, momentum axis) / L^2 -> scratchA / scratchB (src/nonlocal/SDE.jl:217-218); L[] is the intermediate
+            C* Lx = ctx->L[pp ? 0 : 1]; C* out = pp ? ctx->scratchA : ctx->scratchB;
+            const long long n = pre * g.NP;
+            LAUNCH(FDGA_T_SDE_RS, dft_axis_kernel, nblk(n, 128), 128, Lx, out, pre, g.L, (long long)g.L, -1, 1.0, ctx->twL);
+            LAUNCH(FDGA_T_SDE_RS, dft_axis_kernel, nblk(n, 128), 128, out, Lx, pre * g.L, g.L, 1LL, -1, 1.0 / ((double)g.L * g.L), ctx->twL);
+            CK(cudaGetLastError());
+            continue;
+        }
         if (dft4(ctx, ctx->L[pp ? 0 : 1], pp ? ctx->scratchA : ctx->scratchB, pre, -1, nrm, FDGA_T_SDE_RS)) return 1;
     }
     lane_use(ctx, 2);
@@ -1708,6 +1843,8 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
         Scope sc(ctx, FDGA_T_SDE_RS);
         CK(cudaMemsetAsync(ctx->SigR, 0, ctx->lenG * sizeof(C), ctx->stream));
         const int twin = std::min(g.LG, 4 * (g.L / 2) + 1);
+        if (ctx->swave) LAUNCH(FDGA_T_SDE_RS, sw_sde_rs_kernel, nblk((long long)ctx->lenG, 128), 128, ctx->GR, ctx->L[0], ctx->L[1], ctx->SigR, g);
+        else
         LAUNCH(FDGA_T_SDE_RS, sde_rs_kernel, nblk((long long)(2 * g.nK2f) * twin * twin * 32, 128), 128, ctx->GR, ctx->L[0], ctx->L[1], ctx->SigR, g, g.nG, g.LG, twin);
         CK(cudaGetLastError());
         if (dft2_G(ctx, ctx->SigR, Sout, ctx->SigTmp, +1, 1.0, FDGA_T_SDE_RS)) return 1;
@@ -2130,14 +2267,14 @@ static int interp_run(fdga_ctx* ctx, C* dst, const fdga_c64* host_in, InterpBox 
 int fdga_interpolate_vertex(fdga_ctx* ctx, int which, int channel, int cls, const fdga_c64* host_Ki, const int32_t* nKi, int Li) {
     CK(cudaSetDevice(ctx->device));
     LevelBuf* lb = which_level(ctx, which);
-    if (!lb || lb->d.type != FDGA_LV_NL2 || channel < 0 || channel > 2 || cls < 0 || cls > 2) FAIL("fdga_interpolate_vertex: bad selector (needs an NL2 level)");
+    if (!lb || (lb->d.type != FDGA_LV_NL2 && lb->d.type != FDGA_LV_NL) || channel < 0 || channel > 2 || cls < 0 || cls > 2) FAIL("fdga_interpolate_vertex: bad selector (needs an NL2 / NL level)");
     if (lb == &ctx->lev[0] && wait_copy(ctx)) return 1;
     const fdga_level_desc& d = lb->d;
     InterpBox b; b.nd = 1; for (int i = 0; i < 3; ++i) { b.no[i] = 1; b.ni[i] = 1; b.shift[i] = 0; }
     int D = 2;
     if (cls == 0) { b.no[0] = 2 * d.nK1 - 1; b.ni[0] = 2 * nKi[0] - 1; b.shift[0] = nKi[0] - d.nK1; }
     else if (cls == 1) {
-        b.nd = 2; D = 4;
+        b.nd = 2; D = lb->d.type == FDGA_LV_NL ? 2 : 4;
         b.no[0] = 2 * d.nK2[0] - 1; b.ni[0] = 2 * nKi[0] - 1; b.shift[0] = nKi[0] - d.nK2[0];
         b.no[1] = 2 * d.nK2[1];     b.ni[1] = 2 * nKi[1];     b.shift[1] = nKi[1] - d.nK2[1];
     } else {
@@ -2169,6 +2306,14 @@ int fdga_mix_bubbles(fdga_ctx* ctx, double mixing) {
     for (int i = 0; i < 2; i++) if (!ctx->PiMixed[i]) CK(cudaMalloc(&ctx->PiMixed[i], ctx->lenPi * sizeof(C)));
     Scope sc(ctx, FDGA_T_MISC);
     const int pi[2] = {FDGA_PIPP, FDGA_PIPH}, pi0[2] = {FDGA_PI0PP, FDGA_PI0PH};
+    if (ctx->swave) {
+        for (int i = 0; i < 2; i++) {
+            LAUNCH(FDGA_T_MISC, axpby_kernel, nblk(ctx->lenPi, 256), 256, ctx->PiMixed[i], (const C*)ctx->Pisw[pi[i]], mixing, (const C*)ctx->Pisw[pi0[i]], 1.0 - mixing, (long long)ctx->lenPi);
+            CK(cudaMemcpyAsync(ctx->Pisw[pi[i]], ctx->PiMixed[i], ctx->lenPi * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        CK(cudaGetLastError());
+        return 0;
+    }
     for (int i = 0; i < 2; i++) {      // the mixed bubbles are not products of Green functions: they live in the full layout
         if (ensure_pi_full(ctx, pi[i]) || ensure_pi_full(ctx, pi0[i])) return 1;
         LAUNCH(FDGA_T_MISC, axpby_kernel, nblk(ctx->lenPi, 256), 256, ctx->PiMixed[i], (const C*)ctx->Pi[pi[i]], mixing, (const C*)ctx->Pi[pi0[i]], 1.0 - mixing, (long long)ctx->lenPi);
@@ -2185,12 +2330,13 @@ int fdga_mix_bubbles(fdga_ctx* ctx, double mixing) {
 int fdga_update_reference(fdga_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     if (!ctx->PiMixed[0]) FAIL("fdga_update_reference: call fdga_mix_bubbles first");
-    if (ctx->nlev < 2 || ctx->lev[1].d.type != FDGA_LV_NL2 || ctx->lev[1].blocklen != ctx->lev[0].blocklen)
-        FAIL("fdga_update_reference: add!(S.F0, S.F) needs S.F0 to be an NL2_Vertex on the meshes of S.F");
+    if (ctx->nlev < 2 || ctx->lev[1].d.type != ctx->lev[0].d.type || ctx->lev[1].blocklen != ctx->lev[0].blocklen)
+        FAIL("fdga_update_reference: add!(S.F0, S.F) needs S.F0 to be a vertex of S.F's own type on the meshes of S.F");
     if (wait_copy(ctx)) return 1;
     Scope sc(ctx, FDGA_T_MISC);
     const int pi0[2] = {FDGA_PI0PP, FDGA_PI0PH};
     for (int i = 0; i < 2; i++) {
+        if (ctx->swave) { CK(cudaMemcpyAsync(ctx->Pisw[pi0[i]], ctx->PiMixed[i], ctx->lenPi * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream)); continue; }
         if (!ctx->Pi[pi0[i]]) CK(cudaMalloc(&ctx->Pi[pi0[i]], ctx->lenPi * sizeof(C)));
         CK(cudaMemcpyAsync(ctx->Pi[pi0[i]], ctx->PiMixed[i], ctx->lenPi * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
         ctx->pi_src[pi0[i]] = PI_FULL; ctx->pi_full_valid[pi0[i]] = true;

@@ -10,6 +10,8 @@
 //   SGph[2] : sK2_NL2_ph1, ph2, ref, rot                   src/nonlocal_2/symmetries.jl:35-46
 //   SGpp[3] : sK3pp1, pp2, pp3, ref, rot   SGph[3] : sK3ph1, ph2, ph3, ref, rot    src/nonlocal/symmetries.jl:70-139
 //   SGppL[3]: sK3pp1, pp3, ref, rot        SGphL[3]: sK3ph1, ph3, ref, rot
+// and of init_sym_grp!(::NL_ParquetSolver), src/nonlocal/ParquetSolver.jl:196-290, whose K2[W,v,P] groups differ:
+//   SGpp[2] : sK2pp1, pp2, ref, rot        SGph[2] : sK2ph1, ph2, ref, rot        src/nonlocal/symmetries.jl:47-72
 // In drop-in use Julia passes SG.classes through fdga_set_symmetry_classes and this builder is not needed.
 #include <cstdint>
 #include <vector>
@@ -32,7 +34,7 @@ struct Builder {
     int len0, len1;
 
     Builder(int which_, int n0_, int n1_, int L_) : which(which_), n0(n0_), n1(n1_), L(L_), NP(L_ * L_) {
-        nfreq = (which <= FDGA_SG_K1) ? 1 : ((which == FDGA_SG_PP2 || which == FDGA_SG_PH2) ? 2 : 3);
+        nfreq = (which <= FDGA_SG_K1) ? 1 : ((which == FDGA_SG_PP2 || which == FDGA_SG_PH2 || which == FDGA_SG_NL_PP2 || which == FDGA_SG_NL_PH2) ? 2 : 3);
         nmom = (which == FDGA_SG_PP2 || which == FDGA_SG_PH2) ? 2 : 1;
         len0 = (which == FDGA_SG_SIGMA) ? 2 * n0 : 2 * n0 - 1;
         len1 = 2 * n1;
@@ -102,6 +104,15 @@ struct Builder {
             b = a;
             if (pp) { b.f1 = a.f0 - a.f1 - 1; b.p1x = fold(a.p0x - a.p1x, L); b.p1y = fold(a.p0y - a.p1y, L); }
             else    { b.f0 = -a.f0; b.f1 = a.f0 + a.f1; neg_mom(b.p0x, b.p0y); b.p1x = fold(a.p0x + a.p1x, L); b.p1y = fold(a.p0y + a.p1y, L); }
+            push(b, 0);
+            b = a; ref_all(b); push(b, 0);
+            b = a; rot_all(b); push(b, 0);
+            break;
+        case FDGA_SG_NL_PP2: case FDGA_SG_NL_PH2:
+            b = a; b.f0 = -a.f0; b.f1 = -a.f1 - 1; neg_mom(b.p0x, b.p0y); push(b, 2);
+            b = a;
+            if (which == FDGA_SG_NL_PP2) b.f1 = a.f0 - a.f1 - 1;
+            else { b.f0 = -a.f0; b.f1 = a.f0 + a.f1; neg_mom(b.p0x, b.p0y); }
             push(b, 0);
             b = a; ref_all(b); push(b, 0);
             b = a; rot_all(b); push(b, 0);

@@ -19,7 +19,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from .types import (CH_NAME, CHANNELS, NL2_Vertex, RefVertex, Vertex, aCh, nB, nF, pCh, tCh, vertex_chain, zeros)
+from .types import (CH_NAME, CHANNELS, NL2_Vertex, NL_Vertex, RefVertex, Vertex, aCh, nB, nF, pCh, tCh, vertex_chain, zeros)
 
 STRATEGY = {"scPA": L.SCPA, "fdPA": L.FDPA, "scPA_new": L.SCPA_NEW, "fdPA_new": L.FDPA_NEW, "fdPA_1loop": L.FDPA_1LOOP}
 _G_NAMES = {"G": L.G, "G0": L.G0, "Gbare": L.GBARE, "Σ": L.SIGMA, "Σ0": L.SIGMA0}
@@ -35,6 +35,12 @@ class NL2_ParquetSolver:
     F0: reference vertex: RefVertex | Vertex | NL2_Vertex (arbitrarily nested).
     L: linear size of the vertex momentum mesh mK_Γ.
     """
+
+    _vertex_cls = NL2_Vertex
+    swave = False
+
+    def _pi_shape(self):
+        return (nB(self.nΠB), nF(self.nΠF), self.NP, self.NP)
 
     def __init__(self, nK1, nK2, nK3, L_, Gbare, G0, Σ0, F0, *, T, mode="threads", mΠν_factor=1, device=0,
                  compute_bubbles=True):
@@ -58,11 +64,11 @@ class NL2_ParquetSolver:
         self.G = self.G0.copy(order="F")
         self.Σ = self.Σ0.copy(order="F")
         self.F0 = F0
-        self.F = NL2_Vertex(F0, self.T, nK1, nK2, nK3, self.L)
+        self.F = self._vertex_cls(F0, self.T, nK1, nK2, nK3, self.L)
         null = RefVertex(self.T, 0.0)
-        self.Fbuff = NL2_Vertex(null, self.T, nK1, nK2, nK3, self.L)
-        self.FL = NL2_Vertex(null.copy(), self.T, nK1, nK2, nK3, self.L)
-        shpΠ = (nB(self.nΠB), nF(self.nΠF), self.NP, self.NP)
+        self.Fbuff = self._vertex_cls(null, self.T, nK1, nK2, nK3, self.L)
+        self.FL = self._vertex_cls(null.copy(), self.T, nK1, nK2, nK3, self.L)
+        shpΠ = self._pi_shape()
         self.Π0pp, self.Π0ph, self.Πpp, self.Πph = (None,) * 4     # pulled on demand (large)
         self._shpΠ = shpΠ
         self.Lpp = zeros(self.F.γp.K2.shape)
@@ -84,9 +90,11 @@ class NL2_ParquetSolver:
                 lv.nK3[0], lv.nK3[1] = V.numK3
                 lv.U_re, lv.U_im = V.U.real, V.U.imag
             else:
-                lv.type = L.LV_NL2 if isinstance(V, NL2_Vertex) else L.LV_LOCAL
-                if isinstance(V, NL2_Vertex) and V.L != self.L:
-                    raise L.FdgaError("all NL2 levels must share the momentum mesh")
+                lv.type = L.LV_NL2 if isinstance(V, NL2_Vertex) else (L.LV_NL if isinstance(V, NL_Vertex) else L.LV_LOCAL)
+                if isinstance(V, (NL2_Vertex, NL_Vertex)) and not isinstance(V, self._vertex_cls):
+                    raise L.FdgaError(f"the momentum-dependent levels of the F0 chain must be {self._vertex_cls.__name__}s")
+                if isinstance(V, (NL2_Vertex, NL_Vertex)) and V.L != self.L:
+                    raise L.FdgaError("all momentum-dependent levels must share the momentum mesh")
                 lv.nK1 = V.numK1
                 lv.nK2[0], lv.nK2[1] = V.numK2
                 lv.nK3[0], lv.nK3[1] = V.numK3
@@ -227,9 +235,10 @@ class NL2_ParquetSolver:
         n = {L.SG_SIGMA: (self.nG, 0), L.SG_K1: (self.nK1, 0),
              L.SG_PP2: self.nK2, L.SG_PH2: self.nK2,
              L.SG_PP3: self.nK3, L.SG_PH3: self.nK3, L.SG_PPL3: self.nK3, L.SG_PHL3: self.nK3}
+        kind = {L.SG_PP2: L.SG_NL_PP2, L.SG_PH2: L.SG_NL_PH2} if self.swave else {}      # src/nonlocal/ParquetSolver.jl:215-250
         for which, (n0, n1) in n.items():
             nq = self.LG if which == L.SG_SIGMA else self.L
-            self.set_symmetry_classes(which, *L.build_symmetry_group(which, n0, n1, nq, self._sg_len(which)))
+            self.set_symmetry_classes(which, *L.build_symmetry_group(kind.get(which, which), n0, n1, nq, self._sg_len(which)))
 
     def num_classes(self, which):
         return len(self._sg[which][0]) - 1
@@ -313,6 +322,22 @@ class NL2_ParquetSolver:
 
     def stream(self):
         return self._lib.fdga_stream(self._ctx)
+
+
+class NL_ParquetSolver(NL2_ParquetSolver):
+    """The s-wave solver NL_ParquetSolver (src/nonlocal/ParquetSolver.jl:1-154; nl_method = 1 of script/run_Wu_point.jl): vertices
+    with bosonic momentum dependence only (NL_Vertex: K2[Ω,ν,P]), bubbles Π[Ω,ν,P] with the 1/ν tail of G at R = 0
+    (src/nonlocal/bubble.jl:87-158), mΠν_factor = 32.  F0: RefVertex | Vertex | NL_Vertex (nested).  Strategies: scPA, fdPA (and
+    the mfRG maps built on them); the `_new` / `_1loop` variants exist for the NL2 solver only."""
+    _vertex_cls = NL_Vertex
+    swave = True
+
+    def _pi_shape(self):
+        return (nB(self.nΠB), nF(self.nΠF), self.NP)
+
+    def __init__(self, nK1, nK2, nK3, L_, Gbare, G0, Σ0, F0, *, T, mode="threads", mΠν_factor=32, device=0, compute_bubbles=True):
+        super().__init__(nK1, nK2, nK3, L_, Gbare, G0, Σ0, F0, T=T, mode=mode, mΠν_factor=mΠν_factor, device=device,
+                         compute_bubbles=compute_bubbles)
 
 
 class ParquetSolver(NL2_ParquetSolver):

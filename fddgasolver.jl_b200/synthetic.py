@@ -9,8 +9,8 @@ import os
 import numpy as np
 
 from .models import hubbard_bare_Green, siam_bare_Green
-from .solver import NL2_ParquetSolver, ParquetSolver
-from .types import NL2_Vertex, RefVertex, Vertex, nB, nF
+from .solver import NL2_ParquetSolver, NL_ParquetSolver, ParquetSolver
+from .types import NL2_Vertex, NL_Vertex, RefVertex, Vertex, nB, nF
 
 
 def parquet_solver_hubbard_parquet_approximation_NL2(nG, nK1, nK2, nK3, LG, L, *, T, U, μ, t1, t2=0.0, t3=0.0,
@@ -21,6 +21,12 @@ def parquet_solver_hubbard_parquet_approximation_NL2(nG, nK1, nK2, nK3, LG, L, *
     Σ0 = np.zeros_like(Gbare)
     F0 = RefVertex(T, U)
     return NL2_ParquetSolver(nK1, nK2, nK3, L, Gbare, G0, Σ0, F0, T=T, mode=mode, device=device)
+
+
+def parquet_solver_hubbard_parquet_approximation(nG, nK1, nK2, nK3, LG, L, *, T, U, μ, t1, t2=0.0, t3=0.0, mode="threads", device=0):
+    """Parquet approximation with the s-wave solver: G0 = Σ0 = 0, F0 = U (src/nonlocal/ParquetSolver.jl:167-194)."""
+    Gbare = hubbard_bare_Green(T, nG, LG, μ=μ, t1=t1, t2=t2, t3=t3)
+    return NL_ParquetSolver(nK1, nK2, nK3, L, Gbare, np.zeros_like(Gbare), np.zeros_like(Gbare), RefVertex(T, U), T=T, mode=mode, device=device)
 
 
 def parquet_solver_siam_parquet_approximation(nG, nK1, nK2, nK3, *, e, Δ, D, T, U, mode="threads", mΠν_factor=6, device=0):
@@ -101,14 +107,15 @@ def load_dmft_fixture(path=DMFT_FIXTURE):
             "params": dict(zip([str(k) for k in z["param_names"]], [float(v) for v in z["param_values"]])), "source": str(z["source"])}
 
 
-def wu_point_inputs(nmax=4, nq=8, LG=48, *, seed=1, F_scale=1e-2, F0_scale=0.0, small_reference=False, data="auto"):
+def wu_point_inputs(nmax=4, nq=8, LG=48, *, seed=1, F_scale=1e-2, F0_scale=0.0, small_reference=False, data="auto", nl_method=2):
     """Pure-numpy inputs of the Wu-point NL2 problem (no device needed): dict with the constructor arguments
     of NL2_ParquetSolver plus the seeded start vertex `F` (an NL2_Vertex whose F0 is the reference vertex).
 
     Mirrors script/benchmark_Wu.jl:7-44: T=0.2, U=5.6, μ=2.1800201007694464-U/2, t1=1, t2=-0.3,
     nG = nK1 = 4 nmax, nK2 = nK3 = (nmax, nmax), G mesh LG x LG, vertex mesh nq x nq,
     F0 = NL2_Vertex(Γ_local), S.F seeded random * F_scale.  F0_scale != 0 also fills S.F0's own K's
-    (state after the first outer iteration).
+    (state after the first outer iteration).  nl_method = 1: the s-wave solver's inputs (script/run_Wu_point.jl:88-90),
+    F0 = NL_Vertex(Γ_local), F an NL_Vertex.
     """
     T, U = 0.2, 5.6
     μ = 2.1800201007694464 - U / 2
@@ -133,10 +140,11 @@ def wu_point_inputs(nmax=4, nq=8, LG=48, *, seed=1, F_scale=1e-2, F0_scale=0.0, 
             Γ = synthetic_local_vertex(T, U, numK1=2 * nK1, numK2=(2 * nmax, 2 * nmax), numK3=(1, 1), core=(nmax + 1, nmax), seed=2)
         else:
             Γ = synthetic_local_vertex(T, U, seed=2)
-    F0 = NL2_Vertex(Γ, T, nK1, nK2, nK3, nq)
+    VT = {1: NL_Vertex, 2: NL2_Vertex}[nl_method]
+    F0 = VT(Γ, T, nK1, nK2, nK3, nq)
     if F0_scale:
         randomize_vertex(F0, seed + 7, scale=F0_scale)
-    F = NL2_Vertex(F0, T, nK1, nK2, nK3, nq)
+    F = VT(F0, T, nK1, nK2, nK3, nq)
     randomize_vertex(F, seed, scale=F_scale)
     return dict(T=T, U=U, nK1=nK1, nK2=nK2, nK3=nK3, L=nq, Gbare=Gbare, G0=G0, Σ0=Σ0, F0=F0, F=F,
                 data=("reference file data/Wu_point.h5 (local DMFT vertex, impurity G and Σ, via tests/golden/wu_point_dmft.npz) + seeded nonlocal start vertex"
@@ -144,10 +152,10 @@ def wu_point_inputs(nmax=4, nq=8, LG=48, *, seed=1, F_scale=1e-2, F0_scale=0.0, 
 
 
 def wu_point_solver(nmax=4, nq=8, LG=48, *, seed=1, device=0, init_sym=True, F_scale=1e-2, F0_scale=0.0,
-                    small_reference=False, data="auto"):
-    """NL2_ParquetSolver on the GPU for wu_point_inputs(...) (see there)."""
-    inp = wu_point_inputs(nmax, nq, LG, seed=seed, F_scale=F_scale, F0_scale=F0_scale, small_reference=small_reference, data=data)
-    S = NL2_ParquetSolver(inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"],
+                    small_reference=False, data="auto", nl_method=2):
+    """NL2_ParquetSolver (nl_method = 2) or NL_ParquetSolver (nl_method = 1) on the GPU for wu_point_inputs(...) (see there)."""
+    inp = wu_point_inputs(nmax, nq, LG, seed=seed, F_scale=F_scale, F0_scale=F0_scale, small_reference=small_reference, data=data, nl_method=nl_method)
+    S = {1: NL_ParquetSolver, 2: NL2_ParquetSolver}[nl_method](inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"],
                           T=inp["T"], device=device)
     S.F.set(inp["F"])
     S.push("F")

@@ -1,8 +1,8 @@
 """Host-side data model mirroring the reference's vertex structs (containers of numpy arrays).
 
 Reference: src/types.jl (tags, array aliases), src/channel.jl:7-48 (Channel), src/nonlocal_2/channel.jl:4-41
-(NL2_Channel), src/refvertex.jl:1-35 (RefVertex), src/vertex.jl:7-36 (Vertex), src/nonlocal_2/vertex.jl:1-32
-(NL2_Vertex).  All arrays are complex128 in Fortran (column-major) order, i.e. byte-identical to the
+(NL2_Channel), src/nonlocal/channel.jl:3-51 (NL_Channel), src/refvertex.jl:1-35 (RefVertex), src/vertex.jl:7-36 (Vertex),
+src/nonlocal_2/vertex.jl:1-32 (NL2_Vertex), src/nonlocal/vertex.jl:1-37 (NL_Vertex).  All arrays are complex128 in Fortran (column-major) order, i.e. byte-identical to the
 Julia ``Array{ComplexF64,N}`` the C-ABI receives.  Evaluation happens on the device (libfdga), not here.
 """
 import numpy as np
@@ -77,6 +77,20 @@ class NL2_Channel(Channel):
         NP = L * L
         self.K1 = zeros((nB(numK1), NP))
         self.K2 = zeros((nB(numK2[0]), nF(numK2[1]), NP, NP))
+        self.K3 = zeros((nB(numK3[0]), nF(numK3[1]), nF(numK3[1]), NP))
+
+
+class NL_Channel(Channel):
+    """K1[Ω,P], K2[Ω,ν,P], K3[Ω,ν,ν',P]: bosonic momentum dependence only (src/nonlocal/channel.jl:3-51)"""
+    nonlocal_ = True
+
+    def __init__(self, T, numK1, numK2, numK3, L):
+        assert numK1 >= numK2[0] and numK1 >= numK2[1], "K1 mesh must contain the K2 meshes"
+        assert numK2[0] >= numK3[0] and numK2[1] >= numK3[1], "K2 meshes must contain the K3 meshes"
+        self.T, self.numK1, self.numK2, self.numK3, self.L = float(T), int(numK1), tuple(numK2), tuple(numK3), int(L)
+        NP = L * L
+        self.K1 = zeros((nB(numK1), NP))
+        self.K2 = zeros((nB(numK2[0]), nF(numK2[1]), NP))
         self.K3 = zeros((nB(numK3[0]), nF(numK3[1]), nF(numK3[1]), NP))
 
 
@@ -179,6 +193,17 @@ class NL2_Vertex(_VertexBase):
         self.γp = NL2_Channel(T, numK1, numK2, numK3, L)
         self.γt = NL2_Channel(T, numK1, numK2, numK3, L)
         self.γa = NL2_Channel(T, numK1, numK2, numK3, L)
+
+
+class NL_Vertex(_VertexBase):
+    """nonlocal vertex with bosonic momentum dependence only, the s-wave solver's vertex (src/nonlocal/vertex.jl:1-37)"""
+
+    def __init__(self, F0, T, numK1, numK2, numK3, L):
+        self.F0 = F0
+        self.L = int(L)
+        self.γp = NL_Channel(T, numK1, numK2, numK3, L)
+        self.γt = NL_Channel(T, numK1, numK2, numK3, L)
+        self.γa = NL_Channel(T, numK1, numK2, numK3, L)
 
 
 def vertex_chain(F):

@@ -37,7 +37,8 @@ enum { FDGA_K1 = 0, FDGA_K2 = 1, FDGA_K3 = 2 };
 /* level types of the nested vertex chain S.F -> S.F.F0 -> ... (src/vertex.jl, src/refvertex.jl) */
 enum { FDGA_LV_NL2 = 0,    /* NL2_Vertex  (src/nonlocal_2/vertex.jl:1-32)  K1[W,P] K2[W,v,P,k] K3[W,v,v',P] */
        FDGA_LV_LOCAL = 1,  /* Vertex      (src/vertex.jl:7-36)             K1[W]   K2[W,v]     K3[W,v,v']   */
-       FDGA_LV_CORE = 2 }; /* RefVertex   (src/refvertex.jl:1-35)          U + Fp_p, Fp_x, Ft_p, Ft_x       */
+       FDGA_LV_CORE = 2,   /* RefVertex   (src/refvertex.jl:1-35)          U + Fp_p, Fp_x, Ft_p, Ft_x       */
+       FDGA_LV_NL = 3 };   /* NL_Vertex   (src/nonlocal/vertex.jl:1-37)    K1[W,P] K2[W,v,P]   K3[W,v,v',P] */
 
 #define FDGA_MAX_LEVELS 6
 
@@ -71,7 +72,10 @@ enum { FDGA_C_GPX = 0, FDGA_C_F0P = 1, FDGA_C_F0A = 2, FDGA_C_F0T = 3, FDGA_C_GP
        FDGA_C_GA = 5, FDGA_C_GT = 6, FDGA_C_FP = 7, FDGA_C_FA = 8, FDGA_C_FT = 9 };
 /* symmetry groups, src/nonlocal_2/ParquetSolver.jl:200-291 (SGxx[i] -> K(i) class) */
 enum { FDGA_SG_SIGMA = 0, FDGA_SG_K1 = 1, FDGA_SG_PP2 = 2, FDGA_SG_PH2 = 3, FDGA_SG_PP3 = 4,
-       FDGA_SG_PH3 = 5, FDGA_SG_PPL3 = 6, FDGA_SG_PHL3 = 7, FDGA_SG_COUNT = 8 };
+       FDGA_SG_PH3 = 5, FDGA_SG_PPL3 = 6, FDGA_SG_PHL3 = 7, FDGA_SG_COUNT = 8,
+       /* builder-only ids (fdga_build_symmetry_group): the K2[W,v,P] groups of the s-wave solver, src/nonlocal/ParquetSolver.jl:215-250;
+        * they are registered in the FDGA_SG_PP2 / FDGA_SG_PH2 slots of an s-wave context */
+       FDGA_SG_NL_PP2 = 8, FDGA_SG_NL_PH2 = 9 };
 /* strategies of src/solve.jl:10, src/SDE.jl:3-33 (:scPA, :fdPA, :scPA_new, :fdPA_new, :fdPA_1loop) */
 enum { FDGA_SCPA = 0, FDGA_FDPA = 1, FDGA_SCPA_NEW = 2, FDGA_FDPA_NEW = 3, FDGA_FDPA_1LOOP = 4 };
 
