@@ -636,6 +636,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     if (dims->nPiB != d0.nK1) { g_create_error = "dims: bubble bosonic mesh must equal the K1 mesh (nPiB == nK1)"; return 2; }
     if (!(d0.nK1 > d0.nK2[0] && d0.nK1 > d0.nK2[1] && d0.nK2[0] >= d0.nK3[0] && d0.nK2[1] >= d0.nK3[1] && dims->nPiF >= d0.nK2[1])) {
         g_create_error = "dims: mesh constraints violated (src/nonlocal_2/channel.jl:26-33)"; return 2; }
+    if (swave && dims->LG < dims->nq) { g_create_error = "dims: the s-wave solver needs LG >= nq (Green-function mesh at least as fine as the vertex mesh)"; return 2; }
     fdga_ctx* ctx = new fdga_ctx();
     ctx->dims = *dims; ctx->device = device; ctx->nlev = dims->nlev; ctx->swave = swave; ctx->swScratch[0] = ctx->swScratch[1] = nullptr;
     ctx->nranks = 1; ctx->rank = 0; ctx->comm = nullptr; memset(&ctx->nccl, 0, sizeof(ctx->nccl));
@@ -1106,8 +1107,14 @@ int fdga_bubbles_real_space(fdga_ctx* ctx, int reference) {
     const C* Gsrc = ctx->G[reference ? FDGA_G0 : FDGA_G];
     if (dft2_G(ctx, Gsrc, ctx->GR, ctx->SigTmp, -1, 1.0 / ((double)g.LG * g.LG), FDGA_T_BUBBLE)) return 1;
     if (ctx->swave) {       // bubbles_real_space!(::NL_MF_Pi; use_G_tail = true): src/nonlocal/bubble.jl:87-158
-        for (int i = 0; i < 2; i++) if (!ctx->swScratch[i]) CK(cudaMalloc(&ctx->swScratch[i], ctx->lenPisw * sizeof(C)));
         const long long pre = (long long)(2 * g.nPiB - 1) * (2 * g.nPiF), n = pre * g.NP;
+        static const bool literal = getenv("FDGA_BUBBLES_RS") ? atoi(getenv("FDGA_BUBBLES_RS")) != 0 : false;
+        if (!literal) {     // back transform as a direct sum on the few inner frequencies that carry one (fdga_swave.cuh)
+            LAUNCH(FDGA_T_BUBBLE, sw_bubbles_direct_kernel, nblk(n, 128), 128, ctx->GR, ctx->Pisw[ipp], ctx->Pisw[iph], g, 1, ctx->twL);
+            CK(cudaGetLastError());
+            return 0;
+        }
+        for (int i = 0; i < 2; i++) if (!ctx->swScratch[i]) CK(cudaMalloc(&ctx->swScratch[i], ctx->lenPisw * sizeof(C)));
         LAUNCH(FDGA_T_BUBBLE, sw_bubbles_rs_kernel, nblk(n, 128), 128, ctx->GR, ctx->swScratch[0], ctx->swScratch[1], g, 1);
         for (int i = 0; i < 2; i++) {      // back transform over the two momentum axes; Pisw[] as the intermediate
             C* dst = ctx->Pisw[i == 0 ? ipp : iph];
@@ -1194,6 +1201,11 @@ int fdga_build_K3_cache(fdga_ctx* ctx, int mfrg, int first) {
 }
 
 // ---- BSE kernels -----------------------------------------------------------------------------------------
+// s-wave contraction kernels (fdga_swave.cuh): one CTA per class representative when the inner sum is long, else one warp
+static bool sw_cta_per_rep(int nw) {
+    static const int lim = getenv("FDGA_SW_CTA_MIN") ? atoi(getenv("FDGA_SW_CTA_MIN")) : 128;
+    return nw >= lim;
+}
 static int pi_kind(int ch, bool reference) { return ch == FDGA_PCH ? (reference ? FDGA_PI0PP : FDGA_PIPP) : (reference ? FDGA_PI0PH : FDGA_PIPH); }
 
 extern "C++" {
@@ -1490,13 +1502,16 @@ static int bse_K1_impl(fdga_ctx* ctx, int ch, int mfrg, int rk_fd) {
         Scope sc(ctx, FDGA_T_K1);
         const double sc1 = ctx->g.T * chsign(ch);
         const C* p0 = ctx->Pisw[pi_kind(ch, true)]; const C* p1 = ctx->Pisw[pi_kind(ch, false)];
-        const unsigned nb = nblk(c1 - c0, FDGA_SW_WARPS);
-#define SWK1(CHT, MFT) LAUNCH(FDGA_T_K1, (sw_bse_k1_kernel<CHT, MFT>), nb, 32 * FDGA_SW_WARPS, F0, F, FL, p0, p1, s.d_repvals, sym_dev(s), c0, c1, ctx->g, sc1)
+        const bool cta = sw_cta_per_rep(2 * ctx->g.nPiF);
+        const unsigned nb = cta ? (unsigned)(c1 - c0) : nblk(c1 - c0, FDGA_SW_WARPS);
+#define SWK1b(CHT, MFT, CT) LAUNCH(FDGA_T_K1, (sw_bse_k1_kernel<CHT, MFT, CT>), nb, FDGA_SW_THREADS, F0, F, FL, p0, p1, s.d_repvals, sym_dev(s), c0, c1, ctx->g, sc1)
+#define SWK1(CHT, MFT) do { if (cta) SWK1b(CHT, MFT, true); else SWK1b(CHT, MFT, false); } while (0)
         if (c1 > c0) {
             if (mfrg) { if (ch == FDGA_PCH) SWK1(CH_P, true); else if (ch == FDGA_TCH) SWK1(CH_T, true); else SWK1(CH_A, true); }
             else      { if (ch == FDGA_PCH) SWK1(CH_P, false); else if (ch == FDGA_TCH) SWK1(CH_T, false); else SWK1(CH_A, false); }
         }
 #undef SWK1
+#undef SWK1b
         CK(cudaGetLastError());
         return finish_or_defer(ctx, s, ctx->Fbuff.K[ch][0], PK_K1, ch);
     }
@@ -1565,10 +1580,13 @@ int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
         Scope sc(ctx, FDGA_T_L_K2);
         const double sc1 = ctx->g.T * chsign(ch);
         const C* p0 = ctx->Pisw[pi_kind(ch, true)];
-        const unsigned nb = nblk(c1 - c0, FDGA_SW_WARPS);
-#define SWLK2(CHT) LAUNCH(FDGA_T_L_K2, sw_bse_lk2_kernel<CHT>, nb, 32 * FDGA_SW_WARPS, F0, F, p0, s.d_repvals, sym_dev(s), c0, c1, ctx->g, sc1)
+        const bool cta = sw_cta_per_rep(2 * ctx->g.nK2f);
+        const unsigned nb = cta ? (unsigned)(c1 - c0) : nblk(c1 - c0, FDGA_SW_WARPS);
+#define SWLK2b(CHT, CT) LAUNCH(FDGA_T_L_K2, (sw_bse_lk2_kernel<CHT, CT>), nb, FDGA_SW_THREADS, F0, F, p0, s.d_repvals, sym_dev(s), c0, c1, ctx->g, sc1)
+#define SWLK2(CHT) do { if (cta) SWLK2b(CHT, true); else SWLK2b(CHT, false); } while (0)
         if (c1 > c0) { if (ch == FDGA_PCH) SWLK2(CH_P); else if (ch == FDGA_TCH) SWLK2(CH_T); else SWLK2(CH_A); }
 #undef SWLK2
+#undef SWLK2b
         CK(cudaGetLastError());
         return finish_or_defer(ctx, s, ctx->FL.K[ch][1], PK_LK2, ch);
     }
@@ -1611,13 +1629,16 @@ static int bse_K2_impl(fdga_ctx* ctx, int ch, int mfrg, int rk_fd) {
             Scope sc(ctx, FDGA_T_K2);
             const double sc1 = ctx->g.T * chsign(ch);
             const C* p0 = ctx->Pisw[pi_kind(ch, true)]; const C* p1 = ctx->Pisw[pi_kind(ch, false)];
-            const unsigned nb = nblk(c1 - c0, FDGA_SW_WARPS);
-#define SWK2(CHT, MFT) LAUNCH(FDGA_T_K2, (sw_bse_k2_kernel<CHT, MFT>), nb, 32 * FDGA_SW_WARPS, F0, F, FL, p0, p1, s.d_repvals, sym_dev(s), c0, c1, ctx->g, sc1)
+            const bool cta = sw_cta_per_rep(2 * ctx->g.nPiF);
+            const unsigned nb = cta ? (unsigned)(c1 - c0) : nblk(c1 - c0, FDGA_SW_WARPS);
+#define SWK2b(CHT, MFT, CT) LAUNCH(FDGA_T_K2, (sw_bse_k2_kernel<CHT, MFT, CT>), nb, FDGA_SW_THREADS, F0, F, FL, p0, p1, s.d_repvals, sym_dev(s), c0, c1, ctx->g, sc1)
+#define SWK2(CHT, MFT) do { if (cta) SWK2b(CHT, MFT, true); else SWK2b(CHT, MFT, false); } while (0)
             if (c1 > c0) {
                 if (mfrg) { if (ch == FDGA_PCH) SWK2(CH_P, true); else if (ch == FDGA_TCH) SWK2(CH_T, true); else SWK2(CH_A, true); }
                 else      { if (ch == FDGA_PCH) SWK2(CH_P, false); else if (ch == FDGA_TCH) SWK2(CH_T, false); else SWK2(CH_A, false); }
             }
 #undef SWK2
+#undef SWK2b
             CK(cudaGetLastError());
         }
         return finish_or_defer(ctx, s, ctx->Fbuff.K[ch][1], PK_K2, ch);
@@ -1749,11 +1770,14 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
             const C* Pi = ctx->Pisw[pp ? (reference ? FDGA_PI0PP : FDGA_PIPP) : (reference ? FDGA_PI0PH : FDGA_PIPH)];
             {
                 Scope sc(ctx, FDGA_T_SDE_L);
-                const unsigned nb = nblk(c1 - c0, FDGA_SW_WARPS);
+                const bool cta = sw_cta_per_rep(2 * g.nPiF);
+                const unsigned nb = cta ? (unsigned)(c1 - c0) : nblk(c1 - c0, FDGA_SW_WARPS);
+#define SWSDE(PPT, CT) LAUNCH(FDGA_T_SDE_L, (sw_sde_L_kernel<PPT, CT>), nb, FDGA_SW_THREADS, V, from, Pi, s.d_repvals, sym_dev(s), c0, c1, g, U, g.T)
                 if (c1 > c0) {
-                    if (pp) LAUNCH(FDGA_T_SDE_L, sw_sde_L_kernel<true>, nb, 32 * FDGA_SW_WARPS, V, from, Pi, s.d_repvals, sym_dev(s), c0, c1, g, U, g.T);
-                    else    LAUNCH(FDGA_T_SDE_L, sw_sde_L_kernel<false>, nb, 32 * FDGA_SW_WARPS, V, from, Pi, s.d_repvals, sym_dev(s), c0, c1, g, U, g.T);
+                    if (pp) { if (cta) SWSDE(true, true); else SWSDE(true, false); }
+                    else    { if (cta) SWSDE(false, true); else SWSDE(false, false); }
                 }
+#undef SWSDE
                 CK(cudaGetLastError());
             }
             if (sg_finish(ctx, s, ctx->L[pp ? 0 : 1])) return 1;

@@ -7,23 +7,36 @@
 // kernels and the caches (fdga_kernels.cuh) are shared with the NL2 solver: src/nonlocal/BSEa/BSEa_K3.jl and
 // src/nonlocal/build_K3_cache.jl:18-94 are the NL2 files with Pi[W,w,P,kSW] -> Pi[W,w,P].
 //
-// The contractions are one-dimensional sums over the inner frequency (no momentum sum, no 1/N_q): one warp per class
-// representative, lanes over w.  At BASELINE config 3 the whole K1 / K2 stage is ~1e7 vertex evaluations, far below one
-// NL2 step; these kernels are written for clarity and are bound by launch latency, not by memory or arithmetic.
+// The contractions are one-dimensional sums over the inner frequency (no momentum sum, no 1/N_q).  There are few class
+// representatives (config 3: 240 for K1, ~500 for K2) and up to 2 N_Pi_nu = 1024 inner frequencies each, so the parallelism is
+// taken from the inner sum: CTA = true gives one CTA of FDGA_SW_THREADS threads per representative (long sums over the bubble
+// mesh), CTA = false one warp per representative (the 2 N_K2_nu terms of BSE_L_K2!).
 #pragma once
 #include "fdga_kernels.cuh"
 
 namespace fdga {
 
-#define FDGA_SW_WARPS 4      // warps (= class representatives) per CTA
+#define FDGA_SW_WARPS 4      // warps per CTA
+#define FDGA_SW_THREADS (32 * FDGA_SW_WARPS)
 
-__device__ __forceinline__ C warp_reduce(C v) {
-    for (int o = 16; o > 0; o >>= 1) {
-        v.x += __shfl_down_sync(0xffffffffu, v.x, o);
-        v.y += __shfl_down_sync(0xffffffffu, v.y, o);
+// work split of the contraction kernels: representative handled by this thread, its first inner index and the stride
+template <bool CTA>
+struct SwSplit {
+    long long cls; int first, stride; bool active;
+    __device__ __forceinline__ SwSplit(long long c0, long long c1) {
+        if (CTA) { cls = c0 + blockIdx.x; first = threadIdx.x; stride = FDGA_SW_THREADS; }
+        else { cls = c0 + blockIdx.x * (long long)FDGA_SW_WARPS + (threadIdx.x >> 5); first = threadIdx.x & 31; stride = 32; }
+        active = cls < c1;
     }
-    return v;   // valid in lane 0
-}
+    // sum over the threads of the representative; the result is valid where `leader()` holds
+    __device__ __forceinline__ C reduce(C v) const { return CTA ? block_reduce(v) : warp_reduce_sw(v); }
+    __device__ __forceinline__ bool leader() const { return CTA ? threadIdx.x == 0 : (threadIdx.x & 31) == 0; }
+    static __device__ __forceinline__ C warp_reduce_sw(C v) {
+        for (int o = 16; o > 0; o >>= 1) { v.x += __shfl_down_sync(0xffffffffu, v.x, o); v.y += __shfl_down_sync(0xffffffffu, v.y, o); }
+        return v;
+    }
+};
+
 __device__ __forceinline__ Arg sw_arg(int W, int v, int w, int iP, int L) {
     Arg a; a.W = W; a.v = v; a.w = w; a.Px = iP % L; a.Py = iP / L; a.kx = a.ky = a.qx = a.qy = 0;
     return a;
@@ -47,19 +60,19 @@ __global__ void swave_tables_nl_kernel(DevLevel lv, int NP, SwOut out) {
 }
 
 // ---- BSE_K1!: src/nonlocal/BSEa/BSEa_K1.jl:2-58.  One warp per class representative (W, P) ----
-template <int CH, bool MF>
-__global__ void __launch_bounds__(32 * FDGA_SW_WARPS)
+template <int CH, bool MF, bool CTA>
+__global__ void __launch_bounds__(FDGA_SW_THREADS)
 sw_bse_k1_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ DevChain F, const __grid_constant__ DevChain FL,
                  const C* __restrict__ Pi0, const C* __restrict__ Pi, C* __restrict__ repvals, SymDev sg, long long c0, long long c1, Grid g, double scale) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
-    const long long cls = c0 + blockIdx.x * (long long)FDGA_SW_WARPS + (threadIdx.x >> 5);
-    if (cls >= c1) return;
-    const int lane = threadIdx.x & 31;
+    const SwSplit<CTA> sp(c0, c1);
+    if (!sp.active) return;           // uniform per warp (CTA = false) resp. per CTA
+    const long long cls = sp.cls;
     const long long idx = sg.index[sg.offsets[cls]];
     const int nB1 = 2 * g.nK1 - 1;
     const int W = (int)(idx % nB1) - (g.nK1 - 1), iP = (int)(idx / nB1);
     C acc = zeroC();
-    for (int w = -g.nPiF + lane; w < g.nPiF; w += 32) {
+    for (int w = -g.nPiF + sp.first; w < g.nPiF; w += sp.stride) {
         const size_t pi = piswat(g, W, w, iP);
         const int wc = crossing<CH>(W, w);
         const C FLr = eval_vertex<true>(FL, 0, CH, SP, sw_arg(W, wc, FDGA_INF, iP, g.L), FL_ALL);
@@ -73,8 +86,8 @@ sw_bse_k1_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ De
             acc += Fl * ((p1 - p0) * F0r + p1 * FLr);
         }
     }
-    acc = warp_reduce(acc);
-    if (lane == 0) repvals[cls] = acc * scale;
+    acc = sp.reduce(acc);
+    if (sp.leader()) repvals[cls] = acc * scale;
 }
 
 // K2-shaped representatives (W, v, P)
@@ -85,38 +98,38 @@ __device__ __forceinline__ void decode_k2sw(const Grid& g, long long idx, int& W
 }
 
 // ---- BSE_L_K2!: src/nonlocal/BSEa/BSEa_K2.jl:1-41 (w over the K2 fermionic mesh) ----
-template <int CH>
-__global__ void __launch_bounds__(32 * FDGA_SW_WARPS)
+template <int CH, bool CTA>
+__global__ void __launch_bounds__(FDGA_SW_THREADS)
 sw_bse_lk2_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ DevChain F, const C* __restrict__ Pi0,
                   C* __restrict__ repvals, SymDev sg, long long c0, long long c1, Grid g, double scale) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
     constexpr unsigned FLG = (CH == CH_P ? 0u : FL_GP) | (CH == CH_T ? 0u : FL_GT) | (CH == CH_A ? 0u : FL_GA);
-    const long long cls = c0 + blockIdx.x * (long long)FDGA_SW_WARPS + (threadIdx.x >> 5);
-    if (cls >= c1) return;
-    const int lane = threadIdx.x & 31;
+    const SwSplit<CTA> sp(c0, c1);
+    if (!sp.active) return;
+    const long long cls = sp.cls;
     int W, v, iP; decode_k2sw(g, sg.index[sg.offsets[cls]], W, v, iP);
     C acc = zeroC();
-    for (int w = -g.nK2f + lane; w < g.nK2f; w += 32) {
+    for (int w = -g.nK2f + sp.first; w < g.nK2f; w += sp.stride) {
         const C Gl = eval_vertex<true>(F, 0, CH, SP, sw_arg(W, v, crossing<CH>(W, w), iP, g.L), FLG);
         const C F0r = eval_vertex<true>(F0, 0, CH, SP, sw_arg(W, w, FDGA_INF, iP, g.L), FL_ALL);
         acc += Gl * Pi0[piswat(g, W, w, iP)] * F0r;
     }
-    acc = warp_reduce(acc);
-    if (lane == 0) repvals[cls] = acc * scale;
+    acc = sp.reduce(acc);
+    if (sp.leader()) repvals[cls] = acc * scale;
 }
 
 // ---- BSE_K2!: src/nonlocal/BSEa/BSEa_K2.jl:44-106 (the FL.K2 add is the caller's post-fix) ----
-template <int CH, bool MF>
-__global__ void __launch_bounds__(32 * FDGA_SW_WARPS)
+template <int CH, bool MF, bool CTA>
+__global__ void __launch_bounds__(FDGA_SW_THREADS)
 sw_bse_k2_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ DevChain F, const __grid_constant__ DevChain FL,
                  const C* __restrict__ Pi0, const C* __restrict__ Pi, C* __restrict__ repvals, SymDev sg, long long c0, long long c1, Grid g, double scale) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
-    const long long cls = c0 + blockIdx.x * (long long)FDGA_SW_WARPS + (threadIdx.x >> 5);
-    if (cls >= c1) return;
-    const int lane = threadIdx.x & 31;
+    const SwSplit<CTA> sp(c0, c1);
+    if (!sp.active) return;
+    const long long cls = sp.cls;
     int W, v, iP; decode_k2sw(g, sg.index[sg.offsets[cls]], W, v, iP);
     C acc = zeroC();
-    for (int w = -g.nPiF + lane; w < g.nPiF; w += 32) {
+    for (int w = -g.nPiF + sp.first; w < g.nPiF; w += sp.stride) {
         const size_t pi = piswat(g, W, w, iP);
         const int wc = crossing<CH>(W, w);
         if (MF) {
@@ -131,23 +144,23 @@ sw_bse_k2_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ De
             acc += Fl * ((p1 - p0) * F0r + p1 * FLr);
         }
     }
-    acc = warp_reduce(acc);
-    if (lane == 0) repvals[cls] = acc * scale;
+    acc = sp.reduce(acc);
+    if (sp.leader()) repvals[cls] = acc * scale;
 }
 
 // ---- SDE_channel_L_pp! / ph!: src/nonlocal/SDE.jl:3-146.  The levels `from..nlev-1` of the chain are summed in one pass
 // (the rest of SDE_compute! is linear in L): own reducible vertex of a Vertex / NL_Vertex level, (core - bare) / 3 of the
 // RefVertex level (SDE.jl:179-183) ----
-template <bool PP>
-__global__ void __launch_bounds__(32 * FDGA_SW_WARPS)
+template <bool PP, bool CTA>
+__global__ void __launch_bounds__(FDGA_SW_THREADS)
 sw_sde_L_kernel(const __grid_constant__ DevChain V, int from, const C* __restrict__ Pi, C* __restrict__ repvals, SymDev sg,
                 long long c0, long long c1, Grid g, C U, double scale) {
-    const long long cls = c0 + blockIdx.x * (long long)FDGA_SW_WARPS + (threadIdx.x >> 5);
-    if (cls >= c1) return;
-    const int lane = threadIdx.x & 31;
+    const SwSplit<CTA> sp(c0, c1);
+    if (!sp.active) return;
+    const long long cls = sp.cls;
     int W, v, iP; decode_k2sw(g, sg.index[sg.offsets[cls]], W, v, iP);
     C acc = zeroC();
-    for (int w = -g.nPiF + lane; w < g.nPiF; w += 32) {
+    for (int w = -g.nPiF + sp.first; w < g.nPiF; w += sp.stride) {
         C d = zeroC();
         for (int l = from; l < V.nlev; ++l) {
             const DevLevel& lv = V.lev[l];
@@ -164,8 +177,16 @@ sw_sde_L_kernel(const __grid_constant__ DevChain V, int from, const C* __restric
         }
         acc += U * Pi[piswat(g, W, w, iP)] * d;
     }
-    acc = warp_reduce(acc);
-    if (lane == 0) repvals[cls] = acc * scale;
+    acc = sp.reduce(acc);
+    if (sp.leader()) repvals[cls] = acc * scale;
+}
+
+// the elements R of the window [-h, h] with R = t (mod n), 0 <= t < n (n >= 2h): at most two
+__device__ __forceinline__ int window_images(int t, int n, int h, int* out) {
+    int k = 0;
+    if (t <= h) out[k++] = t;
+    if (t - n >= -h) out[k++] = t - n;
+    return k;
 }
 
 // ---- bubbles_real_space!(::NL_MF_Pi): src/nonlocal/bubble.jl:87-158.  GR = fft(G) / LG^2 [nu, R].  Real-space fill in gather
@@ -181,10 +202,12 @@ __global__ void sw_bubbles_rs_kernel(const C* __restrict__ GR, C* __restrict__ P
     const int W = iW - (g.nPiB - 1), w = iw - g.nPiF, tx = iR % L, ty = iR / L;
     const double pi = 3.14159265358979323846;
     C pp = zeroC(), ph = zeroC();
-    for (int R2 = -h; R2 <= h; ++R2) {
-        if (modL(R2, L) != ty) continue;
-        for (int R1 = -h; R1 <= h; ++R1) {
-            if (modL(R1, L) != tx) continue;
+    // the R in [-h, h] with R = t (mod L): t itself and t - L (both at the zone edge of an even mesh)
+    int c1[2], c2[2]; const int n1 = window_images(tx, L, h, c1), n2 = window_images(ty, L, h, c2);
+    for (int i2 = 0; i2 < n2; ++i2) {
+        const int R2 = c2[i2];
+        for (int i1 = 0; i1 < n1; ++i1) {
+            const int R1 = c1[i1];
             double wt = 1.0;
             if (LG % 2 == 0) { if (abs(R1) == LG / 2) wt *= 0.5; if (abs(R2) == LG / 2) wt *= 0.5; }
             const bool tail = use_tail && R1 == 0 && R2 == 0;
@@ -201,6 +224,43 @@ __global__ void sw_bubbles_rs_kernel(const C* __restrict__ GR, C* __restrict__ P
     PippR[i] = pp; PiphR[i] = ph;
 }
 
+// The same bubbles without the bubble-sized transforms (default route; the kernel above + two DFT passes is the literal one,
+// FDGA_BUBBLES_RS=1).  Pi(R)[W,w] vanishes unless BOTH frequencies lie on the G mesh -- 2 N_G of the 2 N_Pi_nu inner frequencies
+// (32 of 1024 at config 3) -- except for the tail, which only lives at R = 0 and is therefore P-independent.  So
+//   both on the mesh:  Pi[W,w,P] = sum_{R in window} wt(R) G(a,R) G(w,+-R) exp(+2 pi i P.R / L)   (the back transform as a direct sum)
+//   otherwise:         Pi[W,w,P] = g~(a) g~(w)  with the local G (R = 0) continued by 1/nu   (0 without the tail).
+__global__ void sw_bubbles_direct_kernel(const C* __restrict__ GR, C* __restrict__ Pipp, C* __restrict__ Piph, Grid g, int use_tail,
+                                         const C* __restrict__ twL) {
+    const int nBP = 2 * g.nPiB - 1, nFP = 2 * g.nPiF, L = g.L, LG = g.LG, NP = g.NP, nG = g.nG, h = L / 2;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)nBP * nFP * NP) return;
+    long long t = i;
+    const int iW = t % nBP; t /= nBP; const int iw = t % nFP; const int iP = (int)(t / nFP);
+    const int W = iW - (g.nPiB - 1), w = iw - g.nPiF, Px = iP % L, Py = iP / L;
+    const double pi = 3.14159265358979323846;
+    const bool bin = inF(w, nG);
+    auto tail = [&](int n) { return mkC(1.0 / ((2 * n + 1) * pi * g.T), 0.0); };
+    const int app = W - w - 1, aph = W + w;
+    const bool pin = inF(app, nG) && bin, hin = inF(aph, nG) && bin;
+    C pp = zeroC(), ph = zeroC();
+    if (pin || hin) {
+        for (int R2 = -h; R2 <= h; ++R2) for (int R1 = -h; R1 <= h; ++R1) {
+            double wt = 1.0;
+            if (LG % 2 == 0) { if (abs(R1) == LG / 2) wt *= 0.5; if (abs(R2) == LG / 2) wt *= 0.5; }
+            const size_t pR = (size_t)2 * nG * (modL(R1, LG) + (size_t)LG * modL(R2, LG)), mR = (size_t)2 * nG * (modL(-R1, LG) + (size_t)LG * modL(-R2, LG));
+            const C ph_ = twL[modL(Px * R1 + Py * R2, L)] * wt;
+            if (pin) pp += GR[posF(app, nG) + pR] * GR[posF(w, nG) + pR] * ph_;
+            if (hin) ph += GR[posF(aph, nG) + pR] * GR[posF(w, nG) + mR] * ph_;
+        }
+    }
+    if (use_tail) {
+        const C gb = bin ? GR[posF(w, nG)] : tail(w);
+        if (!pin) pp = (inF(app, nG) ? GR[posF(app, nG)] : tail(app)) * gb;
+        if (!hin) ph = (inF(aph, nG) ? GR[posF(aph, nG)] : tail(aph)) * gb;
+    }
+    Pipp[i] = pp; Piph[i] = ph;
+}
+
 // ---- SDE_compute_inner! (use_real_space = true): src/nonlocal/SDE.jl:191-275.  LppR / LphR = fft(L) / L^2 over the momentum
 // axis [W, v, R]; GR = fft(G) / LG^2.  Gather form, one thread per (nu, target R of Sigma):
 //   Sigma( R) += G(W - nu, -R) Lpp(W, nu, R) wt,   Sigma(-R) += G(W + nu, -R) Lph(W, nu, R) wt,   R in [-L/2, L/2]^2 ----
@@ -213,7 +273,16 @@ __global__ void sw_sde_rs_kernel(const C* __restrict__ GR, const C* __restrict__
     C acc = zeroC();
     if (inF(v, g.nK2f)) {
         const size_t pre = (size_t)nB * nF;
-        for (int R2 = -h; R2 <= h; ++R2) for (int R1 = -h; R1 <= h; ++R1) {
+        // sources R with R = t (pp term) or -R = t (ph term) modulo LG, both inside the window: the images of t and of -t
+        int cand1[4], cand2[4];
+        int n1 = window_images(tx, LG, h, cand1), n2 = window_images(ty, LG, h, cand2);
+        n1 += window_images(modL(-tx, LG), LG, h, cand1 + n1); n2 += window_images(modL(-ty, LG), LG, h, cand2 + n2);
+        for (int i2 = 0; i2 < n2; ++i2) for (int i1 = 0; i1 < n1; ++i1) {
+            const int R1 = cand1[i1], R2 = cand2[i2];
+            bool dup = false;       // t = -t (mod LG) lists the same R twice
+            for (int j = 0; j < i1; ++j) dup = dup || cand1[j] == R1;
+            for (int j = 0; j < i2; ++j) dup = dup || cand2[j] == R2;
+            if (dup) continue;
             const bool hit_p = modL(R1, LG) == tx && modL(R2, LG) == ty, hit_m = modL(-R1, LG) == tx && modL(-R2, LG) == ty;
             if (!hit_p && !hit_m) continue;
             double wt = 1.0;

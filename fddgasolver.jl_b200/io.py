@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 from . import h5min
-from .types import NL2_Vertex, RefVertex, Vertex
+from .types import NL2_Vertex, NL_Vertex, RefVertex, Vertex
 
 
 def _mats_mesh(kind, T, N):
@@ -57,20 +57,21 @@ def load_mesh_function(group):
 def _channel_spec(g, nonlocal_L=None):
     T = g.T
     bz = [] if nonlocal_L is None else [_bz_mesh(nonlocal_L)]
+    bz2 = bz * (g.K2.ndim - 2)          # NL2_Channel: K2[Ω,ν,P,k]; NL_Channel: K2[Ω,ν,P]
     return h5min.GroupSpec({
         "K1": mesh_function_spec(g.K1, [_mats_mesh("Boson", T, g.numK1)] + bz),
-        "K2": mesh_function_spec(g.K2, [_mats_mesh("Boson", T, g.numK2[0]), _mats_mesh("Fermion", T, g.numK2[1])] + bz + bz),
+        "K2": mesh_function_spec(g.K2, [_mats_mesh("Boson", T, g.numK2[0]), _mats_mesh("Fermion", T, g.numK2[1])] + bz2),
         "K3": mesh_function_spec(g.K3, [_mats_mesh("Boson", T, g.numK3[0]), _mats_mesh("Fermion", T, g.numK3[1]),
                                         _mats_mesh("Fermion", T, g.numK3[1])] + bz)})
 
 
 def vertex_spec(F):
-    """save!(file, label, F) for RefVertex / Vertex / NL2_Vertex (recursively through F.F0)"""
+    """save!(file, label, F) for RefVertex / Vertex / NL2_Vertex / NL_Vertex (recursively through F.F0)"""
     if isinstance(F, RefVertex):
         ms = [_mats_mesh("Boson", F.T, F.numK3[0]), _mats_mesh("Fermion", F.T, F.numK3[1]), _mats_mesh("Fermion", F.T, F.numK3[1])]
         return h5min.GroupSpec({n: mesh_function_spec(getattr(F, n), ms) for n in ("Fp_p", "Fp_x", "Ft_p", "Ft_x")},
                                attrs={"U": np.complex128(F.U)})
-    L = getattr(F, "L", None) if isinstance(F, NL2_Vertex) else None
+    L = getattr(F, "L", None) if isinstance(F, (NL2_Vertex, NL_Vertex)) else None
     return h5min.GroupSpec({"F0": vertex_spec(F.F0), "γp": _channel_spec(F.γp, L), "γt": _channel_spec(F.γt, L), "γa": _channel_spec(F.γa, L)})
 
 
@@ -107,8 +108,10 @@ def load_vertex(group):
         F = Vertex(F0, T, n1, n2, n3)
     elif len(m2) == 4:
         F = NL2_Vertex(F0, T, n1, n2, n3, m1[1]["L"])
+    elif len(m2) == 3:
+        F = NL_Vertex(F0, T, n1, n2, n3, m1[1]["L"])
     else:
-        raise h5min.H5Error(f"{group.name}: vertex type with a {len(m2)}-axis K2 is outside this package's scope (NL / NL3 / MBE)")
+        raise h5min.H5Error(f"{group.name}: vertex type with a {len(m2)}-axis K2 is outside this package's scope (NL3 / MBE)")
     for n in ("γp", "γt", "γa"):
         _load_channel_into(getattr(F, n), group[n])
     return F
@@ -142,7 +145,7 @@ def solver_spec(S):
         tree[n] = mesh_function_spec(getattr(S, n), [_mats_mesh("Fermion", T, S.nG), _bz_mesh(LG)])
     for n in _PI_NAMES:
         a = getattr(S, n)
-        tree[n] = mesh_function_spec(a, [_mats_mesh("Boson", T, (a.shape[0] + 1) // 2), _mats_mesh("Fermion", T, a.shape[1] // 2), _bz_mesh(L), _bz_mesh(L)])
+        tree[n] = mesh_function_spec(a, [_mats_mesh("Boson", T, (a.shape[0] + 1) // 2), _mats_mesh("Fermion", T, a.shape[1] // 2)] + [_bz_mesh(L)] * (a.ndim - 2))
     tree["F0"] = vertex_spec(S.F0)
     tree["F"] = vertex_spec(S.F)
     return tree

@@ -201,3 +201,84 @@ def test_swave_converged_fdPA_matches_scPA_on_device(orc):
         assert np.max(np.abs(d)) < tol, (cls, ch, np.max(np.abs(d)))
     for X in (S0, S, Sfd):
         X.close()
+
+
+def test_swave_dqgmres_and_preconditioned_fixed_point(orc):
+    import fddgasolver_jl_b200 as fd
+    S, R = make_pair(orc)
+    rng = np.random.default_rng(7)
+    n = S.length_F()
+    assert n == len(R.F)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    xg, sg = fd.dqgmres(fd.mfRGLinearMap(S), b, memory=5, atol=1e-9, rtol=1e-9, itmax=30)
+    xo, so = orc.dqgmres(orc.mfRGLinearMap(R), b, memory=5, atol=1e-9, rtol=1e-9, itmax=30)
+    assert sg["niter"] == so["niter"] and sg["solved"] == so["solved"]
+    assert np.max(np.abs(np.array(so["residuals"]) - np.array(sg["residuals"])) / so["residuals"][0]) < 1e-9
+    assert rel(xg, xo) < 1e-8
+    x = S.F.flatten() * (1.0 + 0.05 * rng.standard_normal(n))
+    Rg, Ro = np.zeros_like(x), np.zeros_like(x)
+    a = fd.fixed_point_preconditioned(Rg, x, S, strategy="fdPA", use_preconditioner=True, krylov_maxiter=25, memory=8)
+    c = orc.fixed_point_preconditioned(Ro, x, R, strategy="fdPA", use_preconditioner=True, krylov_maxiter=25, memory=8)
+    assert a == c and rel(Rg, Ro) < 1e-8
+    S.close()
+
+
+def test_swave_solve_using_mfRG_outer_loop_and_checkpoint(orc, tmp_path):
+    """solve_using_mfRG! with the s-wave solver (the call of script/run_Wu_point.jl:100 for nl_method = 1) against the oracle's
+    restatement: bubble mixing, chemical potential, preconditioned Anderson, SDE, reference update; then a checkpoint written by
+    save_solver restores the device state of a fresh solver"""
+    import fddgasolver_jl_b200 as fd
+    T, U, nG, LG, L = 0.5, 2.0, 8, 6, 3
+    hp = {"t1": 1.0, "t2": -0.3}
+    Gb = fd.hubbard_bare_Green(T, nG, LG, μ=0.3, **hp)
+    G0 = fd.hubbard_bare_Green(T, nG, LG, μ=0.1, **hp)
+    mk = lambda: fd.NL_Vertex(fd.RefVertex(T, U), T, 8, (2, 2), (2, 2), L)
+    new = lambda: fd.NL_ParquetSolver(8, (2, 2), (2, 2), L, Gb, G0, np.zeros_like(G0), mk(), T=T, mΠν_factor=4)
+    S = new(); S.init_sym_grp()
+    R = orc.OracleNLSolver(8, (2, 2), (2, 2), L, Gb, G0, np.zeros_like(G0), mk(), T=T, mΠν_factor=4)
+    R.init_sym_grp()
+    kw = dict(occ_target=0.45, hubbard_params=hp, mixing_init=0.5, tol=1e-5, strategy="fdPA", anderson_iterations=30, krylov_maxiter=40, memory=10)
+    hg = fd.solve_using_mfRG(S, maxiter=2, **kw)
+    ho = orc.solve_using_mfRG(R, maxiter=2, **kw)
+    assert len(hg["Σ_err"]) == len(ho["Σ_err"]) == 2 and hg["mixing"] == ho["mixing"]
+    assert np.allclose(hg["Σ_err"], ho["Σ_err"], rtol=1e-4) and np.allclose(hg["μ"], ho["μ"], rtol=0, atol=1e-5)
+    S.pull("F", "F0", "Σ", "Σ0", "G", "G0", "Π")
+    assert S.Πpp.ndim == 3
+    assert rel(S.Σ0, R.Σ0) < 1e-4 and rel(S.G, R.G) < 1e-4 and rel(S.Π0pp, R.Π0pp) < 1e-4 and rel(S.Πph, R.Πph) < 1e-4
+    for a, b in zip(S.F0.channels(), R.F0.channels()):
+        for x, y in zip(a.arrays(), b.arrays()):
+            assert rel(x, y) < 1e-4
+    assert np.max(np.abs(S.F0.flatten())) > 0.02 and not np.any(S.F.flatten())
+    # checkpoint round trip through the reference's file layout
+    path = str(tmp_path / "swave.iter2.h5")
+    fd.save_solver(S, path, extra={"mixing": hg["mixing"][-1]})
+    S2 = new(); S2.init_sym_grp()
+    fd.load_solver(S2, path)
+    fd.iterate_solver(S, "fdPA"); fd.iterate_solver(S2, "fdPA")
+    S.pull("F", "Σ"); S2.pull("F", "Σ")
+    assert rel(S.F.flatten(), S2.F.flatten()) < 1e-13 and rel(S.Σ, S2.Σ) < 1e-13
+    S.close(); S2.close()
+
+
+@pytest.mark.slow
+def test_swave_fullsize_config3_iteration_and_matvec(orc):
+    """BASELINE config 3 sizes with the s-wave solver on the reference's DMFT data (script/run_Wu_point.jl, nl_method = 1):
+    nmax = 4, nq = 8, LG = 48, bubble mesh 16 x 512 (mΠν_factor = 32).  One complete fdPA iteration with the self-energy update
+    and one mfRG matvec, every array compared un-sampled."""
+    import fddgasolver_jl_b200 as fd
+    S = fd.wu_point_solver(nmax=4, nq=8, LG=48, nl_method=1, F_scale=0.05, F0_scale=0.02)
+    assert S.nΠF == 512 and S.F.γp.K2.shape == (7, 8, 64)
+    R = orc.OracleNLSolver(S.nK1, S.nK2, S.nK3, S.L, S.Gbare, S.G0, S.Σ0, S.F0, T=S.T)
+    R.init_sym_grp()
+    R.F.set(S.F)
+    S.pull("Π")
+    for n in ("Π0pp", "Π0ph", "Πpp", "Πph"):
+        assert rel(getattr(S, n), getattr(R, n)) < TOL, n
+    fd.iterate_solver(S, "fdPA"); orc.iterate_solver(R, "fdPA")
+    S.pull("F", "FL", "Σ", "G")
+    compare_vertex(S.F, R.F, "F")
+    compare_vertex(S.FL, R.FL, "FL", ("K2", "K3"))
+    assert rel(S.Σ, R.Σ) < TOL and rel(S.G, R.G) < TOL
+    x = S.F.flatten() * 2.0
+    assert rel(fd.mfRGLinearMap(S).matvec(x), orc.mfRGLinearMap(R).matvec(x)) < TOL
+    S.close()

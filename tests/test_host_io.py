@@ -62,6 +62,19 @@ def test_vertex_round_trip_through_the_reference_layout(tmp_path):
         assert np.array_equal(a, b)
 
 
+def test_swave_vertex_round_trip(tmp_path):
+    """test/test_nonlocal_vertex.jl:154-166, test/test_nonlocal_solver.jl:47-62: save! / load_vertex(NL_Vertex, ...)"""
+    T = 0.3
+    V = fd.NL_Vertex(fd.RefVertex(T, 3.0), T, 10, (4, 3), (2, 1), 3)
+    fd.randomize_vertex(V, 5, 0.5)
+    p = str(tmp_path / "nl.h5")
+    h5min.write_file(p, {"f": io.vertex_spec(V)})
+    f = h5min.File(p)
+    assert f["f/γt/K2/data"].shape == V.γt.K2.shape[::-1] and len(f["f/γt/K2/meshes"].keys()) == 3
+    W = io.load_vertex(f["f"])
+    assert isinstance(W, fd.NL_Vertex) and W.L == 3 and np.array_equal(W.flatten(), V.flatten())
+
+
 def _fake_solver(seed):
     rng = np.random.default_rng(seed)
     T, L, LG, nG = 0.25, 3, 6, 4

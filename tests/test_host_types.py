@@ -45,3 +45,22 @@ def test_flatten_order_matches_the_independent_restatement():
         for u, v in zip(ga.arrays(), gb.arrays()):
             assert np.array_equal(u, v)
     assert np.array_equal(b.flatten(), y)
+
+
+def test_swave_vertex_shapes_and_flatten_order():
+    """NL_Vertex (src/nonlocal/vertex.jl, channel.jl:3-51): K2[Ω, ν, P]; same flatten order; test/test_nonlocal_solver.jl:39-45"""
+    T = 0.3
+    a = fd.NL_Vertex(fd.Vertex(fd.RefVertex(T, 1.0), T, 6, (4, 3), (2, 2)), T, 5, (3, 2), (2, 1), 3)
+    assert a.γp.K1.shape == (9, 9) and a.γp.K2.shape == (5, 4, 9) and a.γp.K3.shape == (3, 2, 2, 9)
+    fd.randomize_vertex(a, 11, 1.0)
+    b = ot.adopt(a)
+    assert isinstance(b, ot.ONL_Vertex) and isinstance(b.F0, ot.OVertex)
+    x = a.flatten()
+    assert np.array_equal(x, b.flatten()) and len(a) == len(b) == x.size
+    g = a.γa
+    iW, iv, iP = 3, 2, 5
+    pos = 2 * len(a.γp) + g.K1.size + iW + g.K2.shape[0] * (iv + g.K2.shape[1] * iP)
+    assert x[pos] == g.K2[iW, iv, iP]
+    c = fd.NL_Vertex(a.F0, T, 5, (3, 2), (2, 1), 3)
+    c.unflatten(x)
+    assert np.array_equal(c.γa.K3, a.γa.K3) and np.array_equal(c.flatten(), x)
