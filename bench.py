@@ -37,12 +37,17 @@ def parse():
     p.add_argument("--nmax", type=int, default=4)
     p.add_argument("--nq", type=int, default=8)
     p.add_argument("--LG", type=int, default=48)
+    p.add_argument("--nl-method", type=int, default=2, choices=[1, 2],
+                   help="2 (default, the headline): NL2_ParquetSolver; 1: the s-wave NL_ParquetSolver of script/run_Wu_point.jl (side workload)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the mfRG matvec / DQGMRES side measurements (large sweep sizes)")
     return p.parse_args()
 
 
 def workload_name(a):
+    if a.nl_method == 1:
+        return (f"s-wave NL_ParquetSolver, Wu point U=5.6 T=0.2 (script/run_Wu_point.jl, nl_method=1): nmax={a.nmax} (nK1={4 * a.nmax}, "
+                f"nK2=nK3=({a.nmax},{a.nmax})), nq={a.nq}, LG={a.LG}, bubble mesh {4 * a.nmax} x {128 * a.nmax} (m_Pi_nu_factor=32)")
     return f"NL2 Wu point U=5.6 T=0.2 (script/benchmark_Wu.jl): nmax={a.nmax} (nK1={4 * a.nmax}, nK2=nK3=({a.nmax},{a.nmax})), nq={a.nq}, LG={a.LG}"
 
 
@@ -115,7 +120,8 @@ def cpu_full_iteration(o, R, F_start):
 
 
 def make_oracle_solver(o, inp, share_bubbles_from=None):
-    R = o.OracleSolver(inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"], T=inp["T"],
+    cls = o.OracleNLSolver if inp["F"].γp.K2.ndim == 3 else o.OracleSolver
+    R = cls(inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"], T=inp["T"],
                        compute_bubbles=share_bubbles_from is None)
     if share_bubbles_from is not None:
         S = share_bubbles_from
@@ -138,7 +144,7 @@ def run_reference(a):
     import oracle as o
     o.build()
     cores = host_threads(o)
-    inp = fd.wu_point_inputs(a.nmax, a.nq, a.LG, F0_scale=0.02)
+    inp = fd.wu_point_inputs(a.nmax, a.nq, a.LG, F0_scale=0.02, nl_method=a.nl_method)
     R = make_oracle_solver(o, inp)
     budget = float(os.environ.get("FDGA_REF_BUDGET_S", "150"))
     t_warm, _ = cpu_full_iteration(o, R, inp["F"]) if a.warmup > 0 else (0.0, None)      # one full warm-up pass (threads, page faults)
@@ -176,8 +182,9 @@ def run_ours(a):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    inp = fd.wu_point_inputs(a.nmax, a.nq, a.LG, F0_scale=0.02)
-    S = fd.NL2_ParquetSolver(inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"], T=inp["T"], device=local)
+    inp = fd.wu_point_inputs(a.nmax, a.nq, a.LG, F0_scale=0.02, nl_method=a.nl_method)
+    Solver = fd.NL_ParquetSolver if a.nl_method == 1 else fd.NL2_ParquetSolver
+    S = Solver(inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"], T=inp["T"], device=local)
     S.F.set(inp["F"]); S.push("F"); S.init_sym_grp()
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8)
@@ -265,6 +272,10 @@ def run_ours(a):
     bytes_per_launch = nB2 * NP * nFΠ * NP * 16 / world + tables + np.mean(chunk) * 16      # R slabs of the K2 bosonic box + vertex tables + outputs
     flop_per_launch = 26.0 * np.mean(chunk) * nFΠ * NP                                       # 26 flop per (representative, w, q) term
     k2 = kernels.get("column_K2", {"ms_per_step": float("nan"), "launches_per_step": 3})
+    if a.nl_method == 1:        # s-wave solver: no inner momentum sum; one launch reads its representatives' two bubble rows + the tables
+        bytes_per_launch = np.mean(chunk) * nFΠ * 2 * 16 + tables + np.mean(chunk) * 16
+        flop_per_launch = 40.0 * np.mean(chunk) * nFΠ
+        k2 = kernels.get("K2", k2)
     k2_ms_launch = k2["ms_per_step"] / max(k2["launches_per_step"], 1)
     peaks = {}
     try:
@@ -280,12 +291,13 @@ def run_ours(a):
     except Exception:
         pass
     ach = bytes_per_launch / (k2_ms_launch * 1e-3) / 1e9
-    roofline = {"kernel": "qlane_kernel<JOB_K2> (BSE_K2!, src/nonlocal_2/BSEa/BSEa_K2.jl:55-138), mean over the p, t, a launches", "bound": "hbm", "achieved": ach, "peak": peak_hbm,
+    roofline = {"kernel": ("sw_bse_k2_kernel (BSE_K2!, src/nonlocal/BSEa/BSEa_K2.jl:44-106), mean over the p, t, a launches" if a.nl_method == 1 else
+                           "qlane_kernel<JOB_K2> (BSE_K2!, src/nonlocal_2/BSEa/BSEa_K2.jl:55-138), mean over the p, t, a launches"), "bound": "hbm", "achieved": ach, "peak": peak_hbm,
                 "unit": "GB/s", "frac": ach / peak_hbm,
                 "traffic": None if traffic is None else traffic["dram_bytes_per_launch"], "traffic_detail": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": k2_ms_launch,
-                "note": "not HBM-bound: a gather contraction whose tables and slabs are L2-resident (DRAM traffic below the algorithmic bytes); bounded by L2 -> L1 latency at the occupancy its registers allow, see fp64 and DESIGN.md section 4",
+                "note": "latency-bound: ~500 class representatives x 1024 inner frequencies per launch, a few MB of L2-resident tables" if a.nl_method == 1 else "not HBM-bound: a gather contraction whose tables and slabs are L2-resident (DRAM traffic below the algorithmic bytes); bounded by L2 -> L1 latency at the occupancy its registers allow, see fp64 and DESIGN.md section 4",
                 "l2": None if (traffic is None or not traffic.get("l2_to_l1_bytes_per_launch")) else {
                     "bytes_per_launch": traffic["l2_to_l1_bytes_per_launch"], "achieved_tbs": traffic["l2_to_l1_bytes_per_launch"] / (k2_ms_launch * 1e-3) / 1e12,
                     "peak_tbs": 6300 * 1.965e9 / 1e12, "frac": traffic["l2_to_l1_bytes_per_launch"] / (k2_ms_launch * 1e-3) / (6300 * 1.965e9),

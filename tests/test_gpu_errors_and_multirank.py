@@ -59,14 +59,18 @@ def test_two_ranks_nccl_match_one_rank():
         pytest.skip("needs 2 GPUs")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
 
-    def run(n):
+    def run(n, extra=()):
         cmd = [sys.executable]
         if n > 1:
             cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", "29577"]
-        cmd += [os.path.join(ROOT, "bench.py"), "--gpus", str(n), "--steps", "3", "--warmup", "3", "--nmax", "3", "--nq", "4", "--LG", "8", "--no-cpu-baseline"]
+        cmd += [os.path.join(ROOT, "bench.py"), "--gpus", str(n), "--steps", "3", "--warmup", "3", "--nmax", "3", "--nq", "4", "--LG", "8", "--no-cpu-baseline"] + list(extra)
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
         assert out.returncode == 0, out.stderr[-2000:]
         return json.loads(out.stdout.strip().splitlines()[-1])
     a, b = run(1), run(2)
     assert abs(a["state_checksum"] - b["state_checksum"]) <= 1e-10 * abs(a["state_checksum"])
+    assert b["n_gpus"] == 2 and "comm" in b["kernels"]
+    # the s-wave solver shards the same way (class representatives of K1 / K2[W,v,P] / K3, one batched all-gather per stage)
+    a, b = run(1, ("--nl-method", "1")), run(2, ("--nl-method", "1"))
+    assert "s-wave" in a["config"]["workload"] and abs(a["state_checksum"] - b["state_checksum"]) <= 1e-10 * abs(a["state_checksum"])
     assert b["n_gpus"] == 2 and "comm" in b["kernels"]
