@@ -39,6 +39,7 @@ def parse():
     p.add_argument("--LG", type=int, default=48)
     p.add_argument("--nl-method", type=int, default=2, choices=[1, 2],
                    help="2 (default, the headline): NL2_ParquetSolver; 1: the s-wave NL_ParquetSolver of script/run_Wu_point.jl (side workload)")
+    p.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying its CUDA graph (1 GPU)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the mfRG matvec / DQGMRES side measurements (large sweep sizes)")
     return p.parse_args()
@@ -212,7 +213,7 @@ def run_ours(a):
         fd.iterate_solver(S, "fdPA", update_Σ=False)
         fd.SDE(S, "scPA")
 
-    def step_e2e():
+    def e2e_device_part():
         if world == 1:
             S.unflatten_F_async(x_np)                   # H2D of this step's input vertex
         else:
@@ -221,9 +222,29 @@ def run_ours(a):
         if rank == 0:
             S.flatten_F_async(y_np)                     # D2H of the updated vertex (the job's result leaves through rank 0),
         fd.SDE(S, "scPA")                               # ... overlapping the SDE
+
+    def step_e2e():
+        e2e_device_part()
         if rank == 0:
             S.get_green_into("Σ", s_np)                 # D2H of the self-energy
         S.sync()                                        # both copies have landed
+
+    # one GPU: a step is ~80 small dependent kernels on three lanes; it is recorded once as a CUDA graph (fdga_graph_begin / _end)
+    # and every timed step is one replay of it -- same kernels, same order, bit-identical state (tools/graph_check.py)
+    use_graph = world == 1 and not a.no_graph
+    step_resident_eager, step_e2e_eager = step_resident, step_e2e
+
+    def make_graph_steps():
+        step_resident_eager(); step_resident_eager()
+        g1 = S.record(step_resident_eager)
+        step_e2e_eager(); step_e2e_eager()
+        g2 = S.record(e2e_device_part)
+
+        def e2e_graph():
+            S.replay(g2)
+            S.get_green_into("Σ", s_np)
+            S.sync()
+        return (lambda: S.replay(g1)), e2e_graph
 
     def timed(step, K, W):
         for _ in range(W):
@@ -244,6 +265,8 @@ def run_ours(a):
         return ms, S.total_launches() - n0
 
     S.unflatten_F(x_np); S.stash_F()
+    if use_graph:
+        step_resident, step_e2e = make_graph_steps()
     W = max(a.warmup, 3)
     clocks = ClockSampler(local)
     if rank == 0:
@@ -258,7 +281,7 @@ def run_ours(a):
     S.profile(True); S.profile_reset()
     PS = min(a.steps, 5)
     for _ in range(PS):
-        step_resident()
+        step_resident_eager()
     kt = S.kernel_times()
     S.profile(False)
     kernels = {k: {"ms_per_step": v[0] / PS, "launches_per_step": v[1] / PS} for k, v in kt.items() if v[1]}
@@ -333,7 +356,7 @@ def run_ours(a):
 
     # state fingerprint after one more iteration from the stashed vertex: identical on every rank and for every N
     import hashlib
-    step_resident()
+    step_resident_eager()
     S.flatten_F(y_np); S.get_green_into("Σ", s_np)
     digest = hashlib.sha1(y_np.tobytes() + s_np.tobytes()).hexdigest()[:16]
     checksum = float(np.abs(y_np).sum() + np.abs(s_np).sum())
@@ -368,7 +391,8 @@ def run_ours(a):
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex)", "data": inp["data"],
                "config": {"workload": workload_name(a), "l2": "inputs larger than L2, nothing flushed between steps: K2 tables of S.F, S.F0, S.F + S.F0, FL, Fbuff and their momentum-fastest copies %.0f MB + compact bubble slabs and right factors (only the (W,P) slabs with class representatives) + scratch tables, against 126 MB of L2" % (16e-6 * S.F.γp.K2.size * 3 * 14),
                           "symmetry_classes": {"K1": S.num_classes(fd._lib.SG_K1), "K2pp": n2cls[0], "K2ph": n2cls[1], "K3pp": S.num_classes(fd._lib.SG_PP3), "K3ph": S.num_classes(fd._lib.SG_PH3)},
-                          "parallelism": f"class representatives sharded over {world} rank(s), NCCL all-gather per kernel" if world > 1 else "1 GPU"},
+                          "parallelism": f"class representatives sharded over {world} rank(s), NCCL all-gather per kernel" if world > 1 else "1 GPU",
+                          "issue": "every timed step is one replay of the step's CUDA graph (recorded once from the same library calls)" if use_graph else "eager launches"},
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(nF * 16), "d2h_bytes_per_step": int(nF * 16 + S.Σ.size * 16), "ms_per_step": ms_e2e / a.steps},
                "gpu_launches": int(launches), "mfrg_matvecs_per_sec_e2e": mfrg_per_s, "mfrg_dqgmres_iterations_per_sec_device_resident": krylov_per_s, "state_sha1": digest, "state_checksum": checksum, "device_memory_gb_per_rank": mem_all, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
         print(json.dumps(out))

@@ -52,6 +52,9 @@ struct SymGroup {
     int nrep; int4* d_reps;   // the same representatives, slab-major, one per warp of qlane_kernel
 };
 struct TimedEvent { cudaEvent_t a, b; int cat; };
+// a recorded sequence of calls (fdga_graph_begin / _end): the instantiated graph, the kernel launches it holds, and the lazy-state
+// signature / allocation epoch it was recorded under (a replay is only valid from the same state)
+struct GraphRec { cudaGraphExec_t exec; cudaGraph_t graph; long long launches; long long n_launch[FDGA_T_COUNT]; std::vector<long long> sig; long long epoch; bool live; };
 struct Pending { SymGroup* s; C* rep; C* out; int kind, ch; bool expanded; };
 enum { PI_NONE = 0, PI_GHAT = 1, PI_FULL = 2 };
 enum { PK_K1 = 0, PK_LK2 = 1, PK_K2 = 2, PK_LK3 = 3, PK_K3 = 4, PK_K2_NOFL = 5 };
@@ -130,6 +133,8 @@ struct fdga_ctx {
     C* PiMixed[2];           // Pipp_mixed, Piph_mixed of solve_using_mfRG! (fdga_mix_bubbles / fdga_update_reference)
     // s-wave solver (NL_ParquetSolver): lev[0] is an FDGA_LV_NL level; bubbles are Pi[W,w,P] and live in Pisw[] (fdga_swave.cuh)
     bool swave; C* swScratch[2];
+    // CUDA graphs
+    bool capturing; long long epoch; std::vector<GraphRec> graphs; std::vector<long long> cap_sig; long long cap_launches0; long long cap_n0[FDGA_T_COUNT];
     C* Rt3[3]; int rt_kind[3]; // per-channel right factors (W on the bubble mesh) reused between BSE_K1! and BSE_K2!
     std::string err, launch_err;
 };
@@ -541,6 +546,8 @@ static ColDev col_dev(const SymGroup& s) {
 static int ensure_slabs(fdga_ctx* ctx) {
     if (!ctx->slabs_dirty) return 0;
     if (ctx->swave) { ctx->slabs_dirty = false; return 0; }
+    if (ctx->capturing) FAIL("fdga_graph: the slab tables must be current before a recording starts (run the sequence once first)");
+    ctx->epoch++;
     const Grid& g = ctx->g;
     const int nB1 = 2 * g.nK1 - 1, nB2 = 2 * g.nK2b - 1, nF2 = 2 * g.nK2f, NP = g.NP;
     for (int kind = 0; kind < 4; kind++) {
@@ -638,6 +645,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
         g_create_error = "dims: mesh constraints violated (src/nonlocal_2/channel.jl:26-33)"; return 2; }
     if (swave && dims->LG < dims->nq) { g_create_error = "dims: the s-wave solver needs LG >= nq (Green-function mesh at least as fine as the vertex mesh)"; return 2; }
     fdga_ctx* ctx = new fdga_ctx();
+    ctx->capturing = false; ctx->epoch = 0;
     ctx->dims = *dims; ctx->device = device; ctx->nlev = dims->nlev; ctx->swave = swave; ctx->swScratch[0] = ctx->swScratch[1] = nullptr;
     ctx->nranks = 1; ctx->rank = 0; ctx->comm = nullptr; memset(&ctx->nccl, 0, sizeof(ctx->nccl));
     ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0; ctx->opt_generic = 0; ctx->opt_hartree_once = 0; ctx->opt_local = 0; ctx->opt_direct_k1 = 0; ctx->opt_qlane = getenv("FDGA_QLANE") ? atoi(getenv("FDGA_QLANE")) : -1; ctx->defer = false;
@@ -736,6 +744,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     cudaFree(ctx->flat); cudaFree(ctx->flat2); cudaFree(ctx->stash); cudaFree(ctx->d_occ); for (int i = 0; i < 3; i++) { cudaFree(ctx->TtabL[i]); cudaFree(ctx->OwnTabL[i]); cudaFree(ctx->RtotL[i]); cudaFree(ctx->ConvTabL[i]); cudaFree(ctx->RtL[i]); } cudaFree(ctx->SigR2); cudaFree(ctx->twL); cudaFree(ctx->twLG); for (int i = 0; i < 3; i++) cudaFree(ctx->Rt3[i]); for (int i = 0; i < 4; i++) { cudaFree(ctx->d_slabs[i]); cudaFree(ctx->d_slabmap[i]); }
     for (int i = 0; i < FDGA_SG_COUNT; i++) { SymGroup& s = ctx->sg[i]; cudaFree(s.d_offsets); cudaFree(s.d_index); cudaFree(s.d_ops); cudaFree(s.d_member_class); for (int k = 0; k < 3; k++) cudaFree(s.d_rep[k]);
         cudaFree(s.d_col_iW); cudaFree(s.d_col_iP); cudaFree(s.d_col_ik); cudaFree(s.d_col_start); cudaFree(s.d_rep_inu); cudaFree(s.d_rep_cls); cudaFree(s.d_grp_start); cudaFree(s.d_reps); }
+    for (auto& r : ctx->graphs) if (r.live) { cudaGraphExecDestroy(r.exec); cudaGraphDestroy(r.graph); }
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_copy_ready); cudaEventDestroy(ctx->ev_copy_done);
     for (int i = 1; i < 3; i++) cudaStreamDestroy(ctx->lane[i]);
@@ -746,6 +755,7 @@ int fdga_destroy(fdga_ctx* ctx) {
 }
 
 int fdga_set_option(fdga_ctx* ctx, int opt, int value) {
+    ctx->epoch++;
     if (opt == FDGA_OPT_SDE_OWN_GAMMA) { ctx->opt_sde_own_gamma = value != 0; return 0; }
     if (opt == FDGA_OPT_GENERIC_KERNELS) { ctx->opt_generic = value != 0; return 0; }
     if (opt == FDGA_OPT_FD_HARTREE_ONCE) { ctx->opt_hartree_once = value != 0; return 0; }
@@ -766,6 +776,7 @@ int fdga_set_option(fdga_ctx* ctx, int opt, int value) {
     FAIL("fdga_set_option: unknown option");
 }
 int fdga_sync(fdga_ctx* ctx) {
+    if (ctx->capturing) FAIL("fdga_sync: not inside a graph recording");
     CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->copy_pending) { CK(cudaStreamSynchronize(ctx->copy_stream)); ctx->copy_pending = false; }
     return 0;
@@ -915,6 +926,7 @@ static size_t sg_target_len(fdga_ctx* ctx, int which) {
 // therefore sorted by the slab (P, W) of their representative, so that the slab-level work is sharded like the column work.
 static int rebuild_sg(fdga_ctx* ctx, int which) {
     SymGroup& s = ctx->sg[which];
+    ctx->epoch++;
     const long long nclasses = (long long)s.o_offsets.size() - 1, nmem = s.o_offsets[nclasses];
     std::vector<long long> perm(nclasses);
     for (long long c = 0; c < nclasses; c++) perm[c] = c;
@@ -2375,6 +2387,77 @@ int fdga_update_reference(fdga_ctx* ctx) {
     for (int l = 0; l < 2; l++) { ctx->lev[l].sw_dirty = true; ctx->lev[l].k1h_dirty = true; ctx->lev[l].mom_valid[0] = ctx->lev[l].mom_valid[1] = ctx->lev[l].mom_valid[2] = 0; }
     ctx->fsum_dirty = true;
     invalidate_rt(ctx);
+    return 0;
+}
+
+// ---- CUDA graphs ----------------------------------------------------------------------------------------------
+// A step of the iteration is ~80 small dependent launches on three lanes; recorded once as a CUDA graph it replays with one
+// launch and without the per-launch gaps.  The library keeps derived tables current lazily (dirty flags on the host), so a
+// recording is only valid as a steady-state cycle: the flags at its end must equal the flags at its start, and a replay is only
+// accepted from that same state (and before any reallocation: `epoch`).
+static std::vector<long long> state_signature(fdga_ctx* ctx) {
+    std::vector<long long> v;
+    auto lvl = [&](const LevelBuf& lb) { v.push_back(lb.sw_dirty); v.push_back(lb.k1h_dirty); for (int c = 0; c < 3; c++) v.push_back(lb.mom_valid[c]); };
+    for (int l = 0; l < ctx->nlev; l++) lvl(ctx->lev[l]);
+    lvl(ctx->FL); lvl(ctx->Fbuff); if (ctx->has_fsum) lvl(ctx->Fsum);
+    v.push_back(ctx->fsum_dirty); v.push_back(ctx->slabs_dirty);
+    for (int i = 0; i < 4; i++) { v.push_back(ctx->pi_dirty[i]); v.push_back(ctx->pi_src[i]); v.push_back(ctx->pi_full_valid[i]); }
+    for (int i = 0; i < 3; i++) v.push_back(ctx->rt_kind[i]);
+    v.push_back(ctx->copy_pending); v.push_back(ctx->opt_serial); v.push_back(ctx->profile);
+    return v;
+}
+int fdga_graph_begin(fdga_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->capturing) FAIL("fdga_graph_begin: already recording");
+    if (ctx->profile) FAIL("fdga_graph_begin: not while profiling (the per-kernel timers need eager launches)");
+    if (ctx->nranks > 1) FAIL("fdga_graph_begin: single-rank contexts only (the NCCL all-gathers are issued eagerly)");
+    if (wait_copy(ctx)) return 1;
+    ctx->copy_pending = false;
+    ctx->cap_sig = state_signature(ctx);
+    ctx->cap_launches0 = ctx->total_launches; memcpy(ctx->cap_n0, ctx->n_launch, sizeof(ctx->cap_n0));
+    CK(cudaStreamBeginCapture(ctx->main_stream, cudaStreamCaptureModeRelaxed));
+    ctx->capturing = true;
+    return 0;
+}
+int fdga_graph_end(fdga_ctx* ctx, int* graph_id) {
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->capturing) FAIL("fdga_graph_end: no recording in progress");
+    if (ctx->forked) lanes_join(ctx);
+    if (ctx->copy_pending) { cudaStreamWaitEvent(ctx->main_stream, ctx->ev_copy_done, 0); ctx->copy_pending = false; }      // the copy stream rejoins
+    ctx->capturing = false;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->main_stream, &g);
+    if (e != cudaSuccess || !g) { ctx->err = std::string("fdga_graph_end: cudaStreamEndCapture: ") + cudaGetErrorString(e); cudaGetLastError(); return 1; }
+    if (state_signature(ctx) != ctx->cap_sig) { cudaGraphDestroy(g); FAIL("fdga_graph_end: the recorded calls do not form a steady-state cycle (lazy tables differ between start and end): run the sequence once eagerly, then record it"); }
+    GraphRec r; r.graph = g; r.exec = nullptr; r.live = true; r.sig = ctx->cap_sig; r.epoch = ctx->epoch;
+    r.launches = ctx->total_launches - ctx->cap_launches0;
+    for (int i = 0; i < FDGA_T_COUNT; i++) r.n_launch[i] = ctx->n_launch[i] - ctx->cap_n0[i];
+    e = cudaGraphInstantiate(&r.exec, g, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); ctx->err = std::string("fdga_graph_end: cudaGraphInstantiate: ") + cudaGetErrorString(e); return 1; }
+    // the recording itself executed nothing: the launch counters go back to their values at fdga_graph_begin
+    ctx->total_launches = ctx->cap_launches0; memcpy(ctx->n_launch, ctx->cap_n0, sizeof(ctx->cap_n0));
+    ctx->graphs.push_back(r);
+    *graph_id = (int)ctx->graphs.size() - 1;
+    return 0;
+}
+int fdga_graph_launch(fdga_ctx* ctx, int graph_id) {
+    CK(cudaSetDevice(ctx->device));
+    if (graph_id < 0 || graph_id >= (int)ctx->graphs.size() || !ctx->graphs[graph_id].live) FAIL("fdga_graph_launch: bad graph id");
+    GraphRec& r = ctx->graphs[graph_id];
+    if (ctx->capturing) FAIL("fdga_graph_launch: not inside a recording");
+    if (r.epoch != ctx->epoch) FAIL("fdga_graph_launch: stale graph (device tables were rebuilt since it was recorded): record it again");
+    if (wait_copy(ctx)) return 1;
+    ctx->copy_pending = false;
+    if (state_signature(ctx) != r.sig) FAIL("fdga_graph_launch: the context is not in the state the graph was recorded from: record it again");
+    CK(cudaGraphLaunch(r.exec, ctx->main_stream));
+    ctx->total_launches += r.launches;
+    for (int i = 0; i < FDGA_T_COUNT; i++) ctx->n_launch[i] += r.n_launch[i];
+    return 0;
+}
+int fdga_graph_destroy(fdga_ctx* ctx, int graph_id) {
+    if (graph_id < 0 || graph_id >= (int)ctx->graphs.size() || !ctx->graphs[graph_id].live) FAIL("fdga_graph_destroy: bad graph id");
+    CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->main_stream));
+    cudaGraphExecDestroy(ctx->graphs[graph_id].exec); cudaGraphDestroy(ctx->graphs[graph_id].graph); ctx->graphs[graph_id].live = false;
     return 0;
 }
 

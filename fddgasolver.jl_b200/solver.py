@@ -296,6 +296,27 @@ class NL2_ParquetSolver:
         self._call("fdga_comm_init", int(nranks), int(rank), L.ptr(uid))
         self.nranks, self.rank = int(nranks), int(rank)
 
+    # ------------------------------------------------------------------ CUDA graphs (include/fdga.h)
+    def record(self, fn):
+        """Record the asynchronous library calls made by fn() as a CUDA graph (nothing executes) and return its id for replay().
+        fn must have run once eagerly before (lazy tables current) and leave the solver in the lazy state it started from."""
+        self._call("fdga_graph_begin")
+        try:
+            fn()
+        except Exception:
+            gid = C.c_int(-1)
+            self._lib.fdga_graph_end(self._ctx, C.byref(gid))       # abandon the recording
+            raise
+        gid = C.c_int(-1)
+        self._call("fdga_graph_end", C.byref(gid))
+        return gid.value
+
+    def replay(self, graph_id):
+        self._call("fdga_graph_launch", int(graph_id))
+
+    def drop_graph(self, graph_id):
+        self._call("fdga_graph_destroy", int(graph_id))
+
     # ------------------------------------------------------------------ profiling
     def profile(self, on=True):
         self._call("fdga_profile_enable", int(on))

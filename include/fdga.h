@@ -233,6 +233,23 @@ int  fdga_interpolate_green(fdga_ctx*, int which, const fdga_c64* host_in, int n
 int  fdga_mix_bubbles(fdga_ctx*, double mixing);
 int  fdga_update_reference(fdga_ctx*);
 
+/* ---- CUDA graphs ------------------------------------------------------------------------
+ * Record a sequence of calls once, replay it with one launch: a step of the iteration is ~80 small dependent kernels on three
+ * concurrent lanes, and the replay removes the per-launch gaps between them.
+ *   fdga_graph_begin(ctx);  <any sequence of asynchronous fdga_* calls: fdga_unstash_F, fdga_unflatten_F (pinned host memory),
+ *                            fdga_iterate_solver, fdga_sde, fdga_bse_*, fdga_flatten_F_async, ...>;  fdga_graph_end(ctx, &id);
+ *   fdga_graph_launch(ctx, id);   ...   fdga_graph_destroy(ctx, id);
+ * Nothing executes while recording.  Calls that synchronise with the host (fdga_sync, fdga_get_*, fdga_set_*, the Krylov drivers)
+ * are not recordable.  The library refreshes derived tables lazily, so the recorded calls must form a steady-state cycle: run the
+ * sequence once eagerly first; fdga_graph_end fails if the lazy state at its end differs from the one at fdga_graph_begin, and
+ * fdga_graph_launch fails ("record it again") if the context is not in that state or device tables were rebuilt since
+ * (fdga_set_symmetry_classes, fdga_set_option, fdga_comm_init).  Host pointers passed while recording are baked in.
+ * Single-rank contexts only. */
+int  fdga_graph_begin(fdga_ctx*);
+int  fdga_graph_end(fdga_ctx*, int* graph_id);
+int  fdga_graph_launch(fdga_ctx*, int graph_id);
+int  fdga_graph_destroy(fdga_ctx*, int graph_id);
+
 /* ---- introspection --------------------------------------------------------------------- */
 /* accumulated device time (CUDA events on the launching stream) and launch counts per kernel id */
 enum { FDGA_T_CACHE = 0, FDGA_T_L_K2 = 1, FDGA_T_L_K3 = 2, FDGA_T_K1 = 3, FDGA_T_K2 = 4, FDGA_T_K3 = 5,
