@@ -231,7 +231,7 @@ def run_ours(a):
 
     # one GPU: a step is ~80 small dependent kernels on three lanes; it is recorded once as a CUDA graph (fdga_graph_begin / _end)
     # and every timed step is one replay of it -- same kernels, same order, bit-identical state (tools/graph_check.py)
-    use_graph = world == 1 and not a.no_graph
+    use_graph = (world == 1 or os.environ.get("FDGA_GRAPH_MULTIRANK", "0") == "1") and not a.no_graph
     step_resident_eager, step_e2e_eager = step_resident, step_e2e
 
     def make_graph_steps():

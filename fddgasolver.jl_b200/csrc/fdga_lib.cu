@@ -147,6 +147,7 @@ struct fdga_ctx {
     ctx->launch_err = std::string(name) + ": " + cudaGetErrorString(cudaPeekAtLastError()); } while (0)
 #define FAIL(msg) do { ctx->err = (msg); return 1; } while (0)
 
+static void auto_forget(fdga_ctx* ctx);
 static void invalidate_rt(fdga_ctx* ctx) { ctx->rt_kind[0] = ctx->rt_kind[1] = ctx->rt_kind[2] = -1; }
 static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
@@ -728,8 +729,12 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
 
 int fdga_destroy(fdga_ctx* ctx) {
     if (!ctx) return 0;
+    auto_forget(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (int i = 1; i < 3; i++) cudaStreamSynchronize(ctx->lane[i]);
+    // graphs that hold NCCL nodes must go before their communicator
+    for (auto& r : ctx->graphs) if (r.live) { cudaGraphExecDestroy(r.exec); cudaGraphDestroy(r.graph); r.live = false; }
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
     for (int l = 0; l < ctx->nlev; l++) free_level(ctx->lev[l]);
     free_level(ctx->FL); free_level(ctx->Fbuff); if (ctx->has_fsum) free_level(ctx->Fsum);
@@ -1898,14 +1903,157 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
     CK(cudaGetLastError());
     return 0;
 }
+// ---- CUDA graphs ----------------------------------------------------------------------------------------------
+// A step of the iteration is ~80 small dependent launches on three lanes; recorded once as a CUDA graph it replays with one
+// launch and without the per-launch gaps.  The library keeps derived tables current lazily (dirty flags on the host), so a
+// recording is only valid as a steady-state cycle: the flags at its end must equal the flags at its start, and a replay is only
+// accepted from that same state (and before any reallocation: `epoch`).
+static std::vector<long long> state_signature(fdga_ctx* ctx) {
+    std::vector<long long> v;
+    auto lvl = [&](const LevelBuf& lb) { v.push_back(lb.sw_dirty); v.push_back(lb.k1h_dirty); for (int c = 0; c < 3; c++) v.push_back(lb.mom_valid[c]); };
+    for (int l = 0; l < ctx->nlev; l++) lvl(ctx->lev[l]);
+    lvl(ctx->FL); lvl(ctx->Fbuff); if (ctx->has_fsum) lvl(ctx->Fsum);
+    v.push_back(ctx->fsum_dirty); v.push_back(ctx->slabs_dirty);
+    for (int i = 0; i < 4; i++) { v.push_back(ctx->pi_dirty[i]); v.push_back(ctx->pi_src[i]); v.push_back(ctx->pi_full_valid[i]); }
+    for (int i = 0; i < 3; i++) v.push_back(ctx->rt_kind[i]);
+    v.push_back(ctx->copy_pending); v.push_back(ctx->opt_serial); v.push_back(ctx->profile);
+    return v;
+}
+int fdga_graph_begin(fdga_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->capturing) FAIL("fdga_graph_begin: already recording");
+    if (ctx->profile) FAIL("fdga_graph_begin: not while profiling (the per-kernel timers need eager launches)");
+    // multi-rank: the NCCL all-gathers / broadcasts are captured with the kernels (every rank must record and replay the same
+    // sequence, like any collective); opt-in until it has been exercised on more boxes
+    static const bool mr = getenv("FDGA_GRAPH_MULTIRANK") ? atoi(getenv("FDGA_GRAPH_MULTIRANK")) != 0 : false;
+    if (ctx->nranks > 1 && !mr) FAIL("fdga_graph_begin: single-rank contexts only (set FDGA_GRAPH_MULTIRANK=1 to record NCCL collectives too)");
+    if (wait_copy(ctx)) return 1;
+    ctx->copy_pending = false;
+    ctx->cap_sig = state_signature(ctx);
+    ctx->cap_launches0 = ctx->total_launches; memcpy(ctx->cap_n0, ctx->n_launch, sizeof(ctx->cap_n0));
+    CK(cudaStreamBeginCapture(ctx->main_stream, cudaStreamCaptureModeRelaxed));
+    ctx->capturing = true;
+    return 0;
+}
+int fdga_graph_end(fdga_ctx* ctx, int* graph_id) {
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->capturing) FAIL("fdga_graph_end: no recording in progress");
+    if (ctx->forked) lanes_join(ctx);
+    if (ctx->copy_pending) { cudaStreamWaitEvent(ctx->main_stream, ctx->ev_copy_done, 0); ctx->copy_pending = false; }      // the copy stream rejoins
+    ctx->capturing = false;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->main_stream, &g);
+    if (e != cudaSuccess || !g) { ctx->err = std::string("fdga_graph_end: cudaStreamEndCapture: ") + cudaGetErrorString(e); cudaGetLastError(); return 1; }
+    if (state_signature(ctx) != ctx->cap_sig) { cudaGraphDestroy(g); FAIL("fdga_graph_end: the recorded calls do not form a steady-state cycle (lazy tables differ between start and end): run the sequence once eagerly, then record it"); }
+    GraphRec r; r.graph = g; r.exec = nullptr; r.live = true; r.sig = ctx->cap_sig; r.epoch = ctx->epoch;
+    r.launches = ctx->total_launches - ctx->cap_launches0;
+    for (int i = 0; i < FDGA_T_COUNT; i++) r.n_launch[i] = ctx->n_launch[i] - ctx->cap_n0[i];
+    e = cudaGraphInstantiate(&r.exec, g, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); ctx->err = std::string("fdga_graph_end: cudaGraphInstantiate: ") + cudaGetErrorString(e); return 1; }
+    // the recording itself executed nothing: the launch counters go back to their values at fdga_graph_begin
+    ctx->total_launches = ctx->cap_launches0; memcpy(ctx->n_launch, ctx->cap_n0, sizeof(ctx->cap_n0));
+    ctx->graphs.push_back(r);
+    *graph_id = (int)ctx->graphs.size() - 1;
+    return 0;
+}
+int fdga_graph_launch(fdga_ctx* ctx, int graph_id) {
+    CK(cudaSetDevice(ctx->device));
+    if (graph_id < 0 || graph_id >= (int)ctx->graphs.size() || !ctx->graphs[graph_id].live) FAIL("fdga_graph_launch: bad graph id");
+    GraphRec& r = ctx->graphs[graph_id];
+    if (ctx->capturing) FAIL("fdga_graph_launch: not inside a recording");
+    if (r.epoch != ctx->epoch) FAIL("fdga_graph_launch: stale graph (device tables were rebuilt since it was recorded): record it again");
+    if (wait_copy(ctx)) return 1;
+    ctx->copy_pending = false;
+    if (state_signature(ctx) != r.sig) FAIL("fdga_graph_launch: the context is not in the state the graph was recorded from: record it again");
+    CK(cudaGraphLaunch(r.exec, ctx->main_stream));
+    ctx->total_launches += r.launches;
+    for (int i = 0; i < FDGA_T_COUNT; i++) ctx->n_launch[i] += r.n_launch[i];
+    return 0;
+}
+int fdga_graph_destroy(fdga_ctx* ctx, int graph_id) {
+    if (graph_id < 0 || graph_id >= (int)ctx->graphs.size() || !ctx->graphs[graph_id].live) FAIL("fdga_graph_destroy: bad graph id");
+    CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->main_stream));
+    cudaGraphExecDestroy(ctx->graphs[graph_id].exec); cudaGraphDestroy(ctx->graphs[graph_id].graph); ctx->graphs[graph_id].live = false;
+    return 0;
+}
+
+
+extern "C++" {
+// ---- automatic graphs behind the plain entry points --------------------------------------------------------------------------
+// fdga_iterate_solver, fdga_sde and the mfRG matvec are called in loops with the same arguments (fixed-point iteration, Krylov
+// solver).  Once such a call is seen twice from the same lazy state it is recorded, and from then on replayed, as a CUDA graph;
+// any call from another state (or after a rebuild of device tables) runs eagerly.  FDGA_AUTOGRAPH=0 switches this off.
+struct AutoGraph { long long key; int id; bool have_prev, bad; std::vector<long long> sig_prev; long long epoch; };
+static std::vector<std::pair<fdga_ctx*, std::vector<AutoGraph>>> g_auto;      // per context (contexts are not thread-safe anyway)
+static std::vector<AutoGraph>& auto_table(fdga_ctx* ctx) {
+    for (auto& p : g_auto) if (p.first == ctx) return p.second;
+    g_auto.push_back({ctx, {}});
+    return g_auto.back().second;
+}
+static void auto_forget(fdga_ctx* ctx) {
+    for (size_t i = 0; i < g_auto.size(); i++) if (g_auto[i].first == ctx) { g_auto.erase(g_auto.begin() + i); return; }
+}
+static void restore_signature(fdga_ctx* ctx, const std::vector<long long>& v) {      // inverse of state_signature
+    size_t i = 0;
+    auto lvl = [&](LevelBuf& lb) { lb.sw_dirty = v[i++] != 0; lb.k1h_dirty = v[i++] != 0; for (int c = 0; c < 3; c++) lb.mom_valid[c] = (unsigned)v[i++]; };
+    for (int l = 0; l < ctx->nlev; l++) lvl(ctx->lev[l]);
+    lvl(ctx->FL); lvl(ctx->Fbuff); if (ctx->has_fsum) lvl(ctx->Fsum);
+    ctx->fsum_dirty = v[i++] != 0; ctx->slabs_dirty = v[i++] != 0;
+    for (int k = 0; k < 4; k++) { ctx->pi_dirty[k] = v[i++] != 0; ctx->pi_src[k] = (int)v[i++]; ctx->pi_full_valid[k] = v[i++] != 0; }
+    for (int k = 0; k < 3; k++) ctx->rt_kind[k] = (int)v[i++];
+}
+static bool autograph_usable(fdga_ctx* ctx) {
+    static const bool on = getenv("FDGA_AUTOGRAPH") ? atoi(getenv("FDGA_AUTOGRAPH")) != 0 : true;
+    return on && !ctx->capturing && !ctx->profile && ctx->nranks == 1 && !ctx->opt_generic;
+}
+template <class Fn>
+static int auto_graphed(fdga_ctx* ctx, long long key, Fn body) {
+    if (!autograph_usable(ctx)) return body();
+    std::vector<AutoGraph>& tab = auto_table(ctx);
+    AutoGraph* a = nullptr;
+    for (auto& e : tab) if (e.key == key) a = &e;
+    if (!a) { AutoGraph e; e.key = key; e.id = -1; e.have_prev = false; e.bad = false; e.epoch = ctx->epoch; tab.push_back(e); a = &tab.back(); }
+    if (a->epoch != ctx->epoch) {       // device tables were rebuilt: forget what was recorded
+        if (a->id >= 0) fdga_graph_destroy(ctx, a->id);
+        a->id = -1; a->have_prev = false; a->bad = false; a->epoch = ctx->epoch;
+    }
+    if (wait_copy(ctx)) return 1;
+    ctx->copy_pending = false;
+    const std::vector<long long> sig = state_signature(ctx);
+    if (a->id >= 0) {
+        if (sig == ctx->graphs[a->id].sig) return fdga_graph_launch(ctx, a->id);
+        return body();                  // off-cycle call
+    }
+    if (a->bad || !a->have_prev || sig != a->sig_prev) { a->sig_prev = sig; a->have_prev = true; return body(); }
+    // second call from the same state: record it (nothing executes), then replay
+    if (fdga_graph_begin(ctx)) { a->bad = true; return body(); }
+    const int rc = body();
+    int id = -1;
+    const int rc2 = fdga_graph_end(ctx, &id);
+    if (rc == 0 && rc2 == 0) { a->id = id; return fdga_graph_launch(ctx, id); }
+    // not recordable (a host synchronisation inside, or not a steady-state cycle): the recording pass changed host flags without
+    // executing anything -- put them back and run the call for real
+    a->bad = true;
+    ctx->capturing = false; ctx->forked = false; ctx->cur_lane = 0; ctx->stream = ctx->main_stream; ctx->defer = false; ctx->pending.clear();
+    cudaGetLastError();
+    restore_signature(ctx, sig);
+    return body();
+}
+
+}  // extern "C++"
+
 int fdga_sde_channel_L(fdga_ctx* ctx, int reference, int from) {
     CK(cudaSetDevice(ctx->device));
     if (from < 0 || from >= ctx->nlev) FAIL("fdga_sde_channel_L: bad level");
     return sde_chain(ctx, nullptr, 0.0, reference ? FDGA_G0 : FDGA_G, reference != 0, from, false, false, true);
 }
+static int sde_body(fdga_ctx* ctx, int strategy, int include_U2, int include_Hartree);
 int fdga_sde(fdga_ctx* ctx, int strategy, int include_U2, int include_Hartree) {
     CK(cudaSetDevice(ctx->device));
     if (strategy < FDGA_SCPA || strategy > FDGA_FDPA_1LOOP) FAIL("fdga_sde: Calculation strategy unknown");      // before S.Sigma is touched (src/SDE.jl:31)
+    return auto_graphed(ctx, 2000 + strategy * 4 + (include_U2 ? 2 : 0) + (include_Hartree ? 1 : 0), [&]() { return sde_body(ctx, strategy, include_U2, include_Hartree); });
+}
+static int sde_body(fdga_ctx* ctx, int strategy, int include_U2, int include_Hartree) {
     C* S = ctx->G[FDGA_SIGMA];
     CK(cudaMemsetAsync(S, 0, ctx->lenG * sizeof(C), ctx->stream));
     if (sde_chain(ctx, S, 1.0, FDGA_G, false, 0, include_U2, include_Hartree)) return 1;
@@ -1977,8 +2125,13 @@ static int bse_stages_variant(fdga_ctx* ctx, int strategy) {
     return rc;
 }
 
+static int iterate_body(fdga_ctx* ctx, int strategy, int update_sigma, int compute_hartree);
 int fdga_iterate_solver(fdga_ctx* ctx, int strategy, int update_sigma, int compute_hartree) {
     if (strategy < FDGA_SCPA || strategy > FDGA_FDPA_1LOOP) FAIL("fdga_iterate_solver: Calculation strategy unknown");
+    CK(cudaSetDevice(ctx->device));
+    return auto_graphed(ctx, 1000 + strategy * 4 + (update_sigma ? 2 : 0) + (compute_hartree ? 1 : 0), [&]() { return iterate_body(ctx, strategy, update_sigma, compute_hartree); });
+}
+static int iterate_body(fdga_ctx* ctx, int strategy, int update_sigma, int compute_hartree) {
     if (update_sigma) { if (fdga_dyson(ctx) || (ctx->opt_local ? fdga_bubbles_local(ctx, 0) : fdga_bubbles_real_space(ctx, 0))) return 1; }
     if (fdga_build_K3_cache(ctx, 0, 0)) return 1;
     if (strategy >= FDGA_SCPA_NEW) { if (bse_stages_variant(ctx, strategy)) return 1; }
@@ -1990,7 +2143,18 @@ int fdga_iterate_solver(fdga_ctx* ctx, int strategy, int update_sigma, int compu
 
 // mfRGLinearMap(S, strategy) * x on DEVICE vectors (src/mfRG.jl:34-89): y = x - flatten(BSE_lin(factor * x)) / factor.
 // x_dev and y_dev may alias.  strategy: fdPA / fdPA_1loop (identical maps, src/mfRG.jl:51) or fdPA_new.
+static int mfrg_matvec_body(fdga_ctx* ctx, const C* x_dev, C* y_dev, int first, int strategy);
 static int mfrg_matvec_dev(fdga_ctx* ctx, const C* x_dev, C* y_dev, int first, int strategy) {
+    if (strategy != FDGA_FDPA && strategy != FDGA_FDPA_NEW && strategy != FDGA_FDPA_1LOOP)
+        FAIL("mfRGLinearMap: Invalid strategy. Must be fdPA or fdPA_new or fdPA_1loop.");      // src/mfRG.jl:26-28
+    if (!autograph_usable(ctx)) return mfrg_matvec_body(ctx, x_dev, y_dev, first, strategy);
+    // the graph works on fixed buffers (flat2 -> flat); Krylov vectors are copied in / out on the device
+    if (x_dev != ctx->flat2) CK(cudaMemcpyAsync(ctx->flat2, x_dev, ctx->lenFlat * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (auto_graphed(ctx, 3000 + strategy * 2 + (first ? 1 : 0), [&]() { return mfrg_matvec_body(ctx, ctx->flat2, ctx->flat, first, strategy); })) return 1;
+    if (y_dev != ctx->flat) CK(cudaMemcpyAsync(y_dev, ctx->flat, ctx->lenFlat * sizeof(C), cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+static int mfrg_matvec_body(fdga_ctx* ctx, const C* x_dev, C* y_dev, int first, int strategy) {
     const double factor = 1e-2;                                  // src/mfRG.jl:37
     if (strategy != FDGA_FDPA && strategy != FDGA_FDPA_NEW && strategy != FDGA_FDPA_1LOOP)
         FAIL("mfRGLinearMap: Invalid strategy. Must be fdPA or fdPA_new or fdPA_1loop.");      // src/mfRG.jl:26-28
@@ -2387,77 +2551,6 @@ int fdga_update_reference(fdga_ctx* ctx) {
     for (int l = 0; l < 2; l++) { ctx->lev[l].sw_dirty = true; ctx->lev[l].k1h_dirty = true; ctx->lev[l].mom_valid[0] = ctx->lev[l].mom_valid[1] = ctx->lev[l].mom_valid[2] = 0; }
     ctx->fsum_dirty = true;
     invalidate_rt(ctx);
-    return 0;
-}
-
-// ---- CUDA graphs ----------------------------------------------------------------------------------------------
-// A step of the iteration is ~80 small dependent launches on three lanes; recorded once as a CUDA graph it replays with one
-// launch and without the per-launch gaps.  The library keeps derived tables current lazily (dirty flags on the host), so a
-// recording is only valid as a steady-state cycle: the flags at its end must equal the flags at its start, and a replay is only
-// accepted from that same state (and before any reallocation: `epoch`).
-static std::vector<long long> state_signature(fdga_ctx* ctx) {
-    std::vector<long long> v;
-    auto lvl = [&](const LevelBuf& lb) { v.push_back(lb.sw_dirty); v.push_back(lb.k1h_dirty); for (int c = 0; c < 3; c++) v.push_back(lb.mom_valid[c]); };
-    for (int l = 0; l < ctx->nlev; l++) lvl(ctx->lev[l]);
-    lvl(ctx->FL); lvl(ctx->Fbuff); if (ctx->has_fsum) lvl(ctx->Fsum);
-    v.push_back(ctx->fsum_dirty); v.push_back(ctx->slabs_dirty);
-    for (int i = 0; i < 4; i++) { v.push_back(ctx->pi_dirty[i]); v.push_back(ctx->pi_src[i]); v.push_back(ctx->pi_full_valid[i]); }
-    for (int i = 0; i < 3; i++) v.push_back(ctx->rt_kind[i]);
-    v.push_back(ctx->copy_pending); v.push_back(ctx->opt_serial); v.push_back(ctx->profile);
-    return v;
-}
-int fdga_graph_begin(fdga_ctx* ctx) {
-    CK(cudaSetDevice(ctx->device));
-    if (ctx->capturing) FAIL("fdga_graph_begin: already recording");
-    if (ctx->profile) FAIL("fdga_graph_begin: not while profiling (the per-kernel timers need eager launches)");
-    if (ctx->nranks > 1) FAIL("fdga_graph_begin: single-rank contexts only (the NCCL all-gathers are issued eagerly)");
-    if (wait_copy(ctx)) return 1;
-    ctx->copy_pending = false;
-    ctx->cap_sig = state_signature(ctx);
-    ctx->cap_launches0 = ctx->total_launches; memcpy(ctx->cap_n0, ctx->n_launch, sizeof(ctx->cap_n0));
-    CK(cudaStreamBeginCapture(ctx->main_stream, cudaStreamCaptureModeRelaxed));
-    ctx->capturing = true;
-    return 0;
-}
-int fdga_graph_end(fdga_ctx* ctx, int* graph_id) {
-    CK(cudaSetDevice(ctx->device));
-    if (!ctx->capturing) FAIL("fdga_graph_end: no recording in progress");
-    if (ctx->forked) lanes_join(ctx);
-    if (ctx->copy_pending) { cudaStreamWaitEvent(ctx->main_stream, ctx->ev_copy_done, 0); ctx->copy_pending = false; }      // the copy stream rejoins
-    ctx->capturing = false;
-    cudaGraph_t g = nullptr;
-    cudaError_t e = cudaStreamEndCapture(ctx->main_stream, &g);
-    if (e != cudaSuccess || !g) { ctx->err = std::string("fdga_graph_end: cudaStreamEndCapture: ") + cudaGetErrorString(e); cudaGetLastError(); return 1; }
-    if (state_signature(ctx) != ctx->cap_sig) { cudaGraphDestroy(g); FAIL("fdga_graph_end: the recorded calls do not form a steady-state cycle (lazy tables differ between start and end): run the sequence once eagerly, then record it"); }
-    GraphRec r; r.graph = g; r.exec = nullptr; r.live = true; r.sig = ctx->cap_sig; r.epoch = ctx->epoch;
-    r.launches = ctx->total_launches - ctx->cap_launches0;
-    for (int i = 0; i < FDGA_T_COUNT; i++) r.n_launch[i] = ctx->n_launch[i] - ctx->cap_n0[i];
-    e = cudaGraphInstantiate(&r.exec, g, 0);
-    if (e != cudaSuccess) { cudaGraphDestroy(g); ctx->err = std::string("fdga_graph_end: cudaGraphInstantiate: ") + cudaGetErrorString(e); return 1; }
-    // the recording itself executed nothing: the launch counters go back to their values at fdga_graph_begin
-    ctx->total_launches = ctx->cap_launches0; memcpy(ctx->n_launch, ctx->cap_n0, sizeof(ctx->cap_n0));
-    ctx->graphs.push_back(r);
-    *graph_id = (int)ctx->graphs.size() - 1;
-    return 0;
-}
-int fdga_graph_launch(fdga_ctx* ctx, int graph_id) {
-    CK(cudaSetDevice(ctx->device));
-    if (graph_id < 0 || graph_id >= (int)ctx->graphs.size() || !ctx->graphs[graph_id].live) FAIL("fdga_graph_launch: bad graph id");
-    GraphRec& r = ctx->graphs[graph_id];
-    if (ctx->capturing) FAIL("fdga_graph_launch: not inside a recording");
-    if (r.epoch != ctx->epoch) FAIL("fdga_graph_launch: stale graph (device tables were rebuilt since it was recorded): record it again");
-    if (wait_copy(ctx)) return 1;
-    ctx->copy_pending = false;
-    if (state_signature(ctx) != r.sig) FAIL("fdga_graph_launch: the context is not in the state the graph was recorded from: record it again");
-    CK(cudaGraphLaunch(r.exec, ctx->main_stream));
-    ctx->total_launches += r.launches;
-    for (int i = 0; i < FDGA_T_COUNT; i++) ctx->n_launch[i] += r.n_launch[i];
-    return 0;
-}
-int fdga_graph_destroy(fdga_ctx* ctx, int graph_id) {
-    if (graph_id < 0 || graph_id >= (int)ctx->graphs.size() || !ctx->graphs[graph_id].live) FAIL("fdga_graph_destroy: bad graph id");
-    CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->main_stream));
-    cudaGraphExecDestroy(ctx->graphs[graph_id].exec); cudaGraphDestroy(ctx->graphs[graph_id].graph); ctx->graphs[graph_id].live = false;
     return 0;
 }
 

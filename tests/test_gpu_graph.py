@@ -86,3 +86,33 @@ def test_guards():
         S.profile(True); S.record(step)
     S.profile(False)
     S.close()
+
+
+@pytest.mark.parametrize("nl_method", [2, 1])
+def test_automatic_graphs_behind_the_plain_entry_points(nl_method):
+    """fdga_iterate_solver / fdga_sde / the mfRG matvec record themselves after two calls from the same lazy state and replay from
+    then on; a solver that is forced to issue eagerly (profiling on) walks through bit-identical states"""
+    import fddgasolver_jl_b200 as fd
+    A, B = _solver(nl_method), _solver(nl_method)
+    B.profile(True)                                     # eager launches only
+    x = A.F.flatten()
+    mapA, mapB = fd.mfRGLinearMap(A), fd.mfRGLinearMap(B)
+    for it in range(6):
+        for S in (A, B):
+            fd.iterate_solver(S, "fdPA")
+        if it % 2:
+            for S in (A, B):
+                fd.SDE(S, "scPA")                       # an extra call now and then: off-cycle states fall back to eager issue
+    ya, yb = A.flatten_F().copy(), B.flatten_F().copy()
+    A.pull("Σ", "G"); B.pull("Σ", "G")
+    assert np.array_equal(ya, yb) and np.array_equal(A.Σ, B.Σ) and np.array_equal(A.G, B.G)
+    for _ in range(4):
+        xa, xb = mapA.matvec(x), mapB.matvec(x)
+        assert np.array_equal(xa, xb)
+        x = xa * 0.5
+    # after a rebuild of device tables the recorded graphs are dropped, not replayed
+    for S in (A, B):
+        S.init_sym_grp()
+        fd.iterate_solver(S, "fdPA"); fd.iterate_solver(S, "fdPA"); fd.iterate_solver(S, "fdPA")
+    assert np.array_equal(A.flatten_F(), B.flatten_F())
+    A.close(); B.close()
