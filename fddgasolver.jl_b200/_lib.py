@@ -35,7 +35,7 @@ EXPORTS = [
     "fdga_set_hubbard_bare_green", "fdga_hubbard_chemical_potential", "fdga_bubbles_momentum_space", "fdga_bubbles_local", "fdga_build_K3_cache", "fdga_bse_L_K2", "fdga_bse_L_K3", "fdga_bse_K1",
     "fdga_bse_K2", "fdga_bse_K3", "fdga_bse_K1_new", "fdga_bse_K2_new", "fdga_bse_K1_1loop", "fdga_bse_K2_1loop", "fdga_bse_K3_1loop",
     "fdga_set_F_from_Fbuff", "fdga_sde", "fdga_sde_channel_L", "fdga_iterate_solver",
-    "fdga_mfrg_matvec", "fdga_mfrg_matvec_strategy", "fdga_mfrg_dqgmres", "fdga_symmetrize_solver", "fdga_fixed_point_preconditioned", "fdga_mix_bubbles", "fdga_update_reference", "fdga_interpolate_vertex", "fdga_interpolate_green",
+    "fdga_mfrg_matvec", "fdga_mfrg_matvec_strategy", "fdga_mfrg_matvec_from_root", "fdga_mfrg_dqgmres", "fdga_symmetrize_solver", "fdga_fixed_point_preconditioned", "fdga_mix_bubbles", "fdga_update_reference", "fdga_interpolate_vertex", "fdga_interpolate_green",
     "fdga_measure_fp64_peak", "fdga_profile_enable", "fdga_profile_reset", "fdga_kernel_time_ms",
     "fdga_total_launches", "fdga_stream", "fdga_graph_begin", "fdga_graph_end", "fdga_graph_launch", "fdga_graph_destroy",
 ]
@@ -115,6 +115,7 @@ def load():
     lib.fdga_hubbard_chemical_potential.argtypes = [vp, dbl, dbl, dbl, dbl, C.POINTER(dbl)]
     lib.fdga_mfrg_matvec.argtypes = [vp, vp, vp, i32]
     lib.fdga_mfrg_matvec_strategy.argtypes = [vp, vp, vp, i32, i32]
+    lib.fdga_mfrg_matvec_from_root.argtypes = [vp, vp, vp, i32, i32, i32]
     lib.fdga_mfrg_dqgmres.argtypes = [vp, vp, vp, i32, i32, dbl, dbl, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(dbl), i32]
     lib.fdga_symmetrize_solver.argtypes = [vp]
     lib.fdga_interpolate_vertex.argtypes = [vp, i32, i32, i32, vp, C.POINTER(C.c_int32), i32]

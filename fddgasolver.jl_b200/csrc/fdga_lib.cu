@@ -1908,6 +1908,10 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
 // launch and without the per-launch gaps.  The library keeps derived tables current lazily (dirty flags on the host), so a
 // recording is only valid as a steady-state cycle: the flags at its end must equal the flags at its start, and a replay is only
 // accepted from that same state (and before any reallocation: `epoch`).
+static bool graph_multirank() {
+    static const bool mr = getenv("FDGA_GRAPH_MULTIRANK") ? atoi(getenv("FDGA_GRAPH_MULTIRANK")) != 0 : false;
+    return mr;
+}
 static std::vector<long long> state_signature(fdga_ctx* ctx) {
     std::vector<long long> v;
     auto lvl = [&](const LevelBuf& lb) { v.push_back(lb.sw_dirty); v.push_back(lb.k1h_dirty); for (int c = 0; c < 3; c++) v.push_back(lb.mom_valid[c]); };
@@ -1925,8 +1929,7 @@ int fdga_graph_begin(fdga_ctx* ctx) {
     if (ctx->profile) FAIL("fdga_graph_begin: not while profiling (the per-kernel timers need eager launches)");
     // multi-rank: the NCCL all-gathers / broadcasts are captured with the kernels (every rank must record and replay the same
     // sequence, like any collective); opt-in until it has been exercised on more boxes
-    static const bool mr = getenv("FDGA_GRAPH_MULTIRANK") ? atoi(getenv("FDGA_GRAPH_MULTIRANK")) != 0 : false;
-    if (ctx->nranks > 1 && !mr) FAIL("fdga_graph_begin: single-rank contexts only (set FDGA_GRAPH_MULTIRANK=1 to record NCCL collectives too)");
+    if (ctx->nranks > 1 && !graph_multirank()) FAIL("fdga_graph_begin: single-rank contexts only (set FDGA_GRAPH_MULTIRANK=1 to record NCCL collectives too)");
     if (wait_copy(ctx)) return 1;
     ctx->copy_pending = false;
     ctx->cap_sig = state_signature(ctx);
@@ -2004,7 +2007,7 @@ static void restore_signature(fdga_ctx* ctx, const std::vector<long long>& v) { 
 }
 static bool autograph_usable(fdga_ctx* ctx) {
     static const bool on = getenv("FDGA_AUTOGRAPH") ? atoi(getenv("FDGA_AUTOGRAPH")) != 0 : true;
-    return on && !ctx->capturing && !ctx->profile && ctx->nranks == 1 && !ctx->opt_generic;
+    return on && !ctx->capturing && !ctx->profile && (ctx->nranks == 1 || graph_multirank()) && !ctx->opt_generic;
 }
 template <class Fn>
 static int auto_graphed(fdga_ctx* ctx, long long key, Fn body) {
@@ -2179,6 +2182,27 @@ int fdga_mfrg_matvec_strategy(fdga_ctx* ctx, const fdga_c64* host_x, fdga_c64* h
     CK(cudaMemcpyAsync(ctx->flat2, host_x, ctx->lenFlat * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
     if (mfrg_matvec_dev(ctx, ctx->flat2, ctx->flat, first, strategy)) return 1;
     CK(cudaMemcpyAsync(host_y, ctx->flat, ctx->lenFlat * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+// the same map for a multi-rank job whose vectors live on ONE host process: x crosses PCIe on the root only and reaches the other
+// ranks over NVLink (ncclBroadcast); y is read back on the root only (host_x / host_y may be NULL elsewhere).  Collective.
+int fdga_mfrg_matvec_from_root(fdga_ctx* ctx, const fdga_c64* host_x, fdga_c64* host_y, int first, int strategy, int root) {
+    CK(cudaSetDevice(ctx->device));
+    if (root < 0 || root >= ctx->nranks) FAIL("fdga_mfrg_matvec_from_root: bad root");
+    if (ctx->rank == root) {
+        if (!host_x || !host_y) FAIL("fdga_mfrg_matvec_from_root: the root needs both host vectors");
+        CK(cudaMemcpyAsync(ctx->flat2, host_x, ctx->lenFlat * sizeof(C), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (ctx->nranks > 1) {
+        if (!ctx->nccl.Broadcast) FAIL("fdga_mfrg_matvec_from_root: ncclBroadcast not available");
+        Scope sc(ctx, FDGA_T_COMM);
+        int rc = ctx->nccl.Broadcast(ctx->flat2, ctx->flat2, ctx->lenFlat * 2, /*ncclDouble*/ 8, root, ctx->comm, ctx->stream);
+        if (rc != 0) FAIL(std::string("ncclBroadcast: ") + ctx->nccl.GetErrorString(rc));
+        ctx->n_launch[FDGA_T_COMM]++;
+    }
+    if (mfrg_matvec_dev(ctx, ctx->flat2, ctx->flat, first, strategy)) return 1;
+    if (ctx->rank == root) CK(cudaMemcpyAsync(host_y, ctx->flat, ctx->lenFlat * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

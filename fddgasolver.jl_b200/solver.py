@@ -566,9 +566,19 @@ class mfRGLinearMap:
     def __matmul__(self, x):
         return self.matvec(x)
 
-    def matvec(self, x, out=None):
+    def matvec(self, x, out=None, root=None):
         """y = A x.  `out` (optional) receives y: pass pinned host buffers for x and out to move them at full PCIe speed
-        (pageable numpy arrays are staged by the driver at a fraction of it)."""
+        (pageable numpy arrays are staged by the driver at a fraction of it).  root (multi-rank jobs, collective): the vectors live
+        on that rank's host only; x is uploaded once and broadcast over NVLink, y comes back on the root (None elsewhere)."""
+        if root is not None:
+            me = getattr(self.S, "rank", 0) == root
+            if me:
+                x = np.ascontiguousarray(x, dtype=np.complex128)
+                y = np.empty_like(x) if out is None else out
+            self.S._call("fdga_mfrg_matvec_from_root", L.ptr(x) if me else None, L.ptr(y) if me else None, int(self.is_first_iteration),
+                         STRATEGY[self.strategy], int(root))
+            self.is_first_iteration = False
+            return y if me else None
         x = np.ascontiguousarray(x, dtype=np.complex128)
         y = np.empty_like(x) if out is None else out
         assert y.dtype == np.complex128 and y.size == x.size and y.flags["C_CONTIGUOUS"]

@@ -205,6 +205,9 @@ int  fdga_mfrg_matvec(fdga_ctx*, const fdga_c64* host_x, fdga_c64* host_y, int f
 
 /* mfRGLinearMap(S, strategy) matvec: src/mfRG.jl:20-89; strategy FDGA_FDPA, FDGA_FDPA_1LOOP (same map) or FDGA_FDPA_NEW */
 int  fdga_mfrg_matvec_strategy(fdga_ctx*, const fdga_c64* host_x, fdga_c64* host_y, int first, int strategy);
+/* the same map when the vectors of a multi-rank job live on ONE host process (collective): x is uploaded by `root` only and
+ * broadcast over NVLink, y is read back on `root` only; host_x / host_y may be NULL on the other ranks */
+int  fdga_mfrg_matvec_from_root(fdga_ctx*, const fdga_c64* host_x, fdga_c64* host_y, int first, int strategy, int root);
 /* Krylov.dqgmres(mfRGLinearMap(S, strategy), b; atol, rtol, itmax, memory) as called at src/mfRG.jl:147-151, with the Krylov
  * basis, the direction vectors and the iterate resident in HBM: b and x cross PCIe once.  x0 = 0, no
  * preconditioner, modified Gram-Schmidt over the last `memory` vectors; stop when the quasi-residual estimate
