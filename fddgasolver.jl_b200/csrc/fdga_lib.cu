@@ -280,7 +280,7 @@ static int refresh_swave(fdga_ctx* ctx) {
         if (lb.d.type == FDGA_LV_NL) {
             long long n = (long long)(2 * lb.d.nK1 - 1) + (long long)(2 * lb.d.nK2[0] - 1) * (2 * lb.d.nK2[1])
                         + (long long)(2 * lb.d.nK3[0] - 1) * (2 * lb.d.nK3[1]) * (2 * lb.d.nK3[1]);
-            LAUNCH(FDGA_T_SWAVE, swave_tables_nl_kernel, dim3(nblk(n, 128), 3), 128, dl, ctx->g.NP, out);
+            LAUNCH(FDGA_T_SWAVE, swave_tables_nl_kernel, dim3(nblk(n * 32, 128), 3), 128, dl, ctx->g.NP, out);
             lb.sw_dirty = false;
             continue;
         }
@@ -1127,7 +1127,8 @@ int fdga_bubbles_real_space(fdga_ctx* ctx, int reference) {
         const long long pre = (long long)(2 * g.nPiB - 1) * (2 * g.nPiF), n = pre * g.NP;
         static const bool literal = getenv("FDGA_BUBBLES_RS") ? atoi(getenv("FDGA_BUBBLES_RS")) != 0 : false;
         if (!literal) {     // back transform as a direct sum on the few inner frequencies that carry one (fdga_swave.cuh)
-            LAUNCH(FDGA_T_BUBBLE, sw_bubbles_direct_kernel, nblk(n, 128), 128, ctx->GR, ctx->Pisw[ipp], ctx->Pisw[iph], g, 1, ctx->twL);
+            const long long nb_fill = nblk(n, 128), nb_sum = nblk((long long)(2 * g.nPiB - 1) * (2 * g.nG) * g.NP * 32, 128);
+            LAUNCH(FDGA_T_BUBBLE, sw_bubbles_direct_kernel, (unsigned)(nb_fill + nb_sum), 128, ctx->GR, ctx->Pisw[ipp], ctx->Pisw[iph], g, 1, ctx->twL, nb_fill);
             CK(cudaGetLastError());
             return 0;
         }

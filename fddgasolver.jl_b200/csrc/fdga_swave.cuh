@@ -16,7 +16,9 @@
 
 namespace fdga {
 
-#define FDGA_SW_WARPS 4      // warps per CTA
+#ifndef FDGA_SW_WARPS
+#define FDGA_SW_WARPS 16     // warps per CTA (CTA-per-representative mode: 1024 inner frequencies -> 2 per thread)
+#endif
 #define FDGA_SW_THREADS (32 * FDGA_SW_WARPS)
 
 // work split of the contraction kernels: representative handled by this thread, its first inner index and the stride
@@ -44,19 +46,22 @@ __device__ __forceinline__ Arg sw_arg(int W, int v, int w, int iP, int L) {
 template <int CH> __device__ __forceinline__ int crossing(int W, int w) { return CH == CH_P ? W - w - 1 : w; }      // src/convention.jl:39-47
 
 // ---- BZ means of an NL level: K1sw[W], K2sww[W,v], K3sw[W,v,w] (src/nonlocal/swave.jl:32-75) ----
+// one warp per output element, lanes over the momentum
 __global__ void swave_tables_nl_kernel(DevLevel lv, int NP, SwOut out) {
     const int r = blockIdx.y;
     const DevChan& c = lv.ch[r];
     const long long n1 = 2 * lv.nK1 - 1, n2 = (long long)(2 * lv.nK2b - 1) * (2 * lv.nK2f), n3 = (long long)(2 * lv.nK3b - 1) * (2 * lv.nK3f) * (2 * lv.nK3f);
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     const C* src; C* dst; long long n;
     if (i < n1) { src = c.K1; dst = out.p[r][0]; n = n1; }
     else if (i < n1 + n2) { i -= n1; src = c.K2; dst = out.p[r][2]; n = n2; }
     else if (i < n1 + n2 + n3) { i -= n1 + n2; src = c.K3; dst = out.p[r][3]; n = n3; }
     else return;
     C s = zeroC();
-    for (int p = 0; p < NP; ++p) s += src[i + n * p];
-    dst[i] = s / (double)NP;
+    for (int p = lane; p < NP; p += 32) s += src[i + n * p];
+    s = SwSplit<false>::warp_reduce_sw(s);
+    if (lane == 0) dst[i] = s / (double)NP;
 }
 
 // ---- BSE_K1!: src/nonlocal/BSEa/BSEa_K1.jl:2-58.  One warp per class representative (W, P) ----
@@ -230,21 +235,44 @@ __global__ void sw_bubbles_rs_kernel(const C* __restrict__ GR, C* __restrict__ P
 //   both on the mesh:  Pi[W,w,P] = sum_{R in window} wt(R) G(a,R) G(w,+-R) exp(+2 pi i P.R / L)   (the back transform as a direct sum)
 //   otherwise:         Pi[W,w,P] = g~(a) g~(w)  with the local G (R = 0) continued by 1/nu   (0 without the tail).
 __global__ void sw_bubbles_direct_kernel(const C* __restrict__ GR, C* __restrict__ Pipp, C* __restrict__ Piph, Grid g, int use_tail,
-                                         const C* __restrict__ twL) {
+                                         const C* __restrict__ twL, long long nblk_fill) {
     const int nBP = 2 * g.nPiB - 1, nFP = 2 * g.nPiF, L = g.L, LG = g.LG, NP = g.NP, nG = g.nG, h = L / 2;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= (long long)nBP * nFP * NP) return;
-    long long t = i;
-    const int iW = t % nBP; t /= nBP; const int iw = t % nFP; const int iP = (int)(t / nFP);
-    const int W = iW - (g.nPiB - 1), w = iw - g.nPiF, Px = iP % L, Py = iP / L;
     const double pi = 3.14159265358979323846;
-    const bool bin = inF(w, nG);
     auto tail = [&](int n) { return mkC(1.0 / ((2 * n + 1) * pi * g.T), 0.0); };
+    if ((long long)blockIdx.x < nblk_fill) {
+        // role 1, one thread per element whose inner frequency w lies OUTSIDE the G mesh: the P-independent tail product (or 0)
+        const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        if (i >= (long long)nBP * nFP * NP) return;
+        long long t = i;
+        const int iW = t % nBP; t /= nBP; const int iw = t % nFP;
+        const int W = iW - (g.nPiB - 1), w = iw - g.nPiF;
+        if (inF(w, nG)) return;                              // role 2 writes these
+        C pp = zeroC(), ph = zeroC();
+        if (use_tail) {
+            const C gb = tail(w);
+            const int app = W - w - 1, aph = W + w;
+            pp = (inF(app, nG) ? GR[posF(app, nG)] : tail(app)) * gb;
+            ph = (inF(aph, nG) ? GR[posF(aph, nG)] : tail(aph)) * gb;
+        }
+        Pipp[i] = pp; Piph[i] = ph;
+        return;
+    }
+    // role 2, one warp per element (W, w on the G mesh, P): lanes over the (L+1)^2 window of R, shuffle reduction
+    const long long e = ((blockIdx.x - nblk_fill) * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long nE = (long long)nBP * (2 * nG) * NP;
+    if (e >= nE) return;
+    long long t = e;
+    const int iW = t % nBP; t /= nBP; const int w = (int)(t % (2 * nG)) - nG; const int iP = (int)(t / (2 * nG));
+    const int W = iW - (g.nPiB - 1), Px = iP % L, Py = iP / L;
+    if (!inF(w, g.nPiF)) return;                             // G mesh wider than the bubble's inner mesh
     const int app = W - w - 1, aph = W + w;
-    const bool pin = inF(app, nG) && bin, hin = inF(aph, nG) && bin;
+    const bool pin = inF(app, nG), hin = inF(aph, nG);
     C pp = zeroC(), ph = zeroC();
     if (pin || hin) {
-        for (int R2 = -h; R2 <= h; ++R2) for (int R1 = -h; R1 <= h; ++R1) {
+        const int win = 2 * h + 1;
+        for (int j = lane; j < win * win; j += 32) {
+            const int R1 = j % win - h, R2 = j / win - h;
             double wt = 1.0;
             if (LG % 2 == 0) { if (abs(R1) == LG / 2) wt *= 0.5; if (abs(R2) == LG / 2) wt *= 0.5; }
             const size_t pR = (size_t)2 * nG * (modL(R1, LG) + (size_t)LG * modL(R2, LG)), mR = (size_t)2 * nG * (modL(-R1, LG) + (size_t)LG * modL(-R2, LG));
@@ -252,13 +280,14 @@ __global__ void sw_bubbles_direct_kernel(const C* __restrict__ GR, C* __restrict
             if (pin) pp += GR[posF(app, nG) + pR] * GR[posF(w, nG) + pR] * ph_;
             if (hin) ph += GR[posF(aph, nG) + pR] * GR[posF(w, nG) + mR] * ph_;
         }
+        pp = SwSplit<false>::warp_reduce_sw(pp); ph = SwSplit<false>::warp_reduce_sw(ph);
     }
-    if (use_tail) {
-        const C gb = bin ? GR[posF(w, nG)] : tail(w);
-        if (!pin) pp = (inF(app, nG) ? GR[posF(app, nG)] : tail(app)) * gb;
-        if (!hin) ph = (inF(aph, nG) ? GR[posF(aph, nG)] : tail(aph)) * gb;
-    }
-    Pipp[i] = pp; Piph[i] = ph;
+    if (lane != 0) return;
+    const C gb = GR[posF(w, nG)];
+    if (!pin) pp = use_tail ? tail(app) * gb : zeroC();
+    if (!hin) ph = use_tail ? tail(aph) * gb : zeroC();
+    const size_t o = (size_t)iW + (size_t)nBP * (posF(w, g.nPiF) + (size_t)nFP * iP);
+    Pipp[o] = pp; Piph[o] = ph;
 }
 
 // ---- SDE_compute_inner! (use_real_space = true): src/nonlocal/SDE.jl:191-275.  LppR / LphR = fft(L) / L^2 over the momentum
