@@ -572,6 +572,34 @@ __global__ void dft_axis_kernel(const C* __restrict__ in, C* __restrict__ out, l
     }
     out[i] = s * scale;
 }
+// 2-d DFT over two ADJACENT axes of size n in one launch: data viewed as [pre][n][n][post], one CTA per (a, b).  The n x n tile
+// is gathered into shared memory, transformed along x, then along y, and written back; in-place use is safe (a CTA reads its whole
+// tile before it writes, tiles are disjoint).  Replaces two dft_axis_kernel launches (and their global round trip) per 2-d transform.
+__global__ void dft2_tile_kernel(const C* __restrict__ in, C* __restrict__ out, long long pre, int n, long long post, int sgn, double scale,
+                                 const C* __restrict__ tw /* tw[j] = exp(+2 pi i j / n) */) {
+    extern __shared__ __align__(16) double dft_sm[];
+    C* A = reinterpret_cast<C*>(dft_sm); C* B = A + n * n; C* w = B + n * n;
+    const long long a = blockIdx.x % pre, b = blockIdx.x / pre;
+    (void)post;
+    const long long base = a + pre * (long long)n * n * b;
+    const int nn = n * n;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) { C t = tw[j]; if (sgn < 0) t.y = -t.y; w[j] = t; }
+    for (int t = threadIdx.x; t < nn; t += blockDim.x) A[t] = in[base + pre * t];
+    __syncthreads();
+    for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+        const int kx = t % n, y = t / n;
+        C s = zeroC(); int jk = 0;
+        for (int x = 0; x < n; ++x) { s += A[x + n * y] * w[jk]; jk += kx; if (jk >= n) jk -= n; }
+        B[t] = s;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+        const int kx = t % n, ky = t / n;
+        C s = zeroC(); int jk = 0;
+        for (int y = 0; y < n; ++y) { s += B[kx + n * y] * w[jk]; jk += ky; if (jk >= n) jk -= n; }
+        out[base + pre * t] = s * scale;
+    }
+}
 __global__ void twiddle_kernel(C* tw, int n) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;

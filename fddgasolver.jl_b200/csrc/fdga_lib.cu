@@ -92,6 +92,7 @@ struct fdga_ctx {
     // concurrency lanes: the three channels of a BSE stage (and the pp / ph / U^2 parts of the SDE) are independent, so
     // they are issued on three streams forked from / joined into the main stream; every lane owns its scratch tables
     cudaStream_t main_stream; cudaStream_t lane[3]; cudaEvent_t ev_fork, ev_join[3];
+    cudaEvent_t ev_cache; bool cache_on_lane;      // fused driver: build_K3_cache! runs on a lane beside BSE_L_K2! / BSE_K1! / BSE_K2!
     int cur_lane; bool forked; int opt_serial;
     C* RtL[3]; C* TtabL[3]; C* OwnTabL[3]; C* RtotL[3]; C* ConvTabL[3];
     cudaStream_t copy_stream; cudaEvent_t ev_copy_ready, ev_copy_done; bool copy_pending;   // fdga_flatten_F_async
@@ -459,10 +460,29 @@ static int add_axpby(fdga_ctx* ctx, C* out, const C* x, double a, const C* y, do
 // t-channel post-fix: X_t <- (X_t + X_a) / 2   (BSE_templates.jl:35-38 etc.)
 static int tfix(fdga_ctx* ctx, C* Xt, const C* Xa, size_t n) { return axpby(ctx, Xt, Xt, 0.5, Xa, 0.5, n); }
 
+// one-launch 2-d transform over two adjacent axes (dft2_tile_kernel); false: the tile does not fit in shared memory / switched off
+static bool dft2_tile(fdga_ctx* ctx, const C* in, C* out, long long pre, int n, long long post, int sgn, double scale, const C* tw, int cat) {
+    static const bool on = getenv("FDGA_DFT_TILE") ? atoi(getenv("FDGA_DFT_TILE")) != 0 : true;
+    const size_t smem = ((size_t)2 * n * n + n) * sizeof(C);
+    // only worth it for many small tiles (the momentum axes of the vertex mesh): a G-sized transform (n = LG = 48, 2 N_G = 32 tiles)
+    // would run on 32 CTAs and is 3-4x slower than the two axis passes with one thread per output (measured)
+    static const int nmax = getenv("FDGA_DFT_TILE_NMAX") ? atoi(getenv("FDGA_DFT_TILE_NMAX")) : 16;
+    if (!on || n > nmax || pre * post < 64 || smem > 200 * 1024 || pre * post > 0x7fffffffLL) return false;
+    if (smem > 48 * 1024) {
+        static size_t attr = 0;
+        if (smem > attr) { if (cudaFuncSetAttribute(dft2_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; } attr = smem; }
+    }
+    const int thr = n * n >= 1024 ? 512 : (n * n >= 256 ? 256 : (n * n >= 64 ? 64 : 32));
+    dft2_tile_kernel<<<(unsigned)(pre * post), thr, smem, ctx->stream>>>(in, out, pre, n, post, sgn, scale, tw);
+    NOTE_LAUNCH("dft2_tile_kernel");
+    ctx->n_launch[cat]++; ctx->total_launches++;
+    return true;
+}
 // 2-d DFT of a G-shaped array over its momentum axes: in -> out (tmp used), out *= scale
 static int dft2_G(fdga_ctx* ctx, const C* in, C* out, C* tmp, int sgn, double scale, int cat) {
     long long nGf = 2 * ctx->g.nG, LG = ctx->g.LG;
     long long n = nGf * LG * LG;
+    if (dft2_tile(ctx, in, out, nGf, (int)LG, 1, sgn, scale, ctx->twLG, cat)) { CK(cudaGetLastError()); return 0; }
     LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, in, tmp, nGf, (int)LG, LG, sgn, 1.0, ctx->twLG);
     LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, tmp, out, nGf * LG, (int)LG, 1LL, sgn, scale, ctx->twLG);
     CK(cudaGetLastError()); return 0;
@@ -470,6 +490,11 @@ static int dft2_G(fdga_ctx* ctx, const C* in, C* out, C* tmp, int sgn, double sc
 // 4-d DFT over the momentum axes of a [pre, L, L, L, L] array; result ends up in `a` (b = scratch)
 static int dft4(fdga_ctx* ctx, C* a, C* b, long long pre, int sgn, double scale, int cat) {
     long long L = ctx->g.L, n = pre * L * L * L * L;
+    // two in-place tile transforms: axes (1, 2) for every (3, 4), then axes (3, 4)
+    if (dft2_tile(ctx, a, a, pre, (int)L, L * L, sgn, 1.0, ctx->twL, cat)) {
+        if (dft2_tile(ctx, a, a, pre * L * L, (int)L, 1, sgn, scale, ctx->twL, cat)) { CK(cudaGetLastError()); return 0; }
+        FAIL("dft4: second tile transform failed to launch");
+    }
     LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, a, b, pre, (int)L, L * L * L, sgn, 1.0, ctx->twL);
     LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, b, a, pre * L, (int)L, L * L, sgn, 1.0, ctx->twL);
     LAUNCH(cat, dft_axis_kernel, nblk(n, 128), 128, a, b, pre * L * L, (int)L, L, sgn, 1.0, ctx->twL);
@@ -667,6 +692,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)); ctx->copy_pending = false;
     CKC(cudaEventCreateWithFlags(&ctx->ev_copy_ready, cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_cache, cudaEventDisableTiming)); ctx->cache_on_lane = false;
     for (int i = 0; i < 3; i++) CKC(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
     for (int l = 0; l < ctx->nlev; l++) if (alloc_level(ctx, ctx->lev[l], dims->lev[l])) { g_create_error = ctx->err; delete ctx; return 1; }
     fdga_level_desc dz = d0;
@@ -753,7 +779,7 @@ int fdga_destroy(fdga_ctx* ctx) {
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_copy_ready); cudaEventDestroy(ctx->ev_copy_done);
     for (int i = 1; i < 3; i++) cudaStreamDestroy(ctx->lane[i]);
-    cudaEventDestroy(ctx->ev_fork); for (int i = 0; i < 3; i++) cudaEventDestroy(ctx->ev_join[i]);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_cache); for (int i = 0; i < 3; i++) cudaEventDestroy(ctx->ev_join[i]);
     cudaStreamDestroy(ctx->main_stream);
     delete ctx;
     return 0;
@@ -1851,6 +1877,7 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
         if (ctx->swave) {       // fft(L, momentum axis) / L^2 -> scratchA / scratchB (src/nonlocal/SDE.jl:217-218); L[] is the intermediate
             C* Lx = ctx->L[pp ? 0 : 1]; C* out = pp ? ctx->scratchA : ctx->scratchB;
             const long long n = pre * g.NP;
+            if (dft2_tile(ctx, Lx, Lx, pre, g.L, 1, -1, 1.0 / ((double)g.L * g.L), ctx->twL, FDGA_T_SDE_RS)) { CK(cudaGetLastError()); continue; }
             LAUNCH(FDGA_T_SDE_RS, dft_axis_kernel, nblk(n, 128), 128, Lx, out, pre, g.L, (long long)g.L, -1, 1.0, ctx->twL);
             LAUNCH(FDGA_T_SDE_RS, dft_axis_kernel, nblk(n, 128), 128, out, Lx, pre * g.L, g.L, 1LL, -1, 1.0 / ((double)g.L * g.L), ctx->twL);
             CK(cudaGetLastError());
@@ -2076,23 +2103,46 @@ static int sde_body(fdga_ctx* ctx, int strategy, int include_U2, int include_Har
 // ---- drivers ---------------------------------------------------------------------------------------------
 // the BSE stages of one iteration: [L_K2, L_K3] | [K1, K2, K3].  The three channels of a stage are independent up to
 // their post-fixes: each runs on its own lane, and the stage ends with one batched SG finish (one NCCL group).
-static int bse_stages(fdga_ctx* ctx, bool with_L, int mfrg) {
+// with_cache: build_K3_cache! (fd flavour) is issued on the lane of the a channel right after the first fork instead of on the main
+// stream before it: only the K3 kernels read the caches, so BSE_L_K2! (or BSE_K1! / BSE_K2! without an L stage) of the other lanes
+// start at once and the K3 kernels wait for the cache event
+static int cache_on_lane_begin(fdga_ctx* ctx) {
+    if (!ctx->forked) return fdga_build_K3_cache(ctx, 0, 0);
+    lane_use(ctx, FDGA_ACH);
+    if (fdga_build_K3_cache(ctx, 0, 0)) return 1;
+    CK(cudaEventRecord(ctx->ev_cache, ctx->stream));
+    ctx->cache_on_lane = true;
+    return 0;
+}
+static int cache_on_lane_wait(fdga_ctx* ctx) {      // every lane (or the main stream) waits for the cache before its K3 kernels
+    if (!ctx->cache_on_lane) return 0;
+    if (ctx->forked) { for (int i = 0; i < 3; i++) CK(cudaStreamWaitEvent(ctx->lane[i], ctx->ev_cache, 0)); }
+    else CK(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_cache, 0));
+    ctx->cache_on_lane = false;
+    return 0;
+}
+static int bse_stages(fdga_ctx* ctx, bool with_L, int mfrg, bool with_cache = false) {
     // issue order: the t channel carries two spin forms (twice the work), so it goes first on the high-priority lane;
     // the post-fixes, which need p, a, t (BSE_templates.jl:35-38: a before t), are ordered by flush_pending
     const int order[3] = {FDGA_TCH, FDGA_PCH, FDGA_ACH};
     ctx->defer = true;
     int rc = 0;
+    if (with_cache && refresh_swave(ctx)) { ctx->defer = false; return 1; }      // the cache kernel's tables, current before the fork
     if (with_L) {
         rc = lanes_fork(ctx, 1u);      // BSE_L_K2!: cross channels of S.F itself
+        if (!rc && with_cache) { rc = cache_on_lane_begin(ctx); with_cache = false; }
         for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_L_K2(ctx, order[i]); }
+        if (!rc) rc = cache_on_lane_wait(ctx);
         for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_L_K3(ctx, order[i]); }   // reads caches and bubbles only
         if (lanes_join(ctx)) rc = 1;
         if (!rc) rc = flush_pending(ctx);
     }
     // BSE_K2!: left vertex S.F + S.F0 (merged level when available), mfRG: S.F0 only
     if (!rc) rc = lanes_fork(ctx, mfrg ? (MOM_ALL & ~MOM_FSUM & ~1u) : (ctx->has_fsum ? (MOM_ALL & ~3u) : (MOM_ALL & ~MOM_FSUM)));
+    if (!rc && with_cache) rc = cache_on_lane_begin(ctx);      // no L stage (scPA): the cache is built beside BSE_K1! / BSE_K2!
     for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_K1(ctx, order[i], mfrg); }
     for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_K2(ctx, order[i], mfrg); }    // K1 and K2 share inputs (FL, right factor)
+    if (!rc) rc = cache_on_lane_wait(ctx);
     // BSE_K3! only reads the caches, the s-wave bubbles and FL.K3 (all final after the L stage): same stage, one SG finish fewer
     for (int i = 0; i < 3 && !rc; i++) { lane_use(ctx, order[i]); rc = fdga_bse_K3(ctx, order[i], mfrg); }
     if (lanes_join(ctx)) rc = 1;
@@ -2137,9 +2187,10 @@ int fdga_iterate_solver(fdga_ctx* ctx, int strategy, int update_sigma, int compu
 }
 static int iterate_body(fdga_ctx* ctx, int strategy, int update_sigma, int compute_hartree) {
     if (update_sigma) { if (fdga_dyson(ctx) || (ctx->opt_local ? fdga_bubbles_local(ctx, 0) : fdga_bubbles_real_space(ctx, 0))) return 1; }
-    if (fdga_build_K3_cache(ctx, 0, 0)) return 1;
-    if (strategy >= FDGA_SCPA_NEW) { if (bse_stages_variant(ctx, strategy)) return 1; }
-    else if (bse_stages(ctx, strategy == FDGA_FDPA, 0)) return 1;
+    static const bool cache_lane = getenv("FDGA_CACHE_ON_LANE") ? atoi(getenv("FDGA_CACHE_ON_LANE")) != 0 : true;
+    if (strategy >= FDGA_SCPA_NEW) { if (fdga_build_K3_cache(ctx, 0, 0) || bse_stages_variant(ctx, strategy)) return 1; }
+    else if (!cache_lane) { if (fdga_build_K3_cache(ctx, 0, 0) || bse_stages(ctx, strategy == FDGA_FDPA, 0)) return 1; }
+    else if (bse_stages(ctx, strategy == FDGA_FDPA, 0, true)) return 1;
     if (fdga_set_F_from_Fbuff(ctx)) return 1;
     if (update_sigma) { if (fdga_sde(ctx, strategy, 1, compute_hartree ? 1 : 0)) return 1; }      // SDE!(S; strategy, include_Hartree = compute_Hartree), src/solve.jl:99
     return 0;
