@@ -1951,6 +1951,15 @@ static std::vector<long long> state_signature(fdga_ctx* ctx) {
     v.push_back(ctx->copy_pending); v.push_back(ctx->opt_serial); v.push_back(ctx->profile);
     return v;
 }
+static void restore_signature(fdga_ctx* ctx, const std::vector<long long>& v) {      // inverse of state_signature
+    size_t i = 0;
+    auto lvl = [&](LevelBuf& lb) { lb.sw_dirty = v[i++] != 0; lb.k1h_dirty = v[i++] != 0; for (int c = 0; c < 3; c++) lb.mom_valid[c] = (unsigned)v[i++]; };
+    for (int l = 0; l < ctx->nlev; l++) lvl(ctx->lev[l]);
+    lvl(ctx->FL); lvl(ctx->Fbuff); if (ctx->has_fsum) lvl(ctx->Fsum);
+    ctx->fsum_dirty = v[i++] != 0; ctx->slabs_dirty = v[i++] != 0;
+    for (int k = 0; k < 4; k++) { ctx->pi_dirty[k] = v[i++] != 0; ctx->pi_src[k] = (int)v[i++]; ctx->pi_full_valid[k] = v[i++] != 0; }
+    for (int k = 0; k < 3; k++) ctx->rt_kind[k] = (int)v[i++];
+}
 int fdga_graph_begin(fdga_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->capturing) FAIL("fdga_graph_begin: already recording");
@@ -1974,8 +1983,9 @@ int fdga_graph_end(fdga_ctx* ctx, int* graph_id) {
     ctx->capturing = false;
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(ctx->main_stream, &g);
-    if (e != cudaSuccess || !g) { ctx->err = std::string("fdga_graph_end: cudaStreamEndCapture: ") + cudaGetErrorString(e); cudaGetLastError(); return 1; }
-    if (state_signature(ctx) != ctx->cap_sig) { cudaGraphDestroy(g); FAIL("fdga_graph_end: the recorded calls do not form a steady-state cycle (lazy tables differ between start and end): run the sequence once eagerly, then record it"); }
+    // a failed recording executed nothing: the lazy-state flags go back to what they were at fdga_graph_begin
+    if (e != cudaSuccess || !g) { restore_signature(ctx, ctx->cap_sig); ctx->err = std::string("fdga_graph_end: cudaStreamEndCapture: ") + cudaGetErrorString(e); cudaGetLastError(); return 1; }
+    if (state_signature(ctx) != ctx->cap_sig) { cudaGraphDestroy(g); restore_signature(ctx, ctx->cap_sig); FAIL("fdga_graph_end: the recorded calls do not form a steady-state cycle (lazy tables differ between start and end): run the sequence once eagerly, then record it"); }
     GraphRec r; r.graph = g; r.exec = nullptr; r.live = true; r.sig = ctx->cap_sig; r.epoch = ctx->epoch;
     r.launches = ctx->total_launches - ctx->cap_launches0;
     for (int i = 0; i < FDGA_T_COUNT; i++) r.n_launch[i] = ctx->n_launch[i] - ctx->cap_n0[i];
@@ -2014,7 +2024,7 @@ extern "C++" {
 // fdga_iterate_solver, fdga_sde and the mfRG matvec are called in loops with the same arguments (fixed-point iteration, Krylov
 // solver).  Once such a call is seen twice from the same lazy state it is recorded, and from then on replayed, as a CUDA graph;
 // any call from another state (or after a rebuild of device tables) runs eagerly.  FDGA_AUTOGRAPH=0 switches this off.
-struct AutoGraph { long long key; int id; bool have_prev, bad; std::vector<long long> sig_prev; long long epoch; };
+struct AutoGraph { long long key; std::vector<int> ids; bool have_prev, bad; std::vector<long long> sig_prev; long long epoch; };      // one graph per lazy state a key was seen in (<= 4)
 static std::vector<std::pair<fdga_ctx*, std::vector<AutoGraph>>> g_auto;      // per context (contexts are not thread-safe anyway)
 static std::vector<AutoGraph>& auto_table(fdga_ctx* ctx) {
     for (auto& p : g_auto) if (p.first == ctx) return p.second;
@@ -2023,15 +2033,6 @@ static std::vector<AutoGraph>& auto_table(fdga_ctx* ctx) {
 }
 static void auto_forget(fdga_ctx* ctx) {
     for (size_t i = 0; i < g_auto.size(); i++) if (g_auto[i].first == ctx) { g_auto.erase(g_auto.begin() + i); return; }
-}
-static void restore_signature(fdga_ctx* ctx, const std::vector<long long>& v) {      // inverse of state_signature
-    size_t i = 0;
-    auto lvl = [&](LevelBuf& lb) { lb.sw_dirty = v[i++] != 0; lb.k1h_dirty = v[i++] != 0; for (int c = 0; c < 3; c++) lb.mom_valid[c] = (unsigned)v[i++]; };
-    for (int l = 0; l < ctx->nlev; l++) lvl(ctx->lev[l]);
-    lvl(ctx->FL); lvl(ctx->Fbuff); if (ctx->has_fsum) lvl(ctx->Fsum);
-    ctx->fsum_dirty = v[i++] != 0; ctx->slabs_dirty = v[i++] != 0;
-    for (int k = 0; k < 4; k++) { ctx->pi_dirty[k] = v[i++] != 0; ctx->pi_src[k] = (int)v[i++]; ctx->pi_full_valid[k] = v[i++] != 0; }
-    for (int k = 0; k < 3; k++) ctx->rt_kind[k] = (int)v[i++];
 }
 static bool autograph_usable(fdga_ctx* ctx) {
     static const bool on = getenv("FDGA_AUTOGRAPH") ? atoi(getenv("FDGA_AUTOGRAPH")) != 0 : true;
@@ -2043,29 +2044,26 @@ static int auto_graphed(fdga_ctx* ctx, long long key, Fn body) {
     std::vector<AutoGraph>& tab = auto_table(ctx);
     AutoGraph* a = nullptr;
     for (auto& e : tab) if (e.key == key) a = &e;
-    if (!a) { AutoGraph e; e.key = key; e.id = -1; e.have_prev = false; e.bad = false; e.epoch = ctx->epoch; tab.push_back(e); a = &tab.back(); }
+    if (!a) { AutoGraph e; e.key = key; e.have_prev = false; e.bad = false; e.epoch = ctx->epoch; tab.push_back(e); a = &tab.back(); }
     if (a->epoch != ctx->epoch) {       // device tables were rebuilt: forget what was recorded
-        if (a->id >= 0) fdga_graph_destroy(ctx, a->id);
-        a->id = -1; a->have_prev = false; a->bad = false; a->epoch = ctx->epoch;
+        for (int id : a->ids) fdga_graph_destroy(ctx, id);
+        a->ids.clear(); a->have_prev = false; a->bad = false; a->epoch = ctx->epoch;
     }
     if (wait_copy(ctx)) return 1;
     ctx->copy_pending = false;
     const std::vector<long long> sig = state_signature(ctx);
-    if (a->id >= 0) {
-        if (sig == ctx->graphs[a->id].sig) return fdga_graph_launch(ctx, a->id);
-        return body();                  // off-cycle call
-    }
-    if (a->bad || !a->have_prev || sig != a->sig_prev) { a->sig_prev = sig; a->have_prev = true; return body(); }
-    // second call from the same state: record it (nothing executes), then replay
+    for (int id : a->ids) if (sig == ctx->graphs[id].sig) return fdga_graph_launch(ctx, id);
+    if (a->bad || a->ids.size() >= 4 || !a->have_prev || sig != a->sig_prev) { a->sig_prev = sig; a->have_prev = true; return body(); }
+    // second call in a row from this state: record it (nothing executes), then replay
     if (fdga_graph_begin(ctx)) { a->bad = true; return body(); }
     const int rc = body();
     int id = -1;
     const int rc2 = fdga_graph_end(ctx, &id);
-    if (rc == 0 && rc2 == 0) { a->id = id; return fdga_graph_launch(ctx, id); }
+    if (rc == 0 && rc2 == 0) { a->ids.push_back(id); return fdga_graph_launch(ctx, id); }
     // not recordable (a host synchronisation inside, or not a steady-state cycle): the recording pass changed host flags without
     // executing anything -- put them back and run the call for real
     a->bad = true;
-    ctx->capturing = false; ctx->forked = false; ctx->cur_lane = 0; ctx->stream = ctx->main_stream; ctx->defer = false; ctx->pending.clear();
+    ctx->capturing = false; ctx->forked = false; ctx->cur_lane = 0; ctx->stream = ctx->main_stream; ctx->defer = false; ctx->pending.clear(); ctx->cache_on_lane = false;
     cudaGetLastError();
     restore_signature(ctx, sig);
     return body();

@@ -116,3 +116,21 @@ def test_automatic_graphs_behind_the_plain_entry_points(nl_method):
         fd.iterate_solver(S, "fdPA"); fd.iterate_solver(S, "fdPA"); fd.iterate_solver(S, "fdPA")
     assert np.array_equal(A.flatten_F(), B.flatten_F())
     A.close(); B.close()
+
+
+def test_automatic_graphs_follow_a_change_of_lazy_state():
+    """after the bubbles switch from the product form to explicit arrays (solve_using_mfRG's mixing) the entry points are called from
+    a different lazy state: a second graph is recorded for it, and the results still equal eager issue"""
+    import fddgasolver_jl_b200 as fd
+    A, B = _solver(2), _solver(2)
+    B.profile(True)
+    for S in (A, B):
+        for _ in range(3):
+            fd.iterate_solver(S, "fdPA", update_Σ=False)
+        fd.mix_bubbles(S, 0.7)
+        for _ in range(4):
+            fd.iterate_solver(S, "fdPA", update_Σ=False)
+            fd.SDE(S, "fdPA")
+    A.pull("Σ"); B.pull("Σ")
+    assert np.array_equal(A.flatten_F(), B.flatten_F()) and np.array_equal(A.Σ, B.Σ)
+    A.close(); B.close()
