@@ -266,7 +266,12 @@ def run_ours(a):
 
     S.unflatten_F(x_np); S.stash_F()
     if use_graph:
-        step_resident, step_e2e = make_graph_steps()
+        try:
+            step_resident, step_e2e = make_graph_steps()
+        except Exception as e:      # never lose the measurement to the replay path: fall back to eager issue and say so
+            print(f"bench.py: CUDA-graph recording failed ({e}); issuing eagerly", file=sys.stderr)
+            use_graph = False
+            step_resident, step_e2e = step_resident_eager, step_e2e_eager
     W = max(a.warmup, 3)
     clocks = ClockSampler(local)
     if rank == 0:
