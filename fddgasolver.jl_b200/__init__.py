@@ -13,7 +13,7 @@ from .solver import (NL2_ParquetSolver, NL_ParquetSolver, ParquetSolver, init_sy
                      BSE_K2, BSE_K3, BSE_K1_new, BSE_K2_new, BSE_K1_1loop, BSE_K2_1loop, BSE_K3_1loop, SDE, SDE_channel_L, iterate_solver, iterate_solver_stepwise, fixed_point, solve, mfRGLinearMap,
                      dqgmres, symmetrize_solver, fixed_point_preconditioned,
                      set_hubbard_bare_Green, compute_hubbard_chemical_potential, mix_bubbles, update_reference, solve_using_mfRG,
-                     interpolate_vertex, interpolate_solver, save_solver, load_solver)
+                     interpolate_vertex, interpolate_solver, save_solver, load_solver, real_array)
 from . import h5min, io, synthetic, types  # noqa: F401,E402
 from .io import load_triqs_data  # noqa: F401,E402
 from .flow import bare_Green_Ω_flow  # noqa: F401,E402

@@ -371,7 +371,15 @@ class ParquetSolver(NL2_ParquetSolver):
 
     local = True
 
-    def __init__(self, nK1, nK2, nK3, Gbare, G0, Σ0, F0, *, T, mode="threads", mΠν_factor=6, device=0):
+    def __init__(self, nK1, nK2, nK3, Gbare, G0, Σ0, F0, *, T, mode="threads", mΠν_factor=6, device=0, Q=np.complex128):
+        # Q = Float64 of the reference (test/test_siam_scPA.jl:22): the particle-hole symmetric impurity has real i G, i Σ and real
+        # vertices.  The device arithmetic is complex128 throughout; with real inputs every imaginary part is an exact zero, and a
+        # real-typed solver insists on that whenever arrays come back (the InexactError Julia would raise) -- see real_array().
+        self.eltype = np.dtype(Q)
+        if self.eltype == np.float64:
+            for a in (Gbare, G0, Σ0):
+                if np.iscomplexobj(a) and np.any(np.asarray(a).imag != 0):
+                    raise L.FdgaError("ParquetSolver(Q = Float64): inputs must be real")
         col = lambda a: np.asfortranarray(np.asarray(a, dtype=np.complex128).reshape(-1, 1))
         super().__init__(nK1, nK2, nK3, 1, col(Gbare), col(G0), col(Σ0), F0, T=T, mode=mode, mΠν_factor=mΠν_factor,
                          device=device, compute_bubbles=False)
@@ -381,6 +389,16 @@ class ParquetSolver(NL2_ParquetSolver):
         self._call("fdga_dyson")
         self._call("fdga_bubbles_local", 0)
         self.pull("G")
+
+
+def real_array(S, a):
+    """the array `a` of a solver in the solver's element type: for ParquetSolver(Q = Float64) the real part, after checking that the
+    imaginary part vanishes identically (what `eltype(S.Σ.data) == Float64` guarantees in the reference)"""
+    if getattr(S, "eltype", np.dtype(np.complex128)) != np.float64:
+        return a
+    if np.any(a.imag != 0):
+        raise L.FdgaError("ParquetSolver(Q = Float64): a complex value appeared in a real-typed solver (InexactError)")
+    return np.ascontiguousarray(a.real)
 
 
 # ---------------------------------------------------------------------- reference-named operations

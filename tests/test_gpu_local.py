@@ -195,3 +195,40 @@ def test_solve_mirror_reproduces_siam_golden_sigma(orc):
     Σ = S.Σ.ravel(order="F")
     assert np.max(np.abs(np.array([Σ[n + nG] for n in (-2, -1, 0, 1)]) - np.array(g["Σ"]))) < 1e-4
     S.close()
+
+
+def test_siam_scPA_real_element_type(orc):
+    """test/test_siam_scPA.jl:22-36 with Q = Float64: the half-filled impurity (e = 0) has real i G, i Σ and real vertices; the
+    real-typed solver goes through the same device arithmetic, every imaginary part is an exact zero, and the golden numbers are
+    reproduced; a doped impurity (complex i G) is refused like Julia's InexactError"""
+    import fddgasolver_jl_b200 as fd
+    T, nmax = 0.1, 6
+    nG, nK1 = 6 * nmax, 4 * nmax
+    g = GOLD[0.0]
+    S = fd.parquet_solver_siam_parquet_approximation(nG, nK1, g["nK2"], g["nK2"], np.float64, e=0.0, Δ=np.pi / 5, D=10.0, T=T, U=1.0, mΠν_factor=1)
+    assert S.eltype == np.float64
+    S.init_sym_grp()
+    nF = S.length_F()
+    x0 = np.concatenate([S.F.flatten(), S.Σ.ravel(order="F")]).real.copy()      # the solver's state is a REAL vector
+
+    def fp(xr):
+        x = xr.astype(np.complex128)
+        R = fd.fixed_point(np.empty_like(x), x, S, "scPA", True)
+        assert not np.any(R.imag)                         # the device never produces an imaginary part from real inputs
+        return R.real.copy()
+    x, it, err = anderson(fp, x0, tol=1e-10)
+    assert err < 1e-10 and x.dtype == np.float64
+    S.unflatten_F(x[:nF].astype(np.complex128)); S.pull("F", "Σ", "G")
+    Σ = fd.real_array(S, S.Σ)
+    assert Σ.dtype == np.float64 and fd.real_array(S, S.G).dtype == np.float64
+    for ch in S.F.channels():
+        for a in ch.arrays():
+            assert fd.real_array(S, a).dtype == np.float64          # raises if any imaginary part is not an exact zero
+    assert np.max(np.abs(np.array([Σ[n + nG, 0] for n in (-2, -1, 0, 1)]) - np.real(np.array(g["Σ"])))) < 1e-4
+    xs = [-4 * np.pi * T + i for i in range(4)]
+    for name, ch in (("γa", S.F.γa), ("γp", S.F.γp), ("γt", S.F.γt)):
+        vals = [orc.interp_boson(ch.K1[:, 0], T, nK1, xx) for xx in xs]
+        assert np.max(np.abs(np.array(vals) - np.array(g[name]))) < 1e-4, name
+    S.close()
+    with pytest.raises(fd.FdgaError, match="must be real"):
+        fd.parquet_solver_siam_parquet_approximation(nG, nK1, g["nK2"], g["nK2"], np.float64, e=0.5, Δ=np.pi / 5, D=10.0, T=T, U=1.0)
