@@ -41,7 +41,11 @@ static const int INF = INT_MAX / 4;
 
 enum { pCh = 0, tCh = 1, aCh = 2 };
 enum { pSp = 0, xSp = 1, dSp = 2 };
-enum { LV_NL2 = 0, LV_LOCAL = 1, LV_CORE = 2, LV_NL = 3 /* NL_Vertex: bosonic momentum only, src/nonlocal/vertex.jl */ };
+enum { LV_NL2 = 0, LV_LOCAL = 1, LV_CORE = 2, LV_NL = 3 /* NL_Vertex: bosonic momentum only, src/nonlocal/vertex.jl */,
+       LV_NL2_MBE = 4, LV_LOCAL_MBE = 5 /* NL2_MBEVertex / MBEVertex: same arrays, multi-boson-exchange evaluation, src/boson_exchange.jl */ };
+enum { CL_K1 = 0, CL_K2 = 1, CL_K2P = 2, CL_K3 = 3, CL_LAMBDA = 4 };      // ClassTag, src/boson_exchange.jl:1-48
+static inline bool is_mbe(int t) { return t == LV_NL2_MBE || t == LV_LOCAL_MBE; }
+static inline bool is_local_lv(int t) { return t == LV_LOCAL || t == LV_LOCAL_MBE; }
 
 // ---------------------------------------------------------------------------------
 // Matsubara index arithmetic (derived from value(nu) = (2n+1) pi T etc.)
@@ -367,9 +371,81 @@ struct VertexEval {
             return -eval(l, W, v, w, P, k, q, tCh, pSp, g);
         }
         // ---- pSp ----
+        if (is_mbe(lv.type)) return eval_mbe(l, W, v, w, P, k, q, Ch, f);
         if (lv.type == LV_LOCAL) return eval_local(l, W, v, w, Ch, f);
         if (lv.type == LV_NL) return eval_nl(l, W, v, w, P, k, q, Ch, f);
         return eval_nl2(l, W, v, w, P, k, q, Ch, f);
+    }
+
+    // ---- multi-boson-exchange vertices, src/boson_exchange.jl ------------------------------------------------------------
+    // F(W, v, w, P, k, q, Ch, Cl): class Cl of channel Ch summed down the chain from level l (:270-330): the MeshFunction CALL of
+    // every level's array (0 outside its mesh and for infinite frequencies; momenta folded; kSW = momentum mean), Lambda from the
+    // RefVertex only (:171-232)
+    cplx eval_class(int l, int W, int v, int w, Mom P, Mom k, Mom q, int Ch, int Cl) const {
+        cplx val = 0;
+        for (int j = l; j < V->nlev; j++) {
+            const orc_level& lv = V->lev[j];
+            if (lv.type == LV_CORE) {
+                if (Cl == CL_LAMBDA) {
+                    if (Ch == pCh) val += core_call(lv, 0, W, v, w);
+                    else if (Ch == tCh) val += core_call(lv, 2, W, v, w);
+                    else val -= core_call(lv, 3, W, w, v);
+                }
+                break;
+            }
+            if (Cl == CL_LAMBDA) continue;
+            if (is_local_lv(lv.type)) {
+                LocChan c = loc(lv, Ch);
+                if (Cl == CL_K1) { if (inB(W, c.nK1)) val += c.k1(W); }
+                else if (Cl == CL_K2) { if (inB(W, c.nK2b) && inF(v, c.nK2f)) val += c.k2(W, v); }
+                else if (Cl == CL_K2P) { if (inB(W, c.nK2b) && inF(w, c.nK2f)) val += c.k2(W, w); }
+                else val += c.k3call(W, v, w);
+            } else {
+                NL2Chan c = nl2(lv, Ch);
+                if (Cl == CL_K1) { if (inB(W, c.nK1)) val += c.k1(W, P); }
+                else if (Cl == CL_K2) { if (inB(W, c.nK2b) && inF(v, c.nK2f)) val += c.k2(W, v, P, k); }
+                else if (Cl == CL_K2P) { if (inB(W, c.nK2b) && inF(w, c.nK2f)) val += c.k2(W, w, P, q); }
+                else if (inB(W, c.nK3b) && inF(v, c.nK3f) && inF(w, c.nK3f)) val += c.k3(W, v, w, P);
+            }
+        }
+        return val;
+    }
+    cplx bare_U() const { const orc_level& c = V->lev[V->nlev - 1]; return cplx(c.U_re, c.U_im); }
+    // parallel spin component of an MBE vertex, :349-422; kSW arguments are explicit mesh averages of the whole expression (:481-560)
+    cplx eval_mbe(int l, int W, int v, int w, Mom P, Mom k, Mom q, int Ch, Flags f) const {
+        if (!is_local_lv(V->lev[l].type) && (k.sw || q.sw)) {
+            cplx s = 0; int n = 0;
+            for (int iq = 0; iq < (q.sw ? NP : 1); iq++) for (int ik = 0; ik < (k.sw ? NP : 1); ik++) {
+                Mom kk = k.sw ? mk(ik % L, ik / L) : k, qq = q.sw ? mk(iq % L, iq / L) : q;
+                s += eval_mbe(l, W, v, w, P, kk, qq, Ch, f); n++;
+            }
+            return s / (double)n;
+        }
+        const cplx U = bare_U();
+        cplx val = U;
+        auto sbe = [&](cplx K1, cplx K2, cplx K2p, cplx K3, cplx u) { return K1 + K2 + K2p + K2 * K2p / (u + K1) + K3; };
+        if (f.gp) {
+            int W2, v2, w2; Mom P2, k2, q2; conv_freq(W, v, w, Ch, pCh, W2, v2, w2); conv_mom(P, k, q, Ch, pCh, P2, k2, q2);
+            val += sbe(eval_class(l, W2, v2, w2, P2, k2, q2, pCh, CL_K1), eval_class(l, W2, v2, w2, P2, k2, q2, pCh, CL_K2),
+                       eval_class(l, W2, v2, w2, P2, k2, q2, pCh, CL_K2P), eval_class(l, W2, v2, w2, P2, k2, q2, pCh, CL_K3), U);
+        }
+        if (f.gt) {       // (tCh, pSp) = (D - M) / 2 with M = -(aCh, pSp), D = 2 (tCh, pSp) - (aCh, pSp), :382-400
+            int W2, v2, w2; Mom P2, k2, q2; conv_freq(W, v, w, Ch, tCh, W2, v2, w2); conv_mom(P, k, q, Ch, tCh, P2, k2, q2);
+            cplx K1 = -eval_class(l, W2, v2, w2, P2, k2, q2, aCh, CL_K1), K2 = -eval_class(l, W2, v2, w2, P2, k2, q2, aCh, CL_K2);
+            cplx K2p = -eval_class(l, W2, v2, w2, P2, k2, q2, aCh, CL_K2P), K3 = -eval_class(l, W2, v2, w2, P2, k2, q2, aCh, CL_K3);
+            val -= sbe(K1, K2, K2p, K3, -U) / 2.0;
+            K1 = 2.0 * eval_class(l, W2, v2, w2, P2, k2, q2, tCh, CL_K1) + K1; K2 = 2.0 * eval_class(l, W2, v2, w2, P2, k2, q2, tCh, CL_K2) + K2;
+            K2p = 2.0 * eval_class(l, W2, v2, w2, P2, k2, q2, tCh, CL_K2P) + K2p; K3 = 2.0 * eval_class(l, W2, v2, w2, P2, k2, q2, tCh, CL_K3) + K3;
+            val += sbe(K1, K2, K2p, K3, U) / 2.0;
+        }
+        if (f.ga) {
+            int W2, v2, w2; Mom P2, k2, q2; conv_freq(W, v, w, Ch, aCh, W2, v2, w2); conv_mom(P, k, q, Ch, aCh, P2, k2, q2);
+            val += sbe(eval_class(l, W2, v2, w2, P2, k2, q2, aCh, CL_K1), eval_class(l, W2, v2, w2, P2, k2, q2, aCh, CL_K2),
+                       eval_class(l, W2, v2, w2, P2, k2, q2, aCh, CL_K2P), eval_class(l, W2, v2, w2, P2, k2, q2, aCh, CL_K3), U);
+        }
+        val += eval_class(l, W, v, w, P, k, q, Ch, CL_LAMBDA);
+        if (!f.F0) { Flags g = f; g.F0 = true; val -= eval(l + 1, W, v, w, P, k, q, Ch, pSp, g); }
+        return val;
     }
 
     // NL_Vertex (bosonic momentum dependence only), src/nonlocal/vertex.jl:69-153 (Brillouin points), :213-377 (s-wave points)
@@ -896,6 +972,48 @@ void orc_build_K3_cache(cplx* const* cache, int nK3b, int nK3f, const orc_vertex
             cache[9][i] = cache[9][i] * 2.0 - cache[8][i];
         }
     }
+}
+
+// ---- build_K3_cache! for MBE vertices: src/boson_exchange.jl:947-1017 (NL2_MBEVertex) and :599-668 (MBEVertex, = the same on a
+// 1 x 1 mesh).  cache_F0* / cache_F* hold the channel-U-irreducible vertex T_r = (I_r - U) + M_r, cache_G* the irreducible
+// finite-difference vertex F - F.F0 ----
+void orc_build_K3_cache_mbe(cplx* const* cache, int nK3b, int nK3f, const orc_vertex* F0, const orc_vertex* F,
+                            const orc_grid* g, int64_t i0, int64_t i1) {
+    int L = g->L, NP = L * L;
+    VertexEval EF0 = {F0, L, NP}, EF = {F, L, NP};
+    K3Shape s = {nK3b, nK3f, NP};
+    int64_t len = (int64_t)s.nB() * s.nF() * s.nF() * NP;
+    if (i1 < 0) i1 = len;
+    Mom sw = SW();
+    const cplx U = EF.bare_U();
+    const Flags np_ = {true, false, true, true}, na = {true, true, true, false}, nt = {true, true, false, true};      // gamma_r = false
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = i0; i < i1; i++) {
+        int W, a, b, iP; decodeK3(i, s, W, a, b, iP); Mom P = mk(iP % L, iP / L);
+        // (W, w, vp, P) = (W, a, b, P): vertices multiplied by bubbles to the left
+        cache[0][i] = EF.eval(0, W, a, b, P, sw, sw, pCh, xSp, np_) - EF.eval(1, W, a, b, P, sw, sw, pCh, xSp, np_);
+        cache[1][i] = EF0.eval(0, W, a, b, P, sw, sw, pCh, xSp, np_) + U - EF0.eval_class(0, W, a, B_minus_F(W, b), P, sw, sw, pCh, CL_K3);
+        cache[2][i] = EF0.eval(0, W, a, b, P, sw, sw, aCh, pSp, na) - U + EF0.eval_class(0, W, a, b, P, sw, sw, aCh, CL_K3);
+        cache[3][i] = EF0.eval(0, W, a, b, P, sw, sw, tCh, pSp, nt) - U + EF0.eval_class(0, W, a, b, P, sw, sw, tCh, CL_K3);
+        cache[3][i] = 2.0 * cache[3][i] - cache[2][i];
+        // (W, v, w, P) = (W, a, b, P): vertices multiplied by bubbles from the right
+        cplx Fp = EF.eval(0, W, a, b, P, sw, sw, pCh, pSp, np_), Fa = EF.eval(0, W, a, b, P, sw, sw, aCh, pSp, na), Ft = EF.eval(0, W, a, b, P, sw, sw, tCh, pSp, nt);
+        cache[4][i] = Fp - EF.eval(1, W, a, b, P, sw, sw, pCh, pSp, np_);
+        cache[5][i] = Fa - EF.eval(1, W, a, b, P, sw, sw, aCh, pSp, na);
+        cache[6][i] = Ft - EF.eval(1, W, a, b, P, sw, sw, tCh, pSp, nt);
+        cache[7][i] = Fp - U + EF.eval_class(0, W, a, b, P, sw, sw, pCh, CL_K3);
+        cache[8][i] = Fa - U + EF.eval_class(0, W, a, b, P, sw, sw, aCh, CL_K3);
+        cache[9][i] = Ft - U + EF.eval_class(0, W, a, b, P, sw, sw, tCh, CL_K3);
+        cache[6][i] = cache[6][i] * 2.0 - cache[5][i];
+        cache[9][i] = cache[9][i] * 2.0 - cache[8][i];
+    }
+}
+
+// evaluator of one asymptotic class for the tests: F(W, v, w, P, k, q, Ch, Cl) from level `level` of the chain
+void orc_eval_class(const orc_vertex* V, int L, int level, int W, int v, int w, const int* P, const int* k, const int* q, int ksw, int qsw,
+                    int Ch, int Cl, cplx* out) {
+    VertexEval E; E.V = V; E.L = L; E.NP = L * L;
+    *out = E.eval_class(level, W, v, w, mk(P[0], P[1]), ksw ? SW() : mk(k[0], k[1]), qsw ? SW() : mk(q[0], q[1]), Ch, Cl);
 }
 
 // ---- build_K3_cache_mfRG!, src/nonlocal_2/build_K3_cache.jl:97-164 ---------------------

@@ -16,7 +16,7 @@ if _HERE not in sys.path:
     sys.path.insert(0, _HERE)
 # the oracle keeps its OWN data model (mesh lengths, shapes, flatten order restated from the reference): oracle/otypes.py.
 # Vertices handed in by tests in the product's containers are copied into it (otypes.adopt), never used in place.
-from otypes import (NL2_Vertex, NL_Vertex, RefVertex, Vertex, aCh, adopt, dSp, nB, nF, pCh, pSp, tCh,  # noqa: E402,F401
+from otypes import (MBEVertex, NL2_MBEVertex, NL2_Vertex, NL_Vertex, RefVertex, Vertex, aCh, adopt, dSp, nB, nF, pCh, pSp, tCh,  # noqa: E402,F401
                     vertex_chain, xSp, zeros)
 
 LIB = os.path.join(_HERE, "_build", "libfdga_oracle.so")
@@ -82,7 +82,7 @@ def vertex_struct(V):
             for j, a in enumerate(X.arrays()):
                 lv.core[j] = a.ctypes.data
         else:
-            lv.type = 0 if isinstance(X, NL2_Vertex) else (3 if isinstance(X, NL_Vertex) else 1)
+            lv.type = (4 if isinstance(X, NL2_MBEVertex) else 0) if isinstance(X, NL2_Vertex) else (3 if isinstance(X, NL_Vertex) else (5 if isinstance(X, MBEVertex) else 1))
             lv.nK1 = X.numK1
             lv.nK2b, lv.nK2f = X.numK2
             lv.nK3b, lv.nK3f = X.numK3
@@ -126,6 +126,21 @@ def eval_vertex(V, L, W, v, w, P, k, q, Ch, Sp, F0=True, Î³p=True, Î³t=True, Î³a
     return complex(out[0])
 
 
+K1Cl, K2Cl, K2pCl, K3Cl, Î›Cl = range(5)
+
+
+def eval_class(V, L, W, v, w, P, k, q, Ch, Cl, level=0):
+    """V(Î©, Î½, Ï‰, P, k, q, Ch, Cl): one asymptotic class summed down the chain (src/boson_exchange.jl:270-330)"""
+    vs = vertex_struct(V)
+    out = np.zeros(1, dtype=np.complex128)
+    ksw, qsw = isinstance(k, str), isinstance(q, str)
+    Pa = (C.c_int * 2)(*P)
+    ka = (C.c_int * 2)(*(k if not ksw else (0, 0)))
+    qa = (C.c_int * 2)(*(q if not qsw else (0, 0)))
+    lib().orc_eval_class(C.byref(vs), L, level, W, v, w, Pa, ka, qa, int(ksw), int(qsw), Ch, Cl, _p(out))
+    return complex(out[0])
+
+
 def eval_channel(V, L, r, W, v, w, P, k, q, K1=True, K2=True, K3=True, level=0):
     vs = vertex_struct(V)
     out = np.zeros(1, dtype=np.complex128)
@@ -144,7 +159,9 @@ SG_NL_PP2, SG_NL_PH2 = 8, 9          # builder kinds of the s-wave solver's K2[Î
 class OracleSolver:
     """CPU restatement of NL2_ParquetSolver (src/nonlocal_2/ParquetSolver.jl:1-154)."""
 
-    def __init__(self, nK1, nK2, nK3, L_, Gbare, G0, Î£0, F0, *, T, mÎ Î½_factor=1, compute_bubbles=True):
+    def __init__(self, nK1, nK2, nK3, L_, Gbare, G0, Î£0, F0, *, T, mÎ Î½_factor=1, compute_bubbles=True, VT=NL2_Vertex):
+        # VT = NL2_MBEVertex: the solver's own vertex S.F is a multi-boson-exchange vertex (src/nonlocal_2/ParquetSolver.jl:86,113);
+        # Fbuff and FL stay asymptotic NL2_Vertex'es (:114)
         self.T, self.L, self.NP = float(T), int(L_), int(L_) ** 2
         self.nK1, self.nK2, self.nK3 = int(nK1), tuple(nK2), tuple(nK3)
         self.Gbare = np.asfortranarray(Gbare, dtype=np.complex128)
@@ -156,7 +173,7 @@ class OracleSolver:
         self.G = self.G0.copy(order="F")
         self.Î£ = self.Î£0.copy(order="F")
         self.F0 = adopt(F0)
-        self.F = NL2_Vertex(self.F0, self.T, nK1, nK2, nK3, self.L)
+        self.F = VT(self.F0, self.T, nK1, nK2, nK3, self.L)
         self.Fbuff = NL2_Vertex(RefVertex(self.T, 0.0), self.T, nK1, nK2, nK3, self.L)
         self.FL = NL2_Vertex(RefVertex(self.T, 0.0), self.T, nK1, nK2, nK3, self.L)
         shpÎ  = (nB(self.nÎ B), nF(self.nÎ F), self.NP, self.NP)
@@ -317,7 +334,7 @@ def build_K3_cache(S, i0=0, i1=-1):
         for c in cs:
             c[...] = 0
     arr = (C.c_void_p * 10)(*[c.ctypes.data for c in cs])
-    lib().orc_build_K3_cache(arr, S.nK3[0], S.nK3[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)),
+    getattr(lib(), "orc_build_K3_cache_mbe" if isinstance(S.F, NL2_MBEVertex) else "orc_build_K3_cache")(arr, S.nK3[0], S.nK3[1], C.byref(vertex_struct(S.F0)), C.byref(vertex_struct(S.F)),
                              C.byref(S.grid), C.c_int64(i0), C.c_int64(i1))
 
 
@@ -826,9 +843,10 @@ class OracleLocalSolver(OracleSolver):
     """CPU restatement of the local ParquetSolver (src/ParquetSolver.jl:5-157): an OracleSolver on a 1 x 1 momentum mesh
     with the local bubbles (1/Î½ tail, mÎ Î½_factor = 6), the local BSE_L_K2! and the local SDE L kernels (own Î³ only)."""
 
-    def __init__(self, nK1, nK2, nK3, Gbare, G0, Î£0, F0, *, T, mÎ Î½_factor=6):
+    def __init__(self, nK1, nK2, nK3, Gbare, G0, Î£0, F0, *, T, mÎ Î½_factor=6, VT=NL2_Vertex):
+        # VT = NL2_MBEVertex: ParquetSolver(...; VT = MBEVertex), carried on the 1 x 1 mesh like everything local
         col = lambda a: np.asfortranarray(np.asarray(a, dtype=np.complex128).reshape(-1, 1))
-        super().__init__(nK1, nK2, nK3, 1, col(Gbare), col(G0), col(Î£0), F0, T=T, mÎ Î½_factor=mÎ Î½_factor, compute_bubbles=False)
+        super().__init__(nK1, nK2, nK3, 1, col(Gbare), col(G0), col(Î£0), F0, T=T, mÎ Î½_factor=mÎ Î½_factor, compute_bubbles=False, VT=VT)
         self.local = True
         bubbles_local(self, self.Î 0pp, self.Î 0ph, self.G0)
         Dyson(self)

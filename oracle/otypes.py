@@ -182,8 +182,17 @@ class ONL_Vertex(_OVertexBase):
             setattr(self, n, OChannel(T, numK1, numK2, numK3, L, swave=True))
 
 
+class OMBEVertex(OVertex):
+    """MBEVertex (src/boson_exchange.jl:237-266): the arrays of a Vertex, evaluated as screened interaction / Hedin vertices /
+    multi-boson part"""
+
+
+class ONL2_MBEVertex(ONL2_Vertex):
+    """NL2_MBEVertex (src/boson_exchange.jl:738-770)"""
+
+
 # the names oracle.py uses
-RefVertex, Vertex, NL2_Vertex, NL_Vertex = ORefVertex, OVertex, ONL2_Vertex, ONL_Vertex
+RefVertex, Vertex, NL2_Vertex, NL_Vertex, MBEVertex, NL2_MBEVertex = ORefVertex, OVertex, ONL2_Vertex, ONL_Vertex, OMBEVertex, ONL2_MBEVertex
 
 
 def adopt(V):
@@ -193,11 +202,12 @@ def adopt(V):
     if hasattr(V, "Fp_p"):
         return ORefVertex(V.T, V.U, V.numK3, V.Fp_p, V.Fp_x, V.Ft_p, V.Ft_x)
     F0 = adopt(V.F0)
+    mbe = bool(getattr(V, "mbe", False)) or type(V).__name__.endswith("MBEVertex")
     if getattr(V, "L", None) is not None and V.γp.K1.ndim == 2:
-        cls = ONL_Vertex if V.γp.K2.ndim == 3 else ONL2_Vertex
+        cls = ONL_Vertex if V.γp.K2.ndim == 3 else (ONL2_MBEVertex if mbe else ONL2_Vertex)
         out = cls(F0, V.T, V.numK1, V.numK2, V.numK3, V.L)
     else:
-        out = OVertex(F0, V.T, V.numK1, V.numK2, V.numK3)
+        out = (OMBEVertex if mbe else OVertex)(F0, V.T, V.numK1, V.numK2, V.numK3)
     out.set(V)
     return out
 

@@ -1,0 +1,134 @@
+"""Multi-boson-exchange vertices (MBEVertex / NL2_MBEVertex, src/boson_exchange.jl) in the CPU oracle, pinned against the reference's
+tests test/test_boson_exchange_NL2.jl and test/test_boson_exchange_local.jl."""
+import numpy as np
+import pytest
+
+from helpers import anderson, flatten_solver, oracle_fixed_point
+
+INF = (2 ** 31 - 1) // 4
+
+
+def _rand(V, seed):
+    rng = np.random.default_rng(seed)
+    for g in V.channels():
+        for a in g.arrays():
+            a[...] = rng.random(a.shape) + 1j * rng.random(a.shape)
+    return V
+
+
+def test_nl2_mbe_bare_vertex_and_infinite_frequencies(orc):
+    """test/test_boson_exchange_NL2.jl:29-42"""
+    from otypes import NL2_MBEVertex, RefVertex, pCh, tCh, aCh, pSp, xSp, dSp
+    T, U, L = 0.5, 2.0, 3
+    Γ = NL2_MBEVertex(RefVertex(T, U), T, 10, (5, 5), (3, 3), L)
+    W, v, w, P, k, q = 0, 0, 1, (0, 1), (2, 1), (-1, 1)
+    for ch in (aCh, pCh, tCh):
+        for sp, u in ((pSp, U), (dSp, U), (xSp, -U)):
+            assert abs(orc.eval_vertex(Γ, L, W, v, w, P, k, q, ch, sp) - u) < 1e-14
+    _rand(Γ, 1)
+    fold = lambda m: (m[0] % L) + L * (m[1] % L)
+    for ch, g in ((aCh, Γ.γa), (pCh, Γ.γp), (tCh, Γ.γt)):
+        K1 = g.K1[W + 9, fold(P)]
+        assert abs(orc.eval_vertex(Γ, L, W, v, INF, P, k, q, ch, pSp) - (U + K1 + g.K2[W + 4, v + 5, fold(P), fold(k)])) < 1e-13
+        assert abs(orc.eval_vertex(Γ, L, W, INF, w, P, k, q, ch, pSp) - (U + K1 + g.K2[W + 4, w + 5, fold(P), fold(q)])) < 1e-13
+        assert abs(orc.eval_vertex(Γ, L, W, INF, INF, P, k, q, ch, pSp) - (U + K1)) < 1e-13
+
+
+def test_mbe_own_channel_formula_and_classes(orc):
+    """src/boson_exchange.jl:349-422 written out for one channel: U + K1 + K2 + K2' + K2 K2' / (U + K1) + K3, with the classes summed
+    over the levels of a nested chain (NL2_MBEVertex over a local MBEVertex over a RefVertex with a core)"""
+    from otypes import MBEVertex, NL2_MBEVertex, RefVertex, pCh, aCh, pSp
+    import oracle as o
+    T, U, L = 0.5, 2.0, 3
+    rng = np.random.default_rng(3)
+    core = RefVertex(T, U, (2, 2), *[rng.random((3, 4, 4)) + 1j * rng.random((3, 4, 4)) for _ in range(4)])
+    F1 = _rand(MBEVertex(core, T, 10, (8, 8), (6, 6)), 4)
+    F3 = _rand(NL2_MBEVertex(F1, T, 6, (5, 5), (4, 4), L), 5)
+    W, v, w, P, k, q = -1, -1, 1, (-1, 2), (2, 6), (1, -2)
+    fold = lambda m: (m[0] % L) + L * (m[1] % L)
+    for ch, g3, g1 in ((pCh, F3.γp, F1.γp), (aCh, F3.γa, F1.γa)):
+        K1 = g3.K1[W + 5, fold(P)] + g1.K1[W + 9]
+        K2 = g3.K2[W + 4, v + 5, fold(P), fold(k)] + g1.K2[W + 7, v + 8]
+        K2p = g3.K2[W + 4, w + 5, fold(P), fold(q)] + g1.K2[W + 7, w + 8]
+        K3 = g3.K3[W + 3, v + 4, w + 4, fold(P)] + g1.K3[W + 5, v + 6, w + 6]
+        for cl, val in ((o.K1Cl, K1), (o.K2Cl, K2), (o.K2pCl, K2p), (o.K3Cl, K3)):
+            assert abs(orc.eval_class(F3, L, W, v, w, P, k, q, ch, cl) - val) < 1e-13
+        Λ = core.Fp_p[W + 1, v + 2, w + 2] if ch == pCh else -core.Ft_x[W + 1, w + 2, v + 2]
+        assert abs(orc.eval_class(F3, L, W, v, w, P, k, q, ch, o.ΛCl) - Λ) < 1e-14
+        kw = dict(γp=ch == pCh, γt=False, γa=ch == aCh)
+        exp = U + K1 + K2 + K2p + K2 * K2p / (U + K1) + K3 + Λ
+        assert abs(orc.eval_vertex(F3, L, W, v, w, P, k, q, ch, pSp, **kw) - exp) < 1e-12
+        # F0 = false subtracts the full evaluation of the reference chain
+        sub = orc.eval_vertex(F3, L, W, v, w, P, k, q, ch, pSp, level=1, **kw)
+        assert abs(orc.eval_vertex(F3, L, W, v, w, P, k, q, ch, pSp, F0=False, **kw) - (exp - sub)) < 1e-12
+
+
+@pytest.mark.parametrize("v,w", [(2, -1), (INF, -1), (2, INF)])
+def test_nl2_mbe_swave_points_are_mesh_averages(orc, v, w):
+    """test/test_boson_exchange_NL2.jl:103-140"""
+    from otypes import NL2_MBEVertex, RefVertex, pCh, tCh, aCh, pSp, xSp, dSp
+    T, L, W = 0.5, 3, 1
+    F = _rand(NL2_MBEVertex(RefVertex(T, 2.0), T, 10, (4, 3), (2, 1), L), 7)
+    pts = [(i, j) for j in range(L) for i in range(L)]
+    P, k = pts[7], pts[3]
+    for ch in (aCh, pCh, tCh):
+        for sp in (pSp, xSp, dSp):
+            for γa, γp, γt, F0 in ((1, 1, 1, 1), (1, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 0, 0, 1)):
+                kw = dict(F0=bool(F0), γp=bool(γp), γt=bool(γt), γa=bool(γa))
+                full = lambda a, b: orc.eval_vertex(F, L, W, v, w, P, a, b, ch, sp, **kw)
+                assert abs(full("sw", k) - np.mean([full(x, k) for x in pts])) < 1e-12
+                assert abs(full(k, "sw") - np.mean([full(k, x) for x in pts])) < 1e-12
+                assert abs(full("sw", "sw") - np.mean([full(x, y) for x in pts for y in pts])) < 1e-12
+
+
+# ------------------------------------------------------------------ test/test_boson_exchange_local.jl: "SIAM parquet MBE"
+def _siam(orc, VT, nmax, nG_factor=6, nK1_factor=4):
+    from otypes import RefVertex
+    T, U, D, e, Δ = 0.1, 1.0, 10.0, 0.5, np.pi / 5
+    Gb = orc.siam_bare_Green(T, nG_factor * nmax, e=e, Δ=Δ, D=D)
+    S = orc.OracleLocalSolver(nK1_factor * nmax, (nmax, nmax), (nmax, nmax), Gb, np.zeros_like(Gb), np.zeros_like(Gb), RefVertex(T, U), T=T, VT=VT)
+    S.init_sym_grp()
+    return S
+
+
+def _solve_local(orc, S, strategy, tol=1e-9):
+    nF = len(S.F)
+
+    def fp(x):
+        S.F.unflatten(x[:nF])
+        S.Σ[...] = x[nF:].reshape(S.Σ.shape, order="F")
+        orc.iterate_solver_local(S, strategy, True)
+        return np.concatenate([S.F.flatten(), S.Σ.ravel(order="F")]) - x
+    x, it, err = anderson(fp, flatten_solver(S), tol=tol)
+    assert err < tol, (it, err)
+    S.F.unflatten(x[:nF]); S.Σ[...] = x[nF:].reshape(S.Σ.shape, order="F")
+    return x
+
+
+@pytest.mark.slow
+def test_siam_parquet_with_mbe_vertex_equals_asymptotic_parquet(orc):
+    """test/test_boson_exchange_local.jl:87-128 at the reference's sizes (nmax = 24) and with its tolerances: the converged scPA
+    solution in the MBE parametrisation and in the asymptotic one have the same self-energy (2e-6), K1 and K2 classes (2e-5) and
+    full vertex in every channel and spin component (1e-4).  This pins evaluator, MBE cache and the shared BSE kernels together."""
+    from otypes import NL2_MBEVertex, NL2_Vertex, pCh, tCh, aCh, pSp, xSp, dSp
+    S1 = _siam(orc, NL2_MBEVertex, 24); _solve_local(orc, S1, "scPA", tol=1e-7)
+    S2 = _siam(orc, NL2_Vertex, 24); _solve_local(orc, S2, "scPA", tol=1e-7)
+    assert np.max(np.abs(S1.Σ - S2.Σ)) < 2e-6
+    for n in ("γa", "γp", "γt"):
+        assert np.max(np.abs(getattr(S1.F, n).K1 - getattr(S2.F, n).K1)) < 2e-5, n
+        assert np.max(np.abs(getattr(S1.F, n).K2 - getattr(S2.F, n).K2)) < 2e-5, n
+    z = (0, 0)
+    for ch in (aCh, pCh, tCh):
+        for sp in (pSp, dSp, xSp):
+            d = max(abs(orc.eval_vertex(S1.F, 1, 0, v, w, z, z, z, ch, sp) - orc.eval_vertex(S2.F, 1, 0, v, w, z, z, z, ch, sp))
+                    for v in range(-20, 20) for w in range(-20, 20))
+            assert d < 1e-4, (ch, sp, d)
+    assert np.max(np.abs(S1.F.γa.K3 - S2.F.γa.K3)) > 1e-4          # K3 of the MBE vertex is the multi-boson part, not the asymptotic K3
+
+
+def test_siam_mbe_fdPA_equals_scPA_for_zero_reference(orc):
+    """test/test_boson_exchange_local.jl:154-165 (smaller boxes)"""
+    from otypes import NL2_MBEVertex
+    S0 = _siam(orc, NL2_MBEVertex, 3, 8, 8); x0 = _solve_local(orc, S0, "scPA", tol=1e-10)
+    S1 = _siam(orc, NL2_MBEVertex, 3, 8, 8); x1 = _solve_local(orc, S1, "fdPA", tol=1e-10)
+    assert np.max(np.abs(x0 - x1)) < 1e-9
