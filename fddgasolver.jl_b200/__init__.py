@@ -5,7 +5,7 @@ reference's NL2_ParquetSolver interface (solver.py).  Import it as ``fddgasolver
 name contains a dot; the top-level shim ``fddgasolver_jl_b200.py`` registers it under that name).
 """
 from ._lib import FdgaError, LIB_PATH, EXPORTS  # noqa: F401
-from .types import (pCh, tCh, aCh, pSp, xSp, dSp, Channel, NL2_Channel, NL_Channel, RefVertex, Vertex, NL2_Vertex, NL_Vertex,  # noqa: F401
+from .types import (pCh, tCh, aCh, pSp, xSp, dSp, Channel, NL2_Channel, NL_Channel, RefVertex, Vertex, NL2_Vertex, NL_Vertex, MBEVertex, NL2_MBEVertex,  # noqa: F401
                     vertex_chain, nB, nF)
 from .models import hubbard_bare_Green, hubbard_band, siam_bare_Green  # noqa: F401
 from .solver import (NL2_ParquetSolver, NL_ParquetSolver, ParquetSolver, init_sym_grp, Dyson, compute_occupation, bubbles, bubbles_real_space,  # noqa: F401

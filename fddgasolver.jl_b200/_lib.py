@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("FDGA_LIB_PATH", os.path.join(_HERE, "libfdga.so"))   
 FDGA_MAX_LEVELS = 6
 PCH, TCH, ACH = 0, 1, 2
 K1, K2, K3 = 0, 1, 2
-LV_NL2, LV_LOCAL, LV_CORE, LV_NL = 0, 1, 2, 3
+LV_NL2, LV_LOCAL, LV_CORE, LV_NL, LV_NL2_MBE, LV_LOCAL_MBE = 0, 1, 2, 3, 4, 5
 V_FL, V_FBUFF = 100, 101
 G, G0, GBARE, SIGMA, SIGMA0 = 0, 1, 2, 3, 4
 PI0PP, PI0PH, PIPP, PIPH = 0, 1, 2, 3

@@ -71,7 +71,7 @@ struct DevChan {
     const C *K1m;     // [P,W]      K1 with the transfer momentum fastest
 };
 struct DevLevel {
-    int type, nK1, nK2b, nK2f, nK3b, nK3f, pad0, pad1;
+    int type, nK1, nK2b, nK2f, nK3b, nK3f, mbe /* 1: MBEVertex / NL2_MBEVertex evaluation (src/boson_exchange.jl) */, pad1;
     C U;
     DevChan ch[3];
     const C* core[4];
@@ -206,13 +206,100 @@ FDGA_HD Arg convert(const Arg& a, int from, int to) {
     return b;
 }
 
+// ---- multi-boson-exchange vertices (src/boson_exchange.jl) ---------------------------------------------------------------------
+// class Cl of channel r summed down the chain from level l0 (:270-330): the MeshFunction CALL of every level's array (0 outside
+// its own mesh and for infinite frequencies), Lambda from the RefVertex only (:171-232).  Momenta are Brillouin points.
+enum { CL_K1 = 0, CL_K2 = 1, CL_K2P = 2, CL_K3 = 3, CL_LAMBDA = 4 };
+struct Classes { C K1, K2, K2p, K3; };
+__host__ __device__ inline Classes mbe_classes(const DevChain& c, int l0, int r, const Arg& b) {
+    Classes o; o.K1 = o.K2 = o.K2p = o.K3 = zeroC();
+    const int L = c.L, NP = c.NP;
+    for (int l = l0; l < c.nlev; ++l) {
+        const DevLevel& lv = c.lev[l];
+        if (lv.type == LV_CORE) break;
+        const DevChan& ch = lv.ch[r];
+        const bool nl2 = lv.type == LV_NL2;
+        const size_t iP = nl2 ? kidx(b.Px, b.Py, L) : 0, ik = nl2 ? kidx(b.kx, b.ky, L) : 0, iq = nl2 ? kidx(b.qx, b.qy, L) : 0;
+        if (inB(b.W, lv.nK1)) o.K1 += ldg(ch.K1 + posB(b.W, lv.nK1) + (size_t)(2 * lv.nK1 - 1) * iP);
+        if (inB(b.W, lv.nK2b)) {
+            const int nB = 2 * lv.nK2b - 1, nF = 2 * lv.nK2f;
+            const size_t sP = (size_t)nB * nF;
+            if (inF(b.v, lv.nK2f)) o.K2 += ldg(ch.K2 + posB(b.W, lv.nK2b) + (size_t)nB * posF(b.v, lv.nK2f) + sP * (iP + (size_t)NP * ik));
+            if (inF(b.w, lv.nK2f)) o.K2p += ldg(ch.K2 + posB(b.W, lv.nK2b) + (size_t)nB * posF(b.w, lv.nK2f) + sP * (iP + (size_t)NP * iq));
+        }
+        if (inB(b.W, lv.nK3b) && inF(b.v, lv.nK3f) && inF(b.w, lv.nK3f)) {
+            const int nB3 = 2 * lv.nK3b - 1, nF3 = 2 * lv.nK3f;
+            o.K3 += ldg(ch.K3 + posB(b.W, lv.nK3b) + (size_t)nB3 * (posF(b.v, lv.nK3f) + (size_t)nF3 * (posF(b.w, lv.nK3f) + (size_t)nF3 * iP)));
+        }
+    }
+    return o;
+}
+__host__ __device__ inline C mbe_lambda(const DevChain& c, int Ch, const Arg& a) {
+    const DevLevel& lv = c.lev[c.nlev - 1];
+    if (Ch == CH_P) return core_call(lv, 0, a.W, a.v, a.w);
+    if (Ch == CH_T) return core_call(lv, 2, a.W, a.v, a.w);
+    return -core_call(lv, 3, a.W, a.w, a.v);
+}
+__host__ __device__ inline Arg convert_inf(const Arg& a, int from, int to) {      // convert() with infinite frequencies propagated
+    Arg b = convert(a, from, to);
+    if (from != to && (isinfF(a.v) || isinfF(a.w))) {
+        // every converted frequency that involves an infinite one is infinite: the class arrays then evaluate to 0 (:349-422 with
+        // the MeshFunction call of an InfiniteMatsubaraFrequency)
+        b.W = FDGA_INF; b.v = isinfF(a.v) || isinfF(a.w) ? FDGA_INF : b.v; b.w = FDGA_INF;
+    }
+    return b;
+}
+FDGA_HD C mbe_sbe(const Classes& k, C u) {      // K1 + K2 + K2' + K2 K2' / (u + K1) + K3
+    const C d = u + k.K1;
+    const double n = d.x * d.x + d.y * d.y;
+    const C num = k.K2 * k.K2p;
+    const C q = mkC((num.x * d.x + num.y * d.y) / n, (num.y * d.x - num.x * d.y) / n);
+    return k.K1 + k.K2 + k.K2p + q + k.K3;
+}
+// F(W, v, w, P, k, q, Ch, pSp; F0 = true, gamma switches) of the MBE chain starting at level l, Brillouin-point momenta (:349-416)
+__host__ __device__ inline C mbe_total(const DevChain& c, int l, int Ch, const Arg& a, unsigned f) {
+    const C U = c.lev[c.nlev - 1].U;
+    C val = U;
+    if (f & FL_GP) val += mbe_sbe(mbe_classes(c, l, CH_P, convert_inf(a, Ch, CH_P)), U);
+    if (f & FL_GT) {      // (tCh, pSp) = (D - M) / 2,  M = -(aCh, pSp),  D = 2 (tCh, pSp) - (aCh, pSp)
+        const Arg b = convert_inf(a, Ch, CH_T);
+        const Classes ka = mbe_classes(c, l, CH_A, b), kt = mbe_classes(c, l, CH_T, b);
+        Classes m; m.K1 = -ka.K1; m.K2 = -ka.K2; m.K2p = -ka.K2p; m.K3 = -ka.K3;
+        Classes d; d.K1 = 2.0 * kt.K1 + m.K1; d.K2 = 2.0 * kt.K2 + m.K2; d.K2p = 2.0 * kt.K2p + m.K2p; d.K3 = 2.0 * kt.K3 + m.K3;
+        val += (mbe_sbe(d, U) - mbe_sbe(m, -U)) * 0.5;
+    }
+    if (f & FL_GA) val += mbe_sbe(mbe_classes(c, l, CH_A, convert_inf(a, Ch, CH_A)), U);
+    return val + mbe_lambda(c, Ch, a);
+}
+
 // ---- full vertex, parallel spin, chain from level lev0 ---------------------------------------
 // SW = false: P, k, q are Brillouin points.  SW = true: k = q = kSW (P a Brillouin point).
 // a.v or a.w may be FDGA_INF (then only the own channel contributes, src/nonlocal/vertex.jl:137-150).
 // `flags` (F0 / gamma switches) act on level lev0 only: the reference calls F.F0(...) without
 // forwarding them (src/nonlocal/vertex.jl:87-89).
+template <bool SW> FDGA_HD C eval_p(const DevChain& c, int lev0, int Ch, const Arg& a, unsigned flags);
+// parallel spin component of an MBE level; SW: k = q = kSW are explicit averages of the whole (nonlinear) expression over the
+// momentum mesh (:481-560); F0 off subtracts the full evaluation of the chain below with the same gamma switches (:418-420)
+template <bool SW>
+__host__ __device__ inline C eval_p_mbe(const DevChain& c, int l, int Ch, const Arg& a, unsigned flags) {
+    const bool below_mbe = c.lev[l + 1].mbe != 0;
+    const unsigned g = flags | FL_F0;
+    auto one = [&](const Arg& x) -> C {
+        C v = mbe_total(c, l, Ch, x, flags);
+        if (!(flags & FL_F0)) v = v - (below_mbe ? mbe_total(c, l + 1, Ch, x, flags) : eval_p<false>(c, l + 1, Ch, x, g));
+        return v;
+    };
+    if (!SW || c.lev[l].type != LV_NL2) return one(a);
+    C s = zeroC();
+    for (int iq = 0; iq < c.NP; ++iq) for (int ik = 0; ik < c.NP; ++ik) {
+        Arg x = a; x.kx = ik % c.L; x.ky = ik / c.L; x.qx = iq % c.L; x.qy = iq / c.L;
+        s += one(x);
+    }
+    return s / ((double)c.NP * (double)c.NP);
+}
 template <bool SW>
 FDGA_HD C eval_p(const DevChain& c, int lev0, int Ch, const Arg& a, unsigned flags) {
+    if (c.lev[lev0].mbe) return eval_p_mbe<SW>(c, lev0, Ch, a, flags);
     C val = zeroC();
     const bool anyinf = isinfF(a.v) || isinfF(a.w);
     const int L = c.L, NP = c.NP;

@@ -493,6 +493,65 @@ __global__ void build_cache_kernel(const __grid_constant__ DevChain F0, const __
     out.c[9][i] = ft * 2.0 - fa;
 }
 
+// ---- build_K3_cache! for MBE vertices: src/boson_exchange.jl:947-1017 (NL2_MBEVertex), :599-668 (MBEVertex = the same on a 1 x 1
+// mesh).  cache_F0* / cache_F*: channel-U-irreducible vertex T_r = (I_r - U) + M_r; cache_G*: F - F.F0.  The kSW evaluations of a
+// nonlinear vertex are explicit N_P^2 averages (eval_p_mbe<true>), as in the reference: a small-mesh path. ----
+__global__ void build_cache_mbe_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ DevChain F, CachePtrs out,
+                                       Grid g, long long i0, long long i1) {
+    long long i = i0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    int W, a1, b1, iP; decode_k3(g, i, W, a1, b1, iP);
+    Arg a; a.W = W; a.v = a1; a.w = b1; a.Px = iP % g.L; a.Py = iP / g.L; a.kx = a.ky = a.qx = a.qy = 0;
+    const C U = F.lev[F.nlev - 1].U;
+    constexpr unsigned NP_ = FL_F0 | FL_GT | FL_GA, NA_ = FL_F0 | FL_GP | FL_GT, NT_ = FL_F0 | FL_GP | FL_GA;      // gamma_r = false
+    // class K3 of a chain at (W, v, w, P): independent of the fermionic momenta
+    auto k3 = [&](const DevChain& V, int l, int r, int v, int w) { Arg x = a; x.v = v; x.w = w; return mbe_classes(V, l, r, x).K3; };
+    // (W, w, v', P) block: vertices multiplied by bubbles to the left
+    out.c[0][i] = eval_vertex<true>(F, 0, CH_P, SP_X, a, NP_) - eval_vertex<true>(F, 1, CH_P, SP_X, a, NP_);
+    out.c[1][i] = eval_vertex<true>(F0, 0, CH_P, SP_X, a, NP_) + U - k3(F0, 0, CH_P, a1, W - b1 - 1);
+    const C f0a = eval_vertex<true>(F0, 0, CH_A, SP_P, a, NA_) - U + k3(F0, 0, CH_A, a1, b1);
+    const C f0t = eval_vertex<true>(F0, 0, CH_T, SP_P, a, NT_) - U + k3(F0, 0, CH_T, a1, b1);
+    out.c[2][i] = f0a;
+    out.c[3][i] = 2.0 * f0t - f0a;
+    // (W, v, w, P) block: vertices multiplied by bubbles from the right
+    const C Fp = eval_vertex<true>(F, 0, CH_P, SP_P, a, NP_), Fa = eval_vertex<true>(F, 0, CH_A, SP_P, a, NA_), Ft = eval_vertex<true>(F, 0, CH_T, SP_P, a, NT_);
+    const C gpp = Fp - eval_vertex<true>(F, 1, CH_P, SP_P, a, NP_);
+    const C ga = Fa - eval_vertex<true>(F, 1, CH_A, SP_P, a, NA_);
+    const C gt = Ft - eval_vertex<true>(F, 1, CH_T, SP_P, a, NT_);
+    const C fp = Fp - U + k3(F, 0, CH_P, a1, b1), fa = Fa - U + k3(F, 0, CH_A, a1, b1), ft = Ft - U + k3(F, 0, CH_T, a1, b1);
+    out.c[4][i] = gpp;
+    out.c[5][i] = ga;
+    out.c[6][i] = gt * 2.0 - ga;
+    out.c[7][i] = fp;
+    out.c[8][i] = fa;
+    out.c[9][i] = ft * 2.0 - fa;
+}
+
+// ---- BSE_L_K2! of the local solver, generic form (one CTA per representative (W, v)): src/BSEa/BSEa_K2.jl:1-40, w over the bubble
+// mesh, crossing on the right vertex (which is inside Rt = RK_LK2_LOC).  Used for MBE vertices, whose left factor does not split
+// into the per-level pieces of the column kernels. ----
+template <int CH>
+__global__ void bse_lk2_loc_kernel(const __grid_constant__ DevChain F, const C* __restrict__ Rt, C* __restrict__ repvals,
+                                   SymDev sg, long long c0, Grid g, double scale, const int* __restrict__ map) {
+    constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
+    constexpr unsigned FLG = (CH == CH_P ? 0u : FL_GP) | (CH == CH_T ? 0u : FL_GT) | (CH == CH_A ? 0u : FL_GA);
+    long long cls = c0 + blockIdx.x;
+    long long idx = sg.index[sg.offsets[cls]];
+    const int nB2 = 2 * g.nK2b - 1, nF2 = 2 * g.nK2f, nw = 2 * g.nPiF;
+    long long t0 = idx;
+    int iW = t0 % nB2; t0 /= nB2; int iv = t0 % nF2; t0 /= nF2; int iP = t0 % g.NP; int ik = t0 / g.NP;
+    int W = iW - (g.nK2b - 1), v = iv - g.nK2f, Px = iP % g.L, Py = iP / g.L, kx = ik % g.L, ky = ik / g.L;
+    const C* slab = Rt + (size_t)nw * g.NP * slab_index(map, iW, nB2, iP);
+    C acc = zeroC();
+    for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
+        int iq = t % g.NP, iw = t / g.NP;
+        Arg a; a.W = W; a.v = v; a.w = iw - g.nPiF; a.Px = Px; a.Py = Py; a.kx = kx; a.ky = ky; a.qx = iq % g.L; a.qy = iq / g.L;
+        acc += eval_vertex<false>(F, 0, CH, SP, a, FLG) * slab[t];
+    }
+    acc = block_reduce(acc);
+    if (threadIdx.x == 0) repvals[cls] = acc * scale;
+}
+
 // ---- build_K3_cache_mfRG!: src/nonlocal_2/build_K3_cache.jl:108-161.  One thread per class rep --------
 //  kind 0: Gpx (pCh,xSp)  1: Gpp (pCh,pSp)  2: Ga  3: Gt   = S.F(...; g_r=false) - S.F.F0(...; g_r=false)
 //  kind 4: Fp  5: Fa  6: Ft                                = S.F0(W,v,w) - S.F0(W,inf,w)

@@ -35,6 +35,7 @@ struct LevelBuf {
     C* core[4];
     size_t corelen;
     bool sw_dirty;
+    bool mbe;             // MBEVertex / NL2_MBEVertex: same arrays as d.type (the BASE type), multi-boson-exchange evaluation
 };
 struct SymGroup {
     bool set;
@@ -134,6 +135,7 @@ struct fdga_ctx {
     C* PiMixed[2];           // Pipp_mixed, Piph_mixed of solve_using_mfRG! (fdga_mix_bubbles / fdga_update_reference)
     // s-wave solver (NL_ParquetSolver): lev[0] is an FDGA_LV_NL level; bubbles are Pi[W,w,P] and live in Pisw[] (fdga_swave.cuh)
     bool swave; C* swScratch[2];
+    bool mbe;             // some level of the S.F chain is an MBE vertex: generic per-term kernels only (the evaluator is nonlinear)
     // CUDA graphs
     bool capturing; long long epoch; std::vector<GraphRec> graphs; std::vector<long long> cap_sig; long long cap_launches0; long long cap_n0[FDGA_T_COUNT];
     C* Rt3[3]; int rt_kind[3]; // per-channel right factors (W on the bubble mesh) reused between BSE_K1! and BSE_K2!
@@ -182,8 +184,12 @@ static size_t lenK(const fdga_level_desc& d, int cls, int NP) {
     return nB3 * nF3 * nF3 * (mom ? NP : 1);
 }
 
-static int alloc_level(fdga_ctx* ctx, LevelBuf& lb, const fdga_level_desc& d) {
+static int alloc_level(fdga_ctx* ctx, LevelBuf& lb, const fdga_level_desc& d_in) {
     memset(&lb, 0, sizeof(lb));
+    fdga_level_desc d = d_in;
+    lb.mbe = d.type == FDGA_LV_NL2_MBE || d.type == FDGA_LV_LOCAL_MBE;
+    if (d.type == FDGA_LV_NL2_MBE) d.type = FDGA_LV_NL2;
+    if (d.type == FDGA_LV_LOCAL_MBE) d.type = FDGA_LV_LOCAL;
     lb.d = d; lb.sw_dirty = true; lb.k1h_dirty = true; lb.mom_valid[0] = lb.mom_valid[1] = lb.mom_valid[2] = 0;
     int NP = ctx->g.NP;
     if (d.type == FDGA_LV_CORE) {
@@ -225,6 +231,7 @@ static void free_level(LevelBuf& lb) {
 static DevLevel dev_level(const LevelBuf& lb) {
     DevLevel d; memset(&d, 0, sizeof(d));
     d.type = lb.d.type == FDGA_LV_NL ? (int)LV_NL2 : lb.d.type;      // evaluated through the kSW forms only (fdga_swave.cuh)
+    d.mbe = lb.mbe ? 1 : 0;
     d.nK1 = lb.d.nK1; d.nK2b = lb.d.nK2[0]; d.nK2f = lb.d.nK2[1]; d.nK3b = lb.d.nK3[0]; d.nK3f = lb.d.nK3[1];
     d.U = mkC(lb.d.U_re, lb.d.U_im);
     for (int ch = 0; ch < 3; ch++) {
@@ -656,6 +663,19 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     if (e != cudaSuccess || ndev == 0) { g_create_error = std::string("no CUDA device available (libfdga has no CPU fallback): ") + cudaGetErrorString(e); return 2; }
     if (device < 0 || device >= ndev) { g_create_error = "invalid device index"; return 2; }
     const bool swave = dims->lev[0].type == FDGA_LV_NL;
+    fdga_dims dims_base = *dims;        // MBE level types -> their base types for the structural checks below
+    bool any_mbe = false;
+    for (int l = 0; l < dims->nlev && l < FDGA_MAX_LEVELS; l++) {
+        int& t = dims_base.lev[l].type;
+        if (t == FDGA_LV_NL2_MBE) { t = FDGA_LV_NL2; any_mbe = true; } else if (t == FDGA_LV_LOCAL_MBE) { t = FDGA_LV_LOCAL; any_mbe = true; }
+        else if (any_mbe && t != FDGA_LV_CORE && l > 0 && !(dims->lev[l - 1].type == FDGA_LV_NL2_MBE || dims->lev[l - 1].type == FDGA_LV_LOCAL_MBE)) { /* asymptotic level below MBE levels: fine */ }
+    }
+    for (int l = 1; l < dims->nlev; l++) {
+        const bool m = dims->lev[l].type == FDGA_LV_NL2_MBE || dims->lev[l].type == FDGA_LV_LOCAL_MBE;
+        const bool mprev = dims->lev[l - 1].type == FDGA_LV_NL2_MBE || dims->lev[l - 1].type == FDGA_LV_LOCAL_MBE;
+        if (m && !mprev) { g_create_error = "dims: MBE levels must form the head of the chain (an MBE vertex below an asymptotic one is not supported)"; return 2; }
+    }
+    const fdga_dims* dims_orig = dims; dims = &dims_base;
     if (dims->nlev < 2 || dims->nlev > FDGA_MAX_LEVELS || (dims->lev[0].type != FDGA_LV_NL2 && !swave) || dims->lev[dims->nlev - 1].type != FDGA_LV_CORE) {
         g_create_error = "dims: need lev[0] = NL2 (or NL for the s-wave solver) and lev[nlev-1] = CORE, 2 <= nlev <= FDGA_MAX_LEVELS"; return 2; }
     for (int l = 1; l < dims->nlev - 1; l++) if (dims->lev[l].type == FDGA_LV_CORE) { g_create_error = "dims: CORE level must be last"; return 2; }
@@ -671,7 +691,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
         g_create_error = "dims: mesh constraints violated (src/nonlocal_2/channel.jl:26-33)"; return 2; }
     if (swave && dims->LG < dims->nq) { g_create_error = "dims: the s-wave solver needs LG >= nq (Green-function mesh at least as fine as the vertex mesh)"; return 2; }
     fdga_ctx* ctx = new fdga_ctx();
-    ctx->capturing = false; ctx->epoch = 0;
+    ctx->capturing = false; ctx->epoch = 0; ctx->mbe = any_mbe;
     ctx->dims = *dims; ctx->device = device; ctx->nlev = dims->nlev; ctx->swave = swave; ctx->swScratch[0] = ctx->swScratch[1] = nullptr;
     ctx->nranks = 1; ctx->rank = 0; ctx->comm = nullptr; memset(&ctx->nccl, 0, sizeof(ctx->nccl));
     ctx->profile = false; ctx->cur_cat = -1; ctx->total_launches = 0; ctx->opt_sde_own_gamma = 0; ctx->opt_generic = 0; ctx->opt_hartree_once = 0; ctx->opt_local = 0; ctx->opt_direct_k1 = 0; ctx->opt_qlane = getenv("FDGA_QLANE") ? atoi(getenv("FDGA_QLANE")) : -1; ctx->defer = false;
@@ -694,7 +714,8 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->ev_cache, cudaEventDisableTiming)); ctx->cache_on_lane = false;
     for (int i = 0; i < 3; i++) CKC(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
-    for (int l = 0; l < ctx->nlev; l++) if (alloc_level(ctx, ctx->lev[l], dims->lev[l])) { g_create_error = ctx->err; delete ctx; return 1; }
+    for (int l = 0; l < ctx->nlev; l++) if (alloc_level(ctx, ctx->lev[l], dims_orig->lev[l])) { g_create_error = ctx->err; delete ctx; return 1; }
+    if (any_mbe) ctx->opt_generic = 1;      // nonlinear evaluator: the piece-wise kernels (right-factor hoisting aside) do not apply
     fdga_level_desc dz = d0;
     if (alloc_level(ctx, ctx->FL, dz) || alloc_level(ctx, ctx->Fbuff, dz)) { g_create_error = ctx->err; delete ctx; return 1; }
     ctx->lenG = (size_t)2 * g.nG * g.LG * g.LG;
@@ -725,7 +746,7 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     for (int i = 0; i < 3; i++) CKC(cudaMalloc(&ctx->ConvTabL[i], ctx->lev[0].len[1] * sizeof(C)));
     {   // merged level (S.F + S.F0) for the K2 left factor
         const fdga_level_desc& a = dims->lev[0]; const fdga_level_desc& b = dims->lev[1];
-        ctx->has_fsum = dims->nlev >= 3 && b.type == FDGA_LV_NL2 && a.nK1 == b.nK1 && a.nK2[0] == b.nK2[0] && a.nK2[1] == b.nK2[1] && a.nK3[0] == b.nK3[0] && a.nK3[1] == b.nK3[1];
+        ctx->has_fsum = !any_mbe && dims->nlev >= 3 && b.type == FDGA_LV_NL2 && a.nK1 == b.nK1 && a.nK2[0] == b.nK2[0] && a.nK2[1] == b.nK2[1] && a.nK3[0] == b.nK3[0] && a.nK3[1] == b.nK3[1];
         ctx->fsum_dirty = true; memset(&ctx->Fsum, 0, sizeof(ctx->Fsum));
         if (ctx->has_fsum && alloc_level(ctx, ctx->Fsum, d0)) { g_create_error = ctx->err; delete ctx; return 1; }
     }
@@ -788,7 +809,10 @@ int fdga_destroy(fdga_ctx* ctx) {
 int fdga_set_option(fdga_ctx* ctx, int opt, int value) {
     ctx->epoch++;
     if (opt == FDGA_OPT_SDE_OWN_GAMMA) { ctx->opt_sde_own_gamma = value != 0; return 0; }
-    if (opt == FDGA_OPT_GENERIC_KERNELS) { ctx->opt_generic = value != 0; return 0; }
+    if (opt == FDGA_OPT_GENERIC_KERNELS) {
+        if (ctx->mbe && !value) FAIL("FDGA_OPT_GENERIC_KERNELS: contexts with MBE vertices only have the generic kernels");
+        ctx->opt_generic = value != 0; return 0;
+    }
     if (opt == FDGA_OPT_FD_HARTREE_ONCE) { ctx->opt_hartree_once = value != 0; return 0; }
     if (opt == FDGA_OPT_LOCAL_SOLVER) {
         if (value && (ctx->g.L != 1 || ctx->g.LG != 1)) FAIL("FDGA_OPT_LOCAL_SOLVER needs nq = LG = 1");
@@ -1222,8 +1246,11 @@ int fdga_build_K3_cache(fdga_ctx* ctx, int mfrg, int first) {
     if (refresh_swave(ctx)) return 1;
     Scope sc(ctx, FDGA_T_CACHE);
     DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0);
+    if (mfrg && ctx->mbe) FAIL("fdga_build_K3_cache: the mfRG cache is not available for MBE vertices");
     if (!mfrg) {
         CachePtrs cp; for (int i = 0; i < 10; i++) cp.c[i] = ctx->cache[i];
+        if (ctx->lev[0].mbe) LAUNCH(FDGA_T_CACHE, build_cache_mbe_kernel, nblk(ctx->lenK3, 64), 64, F0, F, cp, ctx->g, 0LL, (long long)ctx->lenK3);
+        else
         LAUNCH(FDGA_T_CACHE, build_cache_kernel, nblk(ctx->lenK3, 64), 64, F0, F, cp, ctx->g, 0LL, (long long)ctx->lenK3);
         CK(cudaGetLastError());
         return 0;
@@ -1636,6 +1663,17 @@ int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
     }
     if (ctx->opt_local) {       // local solver: omega over the bubble mesh, crossing on the right vertex
         if (launch_right<RK_LK2_LOC>(ctx, ch, F0, FL, ctx->g.nK2b, ctx->g.nPiF)) return 1;
+        if (ctx->mbe) {      // generic per-term form
+            Scope sc(ctx, FDGA_T_L_K2);
+            const int* map = ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3];
+            if (c1 > c0) {
+                if (ch == FDGA_PCH)      LAUNCH(FDGA_T_L_K2, bse_lk2_loc_kernel<CH_P>, (unsigned)(c1 - c0), 128, F, ctx->RtL[ctx->cur_lane], s.d_repvals, sym_dev(s), c0, ctx->g, scale, map);
+                else if (ch == FDGA_TCH) LAUNCH(FDGA_T_L_K2, bse_lk2_loc_kernel<CH_T>, (unsigned)(c1 - c0), 128, F, ctx->RtL[ctx->cur_lane], s.d_repvals, sym_dev(s), c0, ctx->g, scale, map);
+                else                     LAUNCH(FDGA_T_L_K2, bse_lk2_loc_kernel<CH_A>, (unsigned)(c1 - c0), 128, F, ctx->RtL[ctx->cur_lane], s.d_repvals, sym_dev(s), c0, ctx->g, scale, map);
+            }
+            CK(cudaGetLastError());
+            return finish_or_defer(ctx, s, ctx->FL.K[ch][1], PK_LK2, ch);
+        }
         ColJob job = make_job(ctx, 0, 2 * ctx->g.nPiF, ctx->g.nPiF, ctx->g.nK2b, mkC(scale, 0.0));
         if (launch_column<JOB_LK2_LOC>(ctx, ch, F, job, s, ctx->RtL[ctx->cur_lane], FDGA_T_L_K2)) return 1;
         return finish_or_defer(ctx, s, ctx->FL.K[ch][1], PK_LK2, ch);

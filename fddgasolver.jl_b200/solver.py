@@ -19,7 +19,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from .types import (CH_NAME, CHANNELS, NL2_Vertex, NL_Vertex, RefVertex, Vertex, aCh, nB, nF, pCh, tCh, vertex_chain, zeros)
+from .types import (CH_NAME, CHANNELS, MBEVertex, NL2_MBEVertex, NL2_Vertex, NL_Vertex, RefVertex, Vertex, aCh, nB, nF, pCh, tCh, vertex_chain, zeros)
 
 STRATEGY = {"scPA": L.SCPA, "fdPA": L.FDPA, "scPA_new": L.SCPA_NEW, "fdPA_new": L.FDPA_NEW, "fdPA_1loop": L.FDPA_1LOOP}
 _G_NAMES = {"G": L.G, "G0": L.G0, "Gbare": L.GBARE, "Σ": L.SIGMA, "Σ0": L.SIGMA0}
@@ -43,7 +43,9 @@ class NL2_ParquetSolver:
         return (nB(self.nΠB), nF(self.nΠF), self.NP, self.NP)
 
     def __init__(self, nK1, nK2, nK3, L_, Gbare, G0, Σ0, F0, *, T, mode="threads", mΠν_factor=1, device=0,
-                 compute_bubbles=True):
+                 compute_bubbles=True, VT=None):
+        # VT = NL2_MBEVertex: S.F is a multi-boson-exchange vertex (NL2_ParquetSolver(..., F0, NL2_MBEVertex), src/nonlocal_2/
+        # ParquetSolver.jl:86,113); Fbuff and FL stay asymptotic.  Such a solver runs the generic per-term kernels: scPA / fdPA only.
         lib = L.load()
         self._lib = lib
         self.mode = mode          # accepted and ignored: parallelism is the GPU's
@@ -64,7 +66,9 @@ class NL2_ParquetSolver:
         self.G = self.G0.copy(order="F")
         self.Σ = self.Σ0.copy(order="F")
         self.F0 = F0
-        self.F = self._vertex_cls(F0, self.T, nK1, nK2, nK3, self.L)
+        self.F = (VT or self._vertex_cls)(F0, self.T, nK1, nK2, nK3, self.L)
+        if not isinstance(self.F, self._vertex_cls):
+            raise L.FdgaError(f"VT must be a {self._vertex_cls.__name__} type")
         null = RefVertex(self.T, 0.0)
         self.Fbuff = self._vertex_cls(null, self.T, nK1, nK2, nK3, self.L)
         self.FL = self._vertex_cls(null.copy(), self.T, nK1, nK2, nK3, self.L)
@@ -91,6 +95,8 @@ class NL2_ParquetSolver:
                 lv.U_re, lv.U_im = V.U.real, V.U.imag
             else:
                 lv.type = L.LV_NL2 if isinstance(V, NL2_Vertex) else (L.LV_NL if isinstance(V, NL_Vertex) else L.LV_LOCAL)
+                if getattr(V, "mbe", False):
+                    lv.type = {L.LV_NL2: L.LV_NL2_MBE, L.LV_LOCAL: L.LV_LOCAL_MBE}[lv.type]
                 if isinstance(V, (NL2_Vertex, NL_Vertex)) and not isinstance(V, self._vertex_cls):
                     raise L.FdgaError(f"the momentum-dependent levels of the F0 chain must be {self._vertex_cls.__name__}s")
                 if isinstance(V, (NL2_Vertex, NL_Vertex)) and V.L != self.L:
@@ -371,7 +377,7 @@ class ParquetSolver(NL2_ParquetSolver):
 
     local = True
 
-    def __init__(self, nK1, nK2, nK3, Gbare, G0, Σ0, F0, *, T, mode="threads", mΠν_factor=6, device=0, Q=np.complex128):
+    def __init__(self, nK1, nK2, nK3, Gbare, G0, Σ0, F0, *, T, mode="threads", mΠν_factor=6, device=0, Q=np.complex128, VT=None):
         # Q = Float64 of the reference (test/test_siam_scPA.jl:22): the particle-hole symmetric impurity has real i G, i Σ and real
         # vertices.  The device arithmetic is complex128 throughout; with real inputs every imaginary part is an exact zero, and a
         # real-typed solver insists on that whenever arrays come back (the InexactError Julia would raise) -- see real_array().
@@ -381,8 +387,10 @@ class ParquetSolver(NL2_ParquetSolver):
                 if np.iscomplexobj(a) and np.any(np.asarray(a).imag != 0):
                     raise L.FdgaError("ParquetSolver(Q = Float64): inputs must be real")
         col = lambda a: np.asfortranarray(np.asarray(a, dtype=np.complex128).reshape(-1, 1))
+        if VT is MBEVertex:
+            VT = NL2_MBEVertex                       # the local solver lives on the 1 x 1 mesh
         super().__init__(nK1, nK2, nK3, 1, col(Gbare), col(G0), col(Σ0), F0, T=T, mode=mode, mΠν_factor=mΠν_factor,
-                         device=device, compute_bubbles=False)
+                         device=device, compute_bubbles=False, VT=VT)
         self.set_option("local_solver", 1)
         self.set_option("sde_own_gamma", 1)          # src/SDE.jl:102-103, 138-140: F(...; F0 = false, own γ)
         self._call("fdga_bubbles_local", 1)

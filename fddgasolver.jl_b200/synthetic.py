@@ -29,14 +29,14 @@ def parquet_solver_hubbard_parquet_approximation(nG, nK1, nK2, nK3, LG, L, *, T,
     return NL_ParquetSolver(nK1, nK2, nK3, L, Gbare, np.zeros_like(Gbare), np.zeros_like(Gbare), RefVertex(T, U), T=T, mode=mode, device=device)
 
 
-def parquet_solver_siam_parquet_approximation(nG, nK1, nK2, nK3, Q=np.complex128, *, e, Δ, D, T, U, mode="threads", mΠν_factor=6, device=0):
+def parquet_solver_siam_parquet_approximation(nG, nK1, nK2, nK3, Q=np.complex128, *, e, Δ, D, T, U, mode="threads", mΠν_factor=6, device=0, VT=None):
     """Parquet approximation for the SIAM: G0 = Σ0 = 0, F0 = U (src/ParquetSolver.jl:170-200).  Q = np.float64: the reference's
     real-typed solver (only meaningful at e = 0, where i G is real)."""
     Gbare = siam_bare_Green(T, nG, e=e, Δ=Δ, D=D)
     if np.dtype(Q) == np.float64:
         Gbare = Gbare.real.astype(np.complex128) if np.all(Gbare.imag == 0) else Gbare      # a complex i G is refused by the solver
     z = np.zeros_like(Gbare)
-    return ParquetSolver(nK1, nK2, nK3, Gbare, z, z, RefVertex(T, U), T=T, mode=mode, mΠν_factor=mΠν_factor, device=device, Q=Q)
+    return ParquetSolver(nK1, nK2, nK3, Gbare, z, z, RefVertex(T, U), T=T, mode=mode, mΠν_factor=mΠν_factor, device=device, Q=Q, VT=VT)
 
 
 def _decay_b(N):

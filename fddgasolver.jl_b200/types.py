@@ -206,6 +206,17 @@ class NL_Vertex(_VertexBase):
         self.γa = NL_Channel(T, numK1, numK2, numK3, L)
 
 
+class MBEVertex(Vertex):
+    """local multi-boson-exchange vertex (src/boson_exchange.jl:237-266): the arrays of a Vertex; K1 = screened interaction - U,
+    K2 = Hedin-vertex part, K3 = multi-boson part M.  Evaluated on the device as U + K1 + K2 + K2' + K2 K2' / (U + K1) + K3."""
+    mbe = True
+
+
+class NL2_MBEVertex(NL2_Vertex):
+    """nonlocal multi-boson-exchange vertex (src/boson_exchange.jl:738-770)"""
+    mbe = True
+
+
 def vertex_chain(F):
     """[F, F.F0, F.F0.F0, ..., RefVertex]"""
     out = [F]

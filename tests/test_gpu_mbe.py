@@ -1,0 +1,136 @@
+"""GPU parity of the multi-boson-exchange parametrisation (MBEVertex / NL2_MBEVertex, src/boson_exchange.jl; nl_method = -2 of
+script/run_Wu_point.jl) through the C-ABI against the CPU oracle: MBE K3 caches (explicit s-wave averages), every BSE entry point,
+SDE and complete iterations, for the nonlocal solver on a small mesh (nested MBE reference chain) and for the local solver."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+_CACHES = ("cache_Γpx", "cache_F0p", "cache_F0a", "cache_F0t", "cache_Γpp", "cache_Γa", "cache_Γt", "cache_Fp", "cache_Fa", "cache_Ft")
+
+
+def rel(a, b):
+    s = max(np.max(np.abs(a)), np.max(np.abs(b)), 1e-300)
+    return float(np.max(np.abs(a - b)) / s)
+
+
+def compare_vertex(Vg, Vo, what, classes=("K1", "K2", "K3")):
+    for ch in range(3):
+        for cls in classes:
+            a, b = getattr(Vg.channel(ch), cls), getattr(Vo.channel(ch), cls)
+            assert rel(a, b) < TOL, f"{what} ch={ch} {cls}: rel dev {rel(a, b):.3e}"
+
+
+def make_nl2(orc, *, nested, sym=True, seed=1):
+    """NL2 solver with S.F an NL2_MBEVertex.  nested: F0 = NL2_MBEVertex over a local MBEVertex over a RefVertex with a core (the
+    state of an fd calculation); else the parquet approximation F0 = U"""
+    import fddgasolver_jl_b200 as fd
+    import oracle as o
+    T, U, nmax, L, LG = 0.5, 2.0, 2, 2, 4
+    rng = np.random.default_rng(seed)
+    Gb = fd.hubbard_bare_Green(T, 4 * nmax, LG, μ=0.3, t1=1.0, t2=-0.2)
+    if nested:
+        core = fd.RefVertex(T, U, (2, 2), *[0.2 * (rng.random((3, 4, 4)) + 1j * rng.random((3, 4, 4))) for _ in range(4)])
+        loc = fd.randomize_vertex(fd.MBEVertex(core, T, 12, (4, 4), (3, 3)), seed + 1, 0.3)
+        F0 = fd.randomize_vertex(fd.NL2_MBEVertex(loc, T, 4 * nmax, (nmax, nmax), (nmax, nmax), L), seed + 2, 0.2)
+        G0 = fd.hubbard_bare_Green(T, 4 * nmax, LG, μ=0.1, t1=1.0, t2=-0.2)
+    else:
+        F0, G0 = fd.RefVertex(T, U), np.zeros_like(Gb)
+    S = fd.NL2_ParquetSolver(4 * nmax, (nmax, nmax), (nmax, nmax), L, Gb, G0, np.zeros_like(Gb), F0, T=T, VT=fd.NL2_MBEVertex)
+    fd.randomize_vertex(S.F, seed + 3, 0.3)
+    S.push("F")
+    R = orc.OracleSolver(S.nK1, S.nK2, S.nK3, S.L, S.Gbare, S.G0, S.Σ0, S.F0, T=S.T, VT=o.NL2_MBEVertex)
+    assert type(R.F0).__name__ == ("ONL2_MBEVertex" if nested else "ORefVertex")
+    if sym:
+        S.init_sym_grp(); R.init_sym_grp()
+    R.F.set(S.F)
+    return S, R
+
+
+@pytest.mark.parametrize("nested,sym", [(True, True), (True, False), (False, True)])
+def test_mbe_caches_and_bse_kernels_stepwise(orc, nested, sym):
+    import fddgasolver_jl_b200 as fd
+    S, R = make_nl2(orc, nested=nested, sym=sym)
+    order = (fd.pCh, fd.aCh, fd.tCh)
+    fd.build_K3_cache(S); orc.build_K3_cache(R)
+    S.pull("cache")
+    for n in _CACHES:
+        assert rel(getattr(S, n), getattr(R, n)) < TOL, n
+    for ch in order:
+        fd.BSE_L_K2(S, ch); orc.BSE_L_K2(R, ch)
+    for ch in order:
+        fd.BSE_L_K3(S, ch); orc.BSE_L_K3(R, ch)
+    S.pull("FL")
+    compare_vertex(S.FL, R.FL, "FL", ("K2", "K3"))
+    for ch in order:
+        fd.BSE_K1(S, ch); orc.BSE_K1(R, ch)
+    for ch in order:
+        fd.BSE_K2(S, ch); orc.BSE_K2(R, ch)
+    for ch in order:
+        fd.BSE_K3(S, ch); orc.BSE_K3(R, ch)
+    S.pull("Fbuff")
+    compare_vertex(S.Fbuff, R.Fbuff, "Fbuff")
+    S.close()
+
+
+@pytest.mark.parametrize("strategy,nested", [("fdPA", True), ("scPA", True), ("scPA", False)])
+def test_mbe_iterate_solver_and_sde(orc, strategy, nested):
+    import fddgasolver_jl_b200 as fd
+    S, R = make_nl2(orc, nested=nested)
+    for it in range(2):
+        fd.iterate_solver(S, strategy); orc.iterate_solver(R, strategy)
+        S.pull("F", "Σ", "G")
+        compare_vertex(S.F, R.F, f"F it{it}")
+        assert rel(S.Σ, R.Σ) < TOL and rel(S.G, R.G) < TOL
+    S.close()
+
+
+def test_mbe_contexts_have_no_fast_or_mfrg_paths(orc):
+    import fddgasolver_jl_b200 as fd
+    S, _ = make_nl2(orc, nested=False)
+    with pytest.raises(fd.FdgaError, match="generic kernels"):
+        S.set_option("generic_kernels", 0)
+    with pytest.raises(fd.FdgaError, match="not available for MBE"):
+        fd.build_K3_cache_mfRG(S, True)
+    S.close()
+    T = 0.5
+    Gb = fd.hubbard_bare_Green(T, 8, 4, μ=0.1, t1=1.0)
+    bad = fd.NL2_Vertex(fd.NL2_MBEVertex(fd.RefVertex(T, 1.0), T, 8, (2, 2), (2, 2), 2), T, 8, (2, 2), (2, 2), 2)      # MBE below asymptotic
+    with pytest.raises(fd.FdgaError, match="head of the chain"):
+        fd.NL2_ParquetSolver(8, (2, 2), (2, 2), 2, Gb, Gb, np.zeros_like(Gb), bad, T=T)
+
+
+def test_local_mbe_solver_matches_oracle_and_the_asymptotic_solution(orc):
+    """ParquetSolver(...; VT = MBEVertex) on the device: two iterations against the oracle at 1e-10, then converged scPA solutions in
+    the MBE and in the asymptotic parametrisation give the same self-energy and K1 (test/test_boson_exchange_local.jl:87-128 at
+    smaller boxes, tolerances scaled accordingly)"""
+    import fddgasolver_jl_b200 as fd
+    import oracle as o
+    from helpers import anderson
+    T, U, D, e, Δ, nmax = 0.1, 1.0, 10.0, 0.5, np.pi / 5, 6
+    mk = lambda VT: fd.parquet_solver_siam_parquet_approximation(6 * nmax, 4 * nmax, (nmax, nmax), (nmax, nmax), e=e, Δ=Δ, D=D, T=T, U=U, VT=VT)
+    S = mk(fd.MBEVertex); S.init_sym_grp()
+    Gb = orc.siam_bare_Green(T, 6 * nmax, e=e, Δ=Δ, D=D)
+    R = orc.OracleLocalSolver(4 * nmax, (nmax, nmax), (nmax, nmax), Gb, np.zeros_like(Gb), np.zeros_like(Gb), o.RefVertex(T, U), T=T, VT=o.NL2_MBEVertex)
+    R.init_sym_grp()
+    for strategy in ("scPA", "fdPA"):
+        fd.iterate_solver(S, strategy); orc.iterate_solver_local(R, strategy, True)
+        S.pull("F", "Σ", "FL")
+        assert rel(S.F.flatten(), R.F.flatten()) < TOL and rel(S.Σ, R.Σ) < TOL and rel(S.FL.flatten(), R.FL.flatten()) < TOL
+
+    def converge(X):
+        nF = X.length_F()
+        x0 = np.concatenate([X.F.flatten() * 0, X.Σ.ravel(order="F") * 0])
+        fp = lambda x: fd.fixed_point(np.empty_like(x), x, X, "scPA", True)
+        x, it, err = anderson(fp, x0, tol=1e-8)
+        assert err < 1e-8
+        X.unflatten_F(x[:nF]); X.pull("F")
+        return x[nF:]
+    Σ1 = converge(S)
+    A = mk(None); A.init_sym_grp()
+    Σ2 = converge(A)
+    assert np.max(np.abs(Σ1 - Σ2)) < 5e-5
+    for n in ("γa", "γp", "γt"):
+        assert np.max(np.abs(getattr(S.F, n).K1 - getattr(A.F, n).K1)) < 5e-5
+    S.close(); A.close()
