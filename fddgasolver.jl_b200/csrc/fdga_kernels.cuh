@@ -215,7 +215,7 @@ __global__ void pi_swave_kernel(const C* __restrict__ Pi, C* __restrict__ Pisw, 
 enum { RK_FD = 0, RK_MF_K1 = 1, RK_MF_K2 = 2, RK_LK2 = 3, RK_LK2_LOC = 4, RK_1L = 5 };
 
 // Only the slabs (W, P) that hold class representatives of this rank are filled: `slabs` lists (iWo, iP) pairs.
-template <int CH, int KIND>
+template <int CH, int KIND, bool MBE = false>
 __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ DevChain FL,
                                     const C* __restrict__ Pi0T, const C* __restrict__ PiT, C* __restrict__ Rt,
                                     Grid g, int No, int Ninner, const int4* __restrict__ slabs, int nslabs, const int* __restrict__ pimap) {
@@ -241,23 +241,23 @@ __global__ void right_factor_kernel(const __grid_constant__ DevChain F0, const _
     }
     C r;
     if (KIND == RK_FD) {
-        C F0r = eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
-        C FLr = eval_vertex<false>(FL, 0, CH, SP, a, FL_ALL);
+        C F0r = eval_vertex<false, MBE>(F0, 0, CH, SP, a, FL_ALL);
+        C FLr = eval_vertex<false, MBE>(FL, 0, CH, SP, a, FL_ALL);
         C p = PiT[pidx], p0 = Pi0T[pidx];
         r = (p - p0) * F0r + p * FLr;
     } else if (KIND == RK_1L) {
-        r = (PiT[pidx] - Pi0T[pidx]) * eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
+        r = (PiT[pidx] - Pi0T[pidx]) * eval_vertex<false, MBE>(F0, 0, CH, SP, a, FL_ALL);
     } else if (KIND == RK_LK2 || KIND == RK_LK2_LOC) {
-        r = Pi0T[pidx] * eval_vertex<false>(F0, 0, CH, SP, a, FL_ALL);
+        r = Pi0T[pidx] * eval_vertex<false, MBE>(F0, 0, CH, SP, a, FL_ALL);
     } else {
-        r = Pi0T[pidx] * eval_vertex<false>(FL, 0, CH, SP, a, FL_ALL);
+        r = Pi0T[pidx] * eval_vertex<false, MBE>(FL, 0, CH, SP, a, FL_ALL);
     }
     (void)nBo;
     Rt[slab_at(iw, iq, g.NP) + (size_t)nw * g.NP * sl] = r;      // compact: slab number = position in the list
 }
 
 // ---- BSE_K1!: src/nonlocal_2/BSEa/BSEa_K1.jl:19-52.  One CTA per class representative (W, P) ------
-template <int CH>
+template <int CH, bool MBE = false>
 __global__ void bse_k1_kernel(const __grid_constant__ DevChain Fleft, const C* __restrict__ Rt, C* __restrict__ repvals,
                               SymDev sg, long long c0, Grid g, double scale, const int* __restrict__ map) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
@@ -271,7 +271,7 @@ __global__ void bse_k1_kernel(const __grid_constant__ DevChain Fleft, const C* _
     for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
         int iq = t % g.NP, iw = t / g.NP;
         Arg a; a.W = W; a.v = FDGA_INF; a.w = iw - g.nPiF; a.Px = Px; a.Py = Py; a.kx = 0; a.ky = 0; a.qx = iq % g.L; a.qy = iq / g.L;
-        C Fl = eval_vertex<false>(Fleft, 0, CH, SP, a, FL_ALL);
+        C Fl = eval_vertex<false, MBE>(Fleft, 0, CH, SP, a, FL_ALL);
         acc += Fl * slab[t];
     }
     acc = block_reduce(acc);
@@ -279,7 +279,7 @@ __global__ void bse_k1_kernel(const __grid_constant__ DevChain Fleft, const C* _
 }
 
 // ---- BSE_L_K2!: src/nonlocal_2/BSEa/BSEa_K2.jl:17-43.  One CTA per representative (W, v, P, k) -----
-template <int CH>
+template <int CH, bool MBE = false>
 __global__ void bse_lk2_kernel(const __grid_constant__ DevChain F, const C* __restrict__ Rt, C* __restrict__ repvals,
                                SymDev sg, long long c0, Grid g, double scale, const int* __restrict__ map) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
@@ -298,7 +298,7 @@ __global__ void bse_lk2_kernel(const __grid_constant__ DevChain F, const C* __re
         Arg a; a.W = W; a.v = v; a.Px = Px; a.Py = Py; a.kx = kx; a.ky = ky;
         a.w = (CH == CH_P) ? W - w - 1 : w;
         a.qx = (CH == CH_P) ? Px - qx : qx; a.qy = (CH == CH_P) ? Py - qy : qy;
-        C Gl = eval_vertex<false>(F, 0, CH, SP, a, FLG);
+        C Gl = eval_vertex<false, MBE>(F, 0, CH, SP, a, FLG);
         acc += Gl * slab[t];
     }
     acc = block_reduce(acc);
@@ -308,7 +308,7 @@ __global__ void bse_lk2_kernel(const __grid_constant__ DevChain F, const C* __re
 // ---- BSE_K2!: src/nonlocal_2/BSEa/BSEa_K2.jl:72-125.  One CTA per representative (W, v, P, k) ------
 //  fd   : [F(W,v,w;P,k,q) - F(W,inf,w;P,k,q)] * Rt                 (Fleft = S.F)
 //  mfRG : [F0(W,v,w~;P,k,q~) - F0(W,inf,w~;P,k,q~)] * Rt           (Fleft = S.F0)
-template <int CH, bool MF>
+template <int CH, bool MF, bool MBE = false>
 __global__ void bse_k2_kernel(const __grid_constant__ DevChain Fleft, const C* __restrict__ Rt, C* __restrict__ repvals,
                               SymDev sg, long long c0, Grid g, double scale, const int* __restrict__ map) {
     constexpr int SP = (CH == CH_T) ? SP_D : SP_P;
@@ -328,9 +328,9 @@ __global__ void bse_k2_kernel(const __grid_constant__ DevChain Fleft, const C* _
             a.w = (CH == CH_P) ? W - w - 1 : w;
             a.qx = (CH == CH_P) ? Px - qx : qx; a.qy = (CH == CH_P) ? Py - qy : qy;
         } else { a.w = w; a.qx = qx; a.qy = qy; }
-        C f1 = eval_vertex<false>(Fleft, 0, CH, SP, a, FL_ALL);
+        C f1 = eval_vertex<false, MBE>(Fleft, 0, CH, SP, a, FL_ALL);
         a.v = FDGA_INF;
-        C f2 = eval_vertex<false>(Fleft, 0, CH, SP, a, FL_ALL);
+        C f2 = eval_vertex<false, MBE>(Fleft, 0, CH, SP, a, FL_ALL);
         acc += (f1 - f2) * slab[t];
     }
     acc = block_reduce(acc);
@@ -507,17 +507,17 @@ __global__ void build_cache_mbe_kernel(const __grid_constant__ DevChain F0, cons
     // class K3 of a chain at (W, v, w, P): independent of the fermionic momenta
     auto k3 = [&](const DevChain& V, int l, int r, int v, int w) { Arg x = a; x.v = v; x.w = w; return mbe_classes(V, l, r, x).K3; };
     // (W, w, v', P) block: vertices multiplied by bubbles to the left
-    out.c[0][i] = eval_vertex<true>(F, 0, CH_P, SP_X, a, NP_) - eval_vertex<true>(F, 1, CH_P, SP_X, a, NP_);
-    out.c[1][i] = eval_vertex<true>(F0, 0, CH_P, SP_X, a, NP_) + U - k3(F0, 0, CH_P, a1, W - b1 - 1);
-    const C f0a = eval_vertex<true>(F0, 0, CH_A, SP_P, a, NA_) - U + k3(F0, 0, CH_A, a1, b1);
-    const C f0t = eval_vertex<true>(F0, 0, CH_T, SP_P, a, NT_) - U + k3(F0, 0, CH_T, a1, b1);
+    out.c[0][i] = eval_vertex<true, true>(F, 0, CH_P, SP_X, a, NP_) - eval_vertex<true, true>(F, 1, CH_P, SP_X, a, NP_);
+    out.c[1][i] = eval_vertex<true, true>(F0, 0, CH_P, SP_X, a, NP_) + U - k3(F0, 0, CH_P, a1, W - b1 - 1);
+    const C f0a = eval_vertex<true, true>(F0, 0, CH_A, SP_P, a, NA_) - U + k3(F0, 0, CH_A, a1, b1);
+    const C f0t = eval_vertex<true, true>(F0, 0, CH_T, SP_P, a, NT_) - U + k3(F0, 0, CH_T, a1, b1);
     out.c[2][i] = f0a;
     out.c[3][i] = 2.0 * f0t - f0a;
     // (W, v, w, P) block: vertices multiplied by bubbles from the right
-    const C Fp = eval_vertex<true>(F, 0, CH_P, SP_P, a, NP_), Fa = eval_vertex<true>(F, 0, CH_A, SP_P, a, NA_), Ft = eval_vertex<true>(F, 0, CH_T, SP_P, a, NT_);
-    const C gpp = Fp - eval_vertex<true>(F, 1, CH_P, SP_P, a, NP_);
-    const C ga = Fa - eval_vertex<true>(F, 1, CH_A, SP_P, a, NA_);
-    const C gt = Ft - eval_vertex<true>(F, 1, CH_T, SP_P, a, NT_);
+    const C Fp = eval_vertex<true, true>(F, 0, CH_P, SP_P, a, NP_), Fa = eval_vertex<true, true>(F, 0, CH_A, SP_P, a, NA_), Ft = eval_vertex<true, true>(F, 0, CH_T, SP_P, a, NT_);
+    const C gpp = Fp - eval_vertex<true, true>(F, 1, CH_P, SP_P, a, NP_);
+    const C ga = Fa - eval_vertex<true, true>(F, 1, CH_A, SP_P, a, NA_);
+    const C gt = Ft - eval_vertex<true, true>(F, 1, CH_T, SP_P, a, NT_);
     const C fp = Fp - U + k3(F, 0, CH_P, a1, b1), fa = Fa - U + k3(F, 0, CH_A, a1, b1), ft = Ft - U + k3(F, 0, CH_T, a1, b1);
     out.c[4][i] = gpp;
     out.c[5][i] = ga;
@@ -546,7 +546,7 @@ __global__ void bse_lk2_loc_kernel(const __grid_constant__ DevChain F, const C* 
     for (int t = threadIdx.x; t < nw * g.NP; t += blockDim.x) {
         int iq = t % g.NP, iw = t / g.NP;
         Arg a; a.W = W; a.v = v; a.w = iw - g.nPiF; a.Px = Px; a.Py = Py; a.kx = kx; a.ky = ky; a.qx = iq % g.L; a.qy = iq / g.L;
-        acc += eval_vertex<false>(F, 0, CH, SP, a, FLG) * slab[t];
+        acc += eval_vertex<false, true>(F, 0, CH, SP, a, FLG) * slab[t];
     }
     acc = block_reduce(acc);
     if (threadIdx.x == 0) repvals[cls] = acc * scale;
@@ -577,7 +577,7 @@ __global__ void cache_mfrg_kernel(const __grid_constant__ DevChain F0, const __g
 }
 
 // ---- SDE_channel_L_pp!/ph!: src/nonlocal_2/SDE.jl:16-33, 54-73, 96-111, 130-145.  CTA per rep --------
-template <bool PP>
+template <bool PP, bool MBE = false>
 __global__ void sde_L_kernel(const __grid_constant__ DevChain V, int level, const C* __restrict__ PiT,
                              C* __restrict__ repvals, SymDev sg, long long c0, Grid g, C U, double scale, int own_only, const int* __restrict__ map) {
     long long cls = c0 + blockIdx.x;
@@ -597,14 +597,14 @@ __global__ void sde_L_kernel(const __grid_constant__ DevChain V, int level, cons
         if (PP) {
             a.v = W - w - 1; a.w = v; a.kx = Px - qx; a.ky = Py - qy; a.qx = kx; a.qy = ky;
             if (is_core) d = core_eval(V.lev[level], CH_P, SP_P, a.W, a.v, a.w) - U;
-            else if (own_only) d = eval_vertex<false>(V, level, CH_P, SP_P, a, FL_GP);
-            else d = eval_vertex<false>(V, level, CH_P, SP_P, a, FL_F0 | FL_GP) - eval_vertex<false>(V, level + 1, CH_P, SP_P, a, FL_F0 | FL_GP);
+            else if (own_only) d = eval_vertex<false, MBE>(V, level, CH_P, SP_P, a, FL_GP);
+            else d = eval_vertex<false, MBE>(V, level, CH_P, SP_P, a, FL_F0 | FL_GP) - eval_vertex<false, MBE>(V, level + 1, CH_P, SP_P, a, FL_F0 | FL_GP);
         } else {
             a.v = v; a.w = w; a.kx = kx; a.ky = ky; a.qx = qx; a.qy = qy;
             if (is_core) d = core_eval(V.lev[level], CH_A, SP_P, W, v, w) + core_eval(V.lev[level], CH_T, SP_P, W, v, w) - U - U;
-            else if (own_only) d = eval_vertex<false>(V, level, CH_A, SP_P, a, FL_GA) + eval_vertex<false>(V, level, CH_T, SP_P, a, FL_GT);
-            else d = eval_vertex<false>(V, level, CH_A, SP_P, a, FL_F0 | FL_GA) + eval_vertex<false>(V, level, CH_T, SP_P, a, FL_F0 | FL_GT)
-                   - eval_vertex<false>(V, level + 1, CH_A, SP_P, a, FL_F0 | FL_GA) - eval_vertex<false>(V, level + 1, CH_T, SP_P, a, FL_F0 | FL_GT);
+            else if (own_only) d = eval_vertex<false, MBE>(V, level, CH_A, SP_P, a, FL_GA) + eval_vertex<false, MBE>(V, level, CH_T, SP_P, a, FL_GT);
+            else d = eval_vertex<false, MBE>(V, level, CH_A, SP_P, a, FL_F0 | FL_GA) + eval_vertex<false, MBE>(V, level, CH_T, SP_P, a, FL_F0 | FL_GT)
+                   - eval_vertex<false, MBE>(V, level + 1, CH_A, SP_P, a, FL_F0 | FL_GA) - eval_vertex<false, MBE>(V, level + 1, CH_T, SP_P, a, FL_F0 | FL_GT);
         }
         acc += U * slab[t] * d;
     }

@@ -1291,9 +1291,9 @@ static int launch_right(fdga_ctx* ctx, int ch, const DevChain& F0, const DevChai
     long long n = (long long)(2 * Ninner) * ctx->g.NP * nsl;
     if (n == 0) return 0;
     const int* pimap = ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1];      // the bubbles live on the bubble-mesh slab list
-    if (ch == FDGA_PCH)      LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_P, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl, pimap);
-    else if (ch == FDGA_TCH) LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_T, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl, pimap);
-    else                     LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_A, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl, pimap);
+    if (ch == FDGA_PCH)      { if (ctx->mbe) LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_P, KIND, true>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl, pimap); else LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_P, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl, pimap); }
+    else if (ch == FDGA_TCH) { if (ctx->mbe) LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_T, KIND, true>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl, pimap); else LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_T, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl, pimap); }
+    else                     { if (ctx->mbe) LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_A, KIND, true>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl, pimap); else LAUNCH(FDGA_T_RIGHT, (right_factor_kernel<CH_A, KIND>), nblk(n, 128), 128, F0, FL, p0, p1, Rdst, ctx->g, No, Ninner, sl, nsl, pimap); }
     CK(cudaGetLastError());
     return 0;
 }
@@ -1592,9 +1592,9 @@ static int bse_K1_impl(fdga_ctx* ctx, int ch, int mfrg, int rk_fd) {
     {
         Scope sc(ctx, FDGA_T_K1);
         if (c1 > c0) {
-            if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_P>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1]);
-            else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_T>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1]);
-            else                     LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_A>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1]);
+            if (ch == FDGA_PCH)      { if (ctx->mbe) LAUNCH(FDGA_T_K1, (bse_k1_kernel<CH_P, true>), (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1]); else LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_P>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1]); }
+            else if (ch == FDGA_TCH) { if (ctx->mbe) LAUNCH(FDGA_T_K1, (bse_k1_kernel<CH_T, true>), (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1]); else LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_T>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1]); }
+            else                     { if (ctx->mbe) LAUNCH(FDGA_T_K1, (bse_k1_kernel<CH_A, true>), (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1]); else LAUNCH(FDGA_T_K1, bse_k1_kernel<CH_A>, (unsigned)(c1 - c0), 256, left, ctx->Rt3[ch], s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 0 : 1]); }
         }
         CK(cudaGetLastError());
     }
@@ -1685,9 +1685,9 @@ int fdga_bse_L_K2(fdga_ctx* ctx, int ch) {
     } else {
         Scope sc(ctx, FDGA_T_L_K2);
         if (c1 > c0) {
-            if (ch == FDGA_PCH)      LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_P>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
-            else if (ch == FDGA_TCH) LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_T>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
-            else                     LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_A>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
+            if (ch == FDGA_PCH)      { if (ctx->mbe) LAUNCH(FDGA_T_L_K2, (bse_lk2_kernel<CH_P, true>), (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); else LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_P>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); }
+            else if (ch == FDGA_TCH) { if (ctx->mbe) LAUNCH(FDGA_T_L_K2, (bse_lk2_kernel<CH_T, true>), (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); else LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_T>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); }
+            else                     { if (ctx->mbe) LAUNCH(FDGA_T_L_K2, (bse_lk2_kernel<CH_A, true>), (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); else LAUNCH(FDGA_T_L_K2, bse_lk2_kernel<CH_A>, (unsigned)(c1 - c0), 128, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); }
         }
         CK(cudaGetLastError());
     }
@@ -1746,13 +1746,13 @@ static int bse_K2_impl(fdga_ctx* ctx, int ch, int mfrg, int rk_fd) {
         unsigned nb = (unsigned)(c1 - c0);
         if (c1 > c0) {
             if (mfrg) {
-                if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_P, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
-                else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_T, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
-                else                     LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_A, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
+                if (ch == FDGA_PCH)      { if (ctx->mbe) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_P, true, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); else LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_P, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); }
+                else if (ch == FDGA_TCH) { if (ctx->mbe) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_T, true, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); else LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_T, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); }
+                else                     { if (ctx->mbe) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_A, true, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); else LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_A, true>), nb, 256, F0, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); }
             } else {
-                if (ch == FDGA_PCH)      LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_P, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
-                else if (ch == FDGA_TCH) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_T, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
-                else                     LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_A, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]);
+                if (ch == FDGA_PCH)      { if (ctx->mbe) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_P, false, true>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); else LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_P, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); }
+                else if (ch == FDGA_TCH) { if (ctx->mbe) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_T, false, true>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); else LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_T, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); }
+                else                     { if (ctx->mbe) LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_A, false, true>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); else LAUNCH(FDGA_T_K2, (bse_k2_kernel<CH_A, false>), nb, 256, F, ctx->Rt, s.d_repvals, sym_dev(s), c0, ctx->g, scale, ctx->d_slabmap[ch == FDGA_PCH ? 2 : 3]); }
             }
         }
         CK(cudaGetLastError());
@@ -1888,8 +1888,8 @@ static int sde_chain(fdga_ctx* ctx, C* acc, double sgn, int gwhich, bool referen
             {
                 Scope sc(ctx, FDGA_T_SDE_L);
                 if (c1 > c0) {
-                    if (pp) LAUNCH(FDGA_T_SDE_L, sde_L_kernel<true>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma, ctx->d_slabmap[0]);
-                    else    LAUNCH(FDGA_T_SDE_L, sde_L_kernel<false>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma, ctx->d_slabmap[1]);
+                    if (pp) { if (ctx->mbe) LAUNCH(FDGA_T_SDE_L, (sde_L_kernel<true, true>), (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma, ctx->d_slabmap[0]); else LAUNCH(FDGA_T_SDE_L, sde_L_kernel<true>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma, ctx->d_slabmap[0]); }
+                    else    { if (ctx->mbe) LAUNCH(FDGA_T_SDE_L, (sde_L_kernel<false, true>), (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma, ctx->d_slabmap[1]); else LAUNCH(FDGA_T_SDE_L, sde_L_kernel<false>, (unsigned)(c1 - c0), 256, V, level, PiT, s.d_repvals, sym_dev(s), c0, g, U, scale, ctx->opt_sde_own_gamma, ctx->d_slabmap[1]); }
                 }
                 CK(cudaGetLastError());
             }
