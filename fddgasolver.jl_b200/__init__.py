@@ -17,5 +17,6 @@ from .solver import (NL2_ParquetSolver, NL_ParquetSolver, ParquetSolver, init_sy
 from . import h5min, io, synthetic, types  # noqa: F401,E402
 from .io import load_triqs_data  # noqa: F401,E402
 from .flow import bare_Green_Ω_flow  # noqa: F401,E402
+from .mbe import asymptotic_to_mbe, mbe_to_asymptotic  # noqa: F401,E402
 from .synthetic import (parquet_solver_hubbard_parquet_approximation_NL2, parquet_solver_hubbard_parquet_approximation, parquet_solver_siam_parquet_approximation, synthetic_local_vertex,  # noqa: F401
                         wu_point_solver, wu_point_inputs, randomize_vertex)

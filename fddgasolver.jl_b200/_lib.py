@@ -37,7 +37,7 @@ EXPORTS = [
     "fdga_set_F_from_Fbuff", "fdga_sde", "fdga_sde_channel_L", "fdga_iterate_solver",
     "fdga_mfrg_matvec", "fdga_mfrg_matvec_strategy", "fdga_mfrg_matvec_from_root", "fdga_mfrg_dqgmres", "fdga_symmetrize_solver", "fdga_fixed_point_preconditioned", "fdga_mix_bubbles", "fdga_update_reference", "fdga_interpolate_vertex", "fdga_interpolate_green",
     "fdga_measure_fp64_peak", "fdga_profile_enable", "fdga_profile_reset", "fdga_kernel_time_ms",
-    "fdga_total_launches", "fdga_stream", "fdga_graph_begin", "fdga_graph_end", "fdga_graph_launch", "fdga_graph_destroy",
+    "fdga_total_launches", "fdga_stream", "fdga_eval_vertex", "fdga_graph_begin", "fdga_graph_end", "fdga_graph_launch", "fdga_graph_destroy",
 ]
 
 
@@ -128,6 +128,7 @@ def load():
     lib.fdga_profile_enable.argtypes = [vp, i32]
     lib.fdga_profile_reset.argtypes = [vp]
     lib.fdga_kernel_time_ms.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(i64)]
+    lib.fdga_eval_vertex.argtypes = [vp, i32, i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.fdga_graph_begin.argtypes = [vp]
     lib.fdga_graph_end.argtypes = [vp, C.POINTER(C.c_int)]
     lib.fdga_graph_launch.argtypes = [vp, i32]

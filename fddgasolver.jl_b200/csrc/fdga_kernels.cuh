@@ -496,35 +496,79 @@ __global__ void build_cache_kernel(const __grid_constant__ DevChain F0, const __
 // ---- build_K3_cache! for MBE vertices: src/boson_exchange.jl:947-1017 (NL2_MBEVertex), :599-668 (MBEVertex = the same on a 1 x 1
 // mesh).  cache_F0* / cache_F*: channel-U-irreducible vertex T_r = (I_r - U) + M_r; cache_G*: F - F.F0.  The kSW evaluations of a
 // nonlinear vertex are explicit N_P^2 averages (eval_p_mbe<true>), as in the reference: a small-mesh path. ----
+// One CTA per K3 grid point: the threads share the (k, q) pairs of the s-wave averages, 11 partial sums are block-reduced.
 __global__ void build_cache_mbe_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ DevChain F, CachePtrs out,
                                        Grid g, long long i0, long long i1) {
-    long long i = i0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long i = i0 + blockIdx.x;
     if (i >= i1) return;
     int W, a1, b1, iP; decode_k3(g, i, W, a1, b1, iP);
     Arg a; a.W = W; a.v = a1; a.w = b1; a.Px = iP % g.L; a.Py = iP / g.L; a.kx = a.ky = a.qx = a.qy = 0;
     const C U = F.lev[F.nlev - 1].U;
     constexpr unsigned NP_ = FL_F0 | FL_GT | FL_GA, NA_ = FL_F0 | FL_GP | FL_GT, NT_ = FL_F0 | FL_GP | FL_GA;      // gamma_r = false
+    // the reference chain is momentum independent (a RefVertex, or local levels only): one evaluation instead of N_P^2
+    bool f0_flat = true;
+    for (int l = 0; l < F0.nlev; ++l) f0_flat = f0_flat && F0.lev[l].type != LV_NL2;
+    C s[11];
+#pragma unroll
+    for (int j = 0; j < 11; ++j) s[j] = zeroC();
+    const int npair = g.NP * g.NP;
+    for (int t = threadIdx.x; t < npair; t += blockDim.x) {
+        Arg x = a; const int ik = t % g.NP, iq = t / g.NP;
+        x.kx = ik % g.L; x.ky = ik / g.L; x.qx = iq % g.L; x.qy = iq / g.L;
+        s[0] += eval_vertex<false, true>(F, 0, CH_P, SP_X, x, NP_) - eval_vertex<false, true>(F, 1, CH_P, SP_X, x, NP_);
+        if (!f0_flat) {
+            s[1] += eval_vertex<false, true>(F0, 0, CH_P, SP_X, x, NP_);
+            s[2] += eval_vertex<false, true>(F0, 0, CH_A, SP_P, x, NA_);
+            s[3] += eval_vertex<false, true>(F0, 0, CH_T, SP_P, x, NT_);
+        }
+        s[4] += eval_vertex<false, true>(F, 0, CH_P, SP_P, x, NP_);
+        s[5] += eval_vertex<false, true>(F, 0, CH_A, SP_P, x, NA_);
+        s[6] += eval_vertex<false, true>(F, 0, CH_T, SP_P, x, NT_);
+        s[7] += eval_vertex<false, true>(F, 1, CH_P, SP_P, x, NP_);
+        s[8] += eval_vertex<false, true>(F, 1, CH_A, SP_P, x, NA_);
+        s[9] += eval_vertex<false, true>(F, 1, CH_T, SP_P, x, NT_);
+    }
+    const double inv = 1.0 / (double)npair;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) s[j] = block_reduce(s[j]) * inv;
+    if (threadIdx.x != 0) return;
+    if (f0_flat) {
+        s[1] = eval_vertex<false, true>(F0, 0, CH_P, SP_X, a, NP_);
+        s[2] = eval_vertex<false, true>(F0, 0, CH_A, SP_P, a, NA_);
+        s[3] = eval_vertex<false, true>(F0, 0, CH_T, SP_P, a, NT_);
+    }
     // class K3 of a chain at (W, v, w, P): independent of the fermionic momenta
     auto k3 = [&](const DevChain& V, int l, int r, int v, int w) { Arg x = a; x.v = v; x.w = w; return mbe_classes(V, l, r, x).K3; };
     // (W, w, v', P) block: vertices multiplied by bubbles to the left
-    out.c[0][i] = eval_vertex<true, true>(F, 0, CH_P, SP_X, a, NP_) - eval_vertex<true, true>(F, 1, CH_P, SP_X, a, NP_);
-    out.c[1][i] = eval_vertex<true, true>(F0, 0, CH_P, SP_X, a, NP_) + U - k3(F0, 0, CH_P, a1, W - b1 - 1);
-    const C f0a = eval_vertex<true, true>(F0, 0, CH_A, SP_P, a, NA_) - U + k3(F0, 0, CH_A, a1, b1);
-    const C f0t = eval_vertex<true, true>(F0, 0, CH_T, SP_P, a, NT_) - U + k3(F0, 0, CH_T, a1, b1);
+    out.c[0][i] = s[0];
+    out.c[1][i] = s[1] + U - k3(F0, 0, CH_P, a1, W - b1 - 1);
+    const C f0a = s[2] - U + k3(F0, 0, CH_A, a1, b1);
+    const C f0t = s[3] - U + k3(F0, 0, CH_T, a1, b1);
     out.c[2][i] = f0a;
     out.c[3][i] = 2.0 * f0t - f0a;
     // (W, v, w, P) block: vertices multiplied by bubbles from the right
-    const C Fp = eval_vertex<true, true>(F, 0, CH_P, SP_P, a, NP_), Fa = eval_vertex<true, true>(F, 0, CH_A, SP_P, a, NA_), Ft = eval_vertex<true, true>(F, 0, CH_T, SP_P, a, NT_);
-    const C gpp = Fp - eval_vertex<true, true>(F, 1, CH_P, SP_P, a, NP_);
-    const C ga = Fa - eval_vertex<true, true>(F, 1, CH_A, SP_P, a, NA_);
-    const C gt = Ft - eval_vertex<true, true>(F, 1, CH_T, SP_P, a, NT_);
-    const C fp = Fp - U + k3(F, 0, CH_P, a1, b1), fa = Fa - U + k3(F, 0, CH_A, a1, b1), ft = Ft - U + k3(F, 0, CH_T, a1, b1);
+    const C gpp = s[4] - s[7], ga = s[5] - s[8], gt = s[6] - s[9];
+    const C fp = s[4] - U + k3(F, 0, CH_P, a1, b1), fa = s[5] - U + k3(F, 0, CH_A, a1, b1), ft = s[6] - U + k3(F, 0, CH_T, a1, b1);
     out.c[4][i] = gpp;
     out.c[5][i] = ga;
     out.c[6][i] = gt * 2.0 - ga;
     out.c[7][i] = fp;
     out.c[8][i] = fa;
     out.c[9][i] = ft * 2.0 - fa;
+}
+
+// ---- the vertex as a callable: F(W, v, w, P, k, q, Ch, Sp; switches) of the chain from `level` at a list of points (what the
+// reference's tests and conversions do on the host, e.g. test/test_boson_exchange_local.jl:76, src/boson_exchange.jl:672-735).
+// Frequencies may be FDGA_INF; ip / ik / iq are linear momentum indices; sw != 0: k = q = kSW. ----
+template <bool MBE>
+__global__ void eval_points_kernel(const __grid_constant__ DevChain V, int level, int Ch, int Sp, unsigned flags, int sw, long long n,
+                                   const int* __restrict__ W, const int* __restrict__ v, const int* __restrict__ w,
+                                   const int* __restrict__ ip, const int* __restrict__ ik, const int* __restrict__ iq, C* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Arg a; a.W = W[i]; a.v = v[i]; a.w = w[i];
+    a.Px = ip[i] % V.L; a.Py = ip[i] / V.L; a.kx = ik[i] % V.L; a.ky = ik[i] / V.L; a.qx = iq[i] % V.L; a.qy = iq[i] / V.L;
+    out[i] = sw ? eval_vertex<true, MBE>(V, level, Ch, Sp, a, flags) : eval_vertex<false, MBE>(V, level, Ch, Sp, a, flags);
 }
 
 // ---- BSE_L_K2! of the local solver, generic form (one CTA per representative (W, v)): src/BSEa/BSEa_K2.jl:1-40, w over the bubble

@@ -1240,6 +1240,35 @@ int fdga_bubbles_momentum_space(fdga_ctx* ctx, int reference) {
     return 0;
 }
 
+// ---- the vertex as a callable ----------------------------------------------------------------------------
+// F(W, v, w, P, k, q, Ch, Sp; F0, gamma_p, gamma_t, gamma_a) of the chain S.F from `level` at n points (host arrays in, host
+// values out).  flags: bit 0 F0, bit 1 gamma_p, bit 2 gamma_t, bit 3 gamma_a.  Synchronous; not a hot path.
+int fdga_eval_vertex(fdga_ctx* ctx, int level, int ch, int sp, int flags, int swave_kq, int64_t n, const int32_t* W, const int32_t* v, const int32_t* w,
+                     const int32_t* iP, const int32_t* ik, const int32_t* iq, fdga_c64* out) {
+    CK(cudaSetDevice(ctx->device));
+    if (level < 0 || level >= ctx->nlev || ch < 0 || ch > 2 || sp < 0 || sp > 2 || n < 0) FAIL("fdga_eval_vertex: bad selector");
+    if (ctx->swave && !swave_kq) FAIL("fdga_eval_vertex: an s-wave (NL) context evaluates at k = q = kSW only");
+    if (n == 0) return 0;
+    for (int64_t i = 0; i < n; i++) if (iP[i] < 0 || iP[i] >= ctx->g.NP || ik[i] < 0 || ik[i] >= ctx->g.NP || iq[i] < 0 || iq[i] >= ctx->g.NP) FAIL("fdga_eval_vertex: momentum index out of range");
+    if (swave_kq && refresh_swave(ctx)) return 1;
+    int* d = nullptr; C* dout = nullptr;
+    CK(cudaMalloc(&d, (size_t)6 * n * sizeof(int))); CK(cudaMalloc(&dout, (size_t)n * sizeof(C)));
+    const int32_t* src[6] = {W, v, w, iP, ik, iq};
+    for (int j = 0; j < 6; j++) CK(cudaMemcpyAsync(d + (size_t)j * n, src[j], (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    DevChain V = chain_F(ctx, 0);
+    {
+        Scope sc(ctx, FDGA_T_MISC);
+        if (ctx->mbe) LAUNCH(FDGA_T_MISC, eval_points_kernel<true>, nblk(n, 64), 64, V, level, ch, sp, (unsigned)flags, swave_kq, (long long)n, d, d + n, d + 2 * n, d + 3 * n, d + 4 * n, d + 5 * n, dout);
+        else          LAUNCH(FDGA_T_MISC, eval_points_kernel<false>, nblk(n, 64), 64, V, level, ch, sp, (unsigned)flags, swave_kq, (long long)n, d, d + n, d + 2 * n, d + 3 * n, d + 4 * n, d + 5 * n, dout);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, (size_t)n * sizeof(C), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d); cudaFree(dout);
+    if (e != cudaSuccess) FAIL(std::string("fdga_eval_vertex: ") + cudaGetErrorString(e));
+    return 0;
+}
+
 // ---- K3 cache ------------------------------------------------------------------------------------------
 int fdga_build_K3_cache(fdga_ctx* ctx, int mfrg, int first) {
     CK(cudaSetDevice(ctx->device));
@@ -1249,7 +1278,10 @@ int fdga_build_K3_cache(fdga_ctx* ctx, int mfrg, int first) {
     if (mfrg && ctx->mbe) FAIL("fdga_build_K3_cache: the mfRG cache is not available for MBE vertices");
     if (!mfrg) {
         CachePtrs cp; for (int i = 0; i < 10; i++) cp.c[i] = ctx->cache[i];
-        if (ctx->lev[0].mbe) LAUNCH(FDGA_T_CACHE, build_cache_mbe_kernel, nblk(ctx->lenK3, 64), 64, F0, F, cp, ctx->g, 0LL, (long long)ctx->lenK3);
+        if (ctx->lev[0].mbe) {
+            const int np2 = ctx->g.NP * ctx->g.NP, thr = np2 >= 128 ? 128 : (np2 >= 64 ? 64 : 32);
+            LAUNCH(FDGA_T_CACHE, build_cache_mbe_kernel, (unsigned)ctx->lenK3, thr, F0, F, cp, ctx->g, 0LL, (long long)ctx->lenK3);
+        }
         else
         LAUNCH(FDGA_T_CACHE, build_cache_kernel, nblk(ctx->lenK3, 64), 64, F0, F, cp, ctx->g, 0LL, (long long)ctx->lenK3);
         CK(cudaGetLastError());

@@ -21,6 +21,7 @@ import numpy as np
 from . import _lib as L
 from .types import (CH_NAME, CHANNELS, MBEVertex, NL2_MBEVertex, NL2_Vertex, NL_Vertex, RefVertex, Vertex, aCh, nB, nF, pCh, tCh, vertex_chain, zeros)
 
+INF_FREQ = 1 << 28           # νInf: an InfiniteMatsubaraFrequency argument of eval_vertex
 STRATEGY = {"scPA": L.SCPA, "fdPA": L.FDPA, "scPA_new": L.SCPA_NEW, "fdPA_new": L.FDPA_NEW, "fdPA_1loop": L.FDPA_1LOOP}
 _G_NAMES = {"G": L.G, "G0": L.G0, "Gbare": L.GBARE, "Σ": L.SIGMA, "Σ0": L.SIGMA0}
 _PI_NAMES = {"Π0pp": L.PI0PP, "Π0ph": L.PI0PH, "Πpp": L.PIPP, "Πph": L.PIPH}
@@ -301,6 +302,23 @@ class NL2_ParquetSolver:
         assert uid.size == 128
         self._call("fdga_comm_init", int(nranks), int(rank), L.ptr(uid))
         self.nranks, self.rank = int(nranks), int(rank)
+
+    # ------------------------------------------------------------------ the vertex as a callable
+    def eval_vertex(self, W, v, w, Ch, Sp, P=0, k=0, q=0, *, level=0, F0=True, γp=True, γt=True, γa=True, swave=False):
+        """F(Ω, ν, ω, P, k, q, Ch, Sp; F0, γp, γt, γa) of the chain S.F (level 0), S.F0 (level 1), ... evaluated on the device at the
+        broadcast of the integer arrays W, v, w (Matsubara indices; v, w may be INF_FREQ) and P, k, q (linear momentum indices
+        ix + L iy, see kidx); swave: k = q = kSW.  Returns a complex array of the broadcast shape."""
+        arrs = np.broadcast_arrays(*[np.asarray(x, dtype=np.int64) for x in (W, v, w, P, k, q)])
+        shape = arrs[0].shape
+        flat = [np.ascontiguousarray(a.reshape(-1), dtype=np.int32) for a in arrs]
+        out = np.empty(flat[0].size, dtype=np.complex128)
+        flags = (1 if F0 else 0) | (2 if γp else 0) | (4 if γt else 0) | (8 if γa else 0)
+        self._call("fdga_eval_vertex", int(level), int(Ch), int(Sp), flags, int(bool(swave)), out.size, *[L.ptr(a) for a in flat], L.ptr(out))
+        return out.reshape(shape)
+
+    def kidx(self, x, y):
+        """linear index of the (folded) Brillouin point (x, y) of the vertex momentum mesh"""
+        return (np.asarray(x) % self.L) + self.L * (np.asarray(y) % self.L)
 
     # ------------------------------------------------------------------ CUDA graphs (include/fdga.h)
     def record(self, fn):

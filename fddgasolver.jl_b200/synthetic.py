@@ -10,7 +10,7 @@ import numpy as np
 
 from .models import hubbard_bare_Green, siam_bare_Green
 from .solver import NL2_ParquetSolver, NL_ParquetSolver, ParquetSolver
-from .types import NL2_Vertex, NL_Vertex, RefVertex, Vertex, nB, nF
+from .types import NL2_MBEVertex, NL2_Vertex, NL_Vertex, RefVertex, Vertex, nB, nF
 
 
 def parquet_solver_hubbard_parquet_approximation_NL2(nG, nK1, nK2, nK3, LG, L, *, T, U, μ, t1, t2=0.0, t3=0.0,
@@ -143,7 +143,10 @@ def wu_point_inputs(nmax=4, nq=8, LG=48, *, seed=1, F_scale=1e-2, F0_scale=0.0, 
             Γ = synthetic_local_vertex(T, U, numK1=2 * nK1, numK2=(2 * nmax, 2 * nmax), numK3=(1, 1), core=(nmax + 1, nmax), seed=2)
         else:
             Γ = synthetic_local_vertex(T, U, seed=2)
-    VT = {1: NL_Vertex, 2: NL2_Vertex}[nl_method]
+    VT = {1: NL_Vertex, 2: NL2_Vertex, -2: NL2_MBEVertex}[nl_method]
+    if nl_method == -2:      # script/run_Wu_point.jl:95: F0 = NL2_MBEVertex(asymptotic_to_mbe(data_triqs.Γ), ...); the conversion runs on the device
+        from .mbe import asymptotic_to_mbe
+        Γ = asymptotic_to_mbe(Γ)
     F0 = VT(Γ, T, nK1, nK2, nK3, nq)
     if F0_scale:
         randomize_vertex(F0, seed + 7, scale=F0_scale)
@@ -158,8 +161,9 @@ def wu_point_solver(nmax=4, nq=8, LG=48, *, seed=1, device=0, init_sym=True, F_s
                     small_reference=False, data="auto", nl_method=2):
     """NL2_ParquetSolver (nl_method = 2) or NL_ParquetSolver (nl_method = 1) on the GPU for wu_point_inputs(...) (see there)."""
     inp = wu_point_inputs(nmax, nq, LG, seed=seed, F_scale=F_scale, F0_scale=F0_scale, small_reference=small_reference, data=data, nl_method=nl_method)
-    S = {1: NL_ParquetSolver, 2: NL2_ParquetSolver}[nl_method](inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"],
-                          T=inp["T"], device=device)
+    kw = dict(VT=NL2_MBEVertex) if nl_method == -2 else {}
+    S = {1: NL_ParquetSolver, 2: NL2_ParquetSolver, -2: NL2_ParquetSolver}[nl_method](inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"],
+                          T=inp["T"], device=device, **kw)
     S.F.set(inp["F"])
     S.push("F")
     if init_sym:

@@ -240,6 +240,15 @@ int  fdga_interpolate_green(fdga_ctx*, int which, const fdga_c64* host_in, int n
 int  fdga_mix_bubbles(fdga_ctx*, double mixing);
 int  fdga_update_reference(fdga_ctx*);
 
+/* ---- the vertex as a callable ---------------------------------------------------------------
+ * F(W, v, w, P, k, q, Ch, Sp; F0, gamma_p, gamma_t, gamma_a) of the chain S.F from `level` (0: S.F, 1: S.F0, ...) at n points:
+ * src/vertex.jl:209-336, src/nonlocal/vertex.jl:69-211, src/nonlocal_2/vertex.jl:207-259, src/boson_exchange.jl:349-560.
+ * W, v, w: Matsubara indices (v, w may be FDGA_INF_FREQ); iP, ik, iq: linear momentum indices; swave_kq != 0: k = q = kSW;
+ * flags: bit 0 F0, bit 1 gamma_p, bit 2 gamma_t, bit 3 gamma_a.  Synchronous utility (tests, conversions), not a hot path. */
+#define FDGA_INF_FREQ (1 << 28)
+int  fdga_eval_vertex(fdga_ctx*, int level, int channel, int spin, int flags, int swave_kq, int64_t n, const int32_t* W, const int32_t* v,
+                      const int32_t* w, const int32_t* iP, const int32_t* ik, const int32_t* iq, fdga_c64* out);
+
 /* ---- CUDA graphs ------------------------------------------------------------------------
  * Record a sequence of calls once, replay it with one launch: a step of the iteration is ~80 small dependent kernels on three
  * concurrent lanes, and the replay removes the per-launch gaps between them.
