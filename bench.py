@@ -37,15 +37,22 @@ def parse():
     p.add_argument("--nmax", type=int, default=4)
     p.add_argument("--nq", type=int, default=8)
     p.add_argument("--LG", type=int, default=48)
-    p.add_argument("--nl-method", type=int, default=2, choices=[1, 2],
-                   help="2 (default, the headline): NL2_ParquetSolver; 1: the s-wave NL_ParquetSolver of script/run_Wu_point.jl (side workload)")
+    p.add_argument("--nl-method", type=int, default=2, choices=[1, 2, -2],
+                   help="2 (default, the headline): NL2_ParquetSolver; 1: the s-wave NL_ParquetSolver of script/run_Wu_point.jl (side workload); "
+                        "-2: NL2_ParquetSolver with multi-boson-exchange vertices (generic kernels; at most 10 steps, no CPU arm, no mfRG extras)")
     p.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying its CUDA graph (1 GPU)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the mfRG matvec / DQGMRES side measurements (large sweep sizes)")
-    return p.parse_args()
+    a = p.parse_args()
+    if a.nl_method == -2:
+        a.steps, a.warmup, a.no_cpu_baseline, a.no_extras, a.no_graph = min(a.steps, 10), min(a.warmup, 3), True, True, True
+    return a
 
 
 def workload_name(a):
+    if a.nl_method == -2:
+        return (f"NL2_ParquetSolver with NL2_MBEVertex, Wu point U=5.6 T=0.2 (script/run_Wu_point.jl, nl_method=-2): nmax={a.nmax} (nK1={4 * a.nmax}, "
+                f"nK2=nK3=({a.nmax},{a.nmax})), nq={a.nq}, LG={a.LG}; generic per-term kernels")
     if a.nl_method == 1:
         return (f"s-wave NL_ParquetSolver, Wu point U=5.6 T=0.2 (script/run_Wu_point.jl, nl_method=1): nmax={a.nmax} (nK1={4 * a.nmax}, "
                 f"nK2=nK3=({a.nmax},{a.nmax})), nq={a.nq}, LG={a.LG}, bubble mesh {4 * a.nmax} x {128 * a.nmax} (m_Pi_nu_factor=32)")
@@ -185,7 +192,8 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     inp = fd.wu_point_inputs(a.nmax, a.nq, a.LG, F0_scale=0.02, nl_method=a.nl_method)
     Solver = fd.NL_ParquetSolver if a.nl_method == 1 else fd.NL2_ParquetSolver
-    S = Solver(inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"], T=inp["T"], device=local)
+    skw = dict(VT=fd.NL2_MBEVertex) if a.nl_method == -2 else {}
+    S = Solver(inp["nK1"], inp["nK2"], inp["nK3"], inp["L"], inp["Gbare"], inp["G0"], inp["Σ0"], inp["F0"], T=inp["T"], device=local, **skw)
     S.F.set(inp["F"]); S.push("F"); S.init_sym_grp()
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8)
@@ -300,6 +308,8 @@ def run_ours(a):
     bytes_per_launch = nB2 * NP * nFΠ * NP * 16 / world + tables + np.mean(chunk) * 16      # R slabs of the K2 bosonic box + vertex tables + outputs
     flop_per_launch = 26.0 * np.mean(chunk) * nFΠ * NP                                       # 26 flop per (representative, w, q) term
     k2 = kernels.get("column_K2", {"ms_per_step": float("nan"), "launches_per_step": 3})
+    if a.nl_method == -2:       # MBE: the generic kernel of BSE_K2! (no column sub-timer)
+        k2 = kernels.get("K2", k2)
     if a.nl_method == 1:        # s-wave solver: no inner momentum sum; one launch reads its representatives' two bubble rows + the tables
         bytes_per_launch = np.mean(chunk) * nFΠ * 2 * 16 + tables + np.mean(chunk) * 16
         flop_per_launch = 40.0 * np.mean(chunk) * nFΠ
