@@ -599,6 +599,7 @@ __global__ void bse_lk2_loc_kernel(const __grid_constant__ DevChain F, const C* 
 // ---- build_K3_cache_mfRG!: src/nonlocal_2/build_K3_cache.jl:108-161.  One thread per class rep --------
 //  kind 0: Gpx (pCh,xSp)  1: Gpp (pCh,pSp)  2: Ga  3: Gt   = S.F(...; g_r=false) - S.F.F0(...; g_r=false)
 //  kind 4: Fp  5: Fa  6: Ft                                = S.F0(W,v,w) - S.F0(W,inf,w)
+template <bool MBE = false>
 __global__ void cache_mfrg_kernel(const __grid_constant__ DevChain F0, const __grid_constant__ DevChain F, int kind,
                                   C* __restrict__ repvals, SymDev sg, long long c0, long long c1, Grid g) {
     long long cls = c0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -611,11 +612,11 @@ __global__ void cache_mfrg_kernel(const __grid_constant__ DevChain F0, const __g
         int Ch = (kind <= 1) ? CH_P : (kind == 2 ? CH_A : CH_T);
         int Sp = (kind == 0) ? SP_X : SP_P;
         unsigned f = FL_ALL & ~(2u << Ch);
-        r = eval_vertex<true>(F, 0, Ch, Sp, a, f) - eval_vertex<true>(F, 1, Ch, Sp, a, f);
+        r = eval_vertex<true, MBE>(F, 0, Ch, Sp, a, f) - eval_vertex<true, MBE>(F, 1, Ch, Sp, a, f);
     } else {
         int Ch = (kind == 4) ? CH_P : (kind == 5 ? CH_A : CH_T);
         Arg av = a; av.v = FDGA_INF;
-        r = eval_vertex<true>(F0, 0, Ch, SP_P, a, FL_ALL) - eval_vertex<true>(F0, 0, Ch, SP_P, av, FL_ALL);
+        r = eval_vertex<true, MBE>(F0, 0, Ch, SP_P, a, FL_ALL) - eval_vertex<true, MBE>(F0, 0, Ch, SP_P, av, FL_ALL);
     }
     repvals[cls] = r;
 }

@@ -1275,7 +1275,6 @@ int fdga_build_K3_cache(fdga_ctx* ctx, int mfrg, int first) {
     if (refresh_swave(ctx)) return 1;
     Scope sc(ctx, FDGA_T_CACHE);
     DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0);
-    if (mfrg && ctx->mbe) FAIL("fdga_build_K3_cache: the mfRG cache is not available for MBE vertices");
     if (!mfrg) {
         CachePtrs cp; for (int i = 0; i < 10; i++) cp.c[i] = ctx->cache[i];
         if (ctx->lev[0].mbe) {
@@ -1294,7 +1293,10 @@ int fdga_build_K3_cache(fdga_ctx* ctx, int mfrg, int first) {
     for (int j = 0; j < njobs; j++) {
         SymGroup& s = ctx->sg[jobs[j].sg];
         long long c0, c1; sg_class_range(ctx, s, c0, c1);
-        if (c1 > c0) LAUNCH(FDGA_T_CACHE, cache_mfrg_kernel, nblk(c1 - c0, 64), 64, F0, F, jobs[j].kind, s.d_repvals, sym_dev(s), c0, c1, ctx->g);
+        if (c1 > c0) {
+            if (ctx->mbe) LAUNCH(FDGA_T_CACHE, cache_mfrg_kernel<true>, nblk(c1 - c0, 64), 64, F0, F, jobs[j].kind, s.d_repvals, sym_dev(s), c0, c1, ctx->g);
+            else          LAUNCH(FDGA_T_CACHE, cache_mfrg_kernel<false>, nblk(c1 - c0, 64), 64, F0, F, jobs[j].kind, s.d_repvals, sym_dev(s), c0, c1, ctx->g);
+        }
         CK(cudaGetLastError());
         if (sg_finish(ctx, s, ctx->cache[jobs[j].cache])) return 1;
         if (jobs[j].kind == 3) { if (axpby(ctx, ctx->cache[FDGA_C_GT], ctx->cache[FDGA_C_GT], 2.0, ctx->cache[FDGA_C_GA], -1.0, ctx->lenK3)) return 1; }

@@ -41,7 +41,7 @@ enum { FDGA_LV_NL2 = 0,    /* NL2_Vertex  (src/nonlocal_2/vertex.jl:1-32)  K1[W,
        FDGA_LV_NL = 3,     /* NL_Vertex   (src/nonlocal/vertex.jl:1-37)    K1[W,P] K2[W,v,P]   K3[W,v,v',P] */
        /* multi-boson-exchange vertices (src/boson_exchange.jl:237-266, 738-770): the arrays of the base type, evaluated as
         * U + K1 + K2 + K2' + K2 K2' / (U + K1) + K3 per channel.  MBE levels form the head of the chain; a context with one runs the
-        * generic per-term kernels (fdPA / scPA, no mfRG cache). */
+        * generic per-term kernels (no `_new` / `_1loop` variants beyond what those kernels provide). */
        FDGA_LV_NL2_MBE = 4, FDGA_LV_LOCAL_MBE = 5 };
 
 #define FDGA_MAX_LEVELS 6

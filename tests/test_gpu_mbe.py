@@ -86,13 +86,11 @@ def test_mbe_iterate_solver_and_sde(orc, strategy, nested):
     S.close()
 
 
-def test_mbe_contexts_have_no_fast_or_mfrg_paths(orc):
+def test_mbe_contexts_have_no_fast_paths(orc):
     import fddgasolver_jl_b200 as fd
     S, _ = make_nl2(orc, nested=False)
     with pytest.raises(fd.FdgaError, match="generic kernels"):
         S.set_option("generic_kernels", 0)
-    with pytest.raises(fd.FdgaError, match="not available for MBE"):
-        fd.build_K3_cache_mfRG(S, True)
     S.close()
     T = 0.5
     Gb = fd.hubbard_bare_Green(T, 8, 4, μ=0.1, t1=1.0)
@@ -234,4 +232,43 @@ def test_wu_point_mbe_construction_and_iteration(orc):
     compare_vertex(S.F, R.F, "F")
     compare_vertex(S.FL, R.FL, "FL", ("K2", "K3"))
     assert rel(S.Σ, R.Σ) < TOL
+    S.close()
+
+
+def test_mbe_mfrg_cache_kernels_and_linear_map(orc):
+    """build_K3_cache_mfRG! is typed for any vertex (src/nonlocal_2/build_K3_cache.jl:97-164) and solve_using_mfRG! is what
+    script/run_Wu_point.jl runs for nl_method = -2 too: mfRG caches, the mfRG branches of the BSE kernels, the linear map and a
+    DQGMRES solve with MBE vertices against the oracle"""
+    import fddgasolver_jl_b200 as fd
+    S, R = make_nl2(orc, nested=True)
+    order = (fd.pCh, fd.aCh, fd.tCh)
+    for first in (True, False):
+        fd.build_K3_cache_mfRG(S, first); orc.build_K3_cache_mfRG(R, first)
+        S.pull("cache")
+        for n in ("cache_Γpx", "cache_Γpp", "cache_Γa", "cache_Γt", "cache_Fp", "cache_Fa", "cache_Ft"):
+            assert rel(getattr(S, n), getattr(R, n)) < TOL, (n, first)
+    for ch in order:
+        fd.BSE_L_K2(S, ch); orc.BSE_L_K2(R, ch)
+    for ch in order:
+        fd.BSE_K1(S, ch, True); orc.BSE_K1(R, ch, True)
+    for ch in order:
+        fd.BSE_K2(S, ch, True); orc.BSE_K2(R, ch, True)
+    for ch in order:
+        fd.BSE_L_K3(S, ch); orc.BSE_L_K3(R, ch)
+    for ch in order:
+        fd.BSE_K3(S, ch, True); orc.BSE_K3(R, ch, True)
+    S.pull("Fbuff", "FL")
+    compare_vertex(S.FL, R.FL, "FL", ("K2", "K3"))
+    compare_vertex(S.Fbuff, R.Fbuff, "Fbuff(mfRG)")
+    x = S.F.flatten() * 2.0
+    A, B = fd.mfRGLinearMap(S), orc.mfRGLinearMap(R)
+    for _ in range(2):
+        yg, yo = A.matvec(x), B.matvec(x)
+        assert rel(yg, yo) < TOL
+        x = yo * 0.5
+    rng = np.random.default_rng(2)
+    b = rng.standard_normal(x.size) + 1j * rng.standard_normal(x.size)
+    xg, sg = fd.dqgmres(A, b, memory=5, atol=1e-9, rtol=1e-9, itmax=20)
+    xo, so = orc.dqgmres(B, b, memory=5, atol=1e-9, rtol=1e-9, itmax=20)
+    assert sg["niter"] == so["niter"] and rel(xg, xo) < 1e-8
     S.close()
