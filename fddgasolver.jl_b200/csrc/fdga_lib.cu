@@ -1646,6 +1646,7 @@ static int bse_new_impl(fdga_ctx* ctx, int ch, int mfrg, int cls) {
     NEED_SG(which);
     if (ctx->opt_local) FAIL("fdga_bse_K*_new: not available for the local solver context");
     if (ctx->swave) FAIL("fdga_bse_K*_new: not available for the s-wave (NL) solver");
+    if (ctx->mbe) FAIL("fdga_bse_K*_new: not available for MBE vertices (the term-by-term kernels assume the asymptotic evaluator)");
     if (ensure_pi(ctx, ch)) return 1;
     DevChain F0 = chain_F(ctx, 1), F = chain_F(ctx, 0);
     SymGroup& s = ctx->sg[which]; s.d_repvals = s.d_rep[ch];

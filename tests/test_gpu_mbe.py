@@ -91,6 +91,11 @@ def test_mbe_contexts_have_no_fast_paths(orc):
     S, _ = make_nl2(orc, nested=False)
     with pytest.raises(fd.FdgaError, match="generic kernels"):
         S.set_option("generic_kernels", 0)
+    for fn in (fd.BSE_K1_new, fd.BSE_K2_new):
+        with pytest.raises(fd.FdgaError, match="not available for MBE"):
+            fn(S, fd.pCh)
+    with pytest.raises(fd.FdgaError, match="not available for MBE"):
+        fd.iterate_solver(S, "fdPA_new")
     S.close()
     T = 0.5
     Gb = fd.hubbard_bare_Green(T, 8, 4, μ=0.1, t1=1.0)
