@@ -74,7 +74,7 @@ def test_mbe_caches_and_bse_kernels_stepwise(orc, nested, sym):
     S.close()
 
 
-@pytest.mark.parametrize("strategy,nested", [("fdPA", True), ("scPA", True), ("scPA", False)])
+@pytest.mark.parametrize("strategy,nested", [("fdPA", True), ("scPA", True), ("scPA", False), ("fdPA_1loop", True)])
 def test_mbe_iterate_solver_and_sde(orc, strategy, nested):
     import fddgasolver_jl_b200 as fd
     S, R = make_nl2(orc, nested=nested)
