@@ -668,7 +668,6 @@ int fdga_create(const fdga_dims* dims, int device, fdga_ctx** out) {
     for (int l = 0; l < dims->nlev && l < FDGA_MAX_LEVELS; l++) {
         int& t = dims_base.lev[l].type;
         if (t == FDGA_LV_NL2_MBE) { t = FDGA_LV_NL2; any_mbe = true; } else if (t == FDGA_LV_LOCAL_MBE) { t = FDGA_LV_LOCAL; any_mbe = true; }
-        else if (any_mbe && t != FDGA_LV_CORE && l > 0 && !(dims->lev[l - 1].type == FDGA_LV_NL2_MBE || dims->lev[l - 1].type == FDGA_LV_LOCAL_MBE)) { /* asymptotic level below MBE levels: fine */ }
     }
     for (int l = 1; l < dims->nlev; l++) {
         const bool m = dims->lev[l].type == FDGA_LV_NL2_MBE || dims->lev[l].type == FDGA_LV_LOCAL_MBE;
