@@ -74,3 +74,6 @@ def test_two_ranks_nccl_match_one_rank():
     a, b = run(1, ("--nl-method", "1")), run(2, ("--nl-method", "1"))
     assert "s-wave" in a["config"]["workload"] and abs(a["state_checksum"] - b["state_checksum"]) <= 1e-10 * abs(a["state_checksum"])
     assert b["n_gpus"] == 2 and "comm" in b["kernels"]
+    # and so do the generic per-term kernels of a solver with MBE vertices
+    a, b = run(1, ("--nl-method", "-2")), run(2, ("--nl-method", "-2"))
+    assert "MBE" in a["config"]["workload"] and a["state_sha1"] == b["state_sha1"] and b["n_gpus"] == 2
