@@ -469,7 +469,9 @@ static int tfix(fdga_ctx* ctx, C* Xt, const C* Xa, size_t n) { return axpby(ctx,
 
 // one-launch 2-d transform over two adjacent axes (dft2_tile_kernel); false: the tile does not fit in shared memory / switched off
 static bool dft2_tile(fdga_ctx* ctx, const C* in, C* out, long long pre, int n, long long post, int sgn, double scale, const C* tw, int cat) {
-    static const bool on = getenv("FDGA_DFT_TILE") ? atoi(getenv("FDGA_DFT_TILE")) != 0 : true;
+    // opt-in (FDGA_DFT_TILE=1): measured performance-neutral (these transforms overlap with the contraction lanes), and the two-pass
+    // order of the axis kernels is the one the committed multi-GPU fingerprints were taken with
+    static const bool on = getenv("FDGA_DFT_TILE") ? atoi(getenv("FDGA_DFT_TILE")) != 0 : false;
     const size_t smem = ((size_t)2 * n * n + n) * sizeof(C);
     // only worth it for many small tiles (the momentum axes of the vertex mesh): a G-sized transform (n = LG = 48, 2 N_G = 32 tiles)
     // would run on 32 CTAs and is 3-4x slower than the two axis passes with one thread per output (measured)
