@@ -222,3 +222,53 @@ def test_nl_symmetry_errors_of_unsymmetrised_scPA_solution(orc):
     for (cls, ch), t in thr.items():
         which = {"K1": o.SG_K1, "K2": o.SG_PP2 if ch == pCh else o.SG_PH2, "K3": o.SG_PP3 if ch == pCh else o.SG_PH3}[cls]
         assert sym_err(which, getattr(S.F.channel(ch), cls)) < t, (cls, ch)
+
+
+@pytest.mark.slow
+def test_nl_fdPA_from_an_impurity_reference_has_symmetric_left_vertices(orc):
+    """test/test_nonlocal_symmetry.jl:111-187: the production configuration of the s-wave solver -- reference system = a converged
+    SIAM (local Vertex with a RefVertex core, impurity G and Σ on every lattice momentum), target = the Hubbard model, fdPA solved
+    WITHOUT symmetry groups -- gives non-zero left vertices FL whose symmetry errors under the s-wave groups are below the
+    reference's thresholds (the symmetries are exact only at convergence)"""
+    import ctypes
+    from otypes import RefVertex, Vertex, pCh, tCh, aCh
+    import oracle as o
+    T, U, μ, t1 = 0.5, 2.0, -2.0, 1.0
+    D, e, Δ = 4 * t1, μ, 1.5
+    nmax0 = 12
+    Gb0 = orc.siam_bare_Green(T, 4 * nmax0, e=e, Δ=Δ, D=D)
+    S0 = orc.OracleLocalSolver(4 * nmax0, (nmax0, nmax0), (nmax0, nmax0), Gb0, np.zeros_like(Gb0), np.zeros_like(Gb0), RefVertex(T, U), T=T)
+    S0.init_sym_grp()
+    nF0 = len(S0.F)
+
+    def fp0(x):
+        S0.F.unflatten(x[:nF0]); S0.Σ[...] = x[nF0:].reshape(S0.Σ.shape, order="F")
+        orc.iterate_solver_local(S0, "scPA", True)
+        return np.concatenate([S0.F.flatten(), S0.Σ.ravel(order="F")]) - x
+    x, it, err = anderson(fp0, flatten_solver(S0), tol=1e-8)
+    assert err < 1e-8
+    S0.F.unflatten(x[:nF0]); S0.Σ[...] = x[nF0:].reshape(S0.Σ.shape, order="F")
+    orc.Dyson(S0)
+    # the converged impurity vertex as a local Vertex, G0 / Σ0 momentum independent
+    Floc = Vertex(RefVertex(T, U), T, 4 * nmax0, (nmax0, nmax0), (nmax0, nmax0))
+    for gl, g0 in zip(Floc.channels(), S0.F.channels()):
+        gl.K1[...] = g0.K1[:, 0]; gl.K2[...] = g0.K2[:, :, 0, 0]; gl.K3[...] = g0.K3[:, :, :, 0]
+    nmax, LG, L = 8, 6, 3
+    nG = 4 * nmax
+    Gbare = orc.hubbard_bare_Green(T, nG, LG, μ=μ, t1=t1)
+    sl = slice(4 * nmax0 - nG, 4 * nmax0 + nG)
+    G0 = np.asfortranarray(np.repeat(S0.G[sl, :], LG * LG, axis=1))
+    Σ0 = np.asfortranarray(np.repeat(S0.Σ[sl, :], LG * LG, axis=1))
+    S = orc.OracleNLSolver(4 * nmax, (nmax, nmax), (nmax, nmax), L, Gbare, G0, Σ0, Floc, T=T)
+    x, it, err = anderson(oracle_fixed_point(orc, S, "fdPA"), flatten_solver(S), tol=1e-7)
+    assert err < 1e-7, (it, err)
+    for ch in (pCh, aCh, tCh):
+        assert np.max(np.abs(S.FL.channel(ch).K2)) > 1e-4 and np.max(np.abs(S.FL.channel(ch).K3)) > 1e-4
+    S.init_sym_grp()
+
+    def sym_err(which, a):
+        b = a.copy(order="F")
+        orc.lib().orc_symmetrize(orc._p(b), ctypes.byref(orc.sg_struct(S.sg[which])))
+        return np.max(np.abs(b - a))
+    assert sym_err(o.SG_PP2, S.FL.γp.K2) < 1e-2 and sym_err(o.SG_PH2, S.FL.γa.K2) < 1e-2 and sym_err(o.SG_PH2, S.FL.γt.K2) < 1e-2
+    assert sym_err(o.SG_PPL3, S.FL.γp.K3) < 1e-3 and sym_err(o.SG_PHL3, S.FL.γa.K3) < 1e-3 and sym_err(o.SG_PHL3, S.FL.γt.K3) < 1e-3
