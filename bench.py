@@ -147,6 +147,9 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if a.nl_method == -2:
+        raise SystemExit("bench.py --impl reference: the MBE side workload has no CPU arm (its inputs are converted on the device and one "
+                         "oracle iteration at config 3 takes hours); use --nl-method 2 or 1")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import fddgasolver_jl_b200 as fd
     import oracle as o
